@@ -1,0 +1,228 @@
+// avbd_collide.cuh — OBB-vs-OBB SAT and contact generation, device side.
+//
+// Behavioural contract: alxspiker/avbd-demo3d source/collision.cpp:56-489
+// (Manifold::collide with flip=false).  Same axis order, same strict ">" tie
+// breaking, same epsilons, same quantised feature keys; compiled with
+// -fmad=false so the outputs are bit-identical to the CPU reference.
+//
+// The SAT is split in two so the pipeline can cull before it builds:
+//   sat_test()      15 axes -> separated? + winning axis packed in one int
+//   build_contacts() recomputes the winning axis' normal (same expression =>
+//                    same bits) and emits <=4 contacts.
+#pragma once
+#include "avbd_math.cuh"
+
+namespace avbd {
+
+struct Obb { V3 c, h, ax[3]; };
+
+struct RawContact {      // collision.cpp:176-206 output, before Manifold::initialize
+    int feature;
+    V3 rA, rB, normal;
+};
+
+AVBD_HD Obb make_obb(V3 pos, Q4 rot, V3 size) {             // collision.cpp:56-66
+    Obb b; b.c = pos; b.h = size * 0.5f;
+    M3 R = qmat(rot); b.ax[0] = R.c[0]; b.ax[1] = R.c[1]; b.ax[2] = R.c[2];
+    return b;
+}
+AVBD_HD float adot(V3 a, V3 b) { return fabsf(dot(a, b)); }
+
+// One axis.  Returns false when separated beyond the persistence margin.
+// `sep`/`n` are only meaningful when `counted` comes back true (degenerate
+// axes are skipped, collision.cpp:211-214).
+AVBD_HD bool sat_axis(const Obb& A, const Obb& B, V3 d, V3 axis, bool& counted, float& sep, V3& n) {   // collision.cpp:208-247
+    counted = false;
+    float l2 = len2(axis);
+    if (l2 < kSatEps) return true;
+    n = axis / sqrtf(l2);
+    if (dot(n, d) < 0.0f) n = -n;
+    float dist = fabsf(dot(d, n));
+    float ra = A.h.x * adot(n, A.ax[0]) + A.h.y * adot(n, A.ax[1]) + A.h.z * adot(n, A.ax[2]);
+    float rb = B.h.x * adot(n, B.ax[0]) + B.h.y * adot(n, B.ax[1]) + B.h.z * adot(n, B.ax[2]);
+    sep = dist - (ra + rb);
+    if (sep > kCollisionMargin) return false;
+    counted = true;
+    return true;
+}
+
+AVBD_HD V3 sat_axis_dir(const Obb& A, const Obb& B, int k) {
+    // k: 0-2 face of A, 3-5 face of B, 6-14 edge i*3+j
+    if (k < 3) return A.ax[k];
+    if (k < 6) return B.ax[k - 3];
+    int e = k - 6;
+    return cross(A.ax[e / 3], B.ax[e % 3]);
+}
+
+// Full 15-axis test.  Returns 0 when separated / no valid face axis, else
+// 1 | (axisIndex << 1) with axisIndex in [0,15) naming the chosen axis after
+// the face-vs-edge preference rule (collision.cpp:459-468).
+AVBD_HD int sat_test(const Obb& A, const Obb& B) {          // collision.cpp:420-468
+    V3 d = B.c - A.c;
+    bool faceValid = false, edgeValid = false;
+    float faceSep = -FLT_MAX, edgeSep = -FLT_MAX;
+    int faceK = 0, edgeK = 0;
+    for (int k = 0; k < 15; ++k) {
+        bool counted; float sep; V3 n;
+        if (!sat_axis(A, B, d, sat_axis_dir(A, B, k), counted, sep, n)) return 0;
+        if (!counted) continue;
+        if (k < 6) { if (!faceValid || sep > faceSep) { faceValid = true; faceSep = sep; faceK = k; } }
+        else       { if (!edgeValid || sep > edgeSep) { edgeValid = true; edgeSep = sep; edgeK = k; } }
+    }
+    if (!faceValid) return 0;
+    int best = faceK;
+    if (edgeValid && kEdgeRelTol * edgeSep > faceSep + kEdgeAbsTol) best = edgeK;
+    return 1 | (best << 1);
+}
+
+AVBD_HD void face_axes(const Obb& b, int k, V3& u, V3& v, float& eu, float& ev) {   // collision.cpp:73-92
+    if (k == 0) { u = b.ax[1]; v = b.ax[2]; eu = b.h.y; ev = b.h.z; }
+    else if (k == 1) { u = b.ax[0]; v = b.ax[2]; eu = b.h.x; ev = b.h.z; }
+    else { u = b.ax[0]; v = b.ax[1]; eu = b.h.x; ev = b.h.y; }
+}
+
+constexpr int kMaxPoly = 16;
+
+// Sutherland-Hodgman against dot(n,p) <= off.  collision.cpp:136-174
+AVBD_HD int clip_poly(const V3* in, int nin, V3 n, float off, V3* out) {
+    if (nin <= 0) return 0;
+    int no = 0;
+    V3 a = in[nin - 1];
+    float da = dot(n, a) - off;
+    for (int i = 0; i < nin; ++i) {
+        V3 b = in[i];
+        float db = dot(n, b) - off;
+        bool ain = da <= kPlaneEps, bin = db <= kPlaneEps;
+        if (ain != bin) {
+            float t = 0.0f, den = da - db;
+            if (fabsf(den) > kSatEps) t = clampf(da / den, 0.0f, 1.0f);
+            if (no < kMaxPoly) out[no++] = a + (b - a) * t;
+        }
+        if (bin && no < kMaxPoly) out[no++] = b;
+        a = b; da = db;
+    }
+    return no;
+}
+
+// collision.cpp:176-206
+AVBD_HD bool push_contact(V3 posA, Q4 rotA, V3 posB, Q4 rotB, RawContact* out, int& n, V3* mids, V3 xA, V3 xB, int key, V3 nBA) {
+    V3 mid = (xA + xB) * 0.5f;
+    for (int i = 0; i < n; ++i) if (len2(mid - mids[i]) < kMergeDistSq) return false;
+    if (n >= 4) return false;
+    RawContact& c = out[n];
+    c.feature = key;
+    c.rA = qrot(qconj(rotA), xA - posA);
+    c.rB = qrot(qconj(rotB), xB - posB);
+    c.normal = nBA;
+    mids[n] = mid; ++n;
+    return true;
+}
+
+// collision.cpp:313-394 (+ helpers :94-134)
+AVBD_HD int face_manifold(V3 posA, Q4 rotA, V3 posB, Q4 rotB, const Obb& A, const Obb& B, bool refIsA, int refAxis, V3 nAB, RawContact* out) {
+    const Obb& R = refIsA ? A : B;
+    const Obb& I = refIsA ? B : A;
+    V3 outward = refIsA ? nAB : -nAB;
+    V3 nBA = -nAB;
+    float sgn = dot(outward, R.ax[refAxis]) >= 0.0f ? 1.0f : -1.0f;
+    V3 fn = R.ax[refAxis] * sgn;
+    V3 fc = R.c + fn * comp(R.h, refAxis);
+    V3 fu, fv; float eu, ev;
+    face_axes(R, refAxis, fu, fv, eu, ev);
+    int inc = 0; float bestd = -FLT_MAX;
+    for (int i = 0; i < 3; ++i) { float d = adot(I.ax[i], fn); if (d > bestd) { bestd = d; inc = i; } }
+    float isg = dot(I.ax[inc], fn) > 0.0f ? -1.0f : 1.0f;
+    V3 inrm = I.ax[inc] * isg;
+    V3 icen = I.c + inrm * comp(I.h, inc);
+    V3 iu, iv; float ieu, iev;
+    face_axes(I, inc, iu, iv, ieu, iev);
+    V3 p0[kMaxPoly], p1[kMaxPoly];
+    p0[0] = (icen + iu * ieu) + iv * iev;
+    p0[1] = (icen - iu * ieu) + iv * iev;
+    p0[2] = (icen - iu * ieu) - iv * iev;
+    p0[3] = (icen + iu * ieu) - iv * iev;
+    int cnt = 4;
+    cnt = clip_poly(p0, cnt, fu, dot(fu, fc) + eu, p1); if (!cnt) return 0;
+    V3 nu = -fu;
+    cnt = clip_poly(p1, cnt, nu, dot(nu, fc) + eu, p0); if (!cnt) return 0;
+    cnt = clip_poly(p0, cnt, fv, dot(fv, fc) + ev, p1); if (!cnt) return 0;
+    V3 nv = -fv;
+    cnt = clip_poly(p1, cnt, nv, dot(nv, fc) + ev, p0); if (!cnt) return 0;
+
+    int n = 0; V3 mids[4];
+    int prefix = ((refIsA ? 0 : 1) << 24) | ((refAxis & 0xFF) << 16) | ((inc & 0xFF) << 8);
+    for (int i = 0; i < cnt && n < 4; ++i) {
+        V3 pi = p0[i];
+        float dist = dot(pi - fc, fn);
+        if (dist > kCollisionMargin) continue;
+        V3 pr = pi - fn * dist;
+        V3 xA = refIsA ? pr : pi, xB = refIsA ? pi : pr;
+        V3 rel = pr - fc;
+        float uc = dot(rel, fu), vc = dot(rel, fv);
+        float un = (eu > kSatEps) ? (uc / eu) : 0.0f;
+        float vn = (ev > kSatEps) ? (vc / ev) : 0.0f;
+        int qu = (int)floorf(clampf((un + 1.0f) * 7.5f, 0.0f, 15.0f));
+        int qv = (int)floorf(clampf((vn + 1.0f) * 7.5f, 0.0f, 15.0f));
+        int key = prefix | ((qu & 0x0F) << 4) | (qv & 0x0F);
+        push_contact(posA, rotA, posB, rotB, out, n, mids, xA, xB, key, nBA);
+    }
+    return n;
+}
+
+AVBD_HD void support_edge(const Obb& b, int k, V3 dir, V3& e0, V3& e1) {      // collision.cpp:249-263
+    int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+    float s1 = dot(dir, b.ax[k1]) >= 0.0f ? 1.0f : -1.0f;
+    float s2 = dot(dir, b.ax[k2]) >= 0.0f ? 1.0f : -1.0f;
+    V3 ec = (b.c + b.ax[k1] * (comp(b.h, k1) * s1)) + b.ax[k2] * (comp(b.h, k2) * s2);
+    e0 = ec - b.ax[k] * comp(b.h, k);
+    e1 = ec + b.ax[k] * comp(b.h, k);
+}
+
+AVBD_HD void seg_closest(V3 p0, V3 p1, V3 q0, V3 q1, V3& c0, V3& c1) {        // collision.cpp:265-311
+    V3 d1 = p1 - p0, d2 = q1 - q0, r = p0 - q0;
+    float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+    float s = 0.0f, t = 0.0f;
+    if (a <= kSatEps && e <= kSatEps) { c0 = p0; c1 = q0; return; }
+    if (a <= kSatEps) {
+        t = clampf(f / e, 0.0f, 1.0f);
+    } else {
+        float c = dot(d1, r);
+        if (e <= kSatEps) {
+            s = clampf(-c / a, 0.0f, 1.0f);
+        } else {
+            float b = dot(d1, d2);
+            float den = a * e - b * b;
+            if (fabsf(den) > kSatEps) s = clampf((b * f - c * e) / den, 0.0f, 1.0f);
+            t = (b * s + f) / e;
+            if (t < 0.0f) { t = 0.0f; s = clampf(-c / a, 0.0f, 1.0f); }
+            else if (t > 1.0f) { t = 1.0f; s = clampf((b - c) / a, 0.0f, 1.0f); }
+        }
+    }
+    c0 = p0 + d1 * s;
+    c1 = q0 + d2 * t;
+}
+
+// Emits the contacts for the axis `satCode` names (from sat_test on the same
+// poses).  collision.cpp:470-476
+AVBD_HD int build_contacts(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 sizeB, int satCode, RawContact* out) {
+    Obb A = make_obb(posA, rotA, sizeA), B = make_obb(posB, rotB, sizeB);
+    int k = satCode >> 1;
+    V3 d = B.c - A.c;
+    bool counted; float sep; V3 n;
+    sat_axis(A, B, d, sat_axis_dir(A, B, k), counted, sep, n);   // same ops as the winning test => same normal bits
+    if (k >= 6) {                                                // buildEdgeContact, collision.cpp:396-416
+        int ia = (k - 6) / 3, ib = (k - 6) % 3;
+        V3 a0, a1, b0, b1, xA, xB;
+        support_edge(A, ia, n, a0, a1);
+        support_edge(B, ib, -n, b0, b1);
+        seg_closest(a0, a1, b0, b1, xA, xB);
+        int cnt = 0; V3 mids[4];
+        int key = (2 << 24) | ((ia & 0xFF) << 8) | (ib & 0xFF);
+        push_contact(posA, rotA, posB, rotB, out, cnt, mids, xA, xB, key, -n);
+        return cnt;
+    }
+    if (k < 3) return face_manifold(posA, rotA, posB, rotB, A, B, true, k, n, out);
+    return face_manifold(posA, rotA, posB, rotB, A, B, false, k - 3, n, out);
+}
+
+} // namespace avbd

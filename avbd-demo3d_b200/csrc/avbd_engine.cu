@@ -1,0 +1,970 @@
+// avbd_engine.cu — world state, stage orchestration and the C ABI of
+// include/avbd_b200.h.  One avbd_world = one CUDA stream on one GPU holding one
+// world or a batch of independent worlds (ensemble).  No CPU fallback: every
+// entry point fails when no CUDA device is usable.
+#include "../../include/avbd_b200.h"
+#include "avbd_kernels_solve.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace avbd;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess) return fail(AVBD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(expr)                \
+    do {                         \
+        int r_ = (expr);         \
+        if (r_ < 0) return r_;   \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n, bool keep, cudaStream_t s) {
+        if (n <= cap) return 0;
+        size_t ncap = std::max<size_t>(n + n / 2, 256);
+        T* q = nullptr;
+        CK(cudaMalloc(&q, ncap * sizeof(T)));
+        if (keep && p && cap) {
+            CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        if (p) cudaFree(p);
+        p = q; cap = ncap;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+inline int blocks_for(long long n, int threads = kThreads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
+
+struct HostBody {   // what the host must remember to (re)classify bodies; dynamic state lives on the device
+    float radius, invMass;
+    int world, local;
+};
+struct HostForce { int type, a, b; };   // 0 joint 1 spring 2 ignore
+
+} // namespace
+
+struct avbd_world {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    SolveParams prm{};
+    long long launches = 0;
+
+    // bodies
+    int n = 0, nDyn = 0, nWorlds = 1;
+    std::vector<HostBody> hb;
+    DevBuf<BodyPose> pose; DevBuf<BodyAux> aux; DevBuf<BodyVel> vel; DevBuf<BodyInit> init;
+    DevBuf<float4> prevLin, size;
+    DevBuf<int> flags, worldId, localIdx, dynList;
+    bool topoDirty = true;
+    int keyShift = 1;
+
+    // broadphase
+    float cell = 1.0f; unsigned tableSize = 256;
+    DevBuf<unsigned> cellKey, cellKeySorted; DevBuf<int> cellVal, cellValSorted, cellStart, cellEnd;
+    DevBuf<int4> sortedCell; DevBuf<float4> sortedPos;
+    DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
+    DevBuf<unsigned long long> cand, candSorted; int nCand = 0, nPairs = 0;
+    DevBuf<int> candInfo, candFlag, candScan, survP;
+
+    // manifolds (ping-pong)
+    struct MBuf { DevBuf<unsigned long long> key; DevBuf<int4> hdr; DevBuf<float4> cA, cB, cN, cL, cP; } mb[2];
+    int cur = 0, nM = 0;
+
+    // graph
+    DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
+    DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
+    int2 hColRange[64]; int nColours = 0; bool graphValid = false;
+
+    // user forces
+    std::vector<JointRec> hJoints; std::vector<SpringRec> hSprings; std::vector<HostForce> hForces;
+    DevBuf<JointRec> joints; DevBuf<SpringRec> springs; DevBuf<int> fadjStart, fadj; DevBuf<unsigned long long> excl;
+    int nExcl = 0; bool forcesDirty = false; int uploadedJoints = 0, uploadedSprings = 0;
+
+    // counters / diagnostics
+    Counters* dCnt = nullptr; Counters* hCnt = nullptr;
+    DevBuf<Diag> dDiag; Diag* hDiag = nullptr; size_t hDiagCap = 0;
+    DevBuf<float> dx;
+    DevBuf<char> temp;
+
+    // timing
+    cudaEvent_t ev[9] = {};
+    bool timed = false;
+    avbd_step_stats stats{};
+
+    ManifoldSet mset(int which) {
+        MBuf& b = mb[which];
+        ManifoldSet s; s.key = b.key.p; s.hdr = b.hdr.p; s.cA = b.cA.p; s.cB = b.cB.p; s.cN = b.cN.p; s.cL = b.cL.p; s.cP = b.cP.p;
+        return s;
+    }
+    int ensure_manifolds(int which, size_t m) {
+        MBuf& b = mb[which];
+        TRY(b.key.ensure(m, false, stream)); TRY(b.hdr.ensure(m, false, stream));
+        TRY(b.cA.ensure(4 * m, false, stream)); TRY(b.cB.ensure(4 * m, false, stream)); TRY(b.cN.ensure(4 * m, false, stream));
+        TRY(b.cL.ensure(4 * m, false, stream)); TRY(b.cP.ensure(4 * m, false, stream));
+        return 0;
+    }
+    BodyView bview() {
+        BodyView v; v.pose = pose.p; v.aux = aux.p; v.vel = vel.p; v.init = init.p; v.prevLin = prevLin.p; v.size = size.p;
+        v.flags = flags.p; v.worldId = worldId.p; v.localIdx = localIdx.p; v.n = n;
+        return v;
+    }
+    GridView gview() {
+        GridView g; g.cell = cell; g.tableMask = tableSize - 1; g.key = cellKey.p; g.keySorted = cellKeySorted.p;
+        g.val = cellVal.p; g.valSorted = cellValSorted.p; g.cellStart = cellStart.p; g.cellEnd = cellEnd.p;
+        g.sortedCell = sortedCell.p; g.sortedPos = sortedPos.p; g.largeList = largeList.p; g.worldLargeStart = worldLargeStart.p;
+        return g;
+    }
+    ForceView fview() {
+        ForceView f; f.joints = joints.p; f.nJoints = (int)hJoints.size(); f.springs = springs.p; f.nSprings = (int)hSprings.size();
+        bool any = f.nJoints + f.nSprings > 0;
+        f.adjStart = any ? fadjStart.p : nullptr; f.adj = any ? fadj.p : nullptr;
+        return f;
+    }
+};
+
+namespace {
+
+int read_counters(avbd_world* w) {
+    CK(cudaMemcpyAsync(w->hCnt, w->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+template <class K, class V>
+int sort_pairs(avbd_world* w, const K* kin, K* kout, const V* vin, V* vout, int n, int bits) {
+    if (n <= 0) return 0;
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, bits, w->stream));
+    TRY(w->temp.ensure(bytes, false, w->stream));
+    CK(cub::DeviceRadixSort::SortPairs(w->temp.p, bytes, kin, kout, vin, vout, n, 0, bits, w->stream));
+    w->launches += 1 + (bits + 7) / 8 * 2;
+    return 0;
+}
+template <class K>
+int sort_keys(avbd_world* w, const K* kin, K* kout, int n, int bits) {
+    if (n <= 0) return 0;
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, kin, kout, n, 0, bits, w->stream));
+    TRY(w->temp.ensure(bytes, false, w->stream));
+    CK(cub::DeviceRadixSort::SortKeys(w->temp.p, bytes, kin, kout, n, 0, bits, w->stream));
+    w->launches += 1 + (bits + 7) / 8 * 2;
+    return 0;
+}
+int exclusive_scan(avbd_world* w, const int* in, int* out, int n) {
+    if (n <= 0) return 0;
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, w->stream));
+    TRY(w->temp.ensure(bytes, false, w->stream));
+    CK(cub::DeviceScan::ExclusiveSum(w->temp.p, bytes, in, out, n, w->stream));
+    w->launches += 2;
+    return 0;
+}
+
+int bits_for(unsigned long long maxValue) { int b = 1; while ((1ull << b) <= maxValue) ++b; return b; }
+
+__global__ void rekey_manifolds(ManifoldSet ms, int nM, int keyShift) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < nM) ms.key[m] = ((unsigned long long)(unsigned)ms.hdr[m].x << keyShift) | (unsigned)ms.hdr[m].y;
+}
+
+// Rebuilds everything that depends on the body / user-force SET (not on poses).
+int prepare(avbd_world* w) {
+    if (!w->topoDirty && !w->forcesDirty) return 0;
+    cudaStream_t s = w->stream;
+    int n = w->n;
+    if (w->topoDirty && n > 0) {
+        std::vector<float> radii(n);
+        for (int i = 0; i < n; ++i) radii[i] = w->hb[i].radius;
+        std::vector<float> sorted = radii;
+        std::nth_element(sorted.begin(), sorted.begin() + n / 2, sorted.end());
+        float median = sorted[n / 2];
+        float thresh = 4.0f * median;
+        float maxSmall = 0.0f;
+        std::vector<int> flags(n), wid(n), lidx(n), dyn, large;
+        int nWorlds = 1;
+        for (int i = 0; i < n; ++i) {
+            bool isLarge = radii[i] > thresh;
+            if (!isLarge) maxSmall = std::max(maxSmall, radii[i]);
+            flags[i] = (w->hb[i].invMass > 0.0f ? kDynamic : 0) | (isLarge ? kLarge : 0);
+            wid[i] = w->hb[i].world; lidx[i] = w->hb[i].local;
+            nWorlds = std::max(nWorlds, wid[i] + 1);
+            if (flags[i] & kDynamic) dyn.push_back(i);
+            if (isLarge) large.push_back(i);
+        }
+        w->nWorlds = nWorlds; w->nDyn = (int)dyn.size(); w->nLarge = (int)large.size();
+        w->cell = std::max(2.02f * maxSmall, 1e-3f);
+        unsigned table = 256; while (table < 2u * (unsigned)n) table <<= 1;
+        w->tableSize = table;
+        std::vector<int> wls(nWorlds + 1, 0);
+        for (int l : large) wls[wid[l] + 1]++;
+        for (int k = 0; k < nWorlds; ++k) wls[k + 1] += wls[k];   // large is ascending by index => grouped by world
+        TRY(w->flags.ensure(n, false, s)); TRY(w->worldId.ensure(n, false, s)); TRY(w->localIdx.ensure(n, false, s));
+        TRY(w->dynList.ensure(std::max(1, w->nDyn), false, s)); TRY(w->largeList.ensure(std::max(1, w->nLarge), false, s));
+        TRY(w->worldLargeStart.ensure(nWorlds + 1, false, s));
+        CK(cudaMemcpyAsync(w->flags.p, flags.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->worldId.p, wid.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->localIdx.p, lidx.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (w->nDyn) CK(cudaMemcpyAsync(w->dynList.p, dyn.data(), dyn.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (w->nLarge) CK(cudaMemcpyAsync(w->largeList.p, large.data(), large.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(w->worldLargeStart.p, wls.data(), wls.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        // per-body scratch
+        TRY(w->cellKey.ensure(n, false, s)); TRY(w->cellKeySorted.ensure(n, false, s)); TRY(w->cellVal.ensure(n, false, s));
+        TRY(w->cellValSorted.ensure(n, false, s)); TRY(w->sortedCell.ensure(n, false, s)); TRY(w->sortedPos.ensure(n, false, s));
+        TRY(w->cellStart.ensure(table, false, s)); TRY(w->cellEnd.ensure(table, false, s));
+        TRY(w->adjRange.ensure(n, false, s)); TRY(w->colour.ensure(n, false, s));
+        TRY(w->colKey.ensure(std::max(1, w->nDyn), false, s)); TRY(w->colKeySorted.ensure(std::max(1, w->nDyn), false, s));
+        TRY(w->colVal.ensure(std::max(1, w->nDyn), false, s)); TRY(w->colOrder.ensure(std::max(1, w->nDyn), false, s));
+        TRY(w->colRange.ensure(64, false, s));
+        TRY(w->dDiag.ensure(nWorlds, false, s));
+        if ((size_t)nWorlds > w->hDiagCap) {
+            if (w->hDiag) cudaFreeHost(w->hDiag);
+            CK(cudaMallocHost(&w->hDiag, sizeof(Diag) * nWorlds));
+            w->hDiagCap = nWorlds;
+            std::memset(w->hDiag, 0, sizeof(Diag) * nWorlds);
+        }
+        int shift = bits_for((unsigned long long)std::max(1, n - 1));
+        if (shift != w->keyShift) {
+            w->keyShift = shift;
+            if (w->nM > 0) { rekey_manifolds<<<blocks_for(w->nM), kThreads, 0, s>>>(w->mset(w->cur), w->nM, shift); w->launches++; }
+            w->forcesDirty = true;   // exclusion keys are packed with keyShift too
+        }
+        w->graphValid = false;
+    }
+    if (w->forcesDirty || w->topoDirty) {
+        int nj = (int)w->hJoints.size(), ns = (int)w->hSprings.size();
+        // device records: only append new ones so lambda/penalty of existing rows survive
+        TRY(w->joints.ensure(std::max(1, nj), true, s)); TRY(w->springs.ensure(std::max(1, ns), true, s));
+        if (nj > w->uploadedJoints)
+            CK(cudaMemcpyAsync(w->joints.p + w->uploadedJoints, w->hJoints.data() + w->uploadedJoints, (nj - w->uploadedJoints) * sizeof(JointRec), cudaMemcpyHostToDevice, s));
+        if (ns > w->uploadedSprings)
+            CK(cudaMemcpyAsync(w->springs.p + w->uploadedSprings, w->hSprings.data() + w->uploadedSprings, (ns - w->uploadedSprings) * sizeof(SpringRec), cudaMemcpyHostToDevice, s));
+        w->uploadedJoints = nj; w->uploadedSprings = ns;
+        // CSR body -> user force rows, and the sorted pair-exclusion list (rigid.cpp:61-69 for non-manifold forces)
+        std::vector<int> start(n + 1, 0), adj;
+        std::vector<unsigned long long> ex;
+        std::vector<std::vector<int>> per(n);
+        int ji = 0, si = 0;
+        for (const HostForce& f : w->hForces) {
+            int idx = f.type == 0 ? ji++ : (f.type == 1 ? si++ : 0);
+            if (f.type != 2) {
+                if (f.a >= 0) per[f.a].push_back(idx * 4 + f.type * 2 + 1);
+                if (f.b >= 0) per[f.b].push_back(idx * 4 + f.type * 2 + 0);
+            }
+            if (f.a >= 0 && f.b >= 0) {
+                unsigned hi = (unsigned)std::max(f.a, f.b), lo = (unsigned)std::min(f.a, f.b);
+                ex.push_back(((unsigned long long)hi << w->keyShift) | lo);
+            }
+        }
+        for (int i = 0; i < n; ++i) { start[i + 1] = start[i] + (int)per[i].size(); adj.insert(adj.end(), per[i].begin(), per[i].end()); }
+        std::sort(ex.begin(), ex.end());
+        ex.erase(std::unique(ex.begin(), ex.end()), ex.end());
+        w->nExcl = (int)ex.size();
+        TRY(w->fadjStart.ensure(n + 1, false, s)); TRY(w->fadj.ensure(std::max<size_t>(1, adj.size()), false, s));
+        TRY(w->excl.ensure(std::max<size_t>(1, ex.size()), false, s));
+        CK(cudaMemcpyAsync(w->fadjStart.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (!adj.empty()) CK(cudaMemcpyAsync(w->fadj.p, adj.data(), adj.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (!ex.empty()) CK(cudaMemcpyAsync(w->excl.p, ex.data(), ex.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        w->graphValid = false;
+    }
+    w->topoDirty = false; w->forcesDirty = false;
+    return 0;
+}
+
+// Emits candidate pair keys and sorts them.  includePersisting adds last step's live manifold keys.
+int run_broadphase(avbd_world* w, bool includePersisting) {
+    cudaStream_t s = w->stream;
+    int n = w->n;
+    w->nCand = 0; w->nPairs = 0;
+    if (n == 0) return 0;
+    BodyView bv = w->bview(); GridView gv = w->gview();
+    bp_cells<<<blocks_for(n), kThreads, 0, s>>>(bv, gv);
+    int tbits = bits_for(w->tableSize);   // sentinel bucket == tableSize needs one more bit
+    TRY(sort_pairs(w, w->cellKey.p, w->cellKeySorted.p, w->cellVal.p, w->cellValSorted.p, n, tbits));
+    CK(cudaMemsetAsync(w->cellStart.p, 0, w->tableSize * sizeof(int), s));
+    CK(cudaMemsetAsync(w->cellEnd.p, 0, w->tableSize * sizeof(int), s));
+    bp_cell_bounds<<<blocks_for(n), kThreads, 0, s>>>(bv, gv);
+    w->launches += 4;
+    if (w->cand.cap == 0) { TRY(w->cand.ensure((size_t)std::max(1024, 16 * n), false, s)); }
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        CK(cudaMemsetAsync(w->dCnt, 0, sizeof(Counters), s));
+        PairSink sink; sink.keys = w->cand.p; sink.cap = (int)w->cand.cap; sink.keyShift = w->keyShift; sink.cnt = w->dCnt;
+        bp_pairs_small<<<blocks_for(n), kThreads, 0, s>>>(bv, gv, sink);
+        if (w->nLarge) bp_pairs_large<<<blocks_for(n), kThreads, 0, s>>>(bv, gv, sink);
+        w->launches += 2 + (w->nLarge ? 1 : 0);
+        TRY(read_counters(w));
+        int pairsOnly = w->hCnt->nCand;
+        if (includePersisting && w->nM > 0) {
+            bp_append_persisting<<<blocks_for(w->nM), kThreads, 0, s>>>(w->mset(w->cur), w->nM, sink);
+            w->launches++;
+            TRY(read_counters(w));
+        }
+        if (w->hCnt->nCand <= (int)w->cand.cap && !(w->hCnt->overflow & 1)) { w->nPairs = pairsOnly; w->nCand = w->hCnt->nCand; break; }
+        TRY(w->cand.ensure((size_t)w->hCnt->nCand + 1024, false, s));
+        if (attempt == 7) return fail(AVBD_ERR_CAPACITY, "pair buffer kept overflowing");
+    }
+    TRY(w->candSorted.ensure(w->cand.cap, false, s));
+    TRY(sort_keys(w, w->cand.p, w->candSorted.p, w->nCand, 2 * w->keyShift));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_collide(avbd_world* w) {
+    cudaStream_t s = w->stream;
+    TRY(prepare(w));
+    if (w->n > 0) CK(cudaMemsetAsync(w->dDiag.p, 0, sizeof(Diag) * w->nWorlds, s));
+    if (w->timed) cudaEventRecord(w->ev[0], s);
+    TRY(run_broadphase(w, true));
+    if (w->timed) cudaEventRecord(w->ev[1], s);
+    int nc = w->nCand;
+    int nSurv = 0;
+    if (nc > 0) {
+        TRY(w->candInfo.ensure(nc, false, s)); TRY(w->candFlag.ensure(nc, false, s));
+        TRY(w->candScan.ensure(nc, false, s)); TRY(w->survP.ensure(nc, false, s));
+        np_cull<<<blocks_for(nc), kThreads, 0, s>>>(w->bview(), w->candSorted.p, nc, w->keyShift, w->excl.p, w->nExcl, w->candInfo.p, w->candFlag.p);
+        TRY(exclusive_scan(w, w->candFlag.p, w->candScan.p, nc));
+        np_compact<<<blocks_for(nc), kThreads, 0, s>>>(w->candFlag.p, w->candScan.p, nc, w->survP.p, w->dCnt);
+        w->launches += 2;
+        TRY(read_counters(w));
+        nSurv = w->hCnt->nSurvive;
+    }
+    int nxt = w->cur ^ 1;
+    if (nSurv > 0) {
+        TRY(w->ensure_manifolds(nxt, nSurv));
+        np_build<<<blocks_for(nSurv), kThreads, 0, s>>>(w->bview(), w->candSorted.p, w->candInfo.p, w->survP.p, nSurv, w->keyShift,
+                                                          w->mset(w->cur), w->nM, w->mset(nxt), w->prm);
+        w->launches++;
+    }
+    w->cur = nxt; w->nM = nSurv;
+    ForceView fv = w->fview();
+    if (fv.nJoints + fv.nSprings > 0) {
+        decay_user_forces<<<blocks_for(fv.nJoints + fv.nSprings), kThreads, 0, s>>>(fv, w->prm);
+        w->launches++;
+    }
+    w->graphValid = false;
+    if (w->timed) cudaEventRecord(w->ev[2], s);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_predict(avbd_world* w) {
+    TRY(prepare(w));
+    if (w->n == 0) return 0;
+    predict_bodies<<<blocks_for(w->n), kThreads, 0, w->stream>>>(w->bview(), w->prm, w->dDiag.p);
+    w->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_colour(avbd_world* w) {
+    cudaStream_t s = w->stream;
+    TRY(prepare(w));
+    w->nColours = 0;
+    if (w->n == 0 || w->nDyn == 0) { w->graphValid = true; return 0; }
+    int nM = w->nM, n = w->n;
+    CK(cudaMemsetAsync(w->adjRange.p, 0, sizeof(int4) * n, s));
+    ManifoldSet ms = w->mset(w->cur);
+    if (nM > 0) {
+        TRY(w->bKey.ensure(nM, false, s)); TRY(w->bKeySorted.ensure(nM, false, s)); TRY(w->bVal.ensure(nM, false, s)); TRY(w->bList.ensure(nM, false, s));
+        adj_a_ranges<<<blocks_for(nM), kThreads, 0, s>>>(ms.hdr, nM, w->flags.p, n, w->adjRange.p, w->bKey.p, w->bVal.p);
+        TRY(sort_pairs(w, w->bKey.p, w->bKeySorted.p, w->bVal.p, w->bList.p, nM, bits_for((unsigned long long)n)));
+        adj_b_ranges<<<blocks_for(nM), kThreads, 0, s>>>(w->bKeySorted.p, nM, n, w->adjRange.p);
+        w->launches += 2;
+    } else {
+        TRY(w->bList.ensure(1, false, s));
+    }
+    colour_init<<<blocks_for(n), kThreads, 0, s>>>(w->flags.p, n, w->colour.p);
+    w->launches++;
+    ForceView fv = w->fview();
+    for (int round = 0;; ++round) {
+        if (round > 4096) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
+        CK(cudaMemsetAsync(&w->dCnt->nUncoloured, 0, sizeof(int), s));
+        colour_round<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p, w->dCnt);
+        w->launches++;
+        TRY(read_counters(w));
+        if (w->hCnt->nUncoloured == 0) break;
+    }
+    if (w->hCnt->overflow & 4) return fail(AVBD_ERR_CAPACITY, "more than 64 colours needed");
+    colour_keys<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);
+    TRY(sort_pairs(w, w->colKey.p, w->colKeySorted.p, w->colVal.p, w->colOrder.p, w->nDyn, 7));
+    CK(cudaMemsetAsync(w->colRange.p, 0, sizeof(int2) * 64, s));
+    colour_bounds<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);
+    w->launches += 2;
+    CK(cudaMemcpyAsync(w->hColRange, w->colRange.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
+    TRY(read_counters(w));
+    w->nColours = w->hCnt->nColours;
+    w->graphValid = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+constexpr int kLanesPerBody = 8;
+
+int run_primal(avbd_world* w, float alpha, float* dxDev) {
+    if (!w->graphValid) TRY(run_colour(w));
+    cudaStream_t s = w->stream;
+    ManifoldSet ms = w->mset(w->cur);
+    ForceView fv = w->fview();
+    for (int c = 0; c < w->nColours; ++c) {
+        int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
+        if (count <= 0) continue;
+        primal_colour<kLanesPerBody><<<blocks_for((long long)count * kLanesPerBody), kThreads, 0, s>>>(
+            w->bview(), w->adjRange.p, w->bList.p, ms, fv, w->colOrder.p + first, count, w->prm, alpha, dxDev, w->dDiag.p);
+        w->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_dual(avbd_world* w, float alpha) {
+    cudaStream_t s = w->stream;
+    if (w->nM > 0) {
+        dual_contacts<<<blocks_for((long long)w->nM * 4), kThreads, 0, s>>>(w->bview(), w->mset(w->cur), w->nM, w->prm, alpha);
+        w->launches++;
+    }
+    ForceView fv = w->fview();
+    if (fv.nJoints + fv.nSprings > 0) {
+        dual_user_forces<<<blocks_for(fv.nJoints + fv.nSprings), kThreads, 0, s>>>(w->bview(), fv, w->prm);
+        w->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int run_velocity(avbd_world* w) {
+    cudaStream_t s = w->stream;
+    if (w->n == 0) return 0;
+    velocity_bodies<<<blocks_for(w->n), kThreads, 0, s>>>(w->bview(), w->prm, w->dDiag.p);
+    w->launches++;
+    if (w->nM > 0) {
+        diagnostics_contacts<<<blocks_for((long long)w->nM * 4), kThreads, 0, s>>>(w->bview(), w->mset(w->cur), w->nM, w->dDiag.p);
+        w->launches++;
+    }
+    CK(cudaMemcpyAsync(w->hDiag, w->dDiag.p, sizeof(Diag) * w->nWorlds, cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int step_once(avbd_world* w) {
+    cudaStream_t s = w->stream;
+    TRY(run_collide(w));
+    TRY(run_predict(w));
+    if (w->timed) cudaEventRecord(w->ev[3], s);
+    TRY(run_colour(w));
+    if (w->timed) cudaEventRecord(w->ev[4], s);
+    int total = w->prm.iterations + (w->prm.postStabilize ? 1 : 0);
+    for (int it = 0; it < total; ++it) {
+        float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
+        TRY(run_primal(w, a, nullptr));
+        if (it < w->prm.iterations) TRY(run_dual(w, a));
+    }
+    if (w->timed) cudaEventRecord(w->ev[5], s);
+    TRY(run_velocity(w));
+    if (w->timed) cudaEventRecord(w->ev[6], s);
+    return 0;
+}
+
+void fill_diag(const Diag& d, avbd_diagnostics* o) {
+    o->maxPenetration = d.maxPenetration; o->maxConstraintViolation = d.maxViolation; o->maxLinearSpeed = d.maxLinearSpeed;
+    o->maxAngularSpeed = d.maxAngularSpeed; o->maxNormalImpulse = d.maxNormalImpulse; o->activeContacts = d.activeContacts;
+    o->activeManifolds = d.activeManifolds; o->dynamicBodies = d.dynamicBodies; o->nanEvents = d.nanEvents;
+}
+
+int use_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(AVBD_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= count) return fail(AVBD_ERR_ARG, "bad device index");
+    CK(cudaSetDevice(device));
+    return 0;
+}
+
+} // namespace
+
+// ============================================================================= C ABI
+extern "C" {
+
+const char* avbd_last_error(void) { return g_err.c_str(); }
+
+int avbd_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+avbd_world* avbd_world_create(int device) {
+    if (use_device(device) < 0) return nullptr;
+    avbd_world* w = new avbd_world();
+    w->device = device;
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&w->dCnt, sizeof(Counters)) != cudaSuccess || cudaMallocHost(&w->hCnt, sizeof(Counters)) != cudaSuccess) {
+        fail(AVBD_ERR_CUDA, "world allocation failed");
+        delete w;
+        return nullptr;
+    }
+    for (auto& e : w->ev) cudaEventCreate(&e);
+    std::memset(w->hCnt, 0, sizeof(Counters));
+    avbd_default_params(w);
+    return w;
+}
+
+void avbd_world_destroy(avbd_world* w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    cudaStreamSynchronize(w->stream);
+    w->pose.release(); w->aux.release(); w->vel.release(); w->init.release(); w->prevLin.release(); w->size.release();
+    w->flags.release(); w->worldId.release(); w->localIdx.release(); w->dynList.release();
+    w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellStart.release(); w->cellEnd.release();
+    w->sortedCell.release(); w->sortedPos.release(); w->largeList.release(); w->worldLargeStart.release();
+    w->cand.release(); w->candSorted.release(); w->candInfo.release(); w->candFlag.release(); w->candScan.release(); w->survP.release();
+    for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.cL.release(); b.cP.release(); }
+    w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
+    w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
+    w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
+    w->dDiag.release(); w->dx.release(); w->temp.release();
+    if (w->dCnt) cudaFree(w->dCnt);
+    if (w->hCnt) cudaFreeHost(w->hCnt);
+    if (w->hDiag) cudaFreeHost(w->hDiag);
+    for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+int avbd_clear(avbd_world* w) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->stream));
+    w->n = 0; w->nDyn = 0; w->nWorlds = 1; w->hb.clear(); w->nM = 0; w->nCand = 0; w->nPairs = 0;
+    w->hJoints.clear(); w->hSprings.clear(); w->hForces.clear(); w->uploadedJoints = 0; w->uploadedSprings = 0; w->nExcl = 0;
+    w->topoDirty = true; w->forcesDirty = true; w->graphValid = false; w->nColours = 0;
+    if (w->hDiag) std::memset(w->hDiag, 0, sizeof(Diag) * w->hDiagCap);
+    return 0;
+}
+
+int avbd_set_params(avbd_world* w, float dt, const float* g, int iterations, float alpha, float beta, float gamma, int ps) {
+    if (!w || !g) return fail(AVBD_ERR_ARG, "null argument");
+    w->prm.dt = dt; w->prm.gx = g[0]; w->prm.gy = g[1]; w->prm.gz = g[2]; w->prm.iterations = iterations;
+    w->prm.alpha = alpha; w->prm.beta = beta; w->prm.gamma = gamma; w->prm.postStabilize = ps ? 1 : 0;
+    return 0;
+}
+
+int avbd_default_params(avbd_world* w) {       // solver.cpp:240-253
+    const float g[3] = {0.0f, -10.0f, 0.0f};
+    return avbd_set_params(w, 1.0f / 60.0f, g, 10, 0.95f, 100000.0f, 0.99f, 0);
+}
+
+int avbd_add_bodies(avbd_world* w, int count, const float* size3, const float* density, const float* friction, const float* pos3,
+                    const float* quat4, const float* lin3, const float* ang3, const int* world_ids) {
+    if (!w || count < 0 || (count > 0 && (!size3 || !density || !friction || !pos3 || !quat4 || !lin3 || !ang3)))
+        return fail(AVBD_ERR_ARG, "bad argument to avbd_add_bodies");
+    CK(cudaSetDevice(w->device));
+    if (count == 0) return w->n;
+    cudaStream_t s = w->stream;
+    int first = w->n, total = first + count;
+    std::vector<BodyPose> pose(count); std::vector<BodyAux> aux(count); std::vector<BodyVel> vel(count); std::vector<BodyInit> init(count);
+    std::vector<float4> prev(count), size(count);
+    w->hb.reserve(total);
+    for (int i = 0; i < count; ++i) {
+        // Rigid::Rigid, rigid.cpp:12-41
+        float sx = size3[3 * i], sy = size3[3 * i + 1], sz = size3[3 * i + 2];
+        float mass = sx * sy * sz * density[i];
+        float invMass = (mass > 0.0f) ? 1.0f / mass : 0.0f;
+        float radius = sqrtf(sx * sx + sy * sy + sz * sz) * 0.5f;
+        float ixx = 0.0f, iyy = 0.0f, izz = 0.0f;
+        if (invMass > 0.0f) {
+            ixx = (1.0f / 12.0f) * mass * (sy * sy + sz * sz);
+            iyy = (1.0f / 12.0f) * mass * (sx * sx + sz * sz);
+            izz = (1.0f / 12.0f) * mass * (sx * sx + sy * sy);
+        }
+        pose[i].pos = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], invMass);
+        pose[i].rot = make_float4(quat4[4 * i], quat4[4 * i + 1], quat4[4 * i + 2], quat4[4 * i + 3]);
+        vel[i].lin = make_float4(lin3[3 * i], lin3[3 * i + 1], lin3[3 * i + 2], 0.0f);
+        vel[i].ang = make_float4(ang3[3 * i], ang3[3 * i + 1], ang3[3 * i + 2], 0.0f);
+        prev[i] = vel[i].lin;
+        init[i].pos0 = make_float4(0.f, 0.f, 0.f, 0.f); init[i].rot0 = make_float4(0.f, 0.f, 0.f, 1.f);
+        aux[i].posI = make_float4(0.f, 0.f, 0.f, 0.f); aux[i].rotI = make_float4(0.f, 0.f, 0.f, 1.f);
+        aux[i].mass = make_float4(mass, invMass, friction[i], radius);
+        aux[i].inert = make_float4(ixx, iyy, izz, 0.0f);
+        size[i] = make_float4(sx, sy, sz, friction[i]);
+        HostBody hb; hb.radius = radius; hb.invMass = invMass; hb.world = world_ids ? world_ids[i] : 0;
+        int prevWorld = w->hb.empty() ? -1 : w->hb.back().world;
+        if (hb.world < prevWorld) return fail(AVBD_ERR_ARG, "world ids must be non-decreasing");
+        hb.local = (hb.world == prevWorld) ? w->hb.back().local + 1 : 0;
+        w->hb.push_back(hb);
+    }
+    TRY(w->pose.ensure(total, true, s)); TRY(w->aux.ensure(total, true, s)); TRY(w->vel.ensure(total, true, s)); TRY(w->init.ensure(total, true, s));
+    TRY(w->prevLin.ensure(total, true, s)); TRY(w->size.ensure(total, true, s));
+    CK(cudaMemcpyAsync(w->pose.p + first, pose.data(), count * sizeof(BodyPose), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w->aux.p + first, aux.data(), count * sizeof(BodyAux), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w->vel.p + first, vel.data(), count * sizeof(BodyVel), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w->init.p + first, init.data(), count * sizeof(BodyInit), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w->prevLin.p + first, prev.data(), count * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w->size.p + first, size.data(), count * sizeof(float4), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    w->n = total;
+    w->topoDirty = true;
+    return first;
+}
+
+int avbd_num_bodies(const avbd_world* w) { return w ? w->n : 0; }
+
+namespace {
+// current pose of one body (joint / spring constructors capture it, joint.cpp:17-19, spring.cpp:19-23)
+int fetch_pose(avbd_world* w, int i, BodyPose& out) {
+    CK(cudaMemcpyAsync(&out, w->pose.p + i, sizeof(BodyPose), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+}
+
+int avbd_add_joint(avbd_world* w, int a, int b, const float* anchorA, const float* anchorB, float linK, float angK) {
+    if (!w || b < 0 || b >= w->n || a >= w->n || a == b || !anchorA) return fail(AVBD_ERR_ARG, "bad joint");
+    CK(cudaSetDevice(w->device));
+    JointRec j{};
+    j.a = a; j.b = b; j.kLin = linK; j.kAng = angK;
+    BodyPose pb; TRY(fetch_pose(w, b, pb));
+    Q4 qB = quat(pb.rot);
+    if (a >= 0) {
+        if (!anchorB) return fail(AVBD_ERR_ARG, "bad joint");
+        BodyPose pa; TRY(fetch_pose(w, a, pa));
+        j.rA = make_float4(anchorA[0], anchorA[1], anchorA[2], 0.f); j.rB = make_float4(anchorB[0], anchorB[1], anchorB[2], 0.f);
+        j.rel0 = f4(qmul(qconj(quat(pa.rot)), qB));                                 // joint.cpp:19
+    } else {
+        V3 wa = mk3(anchorA[0], anchorA[1], anchorA[2]);
+        j.rA = f4(wa, 0.f);
+        M3 R = qmat(qB);                                                            // joint.cpp:47: transpose(R) * (anchor - pos)
+        V3 d = wa - xyz(pb.pos);
+        M3 Rt = m3(mk3(R.c[0].x, R.c[1].x, R.c[2].x), mk3(R.c[0].y, R.c[1].y, R.c[2].y), mk3(R.c[0].z, R.c[1].z, R.c[2].z));
+        j.rB = f4(mv(Rt, d), 0.f);
+        j.rel0 = f4(qB);
+    }
+    for (int r = 0; r < 6; ++r) { j.lambda[r] = 0.0f; j.penalty[r] = kPenaltyMin; }
+    w->hJoints.push_back(j);
+    w->hForces.push_back(HostForce{0, a, b});
+    w->forcesDirty = true;
+    return (int)w->hJoints.size() - 1;
+}
+
+int avbd_add_spring(avbd_world* w, int a, int b, const float* anchorA, const float* anchorB, float k, float rest) {
+    if (!w || a < 0 || b < 0 || a >= w->n || b >= w->n || a == b || !anchorA || !anchorB) return fail(AVBD_ERR_ARG, "bad spring");
+    CK(cudaSetDevice(w->device));
+    SpringRec sp{};
+    sp.a = a; sp.b = b; sp.k = k; sp.rest = rest;
+    sp.rA = make_float4(anchorA[0], anchorA[1], anchorA[2], 0.f); sp.rB = make_float4(anchorB[0], anchorB[1], anchorB[2], 0.f);
+    if (rest < 0) {                                                                  // spring.cpp:19-23
+        BodyPose pa, pb; TRY(fetch_pose(w, a, pa)); TRY(fetch_pose(w, b, pb));
+        V3 pA = xyz(pa.pos) + qrot(quat(pa.rot), xyz(sp.rA)), pB = xyz(pb.pos) + qrot(quat(pb.rot), xyz(sp.rB));
+        sp.rest = len(pA - pB);
+    }
+    sp.lambda = 0.0f; sp.penalty = kPenaltyMin;
+    w->hSprings.push_back(sp);
+    w->hForces.push_back(HostForce{1, a, b});
+    w->forcesDirty = true;
+    return (int)w->hSprings.size() - 1;
+}
+
+int avbd_add_ignore(avbd_world* w, int a, int b) {
+    if (!w || a < 0 || b < 0 || a >= w->n || b >= w->n || a == b) return fail(AVBD_ERR_ARG, "bad ignore pair");
+    w->hForces.push_back(HostForce{2, a, b});
+    w->forcesDirty = true;
+    return 0;
+}
+
+int avbd_step(avbd_world* w, int nSteps) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    for (int i = 0; i < nSteps; ++i) TRY(step_once(w));
+    return 0;
+}
+
+int avbd_sync(avbd_world* w) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int avbd_download_state(avbd_world* w, float* out) {
+    if (!w || (!out && w->n)) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    int n = w->n; if (!n) return 0;
+    std::vector<BodyPose> pose(n); std::vector<BodyVel> vel(n);
+    CK(cudaMemcpyAsync(pose.data(), w->pose.p, n * sizeof(BodyPose), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(vel.data(), w->vel.p, n * sizeof(BodyVel), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    for (int i = 0; i < n; ++i) {
+        float* o = out + 13 * (size_t)i;
+        o[0] = pose[i].pos.x; o[1] = pose[i].pos.y; o[2] = pose[i].pos.z;
+        o[3] = pose[i].rot.x; o[4] = pose[i].rot.y; o[5] = pose[i].rot.z; o[6] = pose[i].rot.w;
+        o[7] = vel[i].lin.x; o[8] = vel[i].lin.y; o[9] = vel[i].lin.z;
+        o[10] = vel[i].ang.x; o[11] = vel[i].ang.y; o[12] = vel[i].ang.z;
+    }
+    return 0;
+}
+
+int avbd_upload_state(avbd_world* w, const float* in) {
+    if (!w || (!in && w->n)) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    int n = w->n; if (!n) return 0;
+    std::vector<BodyPose> pose(n); std::vector<BodyVel> vel(n);
+    for (int i = 0; i < n; ++i) {
+        const float* o = in + 13 * (size_t)i;
+        pose[i].pos = make_float4(o[0], o[1], o[2], w->hb[i].invMass);
+        pose[i].rot = make_float4(o[3], o[4], o[5], o[6]);
+        vel[i].lin = make_float4(o[7], o[8], o[9], 0.f); vel[i].ang = make_float4(o[10], o[11], o[12], 0.f);
+    }
+    CK(cudaMemcpyAsync(w->pose.p, pose.data(), n * sizeof(BodyPose), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaMemcpyAsync(w->vel.p, vel.data(), n * sizeof(BodyVel), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int avbd_download_prev_linvel(avbd_world* w, float* out) {
+    if (!w || (!out && w->n)) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    int n = w->n; if (!n) return 0;
+    std::vector<float4> p(n);
+    CK(cudaMemcpyAsync(p.data(), w->prevLin.p, n * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    for (int i = 0; i < n; ++i) { out[3 * i] = p[i].x; out[3 * i + 1] = p[i].y; out[3 * i + 2] = p[i].z; }
+    return 0;
+}
+
+int avbd_upload_prev_linvel(avbd_world* w, const float* in) {
+    if (!w || (!in && w->n)) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    int n = w->n; if (!n) return 0;
+    std::vector<float4> p(n);
+    for (int i = 0; i < n; ++i) p[i] = make_float4(in[3 * i], in[3 * i + 1], in[3 * i + 2], 0.f);
+    CK(cudaMemcpyAsync(w->prevLin.p, p.data(), n * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int avbd_download_body_props(avbd_world* w, float* out) {
+    if (!w || (!out && w->n)) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    int n = w->n; if (!n) return 0;
+    std::vector<BodyAux> aux(n); std::vector<float4> size(n);
+    CK(cudaMemcpyAsync(aux.data(), w->aux.p, n * sizeof(BodyAux), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(size.data(), w->size.p, n * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    for (int i = 0; i < n; ++i) {
+        float* o = out + 10 * (size_t)i;
+        o[0] = size[i].x; o[1] = size[i].y; o[2] = size[i].z; o[3] = aux[i].mass.x; o[4] = aux[i].mass.y;
+        o[5] = aux[i].inert.x; o[6] = aux[i].inert.y; o[7] = aux[i].inert.z; o[8] = aux[i].mass.z; o[9] = aux[i].mass.w;
+    }
+    return 0;
+}
+
+int avbd_num_worlds(const avbd_world* w) { return w ? w->nWorlds : 0; }
+
+int avbd_get_world_diagnostics(avbd_world* w, avbd_diagnostics* out, int count) {
+    if (!w || !out) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->stream));
+    for (int k = 0; k < count; ++k) {
+        if (k < w->nWorlds && w->hDiag) fill_diag(w->hDiag[k], out + k);
+        else std::memset(out + k, 0, sizeof(avbd_diagnostics));
+    }
+    return 0;
+}
+
+int avbd_get_diagnostics(avbd_world* w, avbd_diagnostics* out) {
+    if (!w || !out) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->stream));
+    Diag acc{};
+    for (int k = 0; k < w->nWorlds && w->hDiag; ++k) {
+        const Diag& d = w->hDiag[k];
+        acc.maxPenetration = std::max(acc.maxPenetration, d.maxPenetration); acc.maxViolation = std::max(acc.maxViolation, d.maxViolation);
+        acc.maxLinearSpeed = std::max(acc.maxLinearSpeed, d.maxLinearSpeed); acc.maxAngularSpeed = std::max(acc.maxAngularSpeed, d.maxAngularSpeed);
+        acc.maxNormalImpulse = std::max(acc.maxNormalImpulse, d.maxNormalImpulse);
+        acc.activeContacts += d.activeContacts; acc.activeManifolds += d.activeManifolds; acc.dynamicBodies += d.dynamicBodies; acc.nanEvents += d.nanEvents;
+    }
+    fill_diag(acc, out);
+    return 0;
+}
+
+int avbd_world_diagnostics_device_ptr(avbd_world* w, void** ptr, int* count) {
+    if (!w || !ptr || !count) return fail(AVBD_ERR_ARG, "null argument");
+    *ptr = w->dDiag.p; *count = w->nWorlds;
+    return 0;
+}
+
+int avbd_get_step_stats(avbd_world* w, avbd_step_stats* out) {
+    if (!w || !out) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->stream));
+    avbd_step_stats st{};
+    if (w->timed) {
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], w->ev[k], w->ev[k + 1]);
+        st.ms_broadphase = t[0]; st.ms_narrowphase = t[1]; st.ms_predict = t[2]; st.ms_graph = t[3]; st.ms_primal = t[4]; st.ms_velocity = t[5];
+        cudaEventElapsedTime(&st.ms_total, w->ev[0], w->ev[6]);
+        cudaGetLastError();
+    }
+    w->timed = true;   // stage events are recorded from the next step on
+    st.bodies = w->n; st.dynamicBodies = w->nDyn; st.pairs = w->nPairs; st.candidates = w->nCand; st.manifolds = w->nM;
+    avbd_diagnostics d; avbd_get_diagnostics(w, &d); st.contacts = d.activeContacts;
+    st.colours = w->nColours; st.iterations = w->prm.iterations; st.kernelLaunches = w->launches;
+    *out = st;
+    return 0;
+}
+
+int avbd_num_manifolds(avbd_world* w) { return w ? w->nM : 0; }
+
+int avbd_download_manifolds(avbd_world* w, int* ints, int* feats, int* stick, float* flts) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    int nM = w->nM; if (!nM) return 0;
+    std::vector<int4> hdr(nM); std::vector<float4> cA(4 * nM), cB(4 * nM), cN(4 * nM), cL(4 * nM), cP(4 * nM);
+    ManifoldSet ms = w->mset(w->cur);
+    cudaStream_t s = w->stream;
+    CK(cudaMemcpyAsync(hdr.data(), ms.hdr, nM * sizeof(int4), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cA.data(), ms.cA, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cB.data(), ms.cB, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cN.data(), ms.cN, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cL.data(), ms.cL, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cP.data(), ms.cP, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int m = 0; m < nM; ++m) {
+        int nc = hdr[m].z;
+        ints[3 * m] = hdr[m].x; ints[3 * m + 1] = hdr[m].y; ints[3 * m + 2] = nc;
+        float* f = flts + 81 * (size_t)m;
+        float mu; std::memcpy(&mu, &hdr[m].w, 4);
+        f[0] = mu;
+        for (int c = 0; c < 4; ++c) {
+            int ci = 4 * m + c; bool live = c < nc;
+            int feat; std::memcpy(&feat, &cP[ci].w, 4);
+            feats[ci] = live ? feat : 0;
+            stick[ci] = live ? (cL[ci].w != 0.0f ? 1 : 0) : 0;
+            float* o = f + 1 + 14 * c;
+            const float v[14] = {cA[ci].x, cA[ci].y, cA[ci].z, cB[ci].x, cB[ci].y, cB[ci].z, cN[ci].x, cN[ci].y, cN[ci].z,
+                                 0.0f /* penetration is draw-only state, not kept on the device */, cA[ci].w, cB[ci].w, cN[ci].w, 0.0f};
+            for (int k = 0; k < 14; ++k) o[k] = live ? v[k] : 0.0f;
+            for (int k = 0; k < 3; ++k) {
+                f[57 + 3 * c + k] = live ? (&cL[ci].x)[k] : 0.0f;
+                f[69 + 3 * c + k] = live ? (&cP[ci].x)[k] : 0.0f;
+            }
+        }
+    }
+    return 0;
+}
+
+int avbd_stage_broadphase(avbd_world* w) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    TRY(prepare(w));
+    TRY(run_broadphase(w, false));
+    return w->nCand;
+}
+
+int avbd_download_pairs(avbd_world* w, int* pairs, int cap) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    int nc = w->nCand;
+    if (nc == 0) return 0;
+    std::vector<unsigned long long> k(nc);
+    CK(cudaMemcpyAsync(k.data(), w->candSorted.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    int out = 0;
+    for (int i = 0; i < nc; ++i) {
+        if (i > 0 && k[i] == k[i - 1]) continue;
+        if (out < cap) { pairs[2 * out] = (int)(k[i] >> w->keyShift); pairs[2 * out + 1] = (int)(k[i] & ((1ull << w->keyShift) - 1ull)); }
+        ++out;
+    }
+    return out;
+}
+
+int avbd_stage_collide(avbd_world* w) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return run_collide(w); }
+int avbd_stage_predict(avbd_world* w) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return run_predict(w); }
+int avbd_stage_colour(avbd_world* w) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return run_colour(w); }
+
+int avbd_download_colours(avbd_world* w, int* colour_of, int* num_colours) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    if (num_colours) *num_colours = w->nColours;
+    if (colour_of && w->n) {
+        CK(cudaMemcpyAsync(colour_of, w->colour.p, w->n * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+    }
+    return 0;
+}
+
+int avbd_stage_primal(avbd_world* w, float alpha, float* dx_out) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    float* dxDev = nullptr;
+    if (dx_out && w->n) {
+        TRY(w->dx.ensure((size_t)w->n * 6, false, w->stream));
+        CK(cudaMemsetAsync(w->dx.p, 0, (size_t)w->n * 6 * sizeof(float), w->stream));
+        dxDev = w->dx.p;
+    }
+    TRY(run_primal(w, alpha, dxDev));
+    if (dxDev) {
+        CK(cudaMemcpyAsync(dx_out, dxDev, (size_t)w->n * 6 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+    }
+    return 0;
+}
+
+int avbd_stage_dual(avbd_world* w, float alpha) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return run_dual(w, alpha); }
+int avbd_stage_velocity(avbd_world* w) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return run_velocity(w); }
+
+int avbd_collide_pairs(int device, int n, const float* a10, const float* b10, int* counts, int* feats4, float* geom36) {
+    TRY(use_device(device));
+    if (n <= 0) return 0;
+    float *da = nullptr, *db = nullptr, *dg = nullptr; int *dc = nullptr, *df = nullptr;
+    CK(cudaMalloc(&da, n * 10 * sizeof(float))); CK(cudaMalloc(&db, n * 10 * sizeof(float))); CK(cudaMalloc(&dg, (size_t)n * 36 * sizeof(float)));
+    CK(cudaMalloc(&dc, n * sizeof(int))); CK(cudaMalloc(&df, n * 4 * sizeof(int)));
+    CK(cudaMemcpy(da, a10, n * 10 * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, b10, n * 10 * sizeof(float), cudaMemcpyHostToDevice));
+    np_collide_batch<<<blocks_for(n, 128), 128>>>(da, db, n, dc, df, dg);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(counts, dc, n * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(feats4, df, n * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(geom36, dg, (size_t)n * 36 * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dg); cudaFree(dc); cudaFree(df);
+    return 0;
+}
+
+int avbd_solve6x6(int device, int n, const float* lhs36, const float* rhs6, float* out6) {
+    TRY(use_device(device));
+    if (n <= 0) return 0;
+    float *dl = nullptr, *dr = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&dl, (size_t)n * 36 * sizeof(float))); CK(cudaMalloc(&dr, n * 6 * sizeof(float))); CK(cudaMalloc(&dout, n * 6 * sizeof(float)));
+    CK(cudaMemcpy(dl, lhs36, (size_t)n * 36 * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dr, rhs6, n * 6 * sizeof(float), cudaMemcpyHostToDevice));
+    solve6_batch<<<blocks_for(n, 128), 128>>>(dl, dr, n, dout);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out6, dout, n * 6 * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(dl); cudaFree(dr); cudaFree(dout);
+    return 0;
+}
+
+int avbd_pick(avbd_world* w, const float* origin3, const float* dir3, float* local3) {
+    (void)w; (void)origin3; (void)dir3; (void)local3;
+    return fail(AVBD_ERR_ARG, "avbd_pick: not implemented yet (SURVEY §8f.1)");
+}
+
+} // extern "C"

@@ -1,0 +1,254 @@
+// avbd_kernels_collide.cuh — broadphase (hashed uniform grid + large-body side
+// list) and narrowphase (SAT cull -> compaction -> manifold build with fused
+// feature-id warm start) kernels.
+//
+// Replaces the reference's O(n^2) pair loop + per-step new/delete of Manifold
+// nodes (solver.cpp:262-279, force.cpp:12-69) and Manifold::initialize
+// (manifold.cpp:71-175).  Candidate set == reference semantics:
+//   {sphere-overlap pairs} U {pairs that already own a manifold} \ {pairs linked by a user force}
+// and A is always the higher creation index (the reference's list is newest-first).
+#pragma once
+#include <cooperative_groups.h>
+#include "avbd_body.cuh"
+#include "avbd_forces.cuh"
+
+namespace avbd {
+namespace cg = cooperative_groups;
+
+constexpr int kThreads = 256;
+
+struct BodyView {
+    BodyPose* pose; BodyAux* aux; BodyVel* vel; BodyInit* init;
+    float4* prevLin; float4* size;      // size: sx sy sz friction
+    int* flags; int* worldId; int* localIdx;
+    int n;
+};
+
+struct GridView {
+    float cell;                         // edge length, >= 2.02 * largest small radius
+    unsigned tableMask;                 // table size - 1 (power of two)
+    unsigned* key; unsigned* keySorted; int* val; int* valSorted;
+    int* cellStart; int* cellEnd;       // per bucket, into the sorted order
+    int4* sortedCell;                   // cx cy cz world
+    float4* sortedPos;                  // pos.xyz, radius
+    const int* largeList; const int* worldLargeStart;
+};
+
+__device__ __forceinline__ unsigned cell_hash(int x, int y, int z, int w) {
+    return ((unsigned)x * 73856093u) ^ ((unsigned)y * 19349663u) ^ ((unsigned)z * 83492791u) ^ ((unsigned)w * 2654435761u);
+}
+__device__ __forceinline__ float body_radius(float4 size) { return len(xyz(size)) * 0.5f; }   // rigid.cpp:28
+__device__ __forceinline__ int3 cell_of(float4 pos, float cell) {
+    return make_int3((int)floorf(pos.x / cell), (int)floorf(pos.y / cell), (int)floorf(pos.z / cell));
+}
+
+// K1a: bucket key per body.  Large bodies (flag) go to the sentinel bucket past the table.
+__global__ void bp_cells(BodyView b, GridView g) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    unsigned k = g.tableMask + 1u;
+    if (!(b.flags[i] & kLarge)) {
+        int3 c = cell_of(b.pose[i].pos, g.cell);
+        k = cell_hash(c.x, c.y, c.z, b.worldId[i]) & g.tableMask;
+    }
+    g.key[i] = k;
+    g.val[i] = i;
+}
+
+// K1b: bucket boundaries in sorted order + sorted copies for the pair sweep.
+__global__ void bp_cell_bounds(BodyView b, GridView g) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= b.n) return;
+    unsigned k = g.keySorted[p];
+    int i = g.valSorted[p];
+    float4 pos = b.pose[i].pos;
+    float r = body_radius(b.size[i]);
+    int3 c = cell_of(pos, g.cell);
+    g.sortedPos[p] = make_float4(pos.x, pos.y, pos.z, r);
+    g.sortedCell[p] = make_int4(c.x, c.y, c.z, b.worldId[i]);
+    if (k > g.tableMask) return;
+    if (p == 0 || g.keySorted[p - 1] != k) g.cellStart[k] = p;
+    if (p == b.n - 1 || g.keySorted[p + 1] != k) g.cellEnd[k] = p + 1;
+}
+
+struct PairSink {
+    unsigned long long* keys; int cap; int keyShift; Counters* cnt;
+};
+
+// Warp-aggregated append: the lanes that reach this call together take one
+// atomic for the group and write a contiguous run.
+__device__ __forceinline__ void emit_pair(const PairSink& s, int a, int b) {
+    cg::coalesced_group grp = cg::coalesced_threads();
+    int base = 0;
+    if (grp.thread_rank() == 0) base = atomicAdd(&s.cnt->nCand, (int)grp.size());
+    base = grp.shfl(base, 0);
+    int idx = base + (int)grp.thread_rank();
+    if (idx < s.cap) s.keys[idx] = ((unsigned long long)(unsigned)a << s.keyShift) | (unsigned long long)(unsigned)b;
+    else atomicOr(&s.cnt->overflow, 1);
+}
+
+// The reference's test, solver.cpp:264-266 (A = higher index).
+__device__ __forceinline__ bool spheres_overlap(float4 pa, float4 pb) {
+    V3 dp = xyz(pa) - xyz(pb);
+    float r = pa.w + pb.w;
+    return dot(dp, dp) <= r * r;
+}
+
+// K1c: small-vs-small through the 27-cell neighbourhood; each pair is emitted
+// by its higher-index member.
+__global__ void bp_pairs_small(BodyView b, GridView g, PairSink sink) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= b.n) return;
+    if (g.keySorted[p] > g.tableMask) return;
+    int i = g.valSorted[p];
+    float4 pi = g.sortedPos[p];
+    int4 ci = g.sortedCell[p];
+    for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                int nx = ci.x + dx, ny = ci.y + dy, nz = ci.z + dz;
+                unsigned hk = cell_hash(nx, ny, nz, ci.w) & g.tableMask;
+                int q0 = g.cellStart[hk], q1 = g.cellEnd[hk];
+                for (int q = q0; q < q1; ++q) {
+                    int4 cq = g.sortedCell[q];
+                    if (cq.x != nx || cq.y != ny || cq.z != nz || cq.w != ci.w) continue;
+                    int j = g.valSorted[q];
+                    if (j >= i) continue;
+                    if (spheres_overlap(pi, g.sortedPos[q])) emit_pair(sink, i, j);
+                }
+            }
+}
+
+// K1d: every body against the large bodies of its own world.
+__global__ void bp_pairs_large(BodyView b, GridView g, PairSink sink) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b.n) return;
+    int w = b.worldId[j];
+    int t0 = g.worldLargeStart[w], t1 = g.worldLargeStart[w + 1];
+    if (t0 == t1) return;
+    bool jLarge = (b.flags[j] & kLarge) != 0;
+    float4 pj = b.pose[j].pos; pj.w = body_radius(b.size[j]);
+    for (int t = t0; t < t1; ++t) {
+        int l = g.largeList[t];
+        if (l == j) continue;
+        if (jLarge && j > l) continue;            // large-large pairs: emitted once, by the lower index
+        float4 pl = b.pose[l].pos; pl.w = body_radius(b.size[l]);
+        int a = j > l ? j : l, c = j > l ? l : j;
+        float4 pa = j > l ? pj : pl, pb = j > l ? pl : pj;
+        if (spheres_overlap(pa, pb)) emit_pair(sink, a, c);
+    }
+}
+
+// K2: manifolds that survived last step persist as candidates whether or not
+// their spheres still overlap (solver.cpp:274-279 only deletes on initialize()==false).
+__global__ void bp_append_persisting(ManifoldSet old, int nOld, PairSink sink) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nOld) return;
+    if (old.hdr[m].z <= 0) return;
+    cg::coalesced_group grp = cg::coalesced_threads();
+    int base = 0;
+    if (grp.thread_rank() == 0) base = atomicAdd(&sink.cnt->nCand, (int)grp.size());
+    base = grp.shfl(base, 0);
+    int idx = base + (int)grp.thread_rank();
+    if (idx < sink.cap) sink.keys[idx] = old.key[m];
+    else atomicOr(&sink.cnt->overflow, 1);
+}
+
+__device__ __forceinline__ int find_key(const unsigned long long* keys, int n, unsigned long long k) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+    return (lo < n && keys[lo] == k) ? lo : -1;
+}
+
+// K3a: SAT cull, one thread per sorted candidate.  info = 0 (dropped) or 1|axis<<1.
+__global__ void np_cull(BodyView b, const unsigned long long* cand, int nCand, int keyShift,
+                        const unsigned long long* excl, int nExcl, int* info, int* flag) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nCand) return;
+    unsigned long long k = cand[p];
+    int code = 0;
+    if (p == 0 || cand[p - 1] != k) {
+        if (nExcl == 0 || find_key(excl, nExcl, k) < 0) {
+            int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
+            BodyPose pa = b.pose[a], pb = b.pose[c];
+            Obb A = make_obb(xyz(pa.pos), quat(pa.rot), xyz(b.size[a]));
+            Obb B = make_obb(xyz(pb.pos), quat(pb.rot), xyz(b.size[c]));
+            code = sat_test(A, B);
+        }
+    }
+    info[p] = code;
+    flag[p] = code ? 1 : 0;
+}
+
+__global__ void np_compact(const int* flag, const int* scan, int nCand, int* survP, Counters* cnt) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nCand) return;
+    if (flag[p]) survP[scan[p]] = p;
+    if (p == nCand - 1) cnt->nSurvive = scan[p] + flag[p];
+}
+
+__device__ __forceinline__ void store_contact(const ManifoldSet& ms, int ci, const ContactState& c) {
+    ms.cA[ci] = f4(c.rA, c.C0n);
+    ms.cB[ci] = f4(c.rB, c.C0t1);
+    ms.cN[ci] = f4(c.n, c.C0t2);
+    ms.cL[ci] = pack_lambda(c);
+    ms.cP[ci] = pack_penalty(c);
+}
+__device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int ci) {
+    return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ms.cL[ci], ms.cP[ci]);
+}
+
+// K3b: build the manifold of each surviving pair at its final (key-sorted)
+// slot, carrying lambda / penalty / stick anchors over from last step's
+// manifold of the same pair, then apply the per-step warm-start decay.
+__global__ void np_build(BodyView b, const unsigned long long* cand, const int* info, const int* survP, int nSurvive,
+                         int keyShift, ManifoldSet old, int nOld, ManifoldSet out, SolveParams prm) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nSurvive) return;
+    int p = survP[s];
+    unsigned long long k = cand[p];
+    int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
+    BodyPose pa = b.pose[a], pb = b.pose[c];
+    float4 sa = b.size[a], sb = b.size[c];
+    OldManifold om; om.n = 0;
+    int slot = find_key(old.key, nOld, k);
+    if (slot >= 0) {
+        om.n = old.hdr[slot].z;
+        for (int i = 0; i < om.n; ++i) om.ct[i] = load_contact(old, slot * 4 + i);
+    }
+    NewManifold nm;
+    manifold_initialize(xyz(pa.pos), quat(pa.rot), xyz(sa), xyz(pb.pos), quat(pb.rot), xyz(sb), info[p], om, prm, nm);
+    float mu = sqrtf(sa.w * sb.w);                                   // manifold.cpp:73
+    out.key[s] = k;
+    out.hdr[s] = make_int4(a, c, nm.n, __float_as_int(mu));
+    for (int i = 0; i < 4; ++i) {
+        if (i < nm.n) store_contact(out, s * 4 + i, nm.ct[i]);
+        else {
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            out.cA[s * 4 + i] = z; out.cB[s * 4 + i] = z; out.cN[s * 4 + i] = z; out.cL[s * 4 + i] = z; out.cP[s * 4 + i] = z;
+        }
+    }
+}
+
+// Stand-alone narrowphase on caller-supplied pairs (parity harness for
+// Manifold::collide, collision.cpp:420).  in: 2 x {size3 pos3 quat4} per pair.
+__global__ void np_collide_batch(const float* a10, const float* b10, int n, int* count, int* feats4, float* out36) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = a10 + 10 * i; const float* c = b10 + 10 * i;
+    V3 sa = mk3(a[0], a[1], a[2]), pa = mk3(a[3], a[4], a[5]); Q4 qa = qmk(a[6], a[7], a[8], a[9]);
+    V3 sb = mk3(c[0], c[1], c[2]), pb = mk3(c[3], c[4], c[5]); Q4 qb = qmk(c[6], c[7], c[8], c[9]);
+    int code = sat_test(make_obb(pa, qa, sa), make_obb(pb, qb, sb));
+    RawContact rc[4];
+    int k = code ? build_contacts(pa, qa, sa, pb, qb, sb, code, rc) : 0;
+    count[i] = k;
+    for (int j = 0; j < 4; ++j) {
+        feats4[4 * i + j] = j < k ? rc[j].feature : 0;
+        float* o = out36 + 36 * i + 9 * j;
+        if (j < k) { o[0] = rc[j].rA.x; o[1] = rc[j].rA.y; o[2] = rc[j].rA.z; o[3] = rc[j].rB.x; o[4] = rc[j].rB.y; o[5] = rc[j].rB.z;
+                     o[6] = rc[j].normal.x; o[7] = rc[j].normal.y; o[8] = rc[j].normal.z; }
+        else for (int t = 0; t < 9; ++t) o[t] = 0.0f;
+    }
+}
+
+} // namespace avbd

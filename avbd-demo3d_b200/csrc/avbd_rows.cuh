@@ -1,0 +1,218 @@
+// avbd_rows.cuh — per-contact row math shared by the primal, dual, warm-start
+// and diagnostics kernels.  One "contact" = 3 rows (normal, tangent1, tangent2)
+// of the reference's Manifold force (solver.h:112-143).
+#pragma once
+#include "avbd_collide.cuh"
+#include "avbd_world.cuh"
+
+namespace avbd {
+
+struct ContactState {     // registers-resident view of one contact slot
+    V3 rA, rB, n;
+    float C0n, C0t1, C0t2;
+    float lam[3], pen[3];
+    bool stick;
+    int feature;
+};
+
+AVBD_HD ContactState unpack_contact(float4 a, float4 b, float4 n, float4 l, float4 p) {
+    ContactState c;
+    c.rA = xyz(a); c.C0n = a.w;
+    c.rB = xyz(b); c.C0t1 = b.w;
+    c.n = xyz(n);  c.C0t2 = n.w;
+    c.lam[0] = l.x; c.lam[1] = l.y; c.lam[2] = l.z; c.stick = l.w != 0.0f;
+    c.pen[0] = p.x; c.pen[1] = p.y; c.pen[2] = p.z; c.feature = f2i(p.w);
+    return c;
+}
+AVBD_HD float4 pack_lambda(const ContactState& c) { return make_float4(c.lam[0], c.lam[1], c.lam[2], c.stick ? 1.0f : 0.0f); }
+AVBD_HD float4 pack_penalty(const ContactState& c) { return make_float4(c.pen[0], c.pen[1], c.pen[2], i2f(c.feature)); }
+
+struct ContactEval {      // transient outputs of computeConstraint for one contact
+    float C[3], fmin[3], fmax[3];
+    V3 basis[3];          // normal, tangent1, tangent2
+    V3 wrA, wrB;          // rotate(rot, r): world lever arms
+};
+
+// Manifold::computeConstraint for ONE contact (manifold.cpp:177-245).  Stateful
+// exactly like the reference: clamps the warm tangential lambda into the
+// current cone and re-evaluates `stick` — the caller writes c.lam / c.stick back.
+AVBD_HD void contact_constraint(V3 posA, Q4 rotA, float invMassA, V3 posB, Q4 rotB, float invMassB,
+                                float mu0, float alpha, ContactState& c, ContactEval& e) {
+    float bias = clampf(1.0f - alpha, 0.0f, 1.0f);
+    contact_basis(c.n, e.basis[0], e.basis[1], e.basis[2]);
+    e.wrA = qrot(rotA, c.rA);
+    e.wrB = qrot(rotB, c.rB);
+    V3 dlt = (posA + e.wrA) - (posB + e.wrB);
+    float sepn = dot(dlt, e.basis[0]) - kNormalContactMargin;
+    float s1 = dot(dlt, e.basis[1]), s2 = dot(dlt, e.basis[2]);
+    e.C[0] = sepn + bias * c.C0n;
+    float ims = invMassA + invMassB;
+    float mscale = (ims > 1.0e-6f) ? (1.0f / ims) : 1.0f;
+    float cap = kNormalForceCap * mscale;
+    e.fmin[0] = -cap; e.fmax[0] = 0.0f;
+    e.C[1] = s1 + bias * c.C0t1;
+    e.C[2] = s2 + bias * c.C0t2;
+    float warmN = fabsf(fmin2(c.lam[0], 0.0f));
+    float trial = c.pen[0] * e.C[0] + c.lam[0];
+    float trialN = fabsf(fmin2(trial, 0.0f));
+    float nmag = fmin2(fmax2(warmN, trialN), cap);
+    float mu = mu0;
+    if (!c.stick) mu *= kKineticFrictionScale;
+    float lim = mu * nmag;
+    float l1 = c.lam[1], l2 = c.lam[2];
+    float tm = sqrtf(l1 * l1 + l2 * l2);
+    if (tm > lim && tm > 1.0e-8f) { float s = lim / tm; c.lam[1] *= s; c.lam[2] *= s; }
+    e.fmin[1] = -lim; e.fmax[1] = lim; e.fmin[2] = -lim; e.fmax[2] = lim;
+    float slip2 = e.C[1] * e.C[1] + e.C[2] * e.C[2];
+    float tl2 = c.lam[1] * c.lam[1] + c.lam[2] * c.lam[2];
+    c.stick = (slip2 <= kStickThresh * kStickThresh) && (tl2 <= lim * lim + 1.0e-8f);
+}
+
+// 6x6 block system of one body, stored as the 27 numbers the Schur solve reads:
+// rhs (6), ll lower triangle (6), la full (9, al == la^T bit for bit), aa lower (6).
+struct BodySystem {
+    float rl[3], ra[3];
+    float ll[6];          // (0,0) (1,0) (2,0) (1,1) (2,1) (2,2)
+    float la[9];          // la[r*3+c] = element (r,c)
+    float aa[6];
+    AVBD_HD void clear() {
+        for (int i = 0; i < 3; ++i) { rl[i] = 0.0f; ra[i] = 0.0f; }
+        for (int i = 0; i < 6; ++i) { ll[i] = 0.0f; aa[i] = 0.0f; }
+        for (int i = 0; i < 9; ++i) la[i] = 0.0f;
+    }
+};
+
+// Adds one row (solver.cpp:374-399).  `gyro` enables the manifold-only
+// diagonal term diag(|Ja x I^-1 Ja| * |f|) (solver.cpp:393-397).
+AVBD_HD void accumulate_row(BodySystem& s, V3 Jl, V3 Ja, float f, float pen, bool gyro, const M3& invIw) {
+    s.rl[0] += Jl.x * f; s.rl[1] += Jl.y * f; s.rl[2] += Jl.z * f;
+    s.ra[0] += Ja.x * f; s.ra[1] += Ja.y * f; s.ra[2] += Ja.z * f;
+    if (pen > 0.0f && finite1(pen)) {
+        float jl[3] = {Jl.x, Jl.y, Jl.z}, ja[3] = {Ja.x, Ja.y, Ja.z};
+        s.ll[0] += (jl[0] * jl[0]) * pen; s.ll[1] += (jl[1] * jl[0]) * pen; s.ll[2] += (jl[2] * jl[0]) * pen;
+        s.ll[3] += (jl[1] * jl[1]) * pen; s.ll[4] += (jl[2] * jl[1]) * pen; s.ll[5] += (jl[2] * jl[2]) * pen;
+        s.aa[0] += (ja[0] * ja[0]) * pen; s.aa[1] += (ja[1] * ja[0]) * pen; s.aa[2] += (ja[2] * ja[0]) * pen;
+        s.aa[3] += (ja[1] * ja[1]) * pen; s.aa[4] += (ja[2] * ja[1]) * pen; s.aa[5] += (ja[2] * ja[2]) * pen;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s.la[r * 3 + c] += (jl[r] * ja[c]) * pen;
+        if (gyro) {
+            V3 g = vabs(cross(Ja, mv(invIw, Ja))) * fabsf(f);
+            s.aa[0] += g.x; s.aa[3] += g.y; s.aa[5] += g.z;
+        }
+    }
+}
+
+// Primal contribution of one contact as seen from body side `isA`
+// (solver.cpp:371-399 with Manifold::computeDerivatives, manifold.cpp:247-271).
+AVBD_HD void accumulate_contact(BodySystem& s, const ContactState& c, const ContactEval& e, bool isA, const M3& invIw) {
+    float sg = isA ? 1.0f : -1.0f;
+    V3 wr = isA ? e.wrA : e.wrB;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        V3 Jl = e.basis[r] * sg;
+        V3 Ja = cross(wr, e.basis[r]) * sg;
+        float f = clampf(c.pen[r] * e.C[r] + c.lam[r], e.fmin[r], e.fmax[r]);
+        accumulate_row(s, Jl, Ja, f, c.pen[r], true, invIw);
+    }
+}
+
+// solver.cpp:68-83 on the packed system.
+AVBD_HD void solve_body_system(const BodySystem& s, V3& dl, V3& da) {
+    M3 ll = m3(mk3(s.ll[0], s.ll[1], s.ll[2]), mk3(s.ll[1], s.ll[3], s.ll[4]), mk3(s.ll[2], s.ll[4], s.ll[5]));
+    M3 aa = m3(mk3(s.aa[0], s.aa[1], s.aa[2]), mk3(s.aa[1], s.aa[3], s.aa[4]), mk3(s.aa[2], s.aa[4], s.aa[5]));
+    // la columns: column c = (la(0,c), la(1,c), la(2,c)); al = la^T so al column c = row c of la
+    M3 la = m3(mk3(s.la[0], s.la[3], s.la[6]), mk3(s.la[1], s.la[4], s.la[7]), mk3(s.la[2], s.la[5], s.la[8]));
+    M3 al = m3(mk3(s.la[0], s.la[1], s.la[2]), mk3(s.la[3], s.la[4], s.la[5]), mk3(s.la[6], s.la[7], s.la[8]));
+    V3 bl = mk3(s.rl[0], s.rl[1], s.rl[2]), ba = mk3(s.ra[0], s.ra[1], s.ra[2]);
+    M3 W = m3(ldl3(ll, la.c[0]), ldl3(ll, la.c[1]), ldl3(ll, la.c[2]));
+    V3 x0 = ldl3(ll, bl);
+    M3 S;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        V3 prod = mv(al, W.c[j]);
+        S.c[j] = aa.c[j] - prod;
+    }
+    V3 rs = ba - mv(al, x0);
+    da = ldl3(S, rs);
+    dl = x0 - mv(W, da);
+}
+
+// Dual + penalty ramp for one contact (solver.cpp:411-430, rowPenaltyGain :94-125).
+AVBD_HD void dual_contact(ContactState& c, const ContactEval& e, float beta) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float lu = clampf(c.pen[r] * e.C[r] + c.lam[r], e.fmin[r], e.fmax[r]);
+        bool active = lu > e.fmin[r] && lu < e.fmax[r];
+        c.lam[r] = lu;
+        if (active) {
+            V3 b = e.basis[r];
+            float lw = 0.0f, aw = 0.0f;
+            lw += len2(b * 1.0f);  aw += len2(cross(e.wrA, b) * 1.0f);
+            lw += len2(b * -1.0f); aw += len2(cross(e.wrB, b) * -1.0f);
+            float tot = lw + aw;
+            float br = beta;
+            if (!(tot < 1.0e-8f)) br = (beta * lw + (beta * kAngularBetaScale) * aw) / tot;
+            c.pen[r] = fmin2(c.pen[r] + br * fabsf(e.C[r]), kManifoldPenaltyCap);
+        }
+    }
+}
+
+struct OldManifold {      // last step's contacts of the same pair, for feature-id carry-over
+    int n;
+    ContactState ct[4];
+};
+
+struct NewManifold {
+    int n;
+    ContactState ct[4];
+};
+
+// Manifold::initialize (manifold.cpp:71-175) followed by the per-row warm-start
+// decay of Solver::step (solver.cpp:281-293; manifold rows are hard so the
+// stiffness cap at :290-292 never applies).
+AVBD_HD void manifold_initialize(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 sizeB, int satCode,
+                                 const OldManifold& old, const SolveParams& prm, NewManifold& out) {
+    RawContact raw[4];
+    out.n = build_contacts(posA, rotA, sizeA, posB, rotB, sizeB, satCode, raw);
+    bool used[4] = {false, false, false, false};
+    for (int i = 0; i < out.n; ++i) {
+        ContactState& c = out.ct[i];
+        c.feature = raw[i].feature; c.rA = raw[i].rA; c.rB = raw[i].rB; c.n = raw[i].normal;
+        for (int k = 0; k < 3; ++k) { c.lam[k] = 0.0f; c.pen[k] = kPenaltyMin; }
+        c.stick = false;
+        int hit = -1;
+        for (int j = 0; j < old.n; ++j) { if (used[j]) continue; if (c.feature == old.ct[j].feature) { hit = j; break; } }
+        if (hit >= 0) {
+            used[hit] = true;
+            const ContactState& o = old.ct[hit];
+            V3 nn = unit_or(c.n, mk3(0.0f, 1.0f, 0.0f));
+            V3 on = unit_or(o.n, nn);
+            float nd = dot(nn, on);
+            V3 oldMid = ((posA + qrot(rotA, o.rA)) + (posB + qrot(rotB, o.rB))) * 0.5f;
+            V3 newMid = ((posA + qrot(rotA, c.rA)) + (posB + qrot(rotB, c.rB))) * 0.5f;
+            float drift2 = len2(newMid - oldMid);
+            bool warm = (nd >= kWarmNormalMinDot) && (drift2 <= kWarmMaxDrift * kWarmMaxDrift);
+            if (warm) for (int k = 0; k < 3; ++k) { c.lam[k] = o.lam[k]; c.pen[k] = clampf(o.pen[k], kPenaltyMin, kManifoldPenaltyCap); }
+            bool reuse = false;
+            if (o.stick && warm) reuse = (nd >= kStickNormalMinDot) && (drift2 <= kStickAnchorMaxDrift * kStickAnchorMaxDrift);
+            c.stick = o.stick && reuse;
+            if (reuse) { c.rA = o.rA; c.rB = o.rB; }
+        }
+        V3 n, t1, t2;
+        contact_basis(c.n, n, t1, t2);
+        c.n = n;
+        V3 dlt = (posA + qrot(rotA, c.rA)) - (posB + qrot(rotB, c.rB));
+        c.C0n = dot(dlt, n) - kNormalContactMargin;
+        c.C0t1 = dot(dlt, t1);
+        c.C0t2 = dot(dlt, t2);
+        // warm-start decay, solver.cpp:281-288
+        for (int k = 0; k < 3; ++k) {
+            if (!prm.postStabilize) c.lam[k] *= prm.alpha * prm.gamma;
+            c.pen[k] = clampf(c.pen[k] * prm.gamma, kPenaltyMin, kPenaltyMax);
+        }
+    }
+}
+
+} // namespace avbd

@@ -1,0 +1,75 @@
+// avbd_world.cuh — device-resident layout of one AVBD world (or a batch of
+// independent worlds packed back to back) and the launch-time view of it.
+//
+// Bodies (replaces the reference's 264-byte Rigid list nodes, solver.h:48-82):
+//   pose[i]  {pos.xyz,radius | rot}            32 B, one sector: the only thing a NEIGHBOUR reads
+//   aux[i]   {posI | rotI | mass,invMass,friction,- | Ixx,Iyy,Izz,-}   64 B, read by the body's own solve
+//   vel[i]   {lin | ang}, init[i] {pos0 | rot0}, prevLin[i], size[i] {sx,sy,sz,friction}
+// Manifolds (replaces 704-byte Manifold nodes, solver.h:112-143), slot m, sorted by pair key:
+//   mhdr[m]  {bodyA, bodyB, numContacts, friction-bits}     16 B
+//   contact arrays indexed ci = 4*m + c, one float4 per field so the 4 contacts of
+//   a manifold are one 64-byte run per field:
+//     cA {rA.xyz, C0_n}  cB {rB.xyz, C0_t.x}  cN {normal.xyz, C0_t.y}
+//     cL {lambda_n, lambda_t1, lambda_t2, stick}   cP {penalty_n, penalty_t1, penalty_t2, feature-bits}
+//   C / fmin / fmax (solver.h:91-92) are recomputed in registers by every
+//   consumer and never stored.
+#pragma once
+#include "avbd_math.cuh"
+
+namespace avbd {
+
+struct BodyPose { float4 pos; float4 rot; };
+struct BodyAux  { float4 posI; float4 rotI; float4 mass; float4 inert; };
+struct BodyVel  { float4 lin; float4 ang; };
+struct BodyInit { float4 pos0; float4 rot0; };
+
+enum BodyFlag : int { kDynamic = 1, kLarge = 2 };
+
+struct SolveParams {          // Solver fields, solver.h:147-151, re-read every step
+    float dt;
+    float gx, gy, gz;
+    int   iterations;
+    float alpha, beta, gamma;
+    int   postStabilize;
+};
+
+struct ManifoldSet {          // one of the two ping-pong generations
+    unsigned long long* key;  // packed pair key (A << keyShift) | B, ascending
+    int4*   hdr;
+    float4* cA; float4* cB; float4* cN; float4* cL; float4* cP;
+};
+
+// Joint (6 rows, joint.cpp) / Spring (1 row, spring.cpp) records.  Unlike
+// manifolds these are created by the user and persist, so they stay AoS.
+struct JointRec {
+    int a, b;                 // a == -1: world anchor
+    float4 rA, rB;            // local anchors (rA = world anchor when a < 0)
+    float4 rel0;              // initial relative orientation
+    float lambda[6], penalty[6];
+    float kLin, kAng;         // stiffness per row group (FLT_MAX = hard)
+};
+struct SpringRec {
+    int a, b;
+    float4 rA, rB;
+    float rest, k;
+    float lambda, penalty;
+};
+
+struct Diag {                 // Solver::Diagnostics, solver.h:155-164 (+ sanitiser events)
+    float maxPenetration, maxViolation, maxLinearSpeed, maxAngularSpeed, maxNormalImpulse;
+    int activeContacts, activeManifolds, dynamicBodies;
+    int nanEvents;            // bodies scrubbed by the NaN guards (solver.cpp:51-66)
+    int pad[3];
+};
+
+struct Counters {             // device-side sizes produced by one stage, consumed by the next
+    int nPairs;               // sphere-overlap pairs emitted this step (before merge with persisting manifolds)
+    int nCand;                // pairs + persisting manifold keys (sort input)
+    int nSurvive;             // candidates that passed the SAT cull == manifolds this step
+    int nUncoloured;
+    int nColours;
+    int overflow;             // bit0 pairs, bit1 manifolds, bit2 colours
+    int pad[2];
+};
+
+} // namespace avbd
