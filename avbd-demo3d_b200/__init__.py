@@ -32,7 +32,18 @@ class StepStats(C.Structure):
     _fields_ = [("ms_broadphase", C.c_float), ("ms_narrowphase", C.c_float), ("ms_graph", C.c_float), ("ms_predict", C.c_float),
                 ("ms_primal", C.c_float), ("ms_dual", C.c_float), ("ms_velocity", C.c_float), ("ms_total", C.c_float),
                 ("bodies", C.c_int), ("dynamicBodies", C.c_int), ("pairs", C.c_int), ("candidates", C.c_int), ("manifolds", C.c_int),
-                ("contacts", C.c_int), ("colours", C.c_int), ("iterations", C.c_int), ("kernelLaunches", C.c_longlong)]
+                ("contacts", C.c_int), ("colours", C.c_int), ("iterations", C.c_int), ("contactVisits", C.c_int),
+                ("kernelLaunches", C.c_longlong)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Profile(C.Structure):
+    _fields_ = [("ms_primal", C.c_double), ("ms_dual", C.c_double), ("steps", C.c_longlong), ("primal_sweeps", C.c_longlong),
+                ("primal_launches", C.c_longlong), ("primal_bodies", C.c_longlong), ("primal_visits", C.c_longlong),
+                ("dual_launches", C.c_longlong), ("dual_contacts", C.c_longlong), ("kernel_launches", C.c_longlong),
+                ("library_launches", C.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -54,6 +65,9 @@ ABI = {
     "avbd_add_ignore": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "avbd_step": (C.c_int, [C.c_void_p, C.c_int]),
     "avbd_sync": (C.c_int, [C.c_void_p]),
+    "avbd_step_timed": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "avbd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "avbd_get_profile": (C.c_int, [C.c_void_p, C.POINTER(Profile)]),
     "avbd_download_state": (C.c_int, [C.c_void_p, _f32p]),
     "avbd_upload_state": (C.c_int, [C.c_void_p, _f32p]),
     "avbd_download_prev_linvel": (C.c_int, [C.c_void_p, _f32p]),
@@ -190,6 +204,24 @@ class World:
     def sync(self):
         _check(self.L.avbd_sync(self.h))
 
+    def step_timed(self, n):
+        """n steps; returns their device time in ms (CUDA events on the world's stream)."""
+        ms = C.c_float(0)
+        _check(self.L.avbd_step_timed(self.h, n, C.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, on=True):
+        _check(self.L.avbd_set_profiling(self.h, int(on)))
+
+    def profile(self):
+        p = Profile()
+        _check(self.L.avbd_get_profile(self.h, C.byref(p)))
+        return p.as_dict()
+
+    def download_state_into(self, out):
+        """Download into a caller-owned float32 [n,13] array (pin it for a single async DMA)."""
+        _check(self.L.avbd_download_state(self.h, out))
+
     @property
     def n(self):
         return self.L.avbd_num_bodies(self.h)
@@ -236,9 +268,8 @@ class World:
     def manifolds_raw(self):
         m = self.L.avbd_num_manifolds(self.h)
         ints, feats, stick, flts = (np.zeros((m, 3), np.int32), np.zeros((m, 4), np.int32), np.zeros((m, 4), np.int32), np.zeros((m, 81), np.float32))
-        if m:
-            _check(self.L.avbd_download_manifolds(self.h, ints, feats, stick, flts))
-        return ints, feats, stick, flts
+        live = _check(self.L.avbd_download_manifolds(self.h, ints, feats, stick, flts)) if m else 0
+        return ints[:live], feats[:live], stick[:live], flts[:live]
 
     # -- stages
     def stage_broadphase(self):

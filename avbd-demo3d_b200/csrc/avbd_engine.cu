@@ -65,7 +65,8 @@ struct avbd_world {
     int device = 0;
     cudaStream_t stream = nullptr;
     SolveParams prm{};
-    long long launches = 0;
+    long long launches = 0;      // this library's own kernels
+    long long libLaunches = 0;   // CUB sort / scan passes (library code, counted apart)
 
     // bodies
     int n = 0, nDyn = 0, nWorlds = 1;
@@ -103,6 +104,12 @@ struct avbd_world {
     DevBuf<Diag> dDiag; Diag* hDiag = nullptr; size_t hDiagCap = 0;
     DevBuf<float> dx;
     DevBuf<char> temp;
+
+    // per-kernel profiling (avbd_set_profiling): events around every primal sweep and dual pass
+    bool profiling = false;
+    std::vector<cudaEvent_t> pev;
+    avbd_profile prof{};
+    DevBuf<float> stateDev;
 
     // timing
     cudaEvent_t ev[9] = {};
@@ -155,7 +162,7 @@ int sort_pairs(avbd_world* w, const K* kin, K* kout, const V* vin, V* vout, int 
     CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, bits, w->stream));
     TRY(w->temp.ensure(bytes, false, w->stream));
     CK(cub::DeviceRadixSort::SortPairs(w->temp.p, bytes, kin, kout, vin, vout, n, 0, bits, w->stream));
-    w->launches += 1 + (bits + 7) / 8 * 2;
+    w->libLaunches += 1 + (bits + 7) / 8 * 2;
     return 0;
 }
 template <class K>
@@ -165,7 +172,7 @@ int sort_keys(avbd_world* w, const K* kin, K* kout, int n, int bits) {
     CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, kin, kout, n, 0, bits, w->stream));
     TRY(w->temp.ensure(bytes, false, w->stream));
     CK(cub::DeviceRadixSort::SortKeys(w->temp.p, bytes, kin, kout, n, 0, bits, w->stream));
-    w->launches += 1 + (bits + 7) / 8 * 2;
+    w->libLaunches += 1 + (bits + 7) / 8 * 2;
     return 0;
 }
 int exclusive_scan(avbd_world* w, const int* in, int* out, int n) {
@@ -174,7 +181,7 @@ int exclusive_scan(avbd_world* w, const int* in, int* out, int n) {
     CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, w->stream));
     TRY(w->temp.ensure(bytes, false, w->stream));
     CK(cub::DeviceScan::ExclusiveSum(w->temp.p, bytes, in, out, n, w->stream));
-    w->launches += 2;
+    w->libLaunches += 2;
     return 0;
 }
 
@@ -427,7 +434,7 @@ int run_primal(avbd_world* w, float alpha, float* dxDev) {
     for (int c = 0; c < w->nColours; ++c) {
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
-        primal_colour<kLanesPerBody><<<blocks_for((long long)count * kLanesPerBody), kThreads, 0, s>>>(
+        primal_colour<kLanesPerBody><<<blocks_for(count, kThreads / kLanesPerBody), kThreads, 0, s>>>(
             w->bview(), w->adjRange.p, w->bList.p, ms, fv, w->colOrder.p + first, count, w->prm, alpha, dxDev, w->dDiag.p);
         w->launches++;
     }
@@ -472,14 +479,37 @@ int step_once(avbd_world* w) {
     TRY(run_colour(w));
     if (w->timed) cudaEventRecord(w->ev[4], s);
     int total = w->prm.iterations + (w->prm.postStabilize ? 1 : 0);
+    bool prof = w->profiling;
+    if (prof) {
+        while ((int)w->pev.size() < 2 * total + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); w->pev.push_back(e); }
+        cudaEventRecord(w->pev[0], s);
+    }
+    int duals = 0;
     for (int it = 0; it < total; ++it) {
         float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
         TRY(run_primal(w, a, nullptr));
-        if (it < w->prm.iterations) TRY(run_dual(w, a));
+        if (prof) cudaEventRecord(w->pev[2 * it + 1], s);
+        if (it < w->prm.iterations) { TRY(run_dual(w, a)); ++duals; }
+        if (prof) cudaEventRecord(w->pev[2 * it + 2], s);
     }
     if (w->timed) cudaEventRecord(w->ev[5], s);
     TRY(run_velocity(w));
     if (w->timed) cudaEventRecord(w->ev[6], s);
+    if (prof) {
+        CK(cudaStreamSynchronize(s));
+        for (int it = 0; it < total; ++it) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, w->pev[2 * it], w->pev[2 * it + 1]);
+            cudaEventElapsedTime(&b, w->pev[2 * it + 1], w->pev[2 * it + 2]);
+            w->prof.ms_primal += a; w->prof.ms_dual += b;
+        }
+        long long contacts = 0, visits = 0;
+        for (int k = 0; k < w->nWorlds && w->hDiag; ++k) { contacts += w->hDiag[k].activeContacts; visits += w->hDiag[k].contactVisits; }
+        w->prof.steps += 1;
+        w->prof.primal_sweeps += total; w->prof.primal_launches += (long long)total * w->nColours;
+        w->prof.primal_bodies += (long long)total * w->nDyn; w->prof.primal_visits += (long long)total * visits;
+        w->prof.dual_launches += duals; w->prof.dual_contacts += (long long)duals * contacts;
+    }
     return 0;
 }
 
@@ -540,7 +570,8 @@ void avbd_world_destroy(avbd_world* w) {
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
-    w->dDiag.release(); w->dx.release(); w->temp.release();
+    w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release();
+    for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
     if (w->hCnt) cudaFreeHost(w->hCnt);
     if (w->hDiag) cudaFreeHost(w->hDiag);
@@ -696,6 +727,34 @@ int avbd_step(avbd_world* w, int nSteps) {
     return 0;
 }
 
+int avbd_step_timed(avbd_world* w, int nSteps, float* ms) {
+    if (!w || !ms) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->stream));
+    CK(cudaEventRecord(w->ev[7], w->stream));
+    for (int i = 0; i < nSteps; ++i) TRY(step_once(w));
+    CK(cudaEventRecord(w->ev[8], w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    CK(cudaEventElapsedTime(ms, w->ev[7], w->ev[8]));
+    return 0;
+}
+
+int avbd_set_profiling(avbd_world* w, int on) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    w->profiling = on != 0;
+    w->prof = avbd_profile{};
+    return 0;
+}
+
+int avbd_get_profile(avbd_world* w, avbd_profile* out) {
+    if (!w || !out) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->stream));
+    *out = w->prof;
+    out->kernel_launches = w->launches; out->library_launches = w->libLaunches;
+    return 0;
+}
+
 int avbd_sync(avbd_world* w) {
     if (!w) return fail(AVBD_ERR_ARG, "null world");
     CK(cudaSetDevice(w->device));
@@ -707,17 +766,11 @@ int avbd_download_state(avbd_world* w, float* out) {
     if (!w || (!out && w->n)) return fail(AVBD_ERR_ARG, "null argument");
     CK(cudaSetDevice(w->device));
     int n = w->n; if (!n) return 0;
-    std::vector<BodyPose> pose(n); std::vector<BodyVel> vel(n);
-    CK(cudaMemcpyAsync(pose.data(), w->pose.p, n * sizeof(BodyPose), cudaMemcpyDeviceToHost, w->stream));
-    CK(cudaMemcpyAsync(vel.data(), w->vel.p, n * sizeof(BodyVel), cudaMemcpyDeviceToHost, w->stream));
+    TRY(w->stateDev.ensure((size_t)n * 13, false, w->stream));
+    pack_state<<<blocks_for(n), kThreads, 0, w->stream>>>(w->bview(), w->stateDev.p);
+    w->launches++;
+    CK(cudaMemcpyAsync(out, w->stateDev.p, (size_t)n * 13 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
-    for (int i = 0; i < n; ++i) {
-        float* o = out + 13 * (size_t)i;
-        o[0] = pose[i].pos.x; o[1] = pose[i].pos.y; o[2] = pose[i].pos.z;
-        o[3] = pose[i].rot.x; o[4] = pose[i].rot.y; o[5] = pose[i].rot.z; o[6] = pose[i].rot.w;
-        o[7] = vel[i].lin.x; o[8] = vel[i].lin.y; o[9] = vel[i].lin.z;
-        o[10] = vel[i].ang.x; o[11] = vel[i].ang.y; o[12] = vel[i].ang.z;
-    }
     return 0;
 }
 
@@ -725,15 +778,10 @@ int avbd_upload_state(avbd_world* w, const float* in) {
     if (!w || (!in && w->n)) return fail(AVBD_ERR_ARG, "null argument");
     CK(cudaSetDevice(w->device));
     int n = w->n; if (!n) return 0;
-    std::vector<BodyPose> pose(n); std::vector<BodyVel> vel(n);
-    for (int i = 0; i < n; ++i) {
-        const float* o = in + 13 * (size_t)i;
-        pose[i].pos = make_float4(o[0], o[1], o[2], w->hb[i].invMass);
-        pose[i].rot = make_float4(o[3], o[4], o[5], o[6]);
-        vel[i].lin = make_float4(o[7], o[8], o[9], 0.f); vel[i].ang = make_float4(o[10], o[11], o[12], 0.f);
-    }
-    CK(cudaMemcpyAsync(w->pose.p, pose.data(), n * sizeof(BodyPose), cudaMemcpyHostToDevice, w->stream));
-    CK(cudaMemcpyAsync(w->vel.p, vel.data(), n * sizeof(BodyVel), cudaMemcpyHostToDevice, w->stream));
+    TRY(w->stateDev.ensure((size_t)n * 13, false, w->stream));
+    CK(cudaMemcpyAsync(w->stateDev.p, in, (size_t)n * 13 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
+    unpack_state<<<blocks_for(n), kThreads, 0, w->stream>>>(w->bview(), w->stateDev.p);
+    w->launches++;
     CK(cudaStreamSynchronize(w->stream));
     return 0;
 }
@@ -827,6 +875,7 @@ int avbd_get_step_stats(avbd_world* w, avbd_step_stats* out) {
     st.bodies = w->n; st.dynamicBodies = w->nDyn; st.pairs = w->nPairs; st.candidates = w->nCand; st.manifolds = w->nM;
     avbd_diagnostics d; avbd_get_diagnostics(w, &d); st.contacts = d.activeContacts;
     st.colours = w->nColours; st.iterations = w->prm.iterations; st.kernelLaunches = w->launches;
+    { long long v = 0; for (int k = 0; k < w->nWorlds && w->hDiag; ++k) v += w->hDiag[k].contactVisits; st.contactVisits = (int)v; }
     *out = st;
     return 0;
 }
@@ -847,28 +896,31 @@ int avbd_download_manifolds(avbd_world* w, int* ints, int* feats, int* stick, fl
     CK(cudaMemcpyAsync(cL.data(), ms.cL, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(cP.data(), ms.cP, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    int live = 0;
     for (int m = 0; m < nM; ++m) {
         int nc = hdr[m].z;
-        ints[3 * m] = hdr[m].x; ints[3 * m + 1] = hdr[m].y; ints[3 * m + 2] = nc;
-        float* f = flts + 81 * (size_t)m;
+        if (nc <= 0) continue;              // SAT passed but no contact survived: the reference deletes these (solver.cpp:274-279)
+        ints[3 * live] = hdr[m].x; ints[3 * live + 1] = hdr[m].y; ints[3 * live + 2] = nc;
+        float* f = flts + 81 * (size_t)live;
         float mu; std::memcpy(&mu, &hdr[m].w, 4);
         f[0] = mu;
         for (int c = 0; c < 4; ++c) {
-            int ci = 4 * m + c; bool live = c < nc;
+            int ci = 4 * m + c; bool on = c < nc;
             int feat; std::memcpy(&feat, &cP[ci].w, 4);
-            feats[ci] = live ? feat : 0;
-            stick[ci] = live ? (cL[ci].w != 0.0f ? 1 : 0) : 0;
+            feats[4 * live + c] = on ? feat : 0;
+            stick[4 * live + c] = on ? (cL[ci].w != 0.0f ? 1 : 0) : 0;
             float* o = f + 1 + 14 * c;
             const float v[14] = {cA[ci].x, cA[ci].y, cA[ci].z, cB[ci].x, cB[ci].y, cB[ci].z, cN[ci].x, cN[ci].y, cN[ci].z,
                                  0.0f /* penetration is draw-only state, not kept on the device */, cA[ci].w, cB[ci].w, cN[ci].w, 0.0f};
-            for (int k = 0; k < 14; ++k) o[k] = live ? v[k] : 0.0f;
+            for (int k = 0; k < 14; ++k) o[k] = on ? v[k] : 0.0f;
             for (int k = 0; k < 3; ++k) {
-                f[57 + 3 * c + k] = live ? (&cL[ci].x)[k] : 0.0f;
-                f[69 + 3 * c + k] = live ? (&cP[ci].x)[k] : 0.0f;
+                f[57 + 3 * c + k] = on ? (&cL[ci].x)[k] : 0.0f;
+                f[69 + 3 * c + k] = on ? (&cP[ci].x)[k] : 0.0f;
             }
         }
+        ++live;
     }
-    return 0;
+    return live;
 }
 
 int avbd_stage_broadphase(avbd_world* w) {

@@ -111,23 +111,38 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
 }
 
 // ------------------------------------------------------------------ predict / warm-start decay of user forces
+// Diagnostics are kept per world (an ensemble batch reports each world separately).  Lanes of a warp that
+// belong to the same world combine first (match_any + masked reduce), then one atomic per (warp, world).
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));       // non-negative floats order like their bit patterns
+}
+struct WorldGroup {
+    unsigned peers; bool leader;
+    __device__ __forceinline__ WorldGroup(int world) {
+        peers = __match_any_sync(0xffffffffu, world);
+        leader = (__ffs(peers) - 1) == (int)(threadIdx.x & 31);
+    }
+    __device__ __forceinline__ float max_nonneg(float v) const { return __uint_as_float(__reduce_max_sync(peers, __float_as_uint(v))); }
+    __device__ __forceinline__ int sum(int v) const { return __reduce_add_sync(peers, v); }
+};
+
 __global__ void predict_bodies(BodyView b, SolveParams prm, Diag* diag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int dyn = 0, ev = 0;
+    int dyn = 0, ev = 0, world = -1;
     if (i < b.n) {
+        world = b.worldId[i];
         BodyPose pose = b.pose[i]; BodyVel vel = b.vel[i]; BodyAux aux = b.aux[i]; BodyInit init;
         float4 pl = b.prevLin[i];
-        // pose.pos.w carries invMass for neighbours; predict_body reads it from aux
         ev = predict_body(pose, vel, pl, aux, init, prm);
         b.pose[i] = pose; b.vel[i] = vel; b.init[i] = init;
         b.aux[i].posI = aux.posI; b.aux[i].rotI = aux.rotI;
         dyn = aux.mass.y > 0.0f ? 1 : 0;
     }
-    dyn = __reduce_add_sync(0xffffffffu, dyn);
-    ev = __reduce_add_sync(0xffffffffu, ev);
-    if ((threadIdx.x & 31) == 0) {
-        if (dyn) atomicAdd(&diag->dynamicBodies, dyn);
-        if (ev) atomicAdd(&diag->nanEvents, ev);
+    WorldGroup wg(world);
+    dyn = wg.sum(dyn); ev = wg.sum(ev);
+    if (wg.leader && world >= 0) {
+        if (dyn) atomicAdd(&diag[world].dynamicBodies, dyn);
+        if (ev) atomicAdd(&diag[world].nanEvents, ev);
     }
 }
 
@@ -194,27 +209,30 @@ __device__ void accumulate_user_forces(BodySystem& s, const ForceView& fv, const
     }
 }
 
-// One colour of the primal sweep (solver.cpp:344-409).  LPB lanes per body;
-// lane l takes contact slots l, l+LPB, ... of the body's manifolds.
+// One colour of the primal sweep (solver.cpp:344-409), in two phases so both are lane-dense:
+//   phase 1  LPB lanes per body: lane l takes contact slots l, l+LPB, ... of the body's manifolds
+//            (computeConstraint + 3 rows each), then a shuffle reduction leaves the 27 sums in lane 0,
+//            which parks them in shared memory;
+//   phase 2  one lane per body (the first kThreads/LPB threads = full warps): inertial terms, Schur
+//            solve, pose update.  Running the serial solve on lane 0 of every group instead would
+//            issue it at 32/LPB-fold cost (measured: 0.8 ms per launch at 1M bodies, issue-bound).
 template <int LPB>
 __global__ void __launch_bounds__(kThreads) primal_colour(BodyView b, const int4* adjRange, const int* bList, ManifoldSet ms,
                                                           ForceView fv, const int* order, int count, SolveParams prm, float alpha,
                                                           float* dxOut, Diag* diag) {
-    int gid = (blockIdx.x * blockDim.x + threadIdx.x) / LPB;
-    int lane = threadIdx.x % LPB;
+    constexpr int BPB = kThreads / LPB;
+    __shared__ float sSys[BPB * 27];                 // stride 27 is odd: conflict-free in phase 2
+    int g = threadIdx.x / LPB, lane = threadIdx.x % LPB;
+    int gid = blockIdx.x * BPB + g;
     bool live = gid < count;
     BodySystem sys; sys.clear();
-    int i = -1; V3 pos = zero3(); Q4 rot = qid(); float invMassSelf = 0.0f;
     if (live) {
-        i = order[gid];
+        int i = order[gid];
         BodyPose self = b.pose[i];
-        BodyAux aux = b.aux[i];
-        pos = xyz(self.pos); rot = quat(self.rot);
-        invMassSelf = aux.mass.y;
-        M3 invIw;
-        BodySystem own;
-        body_self_system(pos, rot, aux, prm.dt, own, invIw);
-        if (lane == 0) sys = own;
+        V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
+        float invMassSelf = self.pos.w;
+        V3 I = xyz(b.aux[i].inert);
+        M3 invIw = rot_diag(qmat(rot), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
         int4 rg = adjRange[i];
         int nA = rg.y - rg.x, nB = rg.w - rg.z;
         int slots = (nA + nB) * 4;
@@ -238,15 +256,39 @@ __global__ void __launch_bounds__(kThreads) primal_colour(BodyView b, const int4
         if (lane == 0 && fv.adjStart) accumulate_user_forces(sys, fv, b.pose, i, pos, rot, invIw);
     }
     if (LPB > 1) reduce_system(sys, LPB);
-    if (live && lane == 0) {
-        V3 dl, da;
-        solve_body_system(sys, dl, da);
-        int ev = apply_body_update(pos, rot, dl, da);
-        BodyPose out; out.pos = f4(pos, invMassSelf); out.rot = f4(rot);
-        b.pose[i] = out;
-        if (dxOut) { float* o = dxOut + 6 * i; o[0] = dl.x; o[1] = dl.y; o[2] = dl.z; o[3] = da.x; o[4] = da.y; o[5] = da.z; }
-        if (ev) atomicAdd(&diag->nanEvents, ev);
+    if (lane == 0) {
+        float* o = sSys + g * 27;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { o[k] = sys.rl[k]; o[3 + k] = sys.ra[k]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { o[6 + k] = sys.ll[k]; o[21 + k] = sys.aa[k]; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o[12 + k] = sys.la[k];
     }
+    __syncthreads();
+    if (threadIdx.x >= BPB) return;
+    gid = blockIdx.x * BPB + threadIdx.x;
+    if (gid >= count) return;
+    int i = order[gid];
+    BodyPose self = b.pose[i];
+    BodyAux aux = b.aux[i];
+    V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
+    BodySystem own; M3 invIw;
+    body_self_system(pos, rot, aux, prm.dt, own, invIw);
+    const float* o = sSys + threadIdx.x * 27;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { own.rl[k] += o[k]; own.ra[k] += o[3 + k]; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { own.ll[k] += o[6 + k]; own.aa[k] += o[21 + k]; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) own.la[k] += o[12 + k];
+    V3 dl, da;
+    solve_body_system(own, dl, da);
+    int ev = apply_body_update(pos, rot, dl, da);
+    BodyPose out; out.pos = f4(pos, self.pos.w); out.rot = f4(rot);
+    b.pose[i] = out;
+    if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
+    if (ev) atomicAdd(&diag[b.worldId[i]].nanEvents, ev);
 }
 
 // ------------------------------------------------------------------ dual
@@ -309,41 +351,39 @@ __global__ void dual_user_forces(BodyView b, ForceView fv, SolveParams prm) {
 }
 
 // ------------------------------------------------------------------ velocity + diagnostics
-__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
-    // non-negative floats order like their bit patterns
-    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
-}
-
 __global__ void velocity_bodies(BodyView b, SolveParams prm, Diag* diag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float ls = 0.0f, as = 0.0f; int ev = 0;
-    if (i < b.n && b.aux[i].mass.y > 0.0f) {
-        BodyVel vel = b.vel[i]; float4 pl;
-        ev = velocity_body(b.pose[i], b.init[i], vel, pl, prm.dt, ls, as);
-        b.vel[i] = vel; b.prevLin[i] = pl;
+    float ls = 0.0f, as = 0.0f; int ev = 0; int world = -1;
+    if (i < b.n) {
+        world = b.worldId[i];
+        if (b.pose[i].pos.w > 0.0f) {
+            BodyVel vel = b.vel[i]; float4 pl;
+            ev = velocity_body(b.pose[i], b.init[i], vel, pl, prm.dt, ls, as);
+            b.vel[i] = vel; b.prevLin[i] = pl;
+        }
     }
-    for (int off = 16; off > 0; off >>= 1) {
-        ls = fmax2(ls, __shfl_xor_sync(0xffffffffu, ls, off));
-        as = fmax2(as, __shfl_xor_sync(0xffffffffu, as, off));
-    }
-    ev = __reduce_add_sync(0xffffffffu, ev);
-    if ((threadIdx.x & 31) == 0) {
-        if (ls > 0.0f) atomic_max_nonneg(&diag->maxLinearSpeed, ls);
-        if (as > 0.0f) atomic_max_nonneg(&diag->maxAngularSpeed, as);
-        if (ev) atomicAdd(&diag->nanEvents, ev);
+    WorldGroup wg(world);
+    ls = wg.max_nonneg(ls); as = wg.max_nonneg(as); ev = wg.sum(ev);
+    if (wg.leader && world >= 0) {
+        Diag* d = diag + world;
+        if (ls > 0.0f) atomic_max_nonneg(&d->maxLinearSpeed, ls);
+        if (as > 0.0f) atomic_max_nonneg(&d->maxAngularSpeed, as);
+        if (ev) atomicAdd(&d->nanEvents, ev);
     }
 }
 
 // solver.cpp:472-497
 __global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nM, Diag* diag) {
     int ci = blockIdx.x * blockDim.x + threadIdx.x;
-    float pen = 0.0f, viol = 0.0f, lam = 0.0f; int nc = 0, nm = 0;
+    float pen = 0.0f, viol = 0.0f, lam = 0.0f; int nc = 0, nm = 0, nv = 0; int world = -1;
     if (ci < nM * 4) {
         int m = ci >> 2, c = ci & 3;
         int4 h = ms.hdr[m];
+        world = b.worldId[h.x];
         if (c == 0 && h.z > 0) { nm = 1; nc = h.z; }
         if (c < h.z) {
             BodyPose pa = b.pose[h.x], pb = b.pose[h.y];
+            nv = (pa.pos.w > 0.0f ? 1 : 0) + (pb.pos.w > 0.0f ? 1 : 0);
             float4 a4 = ms.cA[ci], b4 = ms.cB[ci], n4 = ms.cN[ci];
             V3 pA = xyz(pa.pos) + qrot(quat(pa.rot), xyz(a4));
             V3 pB = xyz(pb.pos) + qrot(quat(pb.rot), xyz(b4));
@@ -353,20 +393,38 @@ __global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nM, Diag* d
             lam = fabsf(ms.cL[ci].x);
         }
     }
-    for (int off = 16; off > 0; off >>= 1) {
-        pen = fmax2(pen, __shfl_xor_sync(0xffffffffu, pen, off));
-        viol = fmax2(viol, __shfl_xor_sync(0xffffffffu, viol, off));
-        lam = fmax2(lam, __shfl_xor_sync(0xffffffffu, lam, off));
+    WorldGroup wg(world);
+    pen = wg.max_nonneg(pen); viol = wg.max_nonneg(viol); lam = wg.max_nonneg(lam);
+    nc = wg.sum(nc); nm = wg.sum(nm); nv = wg.sum(nv);
+    if (wg.leader && world >= 0) {
+        Diag* d = diag + world;
+        if (pen > 0.0f) atomic_max_nonneg(&d->maxPenetration, pen);
+        if (viol > 0.0f) atomic_max_nonneg(&d->maxViolation, viol);
+        if (lam > 0.0f) atomic_max_nonneg(&d->maxNormalImpulse, lam);
+        if (nc) atomicAdd(&d->activeContacts, nc);
+        if (nm) atomicAdd(&d->activeManifolds, nm);
+        if (nv) atomicAdd(&d->contactVisits, nv);
     }
-    nc = __reduce_add_sync(0xffffffffu, nc);
-    nm = __reduce_add_sync(0xffffffffu, nm);
-    if ((threadIdx.x & 31) == 0) {
-        if (pen > 0.0f) atomic_max_nonneg(&diag->maxPenetration, pen);
-        if (viol > 0.0f) atomic_max_nonneg(&diag->maxViolation, viol);
-        if (lam > 0.0f) atomic_max_nonneg(&diag->maxNormalImpulse, lam);
-        if (nc) atomicAdd(&diag->activeContacts, nc);
-        if (nm) atomicAdd(&diag->activeManifolds, nm);
-    }
+}
+
+// Rigid public state <-> the 13-float-per-body host layout (pos3 quat4 lin3 ang3), on the device so the
+// host side of Solver::step() is one DMA each way.
+__global__ void pack_state(BodyView b, float* out13) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    BodyPose p = b.pose[i]; BodyVel v = b.vel[i];
+    float* o = out13 + 13 * (size_t)i;
+    o[0] = p.pos.x; o[1] = p.pos.y; o[2] = p.pos.z; o[3] = p.rot.x; o[4] = p.rot.y; o[5] = p.rot.z; o[6] = p.rot.w;
+    o[7] = v.lin.x; o[8] = v.lin.y; o[9] = v.lin.z; o[10] = v.ang.x; o[11] = v.ang.y; o[12] = v.ang.z;
+}
+__global__ void unpack_state(BodyView b, const float* in13) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const float* o = in13 + 13 * (size_t)i;
+    float invMass = b.aux[i].mass.y;
+    BodyPose p; p.pos = make_float4(o[0], o[1], o[2], invMass); p.rot = make_float4(o[3], o[4], o[5], o[6]);
+    BodyVel v; v.lin = make_float4(o[7], o[8], o[9], 0.f); v.ang = make_float4(o[10], o[11], o[12], 0.f);
+    b.pose[i] = p; b.vel[i] = v;
 }
 
 // Batched 6x6 solves on caller data (parity harness for solve6x6, solver.cpp:68-83).

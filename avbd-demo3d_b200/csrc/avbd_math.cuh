@@ -145,6 +145,30 @@ AVBD_HD V3 ldl3(const M3& A, V3 b) {
     return x;
 }
 
+// The same LDL^T split into factor + substitute: the factor depends on A only, so solving several right-hand
+// sides against one factor gives bit-identical results to calling ldl3 once per right-hand side.
+struct Ldl3 { float d0, d1, d2, l10, l20, l21; bool ok; };
+AVBD_HD Ldl3 ldl3_factor(const M3& A) {
+    Ldl3 f; f.ok = false; f.d0 = f.d1 = f.d2 = 1.0f; f.l10 = f.l20 = f.l21 = 0.0f;
+    V3 L0 = A.c[0];
+    if (fabsf(L0.x) < FLT_EPSILON) return f;
+    f.d0 = L0.x; f.l10 = L0.y / f.d0; f.l20 = L0.z / f.d0;
+    V3 L1 = A.c[1] - L0 * f.l10;
+    if (fabsf(L1.y) < FLT_EPSILON) return f;
+    f.d1 = L1.y; f.l21 = L1.z / f.d1;
+    V3 L2 = (A.c[2] - L0 * f.l20) - L1 * f.l21;
+    if (fabsf(L2.z) < FLT_EPSILON) return f;
+    f.d2 = L2.z; f.ok = true;
+    return f;
+}
+AVBD_HD V3 ldl3_solve(const Ldl3& f, V3 b) {
+    if (!f.ok) return zero3();
+    V3 y; y.x = b.x; y.y = b.y - f.l10 * y.x; y.z = b.z - f.l20 * y.x - f.l21 * y.y;
+    V3 z; z.x = y.x / f.d0; z.y = y.y / f.d1; z.z = y.z / f.d2;
+    V3 x; x.z = z.z; x.y = z.y - f.l21 * x.z; x.x = z.x - f.l10 * x.y - f.l20 * x.z;
+    return x;
+}
+
 // Contact frame from a stored normal.  manifold.cpp:39-50
 AVBD_HD void contact_basis(V3 nin, V3& n, V3& t1, V3& t2) {
     n = unit_or(nin, mk3(0.0f, 1.0f, 0.0f));

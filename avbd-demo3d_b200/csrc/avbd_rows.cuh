@@ -126,8 +126,9 @@ AVBD_HD void solve_body_system(const BodySystem& s, V3& dl, V3& da) {
     M3 la = m3(mk3(s.la[0], s.la[3], s.la[6]), mk3(s.la[1], s.la[4], s.la[7]), mk3(s.la[2], s.la[5], s.la[8]));
     M3 al = m3(mk3(s.la[0], s.la[1], s.la[2]), mk3(s.la[3], s.la[4], s.la[5]), mk3(s.la[6], s.la[7], s.la[8]));
     V3 bl = mk3(s.rl[0], s.rl[1], s.rl[2]), ba = mk3(s.ra[0], s.ra[1], s.ra[2]);
-    M3 W = m3(ldl3(ll, la.c[0]), ldl3(ll, la.c[1]), ldl3(ll, la.c[2]));
-    V3 x0 = ldl3(ll, bl);
+    Ldl3 fl = ldl3_factor(ll);
+    M3 W = m3(ldl3_solve(fl, la.c[0]), ldl3_solve(fl, la.c[1]), ldl3_solve(fl, la.c[2]));
+    V3 x0 = ldl3_solve(fl, bl);
     M3 S;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {

@@ -59,7 +59,8 @@ struct Diag {                 // Solver::Diagnostics, solver.h:155-164 (+ saniti
     float maxPenetration, maxViolation, maxLinearSpeed, maxAngularSpeed, maxNormalImpulse;
     int activeContacts, activeManifolds, dynamicBodies;
     int nanEvents;            // bodies scrubbed by the NaN guards (solver.cpp:51-66)
-    int pad[3];
+    int contactVisits;        // contacts counted once per DYNAMIC endpoint (= primal contact visits per iteration)
+    int pad[2];
 };
 
 struct Counters {             // device-side sizes produced by one stage, consumed by the next

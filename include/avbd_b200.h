@@ -43,8 +43,17 @@ typedef struct avbd_diagnostics {
 typedef struct avbd_step_stats {
     float ms_broadphase, ms_narrowphase, ms_graph, ms_predict, ms_primal, ms_dual, ms_velocity, ms_total;
     int bodies, dynamicBodies, pairs, candidates, manifolds, contacts, colours, iterations;
-    long long kernelLaunches;   /* launches of this library's kernels since world creation */
+    int contactVisits;          /* contacts counted once per dynamic endpoint = primal contact visits per iteration */
+    long long kernelLaunches;   /* launches of this library's own kernels since world creation */
 } avbd_step_stats;
+
+/* Accumulated since avbd_set_profiling(w, 1): device time (CUDA events on the world's stream) of the primal
+ * sweeps and dual passes, with the work they covered, so a caller can form algorithmic-bytes / time. */
+typedef struct avbd_profile {
+    double ms_primal, ms_dual;
+    long long steps, primal_sweeps, primal_launches, primal_bodies, primal_visits, dual_launches, dual_contacts;
+    long long kernel_launches, library_launches;   /* totals since world creation: own kernels / CUB passes */
+} avbd_profile;
 
 const char* avbd_last_error(void);
 int  avbd_device_count(void);
@@ -79,6 +88,10 @@ int  avbd_add_ignore(avbd_world* w, int a, int b);
 /* Solver::step() x n (solver.cpp:255-514).  Asynchronous on the world's stream. */
 int  avbd_step(avbd_world* w, int n);
 int  avbd_sync(avbd_world* w);
+/* n steps bracketed by CUDA events on the world's stream; *ms = device time of the n steps. */
+int  avbd_step_timed(avbd_world* w, int n, float* ms);
+int  avbd_set_profiling(avbd_world* w, int on);
+int  avbd_get_profile(avbd_world* w, avbd_profile* out);
 
 /* Rigid public state (solver.h:56-60): 13 floats per body pos3 quat4 lin3 ang3, creation order. */
 int  avbd_download_state(avbd_world* w, float* out13);
@@ -98,6 +111,9 @@ int  avbd_world_diagnostics_device_ptr(avbd_world* w, void** ptr, int* count);
 
 /* The Manifold list (solver.h:112-143) in pair-key order.  Layout per manifold identical to the
  * oracle dumps: ints3 {idxA idxB numContacts}, feats4, stick4, flts81 {friction, 4 x (rA3 rB3 n3 pen C0n C0t3), lambda12, penalty12}. */
+/* avbd_num_manifolds = slots in use (upper bound for sizing buffers); avbd_download_manifolds returns how many
+ * LIVE manifolds (numContacts > 0) it wrote — pairs whose SAT passed but produced no contact are skipped,
+ * as the reference deletes them (solver.cpp:274-279). */
 int  avbd_num_manifolds(avbd_world* w);
 int  avbd_download_manifolds(avbd_world* w, int* ints3, int* feats4, int* stick4, float* flts81);
 
