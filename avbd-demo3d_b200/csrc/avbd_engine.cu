@@ -3,7 +3,7 @@
 // world or a batch of independent worlds (ensemble).  No CPU fallback: every
 // entry point fails when no CUDA device is usable.
 #include "../../include/avbd_b200.h"
-#include "avbd_kernels_solve.cuh"
+#include "avbd_kernels_graph.cuh"
 
 #include <cub/cub.cuh>
 
@@ -84,6 +84,7 @@ struct avbd_world {
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
     DevBuf<unsigned long long> cand, candSorted; int nCand = 0, nPairs = 0;
     DevBuf<int> candInfo, candFlag, candScan, survP;
+    DevBuf<int> mcount, contactStart, contactList, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;
 
     // manifolds (ping-pong)
     struct MBuf { DevBuf<unsigned long long> key; DevBuf<int4> hdr; DevBuf<float4> cA, cB, cN, cL, cP; } mb[2];
@@ -357,9 +358,18 @@ int run_collide(avbd_world* w) {
     int nxt = w->cur ^ 1;
     if (nSurv > 0) {
         TRY(w->ensure_manifolds(nxt, nSurv));
+        TRY(w->mcount.ensure(nSurv, false, s)); TRY(w->contactStart.ensure(nSurv, false, s)); TRY(w->contactList.ensure((size_t)nSurv * 4, false, s));
         np_build<<<blocks_for(nSurv), kThreads, 0, s>>>(w->bview(), w->candSorted.p, w->candInfo.p, w->survP.p, nSurv, w->keyShift,
-                                                          w->mset(w->cur), w->nM, w->mset(nxt), w->prm);
+                                                          w->mset(w->cur), w->nM, w->mset(nxt), w->mcount.p, w->prm);
         w->launches++;
+        // dense list of live contacts (the dual's work list; also sizes the visit list)
+        TRY(exclusive_scan(w, w->mcount.p, w->contactStart.p, nSurv));
+        contact_list_fill<<<blocks_for(nSurv), kThreads, 0, s>>>(w->mset(nxt).hdr, w->contactStart.p, nSurv, w->contactList.p, w->dCnt);
+        w->launches++;
+        TRY(read_counters(w));
+        w->nContacts = w->hCnt->nContacts;
+    } else {
+        w->nContacts = 0;
     }
     w->cur = nxt; w->nM = nSurv;
     ForceView fv = w->fview();
@@ -399,6 +409,14 @@ int run_colour(avbd_world* w) {
     } else {
         TRY(w->bList.ensure(1, false, s));
     }
+    // per-body runs of contact visits (the primal's work list)
+    TRY(w->visitCount.ensure((size_t)n + 1, false, s)); TRY(w->visitStart.ensure((size_t)n + 1, false, s));
+    TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
+    CK(cudaMemsetAsync(w->visitCount.p, 0, sizeof(int) * ((size_t)n + 1), s));
+    visit_count<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
+    TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, n + 1));
+    visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitStart.p, w->visits.p);
+    w->launches += 2;
     colour_init<<<blocks_for(n), kThreads, 0, s>>>(w->flags.p, n, w->colour.p);
     w->launches++;
     ForceView fv = w->fview();
@@ -424,8 +442,6 @@ int run_colour(avbd_world* w) {
     return 0;
 }
 
-constexpr int kLanesPerBody = 8;
-
 int run_primal(avbd_world* w, float alpha, float* dxDev) {
     if (!w->graphValid) TRY(run_colour(w));
     cudaStream_t s = w->stream;
@@ -434,8 +450,7 @@ int run_primal(avbd_world* w, float alpha, float* dxDev) {
     for (int c = 0; c < w->nColours; ++c) {
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
-        primal_colour<kLanesPerBody><<<blocks_for(count, kThreads / kLanesPerBody), kThreads, 0, s>>>(
-            w->bview(), w->adjRange.p, w->bList.p, ms, fv, w->colOrder.p + first, count, w->prm, alpha, dxDev, w->dDiag.p);
+        launch_primal(s, w->bview(), w->visitStart.p, w->visits.p, ms, fv, w->colOrder.p + first, count, w->prm, alpha, dxDev, w->dDiag.p);
         w->launches++;
     }
     CK(cudaGetLastError());
@@ -444,13 +459,13 @@ int run_primal(avbd_world* w, float alpha, float* dxDev) {
 
 int run_dual(avbd_world* w, float alpha) {
     cudaStream_t s = w->stream;
-    if (w->nM > 0) {
-        dual_contacts<<<blocks_for((long long)w->nM * 4), kThreads, 0, s>>>(w->bview(), w->mset(w->cur), w->nM, w->prm, alpha);
+    if (w->nContacts > 0) {
+        launch_dual(s, w->bview(), w->mset(w->cur), w->contactList.p, w->nContacts, w->prm, alpha);
         w->launches++;
     }
     ForceView fv = w->fview();
     if (fv.nJoints + fv.nSprings > 0) {
-        dual_user_forces<<<blocks_for(fv.nJoints + fv.nSprings), kThreads, 0, s>>>(w->bview(), fv, w->prm);
+        launch_dual_user_forces(s, w->bview(), fv, w->prm);
         w->launches++;
     }
     CK(cudaGetLastError());
@@ -571,6 +586,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
     w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release();
+    w->mcount.release(); w->contactStart.release(); w->contactList.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
     if (w->hCnt) cudaFreeHost(w->hCnt);
@@ -584,7 +600,7 @@ int avbd_clear(avbd_world* w) {
     if (!w) return fail(AVBD_ERR_ARG, "null world");
     CK(cudaSetDevice(w->device));
     CK(cudaStreamSynchronize(w->stream));
-    w->n = 0; w->nDyn = 0; w->nWorlds = 1; w->hb.clear(); w->nM = 0; w->nCand = 0; w->nPairs = 0;
+    w->n = 0; w->nDyn = 0; w->nWorlds = 1; w->hb.clear(); w->nM = 0; w->nCand = 0; w->nPairs = 0; w->nContacts = 0;
     w->hJoints.clear(); w->hSprings.clear(); w->hForces.clear(); w->uploadedJoints = 0; w->uploadedSprings = 0; w->nExcl = 0;
     w->topoDirty = true; w->forcesDirty = true; w->graphValid = false; w->nColours = 0;
     if (w->hDiag) std::memset(w->hDiag, 0, sizeof(Diag) * w->hDiagCap);
@@ -1007,7 +1023,7 @@ int avbd_solve6x6(int device, int n, const float* lhs36, const float* rhs6, floa
     CK(cudaMalloc(&dl, (size_t)n * 36 * sizeof(float))); CK(cudaMalloc(&dr, n * 6 * sizeof(float))); CK(cudaMalloc(&dout, n * 6 * sizeof(float)));
     CK(cudaMemcpy(dl, lhs36, (size_t)n * 36 * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dr, rhs6, n * 6 * sizeof(float), cudaMemcpyHostToDevice));
-    solve6_batch<<<blocks_for(n, 128), 128>>>(dl, dr, n, dout);
+    launch_solve6_batch(nullptr, dl, dr, n, dout);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out6, dout, n * 6 * sizeof(float), cudaMemcpyDeviceToHost));
     cudaFree(dl); cudaFree(dr); cudaFree(dout);

@@ -11,18 +11,11 @@
 #include <cooperative_groups.h>
 #include "avbd_body.cuh"
 #include "avbd_forces.cuh"
+#include "avbd_launch.h"
 
 namespace avbd {
 namespace cg = cooperative_groups;
 
-constexpr int kThreads = 256;
-
-struct BodyView {
-    BodyPose* pose; BodyAux* aux; BodyVel* vel; BodyInit* init;
-    float4* prevLin; float4* size;      // size: sx sy sz friction
-    int* flags; int* worldId; int* localIdx;
-    int n;
-};
 
 struct GridView {
     float cell;                         // edge length, >= 2.02 * largest small radius
@@ -202,7 +195,7 @@ __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int 
 // slot, carrying lambda / penalty / stick anchors over from last step's
 // manifold of the same pair, then apply the per-step warm-start decay.
 __global__ void np_build(BodyView b, const unsigned long long* cand, const int* info, const int* survP, int nSurvive,
-                         int keyShift, ManifoldSet old, int nOld, ManifoldSet out, SolveParams prm) {
+                         int keyShift, ManifoldSet old, int nOld, ManifoldSet out, int* mcount, SolveParams prm) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nSurvive) return;
     int p = survP[s];
@@ -221,6 +214,7 @@ __global__ void np_build(BodyView b, const unsigned long long* cand, const int* 
     float mu = sqrtf(sa.w * sb.w);                                   // manifold.cpp:73
     out.key[s] = k;
     out.hdr[s] = make_int4(a, c, nm.n, __float_as_int(mu));
+    mcount[s] = nm.n;
     for (int i = 0; i < 4; ++i) {
         if (i < nm.n) store_contact(out, s * 4 + i, nm.ct[i]);
         else {

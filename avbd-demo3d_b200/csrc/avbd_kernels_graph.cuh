@@ -1,0 +1,259 @@
+// avbd_kernels_graph.cuh — body/manifold graph (adjacency ranges, greedy colouring, dense contact and
+// contact-visit lists) plus the once-per-step body kernels (predict, velocity recovery, diagnostics, state
+// pack/unpack).  Compiled in the -fmad=false translation unit with the collision kernels.
+#pragma once
+#include "avbd_kernels_collide.cuh"
+#include "avbd_launch.h"
+
+namespace avbd {
+
+// ------------------------------------------------------------------ adjacency
+// Manifolds are sorted by (A,B): a body's "I am A" manifolds are one contiguous
+// run [x,y).  Its "I am B" manifolds are a run [z,w) of bList (manifold ids
+// stably sorted by B).  adjRange must be zeroed before these two kernels.
+__global__ void adj_a_ranges(const int4* hdr, int nM, const int* flags, int nBodies, int4* adjRange, unsigned* bKey, int* bVal) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nM) return;
+    int4 h = hdr[m];
+    if (m == 0 || hdr[m - 1].x != h.x) adjRange[h.x].x = m;
+    if (m == nM - 1 || hdr[m + 1].x != h.x) adjRange[h.x].y = m + 1;
+    bKey[m] = (flags[h.y] & kDynamic) ? (unsigned)h.y : (unsigned)nBodies;   // static B never solves: park at the end
+    bVal[m] = m;
+}
+__global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, int4* adjRange) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nM) return;
+    unsigned k = bKeySorted[t];
+    if (k >= (unsigned)nBodies) return;
+    if (t == 0 || bKeySorted[t - 1] != k) adjRange[k].z = t;
+    if (t == nM - 1 || bKeySorted[t + 1] != k) adjRange[k].w = t + 1;
+}
+
+// ------------------------------------------------------------------ dense contact / visit lists
+// Manifold slots hold up to 4 contacts but the live count varies (about 2 on a settled box grid), so the
+// per-iteration kernels never walk slots: the dual walks `contactList` (live contact ids ci = 4m+c) and the
+// primal walks, per dynamic body, a run of `visits` {ci, other body, body-is-A, friction bits} — one entry per
+// live contact of every manifold touching the body, built once per step.
+__global__ void contact_list_fill(const int4* hdr, const int* contactStart, int nM, int* contactList, Counters* cnt) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nM) return;
+    int n = hdr[m].z, s = contactStart[m];
+    for (int c = 0; c < n; ++c) contactList[s + c] = 4 * m + c;
+    if (m == nM - 1) cnt->nContacts = s + n;
+}
+__global__ void visit_count(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    int i = dynList[t];
+    int4 rg = adjRange[i];
+    int k = 0;
+    for (int m = rg.x; m < rg.y; ++m) k += hdr[m].z;
+    for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z;
+    visitCount[i] = k;
+}
+__global__ void visit_fill(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* visitStart, int4* visits) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    int i = dynList[t];
+    int4 rg = adjRange[i];
+    int o = visitStart[i];
+    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(4 * m + c, h.y, 1, h.w); }
+    for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(4 * m + c, h.x, 0, h.w); }
+}
+
+// ------------------------------------------------------------------ colouring
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
+}
+// Priority is a function of the WORLD-LOCAL index only, so a world colours the
+// same way wherever it sits in a batch (ensemble runs are partition-invariant).
+__device__ __forceinline__ bool outranks(int localA, int localB) {
+    unsigned ha = mix32((unsigned)localA + 0x9e3779b9u), hb = mix32((unsigned)localB + 0x9e3779b9u);
+    return ha != hb ? ha > hb : localA > localB;
+}
+
+__global__ void colour_init(const int* flags, int n, int* colour) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) colour[i] = (flags[i] & kDynamic) ? -1 : -2;
+}
+
+// One Jones-Plassmann round: a body takes the smallest colour unused by its
+// neighbours once every higher-priority neighbour is coloured.  The result is
+// the sequential greedy colouring in priority order, independent of timing.
+__global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
+                             ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    int i = dynList[t];
+    if (colour[i] >= 0) return;
+    int li = localIdx[i];
+    unsigned long long used = 0ull;
+    bool ready = true;
+    int4 rg = adjRange[i];
+    auto visit = [&](int other) {
+        if (other < 0) return;
+        int co = colour[other];
+        if (co >= 0) used |= 1ull << co;
+        else if (co == -1 && outranks(localIdx[other], li)) ready = false;
+    };
+    for (int m = rg.x; m < rg.y && ready; ++m) visit(hdr[m].y);
+    for (int k = rg.z; k < rg.w && ready; ++k) visit(hdr[bList[k]].x);
+    if (fv.adjStart) {
+        for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && ready; ++k) {
+            int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
+            int other = (e & 2) ? (isA ? fv.springs[idx].b : fv.springs[idx].a) : (isA ? fv.joints[idx].b : fv.joints[idx].a);
+            visit(other);
+        }
+    }
+    if (ready) {
+        int c = __ffsll((long long)~used) - 1;
+        if (c < 0) { c = 63; atomicOr(&cnt->overflow, 4); }
+        colour[i] = c;
+    } else {
+        cg::coalesced_group grp = cg::coalesced_threads();
+        if (grp.thread_rank() == 0) atomicAdd(&cnt->nUncoloured, (int)grp.size());
+    }
+}
+
+__global__ void colour_keys(const int* dynList, int nDyn, const int* colour, unsigned* key, int* val) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    int i = dynList[t];
+    key[t] = (unsigned)colour[i];
+    val[t] = i;
+}
+// colourRange[c] = {first, last+1} in the colour-sorted body order; must be zeroed first.
+__global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourRange, Counters* cnt) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    unsigned c = keySorted[t];
+    if (t == 0 || keySorted[t - 1] != c) colourRange[c].x = t;
+    if (t == nDyn - 1 || keySorted[t + 1] != c) colourRange[c].y = t + 1;
+    if (t == nDyn - 1) cnt->nColours = (int)c + 1;
+}
+
+// ------------------------------------------------------------------ predict / warm-start decay of user forces
+// Diagnostics are kept per world (an ensemble batch reports each world separately).  Lanes of a warp that
+// belong to the same world combine first (match_any + masked reduce), then one atomic per (warp, world).
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));       // non-negative floats order like their bit patterns
+}
+struct WorldGroup {
+    unsigned peers; bool leader;
+    __device__ __forceinline__ WorldGroup(int world) {
+        peers = __match_any_sync(0xffffffffu, world);
+        leader = (__ffs(peers) - 1) == (int)(threadIdx.x & 31);
+    }
+    __device__ __forceinline__ float max_nonneg(float v) const { return __uint_as_float(__reduce_max_sync(peers, __float_as_uint(v))); }
+    __device__ __forceinline__ int sum(int v) const { return __reduce_add_sync(peers, v); }
+};
+
+__global__ void predict_bodies(BodyView b, SolveParams prm, Diag* diag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int dyn = 0, ev = 0, world = -1;
+    if (i < b.n) {
+        world = b.worldId[i];
+        BodyPose pose = b.pose[i]; BodyVel vel = b.vel[i]; BodyAux aux = b.aux[i]; BodyInit init;
+        float4 pl = b.prevLin[i];
+        ev = predict_body(pose, vel, pl, aux, init, prm);
+        b.pose[i] = pose; b.vel[i] = vel; b.init[i] = init;
+        b.aux[i].posI = aux.posI; b.aux[i].rotI = aux.rotI;
+        dyn = aux.mass.y > 0.0f ? 1 : 0;
+    }
+    WorldGroup wg(world);
+    dyn = wg.sum(dyn); ev = wg.sum(ev);
+    if (wg.leader && world >= 0) {
+        if (dyn) atomicAdd(&diag[world].dynamicBodies, dyn);
+        if (ev) atomicAdd(&diag[world].nanEvents, ev);
+    }
+}
+
+__global__ void decay_user_forces(ForceView fv, SolveParams prm) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < fv.nJoints) {
+        JointRec& j = fv.joints[t];
+        for (int r = 0; r < 6; ++r) decay_row(j.lambda[r], j.penalty[r], r < 3 ? j.kLin : j.kAng, prm);
+    } else if (t - fv.nJoints < fv.nSprings) {
+        SpringRec& s = fv.springs[t - fv.nJoints];
+        decay_row(s.lambda, s.penalty, s.k, prm);
+    }
+}
+
+// ------------------------------------------------------------------ velocity + diagnostics
+__global__ void velocity_bodies(BodyView b, SolveParams prm, Diag* diag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float ls = 0.0f, as = 0.0f; int ev = 0; int world = -1;
+    if (i < b.n) {
+        world = b.worldId[i];
+        if (b.pose[i].pos.w > 0.0f) {
+            BodyVel vel = b.vel[i]; float4 pl;
+            ev = velocity_body(b.pose[i], b.init[i], vel, pl, prm.dt, ls, as);
+            b.vel[i] = vel; b.prevLin[i] = pl;
+        }
+    }
+    WorldGroup wg(world);
+    ls = wg.max_nonneg(ls); as = wg.max_nonneg(as); ev = wg.sum(ev);
+    if (wg.leader && world >= 0) {
+        Diag* d = diag + world;
+        if (ls > 0.0f) atomic_max_nonneg(&d->maxLinearSpeed, ls);
+        if (as > 0.0f) atomic_max_nonneg(&d->maxAngularSpeed, as);
+        if (ev) atomicAdd(&d->nanEvents, ev);
+    }
+}
+
+// solver.cpp:472-497
+__global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nM, Diag* diag) {
+    int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    float pen = 0.0f, viol = 0.0f, lam = 0.0f; int nc = 0, nm = 0, nv = 0; int world = -1;
+    if (ci < nM * 4) {
+        int m = ci >> 2, c = ci & 3;
+        int4 h = ms.hdr[m];
+        world = b.worldId[h.x];
+        if (c == 0 && h.z > 0) { nm = 1; nc = h.z; }
+        if (c < h.z) {
+            BodyPose pa = b.pose[h.x], pb = b.pose[h.y];
+            nv = (pa.pos.w > 0.0f ? 1 : 0) + (pb.pos.w > 0.0f ? 1 : 0);
+            float4 a4 = ms.cA[ci], b4 = ms.cB[ci], n4 = ms.cN[ci];
+            V3 pA = xyz(pa.pos) + qrot(quat(pa.rot), xyz(a4));
+            V3 pB = xyz(pb.pos) + qrot(quat(pb.rot), xyz(b4));
+            float sepn = dot(pA - pB, xyz(n4));
+            pen = fmax2(0.0f, -sepn);
+            viol = fmax2(0.0f, kPenetrationSlop - sepn);
+            lam = fabsf(ms.cL[ci].x);
+        }
+    }
+    WorldGroup wg(world);
+    pen = wg.max_nonneg(pen); viol = wg.max_nonneg(viol); lam = wg.max_nonneg(lam);
+    nc = wg.sum(nc); nm = wg.sum(nm); nv = wg.sum(nv);
+    if (wg.leader && world >= 0) {
+        Diag* d = diag + world;
+        if (pen > 0.0f) atomic_max_nonneg(&d->maxPenetration, pen);
+        if (viol > 0.0f) atomic_max_nonneg(&d->maxViolation, viol);
+        if (lam > 0.0f) atomic_max_nonneg(&d->maxNormalImpulse, lam);
+        if (nc) atomicAdd(&d->activeContacts, nc);
+        if (nm) atomicAdd(&d->activeManifolds, nm);
+        if (nv) atomicAdd(&d->contactVisits, nv);
+    }
+}
+
+// Rigid public state <-> the 13-float-per-body host layout (pos3 quat4 lin3 ang3), on the device so the
+// host side of Solver::step() is one DMA each way.
+__global__ void pack_state(BodyView b, float* out13) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    BodyPose p = b.pose[i]; BodyVel v = b.vel[i];
+    float* o = out13 + 13 * (size_t)i;
+    o[0] = p.pos.x; o[1] = p.pos.y; o[2] = p.pos.z; o[3] = p.rot.x; o[4] = p.rot.y; o[5] = p.rot.z; o[6] = p.rot.w;
+    o[7] = v.lin.x; o[8] = v.lin.y; o[9] = v.lin.z; o[10] = v.ang.x; o[11] = v.ang.y; o[12] = v.ang.z;
+}
+__global__ void unpack_state(BodyView b, const float* in13) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const float* o = in13 + 13 * (size_t)i;
+    float invMass = b.aux[i].mass.y;
+    BodyPose p; p.pos = make_float4(o[0], o[1], o[2], invMass); p.rot = make_float4(o[3], o[4], o[5], o[6]);
+    BodyVel v; v.lin = make_float4(o[7], o[8], o[9], 0.f); v.ang = make_float4(o[10], o[11], o[12], 0.f);
+    b.pose[i] = p; b.vel[i] = v;
+}
+
+} // namespace avbd

@@ -148,6 +148,27 @@ AVBD_HD V3 ldl3(const M3& A, V3 b) {
 // The same LDL^T split into factor + substitute: the factor depends on A only, so solving several right-hand
 // sides against one factor gives bit-identical results to calling ldl3 once per right-hand side.
 struct Ldl3 { float d0, d1, d2, l10, l20, l21; bool ok; };
+// Reciprocal-pivot variant for the solver kernels (tolerance path): 3 divisions per factor, none per solve.
+struct Ldl3R { float i0, i1, i2, l10, l20, l21; bool ok; };
+AVBD_HD Ldl3R ldl3r_factor(const M3& A) {
+    Ldl3R f; f.ok = false; f.i0 = f.i1 = f.i2 = 0.0f; f.l10 = f.l20 = f.l21 = 0.0f;
+    V3 L0 = A.c[0];
+    if (fabsf(L0.x) < FLT_EPSILON) return f;
+    f.i0 = 1.0f / L0.x; f.l10 = L0.y * f.i0; f.l20 = L0.z * f.i0;
+    float d1 = A.c[1].y - L0.y * f.l10, l1z = A.c[1].z - L0.z * f.l10;
+    if (fabsf(d1) < FLT_EPSILON) return f;
+    f.i1 = 1.0f / d1; f.l21 = l1z * f.i1;
+    float d2 = (A.c[2].z - L0.z * f.l20) - l1z * f.l21;
+    if (fabsf(d2) < FLT_EPSILON) return f;
+    f.i2 = 1.0f / d2; f.ok = true;
+    return f;
+}
+AVBD_HD V3 ldl3r_solve(const Ldl3R& f, V3 b) {
+    if (!f.ok) return zero3();
+    float y0 = b.x, y1 = b.y - f.l10 * y0, y2 = b.z - f.l20 * y0 - f.l21 * y1;
+    V3 x; x.z = y2 * f.i2; x.y = y1 * f.i1 - f.l21 * x.z; x.x = y0 * f.i0 - f.l10 * x.y - f.l20 * x.z;
+    return x;
+}
 AVBD_HD Ldl3 ldl3_factor(const M3& A) {
     Ldl3 f; f.ok = false; f.d0 = f.d1 = f.d2 = 1.0f; f.l10 = f.l20 = f.l21 = 0.0f;
     V3 L0 = A.c[0];
@@ -167,6 +188,22 @@ AVBD_HD V3 ldl3_solve(const Ldl3& f, V3 b) {
     V3 z; z.x = y.x / f.d0; z.y = y.y / f.d1; z.z = y.z / f.d2;
     V3 x; x.z = z.z; x.y = z.y - f.l21 * x.z; x.x = z.x - f.l10 * x.y - f.l20 * x.z;
     return x;
+}
+
+// Contact frame of an ALREADY-UNIT normal (stored normals are normalised once by Manifold::initialize,
+// manifold.cpp:157-159).  Same axis choice as manifold.cpp:39-50; the reference's re-normalisation of n
+// and t2 is idempotent up to 1 ulp, so it is skipped here (solver-side tolerance, not the bit-exact path).
+AVBD_HD void contact_basis_unit(V3 n, V3& t1, V3& t2) {
+    float a, b, l2;
+    bool useX = fabsf(n.x) >= fabsf(n.z);
+    if (useX) { a = -n.y; b = n.x; } else { a = -n.z; b = n.y; }
+    l2 = a * a + b * b;
+    if (l2 < kVecEps) { t1 = mk3(1.0f, 0.0f, 0.0f); }
+    else {
+        float inv = 1.0f / sqrtf(l2);
+        t1 = useX ? mk3(a * inv, b * inv, 0.0f) : mk3(0.0f, a * inv, b * inv);
+    }
+    t2 = cross(n, t1);
 }
 
 // Contact frame from a stored normal.  manifold.cpp:39-50

@@ -39,7 +39,8 @@ struct ContactEval {      // transient outputs of computeConstraint for one cont
 AVBD_HD void contact_constraint(V3 posA, Q4 rotA, float invMassA, V3 posB, Q4 rotB, float invMassB,
                                 float mu0, float alpha, ContactState& c, ContactEval& e) {
     float bias = clampf(1.0f - alpha, 0.0f, 1.0f);
-    contact_basis(c.n, e.basis[0], e.basis[1], e.basis[2]);
+    e.basis[0] = c.n;
+    contact_basis_unit(c.n, e.basis[1], e.basis[2]);
     e.wrA = qrot(rotA, c.rA);
     e.wrB = qrot(rotB, c.rB);
     V3 dlt = (posA + e.wrA) - (posB + e.wrB);
@@ -88,18 +89,21 @@ AVBD_HD void accumulate_row(BodySystem& s, V3 Jl, V3 Ja, float f, float pen, boo
     s.rl[0] += Jl.x * f; s.rl[1] += Jl.y * f; s.rl[2] += Jl.z * f;
     s.ra[0] += Ja.x * f; s.ra[1] += Ja.y * f; s.ra[2] += Ja.z * f;
     if (pen > 0.0f && finite1(pen)) {
+        // (J*pen) J^T: one multiply per vector entry, then one multiply-add per matrix entry
+        float lp[3] = {Jl.x * pen, Jl.y * pen, Jl.z * pen}, ap[3] = {Ja.x * pen, Ja.y * pen, Ja.z * pen};
         float jl[3] = {Jl.x, Jl.y, Jl.z}, ja[3] = {Ja.x, Ja.y, Ja.z};
-        s.ll[0] += (jl[0] * jl[0]) * pen; s.ll[1] += (jl[1] * jl[0]) * pen; s.ll[2] += (jl[2] * jl[0]) * pen;
-        s.ll[3] += (jl[1] * jl[1]) * pen; s.ll[4] += (jl[2] * jl[1]) * pen; s.ll[5] += (jl[2] * jl[2]) * pen;
-        s.aa[0] += (ja[0] * ja[0]) * pen; s.aa[1] += (ja[1] * ja[0]) * pen; s.aa[2] += (ja[2] * ja[0]) * pen;
-        s.aa[3] += (ja[1] * ja[1]) * pen; s.aa[4] += (ja[2] * ja[1]) * pen; s.aa[5] += (ja[2] * ja[2]) * pen;
+        s.ll[0] += lp[0] * jl[0]; s.ll[1] += lp[1] * jl[0]; s.ll[2] += lp[2] * jl[0];
+        s.ll[3] += lp[1] * jl[1]; s.ll[4] += lp[2] * jl[1]; s.ll[5] += lp[2] * jl[2];
+        s.aa[0] += ap[0] * ja[0]; s.aa[1] += ap[1] * ja[0]; s.aa[2] += ap[2] * ja[0];
+        s.aa[3] += ap[1] * ja[1]; s.aa[4] += ap[2] * ja[1]; s.aa[5] += ap[2] * ja[2];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) s.la[r * 3 + c] += (jl[r] * ja[c]) * pen;
+            for (int c = 0; c < 3; ++c) s.la[r * 3 + c] += lp[r] * ja[c];
         if (gyro) {
-            V3 g = vabs(cross(Ja, mv(invIw, Ja))) * fabsf(f);
-            s.aa[0] += g.x; s.aa[3] += g.y; s.aa[5] += g.z;
+            V3 g = vabs(cross(Ja, mv(invIw, Ja)));
+            float af = fabsf(f);
+            s.aa[0] += g.x * af; s.aa[3] += g.y * af; s.aa[5] += g.z * af;
         }
     }
 }
@@ -126,9 +130,9 @@ AVBD_HD void solve_body_system(const BodySystem& s, V3& dl, V3& da) {
     M3 la = m3(mk3(s.la[0], s.la[3], s.la[6]), mk3(s.la[1], s.la[4], s.la[7]), mk3(s.la[2], s.la[5], s.la[8]));
     M3 al = m3(mk3(s.la[0], s.la[1], s.la[2]), mk3(s.la[3], s.la[4], s.la[5]), mk3(s.la[6], s.la[7], s.la[8]));
     V3 bl = mk3(s.rl[0], s.rl[1], s.rl[2]), ba = mk3(s.ra[0], s.ra[1], s.ra[2]);
-    Ldl3 fl = ldl3_factor(ll);
-    M3 W = m3(ldl3_solve(fl, la.c[0]), ldl3_solve(fl, la.c[1]), ldl3_solve(fl, la.c[2]));
-    V3 x0 = ldl3_solve(fl, bl);
+    Ldl3R fl = ldl3r_factor(ll);
+    M3 W = m3(ldl3r_solve(fl, la.c[0]), ldl3r_solve(fl, la.c[1]), ldl3r_solve(fl, la.c[2]));
+    V3 x0 = ldl3r_solve(fl, bl);
     M3 S;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -136,7 +140,7 @@ AVBD_HD void solve_body_system(const BodySystem& s, V3& dl, V3& da) {
         S.c[j] = aa.c[j] - prod;
     }
     V3 rs = ba - mv(al, x0);
-    da = ldl3(S, rs);
+    da = ldl3r_solve(ldl3r_factor(S), rs);
     dl = x0 - mv(W, da);
 }
 

@@ -69,8 +69,9 @@ struct Counters {             // device-side sizes produced by one stage, consum
     int nSurvive;             // candidates that passed the SAT cull == manifolds this step
     int nUncoloured;
     int nColours;
+    int nContacts;            // live contacts this step (dense contact list length)
     int overflow;             // bit0 pairs, bit1 manifolds, bit2 colours
-    int pad[2];
+    int pad[1];
 };
 
 } // namespace avbd
