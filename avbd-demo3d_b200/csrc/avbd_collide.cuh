@@ -32,7 +32,7 @@ AVBD_HD float adot(V3 a, V3 b) { return fabsf(dot(a, b)); }
 // `sep`/`n` are only meaningful when `counted` comes back true (degenerate
 // axes are skipped, collision.cpp:211-214).
 AVBD_HD bool sat_axis(const Obb& A, const Obb& B, V3 d, V3 axis, bool& counted, float& sep, V3& n) {   // collision.cpp:208-247
-    counted = false;
+    counted = false; sep = 0.0f; n = zero3();
     float l2 = len2(axis);
     if (l2 < kSatEps) return true;
     n = axis / sqrtf(l2);

@@ -561,7 +561,7 @@ avbd_world* avbd_world_create(int device) {
     avbd_world* w = new avbd_world();
     w->device = device;
     if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&w->dCnt, sizeof(Counters)) != cudaSuccess || cudaMallocHost(&w->hCnt, sizeof(Counters)) != cudaSuccess) {
+        cudaMalloc(&w->dCnt, sizeof(Counters) + 16) != cudaSuccess || cudaMallocHost(&w->hCnt, sizeof(Counters)) != cudaSuccess) {
         fail(AVBD_ERR_CUDA, "world allocation failed");
         delete w;
         return nullptr;
@@ -1031,8 +1031,30 @@ int avbd_solve6x6(int device, int n, const float* lhs36, const float* rhs6, floa
 }
 
 int avbd_pick(avbd_world* w, const float* origin3, const float* dir3, float* local3) {
-    (void)w; (void)origin3; (void)dir3; (void)local3;
-    return fail(AVBD_ERR_ARG, "avbd_pick: not implemented yet (SURVEY §8f.1)");
+    if (!w || !origin3 || !dir3 || !local3) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    if (w->n == 0) return -1;
+    V3 origin = mk3(origin3[0], origin3[1], origin3[2]), dir = mk3(dir3[0], dir3[1], dir3[2]);
+    float l2 = len2(dir);
+    if (l2 < 1.0e-6f) return -1;                                    // solver.cpp:153-157
+    V3 rayDir = dir / sqrtf(l2);
+    unsigned long long* dBest = reinterpret_cast<unsigned long long*>(w->dCnt + 1);   // scratch slot after the counters
+    unsigned long long init = ~0ull, best = ~0ull;
+    CK(cudaMemcpyAsync(dBest, &init, sizeof(init), cudaMemcpyHostToDevice, w->stream));
+    pick_bodies<<<blocks_for(w->n), kThreads, 0, w->stream>>>(w->bview(), origin, rayDir, dBest);
+    w->launches++;
+    CK(cudaMemcpyAsync(&best, dBest, sizeof(best), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    if (best == ~0ull) return -1;
+    int i = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
+    BodyPose p; float4 sz;
+    CK(cudaMemcpyAsync(&p, w->pose.p + i, sizeof(p), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(&sz, w->size.p + i, sizeof(sz), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    float t; V3 local;
+    ray_obb(origin, rayDir, xyz(p.pos), quat(p.rot), xyz(sz), t, local);   // same function the kernel ran, for the local hit point
+    local3[0] = local.x; local3[1] = local.y; local3[2] = local.z;
+    return i;
 }
 
 } // extern "C"

@@ -256,4 +256,35 @@ __global__ void unpack_state(BodyView b, const float* in13) {
     b.pose[i] = p; b.vel[i] = v;
 }
 
+// Solver::pick (solver.cpp:145-228): ray against every dynamic OBB (slab test in body space); the closest hit wins,
+// ties going to the newest body like the reference's list walk.  best = (tHit bits << 32) | (0xFFFFFFFF - index).
+AVBD_HD bool ray_obb(V3 origin, V3 rayDir, V3 pos, Q4 rot, V3 size, float& tHit, V3& local) {
+    const float eps = 1.0e-6f;
+    Q4 inv = qconj(rot);
+    V3 lo = qrot(inv, origin - pos), ld = qrot(inv, rayDir), half = size * 0.5f;
+    float tEnter = 0.0f, tExit = FLT_MAX;
+    for (int axis = 0; axis < 3; ++axis) {
+        float o = comp(lo, axis), d = comp(ld, axis), mn = -comp(half, axis), mx = comp(half, axis);
+        if (fabsf(d) < eps) { if (o < mn || o > mx) return false; continue; }
+        float invD = 1.0f / d, t0 = (mn - o) * invD, t1 = (mx - o) * invD;
+        if (t0 > t1) { float t = t0; t0 = t1; t1 = t; }
+        tEnter = fmax2(tEnter, t0); tExit = fmin2(tExit, t1);
+        if (tEnter > tExit) return false;
+    }
+    tHit = (tEnter >= 0.0f) ? tEnter : tExit;
+    if (tHit < 0.0f) return false;
+    local = lo + ld * tHit;
+    return true;
+}
+__global__ void pick_bodies(BodyView b, V3 origin, V3 rayDir, unsigned long long* best) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    BodyPose p = b.pose[i];
+    if (p.pos.w <= 0.0f) return;
+    float t; V3 local;
+    if (!ray_obb(origin, rayDir, xyz(p.pos), quat(p.rot), xyz(b.size[i]), t, local)) return;
+    unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+    atomicMin(best, key);
+}
+
 } // namespace avbd

@@ -22,7 +22,7 @@ struct ForceView {
 };
 
 constexpr int kThreads = 256;
-constexpr int kLanesPerBody = 8;
+constexpr int kLanesPerBody = 4;
 
 // One colour of the primal sweep: `count` bodies listed in `order`.
 void launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,

@@ -5,6 +5,7 @@
 // The reference walks bodies serially (Gauss-Seidel, solver.cpp:344); here bodies of one colour share no
 // manifold, so a colour is solved in one launch with LPB lanes cooperating on each body (one contact visit =
 // computeConstraint + 3 rows per lane).
+#include <cstdlib>
 #include "avbd_launch.h"
 #include "avbd_body.cuh"
 #include "avbd_forces.cuh"
@@ -73,8 +74,8 @@ __device__ void accumulate_user_forces(BodySystem& s, const ForceView& fv, const
 //            parks them in shared memory;
 //   phase 2  one lane per body (the first kThreads/LPB threads = full warps): inertial terms, Schur solve,
 //            pose update.
-template <int LPB>
-__global__ void __launch_bounds__(kThreads) primal_colour(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
+template <int LPB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) primal_colour(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
                                                           ManifoldSet ms, ForceView fv, const int* __restrict__ order, int count,
                                                           SolveParams prm, float alpha, float* dxOut, Diag* diag) {
     constexpr int BPB = kThreads / LPB;
@@ -227,10 +228,23 @@ __global__ void solve6_batch(const float* lhs36, const float* rhs6, int n, float
 // ------------------------------------------------------------------ launchers (declared in avbd_launch.h)
 static inline int blocks_of(long long n, int per) { long long b = (n + per - 1) / per; return (int)(b < 1 ? 1 : b); }
 
+template <int LPB, int MINB>
+static void launch_primal_variant(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
+                                  const int* order, int count, SolveParams prm, float alpha, float* dxOut, Diag* diag) {
+    primal_colour<LPB, MINB><<<blocks_of(count, kThreads / LPB), kThreads, 0, s>>>(b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag);
+}
+
+// AVBD_PRIMAL_VARIANT (tuning aid): "<lanes per body><min blocks per SM>": 43 (default; measured best on the 1M grid,
+// profiles/README.md), 82, 83, 42, 44, 23.
 void launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
                    const int* order, int count, SolveParams prm, float alpha, float* dxOut, Diag* diag) {
-    primal_colour<kLanesPerBody><<<blocks_of(count, kThreads / kLanesPerBody), kThreads, 0, s>>>(b, visitStart, visits, ms, fv, order, count, prm,
-                                                                                                   alpha, dxOut, diag);
+    static int variant = [] { const char* e = getenv("AVBD_PRIMAL_VARIANT"); return e ? atoi(e) : kLanesPerBody * 10 + 3; }();
+#define AVBD_PV(L, M) case L * 10 + M: launch_primal_variant<L, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag); break;
+    switch (variant) {
+        AVBD_PV(8, 2) AVBD_PV(8, 3) AVBD_PV(4, 2) AVBD_PV(4, 4) AVBD_PV(2, 3)
+        default: launch_primal_variant<4, 3>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag); break;
+    }
+#undef AVBD_PV
 }
 void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, const int* contactList, int nContacts, SolveParams prm, float alpha) {
     dual_contacts<<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, contactList, nContacts, prm, alpha);

@@ -256,7 +256,7 @@ def main():
                         colours=stats["colours"], iterations=iters, parallelism=f"independent-worlds x{world_size}",
                         l2="inputs larger than L2 (body + contact state > 126 MB)" if n_bodies > 300000 else "state is L2-resident; steady-state stepping, no flush"),
             steps_per_s=args.steps / (ms_max * 1e-3),
-            roofline=dict(bound="hbm", kernel="primal_colour<8>", achieved=primal_gbs, peak=peak, unit="GB/s", frac=primal_gbs / peak, traffic=None,
+            roofline=dict(bound="hbm", kernel="primal_colour<4,3>", achieved=primal_gbs, peak=peak, unit="GB/s", frac=primal_gbs / peak, traffic=None,
                           peak_source=peak_src, algorithmic_bytes_per_launch=primal_bytes / max(prof["primal_launches"], 1),
                           avg_launch_ms=prof["ms_primal"] / max(prof["primal_launches"], 1), share_of_step=prof["ms_primal"] / ms,
                           dual=dict(kernel="dual_contacts", achieved=dual_gbs, frac=dual_gbs / peak, share_of_step=prof["ms_dual"] / ms,
