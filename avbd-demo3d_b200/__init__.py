@@ -281,6 +281,14 @@ class World:
     def stage(self, name, *args):
         _check(getattr(self.L, "avbd_stage_" + name)(self.h, *args))
 
+    def pick(self, origin, direction):
+        """Solver::pick: (body index or -1, body-local hit point)."""
+        local = np.zeros(3, np.float32)
+        i = self.L.avbd_pick(self.h, _f(origin), _f(direction), local)
+        if i < -1:
+            _check(i)
+        return i, local
+
     def colours(self):
         col = np.zeros(max(self.n, 1), np.int32)
         k = C.c_int(0)

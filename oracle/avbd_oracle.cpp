@@ -1139,6 +1139,39 @@ void orc_solve6x6(const float* lhs, const float* rhs, float* out) {
     V6 x = schur6(A, V6{p3(rhs), p3(rhs + 3)});
     out[0] = x.l.x; out[1] = x.l.y; out[2] = x.l.z; out[3] = x.a.x; out[4] = x.a.y; out[5] = x.a.z;
 }
+// Solver::pick, solver.cpp:145-228.  Returns the creation index of the closest dynamic body hit, or -1.
+int orc_pick(void* h, const float* origin3, const float* dir3, float* local3) {
+    World& w = W(h);
+    const float eps = 1.0e-6f;
+    float bestT = FLT_MAX; int best = -1; V3 bestLocal = zero3();
+    V3 origin = p3(origin3), rd = p3(dir3);
+    float dl2 = len2(rd);
+    if (dl2 < eps) return -1;
+    rd = dvd(rd, sqrtf(dl2));
+    for (int i = (int)w.bodies.size() - 1; i >= 0; --i) {          // list order: newest first
+        const Body& b = w.bodies[i];
+        if (b.invMass <= 0.0f) continue;
+        Q4 inv = qconj(b.rot);
+        V3 lo = qrot(inv, sub(origin, b.pos)), ld = qrot(inv, rd), half = scl(b.size, 0.5f);
+        float tIn = 0.0f, tOut = FLT_MAX; bool hit = true;
+        for (int ax = 0; ax < 3; ++ax) {
+            float o = comp(lo, ax), d = comp(ld, ax), mn = -comp(half, ax), mx = comp(half, ax);
+            if (fabsf(d) < eps) { if (o < mn || o > mx) { hit = false; break; } continue; }
+            float invD = 1.0f / d, t0 = (mn - o) * invD, t1 = (mx - o) * invD;
+            if (t0 > t1) { float t = t0; t0 = t1; t1 = t; }
+            tIn = fmax2(tIn, t0); tOut = fmin2(tOut, t1);
+            if (tIn > tOut) { hit = false; break; }
+        }
+        if (!hit) continue;
+        float tHit = (tIn >= 0.0f) ? tIn : tOut;
+        if (tHit < 0.0f) continue;
+        if (tHit < bestT) { bestT = tHit; best = i; bestLocal = add(lo, scl(ld, tHit)); }
+    }
+    if (best < 0) return -1;
+    local3[0] = bestLocal.x; local3[1] = bestLocal.y; local3[2] = bestLocal.z;
+    return best;
+}
+
 void orc_solve3(const float* A, const float* b, float* out) {
     V3 x = ldl3(m3(p3(A), p3(A + 3), p3(A + 6)), p3(b)); out[0] = x.x; out[1] = x.y; out[2] = x.z;
 }

@@ -74,6 +74,7 @@ int   orc_overlap_pairs(void* w, int* pairs2, int cap);
 
 int   orc_collide(const float* a10, const float* b10, int* feats4, float* out40);   /* collision.cpp:420 */
 void  orc_solve6x6(const float* lhs36, const float* rhs6, float* out6);             /* solver.cpp:68 */
+int   orc_pick(void* w, const float* origin3, const float* dir3, float* local3);                /* solver.cpp:145 */
 void  orc_solve3(const float* A9, const float* b3, float* out3);                    /* maths.h:104 */
 
 #ifdef __cplusplus

@@ -237,6 +237,16 @@ void ref_solve6x6(const float* lhs, const float* rhs, float* out) {
     out[0] = x.l.x; out[1] = x.l.y; out[2] = x.l.z; out[3] = x.a.x; out[4] = x.a.y; out[5] = x.a.z;
 }
 
+// Solver::pick (solver.cpp:145): creation index of the hit body or -1.
+int ref_pick(void* h, const float* origin, const float* dir, float* local3) {
+    RefWorld* w = (RefWorld*)h;
+    vec3 local;
+    Rigid* b = w->solver->pick(v3(origin), v3(dir), local);
+    if (!b) return -1;
+    local3[0] = local.x; local3[1] = local.y; local3[2] = local.z;
+    return w->index[b];
+}
+
 // 3x3 LDL^T solve, maths.h:104.  A column-major.
 void ref_solve3(const float* A, const float* b, float* out) {
     mat3 M(v3(A), v3(A + 3), v3(A + 6));

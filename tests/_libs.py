@@ -80,6 +80,7 @@ class Oracle:
         self._fn("collide", C.c_int, [f32p, f32p, i32p, f32p])
         self._fn("solve6x6", None, [f32p, f32p, f32p])
         self._fn("solve3", None, [f32p, f32p, f32p])
+        self._fn("pick", C.c_int, [C.c_void_p, f32p, f32p, f32p])
         if kind == "port":
             self._fn("step_ordered", None, [C.c_void_p, i32p, C.c_int])
             self._fn("stage_broadphase", None, [C.c_void_p])
@@ -206,6 +207,11 @@ class Oracle:
         self._stage_primal(self.h, alpha, None if o is None else o.ctypes.data_as(C.c_void_p), 0 if o is None else len(o),
                            None if dx is None else dx.ctypes.data_as(C.c_void_p))
         return dx
+
+    def pick(self, origin, direction):
+        local = np.zeros(3, np.float32)
+        i = self._pick(self.h, _f(origin), _f(direction), local)
+        return i, local
 
     # -- stateless helpers
     def collide(self, a10, b10):

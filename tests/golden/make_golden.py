@@ -103,6 +103,22 @@ def main():
         out[f"traj/{name}/diag"] = dg
         for k, v in mf.items():
             out[f"traj/{name}/manifold_{k}"] = v
+    # 5. Stress1000 x600 (BASELINE.json config 3): diagnostics every 50 steps and the end state
+    o = Oracle("ref").create(); o.set_params(); o.load_scene("Stress1000")
+    dg = []
+    for s in range(600):
+        o.step(1)
+        if (s + 1) % 50 == 0:
+            d = o.diagnostics(); dg.append([d["maxPen"], d["maxViol"], d["maxLin"], d["maxAng"], d["maxLambda"], d["contacts"], d["manifolds"], d["dynBodies"]])
+    out["traj/Stress1000/diag"] = np.array(dg, np.float64)
+    out["traj/Stress1000/state_final"] = o.state()
+    # 6. Solver::pick on the settled Stress1000 pile
+    rays = np.concatenate([rng.uniform(-8, 8, (64, 1)), rng.uniform(5, 25, (64, 1)), rng.uniform(-8, 8, (64, 1)), rng.normal(size=(64, 3)) * 0.3 + np.array([0, -1, 0])], axis=1).astype(np.float32)
+    hits, locs = np.zeros(64, np.int32), np.zeros((64, 3), np.float32)
+    for t in range(64):
+        hits[t], locs[t] = o.pick(rays[t, :3], rays[t, 3:])
+    out.update({"pick/rays": rays, "pick/hit": hits, "pick/local": locs})
+    o.close()
     out["pile40/bodies"] = np.array([list(b["size"]) + [b["density"], b["friction"]] + list(b["pos"]) + list(b["quat"]) + list(b["lin"]) + list(b["ang"]) for b in pile], np.float64)
     np.savez_compressed(os.path.join(HERE, "golden.npz"), **out)
     print("wrote", os.path.join(HERE, "golden.npz"), os.path.getsize(os.path.join(HERE, "golden.npz")), "bytes,", len(out), "arrays")

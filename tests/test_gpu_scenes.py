@@ -1,0 +1,199 @@
+"""Whole-scene parity of the CUDA path: trajectories (statistical, SURVEY.md section 8d tolerances), user forces,
+Solver::pick, the host C++ CLI, and ensemble batching (bit-identical across partitions).  Needs a GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from _libs import PKG_DIR, ROOT, Oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))
+
+REST_TOL = 1e-3          # per-body rest height, mean over the last 100 steps (reference vs reversed-order reference: 5e-4)
+PEN_TOL = 1e-3           # max penetration at rest
+
+
+def run_scene(avbd, name, steps, tail=100):
+    from avbd_demo3d_b200 import scenes
+    w = avbd.World()
+    scenes.load(w, scenes.scene(name))
+    w.step(steps - tail)
+    ys = []
+    for _ in range(tail):
+        w.step(1)
+        ys.append(w.state()[:, 1].copy())
+    return w, np.mean(ys, axis=0)
+
+
+def oracle_rest(name, steps, tail=100):
+    o = Oracle("port").create()
+    o.load_scene(name)
+    o.step(steps - tail)
+    ys = []
+    for _ in range(tail):
+        o.step(1)
+        ys.append(o.state()[:, 1].copy())
+    return o, np.mean(ys, axis=0)
+
+
+def test_two_block_drop_settles_like_the_reference(avbd):
+    """BASELINE.json config 0: both boxes rest at y = 0.5100, 2 manifolds / 8 contacts, zero velocity by step 299."""
+    w, y = run_scene(avbd, "TwoBlockDrop", 300, tail=20)
+    st, d = w.state(), w.diagnostics()
+    ref = GOLD["traj/TwoBlockDrop/state"][-1]
+    assert np.abs(st[1:, 1] - ref[1:, 1]).max() < REST_TOL and np.abs(st[1:, 1] - 0.51).max() < REST_TOL
+    assert d["manifolds"] == 2 and d["contacts"] == 8 and d["maxPen"] <= PEN_TOL
+    assert np.abs(st[:, 7:]).max() < 1e-3
+    assert d["nanEvents"] == 0
+    w.close()
+
+
+@pytest.mark.parametrize("name,steps", [("Stack", 600), ("Pyramid", 600)])
+def test_stacked_scenes_rest_heights_and_counts(avbd, name, steps):
+    """BASELINE.json config 1: rest heights (mean of the last 100 steps) within 1e-3 of the reference's, equal
+    manifold / contact counts, no penetration at rest, kinetic-energy proxy no worse than 2x the reference's."""
+    w, y = run_scene(avbd, name, steps)
+    o, yo = oracle_rest(name, steps)
+    d, do = w.diagnostics(), o.diagnostics()
+    assert np.abs(y - yo).max() < REST_TOL, float(np.abs(y - yo).max())
+    assert (d["manifolds"], d["contacts"]) == (do["manifolds"], do["contacts"]), (d, do)
+    assert d["maxPen"] <= PEN_TOL
+    ke = lambda s: float((s[:, 7:10] ** 2).sum())
+    assert ke(w.state()) <= 2.0 * ke(o.state()) + 1e-3, (ke(w.state()), ke(o.state()))
+    assert d["nanEvents"] == 0
+    w.close(); o.close()
+
+
+def test_stress1000_statistics(avbd):
+    """BASELINE.json config 2 (iterations=20, beta=30000, gamma=0.995), 600 steps, against the reference's end state
+    (golden fixture): contacts 4367 +-5 %, manifolds 1694 +-6 %, escaped bodies <= 30, layer histogram +-10 % of N."""
+    from avbd_demo3d_b200 import scenes
+    w = avbd.World()
+    scenes.load(w, scenes.scene("Stress1000"))
+    peak = 0.0
+    for _ in range(60):
+        w.step(10)
+        peak = max(peak, w.diagnostics()["maxPen"])
+    st, d = w.state(), w.diagnostics()
+    ref, dref = GOLD["traj/Stress1000/state_final"], GOLD["traj/Stress1000/diag"][-1]
+    assert abs(d["contacts"] - dref[5]) <= 0.05 * dref[5], (d["contacts"], dref[5])
+    assert abs(d["manifolds"] - dref[6]) <= 0.06 * dref[6], (d["manifolds"], dref[6])
+    assert d["dynBodies"] == 1000 and d["nanEvents"] == 0
+    escaped = int((st[1:, 1] < -0.5).sum())
+    assert escaped <= 30, escaped
+    bins = np.arange(-0.5, 14.5, 1.0)
+    h, href = np.histogram(st[1:, 1], bins)[0], np.histogram(ref[1:, 1], bins)[0]
+    assert np.abs(h - href).max() <= 100, (h, href)
+    assert peak < 2.0          # reference peak maxPen is 1.10
+    w.close()
+
+
+def _jointed(o):
+    o.add_body((20, 1, 20), 0.0, 0.5, (0, -0.5, 0))
+    o.add_body((1, 1, 1), 1.0, 0.5, (0, 3, 0))
+    o.add_body((1, 1, 1), 1.0, 0.5, (3, 3, 0))
+    o.add_body((1, 1, 1), 1.0, 0.5, (3, 5, 0))
+    o.add_body((1, 1, 1), 1.0, 0.5, (-3, 0.5, 0))
+    o.add_body((1, 1, 1), 1.0, 0.5, (-3.2, 0.6, 0.1))
+    o.add_joint(-1, 1, (0, 3.5, 0))
+    o.add_spring(2, 3, (0, 0.5, 0), (0, -0.5, 0), 1000.0, 1.0)
+    o.add_joint(-1, 2, (3, 3.5, 0))
+    o.add_ignore(4, 5)
+
+
+def test_joint_spring_ignore_match_reference(avbd):
+    """Joint (body-world weld), Spring (soft row, no dual) and IgnoreCollision (pair exclusion) against the reference
+    trajectory in the golden fixture."""
+    w = avbd.World()
+    _jointed(w)
+    ref = GOLD["traj/Jointed/state"]
+    k = 0
+    for s in range(120):
+        w.step(1)
+        if (s + 1) % 30 == 0 or s == 119:
+            st = w.state()
+            assert np.abs(st[[1, 2, 3], :7] - ref[k][[1, 2, 3], :7]).max() < 2e-3, (s, np.abs(st[:, :7] - ref[k][:, :7]).max())
+            k += 1
+    st = w.state()
+    assert np.abs(st[1, :3] - np.array([0, 3, 0])).max() < 5e-3                  # welded to the world
+    ints, _, _, _ = w.manifolds_raw()
+    pairs = {(int(a), int(b)) for a, b, _ in ints}
+    assert (5, 4) not in pairs                                                   # IgnoreCollision suppressed the manifold
+    assert (4, 0) in pairs and (5, 0) in pairs                                   # while both still collide with the ground
+    ext = float(st[2, 1] - st[3, 1]) - 1.0 - 1.0        # body centres are one unit from their anchors
+    assert abs(ext - 0.01) < 2e-3, ext                   # k=1000, m=1, g=10 hangs at 0.0100
+    w.close()
+
+
+def test_pick_matches_reference(avbd):
+    w = avbd.World()
+    ref = GOLD["traj/Stress1000/state_final"]
+    from avbd_demo3d_b200 import scenes
+    scenes.load(w, scenes.scene("Stress1000"))
+    w.set_state(ref)
+    rays, hits, locs = GOLD["pick/rays"], GOLD["pick/hit"], GOLD["pick/local"]
+    assert (hits >= 0).sum() > 30
+    for t in range(len(rays)):
+        i, local = w.pick(rays[t, :3], rays[t, 3:])
+        assert i == hits[t], (t, i, hits[t])
+        if i >= 0:
+            assert np.abs(local - locs[t]).max() < 1e-5
+    assert w.pick((0, 50, 0), (0, 0, 0))[0] == -1
+    w.close()
+
+
+def test_host_cli_matches_reference_cli(avbd):
+    """The C++17 host mirror end to end: same flags, same stdout format; free fall (first 15 steps) prints identically
+    to the reference and the scene settles at the reference's rest heights."""
+    exe = os.path.join(PKG_DIR, "host", "avbd_demo3d")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", os.path.join(PKG_DIR, "host")], check=True)
+    mine = subprocess.run([exe, "--nogfx", "--scene", "TwoBlockDrop", "--steps", "300"], capture_output=True, text=True, check=True).stdout.splitlines()
+    want = subprocess.run([os.path.join(ROOT, "oracle", "avbd_oracle_cli"), "--nogfx", "--scene", "TwoBlockDrop", "--steps", "300"],
+                          capture_output=True, text=True, check=True).stdout.splitlines()
+    assert len(mine) == len(want) == 1 + 300 * 6
+    assert mine[0] == want[0] == "Running in headless mode: scene 'TwoBlockDrop', steps=300"
+    assert mine[: 1 + 15 * 6] == want[: 1 + 15 * 6]
+    body = lambda line: [float(x) for x in line.split("Pos(")[1].split(")")[0].split(",")]
+    for a, b in zip(mine[-5:-2], want[-5:-2]):
+        assert a.split(":")[0] == b.split(":")[0]                 # same body ids in the same (newest first) order
+        assert abs(body(a)[1] - body(b)[1]) < REST_TOL
+    assert mine[-1].split("maxPen")[0] == want[-1].split("maxPen")[0]     # manifolds=2 contacts=8 dynBodies=2
+
+
+def test_host_cli_unknown_scene_falls_back_to_empty(avbd):
+    exe = os.path.join(PKG_DIR, "host", "avbd_demo3d")
+    out = subprocess.run([exe, "--nogfx", "--scene", "NoSuchScene", "--steps", "2"], capture_output=True, text=True, check=True).stdout
+    assert "scene 'Empty'" in out and "manifolds=0 contacts=0 dynBodies=0" in out
+
+
+# --------------------------------------------------------------------------- ensembles
+def _ensemble_states(avbd, base, worlds, first, steps):
+    from avbd_demo3d_b200 import scenes
+    w = avbd.World()
+    scenes.load(w, scenes.ensemble(base, worlds, first_world=first))
+    w.step(steps)
+    st, dg = w.state(), w.world_diagnostics()
+    w.close()
+    return st, dg
+
+
+@pytest.mark.parametrize("name,steps", [("Stack", 80), ("Pyramid", 40)])
+def test_ensemble_is_bit_identical_across_partitions(avbd, name, steps):
+    """worlds are independent, so a world's trajectory may not depend on how the batch is split
+    across GPUs: 8 worlds in one batch == two batches of 4 == each world alone, bit for bit."""
+    from avbd_demo3d_b200 import scenes
+    base = scenes.scene(name)
+    n = len(base["size"])
+    whole, dwhole = _ensemble_states(avbd, base, 8, 0, steps)
+    lo, dlo = _ensemble_states(avbd, base, 4, 0, steps)
+    hi, dhi = _ensemble_states(avbd, base, 4, 4, steps)
+    assert whole[: 4 * n].tobytes() == lo.tobytes()
+    assert whole[4 * n:].tobytes() == hi.tobytes()
+    assert dwhole[:4] == dlo and dwhole[4:] == dhi
+    solo, dsolo = _ensemble_states(avbd, base, 1, 5, steps)
+    assert whole[5 * n: 6 * n].tobytes() == solo.tobytes() and dwhole[5] == dsolo[0]
+    assert len({whole[k * n + 1: (k + 1) * n].tobytes() for k in range(8)}) == 8          # the worlds really differ
+    assert dwhole[0]["activeManifolds"] > 0 and dwhole[0]["dynamicBodies"] == n - 1
