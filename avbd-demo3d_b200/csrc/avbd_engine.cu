@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -93,7 +94,8 @@ struct avbd_world {
     // graph
     DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
-    int2 hColRange[64]; int nColours = 0; bool graphValid = false;
+    int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
+    long long graphReuses = 0; int persistentMaxBodies = 20000; unsigned* dBarrier = nullptr;
 
     // user forces
     std::vector<JointRec> hJoints; std::vector<SpringRec> hSprings; std::vector<HostForce> hForces;
@@ -360,7 +362,7 @@ int run_collide(avbd_world* w) {
         TRY(w->ensure_manifolds(nxt, nSurv));
         TRY(w->mcount.ensure(nSurv, false, s)); TRY(w->contactStart.ensure(nSurv, false, s)); TRY(w->contactList.ensure((size_t)nSurv * 4, false, s));
         np_build<<<blocks_for(nSurv), kThreads, 0, s>>>(w->bview(), w->candSorted.p, w->candInfo.p, w->survP.p, nSurv, w->keyShift,
-                                                          w->mset(w->cur), w->nM, w->mset(nxt), w->mcount.p, w->prm);
+                                                          w->mset(w->cur), w->nM, w->mset(nxt), w->mcount.p, w->prm, w->dCnt);
         w->launches++;
         // dense list of live contacts (the dual's work list; also sizes the visit list)
         TRY(exclusive_scan(w, w->mcount.p, w->contactStart.p, nSurv));
@@ -371,13 +373,15 @@ int run_collide(avbd_world* w) {
     } else {
         w->nContacts = 0;
     }
+    // adjacency, colouring and visit lists only depend on (pair, contact count) per slot: keep them when nothing moved
+    bool sameTopology = w->graphValid && nSurv == w->nM && nSurv > 0 && !w->hCnt->topoChanged && !w->forceRegraph;
     w->cur = nxt; w->nM = nSurv;
     ForceView fv = w->fview();
     if (fv.nJoints + fv.nSprings > 0) {
         decay_user_forces<<<blocks_for(fv.nJoints + fv.nSprings), kThreads, 0, s>>>(fv, w->prm);
         w->launches++;
     }
-    w->graphValid = false;
+    w->graphValid = sameTopology;
     if (w->timed) cudaEventRecord(w->ev[2], s);
     CK(cudaGetLastError());
     return 0;
@@ -437,6 +441,8 @@ int run_colour(avbd_world* w) {
     CK(cudaMemcpyAsync(w->hColRange, w->colRange.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
     TRY(read_counters(w));
     w->nColours = w->hCnt->nColours;
+    w->maxColourCount = 0;
+    for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;
@@ -491,16 +497,25 @@ int step_once(avbd_world* w) {
     TRY(run_collide(w));
     TRY(run_predict(w));
     if (w->timed) cudaEventRecord(w->ev[3], s);
-    TRY(run_colour(w));
+    if (!w->graphValid) TRY(run_colour(w)); else w->graphReuses++;
     if (w->timed) cudaEventRecord(w->ev[4], s);
     int total = w->prm.iterations + (w->prm.postStabilize ? 1 : 0);
     bool prof = w->profiling;
+    ForceView fvAll = w->fview();
+    bool persistent = !prof && w->nColours > 0 && w->nDyn <= w->persistentMaxBodies && fvAll.nJoints + fvAll.nSprings == 0;
+    if (persistent) {
+        // small world: the whole iteration loop in one cooperative launch (grid barriers instead of kernel boundaries)
+        unsigned* barrier = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(w->dCnt + 1) + 8);
+        persistent = launch_solve_loop(s, w->bview(), w->visitStart.p, w->visits.p, w->mset(w->cur), fvAll, w->colOrder.p, w->colRange.p,
+                                       w->nColours, w->maxColourCount, w->contactList.p, w->nContacts, w->prm, w->dDiag.p, barrier);
+        if (persistent) w->launches++; else cudaGetLastError();
+    }
     if (prof) {
         while ((int)w->pev.size() < 2 * total + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); w->pev.push_back(e); }
         cudaEventRecord(w->pev[0], s);
     }
     int duals = 0;
-    for (int it = 0; it < total; ++it) {
+    for (int it = 0; it < total && !persistent; ++it) {
         float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
         TRY(run_primal(w, a, nullptr));
         if (prof) cudaEventRecord(w->pev[2 * it + 1], s);
@@ -567,6 +582,8 @@ avbd_world* avbd_world_create(int device) {
         return nullptr;
     }
     for (auto& e : w->ev) cudaEventCreate(&e);
+    if (const char* e = std::getenv("AVBD_PERSISTENT_MAX_BODIES")) w->persistentMaxBodies = std::atoi(e);
+    if (const char* e = std::getenv("AVBD_FORCE_REGRAPH")) w->forceRegraph = std::atoi(e) != 0;
     std::memset(w->hCnt, 0, sizeof(Counters));
     avbd_default_params(w);
     return w;
@@ -966,7 +983,7 @@ int avbd_download_pairs(avbd_world* w, int* pairs, int cap) {
 
 int avbd_stage_collide(avbd_world* w) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return run_collide(w); }
 int avbd_stage_predict(avbd_world* w) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return run_predict(w); }
-int avbd_stage_colour(avbd_world* w) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return run_colour(w); }
+int avbd_stage_colour(avbd_world* w) { if (!w) return fail(AVBD_ERR_ARG, "null world"); CK(cudaSetDevice(w->device)); return w->graphValid ? 0 : run_colour(w); }
 
 int avbd_download_colours(avbd_world* w, int* colour_of, int* num_colours) {
     if (!w) return fail(AVBD_ERR_ARG, "null world");

@@ -27,8 +27,13 @@ struct GridView {
     const int* largeList; const int* worldLargeStart;
 };
 
+// Bucket of a grid cell.  Cells are grouped in 4x4x4 blocks: the block is hashed, the position inside the block
+// fills the low 6 bits, so the 64 cells of a block — and the bodies in them after the sort — stay contiguous and
+// the 27-cell sweep of neighbouring bodies touches neighbouring memory (a plain per-cell hash scatters them).
 __device__ __forceinline__ unsigned cell_hash(int x, int y, int z, int w) {
-    return ((unsigned)x * 73856093u) ^ ((unsigned)y * 19349663u) ^ ((unsigned)z * 83492791u) ^ ((unsigned)w * 2654435761u);
+    unsigned h = ((unsigned)(x >> 2) * 73856093u) ^ ((unsigned)(y >> 2) * 19349663u) ^ ((unsigned)(z >> 2) * 83492791u) ^ ((unsigned)w * 2654435761u);
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+    return (h << 6) | (unsigned)((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
 }
 __device__ __forceinline__ float body_radius(float4 size) { return len(xyz(size)) * 0.5f; }   // rigid.cpp:28
 __device__ __forceinline__ int3 cell_of(float4 pos, float cell) {
@@ -195,7 +200,7 @@ __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int 
 // slot, carrying lambda / penalty / stick anchors over from last step's
 // manifold of the same pair, then apply the per-step warm-start decay.
 __global__ void np_build(BodyView b, const unsigned long long* cand, const int* info, const int* survP, int nSurvive,
-                         int keyShift, ManifoldSet old, int nOld, ManifoldSet out, int* mcount, SolveParams prm) {
+                         int keyShift, ManifoldSet old, int nOld, ManifoldSet out, int* mcount, SolveParams prm, Counters* cnt) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nSurvive) return;
     int p = survP[s];
@@ -215,6 +220,7 @@ __global__ void np_build(BodyView b, const unsigned long long* cand, const int* 
     out.key[s] = k;
     out.hdr[s] = make_int4(a, c, nm.n, __float_as_int(mu));
     mcount[s] = nm.n;
+    if (slot != s || om.n != nm.n) cnt->topoChanged = 1;      // same-value racing stores are fine
     for (int i = 0; i < 4; ++i) {
         if (i < nm.n) store_contact(out, s * 4 + i, nm.ct[i]);
         else {

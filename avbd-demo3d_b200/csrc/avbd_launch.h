@@ -29,6 +29,11 @@ void launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4
                    const int* order, int count, SolveParams prm, float alpha, float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live contacts in contactList.
 void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, const int* contactList, int nContacts, SolveParams prm, float alpha);
+// Small worlds: the whole iteration loop (solver.cpp:340-431, manifold rows only) in ONE cooperative launch.
+// Returns false if the launch was refused (caller falls back to per-colour launches).
+bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
+                       const int2* colRange, int nColours, int maxColourCount, const int* contactList, int nContacts, SolveParams prm,
+                       Diag* diag, unsigned* barrier);
 void launch_dual_user_forces(cudaStream_t s, BodyView b, ForceView fv, SolveParams prm);
 void launch_solve6_batch(cudaStream_t s, const float* lhs36, const float* rhs6, int n, float* out6);
 

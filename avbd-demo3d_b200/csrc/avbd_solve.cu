@@ -68,20 +68,29 @@ __device__ void accumulate_user_forces(BodySystem& s, const ForceView& fv, const
     }
 }
 
-// One colour of the primal sweep (solver.cpp:344-409), in two phases so both are lane-dense:
+// Loads of data another CTA may have written earlier in the SAME launch (persistent loop): bypass L1.
+template <bool COH> __device__ __forceinline__ float4 ld4(const float4* p) { return COH ? __ldcg(p) : *p; }
+template <bool COH> __device__ __forceinline__ BodyPose load_pose(const BodyPose* p) {
+    BodyPose r; r.pos = ld4<COH>(&p->pos); r.rot = ld4<COH>(&p->rot); return r;
+}
+template <bool COH> __device__ __forceinline__ ContactState load_contact_c(const ManifoldSet& ms, int ci) {
+    return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ld4<COH>(ms.cL + ci), ld4<COH>(ms.cP + ci));
+}
+
+// One tile (kThreads/LPB bodies of one colour) of the primal sweep (solver.cpp:344-409), in two phases so both are
+// lane-dense:
 //   phase 1  LPB lanes per body walk the body's run of contact visits (lane l takes visits l, l+LPB, ...):
 //            computeConstraint + 3 rows each, then a shuffle reduction leaves the 27 sums in lane 0, which
 //            parks them in shared memory;
 //   phase 2  one lane per body (the first kThreads/LPB threads = full warps): inertial terms, Schur solve,
 //            pose update.
-template <int LPB, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) primal_colour(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
-                                                          ManifoldSet ms, ForceView fv, const int* __restrict__ order, int count,
-                                                          SolveParams prm, float alpha, float* dxOut, Diag* diag) {
+template <int LPB, bool COH>
+__device__ __forceinline__ void primal_tile(const BodyView& b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
+                                            const ManifoldSet& ms, const ForceView& fv, const int* __restrict__ order, int count, int tile,
+                                            const SolveParams& prm, float alpha, float* dxOut, Diag* diag, float* sSys) {
     constexpr int BPB = kThreads / LPB;
-    __shared__ float sSys[BPB * 27];                 // stride 27 is odd: conflict-free in phase 2
     int g = threadIdx.x / LPB, lane = threadIdx.x % LPB;
-    int gid = blockIdx.x * BPB + g;
+    int gid = tile * BPB + g;
     bool live = gid < count;
     BodySystem sys; sys.clear();
     if (live) {
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_colour(BodyView b, cons
         int v0 = visitStart[i], v1 = visitStart[i + 1];
         bool userForces = fv.adjStart != nullptr && lane == 0 && fv.adjStart[i + 1] > fv.adjStart[i];
         if (v0 + lane < v1 || userForces) {
-            BodyPose self = b.pose[i];
+            BodyPose self = load_pose<COH>(b.pose + i);
             V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
             float invMassSelf = self.pos.w;
             V3 I = xyz(b.aux[i].inert);
@@ -97,8 +106,8 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_colour(BodyView b, cons
             for (int v = v0 + lane; v < v1; v += LPB) {
                 int4 e = visits[v];
                 int ci = e.x; bool isA = e.z != 0;
-                BodyPose po = b.pose[e.y];
-                ContactState cs = load_contact(ms, ci);
+                BodyPose po = load_pose<COH>(b.pose + e.y);
+                ContactState cs = load_contact_c<COH>(ms, ci);
                 ContactEval ev;
                 float mu = __int_as_float(e.w);
                 if (isA) contact_constraint(pos, rot, invMassSelf, xyz(po.pos), quat(po.rot), po.pos.w, mu, alpha, cs, ev);
@@ -120,46 +129,103 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_colour(BodyView b, cons
         for (int k = 0; k < 9; ++k) o[12 + k] = sys.la[k];
     }
     __syncthreads();
-    if (threadIdx.x >= BPB) return;
-    gid = blockIdx.x * BPB + threadIdx.x;
-    if (gid >= count) return;
-    int i = order[gid];
-    BodyPose self = b.pose[i];
-    BodyAux aux = b.aux[i];
-    V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
-    BodySystem own; M3 invIw;
-    body_self_system(pos, rot, aux, prm.dt, own, invIw);
-    const float* o = sSys + threadIdx.x * 27;
+    gid = tile * BPB + threadIdx.x;
+    if (threadIdx.x < BPB && gid < count) {
+        int i = order[gid];
+        BodyPose self = load_pose<COH>(b.pose + i);
+        BodyAux aux = b.aux[i];
+        V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
+        BodySystem own; M3 invIw;
+        body_self_system(pos, rot, aux, prm.dt, own, invIw);
+        const float* o = sSys + threadIdx.x * 27;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { own.rl[k] += o[k]; own.ra[k] += o[3 + k]; }
+        for (int k = 0; k < 3; ++k) { own.rl[k] += o[k]; own.ra[k] += o[3 + k]; }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { own.ll[k] += o[6 + k]; own.aa[k] += o[21 + k]; }
+        for (int k = 0; k < 6; ++k) { own.ll[k] += o[6 + k]; own.aa[k] += o[21 + k]; }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) own.la[k] += o[12 + k];
-    V3 dl, da;
-    solve_body_system(own, dl, da);
-    int ev = apply_body_update(pos, rot, dl, da);
-    BodyPose out; out.pos = f4(pos, self.pos.w); out.rot = f4(rot);
-    b.pose[i] = out;
-    if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
-    if (ev) atomicAdd(&diag[b.worldId[i]].nanEvents, ev);
+        for (int k = 0; k < 9; ++k) own.la[k] += o[12 + k];
+        V3 dl, da;
+        solve_body_system(own, dl, da);
+        int ev = apply_body_update(pos, rot, dl, da);
+        BodyPose out; out.pos = f4(pos, self.pos.w); out.rot = f4(rot);
+        b.pose[i] = out;
+        if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
+        if (ev) atomicAdd(&diag[b.worldId[i]].nanEvents, ev);
+    }
+}
+
+template <int LPB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) primal_colour(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
+                                                                ManifoldSet ms, ForceView fv, const int* __restrict__ order, int count,
+                                                                SolveParams prm, float alpha, float* dxOut, Diag* diag) {
+    __shared__ float sSys[(kThreads / LPB) * 27];    // stride 27 is odd: conflict-free in phase 2
+    primal_tile<LPB, false>(b, visitStart, visits, ms, fv, order, count, blockIdx.x, prm, alpha, dxOut, diag, sSys);
 }
 
 // ------------------------------------------------------------------ dual
-// One thread per LIVE contact (solver.cpp:411-430 for manifold rows).
-__global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSet ms, const int* __restrict__ contactList, int nContacts,
-                                                          SolveParams prm, float alpha) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nContacts) return;
-    int ci = contactList[t];
+// One LIVE contact (solver.cpp:411-430 for manifold rows).
+template <bool COH>
+__device__ __forceinline__ void dual_one(const BodyView& b, const ManifoldSet& ms, int ci, const SolveParams& prm, float alpha) {
     int4 h = ms.hdr[ci >> 2];
-    BodyPose pa = b.pose[h.x], pb = b.pose[h.y];
-    ContactState cs = load_contact(ms, ci);
+    BodyPose pa = load_pose<COH>(b.pose + h.x), pb = load_pose<COH>(b.pose + h.y);
+    ContactState cs = load_contact_c<COH>(ms, ci);
     ContactEval ev;
     contact_constraint(xyz(pa.pos), quat(pa.rot), pa.pos.w, xyz(pb.pos), quat(pb.rot), pb.pos.w, __int_as_float(h.w), alpha, cs, ev);
     dual_contact(cs, ev, prm.beta);
     ms.cL[ci] = pack_lambda(cs);
     ms.cP[ci] = pack_penalty(cs);
+}
+
+__global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSet ms, const int* __restrict__ contactList, int nContacts,
+                                                          SolveParams prm, float alpha) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nContacts) dual_one<false>(b, ms, contactList[t], prm, alpha);
+}
+
+// ------------------------------------------------------------------ persistent iteration loop (small worlds)
+// A Stress1000-sized world is launch-latency bound: iterations x (colours + dual) dependent launches of a few
+// hundred threads each.  This kernel runs the WHOLE loop of solver.cpp:340-431 in one cooperative launch; colours
+// and the dual pass are separated by a grid-wide barrier instead of a kernel boundary.  Data other CTAs write
+// between barriers (poses, lambda, penalty) is read with ld.global.cg.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int LPB>
+__global__ void __launch_bounds__(kThreads, 2) solve_loop_persistent(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
+                                                                     ManifoldSet ms, ForceView fv, const int* __restrict__ order,
+                                                                     const int2* __restrict__ colRange, int nColours,
+                                                                     const int* __restrict__ contactList, int nContacts, SolveParams prm,
+                                                                     Diag* diag, unsigned* barrier) {
+    constexpr int BPB = kThreads / LPB;
+    __shared__ float sSys[BPB * 27];
+    unsigned target = 0;
+    int total = prm.iterations + (prm.postStabilize ? 1 : 0);
+    for (int it = 0; it < total; ++it) {
+        float alpha = prm.postStabilize ? (it < prm.iterations ? 1.0f : 0.0f) : prm.alpha;      // solver.cpp:340-342
+        for (int c = 0; c < nColours; ++c) {
+            int2 r = colRange[c];
+            int count = r.y - r.x;
+            for (int tile = blockIdx.x; tile * BPB < count; tile += gridDim.x) {
+                primal_tile<LPB, true>(b, visitStart, visits, ms, fv, order + r.x, count, tile, prm, alpha, nullptr, diag, sSys);
+                __syncthreads();
+            }
+            grid_barrier(barrier, target);
+        }
+        if (it < prm.iterations) {
+            for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nContacts; t += gridDim.x * blockDim.x)
+                dual_one<true>(b, ms, contactList[t], prm, alpha);
+            grid_barrier(barrier, target);
+        }
+    }
 }
 
 __global__ void dual_user_forces(BodyView b, ForceView fv, SolveParams prm) {
@@ -246,6 +312,27 @@ void launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4
     }
 #undef AVBD_PV
 }
+bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
+                       const int2* colRange, int nColours, int maxColourCount, const int* contactList, int nContacts, SolveParams prm,
+                       Diag* diag, unsigned* barrier) {
+    constexpr int LPB = kLanesPerBody;
+    static int maxBlocks = [] {
+        int dev = 0, sms = 0, perSm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, solve_loop_persistent<LPB>, kThreads, 0);
+        return sms * (perSm < 1 ? 1 : perSm);
+    }();
+    int want = blocks_of(maxColourCount, kThreads / LPB);
+    int wantDual = blocks_of(nContacts, kThreads);
+    int grid = want > wantDual ? want : wantDual;
+    if (grid > maxBlocks) grid = maxBlocks;
+    if (grid < 1) grid = 1;
+    cudaMemsetAsync(barrier, 0, sizeof(unsigned), s);
+    void* args[] = {&b, &visitStart, &visits, &ms, &fv, &order, &colRange, &nColours, &contactList, &nContacts, &prm, &diag, &barrier};
+    return cudaLaunchCooperativeKernel((void*)solve_loop_persistent<LPB>, dim3(grid), dim3(kThreads), args, 0, s) == cudaSuccess;
+}
+
 void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, const int* contactList, int nContacts, SolveParams prm, float alpha) {
     dual_contacts<<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, contactList, nContacts, prm, alpha);
 }

@@ -71,7 +71,7 @@ struct Counters {             // device-side sizes produced by one stage, consum
     int nColours;
     int nContacts;            // live contacts this step (dense contact list length)
     int overflow;             // bit0 pairs, bit1 manifolds, bit2 colours
-    int pad[1];
+    int topoChanged;          // set by np_build when a manifold's slot or contact count differs from last step
 };
 
 } // namespace avbd
