@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavbd_b200.so")
+LIB_PATH = os.environ.get("AVBD_B200_LIB") or os.path.join(_HERE, "libavbd_b200.so")   # override: A/B builds while tuning
 FLT_MAX = 3.4028234663852886e38
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")

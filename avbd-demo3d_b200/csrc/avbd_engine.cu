@@ -105,7 +105,7 @@ struct avbd_world {
     // counters / diagnostics
     Counters* dCnt = nullptr; Counters* hCnt = nullptr;
     DevBuf<Diag> dDiag; Diag* hDiag = nullptr; size_t hDiagCap = 0;
-    DevBuf<float> dx;
+    DevBuf<float> dx, sums;
     DevBuf<char> temp;
 
     // per-kernel profiling (avbd_set_profiling): events around every primal sweep and dual pass
@@ -413,14 +413,6 @@ int run_colour(avbd_world* w) {
     } else {
         TRY(w->bList.ensure(1, false, s));
     }
-    // per-body runs of contact visits (the primal's work list)
-    TRY(w->visitCount.ensure((size_t)n + 1, false, s)); TRY(w->visitStart.ensure((size_t)n + 1, false, s));
-    TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
-    CK(cudaMemsetAsync(w->visitCount.p, 0, sizeof(int) * ((size_t)n + 1), s));
-    visit_count<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
-    TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, n + 1));
-    visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitStart.p, w->visits.p);
-    w->launches += 2;
     colour_init<<<blocks_for(n), kThreads, 0, s>>>(w->flags.p, n, w->colour.p);
     w->launches++;
     ForceView fv = w->fview();
@@ -443,6 +435,14 @@ int run_colour(avbd_world* w) {
     w->nColours = w->hCnt->nColours;
     w->maxColourCount = 0;
     for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);
+    // contact visits in colour order (the primal's work list): visitStart[k] belongs to colOrder[k]
+    TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
+    TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
+    CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
+    visit_count<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
+    TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
+    visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitStart.p, w->aux.p, w->visits.p);
+    w->launches += 2;
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;
@@ -453,11 +453,13 @@ int run_primal(avbd_world* w, float alpha, float* dxDev) {
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
+    TRY(w->sums.ensure((size_t)std::max(1, w->maxColourCount) * 28, false, s));
+    float avgVisits = w->nDyn > 0 ? 2.0f * (float)w->nContacts / (float)w->nDyn : 0.0f;   // upper bound: static endpoints do not visit
     for (int c = 0; c < w->nColours; ++c) {
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
-        launch_primal(s, w->bview(), w->visitStart.p, w->visits.p, ms, fv, w->colOrder.p + first, count, w->prm, alpha, dxDev, w->dDiag.p);
-        w->launches++;
+        w->launches += launch_primal(s, w->bview(), w->visitStart.p + first, w->visits.p, ms, fv, w->colOrder.p + first, count, avgVisits, w->prm, alpha,
+                                     w->sums.p, dxDev, w->dDiag.p);
     }
     CK(cudaGetLastError());
     return 0;
@@ -602,7 +604,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
-    w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release();
+    w->dDiag.release(); w->dx.release(); w->sums.release(); w->temp.release(); w->stateDev.release();
     w->mcount.release(); w->contactStart.release(); w->contactList.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);

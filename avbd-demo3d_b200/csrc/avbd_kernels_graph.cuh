@@ -32,8 +32,8 @@ __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, in
 // ------------------------------------------------------------------ dense contact / visit lists
 // Manifold slots hold up to 4 contacts but the live count varies (about 2 on a settled box grid), so the
 // per-iteration kernels never walk slots: the dual walks `contactList` (live contact ids ci = 4m+c) and the
-// primal walks, per dynamic body, a run of `visits` {ci, other body, body-is-A, friction bits} — one entry per
-// live contact of every manifold touching the body, built once per step.
+// primal walks, per dynamic body, a run of `visits` — one entry per live contact of every manifold touching the
+// body, rebuilt whenever the topology changes.
 __global__ void contact_list_fill(const int4* hdr, const int* contactStart, int nM, int* contactList, Counters* cnt) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nM) return;
@@ -41,24 +41,30 @@ __global__ void contact_list_fill(const int4* hdr, const int* contactStart, int 
     for (int c = 0; c < n; ++c) contactList[s + c] = 4 * m + c;
     if (m == nM - 1) cnt->nContacts = s + n;
 }
-__global__ void visit_count(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount) {
+// Both run over the COLOUR-SORTED body order (colOrder[k], k = 0..nDyn-1): visitStart[k] is indexed by that position, so the
+// visits of the bodies of one colour tile are one contiguous run of `visits` and a tile can be walked one visit per thread.
+// Entry: {contact id, other body, (visiting body << 2) | anisotropic-inertia << 1 | body-is-A, friction bits}.
+__global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
-    int i = dynList[t];
+    int i = colOrder[t];
     int4 rg = adjRange[i];
     int k = 0;
     for (int m = rg.x; m < rg.y; ++m) k += hdr[m].z;
     for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z;
-    visitCount[i] = k;
+    visitCount[t] = k;
 }
-__global__ void visit_fill(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* visitStart, int4* visits) {
+__global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* visitStart,
+                           const BodyAux* aux, int4* visits) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
-    int i = dynList[t];
+    int i = colOrder[t];
     int4 rg = adjRange[i];
-    int o = visitStart[i];
-    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(4 * m + c, h.y, 1, h.w); }
-    for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(4 * m + c, h.x, 0, h.w); }
+    int o = visitStart[t];
+    float4 I = aux[i].inert;
+    int idx = (i << 2) | ((I.x == I.y && I.y == I.z) ? 0 : 2);
+    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(4 * m + c, h.y, idx | 1, h.w); }
+    for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(4 * m + c, h.x, idx, h.w); }
 }
 
 // ------------------------------------------------------------------ colouring

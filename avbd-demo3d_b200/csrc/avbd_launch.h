@@ -24,9 +24,11 @@ struct ForceView {
 constexpr int kThreads = 256;
 constexpr int kLanesPerBody = 4;
 
-// One colour of the primal sweep: `count` bodies listed in `order`.
-void launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
-                   const int* order, int count, SolveParams prm, float alpha, float* dxOut, Diag* diag);
+// One colour of the primal sweep: `count` bodies listed in `order`; visitStart[k] .. visitStart[k+1] is the run of
+// `visits` of body order[k]; avgVisits (visits per body, whole world) picks the tile shape.
+// `sums` is scratch for the split path: 28 floats per body of the colour.  Returns the number of kernels launched.
+int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
+                  const int* order, int count, float avgVisits, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live contacts in contactList.
 void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, const int* contactList, int nContacts, SolveParams prm, float alpha);
 // Small worlds: the whole iteration loop (solver.cpp:340-431, manifold rows only) in ONE cooperative launch.

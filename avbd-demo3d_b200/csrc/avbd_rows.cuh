@@ -110,7 +110,7 @@ AVBD_HD void accumulate_row(BodySystem& s, V3 Jl, V3 Ja, float f, float pen, boo
 
 // Primal contribution of one contact as seen from body side `isA`
 // (solver.cpp:371-399 with Manifold::computeDerivatives, manifold.cpp:247-271).
-AVBD_HD void accumulate_contact(BodySystem& s, const ContactState& c, const ContactEval& e, bool isA, const M3& invIw) {
+AVBD_HD void accumulate_contact(BodySystem& s, const ContactState& c, const ContactEval& e, bool isA, const M3& invIw, bool gyro = true) {
     float sg = isA ? 1.0f : -1.0f;
     V3 wr = isA ? e.wrA : e.wrB;
 #pragma unroll
@@ -118,8 +118,64 @@ AVBD_HD void accumulate_contact(BodySystem& s, const ContactState& c, const Cont
         V3 Jl = e.basis[r] * sg;
         V3 Ja = cross(wr, e.basis[r]) * sg;
         float f = clampf(c.pen[r] * e.C[r] + c.lam[r], e.fmin[r], e.fmax[r]);
-        accumulate_row(s, Jl, Ja, f, c.pen[r], true, invIw);
+        accumulate_row(s, Jl, Ja, f, c.pen[r], gyro, invIw);
     }
+}
+
+// The same contribution as accumulate_contact, OVERWRITING `s` (the solver kernels' form: one visit = one partial sum
+// that the kernel then adds in visit order).  The body-side sign is folded into f: (sg J) f = J (sg f) and
+// pen (sg J)(sg J)^T = pen J J^T hold bit for bit, so every one of the 27 numbers equals accumulate_contact's on a cleared
+// system (tests/test_abi_and_host.py).  The outer products stay per row ON PURPOSE: re-associating them through
+// M = sum_r p_r b_r b_r^T is ~45 instructions cheaper but loses up to the penalty ratio (100x) in relative accuracy when the
+// lever arm is nearly parallel to the stiffest row, and the Schur complement amplifies that by the system's condition.
+AVBD_HD void contact_system(BodySystem& s, const ContactState& c, const ContactEval& e, bool isA, bool gyro, const M3& invIw) {
+    V3 w = isA ? e.wrA : e.wrB;
+    float sg = isA ? 1.0f : -1.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        V3 Jl = e.basis[r];
+        V3 Ja = cross(w, e.basis[r]);
+        float f0 = clampf(c.pen[r] * e.C[r] + c.lam[r], e.fmin[r], e.fmax[r]);
+        float f = f0 * sg;
+        float pen = c.pen[r];
+        bool stiff = pen > 0.0f && finite1(pen);                 // solver.cpp:381: otherwise the row adds no stiffness
+        if (!stiff) pen = 0.0f;
+        float lp[3] = {Jl.x * pen, Jl.y * pen, Jl.z * pen}, ap[3] = {Ja.x * pen, Ja.y * pen, Ja.z * pen};
+        float jl[3] = {Jl.x, Jl.y, Jl.z}, ja[3] = {Ja.x, Ja.y, Ja.z};
+        if (r == 0) {
+            s.rl[0] = Jl.x * f; s.rl[1] = Jl.y * f; s.rl[2] = Jl.z * f;
+            s.ra[0] = Ja.x * f; s.ra[1] = Ja.y * f; s.ra[2] = Ja.z * f;
+            s.ll[0] = lp[0] * jl[0]; s.ll[1] = lp[1] * jl[0]; s.ll[2] = lp[2] * jl[0];
+            s.ll[3] = lp[1] * jl[1]; s.ll[4] = lp[2] * jl[1]; s.ll[5] = lp[2] * jl[2];
+            s.aa[0] = ap[0] * ja[0]; s.aa[1] = ap[1] * ja[0]; s.aa[2] = ap[2] * ja[0];
+            s.aa[3] = ap[1] * ja[1]; s.aa[4] = ap[2] * ja[1]; s.aa[5] = ap[2] * ja[2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s.la[i * 3 + k] = lp[i] * ja[k];
+        } else {
+            s.rl[0] += Jl.x * f; s.rl[1] += Jl.y * f; s.rl[2] += Jl.z * f;
+            s.ra[0] += Ja.x * f; s.ra[1] += Ja.y * f; s.ra[2] += Ja.z * f;
+            s.ll[0] += lp[0] * jl[0]; s.ll[1] += lp[1] * jl[0]; s.ll[2] += lp[2] * jl[0];
+            s.ll[3] += lp[1] * jl[1]; s.ll[4] += lp[2] * jl[1]; s.ll[5] += lp[2] * jl[2];
+            s.aa[0] += ap[0] * ja[0]; s.aa[1] += ap[1] * ja[0]; s.aa[2] += ap[2] * ja[0];
+            s.aa[3] += ap[1] * ja[1]; s.aa[4] += ap[2] * ja[1]; s.aa[5] += ap[2] * ja[2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s.la[i * 3 + k] += lp[i] * ja[k];
+        }
+        if (gyro && stiff) {                                     // solver.cpp:393-397; exactly zero for isotropic inertia
+            V3 g = vabs(cross(Ja, mv(invIw, Ja)));
+            float af = fabsf(f0);
+            s.aa[0] += g.x * af; s.aa[3] += g.y * af; s.aa[5] += g.z * af;
+        }
+    }
+}
+AVBD_HD void add_system(BodySystem& s, const BodySystem& o) {
+    for (int i = 0; i < 3; ++i) { s.rl[i] += o.rl[i]; s.ra[i] += o.ra[i]; }
+    for (int i = 0; i < 6; ++i) { s.ll[i] += o.ll[i]; s.aa[i] += o.aa[i]; }
+    for (int i = 0; i < 9; ++i) s.la[i] += o.la[i];
 }
 
 // solver.cpp:68-83 on the packed system.

@@ -68,6 +68,26 @@ __device__ void accumulate_user_forces(BodySystem& s, const ForceView& fv, const
     }
 }
 
+// L2 residency hints.  Poses (32 B per body) are gathered at random by every contact visit, several times per sweep, while
+// contact data streams past once per visit; without a hint the stream evicts the poses and each pose gather goes back to
+// HBM (dragging a 64-byte granule for 32 useful bytes).  Pose loads / stores carry an evict_last policy.
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld4_keep(const float4* ptr, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st4_keep(float4* ptr, float4 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ BodyPose load_pose_keep(const BodyPose* p, unsigned long long pol) {
+    BodyPose r; r.pos = ld4_keep(&p->pos, pol); r.rot = ld4_keep(&p->rot, pol); return r;
+}
+
 // Loads of data another CTA may have written earlier in the SAME launch (persistent loop): bypass L1.
 template <bool COH> __device__ __forceinline__ float4 ld4(const float4* p) { return COH ? __ldcg(p) : *p; }
 template <bool COH> __device__ __forceinline__ BodyPose load_pose(const BodyPose* p) {
@@ -95,7 +115,7 @@ __device__ __forceinline__ void primal_tile(const BodyView& b, const int* __rest
     BodySystem sys; sys.clear();
     if (live) {
         int i = order[gid];
-        int v0 = visitStart[i], v1 = visitStart[i + 1];
+        int v0 = visitStart[gid], v1 = visitStart[gid + 1];
         bool userForces = fv.adjStart != nullptr && lane == 0 && fv.adjStart[i + 1] > fv.adjStart[i];
         if (v0 + lane < v1 || userForces) {
             BodyPose self = load_pose<COH>(b.pose + i);
@@ -105,14 +125,18 @@ __device__ __forceinline__ void primal_tile(const BodyView& b, const int* __rest
             M3 invIw = rot_diag(qmat(rot), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
             for (int v = v0 + lane; v < v1; v += LPB) {
                 int4 e = visits[v];
-                int ci = e.x; bool isA = e.z != 0;
+                int ci = e.x; bool isA = (e.z & 1) != 0;
                 BodyPose po = load_pose<COH>(b.pose + e.y);
                 ContactState cs = load_contact_c<COH>(ms, ci);
                 ContactEval ev;
                 float mu = __int_as_float(e.w);
-                if (isA) contact_constraint(pos, rot, invMassSelf, xyz(po.pos), quat(po.rot), po.pos.w, mu, alpha, cs, ev);
-                else     contact_constraint(xyz(po.pos), quat(po.rot), po.pos.w, pos, rot, invMassSelf, mu, alpha, cs, ev);
-                accumulate_contact(sys, cs, ev, isA, invIw);
+                {
+                    float4 pa4 = isA ? self.pos : po.pos, qa4 = isA ? self.rot : po.rot, pb4 = isA ? po.pos : self.pos, qb4 = isA ? po.rot : self.rot;
+                    contact_constraint(xyz(pa4), quat(qa4), pa4.w, xyz(pb4), quat(qb4), pb4.w, mu, alpha, cs, ev);
+                }
+                BodySystem part;
+                contact_system(part, cs, ev, isA, true, invIw);
+                add_system(sys, part);
                 ms.cL[ci] = pack_lambda(cs);      // computeConstraint's side effects (manifold.cpp:224-241)
             }
             if (userForces) accumulate_user_forces(sys, fv, b.pose, i, pos, rot, invIw);
@@ -160,6 +184,265 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_colour(BodyView b, cons
                                                                 SolveParams prm, float alpha, float* dxOut, Diag* diag) {
     __shared__ float sSys[(kThreads / LPB) * 27];    // stride 27 is odd: conflict-free in phase 2
     primal_tile<LPB, false>(b, visitStart, visits, ms, fv, order, count, blockIdx.x, prm, alpha, dxOut, diag, sSys);
+}
+
+// ------------------------------------------------------------------ primal, visit-parallel (the large-world path)
+// The visit list is laid out in colour order, so the visits of a tile of BPB consecutive bodies of one colour are ONE
+// contiguous run.  The tile walks that run one visit per thread (every lane busy, every lane's gathers independent
+// and in flight together — the kernel is latency bound otherwise):
+//   phase 0  thread t < BPB stages body t of the tile in shared memory (pose, inertial target, mass, inverse inertia)
+//   phase 1  thread t takes visit base+t: computeConstraint + 3 rows -> its 27 partial sums, parked transposed in
+//            shared memory (row stride 257: conflict free)
+//   phase 2  L = 256/BPB lanes per body add the body's run of partial sums in visit order (deterministic), each lane
+//            owning ceil(27/L) of the 27 components
+//   phase 3  thread t < BPB: inertial terms, Schur 3x3 LDL^T, pose update (solver.cpp:402-408)
+// Runs longer than 256 visits loop over phases 1-2.
+template <int BPB>
+struct PrimalSmem {
+    float c[27][kThreads + 1];
+    float sys[BPB][27];
+    float4 pos[BPB], rot[BPB], posI[BPB], rotI[BPB];
+    float4 mass[BPB];              // mass, invMass, friction, radius
+    float4 inert[BPB];             // Ixx Iyy Izz, w = 1 when the inertia is anisotropic (gyroscopic row term is non-zero)
+    float inv[BPB][6];             // world inverse inertia (0,0) (1,0) (2,0) (1,1) (2,1) (2,2), only when anisotropic
+    int vs[BPB + 1];
+    int body[BPB];
+};
+
+template <int BPB, bool COH>
+__device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int* __restrict__ vstart, const int4* __restrict__ visits,
+                                                   const ManifoldSet& ms, const ForceView& fv, const int* __restrict__ order, int count, int tile,
+                                                   const SolveParams& prm, float alpha, float* dxOut, Diag* diag, PrimalSmem<BPB>& sm) {
+    constexpr int L = kThreads / BPB;
+    constexpr int CPL = (27 + L - 1) / L;
+    const int t = threadIdx.x;
+    const int k0 = tile * BPB;
+    const int nb = (count - k0) < BPB ? (count - k0) : BPB;
+    if (t <= nb) sm.vs[t] = vstart[k0 + t];
+    if (t < nb) {
+        int i = order[k0 + t];
+        sm.body[t] = i;
+        BodyPose self = load_pose<COH>(b.pose + i);
+        BodyAux aux = b.aux[i];
+        sm.pos[t] = self.pos; sm.rot[t] = self.rot; sm.posI[t] = aux.posI; sm.rotI[t] = aux.rotI; sm.mass[t] = aux.mass;
+        V3 I = xyz(aux.inert);
+        // isotropic inertia: R diag(c) R^T = c*Id, so Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero; skip the term
+        bool aniso = !(I.x == I.y && I.y == I.z);
+        sm.inert[t] = make_float4(I.x, I.y, I.z, aniso ? 1.0f : 0.0f);
+        if (aniso) {
+            M3 inv = rot_diag(qmat(quat(self.rot)), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
+            sm.inv[t][0] = inv.c[0].x; sm.inv[t][1] = inv.c[0].y; sm.inv[t][2] = inv.c[0].z;
+            sm.inv[t][3] = inv.c[1].y; sm.inv[t][4] = inv.c[1].z; sm.inv[t][5] = inv.c[2].z;
+        }
+    }
+    __syncthreads();
+    const int v0 = sm.vs[0], v1 = sm.vs[nb];
+    float acc[CPL];
+#pragma unroll
+    for (int m = 0; m < CPL; ++m) acc[m] = 0.0f;
+    const int rs = t / L, rj = t % L;
+    int rlo = 0, rhi = 0;
+    if (rs < nb) { rlo = sm.vs[rs]; rhi = sm.vs[rs + 1]; }
+    for (int base = v0; base < v1; base += kThreads) {
+        int v = base + t;
+        if (v < v1) {
+            int4 e = visits[v];
+            int ci = e.x; bool isA = (e.z & 1) != 0;
+            BodyPose po = load_pose<COH>(b.pose + e.y);
+            float4 a4 = ms.cA[ci], b4 = ms.cB[ci], n4 = ms.cN[ci];
+            float4 l4 = ld4<COH>(ms.cL + ci), p4 = ld4<COH>(ms.cP + ci);
+            int lo = 0, hi = nb;                                  // slot: vs[lo] <= v < vs[lo + 1]
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.vs[mid] <= v) lo = mid; else hi = mid; }
+            float4 sp = sm.pos[lo], sr = sm.rot[lo];
+            V3 pos = xyz(sp); Q4 rot = quat(sr);
+            ContactState cs = unpack_contact(a4, b4, n4, l4, p4);
+            ContactEval ev;
+            float mu = __int_as_float(e.w);
+            {
+                float4 pa4 = isA ? sp : po.pos, qa4 = isA ? sr : po.rot, pb4 = isA ? po.pos : sp, qb4 = isA ? po.rot : sr;
+                contact_constraint(xyz(pa4), quat(qa4), pa4.w, xyz(pb4), quat(qb4), pb4.w, mu, alpha, cs, ev);
+            }
+            bool gyro = sm.inert[lo].w != 0.0f;
+            M3 invIw;
+            if (gyro) {
+                const float* q = sm.inv[lo];
+                invIw = m3(mk3(q[0], q[1], q[2]), mk3(q[1], q[3], q[4]), mk3(q[2], q[4], q[5]));
+            } else {
+                invIw = m3(zero3(), zero3(), zero3());
+            }
+            BodySystem sys;
+            contact_system(sys, cs, ev, isA, gyro, invIw);
+            // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
+            float4 nl = pack_lambda(cs);
+            if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) ms.cL[ci] = nl;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { sm.c[6 + k][t] = sys.ll[k]; sm.c[21 + k][t] = sys.aa[k]; }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sm.c[12 + k][t] = sys.la[k];
+        }
+        __syncthreads();
+        if (rs < nb) {
+            int a = (rlo > base ? rlo : base) - base;
+            int z = (rhi < base + kThreads ? rhi : base + kThreads) - base;
+            for (int lv = a; lv < z; ++lv) {
+#pragma unroll
+                for (int m = 0; m < CPL; ++m) { int k = rj + m * L; if (k < 27) acc[m] += sm.c[k][lv]; }
+            }
+        }
+        __syncthreads();
+    }
+    if (rs < nb) {
+#pragma unroll
+        for (int m = 0; m < CPL; ++m) { int k = rj + m * L; if (k < 27) sm.sys[rs][k] = acc[m]; }
+    }
+    __syncthreads();
+    if (t < nb) {
+        int i = sm.body[t];
+        float4 sp = sm.pos[t];
+        V3 pos = xyz(sp); Q4 rot = quat(sm.rot[t]);
+        BodyAux aux; aux.posI = sm.posI[t]; aux.rotI = sm.rotI[t]; aux.mass = sm.mass[t]; aux.inert = sm.inert[t];
+        BodySystem own; M3 invIw;
+        body_self_system(pos, rot, aux, prm.dt, own, invIw);
+        const float* o = sm.sys[t];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { own.rl[k] += o[k]; own.ra[k] += o[3 + k]; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { own.ll[k] += o[6 + k]; own.aa[k] += o[21 + k]; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) own.la[k] += o[12 + k];
+        if (fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i]) accumulate_user_forces(own, fv, b.pose, i, pos, rot, invIw);
+        V3 dl, da;
+        solve_body_system(own, dl, da);
+        int evn = apply_body_update(pos, rot, dl, da);
+        BodyPose out; out.pos = f4(pos, sp.w); out.rot = f4(rot);
+        b.pose[i] = out;
+        if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
+        if (evn) atomicAdd(&diag[b.worldId[i]].nanEvents, evn);
+    }
+}
+
+template <int BPB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) primal_visits(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits,
+                                                                ManifoldSet ms, ForceView fv, const int* __restrict__ order, int count,
+                                                                SolveParams prm, float alpha, float* dxOut, Diag* diag) {
+    __shared__ PrimalSmem<BPB> sm;
+    primal_tile_visits<BPB, false>(b, vstart, visits, ms, fv, order, count, blockIdx.x, prm, alpha, dxOut, diag, sm);
+}
+
+// ------------------------------------------------------------------ primal, split (visit sums -> block solve)
+// Keeping the 6x6 solve inside the visit kernel leaves 1/4 .. 1/8 of a block's threads running a long serial chain while
+// the block pins its registers and shared memory.  The large-world path therefore runs two lane-dense kernels per colour:
+//   primal_visit_sums  one visit per thread -> per-body sums of the 27 row contributions (shared-memory transpose +
+//                      in-order reduction), written to `sums` in colour order (28 floats per body)
+//   primal_solve       one body per thread: inertial terms + sums -> Schur solve -> pose update
+// Visit entry (built with the graph): {contact id, other body, (self body << 2) | anisotropic-inertia << 1 | body-is-A, mu}.
+template <int BPB>
+struct VisitSmem {
+    float c[27][kThreads + 1];
+    int vs[BPB + 1];
+};
+constexpr int kSumStride = 28;
+
+template <int BPB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits,
+                                                                    ManifoldSet ms, int count, float alpha, float* __restrict__ sums) {
+    constexpr int L = kThreads / BPB;
+    constexpr int CPL = (27 + L - 1) / L;
+    __shared__ VisitSmem<BPB> sm;
+    const int t = threadIdx.x;
+    const int k0 = blockIdx.x * BPB;
+    const int nb = (count - k0) < BPB ? (count - k0) : BPB;
+    if (t <= nb) sm.vs[t] = vstart[k0 + t];
+    const int v0 = vstart[k0], v1 = vstart[k0 + nb];
+    float acc[CPL];
+#pragma unroll
+    for (int m = 0; m < CPL; ++m) acc[m] = 0.0f;
+    const int rs = t / L, rj = t % L;
+    const unsigned long long keep = l2_keep_policy();
+    for (int base = v0; base < v1; base += kThreads) {
+        int v = base + t;
+        if (v < v1) {
+            int4 e = visits[v];
+            int ci = e.x, self = e.z >> 2; bool isA = (e.z & 1) != 0, gyro = (e.z & 2) != 0;
+            BodyPose ps = load_pose_keep(b.pose + self, keep);
+            BodyPose po = load_pose_keep(b.pose + e.y, keep);
+            // contact geometry is read once per visit: stream it past L2 (evict-first) so it does not push the poses out
+            float4 a4 = __ldcs(ms.cA + ci), b4 = __ldcs(ms.cB + ci), n4 = __ldcs(ms.cN + ci), l4 = ms.cL[ci], p4 = ms.cP[ci];
+            V3 pos = xyz(ps.pos); Q4 rot = quat(ps.rot);
+            ContactState cs = unpack_contact(a4, b4, n4, l4, p4);
+            ContactEval ev;
+            float mu = __int_as_float(e.w);
+            {   // one call with the operands swapped by selects: an if/else duplicates the code and mixed warps run both arms
+                float4 pa4 = isA ? ps.pos : po.pos, qa4 = isA ? ps.rot : po.rot, pb4 = isA ? po.pos : ps.pos, qb4 = isA ? po.rot : ps.rot;
+                contact_constraint(xyz(pa4), quat(qa4), pa4.w, xyz(pb4), quat(qb4), pb4.w, mu, alpha, cs, ev);
+            }
+            M3 invIw = m3(zero3(), zero3(), zero3());
+            if (gyro) {   // anisotropic inertia only: for R diag(c) R^T = c Id the term Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero
+                V3 I = xyz(b.aux[self].inert);
+                invIw = rot_diag(qmat(rot), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
+            }
+            BodySystem sys;
+            contact_system(sys, cs, ev, isA, gyro, invIw);
+            // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
+            float4 nl = pack_lambda(cs);
+            if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) ms.cL[ci] = nl;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { sm.c[6 + k][t] = sys.ll[k]; sm.c[21 + k][t] = sys.aa[k]; }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sm.c[12 + k][t] = sys.la[k];
+        }
+        __syncthreads();
+        if (rs < nb) {
+            int rlo = sm.vs[rs], rhi = sm.vs[rs + 1];
+            int a = (rlo > base ? rlo : base) - base;
+            int z = (rhi < base + kThreads ? rhi : base + kThreads) - base;
+            for (int lv = a; lv < z; ++lv) {
+#pragma unroll
+                for (int m = 0; m < CPL; ++m) { int k = rj + m * L; if (k < 27) acc[m] += sm.c[k][lv]; }
+            }
+        }
+        if (base + kThreads < v1) __syncthreads();
+    }
+    if (rs < nb) {
+        float* o = sums + (size_t)(k0 + rs) * kSumStride;
+#pragma unroll
+        for (int m = 0; m < CPL; ++m) { int k = rj + m * L; if (k < 27) o[k] = acc[m]; }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) primal_solve(BodyView b, ForceView fv, const int* __restrict__ order, int count,
+                                                         const float* __restrict__ sums, SolveParams prm, float* dxOut, Diag* diag) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    int i = order[k];
+    const unsigned long long keep = l2_keep_policy();
+    BodyPose self = load_pose_keep(b.pose + i, keep);
+    BodyAux aux = b.aux[i];
+    const float4* s4 = reinterpret_cast<const float4*>(sums + (size_t)k * kSumStride);
+    float o[kSumStride];
+#pragma unroll
+    for (int q = 0; q < kSumStride / 4; ++q) { float4 x = s4[q]; o[4 * q] = x.x; o[4 * q + 1] = x.y; o[4 * q + 2] = x.z; o[4 * q + 3] = x.w; }
+    V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
+    BodySystem own; M3 invIw;
+    body_self_system(pos, rot, aux, prm.dt, own, invIw);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { own.rl[q] += o[q]; own.ra[q] += o[3 + q]; }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { own.ll[q] += o[6 + q]; own.aa[q] += o[21 + q]; }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) own.la[q] += o[12 + q];
+    if (fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i]) accumulate_user_forces(own, fv, b.pose, i, pos, rot, invIw);
+    V3 dl, da;
+    solve_body_system(own, dl, da);
+    int evn = apply_body_update(pos, rot, dl, da);
+    st4_keep(&b.pose[i].pos, f4(pos, self.pos.w), keep);
+    st4_keep(&b.pose[i].rot, f4(rot), keep);
+    if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
+    if (evn) atomicAdd(&diag[b.worldId[i]].nanEvents, evn);
 }
 
 // ------------------------------------------------------------------ dual
@@ -215,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_loop_persistent(BodyView b,
             int2 r = colRange[c];
             int count = r.y - r.x;
             for (int tile = blockIdx.x; tile * BPB < count; tile += gridDim.x) {
-                primal_tile<LPB, true>(b, visitStart, visits, ms, fv, order + r.x, count, tile, prm, alpha, nullptr, diag, sSys);
+                primal_tile<LPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, nullptr, diag, sSys);
                 __syncthreads();
             }
             grid_barrier(barrier, target);
@@ -300,17 +583,61 @@ static void launch_primal_variant(cudaStream_t s, BodyView b, const int* visitSt
     primal_colour<LPB, MINB><<<blocks_of(count, kThreads / LPB), kThreads, 0, s>>>(b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag);
 }
 
-// AVBD_PRIMAL_VARIANT (tuning aid): "<lanes per body><min blocks per SM>": 43 (default; measured best on the 1M grid,
-// profiles/README.md), 82, 83, 42, 44, 23.
-void launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
-                   const int* order, int count, SolveParams prm, float alpha, float* dxOut, Diag* diag) {
-    static int variant = [] { const char* e = getenv("AVBD_PRIMAL_VARIANT"); return e ? atoi(e) : kLanesPerBody * 10 + 3; }();
-#define AVBD_PV(L, M) case L * 10 + M: launch_primal_variant<L, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag); break;
-    switch (variant) {
-        AVBD_PV(8, 2) AVBD_PV(8, 3) AVBD_PV(4, 2) AVBD_PV(4, 4) AVBD_PV(2, 3)
-        default: launch_primal_variant<4, 3>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag); break;
+template <int BPB, int MINB>
+static void launch_primal_visits(cudaStream_t s, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, ForceView fv,
+                                 const int* order, int count, SolveParams prm, float alpha, float* dxOut, Diag* diag) {
+    primal_visits<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, ms, fv, order, count, prm, alpha, dxOut, diag);
+}
+
+template <int BPB, int MINB>
+static void launch_split(cudaStream_t s, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, ForceView fv,
+                         const int* order, int count, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag) {
+    primal_visit_sums<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, ms, count, alpha, sums);
+    primal_solve<<<blocks_of(count, kThreads), kThreads, 0, s>>>(b, fv, order, count, sums, prm, dxOut, diag);
+}
+
+// Default: the split path (visit sums + block solve), bodies per tile chosen so a tile's visits fill the block once.
+// AVBD_PRIMAL_VARIANT (tuning aid): "s<BPB>[m<MINB>]" split path with a forced tile size (s16 s28 s64; m3 m4);
+// "v<BPB>[m<MINB>]" the fused visit-parallel kernel; "<lanes per body><min blocks per SM>" the lanes-per-body kernel (43 ...).
+// Returns the number of kernels launched.
+int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
+                  const int* order, int count, float avgVisits, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag) {
+    static int variant = 0, minb = 3; static char kind = 's';
+    static bool init = [] {
+        const char* e = getenv("AVBD_PRIMAL_VARIANT");
+        if (!e) return true;
+        if (e[0] == 'v' || e[0] == 's') {
+            kind = e[0];
+            variant = -atoi(e + 1);
+            for (const char* p = e; *p; ++p) if (*p == 'm') minb = atoi(p + 1);
+        } else variant = atoi(e);
+        return true;
+    }();
+    (void)init;
+#define AVBD_PV(L, M) case L * 10 + M: launch_primal_variant<L, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag); return 1;
+#define AVBD_VV(B, M) launch_primal_visits<B, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag)
+#define AVBD_SV(B, M) launch_split<B, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, sums, dxOut, diag)
+    if (variant > 0) {
+        switch (variant) {
+            AVBD_PV(8, 2) AVBD_PV(8, 3) AVBD_PV(4, 2) AVBD_PV(4, 3) AVBD_PV(4, 4) AVBD_PV(2, 3)
+            default: break;
+        }
     }
+    int bpb = variant < 0 ? -variant : (avgVisits <= 3.7f ? 64 : (avgVisits <= 9.0f ? 28 : (avgVisits <= 16.0f ? 16 : 8)));
+    if (kind == 'v') {
+        if (bpb >= 64) { if (minb == 4) AVBD_VV(64, 4); else AVBD_VV(64, 3); }
+        else if (bpb >= 28) { if (minb == 4) AVBD_VV(28, 4); else AVBD_VV(28, 3); }
+        else if (bpb >= 16) AVBD_VV(16, 3); else AVBD_VV(8, 3);
+        return 1;
+    }
+    if (bpb >= 64) { if (minb == 4) AVBD_SV(64, 4); else AVBD_SV(64, 3); }
+    else if (bpb >= 28) { if (minb == 4) AVBD_SV(28, 4); else AVBD_SV(28, 3); }
+    else if (bpb >= 16) { if (minb == 4) AVBD_SV(16, 4); else AVBD_SV(16, 3); }
+    else AVBD_SV(8, 3);
+    return 2;
 #undef AVBD_PV
+#undef AVBD_VV
+#undef AVBD_SV
 }
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, const int* contactList, int nContacts, SolveParams prm,

@@ -39,8 +39,9 @@ def hash_float01(x):
     return (x & np.uint32(0x00FFFFFF)).astype(F) / F(16777215.0)
 
 
-def stress_grid(nx, ny, nz, spacing_y=2.0, start_y=20.0, wide_ground=False):
-    """scenes.h:86-132 with NX/NY/NZ, spacingY and startY free.  wide_ground widens the static ground so it
+def stress_grid(nx, ny, nz, spacing_y=2.0, start_y=20.0, wide_ground=False, jitter_y=0.25):
+    """scenes.h:86-132 with NX/NY/NZ, spacingY, startY and the vertical jitter amplitude free (0.25 upstream; a
+    pre-stacked grid with spacingY=1.01 needs 0 or neighbouring layers start up to 0.24 deep inside each other).  wide_ground widens the static ground so it
     covers the grid footprint (the stock 100x1x100 slab is too small beyond ~80 columns)."""
     gx = gz = 100.0
     if wide_ground:
@@ -52,7 +53,7 @@ def stress_grid(nx, ny, nz, spacing_y=2.0, start_y=20.0, wide_ground=False):
         seed = (x + nx * (z + nz * y) + 1).astype(np.uint32)
         jx = (hash_float01(seed * np.uint32(9781)) * F(2.0) - F(1.0)) * F(0.04)
         jz = (hash_float01(seed * np.uint32(6271)) * F(2.0) - F(1.0)) * F(0.04)
-        jy = hash_float01(seed * np.uint32(3343)) * F(0.25)
+        jy = hash_float01(seed * np.uint32(3343)) * F(jitter_y)
     px = (x.astype(F) - F(nx - 1) * F(0.5)) * F(1.15) + jx
     py = F(start_y) + y.astype(F) * F(spacing_y) + jy
     pz = (z.astype(F) - F(nz - 1) * F(0.5)) * F(1.15) + jz

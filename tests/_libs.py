@@ -256,6 +256,7 @@ class Emul:
         L.emu_num_manifolds.argtypes = [C.c_void_p]
         L.emu_get_manifolds.argtypes = [C.c_void_p, i32p, i32p, i32p, f32p]
         L.emu_collide.argtypes = [f32p, f32p, i32p, f32p]
+        L.emu_contact_system.argtypes = [f32p, f32p]
         self.h = L.emu_create()
         self.n = 0
 
@@ -270,6 +271,12 @@ class Emul:
     def add_body(self, size, density, friction, pos, quat=(0, 0, 0, 1), lin=(0, 0, 0), ang=(0, 0, 0)):
         self.n += 1
         return self.lib.emu_add_body(self.h, _f(size), density, friction, _f(pos), _f(quat), _f(lin), _f(ang))
+
+    def contact_system(self, inp):
+        """(fused 27, row-by-row 27) contribution of one contact visit: contact_system vs accumulate_contact."""
+        out = np.zeros(54, np.float32)
+        self.lib.emu_contact_system(_f(inp), out)
+        return out[:27], out[27:]
 
     def set_order(self, order):
         o = np.ascontiguousarray(order, np.int32)

@@ -107,7 +107,11 @@ static void primal_stage(EWorld* w, float alpha, float* dxOut) {
                 for (int c = 0; c < m.n; ++c) {
                     ContactEval ev;
                     contact_constraint(A.pos, A.rot, A.invMass, B.pos, B.rot, B.invMass, m.mu, alpha, m.ct[c], ev);
+#ifdef PARTIAL_SUMS
+                    { BodySystem part; contact_system(part, m.ct[c], ev, isA, true, invIw); add_system(sys, part); }
+#else
                     accumulate_contact(sys, m.ct[c], ev, isA, invIw);
+#endif
                 }
             }
         V3 dl, da;
@@ -179,6 +183,38 @@ void emu_get_manifolds(void* h, int* ints, int* feats, int* stick, float* flts) 
         }
         for (int i = 0; i < 4; ++i) for (int k = 0; k < 3; ++k) *flts++ = i < m.n ? m.ct[i].lam[k] : 0.0f;
         for (int i = 0; i < 4; ++i) for (int k = 0; k < 3; ++k) *flts++ = i < m.n ? m.ct[i].pen[k] : 0.0f;
+    }
+}
+
+// contact_system (the solver kernels' fused three-row form) against accumulate_contact (row by row, the reference's
+// association) on one contact: in[0..6] pose A, [7..13] pose B, [14..22] rA rB n, [23..25] C0, [26..28] lambda,
+// [29..31] penalty, [32] stick, [33] mu, [34] alpha, [35..37] inertia diag of the visiting body, [38] isA.
+// out: 27 fused then 27 row-by-row (rl ra ll la aa).
+void emu_contact_system(const float* in, float* out) {
+    V3 pA = mk3(in[0], in[1], in[2]); Q4 qA = qunit(qmk(in[3], in[4], in[5], in[6]));
+    V3 pB = mk3(in[7], in[8], in[9]); Q4 qB = qunit(qmk(in[10], in[11], in[12], in[13]));
+    ContactState c{};
+    c.rA = mk3(in[14], in[15], in[16]); c.rB = mk3(in[17], in[18], in[19]); c.n = unit_or(mk3(in[20], in[21], in[22]), mk3(0, 1, 0));
+    c.C0n = in[23]; c.C0t1 = in[24]; c.C0t2 = in[25];
+    for (int k = 0; k < 3; ++k) { c.lam[k] = in[26 + k]; c.pen[k] = in[29 + k]; }
+    c.stick = in[32] != 0.0f;
+    bool isA = in[38] != 0.0f;
+    V3 I = mk3(in[35], in[36], in[37]);
+    M3 invIw = rot_diag(qmat(isA ? qA : qB), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
+    ContactState c1 = c, c2 = c;
+    ContactEval e1, e2;
+    contact_constraint(pA, qA, 1.0f, pB, qB, 1.0f, in[33], in[34], c1, e1);
+    contact_constraint(pA, qA, 1.0f, pB, qB, 1.0f, in[33], in[34], c2, e2);
+    BodySystem a, b; b.clear();
+    contact_system(a, c1, e1, isA, true, invIw);
+    accumulate_contact(b, c2, e2, isA, invIw);
+    const BodySystem* two[2] = {&a, &b};
+    for (int t = 0; t < 2; ++t) {
+        const BodySystem& s = *two[t];
+        float* o = out + 27 * t;
+        for (int k = 0; k < 3; ++k) { o[k] = s.rl[k]; o[3 + k] = s.ra[k]; }
+        for (int k = 0; k < 6; ++k) { o[6 + k] = s.ll[k]; o[21 + k] = s.aa[k]; }
+        for (int k = 0; k < 9; ++k) o[12 + k] = s.la[k];
     }
 }
 

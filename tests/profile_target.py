@@ -12,7 +12,7 @@ if name == "stress1000":
 else:
     n = 100 if name == "grid100" else 50
     s = scenes.stress_grid(n, n, n, spacing_y=1.01, start_y=0.51, wide_ground=True); s["params"]["iterations"] = 10
-    scenes.load(w, s); w.step(3)
+    scenes.load(w, s); w.step(12)
 w.step(steps)
 print(w.step_stats())
 w.close()

@@ -81,3 +81,30 @@ def test_device_step_math_tracks_oracle_on_host(scene, steps, tol):
     mo, me = o.manifolds(), e.manifolds()
     assert set(mo) == set(me)
     o.close(); e.close()
+
+
+def test_fused_contact_rows_match_row_by_row_accumulation():
+    """contact_system (csrc/avbd_rows.cuh: one contact visit as the solver kernels evaluate it, body-side sign folded
+    into the force) against accumulate_contact (solver.cpp:371-399 row by row) on random contacts: all 27 sums are
+    bit-identical.  (Checked per contribution on purpose: after the 6x6 solve a penalty-dominated system amplifies ANY
+    rounding difference — summation order included — by its condition number.)"""
+    rng = np.random.default_rng(21)
+    emu = Emul()
+    worst = 0.0
+    for t in range(3000):
+        v = np.zeros(39, np.float32)
+        v[0:3] = rng.uniform(-1, 1, 3); v[3:7] = rng.normal(size=4)
+        v[7:10] = rng.uniform(-1, 1, 3); v[10:14] = rng.normal(size=4)
+        v[14:20] = rng.uniform(-0.8, 0.8, 6); v[20:23] = rng.normal(size=3)
+        v[23:26] = rng.uniform(-0.05, 0.05, 3)
+        v[26] = -rng.uniform(0, 200); v[27:29] = rng.uniform(-40, 40, 2)
+        v[29:32] = 10 ** rng.uniform(4.3, 6.3, 3)
+        v[32] = t % 2; v[33] = 0.5; v[34] = 0.95
+        v[35:38] = rng.uniform(0.05, 0.5, 3) if t % 3 else 1.0 / 6.0
+        v[38] = t % 2 if t % 5 else 1 - t % 2
+        fused, rows = emu.contact_system(v)
+        for blk in (slice(0, 3), slice(3, 6), slice(6, 12), slice(12, 21), slice(21, 27)):
+            scale = np.abs(rows[blk]).max() + 1e-20
+            worst = max(worst, float(np.abs(fused[blk] - rows[blk]).max() / scale))
+    emu.close()
+    assert worst == 0.0, worst
