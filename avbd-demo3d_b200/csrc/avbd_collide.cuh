@@ -221,8 +221,9 @@ AVBD_HD int build_contacts(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 size
         push_contact(posA, rotA, posB, rotB, out, cnt, mids, xA, xB, key, -n);
         return cnt;
     }
-    if (k < 3) return face_manifold(posA, rotA, posB, rotB, A, B, true, k, n, out);
-    return face_manifold(posA, rotA, posB, rotB, A, B, false, k - 3, n, out);
+    // one instance for both reference sides: two inlined copies would run back to back in every mixed warp
+    bool refIsA = k < 3;
+    return face_manifold(posA, rotA, posB, rotB, A, B, refIsA, refIsA ? k : k - 3, n, out);
 }
 
 } // namespace avbd

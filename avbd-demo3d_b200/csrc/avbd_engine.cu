@@ -76,15 +76,16 @@ struct avbd_world {
     DevBuf<float4> prevLin, size;
     DevBuf<int> flags, worldId, localIdx, dynList;
     bool topoDirty = true;
+    bool contactDiagDone = false;   // the step's last dual pass reduced the contact diagnostics already
     int keyShift = 1;
 
     // broadphase
     float cell = 1.0f; unsigned tableSize = 256;
-    DevBuf<unsigned> cellKey, cellKeySorted; DevBuf<int> cellVal, cellValSorted, cellStart, cellEnd;
-    DevBuf<int4> sortedCell; DevBuf<float4> sortedPos;
+    DevBuf<unsigned> cellKey, cellKeySorted; DevBuf<int> cellVal, cellValSorted; DevBuf<int2> cellRange;
+    DevBuf<int2> sortedCell; DevBuf<float4> sortedPos;
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
-    DevBuf<unsigned long long> cand, candSorted; int nCand = 0, nPairs = 0;
-    DevBuf<int> candInfo, candFlag, candScan, survP;
+    DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
+    DevBuf<int> candCode, candCodeSorted;
     DevBuf<int> mcount, contactStart, contactList, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;
 
     // manifolds (ping-pong)
@@ -138,7 +139,7 @@ struct avbd_world {
     }
     GridView gview() {
         GridView g; g.cell = cell; g.tableMask = tableSize - 1; g.key = cellKey.p; g.keySorted = cellKeySorted.p;
-        g.val = cellVal.p; g.valSorted = cellValSorted.p; g.cellStart = cellStart.p; g.cellEnd = cellEnd.p;
+        g.val = cellVal.p; g.valSorted = cellValSorted.p; g.cellRange = cellRange.p;
         g.sortedCell = sortedCell.p; g.sortedPos = sortedPos.p; g.largeList = largeList.p; g.worldLargeStart = worldLargeStart.p;
         return g;
     }
@@ -195,6 +196,13 @@ __global__ void rekey_manifolds(ManifoldSet ms, int nM, int keyShift) {
     if (m < nM) ms.key[m] = ((unsigned long long)(unsigned)ms.hdr[m].x << keyShift) | (unsigned)ms.hdr[m].y;
 }
 
+int np_sat_launch(avbd_world* w, const BodyView& bv, const PairSink& raw, int expect, const PairSink& out) {
+    np_sat<<<blocks_for(expect), kThreads, 0, w->stream>>>(bv, raw.keys, raw.count, raw.cap, w->keyShift, w->excl.p, w->nExcl, out);
+    w->satLaunched = (long long)blocks_for(expect) * kThreads;
+    w->launches++;
+    return 0;
+}
+
 // Rebuilds everything that depends on the body / user-force SET (not on poses).
 int prepare(avbd_world* w) {
     if (!w->topoDirty && !w->forcesDirty) return 0;
@@ -239,7 +247,7 @@ int prepare(avbd_world* w) {
         // per-body scratch
         TRY(w->cellKey.ensure(n, false, s)); TRY(w->cellKeySorted.ensure(n, false, s)); TRY(w->cellVal.ensure(n, false, s));
         TRY(w->cellValSorted.ensure(n, false, s)); TRY(w->sortedCell.ensure(n, false, s)); TRY(w->sortedPos.ensure(n, false, s));
-        TRY(w->cellStart.ensure(table, false, s)); TRY(w->cellEnd.ensure(table, false, s));
+        TRY(w->cellRange.ensure(table, false, s));
         TRY(w->adjRange.ensure(n, false, s)); TRY(w->colour.ensure(n, false, s));
         TRY(w->colKey.ensure(std::max(1, w->nDyn), false, s)); TRY(w->colKeySorted.ensure(std::max(1, w->nDyn), false, s));
         TRY(w->colVal.ensure(std::max(1, w->nDyn), false, s)); TRY(w->colOrder.ensure(std::max(1, w->nDyn), false, s));
@@ -300,8 +308,11 @@ int prepare(avbd_world* w) {
     return 0;
 }
 
-// Emits candidate pair keys and sorts them.  includePersisting adds last step's live manifold keys.
-int run_broadphase(avbd_world* w, bool includePersisting) {
+// Broadphase (+ SAT cull): leaves the key-sorted pairs in candSorted (and, with `sat`, their winning SAT axis in
+// candCodeSorted).  sat = false stops at the sphere-overlap pairs (stage API: the reference's solver.cpp:262-266
+// candidate set).  sat = true merges last step's manifolds whose spheres no longer overlap, applies the exclusion list
+// and the 15-axis test, so what comes out is exactly the set of manifolds to build.  One host sync (sizes + overflow).
+int run_broadphase(avbd_world* w, bool sat) {
     cudaStream_t s = w->stream;
     int n = w->n;
     w->nCand = 0; w->nPairs = 0;
@@ -310,30 +321,41 @@ int run_broadphase(avbd_world* w, bool includePersisting) {
     bp_cells<<<blocks_for(n), kThreads, 0, s>>>(bv, gv);
     int tbits = bits_for(w->tableSize);   // sentinel bucket == tableSize needs one more bit
     TRY(sort_pairs(w, w->cellKey.p, w->cellKeySorted.p, w->cellVal.p, w->cellValSorted.p, n, tbits));
-    CK(cudaMemsetAsync(w->cellStart.p, 0, w->tableSize * sizeof(int), s));
-    CK(cudaMemsetAsync(w->cellEnd.p, 0, w->tableSize * sizeof(int), s));
+    CK(cudaMemsetAsync(w->cellRange.p, 0, w->tableSize * sizeof(int2), s));
     bp_cell_bounds<<<blocks_for(n), kThreads, 0, s>>>(bv, gv);
-    w->launches += 4;
-    if (w->cand.cap == 0) { TRY(w->cand.ensure((size_t)std::max(1024, 16 * n), false, s)); }
+    w->launches += 2;
+    if (w->pairs.cap == 0) TRY(w->pairs.ensure((size_t)std::max(1024, 12 * n), false, s));
+    if (w->cand.cap == 0) { TRY(w->cand.ensure((size_t)std::max(1024, 3 * n), false, s)); TRY(w->candCode.ensure(w->cand.cap, false, s)); }
     for (int attempt = 0; attempt < 8; ++attempt) {
         CK(cudaMemsetAsync(w->dCnt, 0, sizeof(Counters), s));
-        PairSink sink; sink.keys = w->cand.p; sink.cap = (int)w->cand.cap; sink.keyShift = w->keyShift; sink.cnt = w->dCnt;
-        bp_pairs_small<<<blocks_for(n), kThreads, 0, s>>>(bv, gv, sink);
-        if (w->nLarge) bp_pairs_large<<<blocks_for(n), kThreads, 0, s>>>(bv, gv, sink);
-        w->launches += 2 + (w->nLarge ? 1 : 0);
-        TRY(read_counters(w));
-        int pairsOnly = w->hCnt->nCand;
-        if (includePersisting && w->nM > 0) {
-            bp_append_persisting<<<blocks_for(w->nM), kThreads, 0, s>>>(w->mset(w->cur), w->nM, sink);
-            w->launches++;
-            TRY(read_counters(w));
+        PairSink raw; raw.keys = w->pairs.p; raw.codes = nullptr; raw.cap = (int)w->pairs.cap; raw.keyShift = w->keyShift;
+        raw.count = &w->dCnt->nPairs; raw.cnt = w->dCnt; raw.overflowBit = 1;
+        bp_sweep<<<blocks_for(16ll * n), kThreads, 0, s>>>(bv, gv, raw);
+        if (w->nLarge) bp_large<<<blocks_for(n), kThreads, 0, s>>>(bv, gv, raw);
+        w->launches += 1 + (w->nLarge ? 1 : 0);
+        if (sat) {
+            if (w->nM > 0) { bp_persisting<<<blocks_for(w->nM), kThreads, 0, s>>>(bv, w->mset(w->cur), w->nM, raw); w->launches++; }
+            PairSink out; out.keys = w->cand.p; out.codes = w->candCode.p; out.cap = (int)std::min(w->cand.cap, w->candCode.cap); out.keyShift = w->keyShift;
+            out.count = &w->dCnt->nCand; out.cnt = w->dCnt; out.overflowBit = 2;
+            // sized by the pair count of the previous step (+ slack); the kernel reads the real count, a shortfall shows as overflow bit 16
+            long long expect = std::min<long long>((long long)raw.cap, std::max<long long>(w->lastPairs + w->lastPairs / 8 + 4096, 1024));
+            np_sat_launch(w, bv, raw, (int)expect, out);
         }
-        if (w->hCnt->nCand <= (int)w->cand.cap && !(w->hCnt->overflow & 1)) { w->nPairs = pairsOnly; w->nCand = w->hCnt->nCand; break; }
-        TRY(w->cand.ensure((size_t)w->hCnt->nCand + 1024, false, s));
+        TRY(read_counters(w));
+        bool rawOver = w->hCnt->nPairs > raw.cap, satShort = sat && w->hCnt->nPairs > w->satLaunched, outOver = sat && w->hCnt->nCand > (int)std::min(w->cand.cap, w->candCode.cap);
+        w->lastPairs = w->hCnt->nPairs;
+        if (!rawOver && !satShort && !outOver) { w->nPairs = w->hCnt->nPairs; w->nCand = sat ? w->hCnt->nCand : w->hCnt->nPairs; break; }
+        if (rawOver) TRY(w->pairs.ensure((size_t)w->hCnt->nPairs + w->hCnt->nPairs / 4 + 1024, false, s));
+        if (outOver) { TRY(w->cand.ensure((size_t)w->hCnt->nCand + w->hCnt->nCand / 4 + 1024, false, s)); TRY(w->candCode.ensure(w->cand.cap, false, s)); }
         if (attempt == 7) return fail(AVBD_ERR_CAPACITY, "pair buffer kept overflowing");
     }
-    TRY(w->candSorted.ensure(w->cand.cap, false, s));
-    TRY(sort_keys(w, w->cand.p, w->candSorted.p, w->nCand, 2 * w->keyShift));
+    if (sat) {
+        TRY(w->candSorted.ensure(w->cand.cap, false, s)); TRY(w->candCodeSorted.ensure(w->cand.cap, false, s));
+        TRY(sort_pairs(w, w->cand.p, w->candSorted.p, w->candCode.p, w->candCodeSorted.p, w->nCand, 2 * w->keyShift));
+    } else {
+        TRY(w->candSorted.ensure(w->pairs.cap, false, s));
+        TRY(sort_keys(w, w->pairs.p, w->candSorted.p, w->nCand, 2 * w->keyShift));
+    }
     CK(cudaGetLastError());
     return 0;
 }
@@ -345,23 +367,12 @@ int run_collide(avbd_world* w) {
     if (w->timed) cudaEventRecord(w->ev[0], s);
     TRY(run_broadphase(w, true));
     if (w->timed) cudaEventRecord(w->ev[1], s);
-    int nc = w->nCand;
-    int nSurv = 0;
-    if (nc > 0) {
-        TRY(w->candInfo.ensure(nc, false, s)); TRY(w->candFlag.ensure(nc, false, s));
-        TRY(w->candScan.ensure(nc, false, s)); TRY(w->survP.ensure(nc, false, s));
-        np_cull<<<blocks_for(nc), kThreads, 0, s>>>(w->bview(), w->candSorted.p, nc, w->keyShift, w->excl.p, w->nExcl, w->candInfo.p, w->candFlag.p);
-        TRY(exclusive_scan(w, w->candFlag.p, w->candScan.p, nc));
-        np_compact<<<blocks_for(nc), kThreads, 0, s>>>(w->candFlag.p, w->candScan.p, nc, w->survP.p, w->dCnt);
-        w->launches += 2;
-        TRY(read_counters(w));
-        nSurv = w->hCnt->nSurvive;
-    }
+    int nSurv = w->nCand;
     int nxt = w->cur ^ 1;
     if (nSurv > 0) {
         TRY(w->ensure_manifolds(nxt, nSurv));
         TRY(w->mcount.ensure(nSurv, false, s)); TRY(w->contactStart.ensure(nSurv, false, s)); TRY(w->contactList.ensure((size_t)nSurv * 4, false, s));
-        np_build<<<blocks_for(nSurv), kThreads, 0, s>>>(w->bview(), w->candSorted.p, w->candInfo.p, w->survP.p, nSurv, w->keyShift,
+        np_build<<<blocks_for(nSurv), kThreads, 0, s>>>(w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift,
                                                           w->mset(w->cur), w->nM, w->mset(nxt), w->mcount.p, w->prm, w->dCnt);
         w->launches++;
         // dense list of live contacts (the dual's work list; also sizes the visit list)
@@ -370,6 +381,7 @@ int run_collide(avbd_world* w) {
         w->launches++;
         TRY(read_counters(w));
         w->nContacts = w->hCnt->nContacts;
+        if (w->hCnt->overflow & 8) return fail(AVBD_ERR_CUDA, "broadphase emitted a pair twice");
     } else {
         w->nContacts = 0;
     }
@@ -465,12 +477,13 @@ int run_primal(avbd_world* w, float alpha, float* dxDev) {
     return 0;
 }
 
-int run_dual(avbd_world* w, float alpha) {
+int run_dual(avbd_world* w, float alpha, bool lastOfStep = false) {
     cudaStream_t s = w->stream;
     if (w->nContacts > 0) {
-        launch_dual(s, w->bview(), w->mset(w->cur), w->contactList.p, w->nContacts, w->prm, alpha);
+        launch_dual(s, w->bview(), w->mset(w->cur), w->contactList.p, w->nContacts, w->prm, alpha, lastOfStep ? w->dDiag.p : nullptr);
         w->launches++;
     }
+    if (lastOfStep) w->contactDiagDone = true;
     ForceView fv = w->fview();
     if (fv.nJoints + fv.nSprings > 0) {
         launch_dual_user_forces(s, w->bview(), fv, w->prm);
@@ -485,10 +498,11 @@ int run_velocity(avbd_world* w) {
     if (w->n == 0) return 0;
     velocity_bodies<<<blocks_for(w->n), kThreads, 0, s>>>(w->bview(), w->prm, w->dDiag.p);
     w->launches++;
-    if (w->nM > 0) {
+    if (w->nM > 0 && !w->contactDiagDone) {     // not already reduced by the step's last dual pass
         diagnostics_contacts<<<blocks_for((long long)w->nM * 4), kThreads, 0, s>>>(w->bview(), w->mset(w->cur), w->nM, w->dDiag.p);
         w->launches++;
     }
+    w->contactDiagDone = false;
     CK(cudaMemcpyAsync(w->hDiag, w->dDiag.p, sizeof(Diag) * w->nWorlds, cudaMemcpyDeviceToHost, s));
     CK(cudaGetLastError());
     return 0;
@@ -508,9 +522,10 @@ int step_once(avbd_world* w) {
     if (persistent) {
         // small world: the whole iteration loop in one cooperative launch (grid barriers instead of kernel boundaries)
         unsigned* barrier = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(w->dCnt + 1) + 8);
+        bool fuseDiag = !w->prm.postStabilize && w->prm.iterations > 0;
         persistent = launch_solve_loop(s, w->bview(), w->visitStart.p, w->visits.p, w->mset(w->cur), fvAll, w->colOrder.p, w->colRange.p,
-                                       w->nColours, w->maxColourCount, w->contactList.p, w->nContacts, w->prm, w->dDiag.p, barrier);
-        if (persistent) w->launches++; else cudaGetLastError();
+                                       w->nColours, w->maxColourCount, w->contactList.p, w->nContacts, w->prm, w->dDiag.p, barrier, fuseDiag);
+        if (persistent) { w->launches++; w->contactDiagDone = fuseDiag; } else cudaGetLastError();
     }
     if (prof) {
         while ((int)w->pev.size() < 2 * total + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); w->pev.push_back(e); }
@@ -521,7 +536,7 @@ int step_once(avbd_world* w) {
         float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
         TRY(run_primal(w, a, nullptr));
         if (prof) cudaEventRecord(w->pev[2 * it + 1], s);
-        if (it < w->prm.iterations) { TRY(run_dual(w, a)); ++duals; }
+        if (it < w->prm.iterations) { TRY(run_dual(w, a, it == total - 1)); ++duals; }   // last pass of the step (no postStabilize sweep after it)
         if (prof) cudaEventRecord(w->pev[2 * it + 2], s);
     }
     if (w->timed) cudaEventRecord(w->ev[5], s);
@@ -597,9 +612,9 @@ void avbd_world_destroy(avbd_world* w) {
     cudaStreamSynchronize(w->stream);
     w->pose.release(); w->aux.release(); w->vel.release(); w->init.release(); w->prevLin.release(); w->size.release();
     w->flags.release(); w->worldId.release(); w->localIdx.release(); w->dynList.release();
-    w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellStart.release(); w->cellEnd.release();
+    w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellRange.release();
     w->sortedCell.release(); w->sortedPos.release(); w->largeList.release(); w->worldLargeStart.release();
-    w->cand.release(); w->candSorted.release(); w->candInfo.release(); w->candFlag.release(); w->candScan.release(); w->survP.release();
+    w->pairs.release(); w->cand.release(); w->candSorted.release(); w->candCode.release(); w->candCodeSorted.release();
     for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.cL.release(); b.cP.release(); }
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();

@@ -1,6 +1,6 @@
 // avbd_kernels_collide.cuh — broadphase (hashed uniform grid + large-body side
-// list) and narrowphase (SAT cull -> compaction -> manifold build with fused
-// feature-id warm start) kernels.
+// list, half-space sweep with the SAT cull fused in) and narrowphase (manifold
+// build with fused feature-id warm start) kernels.
 //
 // Replaces the reference's O(n^2) pair loop + per-step new/delete of Manifold
 // nodes (solver.cpp:262-279, force.cpp:12-69) and Manifold::initialize
@@ -21,20 +21,23 @@ struct GridView {
     float cell;                         // edge length, >= 2.02 * largest small radius
     unsigned tableMask;                 // table size - 1 (power of two)
     unsigned* key; unsigned* keySorted; int* val; int* valSorted;
-    int* cellStart; int* cellEnd;       // per bucket, into the sorted order
-    int4* sortedCell;                   // cx cy cz world
+    int2* cellRange;                    // per bucket: [start, end) in the sorted order
+    int2* sortedCell;                   // {packed cell (10 low bits of cx, cy, cz), world}
     float4* sortedPos;                  // pos.xyz, radius
     const int* largeList; const int* worldLargeStart;
 };
 
 // Bucket of a grid cell.  Cells are grouped in 4x4x4 blocks: the block is hashed, the position inside the block
 // fills the low 6 bits, so the 64 cells of a block — and the bodies in them after the sort — stay contiguous and
-// the 27-cell sweep of neighbouring bodies touches neighbouring memory (a plain per-cell hash scatters them).
+// the neighbourhood sweep of neighbouring bodies touches neighbouring memory (a plain per-cell hash scatters them).
 __device__ __forceinline__ unsigned cell_hash(int x, int y, int z, int w) {
     unsigned h = ((unsigned)(x >> 2) * 73856093u) ^ ((unsigned)(y >> 2) * 19349663u) ^ ((unsigned)(z >> 2) * 83492791u) ^ ((unsigned)w * 2654435761u);
     h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
     return (h << 6) | (unsigned)((x & 3) | ((y & 3) << 2) | ((z & 3) << 4));
 }
+// Identity of a cell among the cells a sweep can confuse it with: two cells that share a bucket AND these 30 bits are
+// >= 1024 cells apart, so the sphere test rejects whatever the mix-up lets through.
+__device__ __forceinline__ int pack_cell(int x, int y, int z) { return (x & 1023) | ((y & 1023) << 10) | ((z & 1023) << 20); }
 __device__ __forceinline__ float body_radius(float4 size) { return len(xyz(size)) * 0.5f; }   // rigid.cpp:28
 __device__ __forceinline__ int3 cell_of(float4 pos, float cell) {
     return make_int3((int)floorf(pos.x / cell), (int)floorf(pos.y / cell), (int)floorf(pos.z / cell));
@@ -53,7 +56,7 @@ __global__ void bp_cells(BodyView b, GridView g) {
     g.val[i] = i;
 }
 
-// K1b: bucket boundaries in sorted order + sorted copies for the pair sweep.
+// K1b: bucket boundaries in sorted order + sorted copies for the pair sweep.  cellRange must be zeroed first.
 __global__ void bp_cell_bounds(BodyView b, GridView g) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= b.n) return;
@@ -63,62 +66,104 @@ __global__ void bp_cell_bounds(BodyView b, GridView g) {
     float r = body_radius(b.size[i]);
     int3 c = cell_of(pos, g.cell);
     g.sortedPos[p] = make_float4(pos.x, pos.y, pos.z, r);
-    g.sortedCell[p] = make_int4(c.x, c.y, c.z, b.worldId[i]);
+    g.sortedCell[p] = make_int2(pack_cell(c.x, c.y, c.z), b.worldId[i]);
     if (k > g.tableMask) return;
-    if (p == 0 || g.keySorted[p - 1] != k) g.cellStart[k] = p;
-    if (p == b.n - 1 || g.keySorted[p + 1] != k) g.cellEnd[k] = p + 1;
+    if (p == 0 || g.keySorted[p - 1] != k) g.cellRange[k].x = p;
+    if (p == b.n - 1 || g.keySorted[p + 1] != k) g.cellRange[k].y = p + 1;
 }
 
 struct PairSink {
-    unsigned long long* keys; int cap; int keyShift; Counters* cnt;
+    unsigned long long* keys; int* codes; int cap; int keyShift; int* count; Counters* cnt; int overflowBit;
 };
 
 // Warp-aggregated append: the lanes that reach this call together take one
 // atomic for the group and write a contiguous run.
-__device__ __forceinline__ void emit_pair(const PairSink& s, int a, int b) {
+__device__ __forceinline__ void emit_pair(const PairSink& s, unsigned long long key, int code) {
     cg::coalesced_group grp = cg::coalesced_threads();
     int base = 0;
-    if (grp.thread_rank() == 0) base = atomicAdd(&s.cnt->nCand, (int)grp.size());
+    if (grp.thread_rank() == 0) base = atomicAdd(s.count, (int)grp.size());
     base = grp.shfl(base, 0);
     int idx = base + (int)grp.thread_rank();
-    if (idx < s.cap) s.keys[idx] = ((unsigned long long)(unsigned)a << s.keyShift) | (unsigned long long)(unsigned)b;
-    else atomicOr(&s.cnt->overflow, 1);
+    if (idx < s.cap) {
+        s.keys[idx] = key;
+        if (s.codes) s.codes[idx] = code;
+    } else atomicOr(&s.cnt->overflow, s.overflowBit);
+}
+__device__ __forceinline__ unsigned long long pair_key(int a, int b, int keyShift) {     // a > b
+    return ((unsigned long long)(unsigned)a << keyShift) | (unsigned long long)(unsigned)b;
 }
 
-// The reference's test, solver.cpp:264-266 (A = higher index).
+// The reference's test, solver.cpp:264-266.  Symmetric bit for bit in its arguments.
 __device__ __forceinline__ bool spheres_overlap(float4 pa, float4 pb) {
     V3 dp = xyz(pa) - xyz(pb);
     float r = pa.w + pb.w;
     return dot(dp, dp) <= r * r;
 }
 
-// K1c: small-vs-small through the 27-cell neighbourhood; each pair is emitted
-// by its higher-index member.
-__global__ void bp_pairs_small(BodyView b, GridView g, PairSink sink) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= b.n) return;
-    if (g.keySorted[p] > g.tableMask) return;
-    int i = g.valSorted[p];
-    float4 pi = g.sortedPos[p];
-    int4 ci = g.sortedCell[p];
-    for (int dz = -1; dz <= 1; ++dz)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-                int nx = ci.x + dx, ny = ci.y + dy, nz = ci.z + dz;
-                unsigned hk = cell_hash(nx, ny, nz, ci.w) & g.tableMask;
-                int q0 = g.cellStart[hk], q1 = g.cellEnd[hk];
-                for (int q = q0; q < q1; ++q) {
-                    int4 cq = g.sortedCell[q];
-                    if (cq.x != nx || cq.y != ny || cq.z != nz || cq.w != ci.w) continue;
-                    int j = g.valSorted[q];
-                    if (j >= i) continue;
-                    if (spheres_overlap(pi, g.sortedPos[q])) emit_pair(sink, i, j);
-                }
-            }
+__device__ __forceinline__ int find_key(const unsigned long long* keys, int n, unsigned long long k) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+    return (lo < n && keys[lo] == k) ? lo : -1;
+}
+
+// K1c: small-vs-small sphere-overlap pairs (solver.cpp:262-266).  Every unordered pair of cells is swept from ONE side:
+// a body looks at its own cell (later sorted positions only) and at the 13 neighbour cells that follow its own in
+// (z, y, x) order — half the lookups and sphere tests of a full 27-cell sweep.  16 lanes per body, one neighbour cell
+// per lane (14 used): the hash lookup -> bucket range -> bucket walk chain is one cell long instead of fourteen, which
+// is what this latency-bound kernel is made of.  Pairs come out unsorted; A (the high half of the key) is the higher
+// creation index: the reference's list is newest first, so its earlier-in-list body is the higher id.
+// Appends to the pair list are staged per block in shared memory and flushed with ONE global atomic per block: a
+// per-warp atomicAdd on the single list counter serialises at its L2 slice (millions of same-address atomics per step
+// were most of this kernel's time).
+constexpr int kSweepStage = 1024;          // staged keys per block of 16 bodies (about 150 expected on a dense pile)
+__global__ void __launch_bounds__(kThreads) bp_sweep(BodyView b, GridView g, PairSink sink) {
+    __shared__ unsigned long long sKeys[kSweepStage];
+    __shared__ int sCount, sBase;
+    if (threadIdx.x == 0) sCount = 0;
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = t >> 4, k = t & 15;
+    if (p < b.n && k < 14 && g.keySorted[p] <= g.tableMask) {
+        // k = 0: own cell; 1: (+1,0,0); 2..4: (dx,+1,0); 5..13: (dx,dy,+1)
+        int dx, dy, dz;
+        if (k < 2) { dx = k; dy = 0; dz = 0; }
+        else if (k < 5) { dx = k - 3; dy = 1; dz = 0; }
+        else { dx = (k - 5) % 3 - 1; dy = (k - 5) / 3 - 1; dz = 1; }
+        int i = g.valSorted[p];
+        float4 pi = g.sortedPos[p];
+        int world = g.sortedCell[p].y;
+        int3 ci = cell_of(pi, g.cell);
+        int nx = ci.x + dx, ny = ci.y + dy, nz = ci.z + dz;
+        int2 r = g.cellRange[cell_hash(nx, ny, nz, world) & g.tableMask];
+        int want = pack_cell(nx, ny, nz);
+        int q = (k == 0) ? (r.x > p + 1 ? r.x : p + 1) : r.x;
+        for (; q < r.y; ++q) {
+            int2 cq = g.sortedCell[q];
+            if (cq.x != want || cq.y != world) continue;
+            if (!spheres_overlap(pi, g.sortedPos[q])) continue;
+            int j = g.valSorted[q];
+            unsigned long long key = i > j ? pair_key(i, j, sink.keyShift) : pair_key(j, i, sink.keyShift);
+            cg::coalesced_group grp = cg::coalesced_threads();
+            int base = 0;
+            if (grp.thread_rank() == 0) base = atomicAdd(&sCount, (int)grp.size());
+            int idx = grp.shfl(base, 0) + (int)grp.thread_rank();
+            if (idx < kSweepStage) sKeys[idx] = key;
+            else emit_pair(sink, key, 1);                  // stage full (a very dense neighbourhood): straight to the list
+        }
+    }
+    __syncthreads();
+    int staged = sCount < kSweepStage ? sCount : kSweepStage;
+    if (threadIdx.x == 0 && staged > 0) sBase = atomicAdd(sink.count, staged);
+    __syncthreads();
+    for (int e = threadIdx.x; e < staged; e += blockDim.x) {
+        int idx = sBase + e;
+        if (idx < sink.cap) sink.keys[idx] = sKeys[e];
+        else atomicOr(&sink.cnt->overflow, sink.overflowBit);
+    }
 }
 
 // K1d: every body against the large bodies of its own world.
-__global__ void bp_pairs_large(BodyView b, GridView g, PairSink sink) {
+__global__ void bp_large(BodyView b, GridView g, PairSink sink) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= b.n) return;
     int w = b.worldId[j];
@@ -131,42 +176,35 @@ __global__ void bp_pairs_large(BodyView b, GridView g, PairSink sink) {
         if (l == j) continue;
         if (jLarge && j > l) continue;            // large-large pairs: emitted once, by the lower index
         float4 pl = b.pose[l].pos; pl.w = body_radius(b.size[l]);
-        int a = j > l ? j : l, c = j > l ? l : j;
-        float4 pa = j > l ? pj : pl, pb = j > l ? pl : pj;
-        if (spheres_overlap(pa, pb)) emit_pair(sink, a, c);
+        if (spheres_overlap(pj, pl)) emit_pair(sink, j > l ? pair_key(j, l, sink.keyShift) : pair_key(l, j, sink.keyShift), 1);
     }
 }
 
-// K2: manifolds that survived last step persist as candidates whether or not
-// their spheres still overlap (solver.cpp:274-279 only deletes on initialize()==false).
-__global__ void bp_append_persisting(ManifoldSet old, int nOld, PairSink sink) {
+// K2: manifolds that survived last step persist as candidates whether or not their spheres still overlap
+// (solver.cpp:274-279 only deletes on initialize()==false).  Pairs whose spheres DO overlap were emitted by the sweeps
+// above; this kernel adds the rest (rare), so every candidate appears exactly once.
+__global__ void bp_persisting(BodyView b, ManifoldSet old, int nOld, PairSink sink) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nOld) return;
-    if (old.hdr[m].z <= 0) return;
-    cg::coalesced_group grp = cg::coalesced_threads();
-    int base = 0;
-    if (grp.thread_rank() == 0) base = atomicAdd(&sink.cnt->nCand, (int)grp.size());
-    base = grp.shfl(base, 0);
-    int idx = base + (int)grp.thread_rank();
-    if (idx < sink.cap) sink.keys[idx] = old.key[m];
-    else atomicOr(&sink.cnt->overflow, 1);
+    int4 h = old.hdr[m];
+    if (h.z <= 0) return;
+    float4 pa = b.pose[h.x].pos; pa.w = body_radius(b.size[h.x]);
+    float4 pb = b.pose[h.y].pos; pb.w = body_radius(b.size[h.y]);
+    if (!spheres_overlap(pa, pb)) emit_pair(sink, old.key[m], 1);
 }
 
-__device__ __forceinline__ int find_key(const unsigned long long* keys, int n, unsigned long long k) {
-    int lo = 0, hi = n;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
-    return (lo < n && keys[lo] == k) ? lo : -1;
-}
-
-// K3a: SAT cull, one thread per sorted candidate.  info = 0 (dropped) or 1|axis<<1.
-__global__ void np_cull(BodyView b, const unsigned long long* cand, int nCand, int keyShift,
-                        const unsigned long long* excl, int nExcl, int* info, int* flag) {
+// K3a: SAT cull (collision.cpp:420-468), one thread per candidate in emission order — which follows the cell-sorted
+// body order, so neighbouring threads gather neighbouring poses.  Survivors {key, winning axis} go to `out`; only
+// they (about a fifth of the candidates on a dense pile) are sorted.  The candidate count is read on the device.
+__global__ void __launch_bounds__(kThreads) np_sat(BodyView b, const unsigned long long* cand, const int* nCand, int cap, int keyShift,
+                                                   const unsigned long long* excl, int nExcl, PairSink out) {
+    __shared__ int sWarp[kThreads / 32], sBase;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nCand) return;
-    unsigned long long k = cand[p];
-    int code = 0;
-    if (p == 0 || cand[p - 1] != k) {
-        if (nExcl == 0 || find_key(excl, nExcl, k) < 0) {
+    int n = *nCand; if (n > cap) n = cap;
+    int code = 0; unsigned long long k = 0;
+    if (p < n) {
+        k = cand[p];
+        if (!(nExcl > 0 && find_key(excl, nExcl, k) >= 0)) {
             int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
             BodyPose pa = b.pose[a], pb = b.pose[c];
             Obb A = make_obb(xyz(pa.pos), quat(pa.rot), xyz(b.size[a]));
@@ -174,15 +212,22 @@ __global__ void np_cull(BodyView b, const unsigned long long* cand, int nCand, i
             code = sat_test(A, B);
         }
     }
-    info[p] = code;
-    flag[p] = code ? 1 : 0;
-}
-
-__global__ void np_compact(const int* flag, const int* scan, int nCand, int* survP, Counters* cnt) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nCand) return;
-    if (flag[p]) survP[scan[p]] = p;
-    if (p == nCand - 1) cnt->nSurvive = scan[p] + flag[p];
+    // block-wide compaction of the survivors: one atomic on the list counter per block
+    unsigned vote = __ballot_sync(0xffffffffu, code != 0);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sWarp[warp] = __popc(vote);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { int c = sWarp[w]; sWarp[w] = tot; tot += c; }
+        sBase = tot > 0 ? atomicAdd(out.count, tot) : 0;
+    }
+    __syncthreads();
+    if (code) {
+        int idx = sBase + sWarp[warp] + __popc(vote & ((1u << lane) - 1u));
+        if (idx < out.cap) { out.keys[idx] = k; out.codes[idx] = code; }
+        else atomicOr(&out.cnt->overflow, out.overflowBit);
+    }
 }
 
 __device__ __forceinline__ void store_contact(const ManifoldSet& ms, int ci, const ContactState& c) {
@@ -199,12 +244,19 @@ __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int 
 // K3b: build the manifold of each surviving pair at its final (key-sorted)
 // slot, carrying lambda / penalty / stick anchors over from last step's
 // manifold of the same pair, then apply the per-step warm-start decay.
-__global__ void np_build(BodyView b, const unsigned long long* cand, const int* info, const int* survP, int nSurvive,
+__global__ void np_build(BodyView b, const unsigned long long* cand, const int* info, int nSurvive,
                          int keyShift, ManifoldSet old, int nOld, ManifoldSet out, int* mcount, SolveParams prm, Counters* cnt) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nSurvive) return;
-    int p = survP[s];
+    int p = s;
     unsigned long long k = cand[p];
+    if (s > 0 && cand[s - 1] == k) {      // the sweeps emit every pair once; a repeat would double a manifold: keep a dead slot, flag it
+        atomicOr(&cnt->overflow, 8);
+        out.key[s] = k; out.hdr[s] = make_int4((int)(k >> keyShift), (int)(k & ((1ull << keyShift) - 1ull)), 0, 0); mcount[s] = 0;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) { out.cA[s * 4 + i] = z; out.cB[s * 4 + i] = z; out.cN[s * 4 + i] = z; out.cL[s * 4 + i] = z; out.cP[s * 4 + i] = z; }
+        return;
+    }
     int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
     BodyPose pa = b.pose[a], pb = b.pose[c];
     float4 sa = b.size[a], sb = b.size[c];

@@ -139,21 +139,6 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
 }
 
 // ------------------------------------------------------------------ predict / warm-start decay of user forces
-// Diagnostics are kept per world (an ensemble batch reports each world separately).  Lanes of a warp that
-// belong to the same world combine first (match_any + masked reduce), then one atomic per (warp, world).
-__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
-    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));       // non-negative floats order like their bit patterns
-}
-struct WorldGroup {
-    unsigned peers; bool leader;
-    __device__ __forceinline__ WorldGroup(int world) {
-        peers = __match_any_sync(0xffffffffu, world);
-        leader = (__ffs(peers) - 1) == (int)(threadIdx.x & 31);
-    }
-    __device__ __forceinline__ float max_nonneg(float v) const { return __uint_as_float(__reduce_max_sync(peers, __float_as_uint(v))); }
-    __device__ __forceinline__ int sum(int v) const { return __reduce_add_sync(peers, v); }
-};
-
 __global__ void predict_bodies(BodyView b, SolveParams prm, Diag* diag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int dyn = 0, ev = 0, world = -1;

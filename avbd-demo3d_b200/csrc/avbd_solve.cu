@@ -446,9 +446,10 @@ __global__ void __launch_bounds__(kThreads) primal_solve(BodyView b, ForceView f
 }
 
 // ------------------------------------------------------------------ dual
-// One LIVE contact (solver.cpp:411-430 for manifold rows).
+// One LIVE contact (solver.cpp:411-430 for manifold rows).  Returns what the diagnostics need.
+struct DualOut { float sepn, lamN; int visits; };
 template <bool COH>
-__device__ __forceinline__ void dual_one(const BodyView& b, const ManifoldSet& ms, int ci, const SolveParams& prm, float alpha) {
+__device__ __forceinline__ DualOut dual_one(const BodyView& b, const ManifoldSet& ms, int ci, const SolveParams& prm, float alpha) {
     int4 h = ms.hdr[ci >> 2];
     BodyPose pa = load_pose<COH>(b.pose + h.x), pb = load_pose<COH>(b.pose + h.y);
     ContactState cs = load_contact_c<COH>(ms, ci);
@@ -457,12 +458,24 @@ __device__ __forceinline__ void dual_one(const BodyView& b, const ManifoldSet& m
     dual_contact(cs, ev, prm.beta);
     ms.cL[ci] = pack_lambda(cs);
     ms.cP[ci] = pack_penalty(cs);
+    DualOut o;
+    o.sepn = dot((xyz(pa.pos) + ev.wrA) - (xyz(pb.pos) + ev.wrB), cs.n);
+    o.lamN = cs.lam[0];
+    o.visits = (pa.pos.w > 0.0f ? 1 : 0) + (pb.pos.w > 0.0f ? 1 : 0);
+    return o;
 }
 
+template <bool DIAG>
 __global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSet ms, const int* __restrict__ contactList, int nContacts,
-                                                          SolveParams prm, float alpha) {
+                                                          SolveParams prm, float alpha, Diag* diag) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nContacts) dual_one<false>(b, ms, contactList[t], prm, alpha);
+    int world = -1, ci = 0; DualOut o{0.0f, 0.0f, 0};
+    if (t < nContacts) {
+        ci = contactList[t];
+        o = dual_one<false>(b, ms, ci, prm, alpha);
+        if (DIAG) world = b.worldId[ms.hdr[ci >> 2].x];
+    }
+    if (DIAG) reduce_contact_diag(world, o.sepn, o.lamN, world >= 0 ? 1 : 0, (world >= 0 && (ci & 3) == 0) ? 1 : 0, o.visits, diag);
 }
 
 // ------------------------------------------------------------------ persistent iteration loop (small worlds)
@@ -487,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 2) solve_loop_persistent(BodyView b,
                                                                      ManifoldSet ms, ForceView fv, const int* __restrict__ order,
                                                                      const int2* __restrict__ colRange, int nColours,
                                                                      const int* __restrict__ contactList, int nContacts, SolveParams prm,
-                                                                     Diag* diag, unsigned* barrier) {
+                                                                     Diag* diag, unsigned* barrier, bool contactDiag) {
     constexpr int BPB = kThreads / LPB;
     __shared__ float sSys[BPB * 27];
     unsigned target = 0;
@@ -504,8 +517,17 @@ __global__ void __launch_bounds__(kThreads, 2) solve_loop_persistent(BodyView b,
             grid_barrier(barrier, target);
         }
         if (it < prm.iterations) {
-            for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nContacts; t += gridDim.x * blockDim.x)
-                dual_one<true>(b, ms, contactList[t], prm, alpha);
+            bool last = contactDiag && it == total - 1;            // nothing moves after this pass: reduce the contact diagnostics here
+            int rounded = (nContacts + 31) & ~31;                   // whole warps stay in the loop (warp-level reductions below)
+            for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += gridDim.x * blockDim.x) {
+                int world = -1, ci = 0; DualOut o{0.0f, 0.0f, 0};
+                if (t < nContacts) {
+                    ci = contactList[t];
+                    o = dual_one<true>(b, ms, ci, prm, alpha);
+                    if (last) world = b.worldId[ms.hdr[ci >> 2].x];
+                }
+                if (last) reduce_contact_diag(world, o.sepn, o.lamN, world >= 0 ? 1 : 0, (world >= 0 && (ci & 3) == 0) ? 1 : 0, o.visits, diag);
+            }
             grid_barrier(barrier, target);
         }
     }
@@ -641,7 +663,7 @@ int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4*
 }
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, const int* contactList, int nContacts, SolveParams prm,
-                       Diag* diag, unsigned* barrier) {
+                       Diag* diag, unsigned* barrier, bool contactDiag) {
     constexpr int LPB = kLanesPerBody;
     static int maxBlocks = [] {
         int dev = 0, sms = 0, perSm = 0;
@@ -656,12 +678,13 @@ bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const 
     if (grid > maxBlocks) grid = maxBlocks;
     if (grid < 1) grid = 1;
     cudaMemsetAsync(barrier, 0, sizeof(unsigned), s);
-    void* args[] = {&b, &visitStart, &visits, &ms, &fv, &order, &colRange, &nColours, &contactList, &nContacts, &prm, &diag, &barrier};
+    void* args[] = {&b, &visitStart, &visits, &ms, &fv, &order, &colRange, &nColours, &contactList, &nContacts, &prm, &diag, &barrier, &contactDiag};
     return cudaLaunchCooperativeKernel((void*)solve_loop_persistent<LPB>, dim3(grid), dim3(kThreads), args, 0, s) == cudaSuccess;
 }
 
-void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, const int* contactList, int nContacts, SolveParams prm, float alpha) {
-    dual_contacts<<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, contactList, nContacts, prm, alpha);
+void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, const int* contactList, int nContacts, SolveParams prm, float alpha, Diag* diag) {
+    if (diag) dual_contacts<true><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, contactList, nContacts, prm, alpha, diag);
+    else      dual_contacts<false><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, contactList, nContacts, prm, alpha, nullptr);
 }
 void launch_dual_user_forces(cudaStream_t s, BodyView b, ForceView fv, SolveParams prm) {
     dual_user_forces<<<blocks_of(fv.nJoints + fv.nSprings, kThreads), kThreads, 0, s>>>(b, fv, prm);

@@ -22,6 +22,9 @@ def launches(path):
     h = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
     H, data = rows[h], rows[h + 1:]
     ki, vi, ui = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Unit")
+    if "--last-step" in sys.argv:       # one whole step: from the last launch of the step's first kernel to the end
+        starts = [i for i, r in enumerate(data) if "bp_cells" in r[ki]]
+        data = data[starts[-1]:]
     agg = collections.OrderedDict()
     for r in data:
         name = r[ki].split("(")[0].replace("void ", "")[:70]
