@@ -27,6 +27,8 @@ AVBD_HD Obb make_obb(V3 pos, Q4 rot, V3 size) {             // collision.cpp:56-
     return b;
 }
 AVBD_HD float adot(V3 a, V3 b) { return fabsf(dot(a, b)); }
+// Indexing by a run-time axis number with selects: a dynamically indexed ax[k] would push the whole Obb to local memory.
+AVBD_HD V3 obb_axis(const Obb& b, int k) { return k == 0 ? b.ax[0] : (k == 1 ? b.ax[1] : b.ax[2]); }
 
 // One axis.  Returns false when separated beyond the persistence margin.
 // `sep`/`n` are only meaningful when `counted` comes back true (degenerate
@@ -48,10 +50,10 @@ AVBD_HD bool sat_axis(const Obb& A, const Obb& B, V3 d, V3 axis, bool& counted, 
 
 AVBD_HD V3 sat_axis_dir(const Obb& A, const Obb& B, int k) {
     // k: 0-2 face of A, 3-5 face of B, 6-14 edge i*3+j
-    if (k < 3) return A.ax[k];
-    if (k < 6) return B.ax[k - 3];
+    if (k < 3) return obb_axis(A, k);
+    if (k < 6) return obb_axis(B, k - 3);
     int e = k - 6;
-    return cross(A.ax[e / 3], B.ax[e % 3]);
+    return cross(obb_axis(A, e / 3), obb_axis(B, e % 3));
 }
 
 // Full 15-axis test.  Returns 0 when separated / no valid face axis, else
@@ -80,79 +82,118 @@ AVBD_HD void face_axes(const Obb& b, int k, V3& u, V3& v, float& eu, float& ev) 
     else if (k == 1) { u = b.ax[0]; v = b.ax[2]; eu = b.h.x; ev = b.h.z; }
     else { u = b.ax[0]; v = b.ax[1]; eu = b.h.x; ev = b.h.y; }
 }
+AVBD_HD V3 sel3(bool c, V3 a, V3 b) { return mk3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
+AVBD_HD Obb sel_obb(bool c, const Obb& a, const Obb& b) {
+    Obb r; r.c = sel3(c, a.c, b.c); r.h = sel3(c, a.h, b.h);
+    r.ax[0] = sel3(c, a.ax[0], b.ax[0]); r.ax[1] = sel3(c, a.ax[1], b.ax[1]); r.ax[2] = sel3(c, a.ax[2], b.ax[2]);
+    return r;
+}
 
 constexpr int kMaxPoly = 16;
 
-// Sutherland-Hodgman against dot(n,p) <= off.  collision.cpp:136-174
-AVBD_HD int clip_poly(const V3* in, int nin, V3 n, float off, V3* out) {
+// Scratch of the Sutherland-Hodgman clipper: two buffers of kMaxPoly vertices.  Per-thread arrays of this size live in
+// local memory; at a million manifolds per step that traffic does not fit L2 and spills to HBM, so the device kernels keep
+// the polygons in shared memory (PolyShared, one column per thread) and only host code uses PolyLocal.
+struct PolyLocal {
+    V3 v[2][kMaxPoly];
+    AVBD_HD V3 get(int b, int i) const { return v[b][i]; }
+    AVBD_HD void set(int b, int i, V3 x) { v[b][i] = x; }
+};
+#ifdef __CUDACC__
+struct PolyShared {          // element (buffer b, vertex i, component c) of this thread at col[((b * kMaxPoly + i) * 3 + c) * stride]
+    float* col; int stride;
+    __device__ __forceinline__ V3 get(int b, int i) const {
+        const float* p = col + (size_t)((b * kMaxPoly + i) * 3) * stride;
+        return mk3(p[0], p[stride], p[2 * stride]);
+    }
+    __device__ __forceinline__ void set(int b, int i, V3 x) {
+        float* p = col + (size_t)((b * kMaxPoly + i) * 3) * stride;
+        p[0] = x.x; p[stride] = x.y; p[2 * stride] = x.z;
+    }
+};
+constexpr int kPolyFloatsPerThread = 2 * kMaxPoly * 3;
+#endif
+
+// Sutherland-Hodgman against dot(n,p) <= off, buffer `src` -> buffer `src ^ 1`.  collision.cpp:136-174
+template <class Poly>
+AVBD_HD int clip_poly(Poly& poly, int src, int nin, V3 n, float off) {
     if (nin <= 0) return 0;
-    int no = 0;
-    V3 a = in[nin - 1];
+    int no = 0, dst = src ^ 1;
+    V3 a = poly.get(src, nin - 1);
     float da = dot(n, a) - off;
     for (int i = 0; i < nin; ++i) {
-        V3 b = in[i];
+        V3 b = poly.get(src, i);
         float db = dot(n, b) - off;
         bool ain = da <= kPlaneEps, bin = db <= kPlaneEps;
         if (ain != bin) {
             float t = 0.0f, den = da - db;
             if (fabsf(den) > kSatEps) t = clampf(da / den, 0.0f, 1.0f);
-            if (no < kMaxPoly) out[no++] = a + (b - a) * t;
+            if (no < kMaxPoly) poly.set(dst, no++, a + (b - a) * t);
         }
-        if (bin && no < kMaxPoly) out[no++] = b;
+        if (bin && no < kMaxPoly) poly.set(dst, no++, b);
         a = b; da = db;
     }
     return no;
 }
 
+// Contacts leave the builder one at a time through `emit(feature, rA, rB, normal)` (in manifold order) so a consumer can
+// finish each one (warm start, C0, store) without holding the other three.
+struct ContactDedupe {        // midpoints of the contacts emitted so far (collision.cpp:176-190)
+    V3 mid[4]; int n;
+};
+
 // collision.cpp:176-206
-AVBD_HD bool push_contact(V3 posA, Q4 rotA, V3 posB, Q4 rotB, RawContact* out, int& n, V3* mids, V3 xA, V3 xB, int key, V3 nBA) {
+template <class Emit>
+AVBD_HD bool push_contact(V3 posA, Q4 rotA, V3 posB, Q4 rotB, ContactDedupe& dd, V3 xA, V3 xB, int key, V3 nBA, Emit& emit) {
     V3 mid = (xA + xB) * 0.5f;
-    for (int i = 0; i < n; ++i) if (len2(mid - mids[i]) < kMergeDistSq) return false;
-    if (n >= 4) return false;
-    RawContact& c = out[n];
-    c.feature = key;
-    c.rA = qrot(qconj(rotA), xA - posA);
-    c.rB = qrot(qconj(rotB), xB - posB);
-    c.normal = nBA;
-    mids[n] = mid; ++n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i < dd.n && len2(mid - dd.mid[i]) < kMergeDistSq) return false;
+    if (dd.n >= 4) return false;
+    emit(key, qrot(qconj(rotA), xA - posA), qrot(qconj(rotB), xB - posB), nBA);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i == dd.n) dd.mid[i] = mid;
+    ++dd.n;
     return true;
 }
 
 // collision.cpp:313-394 (+ helpers :94-134)
-AVBD_HD int face_manifold(V3 posA, Q4 rotA, V3 posB, Q4 rotB, const Obb& A, const Obb& B, bool refIsA, int refAxis, V3 nAB, RawContact* out) {
-    const Obb& R = refIsA ? A : B;
-    const Obb& I = refIsA ? B : A;
+template <class Poly, class Emit>
+AVBD_HD int face_manifold(V3 posA, Q4 rotA, V3 posB, Q4 rotB, const Obb& A, const Obb& B, bool refIsA, int refAxis, V3 nAB, Poly& poly, Emit& emit) {
+    Obb R = sel_obb(refIsA, A, B);
+    Obb I = sel_obb(refIsA, B, A);
     V3 outward = refIsA ? nAB : -nAB;
     V3 nBA = -nAB;
-    float sgn = dot(outward, R.ax[refAxis]) >= 0.0f ? 1.0f : -1.0f;
-    V3 fn = R.ax[refAxis] * sgn;
+    V3 rax = obb_axis(R, refAxis);
+    float sgn = dot(outward, rax) >= 0.0f ? 1.0f : -1.0f;
+    V3 fn = rax * sgn;
     V3 fc = R.c + fn * comp(R.h, refAxis);
     V3 fu, fv; float eu, ev;
     face_axes(R, refAxis, fu, fv, eu, ev);
     int inc = 0; float bestd = -FLT_MAX;
+#pragma unroll
     for (int i = 0; i < 3; ++i) { float d = adot(I.ax[i], fn); if (d > bestd) { bestd = d; inc = i; } }
-    float isg = dot(I.ax[inc], fn) > 0.0f ? -1.0f : 1.0f;
-    V3 inrm = I.ax[inc] * isg;
+    V3 iax = obb_axis(I, inc);
+    float isg = dot(iax, fn) > 0.0f ? -1.0f : 1.0f;
+    V3 inrm = iax * isg;
     V3 icen = I.c + inrm * comp(I.h, inc);
     V3 iu, iv; float ieu, iev;
     face_axes(I, inc, iu, iv, ieu, iev);
-    V3 p0[kMaxPoly], p1[kMaxPoly];
-    p0[0] = (icen + iu * ieu) + iv * iev;
-    p0[1] = (icen - iu * ieu) + iv * iev;
-    p0[2] = (icen - iu * ieu) - iv * iev;
-    p0[3] = (icen + iu * ieu) - iv * iev;
+    poly.set(0, 0, (icen + iu * ieu) + iv * iev);
+    poly.set(0, 1, (icen - iu * ieu) + iv * iev);
+    poly.set(0, 2, (icen - iu * ieu) - iv * iev);
+    poly.set(0, 3, (icen + iu * ieu) - iv * iev);
     int cnt = 4;
-    cnt = clip_poly(p0, cnt, fu, dot(fu, fc) + eu, p1); if (!cnt) return 0;
+    cnt = clip_poly(poly, 0, cnt, fu, dot(fu, fc) + eu); if (!cnt) return 0;
     V3 nu = -fu;
-    cnt = clip_poly(p1, cnt, nu, dot(nu, fc) + eu, p0); if (!cnt) return 0;
-    cnt = clip_poly(p0, cnt, fv, dot(fv, fc) + ev, p1); if (!cnt) return 0;
+    cnt = clip_poly(poly, 1, cnt, nu, dot(nu, fc) + eu); if (!cnt) return 0;
+    cnt = clip_poly(poly, 0, cnt, fv, dot(fv, fc) + ev); if (!cnt) return 0;
     V3 nv = -fv;
-    cnt = clip_poly(p1, cnt, nv, dot(nv, fc) + ev, p0); if (!cnt) return 0;
+    cnt = clip_poly(poly, 1, cnt, nv, dot(nv, fc) + ev); if (!cnt) return 0;
 
-    int n = 0; V3 mids[4];
+    ContactDedupe dd; dd.n = 0;
     int prefix = ((refIsA ? 0 : 1) << 24) | ((refAxis & 0xFF) << 16) | ((inc & 0xFF) << 8);
-    for (int i = 0; i < cnt && n < 4; ++i) {
-        V3 pi = p0[i];
+    for (int i = 0; i < cnt && dd.n < 4; ++i) {
+        V3 pi = poly.get(0, i);
         float dist = dot(pi - fc, fn);
         if (dist > kCollisionMargin) continue;
         V3 pr = pi - fn * dist;
@@ -164,18 +205,19 @@ AVBD_HD int face_manifold(V3 posA, Q4 rotA, V3 posB, Q4 rotB, const Obb& A, cons
         int qu = (int)floorf(clampf((un + 1.0f) * 7.5f, 0.0f, 15.0f));
         int qv = (int)floorf(clampf((vn + 1.0f) * 7.5f, 0.0f, 15.0f));
         int key = prefix | ((qu & 0x0F) << 4) | (qv & 0x0F);
-        push_contact(posA, rotA, posB, rotB, out, n, mids, xA, xB, key, nBA);
+        push_contact(posA, rotA, posB, rotB, dd, xA, xB, key, nBA, emit);
     }
-    return n;
+    return dd.n;
 }
 
 AVBD_HD void support_edge(const Obb& b, int k, V3 dir, V3& e0, V3& e1) {      // collision.cpp:249-263
     int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
-    float s1 = dot(dir, b.ax[k1]) >= 0.0f ? 1.0f : -1.0f;
-    float s2 = dot(dir, b.ax[k2]) >= 0.0f ? 1.0f : -1.0f;
-    V3 ec = (b.c + b.ax[k1] * (comp(b.h, k1) * s1)) + b.ax[k2] * (comp(b.h, k2) * s2);
-    e0 = ec - b.ax[k] * comp(b.h, k);
-    e1 = ec + b.ax[k] * comp(b.h, k);
+    V3 a0 = obb_axis(b, k), a1 = obb_axis(b, k1), a2 = obb_axis(b, k2);
+    float s1 = dot(dir, a1) >= 0.0f ? 1.0f : -1.0f;
+    float s2 = dot(dir, a2) >= 0.0f ? 1.0f : -1.0f;
+    V3 ec = (b.c + a1 * (comp(b.h, k1) * s1)) + a2 * (comp(b.h, k2) * s2);
+    e0 = ec - a0 * comp(b.h, k);
+    e1 = ec + a0 * comp(b.h, k);
 }
 
 AVBD_HD void seg_closest(V3 p0, V3 p1, V3 q0, V3 q1, V3& c0, V3& c1) {        // collision.cpp:265-311
@@ -204,7 +246,8 @@ AVBD_HD void seg_closest(V3 p0, V3 p1, V3 q0, V3 q1, V3& c0, V3& c1) {        //
 
 // Emits the contacts for the axis `satCode` names (from sat_test on the same
 // poses).  collision.cpp:470-476
-AVBD_HD int build_contacts(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 sizeB, int satCode, RawContact* out) {
+template <class Poly, class Emit>
+AVBD_HD int build_contacts_emit(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 sizeB, int satCode, Poly& poly, Emit& emit) {
     Obb A = make_obb(posA, rotA, sizeA), B = make_obb(posB, rotB, sizeB);
     int k = satCode >> 1;
     V3 d = B.c - A.c;
@@ -216,14 +259,33 @@ AVBD_HD int build_contacts(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 size
         support_edge(A, ia, n, a0, a1);
         support_edge(B, ib, -n, b0, b1);
         seg_closest(a0, a1, b0, b1, xA, xB);
-        int cnt = 0; V3 mids[4];
+        ContactDedupe dd; dd.n = 0;
         int key = (2 << 24) | ((ia & 0xFF) << 8) | (ib & 0xFF);
-        push_contact(posA, rotA, posB, rotB, out, cnt, mids, xA, xB, key, -n);
-        return cnt;
+        push_contact(posA, rotA, posB, rotB, dd, xA, xB, key, -n, emit);
+        return dd.n;
     }
     // one instance for both reference sides: two inlined copies would run back to back in every mixed warp
     bool refIsA = k < 3;
-    return face_manifold(posA, rotA, posB, rotB, A, B, refIsA, refIsA ? k : k - 3, n, out);
+    return face_manifold(posA, rotA, posB, rotB, A, B, refIsA, refIsA ? k : k - 3, n, poly, emit);
+}
+
+// Array form (host mirror, parity harness): contacts collected into out[4].
+struct RawContactCollector {
+    RawContact* out; int n;
+    AVBD_HD void operator()(int feature, V3 rA, V3 rB, V3 normal) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i == n) { out[i].feature = feature; out[i].rA = rA; out[i].rB = rB; out[i].normal = normal; }
+        ++n;
+    }
+};
+template <class Poly>
+AVBD_HD int build_contacts(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 sizeB, int satCode, RawContact* out, Poly& poly) {
+    RawContactCollector col{out, 0};
+    return build_contacts_emit(posA, rotA, sizeA, posB, rotB, sizeB, satCode, poly, col);
+}
+inline int build_contacts(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 sizeB, int satCode, RawContact* out) {   // host only
+    PolyLocal poly;
+    return build_contacts(posA, rotA, sizeA, posB, rotB, sizeB, satCode, out, poly);
 }
 
 } // namespace avbd

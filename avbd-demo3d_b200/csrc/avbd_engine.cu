@@ -86,10 +86,11 @@ struct avbd_world {
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<int> candCode, candCodeSorted;
-    DevBuf<int> mcount, contactStart, contactList, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;
+    DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;
+    DevBuf<float4> stA, stB, stN, stL, stP;      // np_build staging (4 slots per manifold), packed by np_compact
 
     // manifolds (ping-pong)
-    struct MBuf { DevBuf<unsigned long long> key; DevBuf<int4> hdr; DevBuf<float4> cA, cB, cN, cL, cP; } mb[2];
+    struct MBuf { DevBuf<unsigned long long> key; DevBuf<int4> hdr; DevBuf<int> cstart, cM; DevBuf<float4> cA, cB, cN, cL, cP; } mb[2];
     int cur = 0, nM = 0;
 
     // graph
@@ -122,14 +123,20 @@ struct avbd_world {
 
     ManifoldSet mset(int which) {
         MBuf& b = mb[which];
-        ManifoldSet s; s.key = b.key.p; s.hdr = b.hdr.p; s.cA = b.cA.p; s.cB = b.cB.p; s.cN = b.cN.p; s.cL = b.cL.p; s.cP = b.cP.p;
+        ManifoldSet s; s.key = b.key.p; s.hdr = b.hdr.p; s.cstart = b.cstart.p; s.cM = b.cM.p; s.cA = b.cA.p; s.cB = b.cB.p; s.cN = b.cN.p; s.cL = b.cL.p; s.cP = b.cP.p;
         return s;
     }
     int ensure_manifolds(int which, size_t m) {
         MBuf& b = mb[which];
-        TRY(b.key.ensure(m, false, stream)); TRY(b.hdr.ensure(m, false, stream));
+        TRY(b.key.ensure(m, false, stream)); TRY(b.hdr.ensure(m, false, stream)); TRY(b.cstart.ensure(m + 1, false, stream)); TRY(b.cM.ensure(4 * m, false, stream));
         TRY(b.cA.ensure(4 * m, false, stream)); TRY(b.cB.ensure(4 * m, false, stream)); TRY(b.cN.ensure(4 * m, false, stream));
         TRY(b.cL.ensure(4 * m, false, stream)); TRY(b.cP.ensure(4 * m, false, stream));
+        return 0;
+    }
+    ContactStage stage() { ContactStage c; c.cA = stA.p; c.cB = stB.p; c.cN = stN.p; c.cL = stL.p; c.cP = stP.p; return c; }
+    int ensure_stage(size_t m) {
+        TRY(stA.ensure(4 * m, false, stream)); TRY(stB.ensure(4 * m, false, stream)); TRY(stN.ensure(4 * m, false, stream));
+        TRY(stL.ensure(4 * m, false, stream)); TRY(stP.ensure(4 * m, false, stream));
         return 0;
     }
     BodyView bview() {
@@ -370,14 +377,20 @@ int run_collide(avbd_world* w) {
     int nSurv = w->nCand;
     int nxt = w->cur ^ 1;
     if (nSurv > 0) {
-        TRY(w->ensure_manifolds(nxt, nSurv));
-        TRY(w->mcount.ensure(nSurv, false, s)); TRY(w->contactStart.ensure(nSurv, false, s)); TRY(w->contactList.ensure((size_t)nSurv * 4, false, s));
-        np_build<<<blocks_for(nSurv), kThreads, 0, s>>>(w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift,
-                                                          w->mset(w->cur), w->nM, w->mset(nxt), w->mcount.p, w->prm, w->dCnt);
+        TRY(w->ensure_manifolds(nxt, nSurv)); TRY(w->ensure_stage(nSurv));
+        TRY(w->mcount.ensure((size_t)nSurv + 1, false, s));
+        CK(cudaMemsetAsync(w->mcount.p + nSurv, 0, sizeof(int), s));
+        static const bool polySmem = [] {
+            cudaFuncSetAttribute(np_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildThreads * kPolyFloatsPerThread * (int)sizeof(float));
+            return true;
+        }();
+        (void)polySmem;
+        np_build<<<blocks_for(nSurv, kBuildThreads), kBuildThreads, kBuildThreads * kPolyFloatsPerThread * sizeof(float), s>>>(
+            w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift, w->mset(w->cur), w->nM, w->mset(nxt), w->stage(), w->mcount.p, w->prm, w->dCnt);
         w->launches++;
-        // dense list of live contacts (the dual's work list; also sizes the visit list)
-        TRY(exclusive_scan(w, w->mcount.p, w->contactStart.p, nSurv));
-        contact_list_fill<<<blocks_for(nSurv), kThreads, 0, s>>>(w->mset(nxt).hdr, w->contactStart.p, nSurv, w->contactList.p, w->dCnt);
+        // live contacts packed densely in manifold order (the dual's and the visit lists' index space)
+        TRY(exclusive_scan(w, w->mcount.p, w->mset(nxt).cstart, nSurv + 1));
+        np_compact<<<blocks_for(4ll * nSurv), kThreads, 0, s>>>(w->mset(nxt).hdr, w->mset(nxt).cstart, nSurv, w->stage(), w->mset(nxt), w->dCnt);
         w->launches++;
         TRY(read_counters(w));
         w->nContacts = w->hCnt->nContacts;
@@ -453,7 +466,7 @@ int run_colour(avbd_world* w) {
     CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
     visit_count<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
     TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
-    visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitStart.p, w->aux.p, w->visits.p);
+    visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->visits.p);
     w->launches += 2;
     w->graphValid = true;
     CK(cudaGetLastError());
@@ -480,7 +493,7 @@ int run_primal(avbd_world* w, float alpha, float* dxDev) {
 int run_dual(avbd_world* w, float alpha, bool lastOfStep = false) {
     cudaStream_t s = w->stream;
     if (w->nContacts > 0) {
-        launch_dual(s, w->bview(), w->mset(w->cur), w->contactList.p, w->nContacts, w->prm, alpha, lastOfStep ? w->dDiag.p : nullptr);
+        launch_dual(s, w->bview(), w->mset(w->cur), w->nContacts, w->prm, alpha, lastOfStep ? w->dDiag.p : nullptr);
         w->launches++;
     }
     if (lastOfStep) w->contactDiagDone = true;
@@ -498,8 +511,8 @@ int run_velocity(avbd_world* w) {
     if (w->n == 0) return 0;
     velocity_bodies<<<blocks_for(w->n), kThreads, 0, s>>>(w->bview(), w->prm, w->dDiag.p);
     w->launches++;
-    if (w->nM > 0 && !w->contactDiagDone) {     // not already reduced by the step's last dual pass
-        diagnostics_contacts<<<blocks_for((long long)w->nM * 4), kThreads, 0, s>>>(w->bview(), w->mset(w->cur), w->nM, w->dDiag.p);
+    if (w->nContacts > 0 && !w->contactDiagDone) {     // not already reduced by the step's last dual pass
+        diagnostics_contacts<<<blocks_for(w->nContacts), kThreads, 0, s>>>(w->bview(), w->mset(w->cur), w->nContacts, w->dDiag.p);
         w->launches++;
     }
     w->contactDiagDone = false;
@@ -524,7 +537,7 @@ int step_once(avbd_world* w) {
         unsigned* barrier = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(w->dCnt + 1) + 8);
         bool fuseDiag = !w->prm.postStabilize && w->prm.iterations > 0;
         persistent = launch_solve_loop(s, w->bview(), w->visitStart.p, w->visits.p, w->mset(w->cur), fvAll, w->colOrder.p, w->colRange.p,
-                                       w->nColours, w->maxColourCount, w->contactList.p, w->nContacts, w->prm, w->dDiag.p, barrier, fuseDiag);
+                                       w->nColours, w->maxColourCount, w->nContacts, w->prm, w->dDiag.p, barrier, fuseDiag);
         if (persistent) { w->launches++; w->contactDiagDone = fuseDiag; } else cudaGetLastError();
     }
     if (prof) {
@@ -615,12 +628,12 @@ void avbd_world_destroy(avbd_world* w) {
     w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellRange.release();
     w->sortedCell.release(); w->sortedPos.release(); w->largeList.release(); w->worldLargeStart.release();
     w->pairs.release(); w->cand.release(); w->candSorted.release(); w->candCode.release(); w->candCodeSorted.release();
-    for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.cL.release(); b.cP.release(); }
+    for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cstart.release(); b.cM.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.cL.release(); b.cP.release(); }
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
     w->dDiag.release(); w->dx.release(); w->sums.release(); w->temp.release(); w->stateDev.release();
-    w->mcount.release(); w->contactStart.release(); w->contactList.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
+    w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stL.release(); w->stP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
     if (w->hCnt) cudaFreeHost(w->hCnt);
@@ -936,15 +949,19 @@ int avbd_download_manifolds(avbd_world* w, int* ints, int* feats, int* stick, fl
     if (!w) return fail(AVBD_ERR_ARG, "null world");
     CK(cudaSetDevice(w->device));
     int nM = w->nM; if (!nM) return 0;
-    std::vector<int4> hdr(nM); std::vector<float4> cA(4 * nM), cB(4 * nM), cN(4 * nM), cL(4 * nM), cP(4 * nM);
+    size_t nC = (size_t)std::max(1, w->nContacts);
+    std::vector<int4> hdr(nM); std::vector<int> cstart(nM + 1); std::vector<float4> cA(nC), cB(nC), cN(nC), cL(nC), cP(nC);
     ManifoldSet ms = w->mset(w->cur);
     cudaStream_t s = w->stream;
     CK(cudaMemcpyAsync(hdr.data(), ms.hdr, nM * sizeof(int4), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(cA.data(), ms.cA, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(cB.data(), ms.cB, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(cN.data(), ms.cN, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(cL.data(), ms.cL, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(cP.data(), ms.cP, 4 * nM * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cstart.data(), ms.cstart, (nM + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (w->nContacts > 0) {
+        CK(cudaMemcpyAsync(cA.data(), ms.cA, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cB.data(), ms.cB, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cN.data(), ms.cN, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cL.data(), ms.cL, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(cP.data(), ms.cP, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
     int live = 0;
     for (int m = 0; m < nM; ++m) {
@@ -955,7 +972,7 @@ int avbd_download_manifolds(avbd_world* w, int* ints, int* feats, int* stick, fl
         float mu; std::memcpy(&mu, &hdr[m].w, 4);
         f[0] = mu;
         for (int c = 0; c < 4; ++c) {
-            int ci = 4 * m + c; bool on = c < nc;
+            bool on = c < nc; int ci = on ? cstart[m] + c : 0;
             int feat; std::memcpy(&feat, &cP[ci].w, 4);
             feats[4 * live + c] = on ? feat : 0;
             stick[4 * live + c] = on ? (cL[ci].w != 0.0f ? 1 : 0) : 0;
@@ -1041,7 +1058,8 @@ int avbd_collide_pairs(int device, int n, const float* a10, const float* b10, in
     CK(cudaMalloc(&dc, n * sizeof(int))); CK(cudaMalloc(&df, n * 4 * sizeof(int)));
     CK(cudaMemcpy(da, a10, n * 10 * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(db, b10, n * 10 * sizeof(float), cudaMemcpyHostToDevice));
-    np_collide_batch<<<blocks_for(n, 128), 128>>>(da, db, n, dc, df, dg);
+    cudaFuncSetAttribute(np_collide_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kPolyFloatsPerThread * (int)sizeof(float));
+    np_collide_batch<<<blocks_for(n, 128), 128, 128 * kPolyFloatsPerThread * sizeof(float)>>>(da, db, n, dc, df, dg);
     CK(cudaGetLastError());
     CK(cudaMemcpy(counts, dc, n * sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(feats4, df, n * 4 * sizeof(int), cudaMemcpyDeviceToHost));
@@ -1061,6 +1079,27 @@ int avbd_solve6x6(int device, int n, const float* lhs36, const float* rhs6, floa
     CK(cudaGetLastError());
     CK(cudaMemcpy(out6, dout, n * 6 * sizeof(float), cudaMemcpyDeviceToHost));
     cudaFree(dl); cudaFree(dr); cudaFree(dout);
+    return 0;
+}
+
+int avbd_debug_time_primal(avbd_world* w, int mode, int reps, float* ms) {
+    if (!w || !ms || reps < 1) return fail(AVBD_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(w->device));
+    if (!w->graphValid || w->nColours == 0) return fail(AVBD_ERR_ARG, "step the world first");
+    cudaStream_t s = w->stream;
+    TRY(w->sums.ensure((size_t)std::max(1, w->maxColourCount) * 28, false, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventRecord(w->ev[7], s));
+    for (int r = 0; r < reps; ++r)
+        for (int c = 0; c < w->nColours; ++c) {
+            int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
+            if (count > 0) launch_primal_experiment(s, mode, w->bview(), w->visitStart.p + first, w->visits.p, w->mset(w->cur), count, w->prm.alpha, w->sums.p, w->nContacts);
+        }
+    CK(cudaEventRecord(w->ev[8], s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(ms, w->ev[7], w->ev[8]));
+    *ms /= (float)reps;
+    CK(cudaGetLastError());
     return 0;
 }
 

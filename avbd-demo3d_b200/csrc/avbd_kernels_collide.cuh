@@ -230,61 +230,76 @@ __global__ void __launch_bounds__(kThreads) np_sat(BodyView b, const unsigned lo
     }
 }
 
-__device__ __forceinline__ void store_contact(const ManifoldSet& ms, int ci, const ContactState& c) {
-    ms.cA[ci] = f4(c.rA, c.C0n);
-    ms.cB[ci] = f4(c.rB, c.C0t1);
-    ms.cN[ci] = f4(c.n, c.C0t2);
-    ms.cL[ci] = pack_lambda(c);
-    ms.cP[ci] = pack_penalty(c);
-}
 __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int ci) {
     return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ms.cL[ci], ms.cP[ci]);
 }
 
-// K3b: build the manifold of each surviving pair at its final (key-sorted)
-// slot, carrying lambda / penalty / stick anchors over from last step's
-// manifold of the same pair, then apply the per-step warm-start decay.
-__global__ void np_build(BodyView b, const unsigned long long* cand, const int* info, int nSurvive,
-                         int keyShift, ManifoldSet old, int nOld, ManifoldSet out, int* mcount, SolveParams prm, Counters* cnt) {
+// K3b: build the manifold of each surviving pair at its final (key-sorted) slot, carrying lambda / penalty / stick
+// anchors over from last step's manifold of the same pair, then apply the per-step warm-start decay.  One thread per
+// manifold; contacts stream out of the builder one at a time straight into the 4-slot staging arrays (nothing is held in
+// per-thread arrays: the clipper's polygons live in shared memory, one column per thread), np_compact then packs the
+// live ones densely.
+constexpr int kBuildThreads = 128;
+__global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsigned long long* cand, const int* info, int nSurvive,
+                                                          int keyShift, ManifoldSet old, int nOld, ManifoldSet out, ContactStage st, int* mcount,
+                                                          SolveParams prm, Counters* cnt) {
+    extern __shared__ float sPoly[];
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nSurvive) return;
-    int p = s;
-    unsigned long long k = cand[p];
+    unsigned long long k = cand[s];
+    int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
+    out.key[s] = k;
     if (s > 0 && cand[s - 1] == k) {      // the sweeps emit every pair once; a repeat would double a manifold: keep a dead slot, flag it
         atomicOr(&cnt->overflow, 8);
-        out.key[s] = k; out.hdr[s] = make_int4((int)(k >> keyShift), (int)(k & ((1ull << keyShift) - 1ull)), 0, 0); mcount[s] = 0;
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = 0; i < 4; ++i) { out.cA[s * 4 + i] = z; out.cB[s * 4 + i] = z; out.cN[s * 4 + i] = z; out.cL[s * 4 + i] = z; out.cP[s * 4 + i] = z; }
+        out.hdr[s] = make_int4(a, c, 0, 0); mcount[s] = 0;
         return;
     }
-    int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
     BodyPose pa = b.pose[a], pb = b.pose[c];
     float4 sa = b.size[a], sb = b.size[c];
-    OldManifold om; om.n = 0;
+    V3 posA = xyz(pa.pos), posB = xyz(pb.pos); Q4 rotA = quat(pa.rot), rotB = quat(pb.rot);
+    int oldN = 0, oldBase = 0;
+    int oldFeat[4] = {0, 0, 0, 0};
     int slot = find_key(old.key, nOld, k);
     if (slot >= 0) {
-        om.n = old.hdr[slot].z;
-        for (int i = 0; i < om.n; ++i) om.ct[i] = load_contact(old, slot * 4 + i);
+        oldN = old.hdr[slot].z; oldBase = old.cstart[slot];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < oldN) oldFeat[j] = f2i(old.cP[oldBase + j].w);
     }
-    NewManifold nm;
-    manifold_initialize(xyz(pa.pos), quat(pa.rot), xyz(sa), xyz(pb.pos), quat(pb.rot), xyz(sb), info[p], om, prm, nm);
+    unsigned used = 0u;
+    int n = 0;
+    auto loadOld = [&](int j) { return load_contact(old, oldBase + j); };
+    auto emit = [&](int feature, V3 rA, V3 rB, V3 normal) {
+        ContactState ct = contact_initialize(posA, rotA, posB, rotB, feature, rA, rB, normal, oldN, oldFeat, used, loadOld, prm);
+        int ci = s * 4 + n;
+        st.cA[ci] = f4(ct.rA, ct.C0n); st.cB[ci] = f4(ct.rB, ct.C0t1); st.cN[ci] = f4(ct.n, ct.C0t2);
+        st.cL[ci] = pack_lambda(ct); st.cP[ci] = pack_penalty(ct);
+        ++n;
+    };
+    PolyShared poly{sPoly + threadIdx.x, (int)blockDim.x};
+    build_contacts_emit(posA, rotA, xyz(sa), posB, rotB, xyz(sb), info[s], poly, emit);
     float mu = sqrtf(sa.w * sb.w);                                   // manifold.cpp:73
-    out.key[s] = k;
-    out.hdr[s] = make_int4(a, c, nm.n, __float_as_int(mu));
-    mcount[s] = nm.n;
-    if (slot != s || om.n != nm.n) cnt->topoChanged = 1;      // same-value racing stores are fine
-    for (int i = 0; i < 4; ++i) {
-        if (i < nm.n) store_contact(out, s * 4 + i, nm.ct[i]);
-        else {
-            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            out.cA[s * 4 + i] = z; out.cB[s * 4 + i] = z; out.cN[s * 4 + i] = z; out.cL[s * 4 + i] = z; out.cP[s * 4 + i] = z;
-        }
-    }
+    out.hdr[s] = make_int4(a, c, n, __float_as_int(mu));
+    mcount[s] = n;
+    if (slot != s || oldN != n) cnt->topoChanged = 1;      // same-value racing stores are fine
+}
+
+// K3c: pack the live contacts of the staging slots densely (ci = cstart[m] + c) and record each contact's manifold.
+// cstart is the exclusive scan of mcount over nM + 1 entries (mcount[nM] = 0), so cstart[nM] is the live contact count.
+__global__ void np_compact(const int4* hdr, const int* cstart, int nM, ContactStage st, ManifoldSet out, Counters* cnt) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 4 * nM) return;
+    int m = t >> 2, c = t & 3;
+    if (t == 0) cnt->nContacts = cstart[nM];
+    if (c >= hdr[m].z) return;
+    int d = cstart[m] + c;
+    out.cA[d] = st.cA[t]; out.cB[d] = st.cB[t]; out.cN[d] = st.cN[t]; out.cL[d] = st.cL[t]; out.cP[d] = st.cP[t];
+    out.cM[d] = m;
 }
 
 // Stand-alone narrowphase on caller-supplied pairs (parity harness for
 // Manifold::collide, collision.cpp:420).  in: 2 x {size3 pos3 quat4} per pair.
 __global__ void np_collide_batch(const float* a10, const float* b10, int n, int* count, int* feats4, float* out36) {
+    extern __shared__ float sPoly[];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* a = a10 + 10 * i; const float* c = b10 + 10 * i;
@@ -292,7 +307,8 @@ __global__ void np_collide_batch(const float* a10, const float* b10, int n, int*
     V3 sb = mk3(c[0], c[1], c[2]), pb = mk3(c[3], c[4], c[5]); Q4 qb = qmk(c[6], c[7], c[8], c[9]);
     int code = sat_test(make_obb(pa, qa, sa), make_obb(pb, qb, sb));
     RawContact rc[4];
-    int k = code ? build_contacts(pa, qa, sa, pb, qb, sb, code, rc) : 0;
+    PolyShared poly{sPoly + threadIdx.x, (int)blockDim.x};
+    int k = code ? build_contacts(pa, qa, sa, pb, qb, sb, code, rc, poly) : 0;
     count[i] = k;
     for (int j = 0; j < 4; ++j) {
         feats4[4 * i + j] = j < k ? rc[j].feature : 0;

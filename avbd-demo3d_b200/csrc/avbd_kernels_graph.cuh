@@ -29,18 +29,9 @@ __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, in
     if (t == nM - 1 || bKeySorted[t + 1] != k) adjRange[k].w = t + 1;
 }
 
-// ------------------------------------------------------------------ dense contact / visit lists
-// Manifold slots hold up to 4 contacts but the live count varies (about 2 on a settled box grid), so the
-// per-iteration kernels never walk slots: the dual walks `contactList` (live contact ids ci = 4m+c) and the
-// primal walks, per dynamic body, a run of `visits` — one entry per live contact of every manifold touching the
-// body, rebuilt whenever the topology changes.
-__global__ void contact_list_fill(const int4* hdr, const int* contactStart, int nM, int* contactList, Counters* cnt) {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= nM) return;
-    int n = hdr[m].z, s = contactStart[m];
-    for (int c = 0; c < n; ++c) contactList[s + c] = 4 * m + c;
-    if (m == nM - 1) cnt->nContacts = s + n;
-}
+// ------------------------------------------------------------------ contact-visit lists
+// Contacts are stored densely (np_compact), so the dual walks them by index; the primal walks, per dynamic body, a run
+// of `visits` — one entry per live contact of every manifold touching the body, rebuilt whenever the topology changes.
 // Both run over the COLOUR-SORTED body order (colOrder[k], k = 0..nDyn-1): visitStart[k] is indexed by that position, so the
 // visits of the bodies of one colour tile are one contiguous run of `visits` and a tile can be walked one visit per thread.
 // Entry: {contact id, other body, (visiting body << 2) | anisotropic-inertia << 1 | body-is-A, friction bits}.
@@ -54,8 +45,8 @@ __global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange,
     for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z;
     visitCount[t] = k;
 }
-__global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* visitStart,
-                           const BodyAux* aux, int4* visits) {
+__global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
+                           const int* visitStart, const BodyAux* aux, int4* visits) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = colOrder[t];
@@ -63,8 +54,8 @@ __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, 
     int o = visitStart[t];
     float4 I = aux[i].inert;
     int idx = (i << 2) | ((I.x == I.y && I.y == I.z) ? 0 : 2);
-    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(4 * m + c, h.y, idx | 1, h.w); }
-    for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(4 * m + c, h.x, idx, h.w); }
+    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; int c0 = cstart[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.y, idx | 1, h.w); }
+    for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; int c0 = cstart[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.x, idx, h.w); }
 }
 
 // ------------------------------------------------------------------ colouring
@@ -192,39 +183,24 @@ __global__ void velocity_bodies(BodyView b, SolveParams prm, Diag* diag) {
     }
 }
 
-// solver.cpp:472-497
-__global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nM, Diag* diag) {
+// solver.cpp:472-497, one thread per live contact (only when the step's last dual pass did not already reduce them)
+__global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nContacts, Diag* diag) {
     int ci = blockIdx.x * blockDim.x + threadIdx.x;
-    float pen = 0.0f, viol = 0.0f, lam = 0.0f; int nc = 0, nm = 0, nv = 0; int world = -1;
-    if (ci < nM * 4) {
-        int m = ci >> 2, c = ci & 3;
+    float sepn = 0.0f, lam = 0.0f; int nm = 0, nv = 0; int world = -1;
+    if (ci < nContacts) {
+        int m = ms.cM[ci];
         int4 h = ms.hdr[m];
         world = b.worldId[h.x];
-        if (c == 0 && h.z > 0) { nm = 1; nc = h.z; }
-        if (c < h.z) {
-            BodyPose pa = b.pose[h.x], pb = b.pose[h.y];
-            nv = (pa.pos.w > 0.0f ? 1 : 0) + (pb.pos.w > 0.0f ? 1 : 0);
-            float4 a4 = ms.cA[ci], b4 = ms.cB[ci], n4 = ms.cN[ci];
-            V3 pA = xyz(pa.pos) + qrot(quat(pa.rot), xyz(a4));
-            V3 pB = xyz(pb.pos) + qrot(quat(pb.rot), xyz(b4));
-            float sepn = dot(pA - pB, xyz(n4));
-            pen = fmax2(0.0f, -sepn);
-            viol = fmax2(0.0f, kPenetrationSlop - sepn);
-            lam = fabsf(ms.cL[ci].x);
-        }
+        nm = (ci == 0 || ms.cM[ci - 1] != m) ? 1 : 0;
+        BodyPose pa = b.pose[h.x], pb = b.pose[h.y];
+        nv = (pa.pos.w > 0.0f ? 1 : 0) + (pb.pos.w > 0.0f ? 1 : 0);
+        float4 a4 = ms.cA[ci], b4 = ms.cB[ci], n4 = ms.cN[ci];
+        V3 pA = xyz(pa.pos) + qrot(quat(pa.rot), xyz(a4));
+        V3 pB = xyz(pb.pos) + qrot(quat(pb.rot), xyz(b4));
+        sepn = dot(pA - pB, xyz(n4));
+        lam = ms.cL[ci].x;
     }
-    WorldGroup wg(world);
-    pen = wg.max_nonneg(pen); viol = wg.max_nonneg(viol); lam = wg.max_nonneg(lam);
-    nc = wg.sum(nc); nm = wg.sum(nm); nv = wg.sum(nv);
-    if (wg.leader && world >= 0) {
-        Diag* d = diag + world;
-        if (pen > 0.0f) atomic_max_nonneg(&d->maxPenetration, pen);
-        if (viol > 0.0f) atomic_max_nonneg(&d->maxViolation, viol);
-        if (lam > 0.0f) atomic_max_nonneg(&d->maxNormalImpulse, lam);
-        if (nc) atomicAdd(&d->activeContacts, nc);
-        if (nm) atomicAdd(&d->activeManifolds, nm);
-        if (nv) atomicAdd(&d->contactVisits, nv);
-    }
+    reduce_contact_diag(world, sepn, lam, world >= 0 ? 1 : 0, nm, nv, diag);
 }
 
 // Rigid public state <-> the 13-float-per-body host layout (pos3 quat4 lin3 ang3), on the device so the

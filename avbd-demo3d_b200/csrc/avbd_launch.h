@@ -71,15 +71,18 @@ constexpr int kLanesPerBody = 4;
 // `sums` is scratch for the split path: 28 floats per body of the colour.  Returns the number of kernels launched.
 int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
                   const int* order, int count, float avgVisits, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag);
-// Dual + penalty ramp over the nContacts live contacts in contactList.
+// Dual + penalty ramp over the nContacts live (densely stored) contacts.
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics
 // (solver.cpp:472-497) are reduced here from the values already in registers instead of by a separate sweep.
-void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, const int* contactList, int nContacts, SolveParams prm, float alpha, Diag* diag);
+void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, Diag* diag);
 // Small worlds: the whole iteration loop (solver.cpp:340-431, manifold rows only) in ONE cooperative launch.
 // Returns false if the launch was refused (caller falls back to per-colour launches).
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
-                       const int2* colRange, int nColours, int maxColourCount, const int* contactList, int nContacts, SolveParams prm,
+                       const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
                        Diag* diag, unsigned* barrier, bool contactDiag);
+// Measurement aid (avbd_debug_time_primal): one colour's visit-sum kernel in mode 0 (product), 1 (memory only), 2 (math only).
+void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, int count, float alpha,
+                              float* sums, int nContacts);
 void launch_dual_user_forces(cudaStream_t s, BodyView b, ForceView fv, SolveParams prm);
 void launch_solve6_batch(cudaStream_t s, const float* lhs36, const float* rhs6, int n, float* out6);
 

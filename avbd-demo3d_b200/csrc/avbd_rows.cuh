@@ -230,50 +230,72 @@ struct NewManifold {
     ContactState ct[4];
 };
 
-// Manifold::initialize (manifold.cpp:71-175) followed by the per-row warm-start
-// decay of Solver::step (solver.cpp:281-293; manifold rows are hard so the
-// stiffness cap at :290-292 never applies).
-AVBD_HD void manifold_initialize(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 sizeB, int satCode,
-                                 const OldManifold& old, const SolveParams& prm, NewManifold& out) {
-    RawContact raw[4];
-    out.n = build_contacts(posA, rotA, sizeA, posB, rotB, sizeB, satCode, raw);
-    bool used[4] = {false, false, false, false};
-    for (int i = 0; i < out.n; ++i) {
-        ContactState& c = out.ct[i];
-        c.feature = raw[i].feature; c.rA = raw[i].rA; c.rB = raw[i].rB; c.n = raw[i].normal;
-        for (int k = 0; k < 3; ++k) { c.lam[k] = 0.0f; c.pen[k] = kPenaltyMin; }
-        c.stick = false;
-        int hit = -1;
-        for (int j = 0; j < old.n; ++j) { if (used[j]) continue; if (c.feature == old.ct[j].feature) { hit = j; break; } }
-        if (hit >= 0) {
-            used[hit] = true;
-            const ContactState& o = old.ct[hit];
-            V3 nn = unit_or(c.n, mk3(0.0f, 1.0f, 0.0f));
-            V3 on = unit_or(o.n, nn);
-            float nd = dot(nn, on);
-            V3 oldMid = ((posA + qrot(rotA, o.rA)) + (posB + qrot(rotB, o.rB))) * 0.5f;
-            V3 newMid = ((posA + qrot(rotA, c.rA)) + (posB + qrot(rotB, c.rB))) * 0.5f;
-            float drift2 = len2(newMid - oldMid);
-            bool warm = (nd >= kWarmNormalMinDot) && (drift2 <= kWarmMaxDrift * kWarmMaxDrift);
-            if (warm) for (int k = 0; k < 3; ++k) { c.lam[k] = o.lam[k]; c.pen[k] = clampf(o.pen[k], kPenaltyMin, kManifoldPenaltyCap); }
-            bool reuse = false;
-            if (o.stick && warm) reuse = (nd >= kStickNormalMinDot) && (drift2 <= kStickAnchorMaxDrift * kStickAnchorMaxDrift);
-            c.stick = o.stick && reuse;
-            if (reuse) { c.rA = o.rA; c.rB = o.rB; }
+// One contact of Manifold::initialize (manifold.cpp:100-171) followed by the per-step warm-start decay of
+// Solver::step (solver.cpp:281-293; manifold rows are hard so the stiffness cap at :290-292 never applies).
+// `oldFeat[j]` (j < oldN) are last step's feature keys of the same pair, `used` the bit mask of old contacts already
+// matched (first unused equal feature wins, manifold.cpp:111-119); `loadOld(j)` fetches old contact j on a match.
+template <class LoadOld>
+AVBD_HD ContactState contact_initialize(V3 posA, Q4 rotA, V3 posB, Q4 rotB, int feature, V3 rA, V3 rB, V3 normal,
+                                        int oldN, const int (&oldFeat)[4], unsigned& used, LoadOld&& loadOld, const SolveParams& prm) {
+    ContactState c;
+    c.feature = feature; c.rA = rA; c.rB = rB; c.n = normal;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { c.lam[k] = 0.0f; c.pen[k] = kPenaltyMin; }
+    c.stick = false;
+    int hit = -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (hit < 0 && j < oldN && !((used >> j) & 1u) && feature == oldFeat[j]) hit = j;
+    if (hit >= 0) {
+        used |= 1u << hit;
+        ContactState o = loadOld(hit);
+        V3 nn = unit_or(c.n, mk3(0.0f, 1.0f, 0.0f));
+        V3 on = unit_or(o.n, nn);
+        float nd = dot(nn, on);
+        V3 oldMid = ((posA + qrot(rotA, o.rA)) + (posB + qrot(rotB, o.rB))) * 0.5f;
+        V3 newMid = ((posA + qrot(rotA, c.rA)) + (posB + qrot(rotB, c.rB))) * 0.5f;
+        float drift2 = len2(newMid - oldMid);
+        bool warm = (nd >= kWarmNormalMinDot) && (drift2 <= kWarmMaxDrift * kWarmMaxDrift);
+        if (warm) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { c.lam[k] = o.lam[k]; c.pen[k] = clampf(o.pen[k], kPenaltyMin, kManifoldPenaltyCap); }
         }
-        V3 n, t1, t2;
-        contact_basis(c.n, n, t1, t2);
-        c.n = n;
-        V3 dlt = (posA + qrot(rotA, c.rA)) - (posB + qrot(rotB, c.rB));
-        c.C0n = dot(dlt, n) - kNormalContactMargin;
-        c.C0t1 = dot(dlt, t1);
-        c.C0t2 = dot(dlt, t2);
-        // warm-start decay, solver.cpp:281-288
-        for (int k = 0; k < 3; ++k) {
-            if (!prm.postStabilize) c.lam[k] *= prm.alpha * prm.gamma;
-            c.pen[k] = clampf(c.pen[k] * prm.gamma, kPenaltyMin, kPenaltyMax);
-        }
+        bool reuse = false;
+        if (o.stick && warm) reuse = (nd >= kStickNormalMinDot) && (drift2 <= kStickAnchorMaxDrift * kStickAnchorMaxDrift);
+        c.stick = o.stick && reuse;
+        if (reuse) { c.rA = o.rA; c.rB = o.rB; }
     }
+    V3 n, t1, t2;
+    contact_basis(c.n, n, t1, t2);
+    c.n = n;
+    V3 dlt = (posA + qrot(rotA, c.rA)) - (posB + qrot(rotB, c.rB));
+    c.C0n = dot(dlt, n) - kNormalContactMargin;
+    c.C0t1 = dot(dlt, t1);
+    c.C0t2 = dot(dlt, t2);
+    // warm-start decay, solver.cpp:281-288
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!prm.postStabilize) c.lam[k] *= prm.alpha * prm.gamma;
+        c.pen[k] = clampf(c.pen[k] * prm.gamma, kPenaltyMin, kPenaltyMax);
+    }
+    return c;
 }
+
+// Manifold::initialize on arrays (host mirror, host emulation; not compiled into the CUDA translation units): the same
+// builder and per-contact routine the kernels run.
+#ifndef __CUDACC__
+inline void manifold_initialize(V3 posA, Q4 rotA, V3 sizeA, V3 posB, Q4 rotB, V3 sizeB, int satCode,
+                                const OldManifold& old, const SolveParams& prm, NewManifold& out) {
+    int oldFeat[4] = {0, 0, 0, 0};
+    for (int j = 0; j < old.n && j < 4; ++j) oldFeat[j] = old.ct[j].feature;
+    unsigned used = 0u;
+    out.n = 0;
+    auto loadOld = [&](int j) { return old.ct[j]; };
+    auto emit = [&](int feature, V3 rA, V3 rB, V3 normal) {
+        out.ct[out.n++] = contact_initialize(posA, rotA, posB, rotB, feature, rA, rB, normal, old.n, oldFeat, used, loadOld, prm);
+    };
+    PolyLocal poly;
+    build_contacts_emit(posA, rotA, sizeA, posB, rotB, sizeB, satCode, poly, emit);
+}
+#endif
 
 } // namespace avbd

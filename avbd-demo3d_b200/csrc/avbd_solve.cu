@@ -345,9 +345,12 @@ struct VisitSmem {
 };
 constexpr int kSumStride = 28;
 
-template <int BPB, int MINB>
+// MODE 0 is the product.  MODE 1 / 2 are measurement aids behind avbd_debug_time_primal (never on the step path): 1 keeps the
+// memory accesses and drops the row math (the kernel's memory-system floor), 2 keeps the math and makes every index
+// sequential (its instruction-issue floor); neither writes solver state.
+template <int BPB, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits,
-                                                                    ManifoldSet ms, int count, float alpha, float* __restrict__ sums) {
+                                                                    ManifoldSet ms, int count, float alpha, float* __restrict__ sums, int nContacts = 0) {
     constexpr int L = kThreads / BPB;
     constexpr int CPL = (27 + L - 1) / L;
     __shared__ VisitSmem<BPB> sm;
@@ -366,6 +369,7 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, 
         if (v < v1) {
             int4 e = visits[v];
             int ci = e.x, self = e.z >> 2; bool isA = (e.z & 1) != 0, gyro = (e.z & 2) != 0;
+            if (MODE == 2) { ci = v % nContacts; self = v % b.n; e.y = (v + 1) % b.n; }
             BodyPose ps = load_pose_keep(b.pose + self, keep);
             BodyPose po = load_pose_keep(b.pose + e.y, keep);
             // contact geometry is read once per visit: stream it past L2 (evict-first) so it does not push the poses out
@@ -374,6 +378,11 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, 
             ContactState cs = unpack_contact(a4, b4, n4, l4, p4);
             ContactEval ev;
             float mu = __int_as_float(e.w);
+            if (MODE == 1) {
+                float q = ps.pos.x + ps.rot.y + po.pos.z + po.rot.w + a4.x + b4.y + n4.z + l4.w + p4.x + mu;
+#pragma unroll
+                for (int k = 0; k < 27; ++k) sm.c[k][t] = q;
+            } else {
             {   // one call with the operands swapped by selects: an if/else duplicates the code and mixed warps run both arms
                 float4 pa4 = isA ? ps.pos : po.pos, qa4 = isA ? ps.rot : po.rot, pb4 = isA ? po.pos : ps.pos, qb4 = isA ? po.rot : ps.rot;
                 contact_constraint(xyz(pa4), quat(qa4), pa4.w, xyz(pb4), quat(qb4), pb4.w, mu, alpha, cs, ev);
@@ -387,13 +396,14 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, 
             contact_system(sys, cs, ev, isA, gyro, invIw);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
-            if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) ms.cL[ci] = nl;
+            if (MODE == 0 && (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w)) ms.cL[ci] = nl;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
 #pragma unroll
             for (int k = 0; k < 6; ++k) { sm.c[6 + k][t] = sys.ll[k]; sm.c[21 + k][t] = sys.aa[k]; }
 #pragma unroll
             for (int k = 0; k < 9; ++k) sm.c[12 + k][t] = sys.la[k];
+            }
         }
         __syncthreads();
         if (rs < nb) {
@@ -447,10 +457,11 @@ __global__ void __launch_bounds__(kThreads) primal_solve(BodyView b, ForceView f
 
 // ------------------------------------------------------------------ dual
 // One LIVE contact (solver.cpp:411-430 for manifold rows).  Returns what the diagnostics need.
-struct DualOut { float sepn, lamN; int visits; };
-template <bool COH>
+struct DualOut { float sepn, lamN; int visits, world, first; };
+template <bool COH, bool DIAG>
 __device__ __forceinline__ DualOut dual_one(const BodyView& b, const ManifoldSet& ms, int ci, const SolveParams& prm, float alpha) {
-    int4 h = ms.hdr[ci >> 2];
+    int m = ms.cM[ci];
+    int4 h = ms.hdr[m];
     BodyPose pa = load_pose<COH>(b.pose + h.x), pb = load_pose<COH>(b.pose + h.y);
     ContactState cs = load_contact_c<COH>(ms, ci);
     ContactEval ev;
@@ -462,20 +473,17 @@ __device__ __forceinline__ DualOut dual_one(const BodyView& b, const ManifoldSet
     o.sepn = dot((xyz(pa.pos) + ev.wrA) - (xyz(pb.pos) + ev.wrB), cs.n);
     o.lamN = cs.lam[0];
     o.visits = (pa.pos.w > 0.0f ? 1 : 0) + (pb.pos.w > 0.0f ? 1 : 0);
+    o.world = -1; o.first = 0;
+    if (DIAG) { o.world = b.worldId[h.x]; o.first = (ci == 0 || ms.cM[ci - 1] != m) ? 1 : 0; }
     return o;
 }
 
 template <bool DIAG>
-__global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSet ms, const int* __restrict__ contactList, int nContacts,
-                                                          SolveParams prm, float alpha, Diag* diag) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int world = -1, ci = 0; DualOut o{0.0f, 0.0f, 0};
-    if (t < nContacts) {
-        ci = contactList[t];
-        o = dual_one<false>(b, ms, ci, prm, alpha);
-        if (DIAG) world = b.worldId[ms.hdr[ci >> 2].x];
-    }
-    if (DIAG) reduce_contact_diag(world, o.sepn, o.lamN, world >= 0 ? 1 : 0, (world >= 0 && (ci & 3) == 0) ? 1 : 0, o.visits, diag);
+__global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, Diag* diag) {
+    int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    DualOut o{0.0f, 0.0f, 0, -1, 0};
+    if (ci < nContacts) o = dual_one<false, DIAG>(b, ms, ci, prm, alpha);
+    if (DIAG) reduce_contact_diag(o.world, o.sepn, o.lamN, o.world >= 0 ? 1 : 0, o.first, o.visits, diag);
 }
 
 // ------------------------------------------------------------------ persistent iteration loop (small worlds)
@@ -498,8 +506,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
 template <int LPB>
 __global__ void __launch_bounds__(kThreads, 2) solve_loop_persistent(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
                                                                      ManifoldSet ms, ForceView fv, const int* __restrict__ order,
-                                                                     const int2* __restrict__ colRange, int nColours,
-                                                                     const int* __restrict__ contactList, int nContacts, SolveParams prm,
+                                                                     const int2* __restrict__ colRange, int nColours, int nContacts, SolveParams prm,
                                                                      Diag* diag, unsigned* barrier, bool contactDiag) {
     constexpr int BPB = kThreads / LPB;
     __shared__ float sSys[BPB * 27];
@@ -520,13 +527,9 @@ __global__ void __launch_bounds__(kThreads, 2) solve_loop_persistent(BodyView b,
             bool last = contactDiag && it == total - 1;            // nothing moves after this pass: reduce the contact diagnostics here
             int rounded = (nContacts + 31) & ~31;                   // whole warps stay in the loop (warp-level reductions below)
             for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += gridDim.x * blockDim.x) {
-                int world = -1, ci = 0; DualOut o{0.0f, 0.0f, 0};
-                if (t < nContacts) {
-                    ci = contactList[t];
-                    o = dual_one<true>(b, ms, ci, prm, alpha);
-                    if (last) world = b.worldId[ms.hdr[ci >> 2].x];
-                }
-                if (last) reduce_contact_diag(world, o.sepn, o.lamN, world >= 0 ? 1 : 0, (world >= 0 && (ci & 3) == 0) ? 1 : 0, o.visits, diag);
+                DualOut o{0.0f, 0.0f, 0, -1, 0};
+                if (t < nContacts) o = dual_one<true, true>(b, ms, t, prm, alpha);
+                if (last) reduce_contact_diag(o.world, o.sepn, o.lamN, o.world >= 0 ? 1 : 0, o.first, o.visits, diag);
             }
             grid_barrier(barrier, target);
         }
@@ -661,8 +664,14 @@ int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4*
 #undef AVBD_VV
 #undef AVBD_SV
 }
+void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, int count, float alpha,
+                              float* sums, int nContacts) {
+    if (mode == 1) primal_visit_sums<28, 3, 1><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, ms, count, alpha, sums, nContacts);
+    else if (mode == 2) primal_visit_sums<28, 3, 2><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, ms, count, alpha, sums, nContacts);
+    else primal_visit_sums<28, 3, 0><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, ms, count, alpha, sums, nContacts);
+}
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
-                       const int2* colRange, int nColours, int maxColourCount, const int* contactList, int nContacts, SolveParams prm,
+                       const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
                        Diag* diag, unsigned* barrier, bool contactDiag) {
     constexpr int LPB = kLanesPerBody;
     static int maxBlocks = [] {
@@ -678,13 +687,13 @@ bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const 
     if (grid > maxBlocks) grid = maxBlocks;
     if (grid < 1) grid = 1;
     cudaMemsetAsync(barrier, 0, sizeof(unsigned), s);
-    void* args[] = {&b, &visitStart, &visits, &ms, &fv, &order, &colRange, &nColours, &contactList, &nContacts, &prm, &diag, &barrier, &contactDiag};
+    void* args[] = {&b, &visitStart, &visits, &ms, &fv, &order, &colRange, &nColours, &nContacts, &prm, &diag, &barrier, &contactDiag};
     return cudaLaunchCooperativeKernel((void*)solve_loop_persistent<LPB>, dim3(grid), dim3(kThreads), args, 0, s) == cudaSuccess;
 }
 
-void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, const int* contactList, int nContacts, SolveParams prm, float alpha, Diag* diag) {
-    if (diag) dual_contacts<true><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, contactList, nContacts, prm, alpha, diag);
-    else      dual_contacts<false><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, contactList, nContacts, prm, alpha, nullptr);
+void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, Diag* diag) {
+    if (diag) dual_contacts<true><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, nContacts, prm, alpha, diag);
+    else      dual_contacts<false><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, nContacts, prm, alpha, nullptr);
 }
 void launch_dual_user_forces(cudaStream_t s, BodyView b, ForceView fv, SolveParams prm) {
     dual_user_forces<<<blocks_of(fv.nJoints + fv.nSprings, kThreads), kThreads, 0, s>>>(b, fv, prm);

@@ -7,10 +7,11 @@
 //   vel[i]   {lin | ang}, init[i] {pos0 | rot0}, prevLin[i], size[i] {sx,sy,sz,friction}
 // Manifolds (replaces 704-byte Manifold nodes, solver.h:112-143), slot m, sorted by pair key:
 //   mhdr[m]  {bodyA, bodyB, numContacts, friction-bits}     16 B
-//   contact arrays indexed ci = 4*m + c, one float4 per field so the 4 contacts of
-//   a manifold are one 64-byte run per field:
+//   cstart[m] first contact of manifold m; contacts are stored DENSE (ci = cstart[m] + c, live contacts only, about 2 per
+//   manifold on a box pile — a fixed 4-slot layout made every 64-byte DRAM granule half dead), one float4 per field:
 //     cA {rA.xyz, C0_n}  cB {rB.xyz, C0_t.x}  cN {normal.xyz, C0_t.y}
 //     cL {lambda_n, lambda_t1, lambda_t2, stick}   cP {penalty_n, penalty_t1, penalty_t2, feature-bits}
+//   cM[ci]   manifold of contact ci
 //   C / fmin / fmax (solver.h:91-92) are recomputed in registers by every
 //   consumer and never stored.
 #pragma once
@@ -36,6 +37,11 @@ struct SolveParams {          // Solver fields, solver.h:147-151, re-read every 
 struct ManifoldSet {          // one of the two ping-pong generations
     unsigned long long* key;  // packed pair key (A << keyShift) | B, ascending
     int4*   hdr;
+    int*    cstart;           // nM + 1 entries
+    int*    cM;               // per dense contact
+    float4* cA; float4* cB; float4* cN; float4* cL; float4* cP;
+};
+struct ContactStage {         // np_build's output before compaction: 4 slots per manifold (ci = 4*m + c)
     float4* cA; float4* cB; float4* cN; float4* cL; float4* cP;
 };
 
