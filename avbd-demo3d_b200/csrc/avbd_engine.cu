@@ -97,7 +97,7 @@ struct avbd_world {
     DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
     int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
-    long long graphReuses = 0; int persistentMaxBodies = 20000; unsigned* dBarrier = nullptr;
+    long long graphReuses = 0; int persistentMaxBodies = 4096;
 
     // user forces
     std::vector<JointRec> hJoints; std::vector<SpringRec> hSprings; std::vector<HostForce> hForces;
@@ -533,11 +533,10 @@ int step_once(avbd_world* w) {
     ForceView fvAll = w->fview();
     bool persistent = !prof && w->nColours > 0 && w->nDyn <= w->persistentMaxBodies && fvAll.nJoints + fvAll.nSprings == 0;
     if (persistent) {
-        // small world: the whole iteration loop in one cooperative launch (grid barriers instead of kernel boundaries)
-        unsigned* barrier = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(w->dCnt + 1) + 8);
+        // small world: the whole iteration loop in one cluster launch (cluster barriers instead of kernel boundaries)
         bool fuseDiag = !w->prm.postStabilize && w->prm.iterations > 0;
         persistent = launch_solve_loop(s, w->bview(), w->visitStart.p, w->visits.p, w->mset(w->cur), fvAll, w->colOrder.p, w->colRange.p,
-                                       w->nColours, w->maxColourCount, w->nContacts, w->prm, w->dDiag.p, barrier, fuseDiag);
+                                       w->nColours, w->maxColourCount, w->nContacts, w->prm, w->dDiag.p, fuseDiag);
         if (persistent) { w->launches++; w->contactDiagDone = fuseDiag; } else cudaGetLastError();
     }
     if (prof) {

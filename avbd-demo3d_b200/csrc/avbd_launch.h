@@ -65,6 +65,7 @@ __device__ __forceinline__ void reduce_contact_diag(int world, float sepn, float
 
 constexpr int kThreads = 256;
 constexpr int kLanesPerBody = 4;
+constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodies per CTA tile (9 lanes per body in the sum phase)
 
 // One colour of the primal sweep: `count` bodies listed in `order`; visitStart[k] .. visitStart[k+1] is the run of
 // `visits` of body order[k]; avgVisits (visits per body, whole world) picks the tile shape.
@@ -75,11 +76,12 @@ int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4*
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics
 // (solver.cpp:472-497) are reduced here from the values already in registers instead of by a separate sweep.
 void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, Diag* diag);
-// Small worlds: the whole iteration loop (solver.cpp:340-431, manifold rows only) in ONE cooperative launch.
-// Returns false if the launch was refused (caller falls back to per-colour launches).
+// Small worlds: the whole iteration loop (solver.cpp:340-431, manifold rows only) in ONE launch of one thread-block
+// cluster (<= 16 CTAs, hardware cluster barrier between phases).  Returns false if the launch was refused (caller
+// falls back to per-colour launches).
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
-                       Diag* diag, unsigned* barrier, bool contactDiag);
+                       Diag* diag, bool contactDiag);
 // Measurement aid (avbd_debug_time_primal): one colour's visit-sum kernel in mode 0 (product), 1 (memory only), 2 (math only).
 void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, int count, float alpha,
                               float* sums, int nContacts);

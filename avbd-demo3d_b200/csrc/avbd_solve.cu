@@ -487,51 +487,47 @@ __global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSe
 }
 
 // ------------------------------------------------------------------ persistent iteration loop (small worlds)
-// A Stress1000-sized world is launch-latency bound: iterations x (colours + dual) dependent launches of a few
-// hundred threads each.  This kernel runs the WHOLE loop of solver.cpp:340-431 in one cooperative launch; colours
-// and the dual pass are separated by a grid-wide barrier instead of a kernel boundary.  Data other CTAs write
-// between barriers (poses, lambda, penalty) is read with ld.global.cg.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
-        __threadfence();
-    }
-    __syncthreads();
+// A Stress1000-sized world is latency bound: iterations x (colours + dual) dependent phases of a few hundred threads
+// each, so per-colour launches pay two launch latencies per phase and a grid-wide atomic barrier is no cheaper.  This
+// kernel runs the WHOLE loop of solver.cpp:340-431 in one launch of ONE thread-block cluster (up to 16 CTAs on the SMs
+// of one GPC): phases are separated by the hardware cluster barrier (barrier.cluster, release / acquire at cluster
+// scope) instead of a kernel boundary, and each phase is the visit-parallel tile of the large-world path (one contact
+// visit per thread, in-order shared-memory sums, block solve).  Data other CTAs write between barriers (poses, lambda,
+// penalty) is read with ld.global.cg (L2); stores are write-through.
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int LPB>
-__global__ void __launch_bounds__(kThreads, 2) solve_loop_persistent(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
-                                                                     ManifoldSet ms, ForceView fv, const int* __restrict__ order,
-                                                                     const int2* __restrict__ colRange, int nColours, int nContacts, SolveParams prm,
-                                                                     Diag* diag, unsigned* barrier, bool contactDiag) {
-    constexpr int BPB = kThreads / LPB;
-    __shared__ float sSys[BPB * 27];
-    unsigned target = 0;
+template <int BPB>
+__global__ void __launch_bounds__(kThreads, 1) solve_loop_cluster(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
+                                                                  ManifoldSet ms, ForceView fv, const int* __restrict__ order,
+                                                                  const int2* __restrict__ colRange, int nColours, int nContacts, SolveParams prm,
+                                                                  Diag* diag, bool contactDiag) {
+    __shared__ PrimalSmem<BPB> sm;
+    const int rank = (int)cluster_rank(), nCta = (int)cluster_size();       // the grid is one cluster
     int total = prm.iterations + (prm.postStabilize ? 1 : 0);
     for (int it = 0; it < total; ++it) {
         float alpha = prm.postStabilize ? (it < prm.iterations ? 1.0f : 0.0f) : prm.alpha;      // solver.cpp:340-342
         for (int c = 0; c < nColours; ++c) {
             int2 r = colRange[c];
             int count = r.y - r.x;
-            for (int tile = blockIdx.x; tile * BPB < count; tile += gridDim.x) {
-                primal_tile<LPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, nullptr, diag, sSys);
+            for (int tile = rank; tile * BPB < count; tile += nCta) {
+                primal_tile_visits<BPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, nullptr, diag, sm);
                 __syncthreads();
             }
-            grid_barrier(barrier, target);
+            cluster_barrier();
         }
         if (it < prm.iterations) {
             bool last = contactDiag && it == total - 1;            // nothing moves after this pass: reduce the contact diagnostics here
             int rounded = (nContacts + 31) & ~31;                   // whole warps stay in the loop (warp-level reductions below)
-            for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += gridDim.x * blockDim.x) {
+            for (int t = rank * kThreads + (int)threadIdx.x; t < rounded; t += nCta * kThreads) {
                 DualOut o{0.0f, 0.0f, 0, -1, 0};
                 if (t < nContacts) o = dual_one<true, true>(b, ms, t, prm, alpha);
                 if (last) reduce_contact_diag(o.world, o.sepn, o.lamN, o.world >= 0 ? 1 : 0, o.first, o.visits, diag);
             }
-            grid_barrier(barrier, target);
+            cluster_barrier();
         }
     }
 }
@@ -672,23 +668,33 @@ void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* v
 }
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
-                       Diag* diag, unsigned* barrier, bool contactDiag) {
-    constexpr int LPB = kLanesPerBody;
-    static int maxBlocks = [] {
-        int dev = 0, sms = 0, perSm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, solve_loop_persistent<LPB>, kThreads, 0);
-        return sms * (perSm < 1 ? 1 : perSm);
+                       Diag* diag, bool contactDiag) {
+    constexpr int BPB = kClusterBodiesPerTile;
+    static int maxCluster = [] {
+        // 16 CTAs need the non-portable opt-in; fall back to the portable 8 if the device refuses it
+        if (cudaFuncSetAttribute(solve_loop_cluster<BPB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 8; }
+        if (const char* e = getenv("AVBD_CLUSTER_MAX")) { int v = atoi(e); if (v >= 1 && v <= 16) return v; }
+        return 16;
     }();
-    int want = blocks_of(maxColourCount, kThreads / LPB);
+    int want = blocks_of(maxColourCount, BPB);
     int wantDual = blocks_of(nContacts, kThreads);
-    int grid = want > wantDual ? want : wantDual;
-    if (grid > maxBlocks) grid = maxBlocks;
-    if (grid < 1) grid = 1;
-    cudaMemsetAsync(barrier, 0, sizeof(unsigned), s);
-    void* args[] = {&b, &visitStart, &visits, &ms, &fv, &order, &colRange, &nColours, &nContacts, &prm, &diag, &barrier, &contactDiag};
-    return cudaLaunchCooperativeKernel((void*)solve_loop_persistent<LPB>, dim3(grid), dim3(kThreads), args, 0, s) == cudaSuccess;
+    int need = want > wantDual ? want : wantDual;
+    int nCta = 1;
+    while (nCta < need && nCta < maxCluster) nCta <<= 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nCta); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag);
+    if (e != cudaSuccess && nCta > 8) {          // a 16-CTA cluster may not be placeable (MIG slices, busy GPCs): retry with the portable size
+        cudaGetLastError();
+        maxCluster = 8;
+        attr[0].val.clusterDim.x = 8; cfg.gridDim = dim3(8);
+        e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag);
+    }
+    return e == cudaSuccess;
 }
 
 void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, Diag* diag) {

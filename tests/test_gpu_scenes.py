@@ -20,10 +20,12 @@ def run_scene(avbd, name, steps, tail=100):
     w = avbd.World()
     scenes.load(w, scenes.scene(name))
     w.step(steps - tail)
-    ys = []
+    ys, kes = [], []
     for _ in range(tail):
         w.step(1)
-        ys.append(w.state()[:, 1].copy())
+        st = w.state()
+        ys.append(st[:, 1].copy()); kes.append(float((st[:, 7:10] ** 2).sum()))
+    w.tail_ke = float(np.mean(kes))          # kinetic-energy proxy (sum |v|^2), mean over the tail
     return w, np.mean(ys, axis=0)
 
 
@@ -31,10 +33,12 @@ def oracle_rest(name, steps, tail=100):
     o = Oracle("port").create()
     o.load_scene(name)
     o.step(steps - tail)
-    ys = []
+    ys, kes = [], []
     for _ in range(tail):
         o.step(1)
-        ys.append(o.state()[:, 1].copy())
+        st = o.state()
+        ys.append(st[:, 1].copy()); kes.append(float((st[:, 7:10] ** 2).sum()))
+    o.tail_ke = float(np.mean(kes))
     return o, np.mean(ys, axis=0)
 
 
@@ -53,7 +57,7 @@ def test_two_block_drop_settles_like_the_reference(avbd):
 @pytest.mark.parametrize("name,steps", [("Stack", 600), ("Pyramid", 600)])
 def test_stacked_scenes_rest_heights_and_counts(avbd, name, steps):
     """BASELINE.json config 1: rest heights (mean of the last 100 steps) within 1e-3 of the reference's, equal
-    manifold / contact counts, no penetration at rest, kinetic-energy proxy no worse than 2x the reference's.
+    manifold / contact counts, no penetration at rest, kinetic-energy proxy (tail mean) no worse than 2x the reference's.
 
     Pyramid counts get a slack of 2 manifolds / 8 contacts: the apex box balances on two supports and the settling
     phase is chaotic — the host build of the SAME row math in the reference's own visiting order is 0.4 m and two
@@ -68,8 +72,9 @@ def test_stacked_scenes_rest_heights_and_counts(avbd, name, steps):
     else:
         assert (d["manifolds"], d["contacts"]) == (do["manifolds"], do["contacts"]), (d, do)
     assert d["maxPen"] <= PEN_TOL
-    ke = lambda s: float((s[:, 7:10] ** 2).sum())
-    assert ke(w.state()) <= 2.0 * ke(o.state()) + 1e-3, (ke(w.state()), ke(o.state()))
+    # kinetic-energy proxy sum |v|^2, averaged over the same 100-step tail as the rest heights: the stack's residual
+    # jitter comes in bursts (reference maxLin up to 0.18), so one instant is a coin toss
+    assert w.tail_ke <= 2.0 * o.tail_ke + 1e-3, (w.tail_ke, o.tail_ke)
     assert d["nanEvents"] == 0
     w.close(); o.close()
 
