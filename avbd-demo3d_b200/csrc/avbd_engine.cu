@@ -441,13 +441,19 @@ int run_colour(avbd_world* w) {
     colour_init<<<blocks_for(n), kThreads, 0, s>>>(w->flags.p, n, w->colour.p);
     w->launches++;
     ForceView fv = w->fview();
-    for (int round = 0;; ++round) {
+    // Jones-Plassmann rounds, launched in batches: a round is a no-op for bodies already coloured, so running a few
+    // rounds too many costs microseconds while every host check of the uncoloured count costs a round trip.  Only the
+    // last round of a batch counts the bodies it left uncoloured.
+    for (int round = 0, batch = 6;;) {
         if (round > 4096) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
         CK(cudaMemsetAsync(&w->dCnt->nUncoloured, 0, sizeof(int), s));
-        colour_round<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p, w->dCnt);
-        w->launches++;
+        for (int k = 0; k < batch; ++k)
+            colour_round<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p,
+                                                                  w->dCnt, k == batch - 1);
+        w->launches += batch; round += batch;
         TRY(read_counters(w));
         if (w->hCnt->nUncoloured == 0) break;
+        batch = 4;
     }
     if (w->hCnt->overflow & 4) return fail(AVBD_ERR_CAPACITY, "more than 64 colours needed");
     colour_keys<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);

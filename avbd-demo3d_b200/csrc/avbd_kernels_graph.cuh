@@ -78,7 +78,7 @@ __global__ void colour_init(const int* flags, int n, int* colour) {
 // neighbours once every higher-priority neighbour is coloured.  The result is
 // the sequential greedy colouring in priority order, independent of timing.
 __global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
-                             ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt) {
+                             ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt, bool countLeft) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = dynList[t];
@@ -106,7 +106,7 @@ __global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange,
         int c = __ffsll((long long)~used) - 1;
         if (c < 0) { c = 63; atomicOr(&cnt->overflow, 4); }
         colour[i] = c;
-    } else {
+    } else if (countLeft) {
         cg::coalesced_group grp = cg::coalesced_threads();
         if (grp.thread_rank() == 0) atomicAdd(&cnt->nUncoloured, (int)grp.size());
     }
