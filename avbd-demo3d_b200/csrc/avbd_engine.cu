@@ -87,10 +87,11 @@ struct avbd_world {
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<int> candCode, candCodeSorted;
     DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;
-    DevBuf<float4> stA, stB, stN, stL, stP;      // np_build staging (4 slots per manifold), packed by np_compact
+    DevBuf<float4> vgA, vgB, vgN; bool visitGeomStale = true;      // contact geometry in visit order (VisitGeom)
+    DevBuf<float4> stA, stB, stN; DevBuf<ContactLP> stLP;      // np_build staging (4 slots per manifold), packed by np_compact
 
     // manifolds (ping-pong)
-    struct MBuf { DevBuf<unsigned long long> key; DevBuf<int4> hdr; DevBuf<int> cstart, cM; DevBuf<float4> cA, cB, cN, cL, cP; } mb[2];
+    struct MBuf { DevBuf<unsigned long long> key; DevBuf<int4> hdr; DevBuf<int> cstart, cM; DevBuf<float4> cA, cB, cN; DevBuf<ContactLP> lp; } mb[2];
     int cur = 0, nM = 0;
 
     // graph
@@ -123,20 +124,21 @@ struct avbd_world {
 
     ManifoldSet mset(int which) {
         MBuf& b = mb[which];
-        ManifoldSet s; s.key = b.key.p; s.hdr = b.hdr.p; s.cstart = b.cstart.p; s.cM = b.cM.p; s.cA = b.cA.p; s.cB = b.cB.p; s.cN = b.cN.p; s.cL = b.cL.p; s.cP = b.cP.p;
+        ManifoldSet s; s.key = b.key.p; s.hdr = b.hdr.p; s.cstart = b.cstart.p; s.cM = b.cM.p; s.cA = b.cA.p; s.cB = b.cB.p; s.cN = b.cN.p; s.lp = b.lp.p;
         return s;
     }
     int ensure_manifolds(int which, size_t m) {
         MBuf& b = mb[which];
         TRY(b.key.ensure(m, false, stream)); TRY(b.hdr.ensure(m, false, stream)); TRY(b.cstart.ensure(m + 1, false, stream)); TRY(b.cM.ensure(4 * m, false, stream));
         TRY(b.cA.ensure(4 * m, false, stream)); TRY(b.cB.ensure(4 * m, false, stream)); TRY(b.cN.ensure(4 * m, false, stream));
-        TRY(b.cL.ensure(4 * m, false, stream)); TRY(b.cP.ensure(4 * m, false, stream));
+        TRY(b.lp.ensure(4 * m, false, stream));
         return 0;
     }
-    ContactStage stage() { ContactStage c; c.cA = stA.p; c.cB = stB.p; c.cN = stN.p; c.cL = stL.p; c.cP = stP.p; return c; }
+    VisitGeom vgeom() { VisitGeom g; g.a = vgA.p; g.b = vgB.p; g.n = vgN.p; return g; }
+    ContactStage stage() { ContactStage c; c.cA = stA.p; c.cB = stB.p; c.cN = stN.p; c.lp = stLP.p; return c; }
     int ensure_stage(size_t m) {
         TRY(stA.ensure(4 * m, false, stream)); TRY(stB.ensure(4 * m, false, stream)); TRY(stN.ensure(4 * m, false, stream));
-        TRY(stL.ensure(4 * m, false, stream)); TRY(stP.ensure(4 * m, false, stream));
+        TRY(stLP.ensure(4 * m, false, stream));
         return 0;
     }
     BodyView bview() {
@@ -407,6 +409,7 @@ int run_collide(avbd_world* w) {
         w->launches++;
     }
     w->graphValid = sameTopology;
+    w->visitGeomStale = true;         // every contact was rebuilt
     if (w->timed) cudaEventRecord(w->ev[2], s);
     CK(cudaGetLastError());
     return 0;
@@ -469,6 +472,7 @@ int run_colour(avbd_world* w) {
     // contact visits in colour order (the primal's work list): visitStart[k] belongs to colOrder[k]
     TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
     TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
+    w->visitGeomStale = true;
     CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
     visit_count<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
     TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
@@ -485,11 +489,18 @@ int run_primal(avbd_world* w, float alpha, float* dxDev) {
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
     TRY(w->sums.ensure((size_t)std::max(1, w->maxColourCount) * 28, false, s));
+    if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
+        size_t cap = w->visits.cap;
+        TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));
+        visit_geometry<<<blocks_for(2ll * w->nContacts), kThreads, 0, s>>>(w->visits.p, w->visitStart.p + w->nDyn, ms, w->vgeom());
+        w->launches++;
+    }
+    w->visitGeomStale = false;
     float avgVisits = w->nDyn > 0 ? 2.0f * (float)w->nContacts / (float)w->nDyn : 0.0f;   // upper bound: static endpoints do not visit
     for (int c = 0; c < w->nColours; ++c) {
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
-        w->launches += launch_primal(s, w->bview(), w->visitStart.p + first, w->visits.p, ms, fv, w->colOrder.p + first, count, avgVisits, w->prm, alpha,
+        w->launches += launch_primal(s, w->bview(), w->visitStart.p + first, w->visits.p, w->vgeom(), ms, fv, w->colOrder.p + first, count, avgVisits, w->prm, alpha,
                                      w->sums.p, dxDev, w->dDiag.p);
     }
     CK(cudaGetLastError());
@@ -633,12 +644,12 @@ void avbd_world_destroy(avbd_world* w) {
     w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellRange.release();
     w->sortedCell.release(); w->sortedPos.release(); w->largeList.release(); w->worldLargeStart.release();
     w->pairs.release(); w->cand.release(); w->candSorted.release(); w->candCode.release(); w->candCodeSorted.release();
-    for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cstart.release(); b.cM.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.cL.release(); b.cP.release(); }
+    for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cstart.release(); b.cM.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.lp.release(); }
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
     w->dDiag.release(); w->dx.release(); w->sums.release(); w->temp.release(); w->stateDev.release();
-    w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stL.release(); w->stP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
+    w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stLP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
     if (w->hCnt) cudaFreeHost(w->hCnt);
@@ -955,7 +966,7 @@ int avbd_download_manifolds(avbd_world* w, int* ints, int* feats, int* stick, fl
     CK(cudaSetDevice(w->device));
     int nM = w->nM; if (!nM) return 0;
     size_t nC = (size_t)std::max(1, w->nContacts);
-    std::vector<int4> hdr(nM); std::vector<int> cstart(nM + 1); std::vector<float4> cA(nC), cB(nC), cN(nC), cL(nC), cP(nC);
+    std::vector<int4> hdr(nM); std::vector<int> cstart(nM + 1); std::vector<float4> cA(nC), cB(nC), cN(nC); std::vector<ContactLP> lp(nC);
     ManifoldSet ms = w->mset(w->cur);
     cudaStream_t s = w->stream;
     CK(cudaMemcpyAsync(hdr.data(), ms.hdr, nM * sizeof(int4), cudaMemcpyDeviceToHost, s));
@@ -964,8 +975,7 @@ int avbd_download_manifolds(avbd_world* w, int* ints, int* feats, int* stick, fl
         CK(cudaMemcpyAsync(cA.data(), ms.cA, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(cB.data(), ms.cB, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(cN.data(), ms.cN, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(cL.data(), ms.cL, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(cP.data(), ms.cP, nC * sizeof(float4), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(lp.data(), ms.lp, nC * sizeof(ContactLP), cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
     int live = 0;
@@ -978,16 +988,16 @@ int avbd_download_manifolds(avbd_world* w, int* ints, int* feats, int* stick, fl
         f[0] = mu;
         for (int c = 0; c < 4; ++c) {
             bool on = c < nc; int ci = on ? cstart[m] + c : 0;
-            int feat; std::memcpy(&feat, &cP[ci].w, 4);
+            int feat; std::memcpy(&feat, &lp[ci].p.w, 4);
             feats[4 * live + c] = on ? feat : 0;
-            stick[4 * live + c] = on ? (cL[ci].w != 0.0f ? 1 : 0) : 0;
+            stick[4 * live + c] = on ? (lp[ci].l.w != 0.0f ? 1 : 0) : 0;
             float* o = f + 1 + 14 * c;
             const float v[14] = {cA[ci].x, cA[ci].y, cA[ci].z, cB[ci].x, cB[ci].y, cB[ci].z, cN[ci].x, cN[ci].y, cN[ci].z,
                                  0.0f /* penetration is draw-only state, not kept on the device */, cA[ci].w, cB[ci].w, cN[ci].w, 0.0f};
             for (int k = 0; k < 14; ++k) o[k] = on ? v[k] : 0.0f;
             for (int k = 0; k < 3; ++k) {
-                f[57 + 3 * c + k] = on ? (&cL[ci].x)[k] : 0.0f;
-                f[69 + 3 * c + k] = on ? (&cP[ci].x)[k] : 0.0f;
+                f[57 + 3 * c + k] = on ? (&lp[ci].l.x)[k] : 0.0f;
+                f[69 + 3 * c + k] = on ? (&lp[ci].p.x)[k] : 0.0f;
             }
         }
         ++live;
@@ -1098,7 +1108,7 @@ int avbd_debug_time_primal(avbd_world* w, int mode, int reps, float* ms) {
     for (int r = 0; r < reps; ++r)
         for (int c = 0; c < w->nColours; ++c) {
             int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
-            if (count > 0) launch_primal_experiment(s, mode, w->bview(), w->visitStart.p + first, w->visits.p, w->mset(w->cur), count, w->prm.alpha, w->sums.p, w->nContacts);
+            if (count > 0) launch_primal_experiment(s, mode, w->bview(), w->visitStart.p + first, w->visits.p, w->vgeom(), w->mset(w->cur), count, w->prm.alpha, w->sums.p, w->nContacts);
         }
     CK(cudaEventRecord(w->ev[8], s));
     CK(cudaStreamSynchronize(s));

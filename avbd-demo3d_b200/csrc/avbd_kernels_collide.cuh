@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(kThreads) np_sat(BodyView b, const unsigned lo
 }
 
 __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int ci) {
-    return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ms.cL[ci], ms.cP[ci]);
+    ContactLP q = ms.lp[ci];
+    return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], q.l, q.p);
 }
 
 // K3b: build the manifold of each surviving pair at its final (key-sorted) slot, carrying lambda / penalty / stick
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
     if (slot >= 0) {
         oldN = old.hdr[slot].z; oldBase = old.cstart[slot];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (j < oldN) oldFeat[j] = f2i(old.cP[oldBase + j].w);
+        for (int j = 0; j < 4; ++j) if (j < oldN) oldFeat[j] = f2i(old.lp[oldBase + j].p.w);
     }
     unsigned used = 0u;
     int n = 0;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
         ContactState ct = contact_initialize(posA, rotA, posB, rotB, feature, rA, rB, normal, oldN, oldFeat, used, loadOld, prm);
         int ci = s * 4 + n;
         st.cA[ci] = f4(ct.rA, ct.C0n); st.cB[ci] = f4(ct.rB, ct.C0t1); st.cN[ci] = f4(ct.n, ct.C0t2);
-        st.cL[ci] = pack_lambda(ct); st.cP[ci] = pack_penalty(ct);
+        ContactLP q; q.l = pack_lambda(ct); q.p = pack_penalty(ct); st.lp[ci] = q;
         ++n;
     };
     PolyShared poly{sPoly + threadIdx.x, (int)blockDim.x};
@@ -292,7 +293,7 @@ __global__ void np_compact(const int4* hdr, const int* cstart, int nM, ContactSt
     if (t == 0) cnt->nContacts = cstart[nM];
     if (c >= hdr[m].z) return;
     int d = cstart[m] + c;
-    out.cA[d] = st.cA[t]; out.cB[d] = st.cB[t]; out.cN[d] = st.cN[t]; out.cL[d] = st.cL[t]; out.cP[d] = st.cP[t];
+    out.cA[d] = st.cA[t]; out.cB[d] = st.cB[t]; out.cN[d] = st.cN[t]; out.lp[d] = st.lp[t];
     out.cM[d] = m;
 }
 

@@ -58,6 +58,15 @@ __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, 
     for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; int c0 = cstart[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.x, idx, h.w); }
 }
 
+// Once per step (the narrowphase rewrites every contact): copy each visit's contact geometry into visit order, so the
+// iterations x colours primal sweeps stream it instead of gathering it.  nVisits lives on the device (visitStart[nDyn]).
+__global__ void visit_geometry(const int4* __restrict__ visits, const int* __restrict__ nVisits, ManifoldSet ms, VisitGeom vg) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= *nVisits) return;
+    int ci = visits[v].x;
+    vg.a[v] = ms.cA[ci]; vg.b[v] = ms.cB[ci]; vg.n[v] = ms.cN[ci];
+}
+
 // ------------------------------------------------------------------ colouring
 __device__ __forceinline__ unsigned mix32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
@@ -198,7 +207,7 @@ __global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nContacts, 
         V3 pA = xyz(pa.pos) + qrot(quat(pa.rot), xyz(a4));
         V3 pB = xyz(pb.pos) + qrot(quat(pb.rot), xyz(b4));
         sepn = dot(pA - pB, xyz(n4));
-        lam = ms.cL[ci].x;
+        lam = ms.lp[ci].l.x;
     }
     reduce_contact_diag(world, sepn, lam, world >= 0 ? 1 : 0, nm, nv, diag);
 }

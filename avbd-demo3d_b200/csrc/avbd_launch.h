@@ -21,6 +21,10 @@ struct ForceView {
     const int* adjStart; const int* adj;    // entry = index*4 + type*2 + isA ; type 0 joint, 1 spring
 };
 
+// Contact geometry in VISIT order (one float4 per field per visit, refreshed once per step by visit_geometry): the primal's
+// visit kernel streams it fully coalesced instead of gathering 3 x 16 B per visit by contact id.  {rA,C0n} {rB,C0t.x} {n,C0t.y}.
+struct VisitGeom { float4* a; float4* b; float4* n; };
+
 #ifdef __CUDACC__
 // Diagnostics are kept per world (an ensemble batch reports each world separately).  Lanes of a warp that
 // belong to the same world combine first (match_any + masked reduce), then one atomic per (warp, world).
@@ -70,7 +74,7 @@ constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodie
 // One colour of the primal sweep: `count` bodies listed in `order`; visitStart[k] .. visitStart[k+1] is the run of
 // `visits` of body order[k]; avgVisits (visits per body, whole world) picks the tile shape.
 // `sums` is scratch for the split path: 28 floats per body of the colour.  Returns the number of kernels launched.
-int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
+int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
                   const int* order, int count, float avgVisits, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live (densely stored) contacts.
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics
@@ -83,7 +87,7 @@ bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const 
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
                        Diag* diag, bool contactDiag);
 // Measurement aid (avbd_debug_time_primal): one colour's visit-sum kernel in mode 0 (product), 1 (memory only), 2 (math only).
-void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, int count, float alpha,
+void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, int count, float alpha,
                               float* sums, int nContacts);
 void launch_dual_user_forces(cudaStream_t s, BodyView b, ForceView fv, SolveParams prm);
 void launch_solve6_batch(cudaStream_t s, const float* lhs36, const float* rhs6, int n, float* out6);

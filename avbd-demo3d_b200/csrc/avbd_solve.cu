@@ -13,7 +13,8 @@
 namespace avbd {
 
 __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int ci) {
-    return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ms.cL[ci], ms.cP[ci]);
+    ContactLP q = ms.lp[ci];
+    return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], q.l, q.p);
 }
 
 // ------------------------------------------------------------------ primal
@@ -94,7 +95,7 @@ template <bool COH> __device__ __forceinline__ BodyPose load_pose(const BodyPose
     BodyPose r; r.pos = ld4<COH>(&p->pos); r.rot = ld4<COH>(&p->rot); return r;
 }
 template <bool COH> __device__ __forceinline__ ContactState load_contact_c(const ManifoldSet& ms, int ci) {
-    return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ld4<COH>(ms.cL + ci), ld4<COH>(ms.cP + ci));
+    return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ld4<COH>(&ms.lp[ci].l), ld4<COH>(&ms.lp[ci].p));
 }
 
 // One tile (kThreads/LPB bodies of one colour) of the primal sweep (solver.cpp:344-409), in two phases so both are
@@ -137,7 +138,7 @@ __device__ __forceinline__ void primal_tile(const BodyView& b, const int* __rest
                 BodySystem part;
                 contact_system(part, cs, ev, isA, true, invIw);
                 add_system(sys, part);
-                ms.cL[ci] = pack_lambda(cs);      // computeConstraint's side effects (manifold.cpp:224-241)
+                ms.lp[ci].l = pack_lambda(cs);    // computeConstraint's side effects (manifold.cpp:224-241)
             }
             if (userForces) accumulate_user_forces(sys, fv, b.pose, i, pos, rot, invIw);
         }
@@ -250,7 +251,7 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
             int ci = e.x; bool isA = (e.z & 1) != 0;
             BodyPose po = load_pose<COH>(b.pose + e.y);
             float4 a4 = ms.cA[ci], b4 = ms.cB[ci], n4 = ms.cN[ci];
-            float4 l4 = ld4<COH>(ms.cL + ci), p4 = ld4<COH>(ms.cP + ci);
+            float4 l4 = ld4<COH>(&ms.lp[ci].l), p4 = ld4<COH>(&ms.lp[ci].p);
             int lo = 0, hi = nb;                                  // slot: vs[lo] <= v < vs[lo + 1]
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.vs[mid] <= v) lo = mid; else hi = mid; }
             float4 sp = sm.pos[lo], sr = sm.rot[lo];
@@ -274,7 +275,7 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
             contact_system(sys, cs, ev, isA, gyro, invIw);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
-            if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) ms.cL[ci] = nl;
+            if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) ms.lp[ci].l = nl;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
 #pragma unroll
@@ -349,7 +350,7 @@ constexpr int kSumStride = 28;
 // memory accesses and drops the row math (the kernel's memory-system floor), 2 keeps the math and makes every index
 // sequential (its instruction-issue floor); neither writes solver state.
 template <int BPB, int MINB, int MODE = 0>
-__global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits,
+__global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits, VisitGeom vg,
                                                                     ManifoldSet ms, int count, float alpha, float* __restrict__ sums, int nContacts = 0) {
     constexpr int L = kThreads / BPB;
     constexpr int CPL = (27 + L - 1) / L;
@@ -367,13 +368,16 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, 
     for (int base = v0; base < v1; base += kThreads) {
         int v = base + t;
         if (v < v1) {
-            int4 e = visits[v];
+            int4 e = __ldcs(visits + v);
             int ci = e.x, self = e.z >> 2; bool isA = (e.z & 1) != 0, gyro = (e.z & 2) != 0;
             if (MODE == 2) { ci = v % nContacts; self = v % b.n; e.y = (v + 1) % b.n; }
             BodyPose ps = load_pose_keep(b.pose + self, keep);
             BodyPose po = load_pose_keep(b.pose + e.y, keep);
-            // contact geometry is read once per visit: stream it past L2 (evict-first) so it does not push the poses out
-            float4 a4 = __ldcs(ms.cA + ci), b4 = __ldcs(ms.cB + ci), n4 = __ldcs(ms.cN + ci), l4 = ms.cL[ci], p4 = ms.cP[ci];
+            // the visit entry and its copy of the contact geometry stream past once per sweep, fully coalesced: evict-first, so
+            // they do not push the poses and the lambda / penalty records (the gathered, re-used data) out of L2
+            float4 a4 = __ldcs(vg.a + v), b4 = __ldcs(vg.b + v), n4 = __ldcs(vg.n + v);
+            ContactLP* lp = ms.lp + ci;
+            float4 l4 = lp->l, p4 = lp->p;
             V3 pos = xyz(ps.pos); Q4 rot = quat(ps.rot);
             ContactState cs = unpack_contact(a4, b4, n4, l4, p4);
             ContactEval ev;
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, 
             contact_system(sys, cs, ev, isA, gyro, invIw);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
-            if (MODE == 0 && (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w)) ms.cL[ci] = nl;
+            if (MODE == 0 && (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w)) lp->l = nl;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
 #pragma unroll
@@ -467,8 +471,8 @@ __device__ __forceinline__ DualOut dual_one(const BodyView& b, const ManifoldSet
     ContactEval ev;
     contact_constraint(xyz(pa.pos), quat(pa.rot), pa.pos.w, xyz(pb.pos), quat(pb.rot), pb.pos.w, __int_as_float(h.w), alpha, cs, ev);
     dual_contact(cs, ev, prm.beta);
-    ms.cL[ci] = pack_lambda(cs);
-    ms.cP[ci] = pack_penalty(cs);
+    ContactLP q; q.l = pack_lambda(cs); q.p = pack_penalty(cs);
+    ms.lp[ci] = q;
     DualOut o;
     o.sepn = dot((xyz(pa.pos) + ev.wrA) - (xyz(pb.pos) + ev.wrB), cs.n);
     o.lamN = cs.lam[0];
@@ -611,9 +615,9 @@ static void launch_primal_visits(cudaStream_t s, BodyView b, const int* vstart, 
 }
 
 template <int BPB, int MINB>
-static void launch_split(cudaStream_t s, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, ForceView fv,
+static void launch_split(cudaStream_t s, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
                          const int* order, int count, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag) {
-    primal_visit_sums<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, ms, count, alpha, sums);
+    primal_visit_sums<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, sums);
     primal_solve<<<blocks_of(count, kThreads), kThreads, 0, s>>>(b, fv, order, count, sums, prm, dxOut, diag);
 }
 
@@ -621,7 +625,7 @@ static void launch_split(cudaStream_t s, BodyView b, const int* vstart, const in
 // AVBD_PRIMAL_VARIANT (tuning aid): "s<BPB>[m<MINB>]" split path with a forced tile size (s16 s28 s64; m3 m4);
 // "v<BPB>[m<MINB>]" the fused visit-parallel kernel; "<lanes per body><min blocks per SM>" the lanes-per-body kernel (43 ...).
 // Returns the number of kernels launched.
-int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
+int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
                   const int* order, int count, float avgVisits, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag) {
     static int variant = 0, minb = 3; static char kind = 's';
     static bool init = [] {
@@ -637,7 +641,7 @@ int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4*
     (void)init;
 #define AVBD_PV(L, M) case L * 10 + M: launch_primal_variant<L, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag); return 1;
 #define AVBD_VV(B, M) launch_primal_visits<B, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag)
-#define AVBD_SV(B, M) launch_split<B, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, sums, dxOut, diag)
+#define AVBD_SV(B, M) launch_split<B, M>(s, b, visitStart, visits, vg, ms, fv, order, count, prm, alpha, sums, dxOut, diag)
     if (variant > 0) {
         switch (variant) {
             AVBD_PV(8, 2) AVBD_PV(8, 3) AVBD_PV(4, 2) AVBD_PV(4, 3) AVBD_PV(4, 4) AVBD_PV(2, 3)
@@ -660,11 +664,11 @@ int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4*
 #undef AVBD_VV
 #undef AVBD_SV
 }
-void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, int count, float alpha,
+void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, int count, float alpha,
                               float* sums, int nContacts) {
-    if (mode == 1) primal_visit_sums<28, 3, 1><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, ms, count, alpha, sums, nContacts);
-    else if (mode == 2) primal_visit_sums<28, 3, 2><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, ms, count, alpha, sums, nContacts);
-    else primal_visit_sums<28, 3, 0><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, ms, count, alpha, sums, nContacts);
+    if (mode == 1) primal_visit_sums<28, 3, 1><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, sums, nContacts);
+    else if (mode == 2) primal_visit_sums<28, 3, 2><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, sums, nContacts);
+    else primal_visit_sums<28, 3, 0><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, sums, nContacts);
 }
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,

@@ -10,7 +10,8 @@
 //   cstart[m] first contact of manifold m; contacts are stored DENSE (ci = cstart[m] + c, live contacts only, about 2 per
 //   manifold on a box pile — a fixed 4-slot layout made every 64-byte DRAM granule half dead), one float4 per field:
 //     cA {rA.xyz, C0_n}  cB {rB.xyz, C0_t.x}  cN {normal.xyz, C0_t.y}
-//     cL {lambda_n, lambda_t1, lambda_t2, stick}   cP {penalty_n, penalty_t1, penalty_t2, feature-bits}
+//     lp {lambda_n, lambda_t1, lambda_t2, stick | penalty_n, penalty_t1, penalty_t2, feature-bits}   32 B = one sector: the
+//        only per-contact state the iterations write, gathered by contact id from both endpoints' visits
 //   cM[ci]   manifold of contact ci
 //   C / fmin / fmax (solver.h:91-92) are recomputed in registers by every
 //   consumer and never stored.
@@ -23,6 +24,7 @@ struct BodyPose { float4 pos; float4 rot; };
 struct BodyAux  { float4 posI; float4 rotI; float4 mass; float4 inert; };
 struct BodyVel  { float4 lin; float4 ang; };
 struct BodyInit { float4 pos0; float4 rot0; };
+struct ContactLP { float4 l; float4 p; };      // {lambda xyz, stick | penalty xyz, feature bits}
 
 enum BodyFlag : int { kDynamic = 1, kLarge = 2 };
 
@@ -39,10 +41,10 @@ struct ManifoldSet {          // one of the two ping-pong generations
     int4*   hdr;
     int*    cstart;           // nM + 1 entries
     int*    cM;               // per dense contact
-    float4* cA; float4* cB; float4* cN; float4* cL; float4* cP;
+    float4* cA; float4* cB; float4* cN; ContactLP* lp;
 };
 struct ContactStage {         // np_build's output before compaction: 4 slots per manifold (ci = 4*m + c)
-    float4* cA; float4* cB; float4* cN; float4* cL; float4* cP;
+    float4* cA; float4* cB; float4* cN; ContactLP* lp;
 };
 
 // Joint (6 rows, joint.cpp) / Spring (1 row, spring.cpp) records.  Unlike
