@@ -43,7 +43,7 @@ class Profile(C.Structure):
     _fields_ = [("ms_primal", C.c_double), ("ms_dual", C.c_double), ("steps", C.c_longlong), ("primal_sweeps", C.c_longlong),
                 ("primal_launches", C.c_longlong), ("primal_bodies", C.c_longlong), ("primal_visits", C.c_longlong),
                 ("dual_launches", C.c_longlong), ("dual_contacts", C.c_longlong), ("kernel_launches", C.c_longlong),
-                ("library_launches", C.c_longlong)]
+                ("library_launches", C.c_longlong), ("deferred_dual_contacts", C.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -71,6 +71,7 @@ struct avbd_world {
 
     // bodies
     int n = 0, nDyn = 0, nWorlds = 1;
+    bool anyUnvisited = false;   // some world holds two static bodies (a contact between them is visited by no body)
     std::vector<HostBody> hb;
     DevBuf<BodyPose> pose; DevBuf<BodyAux> aux; DevBuf<BodyVel> vel; DevBuf<BodyInit> init;
     DevBuf<float4> prevLin, size;
@@ -237,6 +238,11 @@ int prepare(avbd_world* w) {
             if (isLarge) large.push_back(i);
         }
         w->nWorlds = nWorlds; w->nDyn = (int)dyn.size(); w->nLarge = (int)large.size();
+        {   // a contact no dynamic body visits needs two static bodies in one world
+            std::vector<int> statics(nWorlds, 0);
+            w->anyUnvisited = false;
+            for (int i = 0; i < n; ++i) if (!(flags[i] & kDynamic) && ++statics[wid[i]] > 1) w->anyUnvisited = true;
+        }
         w->cell = std::max(2.02f * maxSmall, 1e-3f);
         unsigned table = 256; while (table < 2u * (unsigned)n) table <<= 1;
         w->tableSize = table;
@@ -476,14 +482,15 @@ int run_colour(avbd_world* w) {
     CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
     visit_count<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
     TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
-    visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->visits.p);
+    visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
     w->launches += 2;
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;
 }
 
-int run_primal(avbd_world* w, float alpha, float* dxDev) {
+// alphaDual >= 0: the sweep also applies the previous iteration's pending dual pass (deferred dual, avbd_solve.cu).
+int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f) {
     if (!w->graphValid) TRY(run_colour(w));
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
@@ -501,19 +508,21 @@ int run_primal(avbd_world* w, float alpha, float* dxDev) {
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
         w->launches += launch_primal(s, w->bview(), w->visitStart.p + first, w->visits.p, w->vgeom(), ms, fv, w->colOrder.p + first, count, avgVisits, w->prm, alpha,
-                                     w->sums.p, dxDev, w->dDiag.p);
+                                     alphaDual, w->sums.p, dxDev, w->dDiag.p);
     }
     CK(cudaGetLastError());
     return 0;
 }
 
-int run_dual(avbd_world* w, float alpha, bool lastOfStep = false) {
+// contacts = false: only the user forces' dual (the manifold rows' pass was deferred into the next sweep).
+// unvisitedReps / onlyUnvisited: see launch_dual.
+int run_dual(avbd_world* w, float alpha, bool lastOfStep = false, bool contacts = true, int unvisitedReps = 0, bool onlyUnvisited = false) {
     cudaStream_t s = w->stream;
-    if (w->nContacts > 0) {
-        launch_dual(s, w->bview(), w->mset(w->cur), w->nContacts, w->prm, alpha, lastOfStep ? w->dDiag.p : nullptr);
+    if (w->nContacts > 0 && contacts) {
+        launch_dual(s, w->bview(), w->mset(w->cur), w->nContacts, w->prm, alpha, unvisitedReps, onlyUnvisited, lastOfStep ? w->dDiag.p : nullptr);
         w->launches++;
+        if (lastOfStep) w->contactDiagDone = true;
     }
-    if (lastOfStep) w->contactDiagDone = true;
     ForceView fv = w->fview();
     if (fv.nJoints + fv.nSprings > 0) {
         launch_dual_user_forces(s, w->bview(), fv, w->prm);
@@ -553,19 +562,33 @@ int step_once(avbd_world* w) {
         // small world: the whole iteration loop in one cluster launch (cluster barriers instead of kernel boundaries)
         bool fuseDiag = !w->prm.postStabilize && w->prm.iterations > 0;
         persistent = launch_solve_loop(s, w->bview(), w->visitStart.p, w->visits.p, w->mset(w->cur), fvAll, w->colOrder.p, w->colRange.p,
-                                       w->nColours, w->maxColourCount, w->nContacts, w->prm, w->dDiag.p, fuseDiag);
+                                       w->nColours, w->maxColourCount, w->nContacts, w->prm, w->dDiag.p, fuseDiag, w->anyUnvisited);
         if (persistent) { w->launches++; w->contactDiagDone = fuseDiag; } else cudaGetLastError();
     }
     if (prof) {
         while ((int)w->pev.size() < 2 * total + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); w->pev.push_back(e); }
         cudaEventRecord(w->pev[0], s);
     }
-    int duals = 0;
+    // Deferred dual: the manifold rows' dual pass of iteration k rides on sweep k+1 (each contact's first visit applies it);
+    // only the pass after the LAST sweep runs as a kernel.  AVBD_SEPARATE_DUAL=1 keeps one dual launch per iteration.
+    const char* sepEnv = getenv("AVBD_SEPARATE_DUAL");
+    const bool separateDual = sepEnv && atoi(sepEnv) != 0;
+    int duals = 0, deferred = 0;
+    float pendingAlpha = -1.0f;
     for (int it = 0; it < total && !persistent; ++it) {
         float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
-        TRY(run_primal(w, a, nullptr));
+        TRY(run_primal(w, a, nullptr, pendingAlpha));
+        if (pendingAlpha >= 0.0f) ++deferred;
+        pendingAlpha = -1.0f;
         if (prof) cudaEventRecord(w->pev[2 * it + 1], s);
-        if (it < w->prm.iterations) { TRY(run_dual(w, a, it == total - 1)); ++duals; }   // last pass of the step (no postStabilize sweep after it)
+        if (it < w->prm.iterations) {
+            bool lastSweep = it == total - 1;                 // nothing moves after this pass: it also reduces the contact diagnostics
+            if (separateDual) { TRY(run_dual(w, a, lastSweep)); ++duals; }
+            else if (lastSweep) { TRY(run_dual(w, a, true, true, w->prm.iterations, false)); ++duals; }
+            else { TRY(run_dual(w, a, false, false)); pendingAlpha = a; }
+        } else if (!separateDual && w->anyUnvisited && w->prm.iterations > 0) {
+            TRY(run_dual(w, 1.0f, false, true, w->prm.iterations, true));    // postStabilize: contacts between static bodies only
+        }
         if (prof) cudaEventRecord(w->pev[2 * it + 2], s);
     }
     if (w->timed) cudaEventRecord(w->ev[5], s);
@@ -585,6 +608,7 @@ int step_once(avbd_world* w) {
         w->prof.primal_sweeps += total; w->prof.primal_launches += (long long)total * w->nColours;
         w->prof.primal_bodies += (long long)total * w->nDyn; w->prof.primal_visits += (long long)total * visits;
         w->prof.dual_launches += duals; w->prof.dual_contacts += (long long)duals * contacts;
+        w->prof.deferred_dual_contacts += (long long)deferred * contacts;
     }
     return 0;
 }

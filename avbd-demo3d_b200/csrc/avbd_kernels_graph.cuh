@@ -34,7 +34,9 @@ __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, in
 // of `visits` — one entry per live contact of every manifold touching the body, rebuilt whenever the topology changes.
 // Both run over the COLOUR-SORTED body order (colOrder[k], k = 0..nDyn-1): visitStart[k] is indexed by that position, so the
 // visits of the bodies of one colour tile are one contiguous run of `visits` and a tile can be walked one visit per thread.
-// Entry: {contact id, other body, (visiting body << 2) | anisotropic-inertia << 1 | body-is-A, friction bits}.
+// Entry: {contact id, other body, (visiting body << 3) | first-visit << 2 | anisotropic-inertia << 1 | body-is-A, friction bits}.
+// first-visit: this is the visit of the contact that comes FIRST in a sweep (the other endpoint is static or has a higher
+// colour) — the one that applies the previous iteration's deferred dual update (avbd_solve.cu).
 __global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
@@ -46,16 +48,24 @@ __global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange,
     visitCount[t] = k;
 }
 __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
-                           const int* visitStart, const BodyAux* aux, int4* visits) {
+                           const int* visitStart, const BodyAux* aux, const int* colour, int4* visits) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = colOrder[t];
     int4 rg = adjRange[i];
     int o = visitStart[t];
     float4 I = aux[i].inert;
-    int idx = (i << 2) | ((I.x == I.y && I.y == I.z) ? 0 : 2);
-    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; int c0 = cstart[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.y, idx | 1, h.w); }
-    for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; int c0 = cstart[m]; for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.x, idx, h.w); }
+    int idx = (i << 3) | ((I.x == I.y && I.y == I.z) ? 0 : 2);
+    int mine = colour[i];
+    auto first = [&](int other) { int co = colour[other]; return (co < 0 || mine < co) ? 4 : 0; };
+    for (int m = rg.x; m < rg.y; ++m) {
+        int4 h = hdr[m]; int c0 = cstart[m]; int tag = idx | 1 | first(h.y);
+        for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.y, tag, h.w);
+    }
+    for (int q = rg.z; q < rg.w; ++q) {
+        int m = bList[q]; int4 h = hdr[m]; int c0 = cstart[m]; int tag = idx | first(h.x);
+        for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.x, tag, h.w);
+    }
 }
 
 // Once per step (the narrowphase rewrites every contact): copy each visit's contact geometry into visit order, so the
@@ -209,7 +219,7 @@ __global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nContacts, 
         sepn = dot(pA - pB, xyz(n4));
         lam = ms.lp[ci].l.x;
     }
-    reduce_contact_diag(world, sepn, lam, world >= 0 ? 1 : 0, nm, nv, diag);
+    reduce_contact_diag_block(world, sepn, lam, world >= 0 ? 1 : 0, nm, nv, diag);
 }
 
 // Rigid public state <-> the 13-float-per-body host layout (pos3 quat4 lin3 ang3), on the device so the

@@ -44,48 +44,87 @@ struct WorldGroup {
 
 // Contact part of Solver::Diagnostics (solver.cpp:472-497) for one warp of contacts: sepn = (pA - pB) . n with the
 // final poses, |lambda_n| after the last dual update; one atomic per (warp, world) and field.
-__device__ __forceinline__ void reduce_contact_diag(int world, float sepn, float lamN, int contacts, int manifolds, int visits, Diag* diag) {
-    float pen = 0.0f, viol = 0.0f, lam = 0.0f;
+struct ContactDiagPart { int world; float pen, viol, lam; int contacts, manifolds, visits; };
+__device__ __forceinline__ ContactDiagPart contact_diag_part(int world, float sepn, float lamN, int contacts, int manifolds, int visits) {
+    ContactDiagPart p{world, 0.0f, 0.0f, 0.0f, contacts, manifolds, visits};
     if (world >= 0 && contacts) {
-        pen = (-sepn > 0.0f) ? -sepn : 0.0f;
+        p.pen = (-sepn > 0.0f) ? -sepn : 0.0f;
         float v = 0.005f - sepn;                       // PENETRATION_SLOP, solver.h:36
-        viol = v > 0.0f ? v : 0.0f;
-        lam = fabsf(lamN);
+        p.viol = v > 0.0f ? v : 0.0f;
+        p.lam = fabsf(lamN);
     }
-    WorldGroup wg(world);
-    pen = wg.max_nonneg(pen); viol = wg.max_nonneg(viol); lam = wg.max_nonneg(lam);
-    contacts = wg.sum(contacts); manifolds = wg.sum(manifolds); visits = wg.sum(visits);
-    if (wg.leader && world >= 0) {
-        Diag* d = diag + world;
-        if (pen > 0.0f) atomic_max_nonneg(&d->maxPenetration, pen);
-        if (viol > 0.0f) atomic_max_nonneg(&d->maxViolation, viol);
-        if (lam > 0.0f) atomic_max_nonneg(&d->maxNormalImpulse, lam);
-        if (contacts) atomicAdd(&d->activeContacts, contacts);
-        if (manifolds) atomicAdd(&d->activeManifolds, manifolds);
-        if (visits) atomicAdd(&d->contactVisits, visits);
+    return p;
+}
+// Combines the lanes of the calling warp that share a world; returns whether this lane is its group's leader.
+__device__ __forceinline__ bool combine_diag_warp(ContactDiagPart& p) {
+    WorldGroup wg(p.world);
+    p.pen = wg.max_nonneg(p.pen); p.viol = wg.max_nonneg(p.viol); p.lam = wg.max_nonneg(p.lam);
+    p.contacts = wg.sum(p.contacts); p.manifolds = wg.sum(p.manifolds); p.visits = wg.sum(p.visits);
+    return wg.leader;
+}
+// The maxima only grow during a step, so a plain read that already shows a value >= ours makes the atomic unnecessary
+// (a stale read only costs a redundant atomic): in steady state almost every warp skips all three.
+__device__ __forceinline__ void commit_diag(const ContactDiagPart& p, Diag* diag) {
+    Diag* d = diag + p.world;
+    if (p.pen > 0.0f && p.pen > *(volatile float*)&d->maxPenetration) atomic_max_nonneg(&d->maxPenetration, p.pen);
+    if (p.viol > 0.0f && p.viol > *(volatile float*)&d->maxViolation) atomic_max_nonneg(&d->maxViolation, p.viol);
+    if (p.lam > 0.0f && p.lam > *(volatile float*)&d->maxNormalImpulse) atomic_max_nonneg(&d->maxNormalImpulse, p.lam);
+    if (p.contacts) atomicAdd(&d->activeContacts, p.contacts);
+    if (p.manifolds) atomicAdd(&d->activeManifolds, p.manifolds);
+    if (p.visits) atomicAdd(&d->contactVisits, p.visits);
+}
+__device__ __forceinline__ void reduce_contact_diag(int world, float sepn, float lamN, int contacts, int manifolds, int visits, Diag* diag) {
+    ContactDiagPart p = contact_diag_part(world, sepn, lamN, contacts, manifolds, visits);
+    bool leader = combine_diag_warp(p);
+    if (leader && p.world >= 0) commit_diag(p, diag);
+}
+// Block-wide form (EVERY thread of a <= 1024-thread block must call it): warps whose lanes all share one world park their
+// partial result in shared memory and the first warp combines them, so a block issues one set of atomics per world it
+// touches instead of one per warp (a 1M-box world is ONE world: 135k warps hammering six addresses cost 0.4 ms).
+__device__ __forceinline__ void reduce_contact_diag_block(int world, float sepn, float lamN, int contacts, int manifolds, int visits, Diag* diag) {
+    __shared__ ContactDiagPart sPart[32];
+    ContactDiagPart p = contact_diag_part(world, sepn, lamN, contacts, manifolds, visits);
+    WorldGroup wg(p.world);
+    bool uniform = wg.peers == 0xffffffffu;
+    bool leader = combine_diag_warp(p);
+    int warp = threadIdx.x >> 5, nWarps = (blockDim.x + 31) >> 5;
+    if (uniform) { if (leader) sPart[warp] = p; }
+    else {
+        if (leader && p.world >= 0) commit_diag(p, diag);
+        if ((threadIdx.x & 31) == 0) sPart[warp].world = -1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        ContactDiagPart q{-1, 0.0f, 0.0f, 0.0f, 0, 0, 0};
+        if ((int)threadIdx.x < nWarps) q = sPart[threadIdx.x];
+        bool lead = combine_diag_warp(q);
+        if (lead && q.world >= 0) commit_diag(q, diag);
     }
 }
 #endif
 
 constexpr int kThreads = 256;
-constexpr int kLanesPerBody = 4;
 constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodies per CTA tile (9 lanes per body in the sum phase)
 
 // One colour of the primal sweep: `count` bodies listed in `order`; visitStart[k] .. visitStart[k+1] is the run of
 // `visits` of body order[k]; avgVisits (visits per body, whole world) picks the tile shape.
-// `sums` is scratch for the split path: 28 floats per body of the colour.  Returns the number of kernels launched.
+// `sums` is scratch for the split path: 28 floats per body of the colour.  alphaDual >= 0: the previous iteration's dual
+// pass (run with that alpha) is still pending and each contact's first visit applies it (deferred dual, avbd_solve.cu);
+// alphaDual < 0: plain primal sweep.  Returns the number of kernels launched.
 int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
-                  const int* order, int count, float avgVisits, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag);
+                  const int* order, int count, float avgVisits, SolveParams prm, float alpha, float alphaDual, float* sums, float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live (densely stored) contacts.
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics
 // (solver.cpp:472-497) are reduced here from the values already in registers instead of by a separate sweep.
-void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, Diag* diag);
+// unvisitedReps > 0 (deferred-dual steps): contacts no dynamic body visits take that many passes here, and with
+// onlyUnvisited all other contacts are skipped.
+void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, int unvisitedReps, bool onlyUnvisited, Diag* diag);
 // Small worlds: the whole iteration loop (solver.cpp:340-431, manifold rows only) in ONE launch of one thread-block
 // cluster (<= 16 CTAs, hardware cluster barrier between phases).  Returns false if the launch was refused (caller
 // falls back to per-colour launches).
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
-                       Diag* diag, bool contactDiag);
+                       Diag* diag, bool contactDiag, bool anyUnvisited);
 // Measurement aid (avbd_debug_time_primal): one colour's visit-sum kernel in mode 0 (product), 1 (memory only), 2 (math only).
 void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, int count, float alpha,
                               float* sums, int nContacts);

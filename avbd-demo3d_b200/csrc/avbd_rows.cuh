@@ -33,26 +33,29 @@ struct ContactEval {      // transient outputs of computeConstraint for one cont
     V3 wrA, wrB;          // rotate(rot, r): world lever arms
 };
 
-// Manifold::computeConstraint for ONE contact (manifold.cpp:177-245).  Stateful
-// exactly like the reference: clamps the warm tangential lambda into the
-// current cone and re-evaluates `stick` — the caller writes c.lam / c.stick back.
-AVBD_HD void contact_constraint(V3 posA, Q4 rotA, float invMassA, V3 posB, Q4 rotB, float invMassB,
-                                float mu0, float alpha, ContactState& c, ContactEval& e) {
-    float bias = clampf(1.0f - alpha, 0.0f, 1.0f);
+// Manifold::computeConstraint for ONE contact (manifold.cpp:177-245), in two halves so a kernel that evaluates the
+// constraint twice on the SAME poses (the deferred dual update followed by the primal rows) pays for the pose-dependent
+// half once.  contact_geometry: basis, world lever arms, separation along the basis (manifold.cpp:183-197).
+AVBD_HD void contact_geometry(V3 posA, Q4 rotA, V3 posB, Q4 rotB, const ContactState& c, ContactEval& e, float (&sep)[3]) {
     e.basis[0] = c.n;
     contact_basis_unit(c.n, e.basis[1], e.basis[2]);
     e.wrA = qrot(rotA, c.rA);
     e.wrB = qrot(rotB, c.rB);
     V3 dlt = (posA + e.wrA) - (posB + e.wrB);
-    float sepn = dot(dlt, e.basis[0]) - kNormalContactMargin;
-    float s1 = dot(dlt, e.basis[1]), s2 = dot(dlt, e.basis[2]);
-    e.C[0] = sepn + bias * c.C0n;
+    sep[0] = dot(dlt, e.basis[0]) - kNormalContactMargin;
+    sep[1] = dot(dlt, e.basis[1]); sep[2] = dot(dlt, e.basis[2]);
+}
+// contact_limits: C, force bounds, friction cone (manifold.cpp:198-241).  Stateful exactly like the reference: clamps
+// the warm tangential lambda into the current cone and re-evaluates `stick` — the caller writes c.lam / c.stick back.
+AVBD_HD void contact_limits(float invMassA, float invMassB, float mu0, float alpha, const float (&sep)[3], ContactState& c, ContactEval& e) {
+    float bias = clampf(1.0f - alpha, 0.0f, 1.0f);
+    e.C[0] = sep[0] + bias * c.C0n;
     float ims = invMassA + invMassB;
     float mscale = (ims > 1.0e-6f) ? (1.0f / ims) : 1.0f;
     float cap = kNormalForceCap * mscale;
     e.fmin[0] = -cap; e.fmax[0] = 0.0f;
-    e.C[1] = s1 + bias * c.C0t1;
-    e.C[2] = s2 + bias * c.C0t2;
+    e.C[1] = sep[1] + bias * c.C0t1;
+    e.C[2] = sep[2] + bias * c.C0t2;
     float warmN = fabsf(fmin2(c.lam[0], 0.0f));
     float trial = c.pen[0] * e.C[0] + c.lam[0];
     float trialN = fabsf(fmin2(trial, 0.0f));
@@ -67,6 +70,12 @@ AVBD_HD void contact_constraint(V3 posA, Q4 rotA, float invMassA, V3 posB, Q4 ro
     float slip2 = e.C[1] * e.C[1] + e.C[2] * e.C[2];
     float tl2 = c.lam[1] * c.lam[1] + c.lam[2] * c.lam[2];
     c.stick = (slip2 <= kStickThresh * kStickThresh) && (tl2 <= lim * lim + 1.0e-8f);
+}
+AVBD_HD void contact_constraint(V3 posA, Q4 rotA, float invMassA, V3 posB, Q4 rotB, float invMassB,
+                                float mu0, float alpha, ContactState& c, ContactEval& e) {
+    float sep[3];
+    contact_geometry(posA, rotA, posB, rotB, c, e, sep);
+    contact_limits(invMassA, invMassB, mu0, alpha, sep, c, e);
 }
 
 // 6x6 block system of one body, stored as the 27 numbers the Schur solve reads:

@@ -3,8 +3,15 @@
 // tolerance against the reference (BASELINE.json north_star), unlike the collision path in avbd_engine.cu.
 //
 // The reference walks bodies serially (Gauss-Seidel, solver.cpp:344); here bodies of one colour share no
-// manifold, so a colour is solved in one launch with LPB lanes cooperating on each body (one contact visit =
-// computeConstraint + 3 rows per lane).
+// manifold, so a colour is solved in one launch, one contact visit (computeConstraint + 3 rows) per thread.
+//
+// Deferred dual.  The dual / penalty-ramp pass of iteration k (solver.cpp:411-430) reads the poses left by sweep k, and
+// nothing moves between it and sweep k+1.  When sweep k+1 reaches the FIRST visit of a contact (its other endpoint is
+// static or has a higher colour) neither endpoint has moved yet, so that visit sees exactly the poses the dual pass
+// would have seen: it applies the pending dual update in registers (same operations, same order), then evaluates the
+// primal rows, and writes lambda / penalty back once.  A step therefore runs ONE stand-alone dual pass (after the last
+// sweep, fused with the contact diagnostics) instead of `iterations` of them.  alphaDual < 0 = nothing pending (first sweep
+// of a step, stage API).
 #include <cstdlib>
 #include "avbd_launch.h"
 #include "avbd_body.cuh"
@@ -18,19 +25,6 @@ __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int 
 }
 
 // ------------------------------------------------------------------ primal
-__device__ __forceinline__ float group_sum(float x, int width) {
-    for (int off = width >> 1; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off, width);
-    return x;
-}
-__device__ __forceinline__ void reduce_system(BodySystem& s, int width) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { s.rl[k] = group_sum(s.rl[k], width); s.ra[k] = group_sum(s.ra[k], width); }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { s.ll[k] = group_sum(s.ll[k], width); s.aa[k] = group_sum(s.aa[k], width); }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s.la[k] = group_sum(s.la[k], width);
-}
-
 // Rows of the user forces touching body i (lane 0 of the group, serial).
 __device__ void accumulate_user_forces(BodySystem& s, const ForceView& fv, const BodyPose* pose, int i, V3 pos, Q4 rot, const M3& invIw) {
     for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1]; ++k) {
@@ -89,6 +83,18 @@ __device__ __forceinline__ BodyPose load_pose_keep(const BodyPose* p, unsigned l
     BodyPose r; r.pos = ld4_keep(&p->pos, pol); r.rot = ld4_keep(&p->rot, pol); return r;
 }
 
+// One contact visit: computeConstraint for the visiting body, with the pending dual update first when `pending`.
+__device__ __forceinline__ void visit_constraint(float4 pa4, float4 qa4, float4 pb4, float4 qb4, float mu, float alpha, bool pending, float alphaDual,
+                                                 float beta, ContactState& cs, ContactEval& ev) {
+    float sep[3];
+    contact_geometry(xyz(pa4), quat(qa4), xyz(pb4), quat(qb4), cs, ev, sep);
+    if (pending) {
+        contact_limits(pa4.w, pb4.w, mu, alphaDual, sep, cs, ev);
+        dual_contact(cs, ev, beta);
+    }
+    contact_limits(pa4.w, pb4.w, mu, alpha, sep, cs, ev);
+}
+
 // Loads of data another CTA may have written earlier in the SAME launch (persistent loop): bypass L1.
 template <bool COH> __device__ __forceinline__ float4 ld4(const float4* p) { return COH ? __ldcg(p) : *p; }
 template <bool COH> __device__ __forceinline__ BodyPose load_pose(const BodyPose* p) {
@@ -96,95 +102,6 @@ template <bool COH> __device__ __forceinline__ BodyPose load_pose(const BodyPose
 }
 template <bool COH> __device__ __forceinline__ ContactState load_contact_c(const ManifoldSet& ms, int ci) {
     return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ld4<COH>(&ms.lp[ci].l), ld4<COH>(&ms.lp[ci].p));
-}
-
-// One tile (kThreads/LPB bodies of one colour) of the primal sweep (solver.cpp:344-409), in two phases so both are
-// lane-dense:
-//   phase 1  LPB lanes per body walk the body's run of contact visits (lane l takes visits l, l+LPB, ...):
-//            computeConstraint + 3 rows each, then a shuffle reduction leaves the 27 sums in lane 0, which
-//            parks them in shared memory;
-//   phase 2  one lane per body (the first kThreads/LPB threads = full warps): inertial terms, Schur solve,
-//            pose update.
-template <int LPB, bool COH>
-__device__ __forceinline__ void primal_tile(const BodyView& b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
-                                            const ManifoldSet& ms, const ForceView& fv, const int* __restrict__ order, int count, int tile,
-                                            const SolveParams& prm, float alpha, float* dxOut, Diag* diag, float* sSys) {
-    constexpr int BPB = kThreads / LPB;
-    int g = threadIdx.x / LPB, lane = threadIdx.x % LPB;
-    int gid = tile * BPB + g;
-    bool live = gid < count;
-    BodySystem sys; sys.clear();
-    if (live) {
-        int i = order[gid];
-        int v0 = visitStart[gid], v1 = visitStart[gid + 1];
-        bool userForces = fv.adjStart != nullptr && lane == 0 && fv.adjStart[i + 1] > fv.adjStart[i];
-        if (v0 + lane < v1 || userForces) {
-            BodyPose self = load_pose<COH>(b.pose + i);
-            V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
-            float invMassSelf = self.pos.w;
-            V3 I = xyz(b.aux[i].inert);
-            M3 invIw = rot_diag(qmat(rot), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
-            for (int v = v0 + lane; v < v1; v += LPB) {
-                int4 e = visits[v];
-                int ci = e.x; bool isA = (e.z & 1) != 0;
-                BodyPose po = load_pose<COH>(b.pose + e.y);
-                ContactState cs = load_contact_c<COH>(ms, ci);
-                ContactEval ev;
-                float mu = __int_as_float(e.w);
-                {
-                    float4 pa4 = isA ? self.pos : po.pos, qa4 = isA ? self.rot : po.rot, pb4 = isA ? po.pos : self.pos, qb4 = isA ? po.rot : self.rot;
-                    contact_constraint(xyz(pa4), quat(qa4), pa4.w, xyz(pb4), quat(qb4), pb4.w, mu, alpha, cs, ev);
-                }
-                BodySystem part;
-                contact_system(part, cs, ev, isA, true, invIw);
-                add_system(sys, part);
-                ms.lp[ci].l = pack_lambda(cs);    // computeConstraint's side effects (manifold.cpp:224-241)
-            }
-            if (userForces) accumulate_user_forces(sys, fv, b.pose, i, pos, rot, invIw);
-        }
-    }
-    if (LPB > 1) reduce_system(sys, LPB);
-    if (lane == 0) {
-        float* o = sSys + g * 27;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { o[k] = sys.rl[k]; o[3 + k] = sys.ra[k]; }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { o[6 + k] = sys.ll[k]; o[21 + k] = sys.aa[k]; }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) o[12 + k] = sys.la[k];
-    }
-    __syncthreads();
-    gid = tile * BPB + threadIdx.x;
-    if (threadIdx.x < BPB && gid < count) {
-        int i = order[gid];
-        BodyPose self = load_pose<COH>(b.pose + i);
-        BodyAux aux = b.aux[i];
-        V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
-        BodySystem own; M3 invIw;
-        body_self_system(pos, rot, aux, prm.dt, own, invIw);
-        const float* o = sSys + threadIdx.x * 27;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { own.rl[k] += o[k]; own.ra[k] += o[3 + k]; }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { own.ll[k] += o[6 + k]; own.aa[k] += o[21 + k]; }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) own.la[k] += o[12 + k];
-        V3 dl, da;
-        solve_body_system(own, dl, da);
-        int ev = apply_body_update(pos, rot, dl, da);
-        BodyPose out; out.pos = f4(pos, self.pos.w); out.rot = f4(rot);
-        b.pose[i] = out;
-        if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
-        if (ev) atomicAdd(&diag[b.worldId[i]].nanEvents, ev);
-    }
-}
-
-template <int LPB, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) primal_colour(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
-                                                                ManifoldSet ms, ForceView fv, const int* __restrict__ order, int count,
-                                                                SolveParams prm, float alpha, float* dxOut, Diag* diag) {
-    __shared__ float sSys[(kThreads / LPB) * 27];    // stride 27 is odd: conflict-free in phase 2
-    primal_tile<LPB, false>(b, visitStart, visits, ms, fv, order, count, blockIdx.x, prm, alpha, dxOut, diag, sSys);
 }
 
 // ------------------------------------------------------------------ primal, visit-parallel (the large-world path)
@@ -213,7 +130,7 @@ struct PrimalSmem {
 template <int BPB, bool COH>
 __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int* __restrict__ vstart, const int4* __restrict__ visits,
                                                    const ManifoldSet& ms, const ForceView& fv, const int* __restrict__ order, int count, int tile,
-                                                   const SolveParams& prm, float alpha, float* dxOut, Diag* diag, PrimalSmem<BPB>& sm) {
+                                                   const SolveParams& prm, float alpha, float alphaDual, float* dxOut, Diag* diag, PrimalSmem<BPB>& sm) {
     constexpr int L = kThreads / BPB;
     constexpr int CPL = (27 + L - 1) / L;
     const int t = threadIdx.x;
@@ -255,13 +172,13 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
             int lo = 0, hi = nb;                                  // slot: vs[lo] <= v < vs[lo + 1]
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.vs[mid] <= v) lo = mid; else hi = mid; }
             float4 sp = sm.pos[lo], sr = sm.rot[lo];
-            V3 pos = xyz(sp); Q4 rot = quat(sr);
             ContactState cs = unpack_contact(a4, b4, n4, l4, p4);
             ContactEval ev;
             float mu = __int_as_float(e.w);
+            bool pending = alphaDual >= 0.0f && (e.z & 4) != 0;
             {
                 float4 pa4 = isA ? sp : po.pos, qa4 = isA ? sr : po.rot, pb4 = isA ? po.pos : sp, qb4 = isA ? po.rot : sr;
-                contact_constraint(xyz(pa4), quat(qa4), pa4.w, xyz(pb4), quat(qb4), pb4.w, mu, alpha, cs, ev);
+                visit_constraint(pa4, qa4, pb4, qb4, mu, alpha, pending, alphaDual, prm.beta, cs, ev);
             }
             bool gyro = sm.inert[lo].w != 0.0f;
             M3 invIw;
@@ -275,7 +192,8 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
             contact_system(sys, cs, ev, isA, gyro, invIw);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
-            if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) ms.lp[ci].l = nl;
+            if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); ms.lp[ci] = q; }
+            else if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) ms.lp[ci].l = nl;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
 #pragma unroll
@@ -327,9 +245,9 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
 template <int BPB, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) primal_visits(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits,
                                                                 ManifoldSet ms, ForceView fv, const int* __restrict__ order, int count,
-                                                                SolveParams prm, float alpha, float* dxOut, Diag* diag) {
+                                                                SolveParams prm, float alpha, float alphaDual, float* dxOut, Diag* diag) {
     __shared__ PrimalSmem<BPB> sm;
-    primal_tile_visits<BPB, false>(b, vstart, visits, ms, fv, order, count, blockIdx.x, prm, alpha, dxOut, diag, sm);
+    primal_tile_visits<BPB, false>(b, vstart, visits, ms, fv, order, count, blockIdx.x, prm, alpha, alphaDual, dxOut, diag, sm);
 }
 
 // ------------------------------------------------------------------ primal, split (visit sums -> block solve)
@@ -338,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visits(BodyView b, cons
 //   primal_visit_sums  one visit per thread -> per-body sums of the 27 row contributions (shared-memory transpose +
 //                      in-order reduction), written to `sums` in colour order (28 floats per body)
 //   primal_solve       one body per thread: inertial terms + sums -> Schur solve -> pose update
-// Visit entry (built with the graph): {contact id, other body, (self body << 2) | anisotropic-inertia << 1 | body-is-A, mu}.
+// Visit entry (built with the graph): {contact id, other body, (self body << 3) | first-visit << 2 | anisotropic-inertia << 1 | body-is-A, mu}.
 template <int BPB>
 struct VisitSmem {
     float c[27][kThreads + 1];
@@ -351,7 +269,8 @@ constexpr int kSumStride = 28;
 // sequential (its instruction-issue floor); neither writes solver state.
 template <int BPB, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits, VisitGeom vg,
-                                                                    ManifoldSet ms, int count, float alpha, float* __restrict__ sums, int nContacts = 0) {
+                                                                    ManifoldSet ms, int count, float alpha, float alphaDual, float beta, float* __restrict__ sums,
+                                                                    int nContacts = 0) {
     constexpr int L = kThreads / BPB;
     constexpr int CPL = (27 + L - 1) / L;
     __shared__ VisitSmem<BPB> sm;
@@ -369,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, 
         int v = base + t;
         if (v < v1) {
             int4 e = __ldcs(visits + v);
-            int ci = e.x, self = e.z >> 2; bool isA = (e.z & 1) != 0, gyro = (e.z & 2) != 0;
+            int ci = e.x, self = e.z >> 3; bool isA = (e.z & 1) != 0, gyro = (e.z & 2) != 0, pending = alphaDual >= 0.0f && (e.z & 4) != 0;
             if (MODE == 2) { ci = v % nContacts; self = v % b.n; e.y = (v + 1) % b.n; }
             BodyPose ps = load_pose_keep(b.pose + self, keep);
             BodyPose po = load_pose_keep(b.pose + e.y, keep);
@@ -389,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, 
             } else {
             {   // one call with the operands swapped by selects: an if/else duplicates the code and mixed warps run both arms
                 float4 pa4 = isA ? ps.pos : po.pos, qa4 = isA ? ps.rot : po.rot, pb4 = isA ? po.pos : ps.pos, qb4 = isA ? po.rot : ps.rot;
-                contact_constraint(xyz(pa4), quat(qa4), pa4.w, xyz(pb4), quat(qb4), pb4.w, mu, alpha, cs, ev);
+                visit_constraint(pa4, qa4, pb4, qb4, mu, alpha, pending, alphaDual, beta, cs, ev);
             }
             M3 invIw = m3(zero3(), zero3(), zero3());
             if (gyro) {   // anisotropic inertia only: for R diag(c) R^T = c Id the term Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero
@@ -400,7 +319,10 @@ __global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, 
             contact_system(sys, cs, ev, isA, gyro, invIw);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
-            if (MODE == 0 && (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w)) lp->l = nl;
+            if (MODE == 0) {
+                if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); *lp = q; }
+                else if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) lp->l = nl;
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
 #pragma unroll
@@ -462,32 +384,43 @@ __global__ void __launch_bounds__(kThreads) primal_solve(BodyView b, ForceView f
 // ------------------------------------------------------------------ dual
 // One LIVE contact (solver.cpp:411-430 for manifold rows).  Returns what the diagnostics need.
 struct DualOut { float sepn, lamN; int visits, world, first; };
+// `unvisitedReps` > 0 is the deferred-dual form (the primal sweeps already applied every pass but the last to each
+// contact they visit): a contact NO dynamic body visits (both endpoints static) takes all `unvisitedReps` passes here —
+// its poses never move, so repeating the update in place equals the reference's once-per-iteration pass — and with
+// `onlyUnvisited` every other contact is left alone (postStabilize: the extra sweep already applied the last pass).
 template <bool COH, bool DIAG>
-__device__ __forceinline__ DualOut dual_one(const BodyView& b, const ManifoldSet& ms, int ci, const SolveParams& prm, float alpha) {
+__device__ __forceinline__ DualOut dual_one(const BodyView& b, const ManifoldSet& ms, int ci, const SolveParams& prm, float alpha,
+                                            int unvisitedReps = 0, bool onlyUnvisited = false) {
     int m = ms.cM[ci];
     int4 h = ms.hdr[m];
     BodyPose pa = load_pose<COH>(b.pose + h.x), pb = load_pose<COH>(b.pose + h.y);
     ContactState cs = load_contact_c<COH>(ms, ci);
     ContactEval ev;
-    contact_constraint(xyz(pa.pos), quat(pa.rot), pa.pos.w, xyz(pb.pos), quat(pb.rot), pb.pos.w, __int_as_float(h.w), alpha, cs, ev);
-    dual_contact(cs, ev, prm.beta);
-    ContactLP q; q.l = pack_lambda(cs); q.p = pack_penalty(cs);
-    ms.lp[ci] = q;
     DualOut o;
+    o.visits = (pa.pos.w > 0.0f ? 1 : 0) + (pb.pos.w > 0.0f ? 1 : 0);
+    int reps = 1;
+    if (unvisitedReps > 0) reps = o.visits == 0 ? unvisitedReps : (onlyUnvisited ? 0 : 1);
+    float sep[3];
+    contact_geometry(xyz(pa.pos), quat(pa.rot), xyz(pb.pos), quat(pb.rot), cs, ev, sep);
+    for (int r = 0; r < reps; ++r) {
+        contact_limits(pa.pos.w, pb.pos.w, __int_as_float(h.w), alpha, sep, cs, ev);
+        dual_contact(cs, ev, prm.beta);
+    }
+    if (reps > 0) { ContactLP q; q.l = pack_lambda(cs); q.p = pack_penalty(cs); ms.lp[ci] = q; }
     o.sepn = dot((xyz(pa.pos) + ev.wrA) - (xyz(pb.pos) + ev.wrB), cs.n);
     o.lamN = cs.lam[0];
-    o.visits = (pa.pos.w > 0.0f ? 1 : 0) + (pb.pos.w > 0.0f ? 1 : 0);
     o.world = -1; o.first = 0;
     if (DIAG) { o.world = b.worldId[h.x]; o.first = (ci == 0 || ms.cM[ci - 1] != m) ? 1 : 0; }
     return o;
 }
 
 template <bool DIAG>
-__global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, Diag* diag) {
+__global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, int unvisitedReps,
+                                                          bool onlyUnvisited, Diag* diag) {
     int ci = blockIdx.x * blockDim.x + threadIdx.x;
     DualOut o{0.0f, 0.0f, 0, -1, 0};
-    if (ci < nContacts) o = dual_one<false, DIAG>(b, ms, ci, prm, alpha);
-    if (DIAG) reduce_contact_diag(o.world, o.sepn, o.lamN, o.world >= 0 ? 1 : 0, o.first, o.visits, diag);
+    if (ci < nContacts) o = dual_one<false, DIAG>(b, ms, ci, prm, alpha, unvisitedReps, onlyUnvisited);
+    if (DIAG) reduce_contact_diag_block(o.world, o.sepn, o.lamN, o.world >= 0 ? 1 : 0, o.first, o.visits, diag);
 }
 
 // ------------------------------------------------------------------ persistent iteration loop (small worlds)
@@ -508,30 +441,36 @@ template <int BPB>
 __global__ void __launch_bounds__(kThreads, 1) solve_loop_cluster(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
                                                                   ManifoldSet ms, ForceView fv, const int* __restrict__ order,
                                                                   const int2* __restrict__ colRange, int nColours, int nContacts, SolveParams prm,
-                                                                  Diag* diag, bool contactDiag) {
+                                                                  Diag* diag, bool contactDiag, bool anyUnvisited) {
     __shared__ PrimalSmem<BPB> sm;
     const int rank = (int)cluster_rank(), nCta = (int)cluster_size();       // the grid is one cluster
     int total = prm.iterations + (prm.postStabilize ? 1 : 0);
+    float alphaDual = -1.0f;                                    // dual pass of the previous iteration still to apply (deferred dual)
     for (int it = 0; it < total; ++it) {
         float alpha = prm.postStabilize ? (it < prm.iterations ? 1.0f : 0.0f) : prm.alpha;      // solver.cpp:340-342
         for (int c = 0; c < nColours; ++c) {
             int2 r = colRange[c];
             int count = r.y - r.x;
             for (int tile = rank; tile * BPB < count; tile += nCta) {
-                primal_tile_visits<BPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, nullptr, diag, sm);
+                primal_tile_visits<BPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, alphaDual, nullptr, diag, sm);
                 __syncthreads();
             }
             cluster_barrier();
         }
-        if (it < prm.iterations) {
-            bool last = contactDiag && it == total - 1;            // nothing moves after this pass: reduce the contact diagnostics here
-            int rounded = (nContacts + 31) & ~31;                   // whole warps stay in the loop (warp-level reductions below)
-            for (int t = rank * kThreads + (int)threadIdx.x; t < rounded; t += nCta * kThreads) {
-                DualOut o{0.0f, 0.0f, 0, -1, 0};
-                if (t < nContacts) o = dual_one<true, true>(b, ms, t, prm, alpha);
-                if (last) reduce_contact_diag(o.world, o.sepn, o.lamN, o.world >= 0 ? 1 : 0, o.first, o.visits, diag);
-            }
-            cluster_barrier();
+        alphaDual = it < prm.iterations ? alpha : -1.0f;
+    }
+    // what the sweeps could not apply: the last iteration's dual pass (nothing moves after it, so the contact diagnostics
+    // are reduced from the same registers), or — when postStabilize's extra sweep already applied it — only the contacts
+    // no dynamic body visits
+    bool lastPending = alphaDual >= 0.0f;
+    if (prm.iterations > 0 && (lastPending || anyUnvisited)) {
+        float alpha = prm.postStabilize ? 1.0f : prm.alpha;
+        bool reduce = contactDiag && lastPending;
+        int rounded = (nContacts + 31) & ~31;                   // whole warps stay in the loop (warp-level reductions below)
+        for (int t = rank * kThreads + (int)threadIdx.x; t < rounded; t += nCta * kThreads) {
+            DualOut o{0.0f, 0.0f, 0, -1, 0};
+            if (t < nContacts) o = dual_one<true, true>(b, ms, t, prm, alpha, prm.iterations, !lastPending);
+            if (reduce) reduce_contact_diag(o.world, o.sepn, o.lamN, o.world >= 0 ? 1 : 0, o.first, o.visits, diag);
         }
     }
 }
@@ -602,53 +541,39 @@ __global__ void solve6_batch(const float* lhs36, const float* rhs6, int n, float
 // ------------------------------------------------------------------ launchers (declared in avbd_launch.h)
 static inline int blocks_of(long long n, int per) { long long b = (n + per - 1) / per; return (int)(b < 1 ? 1 : b); }
 
-template <int LPB, int MINB>
-static void launch_primal_variant(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv,
-                                  const int* order, int count, SolveParams prm, float alpha, float* dxOut, Diag* diag) {
-    primal_colour<LPB, MINB><<<blocks_of(count, kThreads / LPB), kThreads, 0, s>>>(b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag);
-}
-
 template <int BPB, int MINB>
 static void launch_primal_visits(cudaStream_t s, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, ForceView fv,
-                                 const int* order, int count, SolveParams prm, float alpha, float* dxOut, Diag* diag) {
-    primal_visits<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, ms, fv, order, count, prm, alpha, dxOut, diag);
+                                 const int* order, int count, SolveParams prm, float alpha, float alphaDual, float* dxOut, Diag* diag) {
+    primal_visits<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, ms, fv, order, count, prm, alpha, alphaDual, dxOut, diag);
 }
 
 template <int BPB, int MINB>
 static void launch_split(cudaStream_t s, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
-                         const int* order, int count, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag) {
-    primal_visit_sums<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, sums);
+                         const int* order, int count, SolveParams prm, float alpha, float alphaDual, float* sums, float* dxOut, Diag* diag) {
+    primal_visit_sums<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, alphaDual, prm.beta, sums);
     primal_solve<<<blocks_of(count, kThreads), kThreads, 0, s>>>(b, fv, order, count, sums, prm, dxOut, diag);
 }
 
 // Default: the split path (visit sums + block solve), bodies per tile chosen so a tile's visits fill the block once.
 // AVBD_PRIMAL_VARIANT (tuning aid): "s<BPB>[m<MINB>]" split path with a forced tile size (s16 s28 s64; m3 m4);
-// "v<BPB>[m<MINB>]" the fused visit-parallel kernel; "<lanes per body><min blocks per SM>" the lanes-per-body kernel (43 ...).
-// Returns the number of kernels launched.
+// "v<BPB>[m<MINB>]" the single-kernel visit-parallel tile.  Returns the number of kernels launched.
 int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
-                  const int* order, int count, float avgVisits, SolveParams prm, float alpha, float* sums, float* dxOut, Diag* diag) {
+                  const int* order, int count, float avgVisits, SolveParams prm, float alpha, float alphaDual, float* sums, float* dxOut, Diag* diag) {
     static int variant = 0, minb = 3; static char kind = 's';
     static bool init = [] {
         const char* e = getenv("AVBD_PRIMAL_VARIANT");
         if (!e) return true;
         if (e[0] == 'v' || e[0] == 's') {
             kind = e[0];
-            variant = -atoi(e + 1);
+            variant = atoi(e + 1);
             for (const char* p = e; *p; ++p) if (*p == 'm') minb = atoi(p + 1);
-        } else variant = atoi(e);
+        }
         return true;
     }();
     (void)init;
-#define AVBD_PV(L, M) case L * 10 + M: launch_primal_variant<L, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag); return 1;
-#define AVBD_VV(B, M) launch_primal_visits<B, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, dxOut, diag)
-#define AVBD_SV(B, M) launch_split<B, M>(s, b, visitStart, visits, vg, ms, fv, order, count, prm, alpha, sums, dxOut, diag)
-    if (variant > 0) {
-        switch (variant) {
-            AVBD_PV(8, 2) AVBD_PV(8, 3) AVBD_PV(4, 2) AVBD_PV(4, 3) AVBD_PV(4, 4) AVBD_PV(2, 3)
-            default: break;
-        }
-    }
-    int bpb = variant < 0 ? -variant : (avgVisits <= 3.7f ? 64 : (avgVisits <= 9.0f ? 28 : (avgVisits <= 16.0f ? 16 : 8)));
+#define AVBD_VV(B, M) launch_primal_visits<B, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, alphaDual, dxOut, diag)
+#define AVBD_SV(B, M) launch_split<B, M>(s, b, visitStart, visits, vg, ms, fv, order, count, prm, alpha, alphaDual, sums, dxOut, diag)
+    int bpb = variant > 0 ? variant : (avgVisits <= 3.7f ? 64 : (avgVisits <= 9.0f ? 28 : (avgVisits <= 16.0f ? 16 : 8)));
     if (kind == 'v') {
         if (bpb >= 64) { if (minb == 4) AVBD_VV(64, 4); else AVBD_VV(64, 3); }
         else if (bpb >= 28) { if (minb == 4) AVBD_VV(28, 4); else AVBD_VV(28, 3); }
@@ -660,19 +585,18 @@ int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4*
     else if (bpb >= 16) { if (minb == 4) AVBD_SV(16, 4); else AVBD_SV(16, 3); }
     else AVBD_SV(8, 3);
     return 2;
-#undef AVBD_PV
 #undef AVBD_VV
 #undef AVBD_SV
 }
 void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, int count, float alpha,
                               float* sums, int nContacts) {
-    if (mode == 1) primal_visit_sums<28, 3, 1><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, sums, nContacts);
-    else if (mode == 2) primal_visit_sums<28, 3, 2><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, sums, nContacts);
-    else primal_visit_sums<28, 3, 0><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, sums, nContacts);
+    if (mode == 1) primal_visit_sums<28, 3, 1><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, -1.0f, 0.0f, sums, nContacts);
+    else if (mode == 2) primal_visit_sums<28, 3, 2><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, -1.0f, 0.0f, sums, nContacts);
+    else primal_visit_sums<28, 3, 0><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, -1.0f, 0.0f, sums, nContacts);
 }
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
-                       Diag* diag, bool contactDiag) {
+                       Diag* diag, bool contactDiag, bool anyUnvisited) {
     constexpr int BPB = kClusterBodiesPerTile;
     static int maxCluster = [] {
         // 16 CTAs need the non-portable opt-in; fall back to the portable 8 if the device refuses it
@@ -691,19 +615,19 @@ bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = nCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag, anyUnvisited);
     if (e != cudaSuccess && nCta > 8) {          // a 16-CTA cluster may not be placeable (MIG slices, busy GPCs): retry with the portable size
         cudaGetLastError();
         maxCluster = 8;
         attr[0].val.clusterDim.x = 8; cfg.gridDim = dim3(8);
-        e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag);
+        e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag, anyUnvisited);
     }
     return e == cudaSuccess;
 }
 
-void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, Diag* diag) {
-    if (diag) dual_contacts<true><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, nContacts, prm, alpha, diag);
-    else      dual_contacts<false><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, nContacts, prm, alpha, nullptr);
+void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, int unvisitedReps, bool onlyUnvisited, Diag* diag) {
+    if (diag) dual_contacts<true><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, nContacts, prm, alpha, unvisitedReps, onlyUnvisited, diag);
+    else      dual_contacts<false><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, nContacts, prm, alpha, unvisitedReps, onlyUnvisited, nullptr);
 }
 void launch_dual_user_forces(cudaStream_t s, BodyView b, ForceView fv, SolveParams prm) {
     dual_user_forces<<<blocks_of(fv.nJoints + fv.nSprings, kThreads), kThreads, 0, s>>>(b, fv, prm);

@@ -53,6 +53,7 @@ typedef struct avbd_profile {
     double ms_primal, ms_dual;
     long long steps, primal_sweeps, primal_launches, primal_bodies, primal_visits, dual_launches, dual_contacts;
     long long kernel_launches, library_launches;   /* totals since world creation: own kernels / CUB passes */
+    long long deferred_dual_contacts;              /* contact dual updates applied INSIDE primal sweeps (deferred dual): their time is in ms_primal */
 } avbd_profile;
 
 const char* avbd_last_error(void);

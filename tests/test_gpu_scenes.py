@@ -210,3 +210,64 @@ def test_ensemble_is_bit_identical_across_partitions(avbd, name, steps):
     assert whole[5 * n: 6 * n].tobytes() == solo.tobytes() and dwhole[5] == dsolo[0]
     assert len({whole[k * n + 1: (k + 1) * n].tobytes() for k in range(8)}) == 8          # the worlds really differ
     assert dwhole[0]["activeManifolds"] > 0 and dwhole[0]["dynamicBodies"] == n - 1
+
+
+# --------------------------------------------------------------------------- deferred dual
+def _run_variant(avbd, build, steps, env):
+    """A fresh world stepped under the given environment toggles (read at world creation / every step)."""
+    keys = ("AVBD_PERSISTENT_MAX_BODIES", "AVBD_SEPARATE_DUAL")
+    old = {k: os.environ.get(k) for k in keys}
+    try:
+        for k in keys:
+            if k in env: os.environ[k] = env[k]
+            else: os.environ.pop(k, None)
+        w = avbd.World()
+        build(w)
+        w.step(steps)
+        st, d = w.state(), w.diagnostics()
+        ints, feats, stick, flts = w.manifolds_raw()
+        w.close()
+        return st, d, ints, feats, stick, flts
+    finally:
+        for k, v in old.items():
+            if v is None: os.environ.pop(k, None)
+            else: os.environ[k] = v
+
+
+def _pile_with_two_statics(post):
+    def build(w):
+        w.set_params(iterations=6, post=post)
+        w.add_body((20, 1, 20), 0.0, 0.5, (0, -0.5, 0))
+        w.add_body((4, 1, 4), 0.0, 0.5, (0, 0.3, 0))               # overlaps the ground: a contact no dynamic body visits
+        rng = np.random.default_rng(7)
+        for k in range(40):
+            p = (float(rng.uniform(-3, 3)), 1.5 + 0.55 * k, float(rng.uniform(-3, 3)))
+            w.add_body((1, 1, 1), 1.0, 0.5, p)
+    return build
+
+
+@pytest.mark.parametrize("case", ["Pyramid", "pile", "pile_post"])
+def test_deferred_dual_equals_one_dual_pass_per_iteration(avbd, case):
+    """The step applies iteration k's dual update at each contact's first visit of sweep k+1 (avbd_solve.cu) instead of
+    in a dual kernel after sweep k.  Same operations on the same poses in the same order, so the per-colour path and the
+    cluster loop must agree with the one-launch-per-iteration form (solver.cpp:411-430 order) to FMA-contraction rounding —
+    including lambda / penalty of a contact between two static bodies, which no sweep visits, and postStabilize's extra
+    sweep (different alpha for the pending dual and the primal rows)."""
+    from avbd_demo3d_b200 import scenes
+    if case == "Pyramid":
+        build, steps = (lambda w: scenes.load(w, scenes.scene("Pyramid"))), 12
+    else:
+        build, steps = _pile_with_two_statics(case == "pile_post"), 25
+    ref = _run_variant(avbd, build, steps, {"AVBD_PERSISTENT_MAX_BODIES": "0", "AVBD_SEPARATE_DUAL": "1"})
+    for env in ({"AVBD_PERSISTENT_MAX_BODIES": "0"}, {}):
+        got = _run_variant(avbd, build, steps, env)
+        assert np.abs(got[0] - ref[0]).max() < 2e-4, (env, float(np.abs(got[0] - ref[0]).max()))
+        assert (got[1]["manifolds"], got[1]["contacts"]) == (ref[1]["manifolds"], ref[1]["contacts"])
+        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+        lam_ref, lam_got = ref[5], got[5]
+        rel = np.abs(lam_got - lam_ref) / (1.0 + np.abs(lam_ref))          # geometry, lambda, penalty of every contact
+        assert rel.max() <= 2e-3, float(rel.max())
+        assert abs(got[1]["maxLambda"] - ref[1]["maxLambda"]) <= 1e-3 * max(1.0, ref[1]["maxLambda"])
+    if case != "Pyramid":
+        pairs = {(int(a), int(b)) for a, b, _ in ref[2]}
+        assert (1, 0) in pairs               # the static-static manifold really exists
