@@ -66,7 +66,6 @@ ABI = {
     "avbd_step": (C.c_int, [C.c_void_p, C.c_int]),
     "avbd_sync": (C.c_int, [C.c_void_p]),
     "avbd_step_timed": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
-    "avbd_debug_time_primal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "avbd_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "avbd_get_profile": (C.c_int, [C.c_void_p, C.POINTER(Profile)]),
     "avbd_download_state": (C.c_int, [C.c_void_p, _f32p]),
@@ -295,11 +294,6 @@ class World:
         k = C.c_int(0)
         _check(self.L.avbd_download_colours(self.h, col, C.byref(k)))
         return col[:self.n], k.value
-
-    def debug_time_primal(self, mode, reps=5):
-        ms = C.c_float(0.0)
-        _check(self.L.avbd_debug_time_primal(self.h, mode, reps, C.byref(ms)))
-        return ms.value
 
     def stage_primal(self, alpha, want_dx=False):
         dx = np.zeros((self.n, 6), np.float32) if want_dx else None

@@ -98,7 +98,7 @@ struct avbd_world {
     // graph
     DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
-    int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
+    int2 hColRange[64]; int hColVisit[65]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
     long long graphReuses = 0; int persistentMaxBodies = 4096;
 
     // user forces
@@ -109,7 +109,7 @@ struct avbd_world {
     // counters / diagnostics
     Counters* dCnt = nullptr; Counters* hCnt = nullptr;
     DevBuf<Diag> dDiag; Diag* hDiag = nullptr; size_t hDiagCap = 0;
-    DevBuf<float> dx, sums;
+    DevBuf<float> dx, sums, carry; DevBuf<int> colVisit;
     DevBuf<char> temp;
 
     // per-kernel profiling (avbd_set_profiling): events around every primal sweep and dual pass
@@ -484,6 +484,12 @@ int run_colour(avbd_world* w) {
     TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
     visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
     w->launches += 2;
+    // first visit of every colour (the flat primal partitions a colour's visits, not its bodies)
+    TRY(w->colVisit.ensure(65, false, s));
+    colour_visit_bounds<<<1, 64, 0, s>>>(w->colRange.p, w->nColours, w->visitStart.p, w->nDyn, w->colVisit.p);
+    w->launches++;
+    CK(cudaMemcpyAsync(w->hColVisit, w->colVisit.p, sizeof(int) * 65, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;
@@ -495,7 +501,9 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
-    TRY(w->sums.ensure((size_t)std::max(1, w->maxColourCount) * 28, false, s));
+    int chunkT = primal_flat_chunk_threads();
+    TRY(w->sums.ensure((size_t)std::max(1, w->n) * 28, false, s));
+    TRY(w->carry.ensure(((size_t)std::max(1, 2 * w->nContacts) / chunkT + 2) * 28, false, s));
     if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
         size_t cap = w->visits.cap;
         TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));
@@ -503,12 +511,11 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f
         w->launches++;
     }
     w->visitGeomStale = false;
-    float avgVisits = w->nDyn > 0 ? 2.0f * (float)w->nContacts / (float)w->nDyn : 0.0f;   // upper bound: static endpoints do not visit
     for (int c = 0; c < w->nColours; ++c) {
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
-        w->launches += launch_primal(s, w->bview(), w->visitStart.p + first, w->visits.p, w->vgeom(), ms, fv, w->colOrder.p + first, count, avgVisits, w->prm, alpha,
-                                     alphaDual, w->sums.p, dxDev, w->dDiag.p);
+        w->launches += launch_primal_flat(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->colOrder.p + first, w->visitStart.p + first, count,
+                                          w->hColVisit[c], w->hColVisit[c + 1], w->prm, alpha, alphaDual, w->sums.p, w->carry.p, dxDev, w->dDiag.p);
     }
     CK(cudaGetLastError());
     return 0;
@@ -672,7 +679,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
-    w->dDiag.release(); w->dx.release(); w->sums.release(); w->temp.release(); w->stateDev.release();
+    w->dDiag.release(); w->dx.release(); w->sums.release(); w->carry.release(); w->colVisit.release(); w->temp.release(); w->stateDev.release();
     w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stLP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
@@ -1118,27 +1125,6 @@ int avbd_solve6x6(int device, int n, const float* lhs36, const float* rhs6, floa
     CK(cudaGetLastError());
     CK(cudaMemcpy(out6, dout, n * 6 * sizeof(float), cudaMemcpyDeviceToHost));
     cudaFree(dl); cudaFree(dr); cudaFree(dout);
-    return 0;
-}
-
-int avbd_debug_time_primal(avbd_world* w, int mode, int reps, float* ms) {
-    if (!w || !ms || reps < 1) return fail(AVBD_ERR_ARG, "bad argument");
-    CK(cudaSetDevice(w->device));
-    if (!w->graphValid || w->nColours == 0) return fail(AVBD_ERR_ARG, "step the world first");
-    cudaStream_t s = w->stream;
-    TRY(w->sums.ensure((size_t)std::max(1, w->maxColourCount) * 28, false, s));
-    CK(cudaStreamSynchronize(s));
-    CK(cudaEventRecord(w->ev[7], s));
-    for (int r = 0; r < reps; ++r)
-        for (int c = 0; c < w->nColours; ++c) {
-            int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
-            if (count > 0) launch_primal_experiment(s, mode, w->bview(), w->visitStart.p + first, w->visits.p, w->vgeom(), w->mset(w->cur), count, w->prm.alpha, w->sums.p, w->nContacts);
-        }
-    CK(cudaEventRecord(w->ev[8], s));
-    CK(cudaStreamSynchronize(s));
-    CK(cudaEventElapsedTime(ms, w->ev[7], w->ev[8]));
-    *ms /= (float)reps;
-    CK(cudaGetLastError());
     return 0;
 }
 

@@ -69,12 +69,17 @@ __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, 
 }
 
 // Once per step (the narrowphase rewrites every contact): copy each visit's contact geometry into visit order, so the
-// iterations x colours primal sweeps stream it instead of gathering it.  nVisits lives on the device (visitStart[nDyn]).
+// iterations x colours primal sweeps stream it instead of gathering it — already in the VISITING body's frame:
+// a = {r_self, C0n}, b = {r_other, C0t.x}, n = {n, C0t.y}.  nVisits lives on the device (visitStart[nDyn]).
 __global__ void visit_geometry(const int4* __restrict__ visits, const int* __restrict__ nVisits, ManifoldSet ms, VisitGeom vg) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= *nVisits) return;
-    int ci = visits[v].x;
-    vg.a[v] = ms.cA[ci]; vg.b[v] = ms.cB[ci]; vg.n[v] = ms.cN[ci];
+    int4 e = visits[v];
+    float4 a = ms.cA[e.x], b = ms.cB[e.x];
+    bool isA = (e.z & 1) != 0;
+    vg.a[v] = isA ? a : make_float4(b.x, b.y, b.z, a.w);
+    vg.b[v] = isA ? b : make_float4(a.x, a.y, a.z, b.w);
+    vg.n[v] = ms.cN[e.x];
 }
 
 // ------------------------------------------------------------------ colouring
@@ -146,6 +151,14 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
     if (t == 0 || keySorted[t - 1] != c) colourRange[c].x = t;
     if (t == nDyn - 1 || keySorted[t + 1] != c) colourRange[c].y = t + 1;
     if (t == nDyn - 1) cnt->nColours = (int)c + 1;
+}
+
+// out[c] = index of colour c's first visit, out[nColours ..] = total visits (colours are contiguous in the visit list).
+__global__ void colour_visit_bounds(const int2* colourRange, int nColours, const int* visitStart, int nDyn, int* out) {
+    int c = threadIdx.x;
+    if (c > 64) return;
+    out[c] = c < nColours ? visitStart[colourRange[c].x] : visitStart[nDyn];
+    if (c == 0) out[64] = visitStart[nDyn];
 }
 
 // ------------------------------------------------------------------ predict / warm-start decay of user forces

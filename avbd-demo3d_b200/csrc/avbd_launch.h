@@ -22,7 +22,8 @@ struct ForceView {
 };
 
 // Contact geometry in VISIT order (one float4 per field per visit, refreshed once per step by visit_geometry): the primal's
-// visit kernel streams it fully coalesced instead of gathering 3 x 16 B per visit by contact id.  {rA,C0n} {rB,C0t.x} {n,C0t.y}.
+// visit kernel streams it fully coalesced instead of gathering 3 x 16 B per visit by contact id, in the visiting body's
+// frame: {r_self,C0n} {r_other,C0t.x} {n,C0t.y}.
 struct VisitGeom { float4* a; float4* b; float4* n; };
 
 #ifdef __CUDACC__
@@ -106,13 +107,13 @@ __device__ __forceinline__ void reduce_contact_diag_block(int world, float sepn,
 constexpr int kThreads = 256;
 constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodies per CTA tile (9 lanes per body in the sum phase)
 
-// One colour of the primal sweep: `count` bodies listed in `order`; visitStart[k] .. visitStart[k+1] is the run of
-// `visits` of body order[k]; avgVisits (visits per body, whole world) picks the tile shape.
-// `sums` is scratch for the split path: 28 floats per body of the colour.  alphaDual >= 0: the previous iteration's dual
-// pass (run with that alpha) is still pending and each contact's first visit applies it (deferred dual, avbd_solve.cu);
-// alphaDual < 0: plain primal sweep.  Returns the number of kernels launched.
-int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
-                  const int* order, int count, float avgVisits, SolveParams prm, float alpha, float alphaDual, float* sums, float* dxOut, Diag* diag);
+// One colour of the large-world primal sweep (flat visit partition, avbd_solve.cu): the colour's visits are [vBegin, vEnd) of
+// `visits`; `vstart` / `order` point at the colour's first body.  `sums` holds 28 floats per body of the WORLD, `carry` 28 floats
+// per chunk of primal_flat_chunk_threads() visits.  alphaDual >= 0: the previous iteration's dual pass (run with that alpha) is
+// still pending and each contact's first visit applies it (deferred dual); < 0: plain primal sweep.  Returns the kernels launched.
+int primal_flat_chunk_threads();
+int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
+                       int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live (densely stored) contacts.
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics
 // (solver.cpp:472-497) are reduced here from the values already in registers instead of by a separate sweep.
@@ -125,9 +126,6 @@ void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, Solv
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
                        Diag* diag, bool contactDiag, bool anyUnvisited);
-// Measurement aid (avbd_debug_time_primal): one colour's visit-sum kernel in mode 0 (product), 1 (memory only), 2 (math only).
-void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, int count, float alpha,
-                              float* sums, int nContacts);
 void launch_dual_user_forces(cudaStream_t s, BodyView b, ForceView fv, SolveParams prm);
 void launch_solve6_batch(cudaStream_t s, const float* lhs36, const float* rhs6, int n, float* out6);
 

@@ -137,9 +137,8 @@ AVBD_HD void accumulate_contact(BodySystem& s, const ContactState& c, const Cont
 // system (tests/test_abi_and_host.py).  The outer products stay per row ON PURPOSE: re-associating them through
 // M = sum_r p_r b_r b_r^T is ~45 instructions cheaper but loses up to the penalty ratio (100x) in relative accuracy when the
 // lever arm is nearly parallel to the stiffest row, and the Schur complement amplifies that by the system's condition.
-AVBD_HD void contact_system(BodySystem& s, const ContactState& c, const ContactEval& e, bool isA, bool gyro, const M3& invIw) {
-    V3 w = isA ? e.wrA : e.wrB;
-    float sg = isA ? 1.0f : -1.0f;
+// `w` = the visiting body's world lever arm, `sg` = +1 when it is body A of the manifold, -1 when it is body B.
+AVBD_HD void contact_system_w(BodySystem& s, const ContactState& c, const ContactEval& e, V3 w, float sg, bool gyro, const M3& invIw) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         V3 Jl = e.basis[r];
@@ -180,6 +179,9 @@ AVBD_HD void contact_system(BodySystem& s, const ContactState& c, const ContactE
             s.aa[0] += g.x * af; s.aa[3] += g.y * af; s.aa[5] += g.z * af;
         }
     }
+}
+AVBD_HD void contact_system(BodySystem& s, const ContactState& c, const ContactEval& e, bool isA, bool gyro, const M3& invIw) {
+    contact_system_w(s, c, e, isA ? e.wrA : e.wrB, isA ? 1.0f : -1.0f, gyro, invIw);
 }
 AVBD_HD void add_system(BodySystem& s, const BodySystem& o) {
     for (int i = 0; i < 3; ++i) { s.rl[i] += o.rl[i]; s.ra[i] += o.ra[i]; }

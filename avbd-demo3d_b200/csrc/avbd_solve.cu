@@ -83,16 +83,89 @@ __device__ __forceinline__ BodyPose load_pose_keep(const BodyPose* p, unsigned l
     BodyPose r; r.pos = ld4_keep(&p->pos, pol); r.rot = ld4_keep(&p->rot, pol); return r;
 }
 
-// One contact visit: computeConstraint for the visiting body, with the pending dual update first when `pending`.
-__device__ __forceinline__ void visit_constraint(float4 pa4, float4 qa4, float4 pb4, float4 qb4, float mu, float alpha, bool pending, float alphaDual,
-                                                 float beta, ContactState& cs, ContactEval& ev) {
-    float sep[3];
-    contact_geometry(xyz(pa4), quat(qa4), xyz(pb4), quat(qb4), cs, ev, sep);
-    if (pending) {
-        contact_limits(pa4.w, pb4.w, mu, alphaDual, sep, cs, ev);
-        dual_contact(cs, ev, beta);
+// ------------------------------------------------------------------ row math of the solver kernels
+// The large-world visit kernel is instruction-issue bound (ncu: ~45 % issue slots busy, DRAM at a third of peak), so the device
+// copy of the row math is written for instruction count.  Same formulas as avbd_rows.cuh (which the host mirror and the host
+// emulation build use, and which the parity tests compare this against), with:
+//   * the contact seen from the VISITING body: geometry arrives as {r_self, r_other, n} (visit_geometry swaps once per step) and
+//     the A/B orientation is one sign, sg — (pA + wA) - (pB + wB) = sg ((pS + wS) - (pO + wO)) exactly, so no operand selects;
+//   * clamps as fminf / fmaxf (one FMNMX each; a NaN operand yields the bound where the reference's ternary clamp passes the
+//     NaN on — NaN states are scrubbed by the pose update either way);
+//   * the dual's |w x b|^2 as |w|^2 - (w . b)^2 for the unit basis vectors b (|b|^2 taken as 1), one division per active row;
+//   * approximate (2 ulp) reciprocal / square root / reciprocal square root instructions, IN THE ROWS ONLY: the block solve and the
+//     pose update keep IEEE division and sqrt — building the whole translation unit with -prec-div=false -prec-sqrt=false
+//     moved the Stack's rest heights by 2e-3 and toppled the Pyramid's apex box (tools/rest_probe.py).
+__device__ __forceinline__ float clampq(float x, float lo, float hi) { return fmaxf(lo, fminf(hi, x)); }
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// contact_basis_unit of avbd_math.cuh (manifold.cpp:39-50 on an already-unit normal)
+__device__ __forceinline__ void basis_fast(V3 n, V3& t1, V3& t2) {
+    bool useX = fabsf(n.x) >= fabsf(n.z);
+    float a = useX ? -n.y : -n.z, b = useX ? n.x : n.y;
+    float l2 = a * a + b * b;
+    float inv = rsqrtf(l2);
+    t1 = useX ? mk3(a * inv, b * inv, 0.0f) : mk3(0.0f, a * inv, b * inv);
+    if (l2 < kVecEps) t1 = mk3(1.0f, 0.0f, 0.0f);
+    t2 = cross(n, t1);
+}
+
+// Manifold::computeConstraint, second half (manifold.cpp:198-241) — contact_limits of avbd_rows.cuh.
+__device__ __forceinline__ void limits_fast(float cap, float mu0, float bias, const float (&sep)[3], ContactState& c, ContactEval& e) {
+    e.C[0] = sep[0] + bias * c.C0n;
+    e.C[1] = sep[1] + bias * c.C0t1;
+    e.C[2] = sep[2] + bias * c.C0t2;
+    e.fmin[0] = -cap; e.fmax[0] = 0.0f;
+    float warmN = fabsf(fminf(c.lam[0], 0.0f));
+    float trialN = fabsf(fminf(c.pen[0] * e.C[0] + c.lam[0], 0.0f));
+    float nmag = fminf(fmaxf(warmN, trialN), cap);
+    float lim = (c.stick ? mu0 : mu0 * kKineticFrictionScale) * nmag;
+    float t2 = c.lam[1] * c.lam[1] + c.lam[2] * c.lam[2];
+    float tm = sqrt_fast(t2);
+    if (tm > lim && tm > 1.0e-8f) { float s = __fdividef(lim, tm); c.lam[1] *= s; c.lam[2] *= s; }
+    e.fmin[1] = -lim; e.fmax[1] = lim; e.fmin[2] = -lim; e.fmax[2] = lim;
+    float slip2 = e.C[1] * e.C[1] + e.C[2] * e.C[2];
+    float tl2 = c.lam[1] * c.lam[1] + c.lam[2] * c.lam[2];
+    c.stick = (slip2 <= kStickThresh * kStickThresh) && (tl2 <= lim * lim + 1.0e-8f);
+}
+// Dual + penalty ramp (solver.cpp:411-430, rowPenaltyGain :94-125) — dual_contact of avbd_rows.cuh.
+__device__ __forceinline__ void dual_fast(ContactState& c, const ContactEval& e, float beta) {
+    float w2 = len2(e.wrA) + len2(e.wrB);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float lu = clampq(c.pen[r] * e.C[r] + c.lam[r], e.fmin[r], e.fmax[r]);
+        bool active = lu > e.fmin[r] && lu < e.fmax[r];
+        c.lam[r] = lu;
+        float da = dot(e.wrA, e.basis[r]), db = dot(e.wrB, e.basis[r]);
+        float aw = fmaxf(w2 - (da * da + db * db), 0.0f);
+        float br = beta * __fdividef(2.0f + kAngularBetaScale * aw, 2.0f + aw);
+        float grown = fminf(c.pen[r] + br * fabsf(e.C[r]), kManifoldPenaltyCap);
+        c.pen[r] = active ? grown : c.pen[r];
     }
-    contact_limits(pa4.w, pb4.w, mu, alpha, sep, cs, ev);
+}
+// One contact visit in the visiting body's frame: computeConstraint (with the pending dual update first), then the 3 rows'
+// contribution to the body's 6x6 system.  `sp,sq` / `op,oq` = self / other pose, g0 g1 g2 = {r_self,C0n} {r_other,C0t.x} {n,C0t.y}.
+// Every solver kernel (flat visit kernel, cluster loop, dual pass) evaluates rows through these, so the deferred and the
+// stand-alone dual agree to FMA-contraction rounding: `stick` is decided by comparing a just-clamped |lambda_t|^2 with lim^2, i.e.
+// by rounding, and a flipped `stick` changes friction by 10 % — two row-math variants would drift apart within a few steps.
+__device__ __forceinline__ float rows_geometry(float4 sp, float4 sq, float4 op, float4 oq, float sg, const ContactState& cs, ContactEval& ev, float (&sep)[3]) {
+    ev.basis[0] = cs.n;
+    basis_fast(cs.n, ev.basis[1], ev.basis[2]);
+    ev.wrA = qrot(quat(sq), cs.rA);                 // self
+    ev.wrB = qrot(quat(oq), cs.rB);                 // other
+    V3 d = (xyz(sp) + ev.wrA) - (xyz(op) + ev.wrB);
+    sep[0] = sg * dot(d, ev.basis[0]) - kNormalContactMargin; sep[1] = sg * dot(d, ev.basis[1]); sep[2] = sg * dot(d, ev.basis[2]);
+    float ims = sp.w + op.w;
+    return kNormalForceCap * ((ims > 1.0e-6f) ? __fdividef(1.0f, ims) : 1.0f);       // normal force cap (manifold.cpp:199-203)
+}
+__device__ __forceinline__ void visit_rows(float4 sp, float4 sq, float4 op, float4 oq, float sg, float mu, float alpha, bool pending, float alphaDual,
+                                           float beta, bool gyro, const M3& invIw, ContactState& cs, BodySystem& sys) {
+    ContactEval ev; float sep[3];
+    float cap = rows_geometry(sp, sq, op, oq, sg, cs, ev, sep);
+    if (pending) {
+        limits_fast(cap, mu, fminf(fmaxf(1.0f - alphaDual, 0.0f), 1.0f), sep, cs, ev);
+        dual_fast(cs, ev, beta);
+    }
+    limits_fast(cap, mu, fminf(fmaxf(1.0f - alpha, 0.0f), 1.0f), sep, cs, ev);
+    contact_system_w(sys, cs, ev, ev.wrA, sg, gyro, invIw);
 }
 
 // Loads of data another CTA may have written earlier in the SAME launch (persistent loop): bypass L1.
@@ -172,14 +245,9 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
             int lo = 0, hi = nb;                                  // slot: vs[lo] <= v < vs[lo + 1]
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.vs[mid] <= v) lo = mid; else hi = mid; }
             float4 sp = sm.pos[lo], sr = sm.rot[lo];
-            ContactState cs = unpack_contact(a4, b4, n4, l4, p4);
-            ContactEval ev;
-            float mu = __int_as_float(e.w);
             bool pending = alphaDual >= 0.0f && (e.z & 4) != 0;
-            {
-                float4 pa4 = isA ? sp : po.pos, qa4 = isA ? sr : po.rot, pb4 = isA ? po.pos : sp, qb4 = isA ? po.rot : sr;
-                visit_constraint(pa4, qa4, pb4, qb4, mu, alpha, pending, alphaDual, prm.beta, cs, ev);
-            }
+            ContactState cs = unpack_contact(isA ? a4 : b4, isA ? b4 : a4, n4, l4, p4);     // rA = r_self, rB = r_other (visit_rows' frame)
+            cs.C0n = a4.w; cs.C0t1 = b4.w;
             bool gyro = sm.inert[lo].w != 0.0f;
             M3 invIw;
             if (gyro) {
@@ -189,7 +257,7 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
                 invIw = m3(zero3(), zero3(), zero3());
             }
             BodySystem sys;
-            contact_system(sys, cs, ev, isA, gyro, invIw);
+            visit_rows(sp, sr, po.pos, po.rot, isA ? 1.0f : -1.0f, __int_as_float(e.w), alpha, pending, alphaDual, prm.beta, gyro, invIw, cs, sys);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
             if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); ms.lp[ci] = q; }
@@ -242,126 +310,144 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
     }
 }
 
-template <int BPB, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) primal_visits(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits,
-                                                                ManifoldSet ms, ForceView fv, const int* __restrict__ order, int count,
-                                                                SolveParams prm, float alpha, float alphaDual, float* dxOut, Diag* diag) {
-    __shared__ PrimalSmem<BPB> sm;
-    primal_tile_visits<BPB, false>(b, vstart, visits, ms, fv, order, count, blockIdx.x, prm, alpha, alphaDual, dxOut, diag, sm);
-}
-
-// ------------------------------------------------------------------ primal, split (visit sums -> block solve)
-// Keeping the 6x6 solve inside the visit kernel leaves 1/4 .. 1/8 of a block's threads running a long serial chain while
-// the block pins its registers and shared memory.  The large-world path therefore runs two lane-dense kernels per colour:
-//   primal_visit_sums  one visit per thread -> per-body sums of the 27 row contributions (shared-memory transpose +
-//                      in-order reduction), written to `sums` in colour order (28 floats per body)
-//   primal_solve       one body per thread: inertial terms + sums -> Schur solve -> pose update
-// Visit entry (built with the graph): {contact id, other body, (self body << 3) | first-visit << 2 | anisotropic-inertia << 1 | body-is-A, mu}.
-template <int BPB>
-struct VisitSmem {
-    float c[27][kThreads + 1];
-    int vs[BPB + 1];
-};
 constexpr int kSumStride = 28;
 
-// MODE 0 is the product.  MODE 1 / 2 are measurement aids behind avbd_debug_time_primal (never on the step path): 1 keeps the
-// memory accesses and drops the row math (the kernel's memory-system floor), 2 keeps the math and makes every index
-// sequential (its instruction-issue floor); neither writes solver state.
-template <int BPB, int MINB, int MODE = 0>
-__global__ void __launch_bounds__(kThreads, MINB) primal_visit_sums(BodyView b, const int* __restrict__ vstart, const int4* __restrict__ visits, VisitGeom vg,
-                                                                    ManifoldSet ms, int count, float alpha, float alphaDual, float beta, float* __restrict__ sums,
-                                                                    int nContacts = 0) {
-    constexpr int L = kThreads / BPB;
-    constexpr int CPL = (27 + L - 1) / L;
-    __shared__ VisitSmem<BPB> sm;
-    const int t = threadIdx.x;
-    const int k0 = blockIdx.x * BPB;
-    const int nb = (count - k0) < BPB ? (count - k0) : BPB;
-    if (t <= nb) sm.vs[t] = vstart[k0 + t];
-    const int v0 = vstart[k0], v1 = vstart[k0 + nb];
-    float acc[CPL];
-#pragma unroll
-    for (int m = 0; m < CPL; ++m) acc[m] = 0.0f;
-    const int rs = t / L, rj = t % L;
+// ------------------------------------------------------------------ primal, flat visit partition (the default large-world path)
+// Giving each block a tile of BODIES makes it load where its visits start (one DRAM round trip), then the visit entries (a
+// second), then what they point at (a third), and leaves ~4 % of the lanes idle because a tile's visits rarely fill the block.
+// This kernel partitions the colour's VISITS instead: chunk c is visits [vBegin + c*T, vBegin + (c+1)*T), every lane busy,
+// start known from the block index.  Blocks are persistent (grid = a few per SM, chunks round-robin) and load the NEXT chunk's
+// visit entry before working on the current one, so only the gathers (poses, lambda / penalty) remain on the critical path.
+//   phase 0  segment heads: lane v starts a segment when visit v-1 belongs to another body (entries carry the visiting body);
+//            ballot + per-warp counts -> compact list of the chunk's segments (start lane, body) in shared memory
+//   phase 1  thread t takes visit base+t: computeConstraint (+ pending dual) + 3 rows -> 27 partial sums, transposed into
+//            shared memory (row stride T+1: conflict free)
+//   phase 2  9 lanes per segment add the segment's run of partial sums in visit order, 3 components each
+//   output   a segment that STARTS in the chunk writes sums[body]; a segment continuing from the previous chunk (a body whose
+//            visits straddle a chunk boundary) writes carry[chunk] instead, and primal_solve_flat adds main + carries in
+//            chunk order — deterministic, no atomics, nothing to zero.
+constexpr int kFlatLanes = 9;                 // lanes per segment in phase 2 (3 of the 27 components each)
+template <int T>
+struct FlatSmem {
+    float c[27][T + 1];
+    int segStart[T + 1];
+    int segBody[T];
+    int warpCnt[T / 32];
+};
+
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, int vBegin, int vEnd,
+                                                             float alpha, float alphaDual, float beta, float* __restrict__ sums, float* __restrict__ carry) {
+    __shared__ FlatSmem<T> sm;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int nChunks = (vEnd - vBegin + T - 1) / T;
     const unsigned long long keep = l2_keep_policy();
-    for (int base = v0; base < v1; base += kThreads) {
-        int v = base + t;
-        if (v < v1) {
-            int4 e = __ldcs(visits + v);
-            int ci = e.x, self = e.z >> 3; bool isA = (e.z & 1) != 0, gyro = (e.z & 2) != 0, pending = alphaDual >= 0.0f && (e.z & 4) != 0;
-            if (MODE == 2) { ci = v % nContacts; self = v % b.n; e.y = (v + 1) % b.n; }
-            BodyPose ps = load_pose_keep(b.pose + self, keep);
-            BodyPose po = load_pose_keep(b.pose + e.y, keep);
-            // the visit entry and its copy of the contact geometry stream past once per sweep, fully coalesced: evict-first, so
-            // they do not push the poses and the lambda / penalty records (the gathered, re-used data) out of L2
-            float4 a4 = __ldcs(vg.a + v), b4 = __ldcs(vg.b + v), n4 = __ldcs(vg.n + v);
-            ContactLP* lp = ms.lp + ci;
-            float4 l4 = lp->l, p4 = lp->p;
-            V3 pos = xyz(ps.pos); Q4 rot = quat(ps.rot);
-            ContactState cs = unpack_contact(a4, b4, n4, l4, p4);
-            ContactEval ev;
-            float mu = __int_as_float(e.w);
-            if (MODE == 1) {
-                float q = ps.pos.x + ps.rot.y + po.pos.z + po.rot.w + a4.x + b4.y + n4.z + l4.w + p4.x + mu;
+    int chunk = blockIdx.x;
+    if (chunk >= nChunks) return;
+    const int4 none = make_int4(0, 0, -8, 0);                        // body -1
+    int4 eNext = none; int prevNext = -8;
+    {
+        int v = vBegin + chunk * T + t;
+        if (v < vEnd) eNext = __ldcs(visits + v);
+        if (lane == 0 && v > vBegin && v < vEnd) prevNext = __ldg(&visits[v - 1].z);
+    }
+    for (; chunk < nChunks; chunk += gridDim.x) {
+        const int base = vBegin + chunk * T;
+        const int v = base + t;
+        const int4 e = eNext; const int prevZ = prevNext;
+        {   // prefetch the next chunk's entries: their latency hides behind this chunk's work
+            int vn = v + gridDim.x * T;
+            eNext = none; prevNext = -8;
+            if (vn < vEnd) { eNext = __ldcs(visits + vn); if (lane == 0) prevNext = __ldg(&visits[vn - 1].z); }
+        }
+        const bool live = v < vEnd;
+        const int self = e.z >> 3;
+        // ---- issue the gathers first, then build the segment list while they are in flight
+        BodyPose ps, po; float4 a4, b4, n4, l4, p4; ContactLP* lp = ms.lp + e.x;
+        if (live) {
+            ps = load_pose_keep(b.pose + self, keep);
+            po = load_pose_keep(b.pose + e.y, keep);
+            a4 = __ldcs(vg.a + v); b4 = __ldcs(vg.b + v); n4 = __ldcs(vg.n + v);
+            l4 = lp->l; p4 = lp->p;
+        }
+        int prevSelf = __shfl_up_sync(0xffffffffu, self, 1);
+        if (lane == 0) prevSelf = prevZ >> 3;                         // -1 at the colour's first visit
+        const bool head = live && (prevSelf != self || t == 0);       // lane 0 of the chunk always opens a segment (maybe a continuation)
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) sm.warpCnt[warp] = __popc(heads);
+        __syncthreads();
+        int segBase = 0, nSeg = 0;
 #pragma unroll
-                for (int k = 0; k < 27; ++k) sm.c[k][t] = q;
-            } else {
-            {   // one call with the operands swapped by selects: an if/else duplicates the code and mixed warps run both arms
-                float4 pa4 = isA ? ps.pos : po.pos, qa4 = isA ? ps.rot : po.rot, pb4 = isA ? po.pos : ps.pos, qb4 = isA ? po.rot : ps.rot;
-                visit_constraint(pa4, qa4, pb4, qb4, mu, alpha, pending, alphaDual, beta, cs, ev);
-            }
+        for (int wq = 0; wq < T / 32; ++wq) { int cnt = sm.warpCnt[wq]; if (wq < warp) segBase += cnt; nSeg += cnt; }
+        if (head) {
+            int sidx = segBase + __popc(heads & ((1u << lane) - 1u));
+            sm.segStart[sidx] = t;
+            sm.segBody[sidx] = (t == 0 && prevSelf == self) ? ~self : self;      // complemented: continues the previous chunk's last segment
+        }
+        if (t == 0) { int liveCount = vEnd - base; sm.segStart[nSeg] = liveCount < T ? liveCount : T; }
+        // ---- phase 1
+        if (live) {
+            bool gyro = (e.z & 2) != 0, pending = alphaDual >= 0.0f && (e.z & 4) != 0;
+            float sg = (e.z & 1) ? 1.0f : -1.0f;                       // visiting body is A / B of the manifold
+            ContactState cs = unpack_contact(a4, b4, n4, l4, p4);       // rA = r_self, rB = r_other here
             M3 invIw = m3(zero3(), zero3(), zero3());
             if (gyro) {   // anisotropic inertia only: for R diag(c) R^T = c Id the term Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero
                 V3 I = xyz(b.aux[self].inert);
-                invIw = rot_diag(qmat(rot), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
+                invIw = rot_diag(qmat(quat(ps.rot)), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
             }
             BodySystem sys;
-            contact_system(sys, cs, ev, isA, gyro, invIw);
+            visit_rows(ps.pos, ps.rot, po.pos, po.rot, sg, __int_as_float(e.w), alpha, pending, alphaDual, beta, gyro, invIw, cs, sys);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
-            if (MODE == 0) {
-                if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); *lp = q; }
-                else if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) lp->l = nl;
-            }
+            if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); *lp = q; }
+            else if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) lp->l = nl;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
 #pragma unroll
             for (int k = 0; k < 6; ++k) { sm.c[6 + k][t] = sys.ll[k]; sm.c[21 + k][t] = sys.aa[k]; }
 #pragma unroll
             for (int k = 0; k < 9; ++k) sm.c[12 + k][t] = sys.la[k];
-            }
         }
         __syncthreads();
-        if (rs < nb) {
-            int rlo = sm.vs[rs], rhi = sm.vs[rs + 1];
-            int a = (rlo > base ? rlo : base) - base;
-            int z = (rhi < base + kThreads ? rhi : base + kThreads) - base;
-            for (int lv = a; lv < z; ++lv) {
-#pragma unroll
-                for (int m = 0; m < CPL; ++m) { int k = rj + m * L; if (k < 27) acc[m] += sm.c[k][lv]; }
-            }
+        // ---- phase 2
+        for (int wi = t; wi < nSeg * kFlatLanes; wi += T) {
+            int sg = wi / kFlatLanes, j = wi - sg * kFlatLanes;
+            int a = sm.segStart[sg], z = sm.segStart[sg + 1];
+            float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
+            for (int lv = a; lv < z; ++lv) { x0 += sm.c[j][lv]; x1 += sm.c[j + 9][lv]; x2 += sm.c[j + 18][lv]; }
+            int body = sm.segBody[sg];
+            float* o = body >= 0 ? sums + (size_t)body * kSumStride : carry + (size_t)chunk * kSumStride;
+            o[j] = x0; o[j + 9] = x1; o[j + 18] = x2;
         }
-        if (base + kThreads < v1) __syncthreads();
-    }
-    if (rs < nb) {
-        float* o = sums + (size_t)(k0 + rs) * kSumStride;
-#pragma unroll
-        for (int m = 0; m < CPL; ++m) { int k = rj + m * L; if (k < 27) o[k] = acc[m]; }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(kThreads) primal_solve(BodyView b, ForceView fv, const int* __restrict__ order, int count,
-                                                         const float* __restrict__ sums, SolveParams prm, float* dxOut, Diag* diag) {
+// One body per thread: main sums + the carries of every later chunk its visits reach, inertial terms, Schur solve, pose update.
+__global__ void __launch_bounds__(kThreads) primal_solve_flat(BodyView b, ForceView fv, const int* __restrict__ order, const int* __restrict__ vstart, int count,
+                                                              int vBegin, int chunkT, const float* __restrict__ sums, const float* __restrict__ carry,
+                                                              SolveParams prm, float* dxOut, Diag* diag) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     int i = order[k];
+    int vs = vstart[k], ve = vstart[k + 1];
     const unsigned long long keep = l2_keep_policy();
     BodyPose self = load_pose_keep(b.pose + i, keep);
     BodyAux aux = b.aux[i];
-    const float4* s4 = reinterpret_cast<const float4*>(sums + (size_t)k * kSumStride);
     float o[kSumStride];
 #pragma unroll
-    for (int q = 0; q < kSumStride / 4; ++q) { float4 x = s4[q]; o[4 * q] = x.x; o[4 * q + 1] = x.y; o[4 * q + 2] = x.z; o[4 * q + 3] = x.w; }
+    for (int q = 0; q < kSumStride; ++q) o[q] = 0.0f;
+    if (ve > vs) {
+        const float4* s4 = reinterpret_cast<const float4*>(sums + (size_t)i * kSumStride);
+#pragma unroll
+        for (int q = 0; q < kSumStride / 4; ++q) { float4 x = __ldcs(s4 + q); o[4 * q] = x.x; o[4 * q + 1] = x.y; o[4 * q + 2] = x.z; o[4 * q + 3] = x.w; }
+        int c0 = (vs - vBegin) / chunkT, c1 = (ve - 1 - vBegin) / chunkT;
+        for (int c = c0 + 1; c <= c1; ++c) {
+            const float4* c4 = reinterpret_cast<const float4*>(carry + (size_t)c * kSumStride);
+#pragma unroll
+            for (int q = 0; q < kSumStride / 4; ++q) { float4 x = c4[q]; o[4 * q] += x.x; o[4 * q + 1] += x.y; o[4 * q + 2] += x.z; o[4 * q + 3] += x.w; }
+        }
+    }
     V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
     BodySystem own; M3 invIw;
     body_self_system(pos, rot, aux, prm.dt, own, invIw);
@@ -401,10 +487,11 @@ __device__ __forceinline__ DualOut dual_one(const BodyView& b, const ManifoldSet
     int reps = 1;
     if (unvisitedReps > 0) reps = o.visits == 0 ? unvisitedReps : (onlyUnvisited ? 0 : 1);
     float sep[3];
-    contact_geometry(xyz(pa.pos), quat(pa.rot), xyz(pb.pos), quat(pb.rot), cs, ev, sep);
+    float cap = rows_geometry(pa.pos, pa.rot, pb.pos, pb.rot, 1.0f, cs, ev, sep);
+    float bias = fminf(fmaxf(1.0f - alpha, 0.0f), 1.0f);
     for (int r = 0; r < reps; ++r) {
-        contact_limits(pa.pos.w, pb.pos.w, __int_as_float(h.w), alpha, sep, cs, ev);
-        dual_contact(cs, ev, prm.beta);
+        limits_fast(cap, __int_as_float(h.w), bias, sep, cs, ev);
+        dual_fast(cs, ev, prm.beta);
     }
     if (reps > 0) { ContactLP q; q.l = pack_lambda(cs); q.p = pack_penalty(cs); ms.lp[ci] = q; }
     o.sepn = dot((xyz(pa.pos) + ev.wrA) - (xyz(pb.pos) + ev.wrB), cs.n);
@@ -541,59 +628,40 @@ __global__ void solve6_batch(const float* lhs36, const float* rhs6, int n, float
 // ------------------------------------------------------------------ launchers (declared in avbd_launch.h)
 static inline int blocks_of(long long n, int per) { long long b = (n + per - 1) / per; return (int)(b < 1 ? 1 : b); }
 
-template <int BPB, int MINB>
-static void launch_primal_visits(cudaStream_t s, BodyView b, const int* vstart, const int4* visits, ManifoldSet ms, ForceView fv,
-                                 const int* order, int count, SolveParams prm, float alpha, float alphaDual, float* dxOut, Diag* diag) {
-    primal_visits<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, ms, fv, order, count, prm, alpha, alphaDual, dxOut, diag);
-}
-
-template <int BPB, int MINB>
-static void launch_split(cudaStream_t s, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
-                         const int* order, int count, SolveParams prm, float alpha, float alphaDual, float* sums, float* dxOut, Diag* diag) {
-    primal_visit_sums<BPB, MINB><<<blocks_of(count, BPB), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, alphaDual, prm.beta, sums);
-    primal_solve<<<blocks_of(count, kThreads), kThreads, 0, s>>>(b, fv, order, count, sums, prm, dxOut, diag);
-}
-
-// Default: the split path (visit sums + block solve), bodies per tile chosen so a tile's visits fill the block once.
-// AVBD_PRIMAL_VARIANT (tuning aid): "s<BPB>[m<MINB>]" split path with a forced tile size (s16 s28 s64; m3 m4);
-// "v<BPB>[m<MINB>]" the single-kernel visit-parallel tile.  Returns the number of kernels launched.
-int launch_primal(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
-                  const int* order, int count, float avgVisits, SolveParams prm, float alpha, float alphaDual, float* sums, float* dxOut, Diag* diag) {
-    static int variant = 0, minb = 3; static char kind = 's';
-    static bool init = [] {
-        const char* e = getenv("AVBD_PRIMAL_VARIANT");
-        if (!e) return true;
-        if (e[0] == 'v' || e[0] == 's') {
-            kind = e[0];
-            variant = atoi(e + 1);
-            for (const char* p = e; *p; ++p) if (*p == 'm') minb = atoi(p + 1);
-        }
-        return true;
-    }();
-    (void)init;
-#define AVBD_VV(B, M) launch_primal_visits<B, M>(s, b, visitStart, visits, ms, fv, order, count, prm, alpha, alphaDual, dxOut, diag)
-#define AVBD_SV(B, M) launch_split<B, M>(s, b, visitStart, visits, vg, ms, fv, order, count, prm, alpha, alphaDual, sums, dxOut, diag)
-    int bpb = variant > 0 ? variant : (avgVisits <= 3.7f ? 64 : (avgVisits <= 9.0f ? 28 : (avgVisits <= 16.0f ? 16 : 8)));
-    if (kind == 'v') {
-        if (bpb >= 64) { if (minb == 4) AVBD_VV(64, 4); else AVBD_VV(64, 3); }
-        else if (bpb >= 28) { if (minb == 4) AVBD_VV(28, 4); else AVBD_VV(28, 3); }
-        else if (bpb >= 16) AVBD_VV(16, 3); else AVBD_VV(8, 3);
-        return 1;
+template <int T, int MINB>
+static void launch_flat(cudaStream_t s, int nSm, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
+                        int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
+    int nChunks = (vEnd - vBegin + T - 1) / T;
+    if (nChunks > 0) {
+        int grid = nChunks < nSm * MINB ? nChunks : nSm * MINB;
+        primal_visit_flat<T, MINB><<<grid, T, 0, s>>>(b, visits, vg, ms, vBegin, vEnd, alpha, alphaDual, prm.beta, sums, carry);
     }
-    if (bpb >= 64) { if (minb == 4) AVBD_SV(64, 4); else AVBD_SV(64, 3); }
-    else if (bpb >= 28) { if (minb == 4) AVBD_SV(28, 4); else AVBD_SV(28, 3); }
-    else if (bpb >= 16) { if (minb == 4) AVBD_SV(16, 4); else AVBD_SV(16, 3); }
-    else AVBD_SV(8, 3);
-    return 2;
-#undef AVBD_VV
-#undef AVBD_SV
+    primal_solve_flat<<<blocks_of(count, kThreads), kThreads, 0, s>>>(b, fv, order, vstart, count, vBegin, T, sums, carry, prm, dxOut, diag);
 }
-void launch_primal_experiment(cudaStream_t s, int mode, BodyView b, const int* vstart, const int4* visits, VisitGeom vg, ManifoldSet ms, int count, float alpha,
-                              float* sums, int nContacts) {
-    if (mode == 1) primal_visit_sums<28, 3, 1><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, -1.0f, 0.0f, sums, nContacts);
-    else if (mode == 2) primal_visit_sums<28, 3, 2><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, -1.0f, 0.0f, sums, nContacts);
-    else primal_visit_sums<28, 3, 0><<<blocks_of(count, 28), kThreads, 0, s>>>(b, vstart, visits, vg, ms, count, alpha, -1.0f, 0.0f, sums, nContacts);
+// The default large-world sweep of one colour: flat visit partition + block solve.  `sums`: 28 floats per BODY of the world;
+// `carry`: 28 floats per chunk (primal_flat_chunks).  AVBD_FLAT (tuning aid) = "<threads per block><blocks per SM>": 1285 (default; 96 registers,
+// 20 warps / SM — measured best on the 1M-box grid: 5.59 ms of sweeps per step against 5.66 for 1284, 5.79 for 2562 and 6.7 - 7.0 for
+// the 80-register builds 1286 / 2563, which spill) 1284 1286 2562 2563.
+int primal_flat_chunk_threads() {
+    static int t = [] { const char* e = getenv("AVBD_FLAT"); int v = e ? atoi(e) : 1285; return v / 10 == 128 ? 128 : 256; }();
+    return t;
 }
+int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
+                       int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
+    static int nSm = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+    static int cfg = [] { const char* e = getenv("AVBD_FLAT"); return e ? atoi(e) : 1285; }();
+#define AVBD_FL(T, M) launch_flat<T, M>(s, nSm, b, visits, vg, ms, fv, order, vstart, count, vBegin, vEnd, prm, alpha, alphaDual, sums, carry, dxOut, diag)
+    switch (cfg) {
+        case 2563: AVBD_FL(256, 3); break;
+        case 2562: AVBD_FL(256, 2); break;
+        case 1286: AVBD_FL(128, 6); break;
+        case 1284: AVBD_FL(128, 4); break;
+        default:   AVBD_FL(128, 5); break;
+    }
+#undef AVBD_FL
+    return vEnd > vBegin ? 2 : 1;
+}
+
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
                        Diag* diag, bool contactDiag, bool anyUnvisited) {

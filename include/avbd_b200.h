@@ -136,11 +136,6 @@ int  avbd_stage_dual(avbd_world* w, float alpha);
 /* solver.cpp:434-497 */
 int  avbd_stage_velocity(avbd_world* w);
 
-/* Measurement aid, not part of the step path: average device ms of one sweep of the primal visit-sum kernels over all colours
- * of the current graph; mode 0 = the product kernel, 1 = its memory accesses without the row math, 2 = its math on sequential
- * indices.  Modes 1 and 2 write no solver state. */
-int  avbd_debug_time_primal(avbd_world* w, int mode, int reps, float* ms);
-
 /* ---- stand-alone kernels on caller data ------------------------------------------------------- */
 /* Manifold::collide (collision.cpp:420) on n pairs; a10/b10 = size3 pos3 quat4; out: counts[n], feats[4n], geom[36n] (rA3 rB3 n3 per contact). */
 int  avbd_collide_pairs(int device, int n, const float* a10, const float* b10, int* counts, int* feats4, float* geom36);

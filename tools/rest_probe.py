@@ -1,7 +1,7 @@
 """Rest-height probe (run under gpurun): Stack / Pyramid rest heights vs the oracle for the cluster loop and the launch path."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tools/ -> repo root
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import avbd_demo3d_b200 as avbd
 from test_gpu_scenes import run_scene, oracle_rest
