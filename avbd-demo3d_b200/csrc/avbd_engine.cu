@@ -109,7 +109,7 @@ struct avbd_world {
     // counters / diagnostics
     Counters* dCnt = nullptr; Counters* hCnt = nullptr;
     DevBuf<Diag> dDiag; Diag* hDiag = nullptr; size_t hDiagCap = 0;
-    DevBuf<float> dx, sums, carry; DevBuf<int> colVisit;
+    DevBuf<float> dx, sums, carry; DevBuf<int> colVisit, kOf;     // kOf[body] = position in colOrder
     DevBuf<char> temp;
 
     // per-kernel profiling (avbd_set_profiling): events around every primal sweep and dual pass
@@ -485,9 +485,10 @@ int run_colour(avbd_world* w) {
     visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
     w->launches += 2;
     // first visit of every colour (the flat primal partitions a colour's visits, not its bodies)
-    TRY(w->colVisit.ensure(65, false, s));
+    TRY(w->colVisit.ensure(65, false, s)); TRY(w->kOf.ensure(n, false, s));
     colour_visit_bounds<<<1, 64, 0, s>>>(w->colRange.p, w->nColours, w->visitStart.p, w->nDyn, w->colVisit.p);
-    w->launches++;
+    invert_order<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->kOf.p);
+    w->launches += 2;
     CK(cudaMemcpyAsync(w->hColVisit, w->colVisit.p, sizeof(int) * 65, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     w->graphValid = true;
@@ -502,7 +503,7 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
     int chunkT = primal_flat_chunk_threads();
-    TRY(w->sums.ensure((size_t)std::max(1, w->n) * 28, false, s));
+    TRY(w->sums.ensure((size_t)std::max(1, w->nDyn) * 28, false, s));
     TRY(w->carry.ensure(((size_t)std::max(1, 2 * w->nContacts) / chunkT + 2) * 28, false, s));
     if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
         size_t cap = w->visits.cap;
@@ -514,7 +515,7 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f
     for (int c = 0; c < w->nColours; ++c) {
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
-        w->launches += launch_primal_flat(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->colOrder.p + first, w->visitStart.p + first, count,
+        w->launches += launch_primal_flat(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->colOrder.p, w->visitStart.p, w->kOf.p, first, count,
                                           w->hColVisit[c], w->hColVisit[c + 1], w->prm, alpha, alphaDual, w->sums.p, w->carry.p, dxDev, w->dDiag.p);
     }
     CK(cudaGetLastError());
@@ -679,7 +680,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
-    w->dDiag.release(); w->dx.release(); w->sums.release(); w->carry.release(); w->colVisit.release(); w->temp.release(); w->stateDev.release();
+    w->dDiag.release(); w->dx.release(); w->sums.release(); w->carry.release(); w->colVisit.release(); w->kOf.release(); w->temp.release(); w->stateDev.release();
     w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stLP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);

@@ -161,6 +161,11 @@ __global__ void colour_visit_bounds(const int2* colourRange, int nColours, const
     if (c == 0) out[64] = visitStart[nDyn];
 }
 
+__global__ void invert_order(const int* order, int n, int* positionOf) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) positionOf[order[k]] = k;
+}
+
 // ------------------------------------------------------------------ predict / warm-start decay of user forces
 __global__ void predict_bodies(BodyView b, SolveParams prm, Diag* diag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

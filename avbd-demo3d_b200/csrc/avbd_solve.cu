@@ -141,6 +141,49 @@ __device__ __forceinline__ void dual_fast(ContactState& c, const ContactEval& e,
         c.pen[r] = active ? grown : c.pen[r];
     }
 }
+// contact_system_w of avbd_rows.cuh without the "does the row add stiffness" test (solver.cpp:381): a manifold row's penalty is
+// always in [PENALTY_MIN, MANIFOLD_PENALTY_CAP] on the device (set at creation, clamped by the warm-start decay and by the ramp,
+// whose fminf maps a NaN to the cap).
+__device__ __forceinline__ void system_fast(BodySystem& s, const ContactState& c, const ContactEval& e, V3 w, float sg, bool gyro, const M3& invIw) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        V3 Jl = e.basis[r];
+        V3 Ja = cross(w, e.basis[r]);
+        float f0 = clampq(c.pen[r] * e.C[r] + c.lam[r], e.fmin[r], e.fmax[r]);
+        float f = f0 * sg;
+        float pen = c.pen[r];
+        float lp[3] = {Jl.x * pen, Jl.y * pen, Jl.z * pen}, ap[3] = {Ja.x * pen, Ja.y * pen, Ja.z * pen};
+        float jl[3] = {Jl.x, Jl.y, Jl.z}, ja[3] = {Ja.x, Ja.y, Ja.z};
+        if (r == 0) {
+            s.rl[0] = Jl.x * f; s.rl[1] = Jl.y * f; s.rl[2] = Jl.z * f;
+            s.ra[0] = Ja.x * f; s.ra[1] = Ja.y * f; s.ra[2] = Ja.z * f;
+            s.ll[0] = lp[0] * jl[0]; s.ll[1] = lp[1] * jl[0]; s.ll[2] = lp[2] * jl[0];
+            s.ll[3] = lp[1] * jl[1]; s.ll[4] = lp[2] * jl[1]; s.ll[5] = lp[2] * jl[2];
+            s.aa[0] = ap[0] * ja[0]; s.aa[1] = ap[1] * ja[0]; s.aa[2] = ap[2] * ja[0];
+            s.aa[3] = ap[1] * ja[1]; s.aa[4] = ap[2] * ja[1]; s.aa[5] = ap[2] * ja[2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s.la[i * 3 + k] = lp[i] * ja[k];
+        } else {
+            s.rl[0] += Jl.x * f; s.rl[1] += Jl.y * f; s.rl[2] += Jl.z * f;
+            s.ra[0] += Ja.x * f; s.ra[1] += Ja.y * f; s.ra[2] += Ja.z * f;
+            s.ll[0] += lp[0] * jl[0]; s.ll[1] += lp[1] * jl[0]; s.ll[2] += lp[2] * jl[0];
+            s.ll[3] += lp[1] * jl[1]; s.ll[4] += lp[2] * jl[1]; s.ll[5] += lp[2] * jl[2];
+            s.aa[0] += ap[0] * ja[0]; s.aa[1] += ap[1] * ja[0]; s.aa[2] += ap[2] * ja[0];
+            s.aa[3] += ap[1] * ja[1]; s.aa[4] += ap[2] * ja[1]; s.aa[5] += ap[2] * ja[2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s.la[i * 3 + k] += lp[i] * ja[k];
+        }
+        if (gyro) {                                              // solver.cpp:393-397; exactly zero for isotropic inertia
+            V3 g = vabs(cross(Ja, mv(invIw, Ja)));
+            float af = fabsf(f0);
+            s.aa[0] += g.x * af; s.aa[3] += g.y * af; s.aa[5] += g.z * af;
+        }
+    }
+}
 // One contact visit in the visiting body's frame: computeConstraint (with the pending dual update first), then the 3 rows'
 // contribution to the body's 6x6 system.  `sp,sq` / `op,oq` = self / other pose, g0 g1 g2 = {r_self,C0n} {r_other,C0t.x} {n,C0t.y}.
 // Every solver kernel (flat visit kernel, cluster loop, dual pass) evaluates rows through these, so the deferred and the
@@ -165,7 +208,7 @@ __device__ __forceinline__ void visit_rows(float4 sp, float4 sq, float4 op, floa
         dual_fast(cs, ev, beta);
     }
     limits_fast(cap, mu, fminf(fmaxf(1.0f - alpha, 0.0f), 1.0f), sep, cs, ev);
-    contact_system_w(sys, cs, ev, ev.wrA, sg, gyro, invIw);
+    system_fast(sys, cs, ev, ev.wrA, sg, gyro, invIw);
 }
 
 // Loads of data another CTA may have written earlier in the SAME launch (persistent loop): bypass L1.
@@ -320,16 +363,16 @@ constexpr int kSumStride = 28;
 // visit entry before working on the current one, so only the gathers (poses, lambda / penalty) remain on the critical path.
 //   phase 0  segment heads: lane v starts a segment when visit v-1 belongs to another body (entries carry the visiting body);
 //            ballot + per-warp counts -> compact list of the chunk's segments (start lane, body) in shared memory
-//   phase 1  thread t takes visit base+t: computeConstraint (+ pending dual) + 3 rows -> 27 partial sums, transposed into
-//            shared memory (row stride T+1: conflict free)
-//   phase 2  9 lanes per segment add the segment's run of partial sums in visit order, 3 components each
-//   output   a segment that STARTS in the chunk writes sums[body]; a segment continuing from the previous chunk (a body whose
+//   phase 1  thread t takes visit base+t: computeConstraint (+ pending dual) + 3 rows -> 27 partial sums, one 112-byte row of
+//            shared memory per visit (7 x STS.128)
+//   phase 2  7 lanes per segment add the segment's run of rows in visit order, one float4 column each (LDS.128, 4 in flight)
+//   output   a segment that STARTS in the chunk writes sums[k], k = the body's position in the colour order; a segment continuing from the previous chunk (a body whose
 //            visits straddle a chunk boundary) writes carry[chunk] instead, and primal_solve_flat adds main + carries in
 //            chunk order — deterministic, no atomics, nothing to zero.
-constexpr int kFlatLanes = 9;                 // lanes per segment in phase 2 (3 of the 27 components each)
+constexpr int kFlatLanes = 7;                 // lanes per segment in phase 2 (one float4 = 4 of the 27(+1) components each)
 template <int T>
 struct FlatSmem {
-    float c[27][T + 1];
+    float4 c[T][7];      // one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad — 128-bit stores / loads, row stride 28 words: conflict free
     int segStart[T + 1];
     int segBody[T];
     int warpCnt[T / 32];
@@ -337,7 +380,8 @@ struct FlatSmem {
 
 template <int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, int vBegin, int vEnd,
-                                                             float alpha, float alphaDual, float beta, float* __restrict__ sums, float* __restrict__ carry) {
+                                                             const int* __restrict__ kOf, float alpha, float alphaDual, float beta, float* __restrict__ sums,
+                                                             float* __restrict__ carry) {
     __shared__ FlatSmem<T> sm;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int nChunks = (vEnd - vBegin + T - 1) / T;
@@ -363,8 +407,9 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
         const bool live = v < vEnd;
         const int self = e.z >> 3;
         // ---- issue the gathers first, then build the segment list while they are in flight
-        BodyPose ps, po; float4 a4, b4, n4, l4, p4; ContactLP* lp = ms.lp + e.x;
+        BodyPose ps, po; float4 a4, b4, n4, l4, p4; ContactLP* lp = ms.lp + e.x; int kSelf = 0;
         if (live) {
+            kSelf = __ldg(kOf + self);                                // the body's position in the colour order = its row of `sums`
             ps = load_pose_keep(b.pose + self, keep);
             po = load_pose_keep(b.pose + e.y, keep);
             a4 = __ldcs(vg.a + v); b4 = __ldcs(vg.b + v); n4 = __ldcs(vg.n + v);
@@ -382,7 +427,7 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
         if (head) {
             int sidx = segBase + __popc(heads & ((1u << lane) - 1u));
             sm.segStart[sidx] = t;
-            sm.segBody[sidx] = (t == 0 && prevSelf == self) ? ~self : self;      // complemented: continues the previous chunk's last segment
+            sm.segBody[sidx] = (t == 0 && prevSelf == self) ? ~kSelf : kSelf;    // complemented: continues the previous chunk's last segment
         }
         if (t == 0) { int liveCount = vEnd - base; sm.segStart[nSeg] = liveCount < T ? liveCount : T; }
         // ---- phase 1
@@ -401,29 +446,37 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
             float4 nl = pack_lambda(cs);
             if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); *lp = q; }
             else if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) lp->l = nl;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { sm.c[k][t] = sys.rl[k]; sm.c[3 + k][t] = sys.ra[k]; }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { sm.c[6 + k][t] = sys.ll[k]; sm.c[21 + k][t] = sys.aa[k]; }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) sm.c[12 + k][t] = sys.la[k];
+            float4* row = sm.c[t];
+            row[0] = make_float4(sys.rl[0], sys.rl[1], sys.rl[2], sys.ra[0]);
+            row[1] = make_float4(sys.ra[1], sys.ra[2], sys.ll[0], sys.ll[1]);
+            row[2] = make_float4(sys.ll[2], sys.ll[3], sys.ll[4], sys.ll[5]);
+            row[3] = make_float4(sys.la[0], sys.la[1], sys.la[2], sys.la[3]);
+            row[4] = make_float4(sys.la[4], sys.la[5], sys.la[6], sys.la[7]);
+            row[5] = make_float4(sys.la[8], sys.aa[0], sys.aa[1], sys.aa[2]);
+            row[6] = make_float4(sys.aa[3], sys.aa[4], sys.aa[5], 0.0f);
         }
         __syncthreads();
         // ---- phase 2
         for (int wi = t; wi < nSeg * kFlatLanes; wi += T) {
-            int sg = wi / kFlatLanes, j = wi - sg * kFlatLanes;
-            int a = sm.segStart[sg], z = sm.segStart[sg + 1];
-            float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
-            for (int lv = a; lv < z; ++lv) { x0 += sm.c[j][lv]; x1 += sm.c[j + 9][lv]; x2 += sm.c[j + 18][lv]; }
-            int body = sm.segBody[sg];
-            float* o = body >= 0 ? sums + (size_t)body * kSumStride : carry + (size_t)chunk * kSumStride;
-            o[j] = x0; o[j + 9] = x1; o[j + 18] = x2;
+            int sgi = wi / kFlatLanes, j = wi - sgi * kFlatLanes;
+            int lv = sm.segStart[sgi], z = sm.segStart[sgi + 1];
+            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            auto add = [&](float4 x) { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; };
+            for (; lv + 4 <= z; lv += 4) {
+                float4 x0 = sm.c[lv][j], x1 = sm.c[lv + 1][j], x2 = sm.c[lv + 2][j], x3 = sm.c[lv + 3][j];
+                add(x0); add(x1); add(x2); add(x3);
+            }
+            for (; lv < z; ++lv) add(sm.c[lv][j]);
+            int idx = sm.segBody[sgi];                  // position in the colour order, complemented for a continuation
+            float* o = idx >= 0 ? sums + (size_t)idx * kSumStride : carry + (size_t)chunk * kSumStride;
+            reinterpret_cast<float4*>(o)[j] = acc;
         }
         __syncthreads();
     }
 }
 
 // One body per thread: main sums + the carries of every later chunk its visits reach, inertial terms, Schur solve, pose update.
+// `order`, `vstart`, `sums` point at the colour's first body.
 __global__ void __launch_bounds__(kThreads) primal_solve_flat(BodyView b, ForceView fv, const int* __restrict__ order, const int* __restrict__ vstart, int count,
                                                               int vBegin, int chunkT, const float* __restrict__ sums, const float* __restrict__ carry,
                                                               SolveParams prm, float* dxOut, Diag* diag) {
@@ -438,7 +491,7 @@ __global__ void __launch_bounds__(kThreads) primal_solve_flat(BodyView b, ForceV
 #pragma unroll
     for (int q = 0; q < kSumStride; ++q) o[q] = 0.0f;
     if (ve > vs) {
-        const float4* s4 = reinterpret_cast<const float4*>(sums + (size_t)i * kSumStride);
+        const float4* s4 = reinterpret_cast<const float4*>(sums + (size_t)k * kSumStride);
 #pragma unroll
         for (int q = 0; q < kSumStride / 4; ++q) { float4 x = __ldcs(s4 + q); o[4 * q] = x.x; o[4 * q + 1] = x.y; o[4 * q + 2] = x.z; o[4 * q + 3] = x.w; }
         int c0 = (vs - vBegin) / chunkT, c1 = (ve - 1 - vBegin) / chunkT;
@@ -630,33 +683,35 @@ static inline int blocks_of(long long n, int per) { long long b = (n + per - 1) 
 
 template <int T, int MINB>
 static void launch_flat(cudaStream_t s, int nSm, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                        int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
+                        const int* kOf, int first, int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
     int nChunks = (vEnd - vBegin + T - 1) / T;
     if (nChunks > 0) {
         int grid = nChunks < nSm * MINB ? nChunks : nSm * MINB;
-        primal_visit_flat<T, MINB><<<grid, T, 0, s>>>(b, visits, vg, ms, vBegin, vEnd, alpha, alphaDual, prm.beta, sums, carry);
+        primal_visit_flat<T, MINB><<<grid, T, 0, s>>>(b, visits, vg, ms, vBegin, vEnd, kOf, alpha, alphaDual, prm.beta, sums, carry);
     }
-    primal_solve_flat<<<blocks_of(count, kThreads), kThreads, 0, s>>>(b, fv, order, vstart, count, vBegin, T, sums, carry, prm, dxOut, diag);
+    primal_solve_flat<<<blocks_of(count, kThreads), kThreads, 0, s>>>(b, fv, order + first, vstart + first, count, vBegin, T, sums + (size_t)first * kSumStride, carry, prm,
+                                                                      dxOut, diag);
 }
-// The default large-world sweep of one colour: flat visit partition + block solve.  `sums`: 28 floats per BODY of the world;
-// `carry`: 28 floats per chunk (primal_flat_chunks).  AVBD_FLAT (tuning aid) = "<threads per block><blocks per SM>": 1285 (default; 96 registers,
-// 20 warps / SM — measured best on the 1M-box grid: 5.59 ms of sweeps per step against 5.66 for 1284, 5.79 for 2562 and 6.7 - 7.0 for
-// the 80-register builds 1286 / 2563, which spill) 1284 1286 2562 2563.
+// The default large-world sweep of one colour: flat visit partition + block solve.  `order` / `vstart` are the WHOLE colour-ordered
+// arrays, the colour is their bodies [first, first + count); kOf[body] = its position in `order`.  `sums`: 28 floats per dynamic body;
+// `carry`: 28 floats per chunk (primal_flat_chunks).  AVBD_FLAT (tuning aid) = "<threads per block><blocks per SM>": 1284 (default; 123 registers, no
+// spills, 16 warps / SM — measured on the 1M-box grid: 5.30 ms of sweeps per step, against 5.41 for 1285 (96 registers), 5.46 for 2562,
+// 5.78 / 6.38 for the 80-register builds 1286 / 2563, which spill) 1285 1286 2562 2563.
 int primal_flat_chunk_threads() {
-    static int t = [] { const char* e = getenv("AVBD_FLAT"); int v = e ? atoi(e) : 1285; return v / 10 == 128 ? 128 : 256; }();
+    static int t = [] { const char* e = getenv("AVBD_FLAT"); int v = e ? atoi(e) : 1284; return v / 10 == 128 ? 128 : 256; }();
     return t;
 }
 int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                       int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
+                       const int* kOf, int first, int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
     static int nSm = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
-    static int cfg = [] { const char* e = getenv("AVBD_FLAT"); return e ? atoi(e) : 1285; }();
-#define AVBD_FL(T, M) launch_flat<T, M>(s, nSm, b, visits, vg, ms, fv, order, vstart, count, vBegin, vEnd, prm, alpha, alphaDual, sums, carry, dxOut, diag)
+    static int cfg = [] { const char* e = getenv("AVBD_FLAT"); return e ? atoi(e) : 1284; }();
+#define AVBD_FL(T, M) launch_flat<T, M>(s, nSm, b, visits, vg, ms, fv, order, vstart, kOf, first, count, vBegin, vEnd, prm, alpha, alphaDual, sums, carry, dxOut, diag)
     switch (cfg) {
         case 2563: AVBD_FL(256, 3); break;
         case 2562: AVBD_FL(256, 2); break;
         case 1286: AVBD_FL(128, 6); break;
-        case 1284: AVBD_FL(128, 4); break;
-        default:   AVBD_FL(128, 5); break;
+        case 1285: AVBD_FL(128, 5); break;
+        default:   AVBD_FL(128, 4); break;
     }
 #undef AVBD_FL
     return vEnd > vBegin ? 2 : 1;
