@@ -56,25 +56,46 @@ AVBD_HD V3 sat_axis_dir(const Obb& A, const Obb& B, int k) {
     return cross(obb_axis(A, e / 3), obb_axis(B, e % 3));
 }
 
-// Full 15-axis test.  Returns 0 when separated / no valid face axis, else
-// 1 | (axisIndex << 1) with axisIndex in [0,15) naming the chosen axis after
-// the face-vs-edge preference rule (collision.cpp:459-468).
-AVBD_HD int sat_test(const Obb& A, const Obb& B) {          // collision.cpp:420-468
+// The 15-axis test in two halves (the cull kernel compacts the pairs that survive the face axes before it runs the
+// edge axes, so its lanes stay dense).  Same axes, same order, same expressions as one loop over k = 0..14.
+struct SatFaces { bool valid; float sep; int k; };
+// Axes 0-5 (faces of A, faces of B).  Returns false when one of them separates the boxes.
+AVBD_HD bool sat_faces(const Obb& A, const Obb& B, SatFaces& f) {
     V3 d = B.c - A.c;
-    bool faceValid = false, edgeValid = false;
-    float faceSep = -FLT_MAX, edgeSep = -FLT_MAX;
-    int faceK = 0, edgeK = 0;
-    for (int k = 0; k < 15; ++k) {
+    f.valid = false; f.sep = -FLT_MAX; f.k = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
         bool counted; float sep; V3 n;
-        if (!sat_axis(A, B, d, sat_axis_dir(A, B, k), counted, sep, n)) return 0;
+        if (!sat_axis(A, B, d, k < 3 ? A.ax[k % 3] : B.ax[k % 3], counted, sep, n)) return false;
         if (!counted) continue;
-        if (k < 6) { if (!faceValid || sep > faceSep) { faceValid = true; faceSep = sep; faceK = k; } }
-        else       { if (!edgeValid || sep > edgeSep) { edgeValid = true; edgeSep = sep; edgeK = k; } }
+        if (!f.valid || sep > f.sep) { f.valid = true; f.sep = sep; f.k = k; }
     }
-    if (!faceValid) return 0;
-    int best = faceK;
-    if (edgeValid && kEdgeRelTol * edgeSep > faceSep + kEdgeAbsTol) best = edgeK;
+    return true;
+}
+// Axes 6-14 (edge x edge) and the face-vs-edge preference rule (collision.cpp:459-468).  Returns 0 when separated / no valid
+// face axis, else 1 | (axisIndex << 1) with axisIndex in [0,15) naming the chosen axis.
+AVBD_HD int sat_edges(const Obb& A, const Obb& B, const SatFaces& f) {
+    V3 d = B.c - A.c;
+    bool edgeValid = false;
+    float edgeSep = -FLT_MAX;
+    int edgeK = 0;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+        bool counted; float sep; V3 n;
+        if (!sat_axis(A, B, d, cross(A.ax[e / 3], B.ax[e % 3]), counted, sep, n)) return 0;
+        if (!counted) continue;
+        if (!edgeValid || sep > edgeSep) { edgeValid = true; edgeSep = sep; edgeK = 6 + e; }
+    }
+    if (!f.valid) return 0;
+    int best = f.k;
+    if (edgeValid && kEdgeRelTol * edgeSep > f.sep + kEdgeAbsTol) best = edgeK;
     return 1 | (best << 1);
+}
+// Full 15-axis test (collision.cpp:420-468).
+AVBD_HD int sat_test(const Obb& A, const Obb& B) {
+    SatFaces f;
+    if (!sat_faces(A, B, f)) return 0;
+    return sat_edges(A, B, f);
 }
 
 AVBD_HD void face_axes(const Obb& b, int k, V3& u, V3& v, float& eu, float& ev) {   // collision.cpp:73-92

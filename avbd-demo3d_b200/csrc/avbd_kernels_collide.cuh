@@ -196,25 +196,55 @@ __global__ void bp_persisting(BodyView b, ManifoldSet old, int nOld, PairSink si
 // K3a: SAT cull (collision.cpp:420-468), one thread per candidate in emission order — which follows the cell-sorted
 // body order, so neighbouring threads gather neighbouring poses.  Survivors {key, winning axis} go to `out`; only
 // they (about a fifth of the candidates on a dense pile) are sorted.  The candidate count is read on the device.
+// Two phases per block so lanes stay dense: every thread runs the 6 face axes of its pair (most candidates of a pile die
+// there); the pairs still alive are compacted in shared memory and the first nAlive threads run the 9 edge axes.
 __global__ void __launch_bounds__(kThreads) np_sat(BodyView b, const unsigned long long* cand, const int* nCand, int cap, int keyShift,
                                                    const unsigned long long* excl, int nExcl, PairSink out) {
     __shared__ int sWarp[kThreads / 32], sBase;
+    __shared__ int sAliveP[kThreads]; __shared__ float sAliveSep[kThreads]; __shared__ int sAliveK[kThreads];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     int n = *nCand; if (n > cap) n = cap;
-    int code = 0; unsigned long long k = 0;
+    auto load_pair = [&](unsigned long long k, Obb& A, Obb& B) {
+        int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
+        BodyPose pa = b.pose[a], pb = b.pose[c];
+        A = make_obb(xyz(pa.pos), quat(pa.rot), xyz(b.size[a]));
+        B = make_obb(xyz(pb.pos), quat(pb.rot), xyz(b.size[c]));
+    };
+    // ---- phase 1: face axes
+    bool alive = false; SatFaces f{false, 0.0f, 0};
     if (p < n) {
-        k = cand[p];
+        unsigned long long k = cand[p];
         if (!(nExcl > 0 && find_key(excl, nExcl, k) >= 0)) {
-            int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
-            BodyPose pa = b.pose[a], pb = b.pose[c];
-            Obb A = make_obb(xyz(pa.pos), quat(pa.rot), xyz(b.size[a]));
-            Obb B = make_obb(xyz(pb.pos), quat(pb.rot), xyz(b.size[c]));
-            code = sat_test(A, B);
+            Obb A, B;
+            load_pair(k, A, B);
+            alive = sat_faces(A, B, f);
         }
+    }
+    unsigned av = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) sWarp[warp] = __popc(av);
+    __syncthreads();
+    int aBase = 0, nAlive = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { int c = sWarp[w]; if (w < warp) aBase += c; nAlive += c; }
+    if (alive) {
+        int idx = aBase + __popc(av & ((1u << lane) - 1u));
+        sAliveP[idx] = p; sAliveSep[idx] = f.sep; sAliveK[idx] = f.valid ? f.k : -1;
+    }
+    __syncthreads();
+    // ---- phase 2: edge axes, dense
+    int code = 0; unsigned long long k = 0;
+    if ((int)threadIdx.x < nAlive) {
+        k = cand[sAliveP[threadIdx.x]];
+        int fk = sAliveK[threadIdx.x];
+        SatFaces g{fk >= 0, fk >= 0 ? sAliveSep[threadIdx.x] : -FLT_MAX, fk >= 0 ? fk : 0};
+        Obb A, B;
+        load_pair(k, A, B);
+        code = sat_edges(A, B, g);
     }
     // block-wide compaction of the survivors: one atomic on the list counter per block
     unsigned vote = __ballot_sync(0xffffffffu, code != 0);
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();                                   // everyone is done reading the phase-1 counts
     if (lane == 0) sWarp[warp] = __popc(vote);
     __syncthreads();
     if (threadIdx.x == 0) {
