@@ -136,6 +136,49 @@ __global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange,
     }
 }
 
+// Incremental recolouring: last step's colouring is still valid except where a NEW manifold joins two bodies of one colour.
+// Of such a pair the lower-priority body is uncoloured (reads the old colours, writes the new array: no race, no dependence on
+// timing) and the usual rounds then colour only those bodies — typically a few hundred of a million, in one or two rounds
+// instead of the ~17 a colouring from scratch needs.
+__global__ void colour_conflicts(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, ForceView fv,
+                                 const int* localIdx, const int* colourPrev, int* colourOut) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    int i = dynList[t];
+    int mine = colourPrev[i];
+    if (mine >= 0) {
+        int li = localIdx[i];
+        bool clash = false;
+        auto visit = [&](int other) {
+            if (other >= 0 && colourPrev[other] == mine && outranks(localIdx[other], li)) clash = true;
+        };
+        int4 rg = adjRange[i];
+        for (int m = rg.x; m < rg.y && !clash; ++m) visit(hdr[m].y);
+        for (int k = rg.z; k < rg.w && !clash; ++k) visit(hdr[bList[k]].x);
+        if (fv.adjStart) {
+            for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && !clash; ++k) {
+                int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
+                visit((e & 2) ? (isA ? fv.springs[idx].b : fv.springs[idx].a) : (isA ? fv.joints[idx].b : fv.joints[idx].a));
+            }
+        }
+        if (clash) mine = -1;
+    } else mine = -1;
+    colourOut[i] = mine;
+}
+
+// Work list of the bodies still uncoloured (order is irrelevant: the colouring does not depend on it).
+__global__ void colour_compact(const int* list, int n, const int* colour, int* out, int* outCount) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false; int i = 0;
+    if (t < n) { i = list[t]; keep = colour[i] < 0; }
+    unsigned vote = __ballot_sync(0xffffffffu, keep);
+    if (!vote) return;
+    int lane = threadIdx.x & 31, base = 0;
+    if (lane == 0) base = atomicAdd(outCount, __popc(vote));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) out[base + __popc(vote & ((1u << lane) - 1u))] = i;
+}
+
 __global__ void colour_keys(const int* dynList, int nDyn, const int* colour, unsigned* key, int* val) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
@@ -153,12 +196,13 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
     if (t == nDyn - 1) cnt->nColours = (int)c + 1;
 }
 
-// out[c] = index of colour c's first visit, out[nColours ..] = total visits (colours are contiguous in the visit list).
-__global__ void colour_visit_bounds(const int2* colourRange, int nColours, const int* visitStart, int nDyn, int* out) {
+// out[c] = {first visit, one past the last visit} of colour c (a colour's bodies, hence its visits, are contiguous); {0, 0} for
+// a colour incremental recolouring left empty.
+__global__ void colour_visit_bounds(const int2* colourRange, int nColours, const int* visitStart, int2* out) {
     int c = threadIdx.x;
-    if (c > 64) return;
-    out[c] = c < nColours ? visitStart[colourRange[c].x] : visitStart[nDyn];
-    if (c == 0) out[64] = visitStart[nDyn];
+    if (c >= 64) return;
+    int2 r = c < nColours ? colourRange[c] : make_int2(0, 0);
+    out[c] = r.y > r.x ? make_int2(visitStart[r.x], visitStart[r.y]) : make_int2(0, 0);
 }
 
 __global__ void invert_order(const int* order, int n, int* positionOf) {

@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star / SURVEY.md §8d):
   FP32 tol    per-body 6x6 solve (dx) given identical inputs: <= 1e-4 * |dx|_inf + 1e-6
   trajectory  rest heights / counts / penetration (tests further down) — colour order differs from the serial order
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -229,6 +231,35 @@ def test_colouring_valid(avbd, scene):
         assert k <= 12, k
     finally:
         o.close(); w.close()
+
+
+def test_incremental_recolouring_stays_valid(avbd):
+    """With AVBD_INCREMENTAL_COLOUR=1 the colouring is updated incrementally after the first step (only bodies a new manifold
+    put in conflict are recoloured): it must stay a valid colouring of every step's graph and must not grow colours without bound while
+    Stress1000 collapses (manifolds appear and disappear every step)."""
+    from avbd_demo3d_b200 import scenes
+    os.environ["AVBD_INCREMENTAL_COLOUR"] = "1"
+    try:
+        w = avbd.World()
+    finally:
+        os.environ.pop("AVBD_INCREMENTAL_COLOUR", None)
+    try:
+        scenes.load(w, scenes.scene("Stress1000"))
+        props = None
+        for chunk in range(12):
+            w.step(20)
+            col, k = w.colours()
+            if props is None:
+                props = w.body_props()
+            ms = gpu_manifolds(w)
+            dyn = props[:, 4] > 0
+            for (a, b) in ms:
+                if dyn[a] and dyn[b]:
+                    assert col[a] != col[b], (chunk, a, b, col[a])
+            assert (col[dyn] >= 0).all() and (col[~dyn] == -2).all()
+            assert k <= 12 and col.max() == k - 1, (chunk, k)
+    finally:
+        w.close()
 
 
 @pytest.mark.parametrize("scene,warm", [("Stack", 30), ("Pyramid", 30), ("TwoBlockDrop", 40), ("Stress1000", 140)])

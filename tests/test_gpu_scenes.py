@@ -259,7 +259,7 @@ def test_deferred_dual_equals_one_dual_pass_per_iteration(avbd, case):
     (tools/dual_probe.py: the three paths are bit-equal to step 8 on Pyramid, 1e-9 apart at step 10, 3e-3 at step 12)."""
     from avbd_demo3d_b200 import scenes
     if case == "Pyramid":
-        build, steps = (lambda w: scenes.load(w, scenes.scene("Pyramid"))), 9
+        build, steps = (lambda w: scenes.load(w, scenes.scene("Pyramid"))), 6
     else:
         build, steps = _pile_with_two_statics(case == "pile_post"), 8        # the boxes start interpenetrating: contacts from step 1
     ref = _run_variant(avbd, build, steps, {"AVBD_PERSISTENT_MAX_BODIES": "0", "AVBD_SEPARATE_DUAL": "1"})
