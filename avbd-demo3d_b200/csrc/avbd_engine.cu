@@ -52,6 +52,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+constexpr int kColourBlockMaxBodies = 8192;      // at most this many dynamic bodies: colouring rounds run in one block
 inline int blocks_for(long long n, int threads = kThreads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
 
 struct HostBody {   // what the host must remember to (re)classify bodies; dynamic state lives on the device
@@ -472,7 +473,11 @@ int run_colour(avbd_world* w) {
     // rounds too many costs microseconds while every host check of the uncoloured count costs a round trip.  Only the
     // last round of a batch counts the bodies it left uncoloured; when that is under half of the current work list the
     // stragglers are compacted into a new list, so late rounds do not sweep a million coloured bodies to find a few thousand.
-    {
+    if (w->nDyn <= kColourBlockMaxBodies) {
+        // small world: every round in one block, no launches or host checks in between (the count is read with the colour ranges below)
+        colour_rounds_block<<<1, kColourBlockThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p, w->dCnt);
+        w->launches++;
+    } else {
         const int* list = w->dynList.p; int listCount = w->nDyn; int which = 0;
         for (int round = 0, batch = incremental ? 2 : 6;;) {
             if (round > 4096) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
@@ -495,18 +500,12 @@ int run_colour(avbd_world* w) {
             batch = 8;          // the work list is short by now: spare rounds are cheaper than another host check
         }
     }
-    if (w->hCnt->overflow & 4) return fail(AVBD_ERR_CAPACITY, "more than 64 colours needed");
     w->colouredBodies = n;
     colour_keys<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);
     TRY(sort_pairs(w, w->colKey.p, w->colKeySorted.p, w->colVal.p, w->colOrder.p, w->nDyn, 7));
     CK(cudaMemsetAsync(w->colRange.p, 0, sizeof(int2) * 64, s));
     colour_bounds<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);
     w->launches += 2;
-    CK(cudaMemcpyAsync(w->hColRange, w->colRange.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
-    TRY(read_counters(w));
-    w->nColours = w->hCnt->nColours;
-    w->maxColourCount = 0;
-    for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);
     // contact visits in colour order (the primal's work list): visitStart[k] belongs to colOrder[k]
     TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
     TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
@@ -516,13 +515,20 @@ int run_colour(avbd_world* w) {
     TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
     visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
     w->launches += 2;
-    // first visit of every colour (the flat primal partitions a colour's visits, not its bodies)
+    // first / last visit of every colour (the flat primal partitions a colour's visits, not its bodies)
     TRY(w->colVisit.ensure(64, false, s)); TRY(w->kOf.ensure(n, false, s));
-    colour_visit_bounds<<<1, 64, 0, s>>>(w->colRange.p, w->nColours, w->visitStart.p, w->colVisit.p);
+    colour_visit_bounds<<<1, 64, 0, s>>>(w->colRange.p, w->dCnt, w->visitStart.p, w->colVisit.p);
     invert_order<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->kOf.p);
     w->launches += 2;
+    // ONE host round trip for everything the launches of the sweeps need: colour ranges, their visit ranges, counters
+    CK(cudaMemcpyAsync(w->hColRange, w->colRange.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(w->hColVisit, w->colVisit.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    TRY(read_counters(w));
+    if (w->hCnt->nUncoloured != 0) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
+    if (w->hCnt->overflow & 4) return fail(AVBD_ERR_CAPACITY, "more than 64 colours needed");
+    w->nColours = w->hCnt->nColours;
+    w->maxColourCount = 0;
+    for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;

@@ -98,15 +98,14 @@ __global__ void colour_init(const int* flags, int n, int* colour) {
     if (i < n) colour[i] = (flags[i] & kDynamic) ? -1 : -2;
 }
 
-// One Jones-Plassmann round: a body takes the smallest colour unused by its
-// neighbours once every higher-priority neighbour is coloured.  The result is
-// the sequential greedy colouring in priority order, independent of timing.
-__global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
-                             ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt, bool countLeft) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nDyn) return;
-    int i = dynList[t];
-    if (colour[i] >= 0) return;
+// One Jones-Plassmann attempt for body i: it takes the smallest colour unused by its neighbours once every
+// higher-priority neighbour is coloured.  A lower-priority neighbour cannot be coloured before i is, so what i sees
+// coloured is exactly its higher-priority neighbourhood whenever it succeeds: the result is the sequential greedy
+// colouring in priority order, independent of timing (timing only changes how many attempts it takes).
+// Returns whether the body is coloured after the attempt.
+__device__ __forceinline__ bool try_colour(int i, const int4* adjRange, const int* bList, const int4* hdr, const ForceView& fv,
+                                           const int* localIdx, volatile int* colour, Counters* cnt) {
+    if (colour[i] >= 0) return true;
     int li = localIdx[i];
     unsigned long long used = 0ull;
     bool ready = true;
@@ -126,14 +125,36 @@ __global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange,
             visit(other);
         }
     }
-    if (ready) {
-        int c = __ffsll((long long)~used) - 1;
-        if (c < 0) { c = 63; atomicOr(&cnt->overflow, 4); }
-        colour[i] = c;
-    } else if (countLeft) {
+    if (!ready) return false;
+    int c = __ffsll((long long)~used) - 1;
+    if (c < 0) { c = 63; atomicOr(&cnt->overflow, 4); }
+    colour[i] = c;
+    return true;
+}
+
+__global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
+                             ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt, bool countLeft) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    if (!try_colour(dynList[t], adjRange, bList, hdr, fv, localIdx, colour, cnt) && countLeft) {
         cg::coalesced_group grp = cg::coalesced_threads();
         if (grp.thread_rank() == 0) atomicAdd(&cnt->nUncoloured, (int)grp.size());
     }
+}
+
+// Small worlds: ALL rounds in one block (block barrier between rounds instead of a launch, no host check of the
+// uncoloured count).  Same attempts, hence the same colouring as colour_round.
+constexpr int kColourBlockThreads = 1024;
+__global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
+                                                                           ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt) {
+    int left = 1;
+    for (int round = 0; round < 4096 && left; ++round) {
+        int mine = 0;
+        for (int t = threadIdx.x; t < nDyn; t += blockDim.x)
+            if (!try_colour(dynList[t], adjRange, bList, hdr, fv, localIdx, colour, cnt)) mine = 1;
+        left = __syncthreads_or(mine);           // also makes this round's colours visible to the whole block
+    }
+    if (threadIdx.x == 0) cnt->nUncoloured = left;
 }
 
 // Incremental recolouring: last step's colouring is still valid except where a NEW manifold joins two bodies of one colour.
@@ -198,10 +219,10 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
 
 // out[c] = {first visit, one past the last visit} of colour c (a colour's bodies, hence its visits, are contiguous); {0, 0} for
 // a colour incremental recolouring left empty.
-__global__ void colour_visit_bounds(const int2* colourRange, int nColours, const int* visitStart, int2* out) {
+__global__ void colour_visit_bounds(const int2* colourRange, const Counters* cnt, const int* visitStart, int2* out) {
     int c = threadIdx.x;
     if (c >= 64) return;
-    int2 r = c < nColours ? colourRange[c] : make_int2(0, 0);
+    int2 r = c < cnt->nColours ? colourRange[c] : make_int2(0, 0);
     out[c] = r.y > r.x ? make_int2(visitStart[r.x], visitStart[r.y]) : make_int2(0, 0);
 }
 

@@ -54,6 +54,17 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """DRAM bytes per primal colour sweep from the committed `ncu --set full` capture of this workload (profiles/r01_traffic.json,
+    written by profiles/summarize.py traffic); None when the file is absent.  Cold-cache, serialised launches: an upper bound."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_colour_sweep"]), "profiles/r01_traffic.json (%s)" % t.get("source", "ncu")
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -250,6 +261,7 @@ def main():
         total_dyn = n_dyn * world_size
         value = total_dyn * iters * args.steps / (ms_max * 1e-3)
         peak, peak_src = measured_peak()
+        traffic, traffic_src = ncu_traffic()
         primal_bytes = (PRIMAL_BYTES_PER_BODY * prof["primal_bodies"] + PRIMAL_BYTES_PER_VISIT * prof["primal_visits"]
                         + DEFERRED_DUAL_BYTES_PER_CONTACT * prof["deferred_dual_contacts"])
         dual_bytes = DUAL_BYTES_PER_CONTACT * prof["dual_contacts"]
@@ -262,7 +274,8 @@ def main():
                         colours=stats["colours"], iterations=iters, parallelism=f"independent-worlds x{world_size}",
                         l2="inputs larger than L2 (body + contact state > 126 MB)" if n_bodies > 300000 else "state is L2-resident; steady-state stepping, no flush"),
             steps_per_s=args.steps / (ms_max * 1e-3),
-            roofline=dict(bound="hbm", kernel="primal_visit_sums<BPB,MINB> + primal_solve (one pair per colour; sweeps 2.. also apply the deferred dual)", achieved=primal_gbs, peak=peak, unit="GB/s", frac=primal_gbs / peak, traffic=None,
+            roofline=dict(bound="hbm", kernel="primal_visit_sums<BPB,MINB> + primal_solve (one pair per colour; sweeps 2.. also apply the deferred dual)", achieved=primal_gbs, peak=peak, unit="GB/s", frac=primal_gbs / peak,
+                          traffic=traffic if args.workload == "grid100" else None, traffic_source=traffic_src if args.workload == "grid100" else None,
                           peak_source=peak_src, algorithmic_bytes_per_launch=primal_bytes / max(prof["primal_launches"], 1),
                           avg_launch_ms=prof["ms_primal"] / max(prof["primal_launches"], 1), share_of_step=prof["ms_primal"] / ms,
                           deferred_dual_passes_per_step=prof["deferred_dual_contacts"] / max(1, prof["steps"] * max(1, stats["contacts"])),

@@ -1,6 +1,7 @@
 """Turns ncu outputs (gpurun_out/) into the small text summaries kept under profiles/.
   python profiles/summarize.py launches <launches.csv> > profiles/<name>.md
   python profiles/summarize.py kernels  <report.ncu-rep> > profiles/<name>.md
+  python profiles/summarize.py traffic  <solve report.ncu-rep> > profiles/<name>.json   (DRAM bytes per primal colour sweep, for bench.py's roofline.traffic)
 """
 import collections
 import csv
@@ -53,5 +54,27 @@ def kernels(path):
         print()
 
 
+def traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the primal kernels of a `capture.sh solve` report, per colour sweep
+    (= one primal_visit_flat + one primal_solve_flat launch, the unit bench.py's roofline is quoted per)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    H, U = rows[0], rows[1]
+    ki, ri, wi, ti = H.index("Kernel Name"), H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("gpu__time_duration.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    visit = solve = 0.0; nv = ns = 0; dual = 0.0; nd = 0
+    for r in rows[2:]:
+        bytes_ = float(r[ri].replace(",", "")) * scale[U[ri]] + float(r[wi].replace(",", "")) * scale[U[wi]]
+        if "primal_visit" in r[ki]: visit += bytes_; nv += 1
+        elif "primal_solve" in r[ki]: solve += bytes_; ns += 1
+        elif "dual_contacts" in r[ki]: dual += bytes_; nd += 1
+    sweeps = max(ns, 1)
+    print(json.dumps({"source": path.split("/")[-1], "how": "ncu --set full --clock-control none (cold caches, serialised launches), 1M-box pre-stacked grid, first sweeps of one step",
+                      "colour_sweeps_captured": sweeps, "visit_kernel_launches": nv, "dram_bytes_per_colour_sweep": (visit + solve) / sweeps,
+                      "visit_kernel_bytes_per_colour_sweep": visit / sweeps, "solve_kernel_bytes_per_colour_sweep": solve / sweeps,
+                      "dual_pass_bytes": dual / nd if nd else None}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernels": kernels}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernels": kernels, "traffic": traffic}[sys.argv[1]](sys.argv[2])
