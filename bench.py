@@ -72,7 +72,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -161,7 +161,7 @@ def run_reference(args, rank):
     r = per[0]
     _, desc = workload_preset(args.workload if args.workload != "stress1000" else "grid100")
     line = dict(metric="body_solves_per_s", value=r["value"], unit="body-solves/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 / r["steps_per_s"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                ms_per_step=1e3 / r["steps_per_s"], higher_is_better=True, scaling="strong" if args.workload == "ensemble" else "weak", vs_baseline=None, dtype="f32", data="synthetic",
                 impl="reference", config=dict(workload=desc, sample=r["sample"]),
                 cpu_baseline=dict(value=r["value"], unit=r["unit"], cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                 e2e=dict(value=r["value"], unit="body-solves/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -269,12 +269,12 @@ def main():
         dual_gbs = dual_bytes / max(prof["ms_dual"], 1e-9) / 1e6
         line = dict(
             metric="body_solves_per_s", value=value, unit="body-solves/s", n_gpus=world_size, steps=args.steps, warmup=max(3, args.warmup),
-            ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+            ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="strong" if args.workload == "ensemble" else "weak", vs_baseline=None, dtype="f32", data="synthetic",
             config=dict(workload=desc, bodies_per_gpu=n_bodies, dynamic_bodies_per_gpu=n_dyn, manifolds=stats["manifolds"], contacts=stats["contacts"],
                         colours=stats["colours"], iterations=iters, parallelism=f"independent-worlds x{world_size}",
                         l2="inputs larger than L2 (body + contact state > 126 MB)" if n_bodies > 300000 else "state is L2-resident; steady-state stepping, no flush"),
             steps_per_s=args.steps / (ms_max * 1e-3),
-            roofline=dict(bound="hbm", kernel="primal_visit_sums<BPB,MINB> + primal_solve (one pair per colour; sweeps 2.. also apply the deferred dual)", achieved=primal_gbs, peak=peak, unit="GB/s", frac=primal_gbs / peak,
+            roofline=dict(bound="hbm", kernel="primal_visit_flat<128,4> + primal_solve_flat (one pair per colour = one colour sweep; sweeps 2.. also apply the deferred dual)", achieved=primal_gbs, peak=peak, unit="GB/s", frac=primal_gbs / peak,
                           traffic=traffic if args.workload == "grid100" else None, traffic_source=traffic_src if args.workload == "grid100" else None,
                           peak_source=peak_src, algorithmic_bytes_per_launch=primal_bytes / max(prof["primal_launches"], 1),
                           avg_launch_ms=prof["ms_primal"] / max(prof["primal_launches"], 1), share_of_step=prof["ms_primal"] / ms,
