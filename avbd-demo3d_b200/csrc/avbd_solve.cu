@@ -12,6 +12,7 @@
 // primal rows, and writes lambda / penalty back once.  A step therefore runs ONE stand-alone dual pass (after the last
 // sweep, fused with the contact diagnostics) instead of `iterations` of them.  alphaDual < 0 = nothing pending (first sweep
 // of a step, stage API).
+#include <cstdio>
 #include <cstdlib>
 #include "avbd_launch.h"
 #include "avbd_body.cuh"
@@ -373,10 +374,26 @@ constexpr int kFlatLanes = 7;                 // lanes per segment in phase 2 (o
 template <int T>
 struct FlatSmem {
     float4 c[T][7];      // one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad — 128-bit stores / loads, row stride 28 words: conflict free
+    float4 stage[9][T];  // the NEXT chunk's gathered operands, filled by cp.async: self pose (2), other pose (2), geometry (3), lambda, penalty
     int segStart[T + 1];
     int segBody[T];
     int warpCnt[T / 32];
 };
+
+// cp.async (LDGSTS) of one 16-byte item into this thread's slot of the gather stage, with an L2 eviction policy.
+__device__ __forceinline__ void stage16(float4* dst, const float4* src, unsigned long long policy) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void stage16_nol1(float4* dst, const float4* src, unsigned long long policy) {      // bypasses L1 (streamed / single-use data)
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_stream_policy() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 
 template <int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, int vBegin, int vEnd,
@@ -385,36 +402,54 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
     __shared__ FlatSmem<T> sm;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int nChunks = (vEnd - vBegin + T - 1) / T;
-    const unsigned long long keep = l2_keep_policy();
+    const unsigned long long keep = l2_keep_policy(), stream = l2_stream_policy();
     int chunk = blockIdx.x;
     if (chunk >= nChunks) return;
     const int4 none = make_int4(0, 0, -8, 0);                        // body -1
-    int4 eNext = none; int prevNext = -8;
-    {
-        int v = vBegin + chunk * T + t;
-        if (v < vEnd) eNext = __ldcs(visits + v);
-        if (lane == 0 && v > vBegin && v < vEnd) prevNext = __ldg(&visits[v - 1].z);
-    }
+    const int stride = gridDim.x * T;
+    // launched with programmatic stream serialization: the grid may already be resident while the previous colour's block solve
+    // drains; nothing it wrote (poses) is read before this point
+    cudaGridDependencySynchronize();
+    // Software pipeline over the block's chunks, two deep: the visit ENTRIES are loaded two chunks ahead (registers), and as soon
+    // as an entry is there the data it points at — two poses, the lambda / penalty record, the streamed geometry: 9 x 16 B per
+    // visit — is fetched one chunk ahead with cp.async into this thread's slots of a shared-memory stage.  A chunk therefore
+    // starts with its operands already on chip; both DRAM round trips hide behind the previous chunk's row math and reduction.
+    auto load_entry = [&](int v, int4& e, int& prevZ) {
+        e = none; prevZ = -8;
+        if (v < vEnd) { e = __ldcs(visits + v); if (lane == 0 && v > vBegin) prevZ = __ldg(&visits[v - 1].z); }
+    };
+    auto issue_gathers = [&](int v, const int4& e, int& kSelf) {         // into the stage; the caller commits the group
+        kSelf = 0;
+        if (v < vEnd) {
+            int self = e.z >> 3;
+            kSelf = __ldg(kOf + self);                                    // the body's position in the colour order = its row of `sums`
+            stage16(&sm.stage[0][t], &b.pose[self].pos, keep); stage16(&sm.stage[1][t], &b.pose[self].rot, keep);
+            stage16(&sm.stage[2][t], &b.pose[e.y].pos, keep);  stage16(&sm.stage[3][t], &b.pose[e.y].rot, keep);
+            stage16_nol1(&sm.stage[4][t], vg.a + v, stream); stage16_nol1(&sm.stage[5][t], vg.b + v, stream); stage16_nol1(&sm.stage[6][t], vg.n + v, stream);
+            stage16_nol1(&sm.stage[7][t], &ms.lp[e.x].l, keep); stage16_nol1(&sm.stage[8][t], &ms.lp[e.x].p, keep);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int4 eCur, eNext; int prevCur, prevNext, kCur;
+    load_entry(vBegin + chunk * T + t, eCur, prevCur);
+    load_entry(vBegin + chunk * T + t + stride, eNext, prevNext);
+    issue_gathers(vBegin + chunk * T + t, eCur, kCur);
     for (; chunk < nChunks; chunk += gridDim.x) {
         const int base = vBegin + chunk * T;
         const int v = base + t;
-        const int4 e = eNext; const int prevZ = prevNext;
-        {   // prefetch the next chunk's entries: their latency hides behind this chunk's work
-            int vn = v + gridDim.x * T;
-            eNext = none; prevNext = -8;
-            if (vn < vEnd) { eNext = __ldcs(visits + vn); if (lane == 0) prevNext = __ldg(&visits[vn - 1].z); }
-        }
+        const int4 e = eCur; const int prevZ = prevCur; const int kSelf = kCur;
         const bool live = v < vEnd;
         const int self = e.z >> 3;
-        // ---- issue the gathers first, then build the segment list while they are in flight
-        BodyPose ps, po; float4 a4, b4, n4, l4, p4; ContactLP* lp = ms.lp + e.x; int kSelf = 0;
-        if (live) {
-            kSelf = __ldg(kOf + self);                                // the body's position in the colour order = its row of `sums`
-            ps = load_pose_keep(b.pose + self, keep);
-            po = load_pose_keep(b.pose + e.y, keep);
-            a4 = __ldcs(vg.a + v); b4 = __ldcs(vg.b + v); n4 = __ldcs(vg.n + v);
-            l4 = lp->l; p4 = lp->p;
-        }
+        ContactLP* lp = ms.lp + e.x;
+        // ---- this chunk's operands: wait for the thread's own copies, move them to registers, and refill the stage at once
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        BodyPose ps, po; float4 a4, b4, n4, l4, p4;
+        ps.pos = sm.stage[0][t]; ps.rot = sm.stage[1][t]; po.pos = sm.stage[2][t]; po.rot = sm.stage[3][t];
+        a4 = sm.stage[4][t]; b4 = sm.stage[5][t]; n4 = sm.stage[6][t]; l4 = sm.stage[7][t]; p4 = sm.stage[8][t];
+        eCur = eNext; prevCur = prevNext;
+        issue_gathers(v + stride, eCur, kCur);                        // next chunk (its entry was loaded a whole chunk ago)
+        load_entry(v + 2 * stride, eNext, prevNext);                  // the entry after that
+        // ---- phase 0: segment list
         int prevSelf = __shfl_up_sync(0xffffffffu, self, 1);
         if (lane == 0) prevSelf = prevZ >> 3;                         // -1 at the colour's first visit
         const bool head = live && (prevSelf != self || t == 0);       // lane 0 of the chunk always opens a segment (maybe a continuation)
@@ -485,6 +520,7 @@ __global__ void __launch_bounds__(kThreads) primal_solve_flat(BodyView b, ForceV
     int i = order[k];
     int vs = vstart[k], ve = vstart[k + 1];
     const unsigned long long keep = l2_keep_policy();
+    cudaGridDependencySynchronize();          // the visit kernel's sums / carries (programmatic stream serialization, see launch_flat)
     BodyPose self = load_pose_keep(b.pose + i, keep);
     BodyAux aux = b.aux[i];
     float o[kSumStride];
@@ -686,19 +722,39 @@ static void launch_flat(cudaStream_t s, int nSm, BodyView b, const int4* visits,
                         const int* kOf, int first, int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
     int nChunks = (vEnd - vBegin + T - 1) / T;
     if (nChunks > 0) {
-        int grid = nChunks < nSm * MINB ? nChunks : nSm * MINB;
-        primal_visit_flat<T, MINB><<<grid, T, 0, s>>>(b, visits, vg, ms, vBegin, vEnd, kOf, alpha, alphaDual, prm.beta, sums, carry);
+        // persistent grid = what is actually resident (a block that has to wait for a slot would start its share of the chunks late)
+        static const int perSm = [] {
+            cudaFuncSetAttribute(primal_visit_flat<T, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, primal_visit_flat<T, MINB>, T, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+            if (getenv("AVBD_DEBUG")) fprintf(stderr, "primal_visit_flat<%d,%d>: %d blocks per SM resident\n", T, MINB, n);
+            return n;
+        }();
+        int grid = nChunks < nSm * perSm ? nChunks : nSm * perSm;
+        // Programmatic dependent launch: each kernel of a sweep is launched while its predecessor still runs and blocks at
+        // cudaGridDependencySynchronize() until that one has completed — a step has ~160 of these dependent launches, and the
+        // launch latency of each would otherwise sit on the critical path.
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = 0; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, primal_visit_flat<T, MINB>, b, visits, vg, ms, vBegin, vEnd, kOf, alpha, alphaDual, prm.beta, sums, carry);
     }
-    primal_solve_flat<<<blocks_of(count, kThreads), kThreads, 0, s>>>(b, fv, order + first, vstart + first, count, vBegin, T, sums + (size_t)first * kSumStride, carry, prm,
-                                                                      dxOut, diag);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3(blocks_of(count, kThreads)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = 1;
+        const int* orderC = order + first; const int* vstartC = vstart + first; const float* sumsC = sums + (size_t)first * kSumStride; const float* carryC = carry;
+        cudaLaunchKernelEx(&cfg, primal_solve_flat, b, fv, orderC, vstartC, count, vBegin, (int)T, sumsC, carryC, prm, dxOut, diag);
+    }
 }
 // The default large-world sweep of one colour: flat visit partition + block solve.  `order` / `vstart` are the WHOLE colour-ordered
 // arrays, the colour is their bodies [first, first + count); kOf[body] = its position in `order`.  `sums`: 28 floats per dynamic body;
-// `carry`: 28 floats per chunk (primal_flat_chunks).  AVBD_FLAT (tuning aid) = "<threads per block><blocks per SM>": 1284 (default; 123 registers, no
-// spills, 16 warps / SM — measured on the 1M-box grid: 5.30 ms of sweeps per step, against 5.41 for 1285 (96 registers), 5.46 for 2562,
-// 5.78 / 6.38 for the 80-register builds 1286 / 2563, which spill) 1285 1286 2562 2563.
+// `carry`: 28 floats per chunk (primal_flat_chunks).  AVBD_FLAT (tuning aid) = "<threads per block><blocks per SM>": 1284 (default; 96 registers, no
+// spills, 33 KB of shared memory per block) 1285 1286 — all within 2 % of each other on the 1M-box grid (5.39 / 5.42 / 5.48 ms of sweeps).
 int primal_flat_chunk_threads() {
-    static int t = [] { const char* e = getenv("AVBD_FLAT"); int v = e ? atoi(e) : 1284; return v / 10 == 128 ? 128 : 256; }();
+    static int t = [] { const char* e = getenv("AVBD_FLAT"); (void)e; return 128; }();
     return t;
 }
 int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
@@ -707,8 +763,6 @@ int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom
     static int cfg = [] { const char* e = getenv("AVBD_FLAT"); return e ? atoi(e) : 1284; }();
 #define AVBD_FL(T, M) launch_flat<T, M>(s, nSm, b, visits, vg, ms, fv, order, vstart, kOf, first, count, vBegin, vEnd, prm, alpha, alphaDual, sums, carry, dxOut, diag)
     switch (cfg) {
-        case 2563: AVBD_FL(256, 3); break;
-        case 2562: AVBD_FL(256, 2); break;
         case 1286: AVBD_FL(128, 6); break;
         case 1285: AVBD_FL(128, 5); break;
         default:   AVBD_FL(128, 4); break;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Tuning aid (run under gpurun): 1M-box step time for each flat-primal configuration (threads per block, blocks per SM).
-for v in 2563 2562 1286 1285 1284; do
+for v in 1286 1285 1284; do
   export AVBD_FLAT=$v
   echo "== $v"; timeout 300 python bench.py --no-cpu-baseline --steps 10 --warmup 3 2>&1 | python -c "
 import sys, json
