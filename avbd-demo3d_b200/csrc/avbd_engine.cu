@@ -206,12 +206,13 @@ int exclusive_scan(avbd_world* w, const int* in, int* out, int n) {
 int bits_for(unsigned long long maxValue) { int b = 1; while ((1ull << b) <= maxValue) ++b; return b; }
 
 __global__ void rekey_manifolds(ManifoldSet ms, int nM, int keyShift) {
+    cudaGridDependencySynchronize();
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < nM) ms.key[m] = ((unsigned long long)(unsigned)ms.hdr[m].x << keyShift) | (unsigned)ms.hdr[m].y;
 }
 
 int np_sat_launch(avbd_world* w, const BodyView& bv, const PairSink& raw, int expect, const PairSink& out) {
-    np_sat<<<blocks_for(expect), kThreads, 0, w->stream>>>(bv, raw.keys, raw.count, raw.cap, w->keyShift, w->excl.p, w->nExcl, out);
+    launch_dep(np_sat, dim3(blocks_for(expect)), dim3(kThreads), 0, w->stream, bv, raw.keys, raw.count, raw.cap, w->keyShift, w->excl.p, w->nExcl, out);
     w->satLaunched = (long long)blocks_for(expect) * kThreads;
     w->launches++;
     return 0;
@@ -281,7 +282,7 @@ int prepare(avbd_world* w) {
         int shift = bits_for((unsigned long long)std::max(1, n - 1));
         if (shift != w->keyShift) {
             w->keyShift = shift;
-            if (w->nM > 0) { rekey_manifolds<<<blocks_for(w->nM), kThreads, 0, s>>>(w->mset(w->cur), w->nM, shift); w->launches++; }
+            if (w->nM > 0) { launch_dep(rekey_manifolds, dim3(blocks_for(w->nM)), dim3(kThreads), 0, s, w->mset(w->cur), w->nM, shift); w->launches++; }
             w->forcesDirty = true;   // exclusion keys are packed with keyShift too
         }
         w->graphValid = false;
@@ -338,11 +339,11 @@ int run_broadphase(avbd_world* w, bool sat) {
     w->nCand = 0; w->nPairs = 0;
     if (n == 0) return 0;
     BodyView bv = w->bview(); GridView gv = w->gview();
-    bp_cells<<<blocks_for(n), kThreads, 0, s>>>(bv, gv);
+    launch_dep(bp_cells, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv);
     int tbits = bits_for(w->tableSize);   // sentinel bucket == tableSize needs one more bit
     TRY(sort_pairs(w, w->cellKey.p, w->cellKeySorted.p, w->cellVal.p, w->cellValSorted.p, n, tbits));
     CK(cudaMemsetAsync(w->cellRange.p, 0, w->tableSize * sizeof(int2), s));
-    bp_cell_bounds<<<blocks_for(n), kThreads, 0, s>>>(bv, gv);
+    launch_dep(bp_cell_bounds, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv);
     w->launches += 2;
     if (w->pairs.cap == 0) TRY(w->pairs.ensure((size_t)std::max(1024, 12 * n), false, s));
     if (w->cand.cap == 0) { TRY(w->cand.ensure((size_t)std::max(1024, 3 * n), false, s)); TRY(w->candCode.ensure(w->cand.cap, false, s)); }
@@ -350,11 +351,11 @@ int run_broadphase(avbd_world* w, bool sat) {
         CK(cudaMemsetAsync(w->dCnt, 0, sizeof(Counters), s));
         PairSink raw; raw.keys = w->pairs.p; raw.codes = nullptr; raw.cap = (int)w->pairs.cap; raw.keyShift = w->keyShift;
         raw.count = &w->dCnt->nPairs; raw.cnt = w->dCnt; raw.overflowBit = 1;
-        bp_sweep<<<blocks_for(16ll * n), kThreads, 0, s>>>(bv, gv, raw);
-        if (w->nLarge) bp_large<<<blocks_for(n), kThreads, 0, s>>>(bv, gv, raw);
+        launch_dep(bp_sweep, dim3(blocks_for(16ll * n)), dim3(kThreads), 0, s, bv, gv, raw);
+        if (w->nLarge) launch_dep(bp_large, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, raw);
         w->launches += 1 + (w->nLarge ? 1 : 0);
         if (sat) {
-            if (w->nM > 0) { bp_persisting<<<blocks_for(w->nM), kThreads, 0, s>>>(bv, w->mset(w->cur), w->nM, raw); w->launches++; }
+            if (w->nM > 0) { launch_dep(bp_persisting, dim3(blocks_for(w->nM)), dim3(kThreads), 0, s, bv, w->mset(w->cur), w->nM, raw); w->launches++; }
             PairSink out; out.keys = w->cand.p; out.codes = w->candCode.p; out.cap = (int)std::min(w->cand.cap, w->candCode.cap); out.keyShift = w->keyShift;
             out.count = &w->dCnt->nCand; out.cnt = w->dCnt; out.overflowBit = 2;
             // sized by the pair count of the previous step (+ slack); the kernel reads the real count, a shortfall shows as overflow bit 16
@@ -398,12 +399,12 @@ int run_collide(avbd_world* w) {
             return true;
         }();
         (void)polySmem;
-        np_build<<<blocks_for(nSurv, kBuildThreads), kBuildThreads, kBuildThreads * kPolyFloatsPerThread * sizeof(float), s>>>(
+        launch_dep(np_build, dim3(blocks_for(nSurv, kBuildThreads)), dim3(kBuildThreads), kBuildThreads * kPolyFloatsPerThread * sizeof(float), s, 
             w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift, w->mset(w->cur), w->nM, w->mset(nxt), w->stage(), w->mcount.p, w->prm, w->dCnt);
         w->launches++;
         // live contacts packed densely in manifold order (the dual's and the visit lists' index space)
         TRY(exclusive_scan(w, w->mcount.p, w->mset(nxt).cstart, nSurv + 1));
-        np_compact<<<blocks_for(4ll * nSurv), kThreads, 0, s>>>(w->mset(nxt).hdr, w->mset(nxt).cstart, nSurv, w->stage(), w->mset(nxt), w->dCnt);
+        launch_dep(np_compact, dim3(blocks_for(4ll * nSurv)), dim3(kThreads), 0, s, w->mset(nxt).hdr, w->mset(nxt).cstart, nSurv, w->stage(), w->mset(nxt), w->dCnt);
         w->launches++;
         TRY(read_counters(w));
         w->nContacts = w->hCnt->nContacts;
@@ -416,7 +417,7 @@ int run_collide(avbd_world* w) {
     w->cur = nxt; w->nM = nSurv;
     ForceView fv = w->fview();
     if (fv.nJoints + fv.nSprings > 0) {
-        decay_user_forces<<<blocks_for(fv.nJoints + fv.nSprings), kThreads, 0, s>>>(fv, w->prm);
+        launch_dep(decay_user_forces, dim3(blocks_for(fv.nJoints + fv.nSprings)), dim3(kThreads), 0, s, fv, w->prm);
         w->launches++;
     }
     w->graphValid = sameTopology;
@@ -429,7 +430,7 @@ int run_collide(avbd_world* w) {
 int run_predict(avbd_world* w) {
     TRY(prepare(w));
     if (w->n == 0) return 0;
-    predict_bodies<<<blocks_for(w->n), kThreads, 0, w->stream>>>(w->bview(), w->prm, w->dDiag.p);
+    launch_dep(predict_bodies, dim3(blocks_for(w->n)), dim3(kThreads), 0, w->stream, w->bview(), w->prm, w->dDiag.p);
     w->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -445,9 +446,9 @@ int run_colour(avbd_world* w) {
     ManifoldSet ms = w->mset(w->cur);
     if (nM > 0) {
         TRY(w->bKey.ensure(nM, false, s)); TRY(w->bKeySorted.ensure(nM, false, s)); TRY(w->bVal.ensure(nM, false, s)); TRY(w->bList.ensure(nM, false, s));
-        adj_a_ranges<<<blocks_for(nM), kThreads, 0, s>>>(ms.hdr, nM, w->flags.p, n, w->adjRange.p, w->bKey.p, w->bVal.p);
+        launch_dep(adj_a_ranges, dim3(blocks_for(nM)), dim3(kThreads), 0, s, ms.hdr, nM, w->flags.p, n, w->adjRange.p, w->bKey.p, w->bVal.p);
         TRY(sort_pairs(w, w->bKey.p, w->bKeySorted.p, w->bVal.p, w->bList.p, nM, bits_for((unsigned long long)n)));
-        adj_b_ranges<<<blocks_for(nM), kThreads, 0, s>>>(w->bKeySorted.p, nM, n, w->adjRange.p);
+        launch_dep(adj_b_ranges, dim3(blocks_for(nM)), dim3(kThreads), 0, s, w->bKeySorted.p, nM, n, w->adjRange.p);
         w->launches += 2;
     } else {
         TRY(w->bList.ensure(1, false, s));
@@ -461,11 +462,11 @@ int run_colour(avbd_world* w) {
     if (incremental) {
         TRY(w->colourNext.ensure(n, false, s));
         CK(cudaMemcpyAsync(w->colourNext.p, w->colour.p, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));     // static bodies keep -2
-        colour_conflicts<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p,
+        launch_dep(colour_conflicts, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p,
                                                                   w->colourNext.p);
         std::swap(w->colour.p, w->colourNext.p); std::swap(w->colour.cap, w->colourNext.cap);
     } else {
-        colour_init<<<blocks_for(n), kThreads, 0, s>>>(w->flags.p, n, w->colour.p);
+        launch_dep(colour_init, dim3(blocks_for(n)), dim3(kThreads), 0, s, w->flags.p, n, w->colour.p);
     }
     w->launches++;
     w->colouredBodies = -1;
@@ -475,7 +476,7 @@ int run_colour(avbd_world* w) {
     // stragglers are compacted into a new list, so late rounds do not sweep a million coloured bodies to find a few thousand.
     if (w->nDyn <= kColourBlockMaxBodies) {
         // small world: every round in one block, no launches or host checks in between (the count is read with the colour ranges below)
-        colour_rounds_block<<<1, kColourBlockThreads, 0, s>>>(w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p, w->dCnt);
+        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p, w->dCnt);
         w->launches++;
     } else {
         const int* list = w->dynList.p; int listCount = w->nDyn; int which = 0;
@@ -483,7 +484,7 @@ int run_colour(avbd_world* w) {
             if (round > 4096) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
             CK(cudaMemsetAsync(&w->dCnt->nUncoloured, 0, sizeof(int), s));
             for (int k = 0; k < batch; ++k)
-                colour_round<<<blocks_for(listCount), kThreads, 0, s>>>(list, listCount, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p,
+                launch_dep(colour_round, dim3(blocks_for(listCount)), dim3(kThreads), 0, s, list, listCount, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p,
                                                                         w->dCnt, k == batch - 1);
             w->launches += batch; round += batch;
             TRY(read_counters(w));
@@ -493,7 +494,7 @@ int run_colour(avbd_world* w) {
                 DevBuf<int>& dst = which ? w->colWorkB : w->colWorkA;
                 TRY(dst.ensure((size_t)left, false, s));
                 CK(cudaMemsetAsync(&w->dCnt->nUncoloured, 0, sizeof(int), s));
-                colour_compact<<<blocks_for(listCount), kThreads, 0, s>>>(list, listCount, w->colour.p, dst.p, &w->dCnt->nUncoloured);
+                launch_dep(colour_compact, dim3(blocks_for(listCount)), dim3(kThreads), 0, s, list, listCount, w->colour.p, dst.p, &w->dCnt->nUncoloured);
                 w->launches++;
                 list = dst.p; listCount = left; which ^= 1;
             }
@@ -501,24 +502,24 @@ int run_colour(avbd_world* w) {
         }
     }
     w->colouredBodies = n;
-    colour_keys<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);
+    launch_dep(colour_keys, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);
     TRY(sort_pairs(w, w->colKey.p, w->colKeySorted.p, w->colVal.p, w->colOrder.p, w->nDyn, 7));
     CK(cudaMemsetAsync(w->colRange.p, 0, sizeof(int2) * 64, s));
-    colour_bounds<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);
+    launch_dep(colour_bounds, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);
     w->launches += 2;
     // contact visits in colour order (the primal's work list): visitStart[k] belongs to colOrder[k]
     TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
     TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
     w->visitGeomStale = true;
     CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
-    visit_count<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
+    launch_dep(visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
     TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
-    visit_fill<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
+    launch_dep(visit_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
     w->launches += 2;
     // first / last visit of every colour (the flat primal partitions a colour's visits, not its bodies)
     TRY(w->colVisit.ensure(64, false, s)); TRY(w->kOf.ensure(n, false, s));
-    colour_visit_bounds<<<1, 64, 0, s>>>(w->colRange.p, w->dCnt, w->visitStart.p, w->colVisit.p);
-    invert_order<<<blocks_for(w->nDyn), kThreads, 0, s>>>(w->colOrder.p, w->nDyn, w->kOf.p);
+    launch_dep(colour_visit_bounds, dim3(1), dim3(64), 0, s, w->colRange.p, w->dCnt, w->visitStart.p, w->colVisit.p);
+    launch_dep(invert_order, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->kOf.p);
     w->launches += 2;
     // ONE host round trip for everything the launches of the sweeps need: colour ranges, their visit ranges, counters
     CK(cudaMemcpyAsync(w->hColRange, w->colRange.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
@@ -546,7 +547,7 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f
     if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
         size_t cap = w->visits.cap;
         TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));
-        visit_geometry<<<blocks_for(2ll * w->nContacts), kThreads, 0, s>>>(w->visits.p, w->visitStart.p + w->nDyn, ms, w->vgeom());
+        launch_dep(visit_geometry, dim3(blocks_for(2ll * w->nContacts)), dim3(kThreads), 0, s, w->visits.p, w->visitStart.p + w->nDyn, ms, w->vgeom());
         w->launches++;
     }
     w->visitGeomStale = false;
@@ -581,10 +582,10 @@ int run_dual(avbd_world* w, float alpha, bool lastOfStep = false, bool contacts 
 int run_velocity(avbd_world* w) {
     cudaStream_t s = w->stream;
     if (w->n == 0) return 0;
-    velocity_bodies<<<blocks_for(w->n), kThreads, 0, s>>>(w->bview(), w->prm, w->dDiag.p);
+    launch_dep(velocity_bodies, dim3(blocks_for(w->n)), dim3(kThreads), 0, s, w->bview(), w->prm, w->dDiag.p);
     w->launches++;
     if (w->nContacts > 0 && !w->contactDiagDone) {     // not already reduced by the step's last dual pass
-        diagnostics_contacts<<<blocks_for(w->nContacts), kThreads, 0, s>>>(w->bview(), w->mset(w->cur), w->nContacts, w->dDiag.p);
+        launch_dep(diagnostics_contacts, dim3(blocks_for(w->nContacts)), dim3(kThreads), 0, s, w->bview(), w->mset(w->cur), w->nContacts, w->dDiag.p);
         w->launches++;
     }
     w->contactDiagDone = false;
@@ -917,7 +918,7 @@ int avbd_download_state(avbd_world* w, float* out) {
     CK(cudaSetDevice(w->device));
     int n = w->n; if (!n) return 0;
     TRY(w->stateDev.ensure((size_t)n * 13, false, w->stream));
-    pack_state<<<blocks_for(n), kThreads, 0, w->stream>>>(w->bview(), w->stateDev.p);
+    launch_dep(pack_state, dim3(blocks_for(n)), dim3(kThreads), 0, w->stream, w->bview(), w->stateDev.p);
     w->launches++;
     CK(cudaMemcpyAsync(out, w->stateDev.p, (size_t)n * 13 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
@@ -930,7 +931,7 @@ int avbd_upload_state(avbd_world* w, const float* in) {
     int n = w->n; if (!n) return 0;
     TRY(w->stateDev.ensure((size_t)n * 13, false, w->stream));
     CK(cudaMemcpyAsync(w->stateDev.p, in, (size_t)n * 13 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
-    unpack_state<<<blocks_for(n), kThreads, 0, w->stream>>>(w->bview(), w->stateDev.p);
+    launch_dep(unpack_state, dim3(blocks_for(n)), dim3(kThreads), 0, w->stream, w->bview(), w->stateDev.p);
     w->launches++;
     CK(cudaStreamSynchronize(w->stream));
     return 0;
@@ -1179,7 +1180,7 @@ int avbd_pick(avbd_world* w, const float* origin3, const float* dir3, float* loc
     unsigned long long* dBest = reinterpret_cast<unsigned long long*>(w->dCnt + 1);   // scratch slot after the counters
     unsigned long long init = ~0ull, best = ~0ull;
     CK(cudaMemcpyAsync(dBest, &init, sizeof(init), cudaMemcpyHostToDevice, w->stream));
-    pick_bodies<<<blocks_for(w->n), kThreads, 0, w->stream>>>(w->bview(), origin, rayDir, dBest);
+    launch_dep(pick_bodies, dim3(blocks_for(w->n)), dim3(kThreads), 0, w->stream, w->bview(), origin, rayDir, dBest);
     w->launches++;
     CK(cudaMemcpyAsync(&best, dBest, sizeof(best), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));

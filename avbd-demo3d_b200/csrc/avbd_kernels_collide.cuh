@@ -45,6 +45,7 @@ __device__ __forceinline__ int3 cell_of(float4 pos, float cell) {
 
 // K1a: bucket key per body.  Large bodies (flag) go to the sentinel bucket past the table.
 __global__ void bp_cells(BodyView b, GridView g) {
+    cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n) return;
     unsigned k = g.tableMask + 1u;
@@ -58,6 +59,7 @@ __global__ void bp_cells(BodyView b, GridView g) {
 
 // K1b: bucket boundaries in sorted order + sorted copies for the pair sweep.  cellRange must be zeroed first.
 __global__ void bp_cell_bounds(BodyView b, GridView g) {
+    cudaGridDependencySynchronize();
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= b.n) return;
     unsigned k = g.keySorted[p];
@@ -117,6 +119,7 @@ __device__ __forceinline__ int find_key(const unsigned long long* keys, int n, u
 // were most of this kernel's time).
 constexpr int kSweepStage = 1024;          // staged keys per block of 16 bodies (about 150 expected on a dense pile)
 __global__ void __launch_bounds__(kThreads) bp_sweep(BodyView b, GridView g, PairSink sink) {
+    cudaGridDependencySynchronize();
     __shared__ unsigned long long sKeys[kSweepStage];
     __shared__ int sCount, sBase;
     if (threadIdx.x == 0) sCount = 0;
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(kThreads) bp_sweep(BodyView b, GridView g, Pai
 
 // K1d: every body against the large bodies of its own world.
 __global__ void bp_large(BodyView b, GridView g, PairSink sink) {
+    cudaGridDependencySynchronize();
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= b.n) return;
     int w = b.worldId[j];
@@ -184,6 +188,7 @@ __global__ void bp_large(BodyView b, GridView g, PairSink sink) {
 // (solver.cpp:274-279 only deletes on initialize()==false).  Pairs whose spheres DO overlap were emitted by the sweeps
 // above; this kernel adds the rest (rare), so every candidate appears exactly once.
 __global__ void bp_persisting(BodyView b, ManifoldSet old, int nOld, PairSink sink) {
+    cudaGridDependencySynchronize();
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nOld) return;
     int4 h = old.hdr[m];
@@ -200,6 +205,7 @@ __global__ void bp_persisting(BodyView b, ManifoldSet old, int nOld, PairSink si
 // there); the pairs still alive are compacted in shared memory and the first nAlive threads run the 9 edge axes.
 __global__ void __launch_bounds__(kThreads) np_sat(BodyView b, const unsigned long long* cand, const int* nCand, int cap, int keyShift,
                                                    const unsigned long long* excl, int nExcl, PairSink out) {
+    cudaGridDependencySynchronize();
     __shared__ int sWarp[kThreads / 32], sBase;
     __shared__ int sAliveP[kThreads]; __shared__ float sAliveSep[kThreads]; __shared__ int sAliveK[kThreads];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -274,6 +280,7 @@ constexpr int kBuildThreads = 128;
 __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsigned long long* cand, const int* info, int nSurvive,
                                                           int keyShift, ManifoldSet old, int nOld, ManifoldSet out, ContactStage st, int* mcount,
                                                           SolveParams prm, Counters* cnt) {
+    cudaGridDependencySynchronize();
     extern __shared__ float sPoly[];
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nSurvive) return;
@@ -317,6 +324,7 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
 // K3c: pack the live contacts of the staging slots densely (ci = cstart[m] + c) and record each contact's manifold.
 // cstart is the exclusive scan of mcount over nM + 1 entries (mcount[nM] = 0), so cstart[nM] is the live contact count.
 __global__ void np_compact(const int4* hdr, const int* cstart, int nM, ContactStage st, ManifoldSet out, Counters* cnt) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 4 * nM) return;
     int m = t >> 2, c = t & 3;
@@ -330,6 +338,7 @@ __global__ void np_compact(const int4* hdr, const int* cstart, int nM, ContactSt
 // Stand-alone narrowphase on caller-supplied pairs (parity harness for
 // Manifold::collide, collision.cpp:420).  in: 2 x {size3 pos3 quat4} per pair.
 __global__ void np_collide_batch(const float* a10, const float* b10, int n, int* count, int* feats4, float* out36) {
+    cudaGridDependencySynchronize();
     extern __shared__ float sPoly[];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

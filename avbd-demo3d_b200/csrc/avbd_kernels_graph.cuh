@@ -12,6 +12,7 @@ namespace avbd {
 // run [x,y).  Its "I am B" manifolds are a run [z,w) of bList (manifold ids
 // stably sorted by B).  adjRange must be zeroed before these two kernels.
 __global__ void adj_a_ranges(const int4* hdr, int nM, const int* flags, int nBodies, int4* adjRange, unsigned* bKey, int* bVal) {
+    cudaGridDependencySynchronize();
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nM) return;
     int4 h = hdr[m];
@@ -21,6 +22,7 @@ __global__ void adj_a_ranges(const int4* hdr, int nM, const int* flags, int nBod
     bVal[m] = m;
 }
 __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, int4* adjRange) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nM) return;
     unsigned k = bKeySorted[t];
@@ -38,6 +40,7 @@ __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, in
 // first-visit: this is the visit of the contact that comes FIRST in a sweep (the other endpoint is static or has a higher
 // colour) — the one that applies the previous iteration's deferred dual update (avbd_solve.cu).
 __global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = colOrder[t];
@@ -49,6 +52,7 @@ __global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange,
 }
 __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
                            const int* visitStart, const BodyAux* aux, const int* colour, int4* visits) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = colOrder[t];
@@ -72,6 +76,7 @@ __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, 
 // iterations x colours primal sweeps stream it instead of gathering it — already in the VISITING body's frame:
 // a = {r_self, C0n}, b = {r_other, C0t.x}, n = {n, C0t.y}.  nVisits lives on the device (visitStart[nDyn]).
 __global__ void visit_geometry(const int4* __restrict__ visits, const int* __restrict__ nVisits, ManifoldSet ms, VisitGeom vg) {
+    cudaGridDependencySynchronize();
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= *nVisits) return;
     int4 e = visits[v];
@@ -94,6 +99,7 @@ __device__ __forceinline__ bool outranks(int localA, int localB) {
 }
 
 __global__ void colour_init(const int* flags, int n, int* colour) {
+    cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) colour[i] = (flags[i] & kDynamic) ? -1 : -2;
 }
@@ -134,6 +140,7 @@ __device__ __forceinline__ bool try_colour(int i, const int4* adjRange, const in
 
 __global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
                              ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt, bool countLeft) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     if (!try_colour(dynList[t], adjRange, bList, hdr, fv, localIdx, colour, cnt) && countLeft) {
@@ -147,6 +154,7 @@ __global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange,
 constexpr int kColourBlockThreads = 1024;
 __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
                                                                            ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt) {
+    cudaGridDependencySynchronize();
     int left = 1;
     for (int round = 0; round < 4096 && left; ++round) {
         int mine = 0;
@@ -163,6 +171,7 @@ __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const
 // instead of the ~17 a colouring from scratch needs.
 __global__ void colour_conflicts(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, ForceView fv,
                                  const int* localIdx, const int* colourPrev, int* colourOut) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = dynList[t];
@@ -189,6 +198,7 @@ __global__ void colour_conflicts(const int* dynList, int nDyn, const int4* adjRa
 
 // Work list of the bodies still uncoloured (order is irrelevant: the colouring does not depend on it).
 __global__ void colour_compact(const int* list, int n, const int* colour, int* out, int* outCount) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false; int i = 0;
     if (t < n) { i = list[t]; keep = colour[i] < 0; }
@@ -201,6 +211,7 @@ __global__ void colour_compact(const int* list, int n, const int* colour, int* o
 }
 
 __global__ void colour_keys(const int* dynList, int nDyn, const int* colour, unsigned* key, int* val) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = dynList[t];
@@ -209,6 +220,7 @@ __global__ void colour_keys(const int* dynList, int nDyn, const int* colour, uns
 }
 // colourRange[c] = {first, last+1} in the colour-sorted body order; must be zeroed first.
 __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourRange, Counters* cnt) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     unsigned c = keySorted[t];
@@ -220,6 +232,7 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
 // out[c] = {first visit, one past the last visit} of colour c (a colour's bodies, hence its visits, are contiguous); {0, 0} for
 // a colour incremental recolouring left empty.
 __global__ void colour_visit_bounds(const int2* colourRange, const Counters* cnt, const int* visitStart, int2* out) {
+    cudaGridDependencySynchronize();
     int c = threadIdx.x;
     if (c >= 64) return;
     int2 r = c < cnt->nColours ? colourRange[c] : make_int2(0, 0);
@@ -227,12 +240,14 @@ __global__ void colour_visit_bounds(const int2* colourRange, const Counters* cnt
 }
 
 __global__ void invert_order(const int* order, int n, int* positionOf) {
+    cudaGridDependencySynchronize();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) positionOf[order[k]] = k;
 }
 
 // ------------------------------------------------------------------ predict / warm-start decay of user forces
 __global__ void predict_bodies(BodyView b, SolveParams prm, Diag* diag) {
+    cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int dyn = 0, ev = 0, world = -1;
     if (i < b.n) {
@@ -253,6 +268,7 @@ __global__ void predict_bodies(BodyView b, SolveParams prm, Diag* diag) {
 }
 
 __global__ void decay_user_forces(ForceView fv, SolveParams prm) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < fv.nJoints) {
         JointRec& j = fv.joints[t];
@@ -265,6 +281,7 @@ __global__ void decay_user_forces(ForceView fv, SolveParams prm) {
 
 // ------------------------------------------------------------------ velocity + diagnostics
 __global__ void velocity_bodies(BodyView b, SolveParams prm, Diag* diag) {
+    cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float ls = 0.0f, as = 0.0f; int ev = 0; int world = -1;
     if (i < b.n) {
@@ -287,6 +304,7 @@ __global__ void velocity_bodies(BodyView b, SolveParams prm, Diag* diag) {
 
 // solver.cpp:472-497, one thread per live contact (only when the step's last dual pass did not already reduce them)
 __global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nContacts, Diag* diag) {
+    cudaGridDependencySynchronize();
     int ci = blockIdx.x * blockDim.x + threadIdx.x;
     float sepn = 0.0f, lam = 0.0f; int nm = 0, nv = 0; int world = -1;
     if (ci < nContacts) {
@@ -308,6 +326,7 @@ __global__ void diagnostics_contacts(BodyView b, ManifoldSet ms, int nContacts, 
 // Rigid public state <-> the 13-float-per-body host layout (pos3 quat4 lin3 ang3), on the device so the
 // host side of Solver::step() is one DMA each way.
 __global__ void pack_state(BodyView b, float* out13) {
+    cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n) return;
     BodyPose p = b.pose[i]; BodyVel v = b.vel[i];
@@ -316,6 +335,7 @@ __global__ void pack_state(BodyView b, float* out13) {
     o[7] = v.lin.x; o[8] = v.lin.y; o[9] = v.lin.z; o[10] = v.ang.x; o[11] = v.ang.y; o[12] = v.ang.z;
 }
 __global__ void unpack_state(BodyView b, const float* in13) {
+    cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n) return;
     const float* o = in13 + 13 * (size_t)i;
@@ -346,6 +366,7 @@ AVBD_HD bool ray_obb(V3 origin, V3 rayDir, V3 pos, Q4 rot, V3 size, float& tHit,
     return true;
 }
 __global__ void pick_bodies(BodyView b, V3 origin, V3 rayDir, unsigned long long* best) {
+    cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n) return;
     BodyPose p = b.pose[i];

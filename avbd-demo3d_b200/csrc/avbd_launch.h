@@ -27,6 +27,19 @@ struct ForceView {
 struct VisitGeom { float4* a; float4* b; float4* n; };
 
 #ifdef __CUDACC__
+// Programmatic dependent launch.  A step is a chain of ~50 (Stress1000) to ~200 (1M boxes) small dependent kernels on one
+// stream; launched this way a kernel may become resident while its predecessor drains, and waits at the
+// cudaGridDependencySynchronize() EVERY kernel of this library executes first, before it reads anything another kernel wrote
+// (no kernel triggers early, so the wait ends when the predecessor has completed and its writes are visible).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Diagnostics are kept per world (an ensemble batch reports each world separately).  Lanes of a warp that
 // belong to the same world combine first (match_any + masked reduce), then one atomic per (warp, world).
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {

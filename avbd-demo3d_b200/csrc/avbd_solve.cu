@@ -399,6 +399,7 @@ template <int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, int vBegin, int vEnd,
                                                              const int* __restrict__ kOf, float alpha, float alphaDual, float beta, float* __restrict__ sums,
                                                              float* __restrict__ carry) {
+    cudaGridDependencySynchronize();
     __shared__ FlatSmem<T> sm;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int nChunks = (vEnd - vBegin + T - 1) / T;
@@ -515,6 +516,7 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
 __global__ void __launch_bounds__(kThreads) primal_solve_flat(BodyView b, ForceView fv, const int* __restrict__ order, const int* __restrict__ vstart, int count,
                                                               int vBegin, int chunkT, const float* __restrict__ sums, const float* __restrict__ carry,
                                                               SolveParams prm, float* dxOut, Diag* diag) {
+    cudaGridDependencySynchronize();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     int i = order[k];
@@ -593,6 +595,7 @@ __device__ __forceinline__ DualOut dual_one(const BodyView& b, const ManifoldSet
 template <bool DIAG>
 __global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, int unvisitedReps,
                                                           bool onlyUnvisited, Diag* diag) {
+    cudaGridDependencySynchronize();
     int ci = blockIdx.x * blockDim.x + threadIdx.x;
     DualOut o{0.0f, 0.0f, 0, -1, 0};
     if (ci < nContacts) o = dual_one<false, DIAG>(b, ms, ci, prm, alpha, unvisitedReps, onlyUnvisited);
@@ -618,6 +621,7 @@ __global__ void __launch_bounds__(kThreads, 1) solve_loop_cluster(BodyView b, co
                                                                   ManifoldSet ms, ForceView fv, const int* __restrict__ order,
                                                                   const int2* __restrict__ colRange, int nColours, int nContacts, SolveParams prm,
                                                                   Diag* diag, bool contactDiag, bool anyUnvisited) {
+    cudaGridDependencySynchronize();
     __shared__ PrimalSmem<BPB> sm;
     const int rank = (int)cluster_rank(), nCta = (int)cluster_size();       // the grid is one cluster
     int total = prm.iterations + (prm.postStabilize ? 1 : 0);
@@ -652,6 +656,7 @@ __global__ void __launch_bounds__(kThreads, 1) solve_loop_cluster(BodyView b, co
 }
 
 __global__ void dual_user_forces(BodyView b, ForceView fv, SolveParams prm) {
+    cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < fv.nJoints) {
         JointRec& j = fv.joints[t];
@@ -697,6 +702,7 @@ __global__ void dual_user_forces(BodyView b, ForceView fv, SolveParams prm) {
 // Batched 6x6 solves on caller data (parity harness for solve6x6, solver.cpp:68-83).
 // lhs: ll la al aa blocks, each 9 floats column-major; only what the solve reads is used.
 __global__ void solve6_batch(const float* lhs36, const float* rhs6, int n, float* out6) {
+    cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* L = lhs36 + 36 * i; const float* r = rhs6 + 6 * i;
@@ -788,10 +794,11 @@ bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const 
     while (nCta < need && nCta < maxCluster) nCta <<= 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nCta); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = nCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;     // see launch_dep
+    cfg.attrs = attr; cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag, anyUnvisited);
     if (e != cudaSuccess && nCta > 8) {          // a 16-CTA cluster may not be placeable (MIG slices, busy GPCs): retry with the portable size
         cudaGetLastError();
@@ -803,11 +810,12 @@ bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const 
 }
 
 void launch_dual(cudaStream_t s, BodyView b, ManifoldSet ms, int nContacts, SolveParams prm, float alpha, int unvisitedReps, bool onlyUnvisited, Diag* diag) {
-    if (diag) dual_contacts<true><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, nContacts, prm, alpha, unvisitedReps, onlyUnvisited, diag);
-    else      dual_contacts<false><<<blocks_of(nContacts, kThreads), kThreads, 0, s>>>(b, ms, nContacts, prm, alpha, unvisitedReps, onlyUnvisited, nullptr);
+    Diag* none = nullptr;
+    if (diag) launch_dep(dual_contacts<true>, dim3(blocks_of(nContacts, kThreads)), dim3(kThreads), 0, s, b, ms, nContacts, prm, alpha, unvisitedReps, onlyUnvisited, diag);
+    else      launch_dep(dual_contacts<false>, dim3(blocks_of(nContacts, kThreads)), dim3(kThreads), 0, s, b, ms, nContacts, prm, alpha, unvisitedReps, onlyUnvisited, none);
 }
 void launch_dual_user_forces(cudaStream_t s, BodyView b, ForceView fv, SolveParams prm) {
-    dual_user_forces<<<blocks_of(fv.nJoints + fv.nSprings, kThreads), kThreads, 0, s>>>(b, fv, prm);
+    launch_dep(dual_user_forces, dim3(blocks_of(fv.nJoints + fv.nSprings, kThreads)), dim3(kThreads), 0, s, b, fv, prm);
 }
 void launch_solve6_batch(cudaStream_t s, const float* lhs36, const float* rhs6, int n, float* out6) {
     solve6_batch<<<blocks_of(n, 128), 128, 0, s>>>(lhs36, rhs6, n, out6);
