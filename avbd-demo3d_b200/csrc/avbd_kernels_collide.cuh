@@ -273,9 +273,8 @@ __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int 
 
 // K3b: build the manifold of each surviving pair at its final (key-sorted) slot, carrying lambda / penalty / stick
 // anchors over from last step's manifold of the same pair, then apply the per-step warm-start decay.  One thread per
-// manifold; contacts stream out of the builder one at a time straight into the 4-slot staging arrays (nothing is held in
-// per-thread arrays: the clipper's polygons live in shared memory, one column per thread), np_compact then packs the
-// live ones densely.
+// manifold; nothing is held in per-thread arrays (the clipper's polygons and the raw contacts live in shared memory, one
+// column per thread); finished contacts go to the 4-slot staging arrays and np_compact then packs the live ones densely.
 constexpr int kBuildThreads = 128;
 __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsigned long long* cand, const int* info, int nSurvive,
                                                           int keyShift, ManifoldSet old, int nOld, ManifoldSet out, ContactStage st, int* mcount,
@@ -303,18 +302,34 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (j < oldN) oldFeat[j] = f2i(old.lp[oldBase + j].p.w);
     }
-    unsigned used = 0u;
+    // Two passes so the expensive half runs converged: the builder's loops (clip, dedupe) reach their emit at different
+    // trip counts in every lane, so finishing a contact inside emit would serialise the lanes; emit only parks the raw contact
+    // (10 floats) in the clipper's second polygon buffer, which is free once the clipped polygon sits in the first, and a
+    // fixed-trip loop then runs Manifold::initialize's per-contact part for all lanes together, in emission order.
+    PolyShared poly{sPoly + threadIdx.x, (int)blockDim.x};
+    float* raw = sPoly + threadIdx.x + (size_t)(kMaxPoly * 3) * blockDim.x;            // buffer 1, this thread's column
+    const int rs = (int)blockDim.x;
     int n = 0;
-    auto loadOld = [&](int j) { return load_contact(old, oldBase + j); };
     auto emit = [&](int feature, V3 rA, V3 rB, V3 normal) {
-        ContactState ct = contact_initialize(posA, rotA, posB, rotB, feature, rA, rB, normal, oldN, oldFeat, used, loadOld, prm);
-        int ci = s * 4 + n;
-        st.cA[ci] = f4(ct.rA, ct.C0n); st.cB[ci] = f4(ct.rB, ct.C0t1); st.cN[ci] = f4(ct.n, ct.C0t2);
-        ContactLP q; q.l = pack_lambda(ct); q.p = pack_penalty(ct); st.lp[ci] = q;
+        float* q = raw + (size_t)(n * 10) * rs;
+        q[0] = i2f(feature); q[rs] = rA.x; q[2 * rs] = rA.y; q[3 * rs] = rA.z; q[4 * rs] = rB.x; q[5 * rs] = rB.y; q[6 * rs] = rB.z;
+        q[7 * rs] = normal.x; q[8 * rs] = normal.y; q[9 * rs] = normal.z;
         ++n;
     };
-    PolyShared poly{sPoly + threadIdx.x, (int)blockDim.x};
     build_contacts_emit(posA, rotA, xyz(sa), posB, rotB, xyz(sb), info[s], poly, emit);
+    unsigned used = 0u;
+    auto loadOld = [&](int j) { return load_contact(old, oldBase + j); };
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        if (c < n) {
+            const float* q = raw + (size_t)(c * 10) * rs;
+            ContactState ct = contact_initialize(posA, rotA, posB, rotB, f2i(q[0]), mk3(q[rs], q[2 * rs], q[3 * rs]), mk3(q[4 * rs], q[5 * rs], q[6 * rs]),
+                                                 mk3(q[7 * rs], q[8 * rs], q[9 * rs]), oldN, oldFeat, used, loadOld, prm);
+            int ci = s * 4 + c;
+            st.cA[ci] = f4(ct.rA, ct.C0n); st.cB[ci] = f4(ct.rB, ct.C0t1); st.cN[ci] = f4(ct.n, ct.C0t2);
+            ContactLP lpq; lpq.l = pack_lambda(ct); lpq.p = pack_penalty(ct); st.lp[ci] = lpq;
+        }
+    }
     float mu = sqrtf(sa.w * sb.w);                                   // manifold.cpp:73
     out.hdr[s] = make_int4(a, c, n, __float_as_int(mu));
     mcount[s] = n;
