@@ -363,21 +363,23 @@ constexpr int kSumStride = 28;
 // start known from the block index.  Blocks are persistent (grid = a few per SM, chunks round-robin) and load the NEXT chunk's
 // visit entry before working on the current one, so only the gathers (poses, lambda / penalty) remain on the critical path.
 //   phase 0  segment heads: lane v starts a segment when visit v-1 belongs to another body (entries carry the visiting body);
-//            ballot + per-warp counts -> compact list of the chunk's segments (start lane, body) in shared memory
+//            ballot -> each warp's compact list of the segments that start in its 32 visits (no barrier)
 //   phase 1  thread t takes visit base+t: computeConstraint (+ pending dual) + 3 rows -> 27 partial sums, one 112-byte row of
 //            shared memory per visit (7 x STS.128)
-//   phase 2  7 lanes per segment add the segment's run of rows in visit order, one float4 column each (LDS.128, 4 in flight)
+//   ---- the chunk's only block barrier (rows and segment lists are double buffered) ----
+//   phase 2  7 lanes per segment add the segment's run of rows in visit order, one float4 column each (LDS.128, 4 in flight);
+//            a warp sums the segments that start in its visits
 //   output   a segment that STARTS in the chunk writes sums[k], k = the body's position in the colour order; a segment continuing from the previous chunk (a body whose
 //            visits straddle a chunk boundary) writes carry[chunk] instead, and primal_solve_flat adds main + carries in
 //            chunk order — deterministic, no atomics, nothing to zero.
 constexpr int kFlatLanes = 7;                 // lanes per segment in phase 2 (one float4 = 4 of the 27(+1) components each)
 template <int T>
 struct FlatSmem {
-    float4 c[T][7];      // one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad — 128-bit stores / loads, row stride 28 words: conflict free
+    float4 c[2][T][7];   // one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad — 128-bit stores / loads, row stride 28 words: conflict free
     float4 stage[9][T];  // the NEXT chunk's gathered operands, filled by cp.async: self pose (2), other pose (2), geometry (3), lambda, penalty
-    int segStart[T + 1];
-    int segBody[T];
-    int warpCnt[T / 32];
+    unsigned char segPos[2][T / 32][32];     // per warp: chunk-local positions (< T <= 256) of the segment heads among its 32 visits
+    int segK[2][T / 32][32];       // ... and each segment's row of `sums` (complemented: goes to `carry`)
+    unsigned headMask[2][T / 32];
 };
 
 // cp.async (LDGSTS) of one 16-byte item into this thread's slot of the gather stage, with an L2 eviction policy.
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
     load_entry(vBegin + chunk * T + t, eCur, prevCur);
     load_entry(vBegin + chunk * T + t + stride, eNext, prevNext);
     issue_gathers(vBegin + chunk * T + t, eCur, kCur);
-    for (; chunk < nChunks; chunk += gridDim.x) {
+    for (int it = 0; chunk < nChunks; chunk += gridDim.x, ++it) {
         const int base = vBegin + chunk * T;
         const int v = base + t;
         const int4 e = eCur; const int prevZ = prevCur; const int kSelf = kCur;
@@ -450,22 +452,18 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
         eCur = eNext; prevCur = prevNext;
         issue_gathers(v + stride, eCur, kCur);                        // next chunk (its entry was loaded a whole chunk ago)
         load_entry(v + 2 * stride, eNext, prevNext);                  // the entry after that
-        // ---- phase 0: segment list
+        // ---- phase 0: this warp's segment heads (no barrier: each warp lists its own, the block barrier after phase 1 publishes them)
+        const int buf = it & 1;                                       // rows and segment lists are double buffered: ONE barrier per chunk
         int prevSelf = __shfl_up_sync(0xffffffffu, self, 1);
         if (lane == 0) prevSelf = prevZ >> 3;                         // -1 at the colour's first visit
         const bool head = live && (prevSelf != self || t == 0);       // lane 0 of the chunk always opens a segment (maybe a continuation)
         const unsigned heads = __ballot_sync(0xffffffffu, head);
-        if (lane == 0) sm.warpCnt[warp] = __popc(heads);
-        __syncthreads();
-        int segBase = 0, nSeg = 0;
-#pragma unroll
-        for (int wq = 0; wq < T / 32; ++wq) { int cnt = sm.warpCnt[wq]; if (wq < warp) segBase += cnt; nSeg += cnt; }
         if (head) {
-            int sidx = segBase + __popc(heads & ((1u << lane) - 1u));
-            sm.segStart[sidx] = t;
-            sm.segBody[sidx] = (t == 0 && prevSelf == self) ? ~kSelf : kSelf;    // complemented: continues the previous chunk's last segment
+            int r = __popc(heads & ((1u << lane) - 1u));
+            sm.segPos[buf][warp][r] = (unsigned char)t;
+            sm.segK[buf][warp][r] = (t == 0 && prevSelf == self) ? ~kSelf : kSelf;    // complemented: continues the previous chunk's last segment
         }
-        if (t == 0) { int liveCount = vEnd - base; sm.segStart[nSeg] = liveCount < T ? liveCount : T; }
+        if (lane == 0) sm.headMask[buf][warp] = heads;
         // ---- phase 1
         if (live) {
             bool gyro = (e.z & 2) != 0, pending = alphaDual >= 0.0f && (e.z & 4) != 0;
@@ -482,7 +480,7 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
             float4 nl = pack_lambda(cs);
             if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); *lp = q; }
             else if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) lp->l = nl;
-            float4* row = sm.c[t];
+            float4* row = sm.c[buf][t];
             row[0] = make_float4(sys.rl[0], sys.rl[1], sys.rl[2], sys.ra[0]);
             row[1] = make_float4(sys.ra[1], sys.ra[2], sys.ll[0], sys.ll[1]);
             row[2] = make_float4(sys.ll[2], sys.ll[3], sys.ll[4], sys.ll[5]);
@@ -491,23 +489,29 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
             row[5] = make_float4(sys.la[8], sys.aa[0], sys.aa[1], sys.aa[2]);
             row[6] = make_float4(sys.aa[3], sys.aa[4], sys.aa[5], 0.0f);
         }
-        __syncthreads();
-        // ---- phase 2
-        for (int wi = t; wi < nSeg * kFlatLanes; wi += T) {
-            int sgi = wi / kFlatLanes, j = wi - sgi * kFlatLanes;
-            int lv = sm.segStart[sgi], z = sm.segStart[sgi + 1];
-            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            auto add = [&](float4 x) { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; };
-            for (; lv + 4 <= z; lv += 4) {
-                float4 x0 = sm.c[lv][j], x1 = sm.c[lv + 1][j], x2 = sm.c[lv + 2][j], x3 = sm.c[lv + 3][j];
-                add(x0); add(x1); add(x2); add(x3);
+        __syncthreads();          // the only barrier of the chunk: buffer `buf` is next written two chunks on, i.e. after the NEXT barrier
+        // ---- phase 2: each warp sums the segments that START in its 32 visits (their rows may run on into later warps')
+        {
+            const int nSegW = __popc(heads);
+            int liveCount = vEnd - base; if (liveCount > T) liveCount = T;
+            int tailEnd = liveCount;                                  // where this warp's last segment ends: the next head of a later warp
+#pragma unroll
+            for (int w2 = T / 32 - 1; w2 >= 1; --w2) { unsigned m = sm.headMask[buf][w2]; if (w2 > warp && m) tailEnd = w2 * 32 + __ffs(m) - 1; }
+            for (int wi = lane; wi < nSegW * kFlatLanes; wi += 32) {
+                int sgi = wi / kFlatLanes, j = wi - sgi * kFlatLanes;
+                int lv = sm.segPos[buf][warp][sgi], z = sgi + 1 < nSegW ? sm.segPos[buf][warp][sgi + 1] : tailEnd;
+                float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                auto add = [&](float4 x) { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; };
+                for (; lv + 4 <= z; lv += 4) {
+                    float4 x0 = sm.c[buf][lv][j], x1 = sm.c[buf][lv + 1][j], x2 = sm.c[buf][lv + 2][j], x3 = sm.c[buf][lv + 3][j];
+                    add(x0); add(x1); add(x2); add(x3);
+                }
+                for (; lv < z; ++lv) add(sm.c[buf][lv][j]);
+                int idx = sm.segK[buf][warp][sgi];          // position in the colour order, complemented for a continuation
+                float* o = idx >= 0 ? sums + (size_t)idx * kSumStride : carry + (size_t)chunk * kSumStride;
+                reinterpret_cast<float4*>(o)[j] = acc;
             }
-            for (; lv < z; ++lv) add(sm.c[lv][j]);
-            int idx = sm.segBody[sgi];                  // position in the colour order, complemented for a continuation
-            float* o = idx >= 0 ? sums + (size_t)idx * kSumStride : carry + (size_t)chunk * kSumStride;
-            reinterpret_cast<float4*>(o)[j] = acc;
         }
-        __syncthreads();
     }
 }
 
