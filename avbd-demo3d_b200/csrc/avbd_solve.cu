@@ -145,7 +145,11 @@ __device__ __forceinline__ void dual_fast(ContactState& c, const ContactEval& e,
 // contact_system_w of avbd_rows.cuh without the "does the row add stiffness" test (solver.cpp:381): a manifold row's penalty is
 // always in [PENALTY_MIN, MANIFOLD_PENALTY_CAP] on the device (set at creation, clamped by the warm-start decay and by the ramp,
 // whose fminf maps a NaN to the cap).
+// The 27 products per row are issued as packed pairs (Blackwell's fma.rn.f32x2 / mul.rn.f32x2: two IEEE FP32 operations per
+// issue slot, each lane rounded exactly like the scalar instruction) in the order of the shared-memory row the visit kernel
+// stores: rl0 rl1 | rl2 ra0 | ra1 ra2 | ll0 ll1 | ll2 ll3 | ll4 ll5 | la0 la1 | la2 la3 | la4 la5 | la6 la7 | la8 aa0 | aa1 aa2 | aa3 aa4 | aa5 -.
 __device__ __forceinline__ void system_fast(BodySystem& s, const ContactState& c, const ContactEval& e, V3 w, float sg, bool gyro, const M3& invIw) {
+    float2 v[14];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         V3 Jl = e.basis[r];
@@ -153,37 +157,29 @@ __device__ __forceinline__ void system_fast(BodySystem& s, const ContactState& c
         float f0 = clampq(c.pen[r] * e.C[r] + c.lam[r], e.fmin[r], e.fmax[r]);
         float f = f0 * sg;
         float pen = c.pen[r];
-        float lp[3] = {Jl.x * pen, Jl.y * pen, Jl.z * pen}, ap[3] = {Ja.x * pen, Ja.y * pen, Ja.z * pen};
-        float jl[3] = {Jl.x, Jl.y, Jl.z}, ja[3] = {Ja.x, Ja.y, Ja.z};
-        if (r == 0) {
-            s.rl[0] = Jl.x * f; s.rl[1] = Jl.y * f; s.rl[2] = Jl.z * f;
-            s.ra[0] = Ja.x * f; s.ra[1] = Ja.y * f; s.ra[2] = Ja.z * f;
-            s.ll[0] = lp[0] * jl[0]; s.ll[1] = lp[1] * jl[0]; s.ll[2] = lp[2] * jl[0];
-            s.ll[3] = lp[1] * jl[1]; s.ll[4] = lp[2] * jl[1]; s.ll[5] = lp[2] * jl[2];
-            s.aa[0] = ap[0] * ja[0]; s.aa[1] = ap[1] * ja[0]; s.aa[2] = ap[2] * ja[0];
-            s.aa[3] = ap[1] * ja[1]; s.aa[4] = ap[2] * ja[1]; s.aa[5] = ap[2] * ja[2];
+        float2 pp = make_float2(pen, pen), ff = make_float2(f, f);
+        float2 lxy = __fmul2_rn(make_float2(Jl.x, Jl.y), pp), lzq = __fmul2_rn(make_float2(Jl.z, Ja.x), pp), qbc = __fmul2_rn(make_float2(Ja.y, Ja.z), pp);
+        const float px = lxy.x, py = lxy.y, pz = lzq.x, qa = lzq.y, qb = qbc.x, qc = qbc.y;       // pen * Jl, pen * Ja
+        const float2 A[14] = {make_float2(Jl.x, Jl.y), make_float2(Jl.z, Ja.x), make_float2(Ja.y, Ja.z),
+                              make_float2(px, py), make_float2(pz, py), make_float2(pz, pz),
+                              make_float2(px, px), make_float2(px, py), make_float2(py, py), make_float2(pz, pz),
+                              make_float2(pz, qa), make_float2(qb, qc), make_float2(qb, qc), make_float2(qc, 0.0f)};
+        const float2 B[14] = {ff, ff, ff,
+                              make_float2(Jl.x, Jl.x), make_float2(Jl.x, Jl.y), make_float2(Jl.y, Jl.z),
+                              make_float2(Ja.x, Ja.y), make_float2(Ja.z, Ja.x), make_float2(Ja.y, Ja.z), make_float2(Ja.x, Ja.y),
+                              make_float2(Ja.z, Ja.x), make_float2(Ja.x, Ja.x), make_float2(Ja.y, Ja.y), make_float2(Ja.z, 0.0f)};
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) s.la[i * 3 + k] = lp[i] * ja[k];
-        } else {
-            s.rl[0] += Jl.x * f; s.rl[1] += Jl.y * f; s.rl[2] += Jl.z * f;
-            s.ra[0] += Ja.x * f; s.ra[1] += Ja.y * f; s.ra[2] += Ja.z * f;
-            s.ll[0] += lp[0] * jl[0]; s.ll[1] += lp[1] * jl[0]; s.ll[2] += lp[2] * jl[0];
-            s.ll[3] += lp[1] * jl[1]; s.ll[4] += lp[2] * jl[1]; s.ll[5] += lp[2] * jl[2];
-            s.aa[0] += ap[0] * ja[0]; s.aa[1] += ap[1] * ja[0]; s.aa[2] += ap[2] * ja[0];
-            s.aa[3] += ap[1] * ja[1]; s.aa[4] += ap[2] * ja[1]; s.aa[5] += ap[2] * ja[2];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) s.la[i * 3 + k] += lp[i] * ja[k];
-        }
+        for (int q = 0; q < 14; ++q) v[q] = r == 0 ? __fmul2_rn(A[q], B[q]) : __ffma2_rn(A[q], B[q], v[q]);
         if (gyro) {                                              // solver.cpp:393-397; exactly zero for isotropic inertia
             V3 g = vabs(cross(Ja, mv(invIw, Ja)));
             float af = fabsf(f0);
-            s.aa[0] += g.x * af; s.aa[3] += g.y * af; s.aa[5] += g.z * af;
+            v[10].y += g.x * af; v[12].x += g.y * af; v[13].x += g.z * af;
         }
     }
+    s.rl[0] = v[0].x; s.rl[1] = v[0].y; s.rl[2] = v[1].x; s.ra[0] = v[1].y; s.ra[1] = v[2].x; s.ra[2] = v[2].y;
+    s.ll[0] = v[3].x; s.ll[1] = v[3].y; s.ll[2] = v[4].x; s.ll[3] = v[4].y; s.ll[4] = v[5].x; s.ll[5] = v[5].y;
+    s.la[0] = v[6].x; s.la[1] = v[6].y; s.la[2] = v[7].x; s.la[3] = v[7].y; s.la[4] = v[8].x; s.la[5] = v[8].y; s.la[6] = v[9].x; s.la[7] = v[9].y;
+    s.la[8] = v[10].x; s.aa[0] = v[10].y; s.aa[1] = v[11].x; s.aa[2] = v[11].y; s.aa[3] = v[12].x; s.aa[4] = v[12].y; s.aa[5] = v[13].x;
 }
 // One contact visit in the visiting body's frame: computeConstraint (with the pending dual update first), then the 3 rows'
 // contribution to the body's 6x6 system.  `sp,sq` / `op,oq` = self / other pose, g0 g1 g2 = {r_self,C0n} {r_other,C0t.x} {n,C0t.y}.
@@ -501,7 +497,10 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
                 int sgi = wi / kFlatLanes, j = wi - sgi * kFlatLanes;
                 int lv = sm.segPos[buf][warp][sgi], z = sgi + 1 < nSegW ? sm.segPos[buf][warp][sgi + 1] : tailEnd;
                 float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                auto add = [&](float4 x) { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; };
+                auto add = [&](float4 x) {                   // two packed adds (add.rn.f32x2) instead of four scalar ones
+                    float2 lo = __fadd2_rn(make_float2(acc.x, acc.y), make_float2(x.x, x.y)), hi = __fadd2_rn(make_float2(acc.z, acc.w), make_float2(x.z, x.w));
+                    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+                };
                 for (; lv + 4 <= z; lv += 4) {
                     float4 x0 = sm.c[buf][lv][j], x1 = sm.c[buf][lv + 1][j], x2 = sm.c[buf][lv + 2][j], x3 = sm.c[buf][lv + 3][j];
                     add(x0); add(x1); add(x2); add(x3);
