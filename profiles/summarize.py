@@ -64,13 +64,20 @@ def traffic(path):
     ki, ri, wi, ti = H.index("Kernel Name"), H.index("dram__bytes_read.sum"), H.index("dram__bytes_write.sum"), H.index("gpu__time_duration.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     visit = solve = 0.0; nv = ns = 0; dual = 0.0; nd = 0
+    gi, lastGrid, done = H.index("launch__grid_size"), None, False
     for r in rows[2:]:
         bytes_ = float(r[ri].replace(",", "")) * scale[U[ri]] + float(r[wi].replace(",", "")) * scale[U[wi]]
-        if "primal_visit" in r[ki]: visit += bytes_; nv += 1
-        elif "primal_solve" in r[ki]: solve += bytes_; ns += 1
+        if "primal_visit" in r[ki]:
+            # ONE whole iteration (every colour once): colours come largest first, so a grid that grows again starts the next iteration
+            grid = int(r[gi].replace(",", ""))
+            if lastGrid is not None and grid > lastGrid: done = True
+            lastGrid = grid
+            if not done: visit += bytes_; nv += 1
+        elif "primal_solve" in r[ki]:
+            if not done: solve += bytes_; ns += 1
         elif "dual_contacts" in r[ki]: dual += bytes_; nd += 1
     sweeps = max(ns, 1)
-    print(json.dumps({"source": path.split("/")[-1], "how": "ncu --set full --clock-control none (cold caches, serialised launches), 1M-box pre-stacked grid, first sweeps of one step",
+    print(json.dumps({"source": path.split("/")[-1], "how": "ncu --set full --clock-control none (cold caches, serialised launches), 1M-box pre-stacked grid, the first iteration (every colour once) of one step",
                       "colour_sweeps_captured": sweeps, "visit_kernel_launches": nv, "dram_bytes_per_colour_sweep": (visit + solve) / sweeps,
                       "visit_kernel_bytes_per_colour_sweep": visit / sweeps, "solve_kernel_bytes_per_colour_sweep": solve / sweeps,
                       "dual_pass_bytes": dual / nd if nd else None}, indent=1))
