@@ -6,7 +6,7 @@ tag=${1:-r01}; shift
 what=${@:-launches solve collide}
 mkdir -p gpurun_out
 export AVBD_PROFILE_RANGE=1
-T="python tests/profile_target.py grid100 1"
+T="python tools/profile_target.py grid100 1"
 NCU="ncu --clock-control none --profile-from-start off"
 for w in $what; do case $w in
 launches)  # every launch of ONE steady-state step with its device time
