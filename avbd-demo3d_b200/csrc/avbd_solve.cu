@@ -240,21 +240,62 @@ struct PrimalSmem {
     int body[BPB];
 };
 
+// What a tile reads that does not change during a step's iteration loop: its bodies, their visit runs and inertial targets,
+// the visit entries and the contact geometry.  The cluster loop keeps it in shared memory across the whole loop: a cluster
+// barrier carries a gpu-scope fence and an L1 invalidation (CCTL.IVALL), so without the copy every one of the ~100 phases of a
+// step would walk the chain visitStart -> visit entry -> geometry through L2 again (two dependent round trips per phase).
+template <int BPB>
+struct TileCache {
+    int4 visit[kThreads];
+    float4 a[kThreads], b[kThreads], n[kThreads];      // cA cB cN of the visit's contact (A / B frame)
+    float4 posI[BPB], rotI[BPB], mass[BPB], inert[BPB];
+    int vs[BPB + 1]; int body[BPB];
+    int usable, pad[2];                                 // 0: the tile's run does not fit (more than kThreads visits) -> read from global
+};
+template <int BPB>
+__device__ __forceinline__ void fill_tile_cache(TileCache<BPB>& tc, const BodyView& b, const int* __restrict__ vstart, const int4* __restrict__ visits,
+                                                const ManifoldSet& ms, const int* __restrict__ order, int count, int tile) {
+    const int t = threadIdx.x;
+    const int k0 = tile * BPB;
+    const int nb = (count - k0) < BPB ? (count - k0) : BPB;
+    if (t <= nb) tc.vs[t] = vstart[k0 + t];
+    __syncthreads();
+    const int v0 = tc.vs[0], v1 = tc.vs[nb];
+    const bool fits = v1 - v0 <= kThreads;
+    if (t == 0) tc.usable = fits ? 1 : 0;
+    if (fits) {
+        if (t < nb) {
+            int i = order[k0 + t];
+            tc.body[t] = i;
+            BodyAux aux = b.aux[i];
+            tc.posI[t] = aux.posI; tc.rotI[t] = aux.rotI; tc.mass[t] = aux.mass; tc.inert[t] = aux.inert;
+        }
+        if (v0 + t < v1) {
+            int4 e = visits[v0 + t];
+            tc.visit[t] = e; tc.a[t] = ms.cA[e.x]; tc.b[t] = ms.cB[e.x]; tc.n[t] = ms.cN[e.x];
+        }
+    }
+    __syncthreads();
+}
+
 template <int BPB, bool COH>
 __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int* __restrict__ vstart, const int4* __restrict__ visits,
                                                    const ManifoldSet& ms, const ForceView& fv, const int* __restrict__ order, int count, int tile,
-                                                   const SolveParams& prm, float alpha, float alphaDual, float* dxOut, Diag* diag, PrimalSmem<BPB>& sm) {
+                                                   const SolveParams& prm, float alpha, float alphaDual, float* dxOut, Diag* diag, PrimalSmem<BPB>& sm,
+                                                   const TileCache<BPB>* tc = nullptr) {
     constexpr int L = kThreads / BPB;
     constexpr int CPL = (27 + L - 1) / L;
     const int t = threadIdx.x;
     const int k0 = tile * BPB;
     const int nb = (count - k0) < BPB ? (count - k0) : BPB;
-    if (t <= nb) sm.vs[t] = vstart[k0 + t];
+    if (t <= nb) sm.vs[t] = tc ? tc->vs[t] : vstart[k0 + t];
     if (t < nb) {
-        int i = order[k0 + t];
+        int i = tc ? tc->body[t] : order[k0 + t];
         sm.body[t] = i;
         BodyPose self = load_pose<COH>(b.pose + i);
-        BodyAux aux = b.aux[i];
+        BodyAux aux;
+        if (tc) { aux.posI = tc->posI[t]; aux.rotI = tc->rotI[t]; aux.mass = tc->mass[t]; aux.inert = tc->inert[t]; }
+        else aux = b.aux[i];
         sm.pos[t] = self.pos; sm.rot[t] = self.rot; sm.posI[t] = aux.posI; sm.rotI[t] = aux.rotI; sm.mass[t] = aux.mass;
         V3 I = xyz(aux.inert);
         // isotropic inertia: R diag(c) R^T = c*Id, so Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero; skip the term
@@ -277,11 +318,13 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
     for (int base = v0; base < v1; base += kThreads) {
         int v = base + t;
         if (v < v1) {
-            int4 e = visits[v];
+            int4 e = tc ? tc->visit[v - v0] : visits[v];
             int ci = e.x; bool isA = (e.z & 1) != 0;
             BodyPose po = load_pose<COH>(b.pose + e.y);
-            float4 a4 = ms.cA[ci], b4 = ms.cB[ci], n4 = ms.cN[ci];
             float4 l4 = ld4<COH>(&ms.lp[ci].l), p4 = ld4<COH>(&ms.lp[ci].p);
+            float4 a4, b4, n4;
+            if (tc) { a4 = tc->a[v - v0]; b4 = tc->b[v - v0]; n4 = tc->n[v - v0]; }
+            else { a4 = ms.cA[ci]; b4 = ms.cB[ci]; n4 = ms.cN[ci]; }
             int lo = 0, hi = nb;                                  // slot: vs[lo] <= v < vs[lo + 1]
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.vs[mid] <= v) lo = mid; else hi = mid; }
             float4 sp = sm.pos[lo], sr = sm.rot[lo];
@@ -623,19 +666,32 @@ template <int BPB>
 __global__ void __launch_bounds__(kThreads, 1) solve_loop_cluster(BodyView b, const int* __restrict__ visitStart, const int4* __restrict__ visits,
                                                                   ManifoldSet ms, ForceView fv, const int* __restrict__ order,
                                                                   const int2* __restrict__ colRange, int nColours, int nContacts, SolveParams prm,
-                                                                  Diag* diag, bool contactDiag, bool anyUnvisited) {
+                                                                  Diag* diag, bool contactDiag, bool anyUnvisited, int nSlots) {
     cudaGridDependencySynchronize();
     __shared__ PrimalSmem<BPB> sm;
+    extern __shared__ __align__(16) unsigned char dynSmem[];
+    TileCache<BPB>* slots = reinterpret_cast<TileCache<BPB>*>(dynSmem);      // nSlots of them: this CTA's first tiles, in processing order
     const int rank = (int)cluster_rank(), nCta = (int)cluster_size();       // the grid is one cluster
     int total = prm.iterations + (prm.postStabilize ? 1 : 0);
+    {
+        int slot = 0;
+        for (int c = 0; c < nColours && slot < nSlots; ++c) {
+            int2 r = colRange[c];
+            int count = r.y - r.x;
+            for (int tile = rank; tile * BPB < count && slot < nSlots; tile += nCta, ++slot)
+                fill_tile_cache<BPB>(slots[slot], b, visitStart + r.x, visits, ms, order + r.x, count, tile);
+        }
+    }
     float alphaDual = -1.0f;                                    // dual pass of the previous iteration still to apply (deferred dual)
     for (int it = 0; it < total; ++it) {
         float alpha = prm.postStabilize ? (it < prm.iterations ? 1.0f : 0.0f) : prm.alpha;      // solver.cpp:340-342
+        int slot = 0;
         for (int c = 0; c < nColours; ++c) {
             int2 r = colRange[c];
             int count = r.y - r.x;
-            for (int tile = rank; tile * BPB < count; tile += nCta) {
-                primal_tile_visits<BPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, alphaDual, nullptr, diag, sm);
+            for (int tile = rank; tile * BPB < count; tile += nCta, ++slot) {
+                const TileCache<BPB>* tc = (slot < nSlots && slots[slot].usable) ? &slots[slot] : nullptr;
+                primal_tile_visits<BPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, alphaDual, nullptr, diag, sm, tc);
                 __syncthreads();
             }
             cluster_barrier();
@@ -790,24 +846,39 @@ bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const 
         if (const char* e = getenv("AVBD_CLUSTER_MAX")) { int v = atoi(e); if (v >= 1 && v <= 16) return v; }
         return 16;
     }();
+    // shared-memory slots for the tile cache: whatever the SM has left next to the kernel's static shared memory
+    static int maxSlots = [] {
+        int dev = 0, optin = 0; cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa{}; cudaFuncGetAttributes(&fa, solve_loop_cluster<BPB>);
+        long long room = (long long)optin - (long long)fa.sharedSizeBytes - 1024;
+        int n = room > 0 ? (int)(room / (long long)sizeof(TileCache<BPB>)) : 0;
+        if (const char* e = getenv("AVBD_TILE_CACHE_SLOTS")) n = atoi(e) < n ? atoi(e) : n;
+        if (n > 0 && cudaFuncSetAttribute(solve_loop_cluster<BPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * (int)sizeof(TileCache<BPB>)) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        return n;
+    }();
     int want = blocks_of(maxColourCount, BPB);
     int wantDual = blocks_of(nContacts, kThreads);
     int need = want > wantDual ? want : wantDual;
     int nCta = 1;
     while (nCta < need && nCta < maxCluster) nCta <<= 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nCta); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    // a CTA runs ceil(tiles of a colour / nCta) tiles per colour: no point in more slots than it has tiles
+    int tilesPerCta = 0;
+    for (int c = 0; c < nColours; ++c) tilesPerCta += (blocks_of(maxColourCount, BPB) + nCta - 1) / nCta;      // upper bound (largest colour for all)
+    int nSlots = tilesPerCta < maxSlots ? tilesPerCta : maxSlots;
+    cfg.gridDim = dim3(nCta); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)nSlots * sizeof(TileCache<BPB>); cfg.stream = s;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = nCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;     // see launch_dep
     cfg.attrs = attr; cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag, anyUnvisited);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag, anyUnvisited, nSlots);
     if (e != cudaSuccess && nCta > 8) {          // a 16-CTA cluster may not be placeable (MIG slices, busy GPCs): retry with the portable size
         cudaGetLastError();
         maxCluster = 8;
         attr[0].val.clusterDim.x = 8; cfg.gridDim = dim3(8);
-        e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag, anyUnvisited);
+        e = cudaLaunchKernelEx(&cfg, solve_loop_cluster<BPB>, b, visitStart, visits, ms, fv, order, colRange, nColours, nContacts, prm, diag, contactDiag, anyUnvisited, nSlots);
     }
     return e == cudaSuccess;
 }
