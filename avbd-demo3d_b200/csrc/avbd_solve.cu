@@ -3,7 +3,9 @@
 // tolerance against the reference (BASELINE.json north_star), unlike the collision path in avbd_engine.cu.
 //
 // The reference walks bodies serially (Gauss-Seidel, solver.cpp:344); here bodies of one colour share no
-// manifold, so a colour is solved in one launch, one contact visit (computeConstraint + 3 rows) per thread.
+// manifold, so a colour is one parallel phase, one contact visit (computeConstraint + 3 rows) per thread:
+//   large worlds   per colour primal_visit_flat (flat visit partition -> per-body sums) + primal_solve_flat (block solve)
+//   small worlds   solve_loop_cluster: the whole iteration loop in one thread-block cluster, a tile of bodies per CTA and phase
 //
 // Deferred dual.  The dual / penalty-ramp pass of iteration k (solver.cpp:411-430) reads the poses left by sweep k, and
 // nothing moves between it and sweep k+1.  When sweep k+1 reaches the FIRST visit of a contact (its other endpoint is
@@ -217,10 +219,11 @@ template <bool COH> __device__ __forceinline__ ContactState load_contact_c(const
     return unpack_contact(ms.cA[ci], ms.cB[ci], ms.cN[ci], ld4<COH>(&ms.lp[ci].l), ld4<COH>(&ms.lp[ci].p));
 }
 
-// ------------------------------------------------------------------ primal, visit-parallel (the large-world path)
+// ------------------------------------------------------------------ primal, one tile of bodies (the cluster loop's phase)
 // The visit list is laid out in colour order, so the visits of a tile of BPB consecutive bodies of one colour are ONE
 // contiguous run.  The tile walks that run one visit per thread (every lane busy, every lane's gathers independent
-// and in flight together — the kernel is latency bound otherwise):
+// and in flight together) and solves its bodies in the same call — small worlds are latency bound, a phase must not
+// be split over launches.  (Large worlds use the flat visit partition further down.)
 //   phase 0  thread t < BPB stages body t of the tile in shared memory (pose, inertial target, mass, inverse inertia)
 //   phase 1  thread t takes visit base+t: computeConstraint + 3 rows -> its 27 partial sums, parked transposed in
 //            shared memory (row stride 257: conflict free)
@@ -653,8 +656,8 @@ __global__ void __launch_bounds__(kThreads) dual_contacts(BodyView b, ManifoldSe
 // each, so per-colour launches pay two launch latencies per phase and a grid-wide atomic barrier is no cheaper.  This
 // kernel runs the WHOLE loop of solver.cpp:340-431 in one launch of ONE thread-block cluster (up to 16 CTAs on the SMs
 // of one GPC): phases are separated by the hardware cluster barrier (barrier.cluster, release / acquire at cluster
-// scope) instead of a kernel boundary, and each phase is the visit-parallel tile of the large-world path (one contact
-// visit per thread, in-order shared-memory sums, block solve).  Data other CTAs write between barriers (poses, lambda,
+// scope) instead of a kernel boundary, and each phase is the tile routine above (one contact visit per thread, in-order
+// shared-memory sums, block solve) on tiles whose static inputs the CTA caches in shared memory (TileCache).  Data other CTAs write between barriers (poses, lambda,
 // penalty) is read with ld.global.cg (L2); stores are write-through.
 __device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
