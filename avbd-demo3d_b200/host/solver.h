@@ -84,6 +84,7 @@ struct Solver {                      // solver.h:146-181
 
     // ---- extensions (not in the reference) ----
     void refreshManifolds();         // rebuilds the Manifold mirrors in `forces` from the device (contacts, lambda, penalty)
+    void syncToDevice();             // uploads parameters, host edits, new bodies and new user forces (step() and pick() call it)
     avbd_world* world;               // the device world behind this Solver
     int device;
     bool rebuild;                    // a body or force was deleted: re-upload everything at the next step

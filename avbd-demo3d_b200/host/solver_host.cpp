@@ -191,7 +191,6 @@ Joint::Joint(Solver* s, Rigid* a, Rigid* b, const vec3& la, const vec3& lb, floa
     initialRelativeOrientation = conjugate(qa) * b->orientation;
     for (int i = 0; i < 6; ++i) { stiffness[i] = i < 3 ? linK : angK; lambda[i] = 0; penalty[i] = PENALTY_MIN; }
     angularStiffness = angK; angularMotor = motor_; angularFracture = fracture_;
-    s->userForces.push_back(this);
 }
 Joint::Joint(Solver* s, Rigid* b, const vec3& worldAnchor, float linK, float angK, float motor_, float fracture_)
     : Force(s, nullptr, b) {                                             // joint.cpp:41-63
@@ -200,7 +199,6 @@ Joint::Joint(Solver* s, Rigid* b, const vec3& worldAnchor, float linK, float ang
     initialRelativeOrientation = b->orientation;
     for (int i = 0; i < 6; ++i) { stiffness[i] = i < 3 ? linK : angK; lambda[i] = 0; penalty[i] = PENALTY_MIN; }
     angularStiffness = angK; angularMotor = motor_; angularFracture = fracture_;
-    s->userForces.push_back(this);
 }
 void Joint::computeConstraint(float) {                                   // joint.cpp:68-106
     avbd::ForceEval e;
@@ -220,7 +218,6 @@ Spring::Spring(Solver* s, Rigid* a, Rigid* b, const vec3& la, const vec3& lb, fl
     stiffness[0] = k;
     if (restLength < 0) restLength = length((a->position + rotate(a->orientation, rA)) - (b->position + rotate(b->orientation, rB)));
     lambda[0] = 0.0f; penalty[0] = PENALTY_MIN; fmin[0] = -FLT_MAX; fmax[0] = FLT_MAX;
-    s->userForces.push_back(this);
 }
 void Spring::computeConstraint(float) {                                  // spring.cpp:33-56
     C[0] = avbd::spring_constraint(spring_rec(*this), bodyA != nullptr, bodyA ? (avbd::V3)bodyA->position : avbd::zero3(),
@@ -272,7 +269,9 @@ void pack_body(const Rigid* b, float* o) {
 }
 }
 
-void Solver::step() {                                                    // solver.cpp:255-514, on the device
+// Everything the host side created or edited since the device last saw it: parameters, moved bodies, new bodies, new
+// user forces.  Runs before every step and before Solver::pick (the reference's pick works on a solver that never stepped).
+void Solver::syncToDevice() {
     if (!world) { world = avbd_world_create(device); if (!world) die("avbd_world_create"); }
     if (rebuild) {               // something was deleted: start the device world over (warm-start history is lost)
         check(avbd_clear(world), "avbd_clear");
@@ -306,7 +305,14 @@ void Solver::step() {                                                    // solv
         for (int i = uploadedBodies; i < n; ++i) pack_body(order[i], &shadow[(size_t)i * 13]);
         uploadedBodies = n;
     }
-    // 3. user forces created since the last step
+    // 3. user forces created since the last step: every Force in the solver's list that is not a Manifold mirror and not
+    //    registered yet (the list is newest first; whatever subclass it is, it is found here — header-only ones included)
+    {
+        std::vector<Force*> fresh;
+        for (Force* f = forces; f; f = f->next)
+            if (f->deviceKind() != 3 && std::find(userForces.begin(), userForces.end(), f) == userForces.end()) fresh.push_back(f);
+        userForces.insert(userForces.end(), fresh.rbegin(), fresh.rend());
+    }
     for (; uploadedForces < (int)userForces.size(); ++uploadedForces) {
         Force* f = userForces[uploadedForces];
         int a = f->bodyA ? f->bodyA->index : -1, b = f->bodyB->index;
@@ -326,6 +332,11 @@ void Solver::step() {                                                    // solv
         }
     }
 
+}
+
+void Solver::step() {                                                    // solver.cpp:255-514, on the device
+    syncToDevice();
+    int n = (int)order.size();
     ++stepIndex;
     check(avbd_step(world, 1), "avbd_step");
     if (n > 0) {
@@ -381,7 +392,8 @@ void Solver::refreshManifolds() {
 void Solver::draw() { refreshManifolds(); }     // GL drawing is out of scope; keeping the mirrors fresh is what a renderer would need
 
 Rigid* Solver::pick(const vec3& origin, const vec3& dir, vec3& local) {      // solver.cpp:145-228, reduction on the device
-    if (!world || order.empty()) return nullptr;
+    if (order.empty()) return nullptr;
+    syncToDevice();
     const float o[3] = {origin.x, origin.y, origin.z}, d[3] = {dir.x, dir.y, dir.z};
     float l[3] = {0, 0, 0};
     int hit = avbd_pick(world, o, d, l);
