@@ -89,6 +89,36 @@ int main() {
 
     solver->clear();
     printf("cleared %d %d\n", (int)(solver->bodies == nullptr), (int)(solver->forces == nullptr));
+
+    // ---- the same Solver reused after clear(): host edits between steps (the GUI's drag / re-spin, main.cpp:88-142), a stacked
+    //      body taken away, diagnostics logging (solver.cpp:499-512), the Manifold objects a renderer walks
+    solver->enableDiagnostics = true; solver->logFrequency = 50;
+    new Rigid(solver, vec3(30, 1, 30), 0.0f, 0.5f, vec3(0, -0.5f, 0));
+    Rigid* p0 = new Rigid(solver, vec3(1, 1, 1), 1.0f, 0.5f, vec3(0, 0.51f, 0));
+    Rigid* p1 = new Rigid(solver, vec3(1, 1, 1), 1.0f, 0.5f, vec3(0, 1.52f, 0));
+    Rigid* p2 = new Rigid(solver, vec3(1, 1, 1), 1.0f, 0.5f, vec3(4, 0.51f, 0));
+    for (int s = 0; s < 100; ++s) solver->step();
+    p2->position = vec3(4, 3.0f, 1);                    // picked up and dropped somewhere else
+    p2->linearVelocity = vec3(0, 0, 0);
+    for (int s = 0; s < 100; ++s) solver->step();
+    printf("moved %.3f %.3f %.3f\n", p2->position.x, p2->position.y, p2->position.z);
+    p1->position = vec3(-6, 0.51f, -2);                 // the top box is lifted off and put on the ground elsewhere (deleting a Rigid that
+    p1->linearVelocity = vec3(0, 0, 0);                 // still has manifolds leaves them dangling upstream, rigid.cpp:43-49: not comparable)
+    for (int s = 0; s < 50; ++s) solver->step();
+    k = 0;
+    for (Rigid* r = solver->bodies; r; r = r->next, ++k) printf("rest2 %d %.3f %.3f %.3f\n", k, r->position.x, r->position.y, r->position.z);
+    solver->draw();
+    for (Force* f = solver->forces; f; f = f->next) {
+        if (!f->isManifold()) continue;
+        Manifold* m = static_cast<Manifold*>(f);
+        float lam = 0.0f;
+        for (int c = 0; c < m->numContacts; ++c) lam += m->lambda[c * 3];
+        // which bodies, how many contacts, the first normal, the total normal force (= weight / ... at rest)
+        printf("manifold %d %d %d n %.3f %.3f %.3f mu %.4f lam %.2f\n", (int)(m->bodyA == p0 || m->bodyB == p0), (int)(m->bodyA == p2 || m->bodyB == p2),
+               m->numContacts, std::fabs(m->contacts[0].normal.x), std::fabs(m->contacts[0].normal.y), std::fabs(m->contacts[0].normal.z), m->combinedFriction, lam);
+    }
+    printf("diag2 %d %d %d\n", solver->lastDiagnostics.activeManifolds, solver->lastDiagnostics.activeContacts, solver->lastDiagnostics.dynamicBodies);
+    (void)p0;
     delete solver;
     return 0;
 }

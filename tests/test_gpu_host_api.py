@@ -20,7 +20,7 @@ def _run(exe):
     rows = {}
     for line in out:
         key, *vals = line.split()
-        if key in ("body", "joint_J", "rest"):
+        if key in ("body", "joint_J", "rest", "rest2"):
             key, vals = key + vals[0], vals[1:]
         rows.setdefault(key, []).append(vals)
     return rows
@@ -59,3 +59,16 @@ def test_same_source_against_reference_and_mirror():
         assert abs(a[1] - b[1]) <= 2e-3, (key, a, b)
         if key != "rest4":
             assert abs(a[0] - b[0]) <= 5e-3 and abs(a[2] - b[2]) <= 5e-3, (key, a, b)
+    # second scene in the re-used solver: a dragged body lands where it was dropped, the Manifold objects a renderer walks
+    # (as a multiset: list order is creation order upstream, key order here), the diagnostics log lines
+    assert all(abs(float(x) - float(y)) <= 5e-3 for x, y in zip(ref["moved"][0], mine["moved"][0])), (ref["moved"], mine["moved"])
+    assert ref["diag2"] == mine["diag2"]
+    canon = lambda rows: sorted((r[0], r[1], r[2], r[4], r[5], r[6], r[8], round(float(r[10]), 0)) for r in rows)
+    assert canon(ref["manifold"]) == canon(mine["manifold"]), (ref["manifold"], mine["manifold"])
+    assert len(ref["[Physics]"]) == len(mine["[Physics]"]) == 5
+    for a, b in zip(ref["[Physics]"], mine["[Physics]"]):
+        ints = lambda r: (r[1], r[4], r[7], r[11])                       # step, manifolds, contacts, dyn bodies
+        assert ints(a) == ints(b), (a, b)
+        assert [x for x in a if not x[0].isdigit() and x[0] != "-"] == [x for x in b if not x[0].isdigit() and x[0] != "-"]      # same words
+        for i in (14, 17, 20, 23, 26):                                   # maxPen maxDrift maxLin maxAng maxLambda
+            assert abs(float(a[i]) - float(b[i])) <= 0.05, (i, a, b)
