@@ -176,6 +176,37 @@ def test_host_cli_matches_reference_cli(avbd):
     assert mine[-1].split("maxPen")[0] == want[-1].split("maxPen")[0]     # manifolds=2 contacts=8 dynBodies=2
 
 
+@pytest.mark.parametrize("scene,steps,calm,first_tol", [("Empty", 5, True, 1e-4), ("Ground", 5, True, 1e-4), ("Stack", 300, False, 5e-3), ("Pyramid", 120, False, 1e-4),
+                                                        ("Wall", 120, False, 5e-3), ("Rod (WIP)", 10, False, 5e-3), ("Soft Body (WIP)", 20, True, 1e-4)])
+def test_host_cli_every_scene_of_scenes_h(avbd, scene, steps, calm, first_tol):
+    """scenes.h:186-212 through the C++17 host mirror's CLI against the reference CLI (the oracle port prints byte-identically to
+    it, tests/test_oracle_pin.py): same line structure and body ids for every scene; the step-0 block (one step from the
+    initial state) agrees to print precision where the scene starts in free fall, and to 5e-3 where it starts in contact or
+    overlapping (Stack, Wall, Rod: the first sweep already depends on the Gauss-Seidel order); final heights within the
+    trajectory tolerance, and for the calm scenes the final diagnostics counts are equal."""
+    exe = os.path.join(PKG_DIR, "host", "avbd_demo3d")
+    args = ["--nogfx", "--scene", scene, "--steps", str(steps)]
+    mine = subprocess.run([exe] + args, capture_output=True, text=True, check=True).stdout.splitlines()
+    want = subprocess.run([os.path.join(ROOT, "oracle", "avbd_oracle_cli")] + args, capture_output=True, text=True, check=True).stdout.splitlines()
+    strip = lambda lines: [l for l in lines if not l.startswith("[Physics]")]
+    mine, want = strip(mine), strip(want)
+    assert len(mine) == len(want) and mine[0] == want[0]
+    per_step = (len(want) - 1) // steps
+    ids = lambda block: [l.split(":")[0] for l in block]
+    assert ids(mine[-per_step:]) == ids(want[-per_step:])
+    pos = lambda l: [float(x) for x in l.split("Pos(")[1].split(")")[0].split(",")]
+    first_m, first_w = mine[1: 1 + per_step], want[1: 1 + per_step]
+    for a, b in zip(first_m, first_w):
+        if "Pos(" in a:
+            assert max(abs(x - y) for x, y in zip(pos(a), pos(b))) <= first_tol, (a, b)
+    for a, b in zip(mine[-per_step:], want[-per_step:]):
+        if "Pos(" in a:
+            assert abs(pos(a)[1] - pos(b)[1]) <= (REST_TOL if calm else 0.05), (a, b)
+    if calm:
+        counts = lambda l: l.split("maxPen")[0]
+        assert counts(mine[-1]) == counts(want[-1]), (mine[-1], want[-1])
+
+
 def test_host_cli_unknown_scene_falls_back_to_empty(avbd):
     exe = os.path.join(PKG_DIR, "host", "avbd_demo3d")
     out = subprocess.run([exe, "--nogfx", "--scene", "NoSuchScene", "--steps", "2"], capture_output=True, text=True, check=True).stdout
