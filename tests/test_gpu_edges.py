@@ -216,3 +216,33 @@ def test_grid_pair_set_against_kdtree(avbd):
         assert sure0 <= with_ground <= maybe0
     finally:
         w.close()
+
+
+def test_live_parameter_edits(avbd):
+    """The GUI edits dt / gravity / iterations / alpha / beta / gamma between steps (main.cpp:88-94, fields re-read by every
+    Solver::step): the same edits applied to the oracle give the same free-fall trajectory (no contacts: order-independent) and
+    the same resting state of TwoBlockDrop."""
+    o = Oracle("port").create()
+    w = avbd.World()
+    for d in (o, w):
+        d.add_body((1, 1, 1), 1.0, 0.5, (0, 100, 0), lin=(1, 0, 0), ang=(0, 0.5, 0))
+    edits = [dict(), dict(g=(0, -3, 0)), dict(dt=1 / 120, g=(1, -3, 0)), dict(dt=1 / 30, iterations=3, alpha=0.9, beta=5e4, gamma=0.97), dict(post=True)]
+    for e in edits:
+        o.set_params(**e); w.set_params(**e)
+        o.step(15); w.step(15)
+        a, b = o.state(), w.state()
+        assert np.abs(a - b).max() <= 2e-5 * max(1.0, float(np.abs(a).max())), (e, float(np.abs(a - b).max()))
+    o.close(); w.close()
+
+    from avbd_demo3d_b200 import scenes
+    o = Oracle("port").create(); o.load_scene("TwoBlockDrop")
+    w = avbd.World(); scenes.load(w, scenes.scene("TwoBlockDrop"))
+    p = o.params()
+    for iters in (10, 4, 16):
+        kw = dict(dt=p["dt"], g=p["g"], iterations=iters, alpha=p["alpha"], beta=p["beta"], gamma=p["gamma"])
+        o.set_params(**kw); w.set_params(**kw)
+        o.step(100); w.step(100)
+    a, b = o.state(), w.state()
+    assert np.abs(a[:, 1] - b[:, 1]).max() < 1e-3 and np.abs(b[1:, 7:]).max() < 1e-3
+    assert (w.diagnostics()["manifolds"], w.diagnostics()["contacts"]) == (o.diagnostics()["manifolds"], o.diagnostics()["contacts"]) == (2, 8)
+    o.close(); w.close()
