@@ -113,7 +113,9 @@ struct avbd_world {
     // counters / diagnostics
     Counters* dCnt = nullptr; Counters* hCnt = nullptr;
     DevBuf<Diag> dDiag; Diag* hDiag = nullptr; size_t hDiagCap = 0;
-    DevBuf<float> dx, sums, carry; DevBuf<int2> colVisit; DevBuf<int> kOf;     // kOf[body] = position in colOrder
+    DevBuf<float> dx, sums, carry; DevBuf<int2> colVisit; DevBuf<int> kOf, flatRange;      // flatRange: per colour, the flat sweep's block boundaries
+    int flatGrid[64] = {0}, flatRangeOff[64] = {0};
+    bool flatAligned = false;          // several worlds in the batch: body-aligned block ranges (sums independent of the batch)     // kOf[body] = position in colOrder
     DevBuf<char> temp;
 
     // per-kernel profiling (avbd_set_profiling): events around every primal sweep and dual pass
@@ -530,6 +532,24 @@ int run_colour(avbd_world* w) {
     w->nColours = w->hCnt->nColours;
     w->maxColourCount = 0;
     for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);
+    // the flat sweep's grids; for a batch of several worlds also its body-aligned block ranges (device only: nothing below waits)
+    {
+        w->flatAligned = w->nWorlds > 1;
+        int total = 0;
+        for (int c = 0; c < w->nColours; ++c) {
+            w->flatGrid[c] = primal_flat_grid(w->hColVisit[c].y - w->hColVisit[c].x);
+            w->flatRangeOff[c] = total; total += w->flatGrid[c] + 1;
+        }
+        if (w->flatAligned) {
+            TRY(w->flatRange.ensure((size_t)std::max(1, total), false, s));
+            for (int c = 0; c < w->nColours; ++c) {
+                int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
+                if (count <= 0 || w->flatGrid[c] <= 0) continue;
+                launch_flat_ranges(s, w->visitStart.p, first, count, w->hColVisit[c].x, w->hColVisit[c].y, w->flatGrid[c], w->flatRange.p + w->flatRangeOff[c]);
+                w->launches++;
+            }
+        }
+    }
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;
@@ -541,9 +561,8 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
-    int chunkT = primal_flat_chunk_threads();
     TRY(w->sums.ensure((size_t)std::max(1, w->nDyn) * 28, false, s));
-    TRY(w->carry.ensure(((size_t)std::max(1, 2 * w->nContacts) / chunkT + 2) * 28, false, s));
+    if (!w->flatAligned) TRY(w->carry.ensure(((size_t)std::max(1, 2 * w->nContacts) / primal_flat_chunk_threads() + 2) * 28, false, s));
     if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
         size_t cap = w->visits.cap;
         TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));
@@ -555,7 +574,8 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
         w->launches += launch_primal_flat(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->colOrder.p, w->visitStart.p, w->kOf.p, first, count,
-                                          w->hColVisit[c].x, w->hColVisit[c].y, w->prm, alpha, alphaDual, w->sums.p, w->carry.p, dxDev, w->dDiag.p);
+                                          w->hColVisit[c].x, w->hColVisit[c].y, w->flatGrid[c], w->flatAligned ? w->flatRange.p + w->flatRangeOff[c] : nullptr,
+                                          w->prm, alpha, alphaDual, w->sums.p, w->carry.p, dxDev, w->dDiag.p);
     }
     CK(cudaGetLastError());
     return 0;
@@ -720,7 +740,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
-    w->dDiag.release(); w->dx.release(); w->sums.release(); w->carry.release(); w->colVisit.release(); w->kOf.release(); w->temp.release(); w->stateDev.release();
+    w->dDiag.release(); w->dx.release(); w->sums.release(); w->carry.release(); w->colVisit.release(); w->kOf.release(); w->flatRange.release(); w->temp.release(); w->stateDev.release();
     w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stLP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);

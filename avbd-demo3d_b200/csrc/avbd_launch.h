@@ -121,13 +121,18 @@ constexpr int kThreads = 256;
 constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodies per CTA tile (9 lanes per body in the sum phase)
 
 // One colour of the large-world primal sweep (flat visit partition, avbd_solve.cu): bodies [first, first + count) of the
-// colour-ordered arrays `order` / `vstart` (kOf[body] = position in `order`), whose visits are [vBegin, vEnd) of `visits`.
-// `sums` holds 28 floats per dynamic body (row = position in `order`), `carry` 28 floats
-// per chunk of primal_flat_chunk_threads() visits.  alphaDual >= 0: the previous iteration's dual pass (run with that alpha) is
-// still pending and each contact's first visit applies it (deferred dual); < 0: plain primal sweep.  Returns the kernels launched.
+// colour-ordered arrays `order` / `vstart` (kOf[body] = position in `order`), whose visits are [vBegin, vEnd).  `grid` =
+// primal_flat_grid(vEnd - vBegin).  `range` == nullptr: chunks round-robin over the blocks, `carry` takes 28 floats per chunk;
+// `range` != nullptr (batches of several worlds): the colour's grid + 1 body-aligned block boundaries (launch_flat_ranges, once
+// per graph build) — sums do not depend on the batch.  `sums` holds 28 floats per dynamic body (row = position in `order`).
+// alphaDual >= 0: the previous iteration's dual pass (run with that alpha) is still pending and each contact's first visit applies
+// it (deferred dual); < 0: plain primal sweep.  Returns the kernels launched.
 int primal_flat_chunk_threads();
+int primal_flat_grid(int nVisits);
+void launch_flat_ranges(cudaStream_t s, const int* vstart, int first, int count, int vBegin, int vEnd, int grid, int* range);
 int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                       const int* kOf, int first, int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag);
+                       const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float alphaDual,
+                       float* sums, float* carry, float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live (densely stored) contacts.
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics
 // (solver.cpp:472-497) are reduced here from the values already in registers instead of by a separate sweep.

@@ -420,8 +420,10 @@ struct FlatSmem {
     float4 c[2][T][7];   // one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad — 128-bit stores / loads, row stride 28 words: conflict free
     float4 stage[9][T];  // the NEXT chunk's gathered operands, filled by cp.async: self pose (2), other pose (2), geometry (3), lambda, penalty
     unsigned char segPos[2][T / 32][32];     // per warp: chunk-local positions (< T <= 256) of the segment heads among its 32 visits
-    int segK[2][T / 32][32];       // ... and each segment's row of `sums` (complemented: goes to `carry`)
+    int segK[2][T / 32][32];       // ... and each segment's row of `sums` (complemented: it continues the previous chunk's last segment)
     unsigned headMask[2][T / 32];
+    float4 carry[2][8];            // partial sum of the body whose run crosses into the next chunk (by chunk parity)
+    int nextK[2];                  // row of the body the next chunk starts with (-1: this is the block's last chunk)
 };
 
 // cp.async (LDGSTS) of one 16-byte item into this thread's slot of the gather stage, with an L2 eviction policy.
@@ -439,22 +441,31 @@ __device__ __forceinline__ unsigned long long l2_stream_policy() {
     return p;
 }
 
-template <int T, int MINB>
-__global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, int vBegin, int vEnd,
-                                                             const int* __restrict__ kOf, float alpha, float alphaDual, float beta, float* __restrict__ sums,
-                                                             float* __restrict__ carry) {
-    cudaGridDependencySynchronize();
+template <int T, int MINB, bool ALIGNED>
+__global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms,
+                                                             int vFirst, int vLast, const int* __restrict__ range, const int* __restrict__ kOf,
+                                                             float alpha, float alphaDual, float beta, float* __restrict__ sums, float* __restrict__ carry) {
     __shared__ FlatSmem<T> sm;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int nChunks = (vEnd - vBegin + T - 1) / T;
     const unsigned long long keep = l2_keep_policy(), stream = l2_stream_policy();
-    int chunk = blockIdx.x;
-    if (chunk >= nChunks) return;
-    const int4 none = make_int4(0, 0, -8, 0);                        // body -1
-    const int stride = gridDim.x * T;
     // launched with programmatic stream serialization: the grid may already be resident while the previous colour's block solve
     // drains; nothing it wrote (poses) is read before this point
     cudaGridDependencySynchronize();
+    // Two ways to hand out the colour's visits [vFirst, vLast):
+    //   range == nullptr  chunks round-robin over the blocks (chunk c = visits vFirst + c*T ...).  Fastest; a body whose run crosses a
+    //                     chunk boundary gets its sum in two pieces (sums[k] + carry[chunk], added by primal_solve_flat), so its
+    //                     rounding depends on where the chunk grid falls — harmless for ONE world, but it makes a world's
+    //                     trajectory depend on what else is in the batch;
+    //   range != nullptr  (batches of several worlds) block r owns the contiguous visits [range[r], range[r + 1]), cut on BODY
+    //                     boundaries (flat_ranges): a run that crosses a chunk boundary stays inside the block, its partial sum
+    //                     waits in shared memory and the sum is one sequence in visit order — exactly the cluster loop's, and
+    //                     independent of the batch (bit-identical ensembles however they are partitioned over GPUs).
+    constexpr bool aligned = ALIGNED;           // compile-time: the round-robin instantiation carries none of the other mode's code
+    const int vBegin = aligned ? range[blockIdx.x] : vFirst, vEnd = aligned ? range[blockIdx.x + 1] : vLast;
+    const int stride = aligned ? T : (int)gridDim.x * T;
+    const int start = aligned ? vBegin : vBegin + (int)blockIdx.x * T;
+    if (start >= vEnd) return;
+    const int4 none = make_int4(0, 0, -8, 0);                        // body -1
     // Software pipeline over the block's chunks, two deep: the visit ENTRIES are loaded two chunks ahead (registers), and as soon
     // as an entry is there the data it points at — two poses, the lambda / penalty record, the streamed geometry: 9 x 16 B per
     // visit — is fetched one chunk ahead with cp.async into this thread's slots of a shared-memory stage.  A chunk therefore
@@ -476,11 +487,10 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     int4 eCur, eNext; int prevCur, prevNext, kCur;
-    load_entry(vBegin + chunk * T + t, eCur, prevCur);
-    load_entry(vBegin + chunk * T + t + stride, eNext, prevNext);
-    issue_gathers(vBegin + chunk * T + t, eCur, kCur);
-    for (int it = 0; chunk < nChunks; chunk += gridDim.x, ++it) {
-        const int base = vBegin + chunk * T;
+    load_entry(start + t, eCur, prevCur);
+    load_entry(start + t + stride, eNext, prevNext);
+    issue_gathers(start + t, eCur, kCur);
+    for (int it = 0, base = start; base < vEnd; base += stride, ++it) {
         const int v = base + t;
         const int4 e = eCur; const int prevZ = prevCur; const int kSelf = kCur;
         const bool live = v < vEnd;
@@ -506,6 +516,7 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
             sm.segK[buf][warp][r] = (t == 0 && prevSelf == self) ? ~kSelf : kSelf;    // complemented: continues the previous chunk's last segment
         }
         if (lane == 0) sm.headMask[buf][warp] = heads;
+        if (aligned && t == 0) sm.nextK[buf] = base + T < vEnd ? kCur : -1;     // row of the body the block's NEXT chunk opens with (kCur was loaded for it above)
         // ---- phase 1
         if (live) {
             bool gyro = (e.z & 2) != 0, pending = alphaDual >= 0.0f && (e.z & 4) != 0;
@@ -542,7 +553,11 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
             for (int wi = lane; wi < nSegW * kFlatLanes; wi += 32) {
                 int sgi = wi / kFlatLanes, j = wi - sgi * kFlatLanes;
                 int lv = sm.segPos[buf][warp][sgi], z = sgi + 1 < nSegW ? sm.segPos[buf][warp][sgi + 1] : tailEnd;
-                float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                int idx = sm.segK[buf][warp][sgi];          // the body's row of `sums`, complemented when the segment continues the previous chunk's last
+                // a body whose run crosses a chunk boundary is summed in one sequence all the same: the partial sum waits in shared memory
+                const bool cont = idx < 0;
+                float4 acc = (cont && aligned) ? sm.carry[buf ^ 1][j] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (cont) idx = ~idx;
                 auto add = [&](float4 x) {                   // two packed adds (add.rn.f32x2) instead of four scalar ones
                     float2 lo = __fadd2_rn(make_float2(acc.x, acc.y), make_float2(x.x, x.y)), hi = __fadd2_rn(make_float2(acc.z, acc.w), make_float2(x.z, x.w));
                     acc = make_float4(lo.x, lo.y, hi.x, hi.y);
@@ -552,40 +567,41 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
                     add(x0); add(x1); add(x2); add(x3);
                 }
                 for (; lv < z; ++lv) add(sm.c[buf][lv][j]);
-                int idx = sm.segK[buf][warp][sgi];          // position in the colour order, complemented for a continuation
-                float* o = idx >= 0 ? sums + (size_t)idx * kSumStride : carry + (size_t)chunk * kSumStride;
-                reinterpret_cast<float4*>(o)[j] = acc;
+                if (aligned && z == liveCount && sm.nextK[buf] == idx) sm.carry[buf][j] = acc;         // aligned: the run goes on in the block's next chunk
+                else if (cont && !aligned) reinterpret_cast<float4*>(carry + (size_t)((base - vBegin) / T) * kSumStride)[j] = acc;   // round-robin: a piece
+                else reinterpret_cast<float4*>(sums + (size_t)idx * kSumStride)[j] = acc;
             }
         }
     }
 }
 
-// One body per thread: main sums + the carries of every later chunk its visits reach, inertial terms, Schur solve, pose update.
-// `order`, `vstart`, `sums` point at the colour's first body.
+// One body per thread: the body's row sums (+ with round-robin chunks the pieces of every later chunk its run reaches, in chunk
+// order), inertial terms, Schur solve, pose update.  `order`, `vstart`, `sums` point at the colour's first body.
 __global__ void __launch_bounds__(kThreads) primal_solve_flat(BodyView b, ForceView fv, const int* __restrict__ order, const int* __restrict__ vstart, int count,
                                                               int vBegin, int chunkT, const float* __restrict__ sums, const float* __restrict__ carry,
                                                               SolveParams prm, float* dxOut, Diag* diag) {
-    cudaGridDependencySynchronize();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     int i = order[k];
     int vs = vstart[k], ve = vstart[k + 1];
     const unsigned long long keep = l2_keep_policy();
-    cudaGridDependencySynchronize();          // the visit kernel's sums / carries (programmatic stream serialization, see launch_flat)
+    cudaGridDependencySynchronize();          // the visit kernel's sums (programmatic stream serialization, see launch_flat)
     BodyPose self = load_pose_keep(b.pose + i, keep);
     BodyAux aux = b.aux[i];
     float o[kSumStride];
 #pragma unroll
     for (int q = 0; q < kSumStride; ++q) o[q] = 0.0f;
-    if (ve > vs) {
+    if (ve > vs) {                            // a body no contact visits has no row: nothing was written for it
         const float4* s4 = reinterpret_cast<const float4*>(sums + (size_t)k * kSumStride);
 #pragma unroll
         for (int q = 0; q < kSumStride / 4; ++q) { float4 x = __ldcs(s4 + q); o[4 * q] = x.x; o[4 * q + 1] = x.y; o[4 * q + 2] = x.z; o[4 * q + 3] = x.w; }
-        int c0 = (vs - vBegin) / chunkT, c1 = (ve - 1 - vBegin) / chunkT;
-        for (int c = c0 + 1; c <= c1; ++c) {
-            const float4* c4 = reinterpret_cast<const float4*>(carry + (size_t)c * kSumStride);
+        if (carry) {
+            int c0 = (vs - vBegin) / chunkT, c1 = (ve - 1 - vBegin) / chunkT;
+            for (int c = c0 + 1; c <= c1; ++c) {
+                const float4* c4 = reinterpret_cast<const float4*>(carry + (size_t)c * kSumStride);
 #pragma unroll
-            for (int q = 0; q < kSumStride / 4; ++q) { float4 x = c4[q]; o[4 * q] += x.x; o[4 * q + 1] += x.y; o[4 * q + 2] += x.z; o[4 * q + 3] += x.w; }
+                for (int q = 0; q < kSumStride / 4; ++q) { float4 x = c4[q]; o[4 * q] += x.x; o[4 * q + 1] += x.y; o[4 * q + 2] += x.z; o[4 * q + 3] += x.w; }
+            }
         }
     }
     V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
@@ -785,60 +801,77 @@ __global__ void solve6_batch(const float* lhs36, const float* rhs6, int n, float
 // ------------------------------------------------------------------ launchers (declared in avbd_launch.h)
 static inline int blocks_of(long long n, int per) { long long b = (n + per - 1) / per; return (int)(b < 1 ? 1 : b); }
 
+// Body-aligned ranges of one colour's visits: range r of `grid` starts at the first body whose run starts at or after
+// the r-th equal share of [vBegin, vEnd) — every body's visits then belong to exactly one block, which sums them in one
+// sequence (no partial sums to merge across blocks, the result does not depend on where the colour's visit list is cut).
+__global__ void flat_ranges(const int* __restrict__ vstart, int count, int vBegin, int vEnd, int grid, int* __restrict__ range) {
+    cudaGridDependencySynchronize();
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > grid) return;
+    long long target = (long long)vBegin + ((long long)(vEnd - vBegin) * r) / grid;
+    int lo = 0, hi = count;                        // first k in [0, count] with vstart[k] >= target (vstart[count] == vEnd)
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (vstart[mid] < target) lo = mid + 1; else hi = mid; }
+    range[r] = vstart[lo];
+}
+
 template <int T, int MINB>
-static void launch_flat(cudaStream_t s, int nSm, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                        const int* kOf, int first, int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
-    int nChunks = (vEnd - vBegin + T - 1) / T;
-    if (nChunks > 0) {
-        // persistent grid = what is actually resident (a block that has to wait for a slot would start its share of the chunks late)
-        static const int perSm = [] {
-            cudaFuncSetAttribute(primal_visit_flat<T, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            int n = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, primal_visit_flat<T, MINB>, T, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
-            if (getenv("AVBD_DEBUG")) fprintf(stderr, "primal_visit_flat<%d,%d>: %d blocks per SM resident\n", T, MINB, n);
-            return n;
-        }();
-        int grid = nChunks < nSm * perSm ? nChunks : nSm * perSm;
-        // Programmatic dependent launch: each kernel of a sweep is launched while its predecessor still runs and blocks at
-        // cudaGridDependencySynchronize() until that one has completed — a step has ~160 of these dependent launches, and the
-        // launch latency of each would otherwise sit on the critical path.
-        cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = 0; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, primal_visit_flat<T, MINB>, b, visits, vg, ms, vBegin, vEnd, kOf, alpha, alphaDual, prm.beta, sums, carry);
-    }
-    {
-        cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.gridDim = dim3(blocks_of(count, kThreads)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = 1;
-        const int* orderC = order + first; const int* vstartC = vstart + first; const float* sumsC = sums + (size_t)first * kSumStride; const float* carryC = carry;
-        cudaLaunchKernelEx(&cfg, primal_solve_flat, b, fv, orderC, vstartC, count, vBegin, (int)T, sumsC, carryC, prm, dxOut, diag);
-    }
+static int flat_resident_blocks() {
+    static const int n = [] {
+        cudaFuncSetAttribute(primal_visit_flat<T, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(primal_visit_flat<T, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int dev = 0, sms = 148, per = 0;
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, primal_visit_flat<T, MINB, true>, T, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 1; }
+        if (getenv("AVBD_DEBUG")) fprintf(stderr, "primal_visit_flat<%d,%d>: %d blocks per SM resident\n", T, MINB, per);
+        return sms * per;
+    }();
+    return n;
 }
+static int flat_config() { static int cfg = [] { const char* e = getenv("AVBD_FLAT"); return e ? atoi(e) : 1284; }(); return cfg; }
+
 // The default large-world sweep of one colour: flat visit partition + block solve.  `order` / `vstart` are the WHOLE colour-ordered
-// arrays, the colour is their bodies [first, first + count); kOf[body] = its position in `order`.  `sums`: 28 floats per dynamic body;
-// `carry`: 28 floats per chunk (primal_flat_chunks).  AVBD_FLAT (tuning aid) = "<threads per block><blocks per SM>": 1284 (default; 96 registers, no
-// spills, 33 KB of shared memory per block) 1285 1286 — all within 2 % of each other on the 1M-box grid (5.39 / 5.42 / 5.48 ms of sweeps).
-int primal_flat_chunk_threads() {
-    static int t = [] { const char* e = getenv("AVBD_FLAT"); (void)e; return 128; }();
-    return t;
+// arrays, the colour is their bodies [first, first + count) with visits [vBegin, vEnd); kOf[body] = its position in `order`.
+// `sums`: 28 floats per dynamic body.
+// AVBD_FLAT (tuning aid) = "<threads per block><blocks per SM>": 1284 (default) 1285 1286 — within 2 % of each other on the 1M-box grid.
+int primal_flat_chunk_threads() { return 128; }
+// Persistent grid of a colour with nVisits visits = what is actually resident (a block that has to wait for a slot would start
+// its share late), at most one block per chunk.
+int primal_flat_grid(int nVisits) {
+    int nChunks = (nVisits + 127) / 128;
+    int resident = flat_config() == 1286 ? flat_resident_blocks<128, 6>() : (flat_config() == 1285 ? flat_resident_blocks<128, 5>() : flat_resident_blocks<128, 4>());
+    return nChunks < resident ? nChunks : resident;
 }
+void launch_flat_ranges(cudaStream_t s, const int* vstart, int first, int count, int vBegin, int vEnd, int grid, int* range) {
+    if (grid > 0) launch_dep(flat_ranges, dim3(blocks_of(grid + 1, kThreads)), dim3(kThreads), 0, s, vstart + first, count, vBegin, vEnd, grid, range);
+}
+
+template <int T, int MINB>
+static void launch_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
+                        const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float alphaDual,
+                        float* sums, float* carry, float* dxOut, Diag* diag) {
+    // Programmatic dependent launch: each kernel of a sweep is launched while its predecessor still runs and blocks at
+    // cudaGridDependencySynchronize() until that one has completed — a step has ~160 of these dependent launches, and the
+    // launch latency of each would otherwise sit on the critical path.
+    if (grid > 0 && range) launch_dep(primal_visit_flat<T, MINB, true>, dim3(grid), dim3(T), 0, s, b, visits, vg, ms, vBegin, vEnd, range, kOf, alpha, alphaDual, prm.beta, sums, carry);
+    else if (grid > 0) launch_dep(primal_visit_flat<T, MINB, false>, dim3(grid), dim3(T), 0, s, b, visits, vg, ms, vBegin, vEnd, range, kOf, alpha, alphaDual, prm.beta, sums, carry);
+    const int* orderC = order + first; const int* vstartC = vstart + first; const float* sumsC = sums + (size_t)first * kSumStride;
+    const float* carryC = range ? nullptr : carry;                       // body-aligned ranges leave no pieces to add
+    launch_dep(primal_solve_flat, dim3(blocks_of(count, kThreads)), dim3(kThreads), 0, s, b, fv, orderC, vstartC, count, vBegin, (int)T, sumsC, carryC, prm, dxOut, diag);
+}
+// `range` == nullptr: round-robin chunks (+ `carry`: 28 floats per chunk of the colour); else the colour's grid + 1 body-aligned
+// block boundaries (launch_flat_ranges, once per graph build).
 int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                       const int* kOf, int first, int count, int vBegin, int vEnd, SolveParams prm, float alpha, float alphaDual, float* sums, float* carry, float* dxOut, Diag* diag) {
-    static int nSm = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
-    static int cfg = [] { const char* e = getenv("AVBD_FLAT"); return e ? atoi(e) : 1284; }();
-#define AVBD_FL(T, M) launch_flat<T, M>(s, nSm, b, visits, vg, ms, fv, order, vstart, kOf, first, count, vBegin, vEnd, prm, alpha, alphaDual, sums, carry, dxOut, diag)
-    switch (cfg) {
+                       const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float alphaDual,
+                       float* sums, float* carry, float* dxOut, Diag* diag) {
+#define AVBD_FL(T, M) launch_flat<T, M>(s, b, visits, vg, ms, fv, order, vstart, kOf, first, count, vBegin, vEnd, grid, range, prm, alpha, alphaDual, sums, carry, dxOut, diag)
+    switch (flat_config()) {
         case 1286: AVBD_FL(128, 6); break;
         case 1285: AVBD_FL(128, 5); break;
         default:   AVBD_FL(128, 4); break;
     }
 #undef AVBD_FL
-    return vEnd > vBegin ? 2 : 1;
+    return grid > 0 ? 2 : 1;
 }
-
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
                        Diag* diag, bool contactDiag, bool anyUnvisited) {

@@ -243,6 +243,22 @@ def test_ensemble_is_bit_identical_across_partitions(avbd, name, steps):
     assert dwhole[0]["activeManifolds"] > 0 and dwhole[0]["dynamicBodies"] == n - 1
 
 
+def test_large_ensemble_is_bit_identical_across_partitions(avbd):
+    """The same at a size the per-colour kernels handle (800 Stack worlds = 8800 bodies, beyond the cluster loop's limit): the
+    flat visit kernel hands each block a body-aligned range of the visit list, so a body's rows are summed in one sequence
+    wherever the world sits in the batch — 800 worlds in one batch == two batches of 400, bit for bit."""
+    from avbd_demo3d_b200 import scenes
+    base = scenes.scene("Stack")
+    n = len(base["size"])
+    whole, dwhole = _ensemble_states(avbd, base, 800, 0, 40)
+    lo, dlo = _ensemble_states(avbd, base, 400, 0, 40)
+    hi, dhi = _ensemble_states(avbd, base, 400, 400, 40)
+    assert whole[: 400 * n].tobytes() == lo.tobytes()
+    assert whole[400 * n:].tobytes() == hi.tobytes()
+    assert dwhole[:400] == dlo and dwhole[400:] == dhi
+    assert dwhole[0]["activeManifolds"] > 0
+
+
 # --------------------------------------------------------------------------- deferred dual
 def _run_variant(avbd, build, steps, env):
     """A fresh world stepped under the given environment toggles (read at world creation / every step)."""
