@@ -184,6 +184,10 @@ def main():
 
     dist = None
     if world_size > 1:
+        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (printed from level VERSION up, which some images
+        # configure) out of it; an explicit INFO / TRACE request is left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
