@@ -43,7 +43,11 @@ class Profile(C.Structure):
     _fields_ = [("ms_primal", C.c_double), ("ms_dual", C.c_double), ("steps", C.c_longlong), ("primal_sweeps", C.c_longlong),
                 ("primal_launches", C.c_longlong), ("primal_bodies", C.c_longlong), ("primal_visits", C.c_longlong),
                 ("dual_launches", C.c_longlong), ("dual_contacts", C.c_longlong), ("kernel_launches", C.c_longlong),
-                ("library_launches", C.c_longlong), ("deferred_dual_contacts", C.c_longlong)]
+                ("library_launches", C.c_longlong), ("deferred_dual_contacts", C.c_longlong),
+                ("ms_broadphase", C.c_double), ("ms_narrowphase", C.c_double), ("ms_graph", C.c_double), ("ms_predict", C.c_double),
+                ("ms_solve", C.c_double), ("ms_velocity", C.c_double), ("ms_step", C.c_double),
+                ("bodies", C.c_longlong), ("pairs", C.c_longlong), ("candidates", C.c_longlong), ("manifolds", C.c_longlong),
+                ("manifolds_prev", C.c_longlong), ("contacts", C.c_longlong), ("visits", C.c_longlong), ("graph_builds", C.c_longlong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -61,6 +65,14 @@ ABI = {
     "avbd_add_bodies": (C.c_int, [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
     "avbd_num_bodies": (C.c_int, [C.c_void_p]),
     "avbd_add_joint": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_float]),
+    "avbd_add_joint_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float]),
+    "avbd_set_force_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "avbd_get_force_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "avbd_download_user_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "avbd_num_joints": (C.c_int, [C.c_void_p]),
+    "avbd_num_springs": (C.c_int, [C.c_void_p]),
+    "avbd_host_alloc": (C.c_void_p, [C.c_longlong]),
+    "avbd_host_free": (None, [C.c_void_p]),
     "avbd_add_spring": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_float]),
     "avbd_add_ignore": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "avbd_step": (C.c_int, [C.c_void_p, C.c_int]),
@@ -70,6 +82,7 @@ ABI = {
     "avbd_get_profile": (C.c_int, [C.c_void_p, C.POINTER(Profile)]),
     "avbd_download_state": (C.c_int, [C.c_void_p, _f32p]),
     "avbd_upload_state": (C.c_int, [C.c_void_p, _f32p]),
+    "avbd_upload_state_range": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p]),
     "avbd_download_prev_linvel": (C.c_int, [C.c_void_p, _f32p]),
     "avbd_upload_prev_linvel": (C.c_int, [C.c_void_p, _f32p]),
     "avbd_download_body_props": (C.c_int, [C.c_void_p, _f32p]),
@@ -80,6 +93,10 @@ ABI = {
     "avbd_world_diagnostics_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "avbd_num_manifolds": (C.c_int, [C.c_void_p]),
     "avbd_download_manifolds": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, _f32p]),
+    "avbd_upload_manifolds": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, _f32p]),
+    "avbd_snapshot_bytes": (C.c_longlong, [C.c_void_p]),
+    "avbd_snapshot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong]),
+    "avbd_restore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong]),
     "avbd_stage_broadphase": (C.c_int, [C.c_void_p]),
     "avbd_download_pairs": (C.c_int, [C.c_void_p, _i32p, C.c_int]),
     "avbd_stage_collide": (C.c_int, [C.c_void_p]),
@@ -190,6 +207,23 @@ class World:
     def add_joint(self, a, b, anchor_a, anchor_b=(0, 0, 0), lin_k=FLT_MAX, ang_k=FLT_MAX):
         return _check(self.L.avbd_add_joint(self.h, a, b, _f(anchor_a), _f(anchor_b), lin_k, ang_k))
 
+    def add_joint_raw(self, a, b, r_a, r_b, rel0, lin_k=FLT_MAX, ang_k=FLT_MAX):
+        """A weld with the caller's construction-time rA / rB / initial relative orientation (joint.h:17-19)."""
+        return _check(self.L.avbd_add_joint_raw(self.h, a, b, _f(r_a), _f(r_b), _f(rel0), lin_k, ang_k))
+
+    def set_force_rows(self, kind, index, lam=None, pen=None, motor=None, stiffness=None):
+        """Edit the public row arrays of a joint (kind 0, 6 rows) or spring (kind 1, 1 row), solver.h:91-97."""
+        n = 6 if kind == 0 else 1
+        arrs = [None if a is None else _f(np.broadcast_to(np.asarray(a, np.float32), (n,))) for a in (lam, pen, motor, stiffness)]
+        ptrs = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]
+        _check(self.L.avbd_set_force_rows(self.h, kind, index, *ptrs))
+
+    def force_rows(self, kind, index):
+        n = 6 if kind == 0 else 1
+        out = [np.zeros(n, np.float32) for _ in range(4)]
+        _check(self.L.avbd_get_force_rows(self.h, kind, index, *[a.ctypes.data_as(C.c_void_p) for a in out]))
+        return dict(lam=out[0], pen=out[1], motor=out[2], stiffness=out[3])
+
     def add_spring(self, a, b, anchor_a, anchor_b, k, rest=-1.0):
         return _check(self.L.avbd_add_spring(self.h, a, b, _f(anchor_a), _f(anchor_b), k, rest))
 
@@ -234,6 +268,10 @@ class World:
     def set_state(self, s):
         _check(self.L.avbd_upload_state(self.h, _f(s)))
 
+    def set_state_range(self, first, s):
+        s = _f(s).reshape(-1, 13)
+        _check(self.L.avbd_upload_state_range(self.h, first, len(s), s))
+
     def prev_linvel(self):
         o = np.zeros((self.n, 3), np.float32)
         _check(self.L.avbd_download_prev_linvel(self.h, o))
@@ -270,6 +308,24 @@ class World:
         ints, feats, stick, flts = (np.zeros((m, 3), np.int32), np.zeros((m, 4), np.int32), np.zeros((m, 4), np.int32), np.zeros((m, 81), np.float32))
         live = _check(self.L.avbd_download_manifolds(self.h, ints, feats, stick, flts)) if m else 0
         return ints[:live], feats[:live], stick[:live], flts[:live]
+
+    def upload_manifolds(self, ints, feats, stick, flts):
+        """Inverse of manifolds_raw(): replaces the manifold set (the warm-start history Manifold::initialize matches against)."""
+        ints = np.ascontiguousarray(ints, np.int32).reshape(-1, 3)
+        m = len(ints)
+        _check(self.L.avbd_upload_manifolds(self.h, m, ints, np.ascontiguousarray(feats, np.int32).reshape(m, 4),
+                                            np.ascontiguousarray(stick, np.int32).reshape(m, 4), _f(flts).reshape(m, 81)))
+
+    def snapshot(self):
+        """Opaque blob of the whole simulation state (bodies, user forces, manifolds with lambda / penalty / anchors, params)."""
+        n = self.L.avbd_snapshot_bytes(self.h)
+        buf = np.zeros(n, np.uint8)
+        _check(self.L.avbd_snapshot(self.h, buf.ctypes.data_as(C.c_void_p), n))
+        return buf
+
+    def restore(self, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        _check(self.L.avbd_restore(self.h, blob.ctypes.data_as(C.c_void_p), len(blob)))
 
     # -- stages
     def stage_broadphase(self):

@@ -97,7 +97,7 @@ struct avbd_world {
 
     // manifolds (ping-pong)
     struct MBuf { DevBuf<unsigned long long> key; DevBuf<int4> hdr; DevBuf<int> cstart, cM; DevBuf<float4> cA, cB, cN; DevBuf<ContactLP> lp; } mb[2];
-    int cur = 0, nM = 0;
+    int cur = 0, nM = 0, nMPrev = 0;
 
     // graph
     DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
@@ -387,20 +387,21 @@ int run_collide(avbd_world* w) {
     cudaStream_t s = w->stream;
     TRY(prepare(w));
     if (w->n > 0) CK(cudaMemsetAsync(w->dDiag.p, 0, sizeof(Diag) * w->nWorlds, s));
-    if (w->timed) cudaEventRecord(w->ev[0], s);
+    if (w->timed || w->profiling) cudaEventRecord(w->ev[0], s);
+    w->nMPrev = w->nM;
     TRY(run_broadphase(w, true));
-    if (w->timed) cudaEventRecord(w->ev[1], s);
+    if (w->timed || w->profiling) cudaEventRecord(w->ev[1], s);
     int nSurv = w->nCand;
     int nxt = w->cur ^ 1;
     if (nSurv > 0) {
         TRY(w->ensure_manifolds(nxt, nSurv)); TRY(w->ensure_stage(nSurv));
         TRY(w->mcount.ensure((size_t)nSurv + 1, false, s));
         CK(cudaMemsetAsync(w->mcount.p + nSurv, 0, sizeof(int), s));
-        static const bool polySmem = [] {
+        static bool polySmem[64] = {false};          // a function attribute is per device
+        if (!polySmem[w->device & 63]) {
             cudaFuncSetAttribute(np_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildThreads * kPolyFloatsPerThread * (int)sizeof(float));
-            return true;
-        }();
-        (void)polySmem;
+            polySmem[w->device & 63] = true;
+        }
         launch_dep(np_build, dim3(blocks_for(nSurv, kBuildThreads)), dim3(kBuildThreads), kBuildThreads * kPolyFloatsPerThread * sizeof(float), s, 
             w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift, w->mset(w->cur), w->nM, w->mset(nxt), w->stage(), w->mcount.p, w->prm, w->dCnt);
         w->launches++;
@@ -424,7 +425,7 @@ int run_collide(avbd_world* w) {
     }
     w->graphValid = sameTopology;
     w->visitGeomStale = true;         // every contact was rebuilt
-    if (w->timed) cudaEventRecord(w->ev[2], s);
+    if (w->timed || w->profiling) cudaEventRecord(w->ev[2], s);
     CK(cudaGetLastError());
     return 0;
 }
@@ -555,8 +556,11 @@ int run_colour(avbd_world* w) {
     return 0;
 }
 
-// alphaDual >= 0: the sweep also applies the previous iteration's pending dual pass (deferred dual, avbd_solve.cu).
-int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f) {
+// biasDual >= 0: the sweep also applies the previous iteration's pending dual pass (deferred dual, avbd_solve.cu); it is that
+// pass's clamp(1 - alpha, 0, 1) (manifold.cpp:179), which lies in [0, 1] for EVERY alpha a caller may set, so a negative value
+// can only mean "nothing pending".
+inline float dual_bias(float alpha) { float b = 1.0f - alpha; b = b > 0.0f ? b : 0.0f; return b < 1.0f ? b : 1.0f; }
+int run_primal(avbd_world* w, float alpha, float* dxDev, float biasDual = -1.0f) {
     if (!w->graphValid) TRY(run_colour(w));
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
@@ -575,7 +579,7 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float alphaDual = -1.0f
         if (count <= 0) continue;
         w->launches += launch_primal_flat(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->colOrder.p, w->visitStart.p, w->kOf.p, first, count,
                                           w->hColVisit[c].x, w->hColVisit[c].y, w->flatGrid[c], w->flatAligned ? w->flatRange.p + w->flatRangeOff[c] : nullptr,
-                                          w->prm, alpha, alphaDual, w->sums.p, w->carry.p, dxDev, w->dDiag.p);
+                                          w->prm, alpha, biasDual, w->sums.p, w->carry.p, dxDev, w->dDiag.p);
     }
     CK(cudaGetLastError());
     return 0;
@@ -618,9 +622,10 @@ int step_once(avbd_world* w) {
     cudaStream_t s = w->stream;
     TRY(run_collide(w));
     TRY(run_predict(w));
-    if (w->timed) cudaEventRecord(w->ev[3], s);
+    if (w->timed || w->profiling) cudaEventRecord(w->ev[3], s);
+    bool rebuiltGraph = !w->graphValid;
     if (!w->graphValid) TRY(run_colour(w)); else w->graphReuses++;
-    if (w->timed) cudaEventRecord(w->ev[4], s);
+    if (w->timed || w->profiling) cudaEventRecord(w->ev[4], s);
     int total = w->prm.iterations + (w->prm.postStabilize ? 1 : 0);
     bool prof = w->profiling;
     ForceView fvAll = w->fview();
@@ -641,26 +646,26 @@ int step_once(avbd_world* w) {
     const char* sepEnv = getenv("AVBD_SEPARATE_DUAL");
     const bool separateDual = sepEnv && atoi(sepEnv) != 0;
     int duals = 0, deferred = 0;
-    float pendingAlpha = -1.0f;
+    float pendingBias = -1.0f;
     for (int it = 0; it < total && !persistent; ++it) {
         float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
-        TRY(run_primal(w, a, nullptr, pendingAlpha));
-        if (pendingAlpha >= 0.0f) ++deferred;
-        pendingAlpha = -1.0f;
+        TRY(run_primal(w, a, nullptr, pendingBias));
+        if (pendingBias >= 0.0f) ++deferred;
+        pendingBias = -1.0f;
         if (prof) cudaEventRecord(w->pev[2 * it + 1], s);
         if (it < w->prm.iterations) {
             bool lastSweep = it == total - 1;                 // nothing moves after this pass: it also reduces the contact diagnostics
             if (separateDual) { TRY(run_dual(w, a, lastSweep)); ++duals; }
             else if (lastSweep) { TRY(run_dual(w, a, true, true, w->prm.iterations, false)); ++duals; }
-            else { TRY(run_dual(w, a, false, false)); pendingAlpha = a; }
+            else { TRY(run_dual(w, a, false, false)); pendingBias = dual_bias(a); }
         } else if (!separateDual && w->anyUnvisited && w->prm.iterations > 0) {
             TRY(run_dual(w, 1.0f, false, true, w->prm.iterations, true));    // postStabilize: contacts between static bodies only
         }
         if (prof) cudaEventRecord(w->pev[2 * it + 2], s);
     }
-    if (w->timed) cudaEventRecord(w->ev[5], s);
+    if (w->timed || w->profiling) cudaEventRecord(w->ev[5], s);
     TRY(run_velocity(w));
-    if (w->timed) cudaEventRecord(w->ev[6], s);
+    if (w->timed || w->profiling) cudaEventRecord(w->ev[6], s);
     if (prof) {
         CK(cudaStreamSynchronize(s));
         for (int it = 0; it < total; ++it) {
@@ -676,6 +681,13 @@ int step_once(avbd_world* w) {
         w->prof.primal_bodies += (long long)total * w->nDyn; w->prof.primal_visits += (long long)total * visits;
         w->prof.dual_launches += duals; w->prof.dual_contacts += (long long)duals * contacts;
         w->prof.deferred_dual_contacts += (long long)deferred * contacts;
+        float t[6] = {0, 0, 0, 0, 0, 0}, tot = 0;
+        for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], w->ev[k], w->ev[k + 1]);
+        cudaEventElapsedTime(&tot, w->ev[0], w->ev[6]);
+        w->prof.ms_broadphase += t[0]; w->prof.ms_narrowphase += t[1]; w->prof.ms_predict += t[2]; w->prof.ms_graph += t[3];
+        w->prof.ms_solve += t[4]; w->prof.ms_velocity += t[5]; w->prof.ms_step += tot;
+        w->prof.bodies += w->n; w->prof.pairs += w->nPairs; w->prof.candidates += w->nCand; w->prof.manifolds += w->nM; w->prof.manifolds_prev += w->nMPrev;
+        w->prof.contacts += contacts; w->prof.visits += visits; w->prof.graph_builds += rebuiltGraph ? 1 : 0;
     }
     return 0;
 }
@@ -701,6 +713,13 @@ int use_device(int device) {
 extern "C" {
 
 const char* avbd_last_error(void) { return g_err.c_str(); }
+
+void* avbd_host_alloc(long long bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); fail(AVBD_ERR_CUDA, "pinned host allocation failed"); return nullptr; }
+    return p;
+}
+void avbd_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int avbd_device_count(void) {
     int count = 0;
@@ -784,6 +803,14 @@ int avbd_add_bodies(avbd_world* w, int count, const float* size3, const float* d
     int first = w->n, total = first + count;
     std::vector<BodyPose> pose(count); std::vector<BodyAux> aux(count); std::vector<BodyVel> vel(count); std::vector<BodyInit> init(count);
     std::vector<float4> prev(count), size(count);
+    if (world_ids) {       // validate everything before touching any state: a mid-loop failure would leave hb[] misaligned with the device
+        int prevWorld = w->hb.empty() ? -1 : w->hb.back().world;
+        for (int i = 0; i < count; ++i) {
+            if (world_ids[i] < 0 || world_ids[i] < prevWorld || world_ids[i] > prevWorld + 1)
+                return fail(AVBD_ERR_ARG, "world ids must start at 0 and be non-decreasing without gaps");
+            prevWorld = world_ids[i];
+        }
+    }
     w->hb.reserve(total);
     for (int i = 0; i < count; ++i) {
         // Rigid::Rigid, rigid.cpp:12-41
@@ -809,7 +836,6 @@ int avbd_add_bodies(avbd_world* w, int count, const float* size3, const float* d
         size[i] = make_float4(sx, sy, sz, friction[i]);
         HostBody hb; hb.radius = radius; hb.invMass = invMass; hb.world = world_ids ? world_ids[i] : 0;
         int prevWorld = w->hb.empty() ? -1 : w->hb.back().world;
-        if (hb.world < prevWorld) return fail(AVBD_ERR_ARG, "world ids must be non-decreasing");
         hb.local = (hb.world == prevWorld) ? w->hb.back().local + 1 : 0;
         w->hb.push_back(hb);
     }
@@ -838,32 +864,40 @@ int fetch_pose(avbd_world* w, int i, BodyPose& out) {
 }
 }
 
+namespace {
+int push_joint(avbd_world* w, int a, int b, float4 rA, float4 rB, float4 rel0, float linK, float angK) {
+    JointRec j{};
+    j.a = a; j.b = b; j.rA = rA; j.rB = rB; j.rel0 = rel0;
+    for (int r = 0; r < 6; ++r) { j.lambda[r] = 0.0f; j.penalty[r] = kPenaltyMin; j.stiffness[r] = r < 3 ? linK : angK; j.motor[r] = 0.0f; }
+    w->hJoints.push_back(j);
+    w->hForces.push_back(HostForce{0, a, b});
+    w->forcesDirty = true;
+    return (int)w->hJoints.size() - 1;
+}
+}
+
 int avbd_add_joint(avbd_world* w, int a, int b, const float* anchorA, const float* anchorB, float linK, float angK) {
     if (!w || b < 0 || b >= w->n || a >= w->n || a == b || !anchorA) return fail(AVBD_ERR_ARG, "bad joint");
     CK(cudaSetDevice(w->device));
-    JointRec j{};
-    j.a = a; j.b = b; j.kLin = linK; j.kAng = angK;
     BodyPose pb; TRY(fetch_pose(w, b, pb));
     Q4 qB = quat(pb.rot);
     if (a >= 0) {
         if (!anchorB) return fail(AVBD_ERR_ARG, "bad joint");
         BodyPose pa; TRY(fetch_pose(w, a, pa));
-        j.rA = make_float4(anchorA[0], anchorA[1], anchorA[2], 0.f); j.rB = make_float4(anchorB[0], anchorB[1], anchorB[2], 0.f);
-        j.rel0 = f4(qmul(qconj(quat(pa.rot)), qB));                                 // joint.cpp:19
-    } else {
-        V3 wa = mk3(anchorA[0], anchorA[1], anchorA[2]);
-        j.rA = f4(wa, 0.f);
-        M3 R = qmat(qB);                                                            // joint.cpp:47: transpose(R) * (anchor - pos)
-        V3 d = wa - xyz(pb.pos);
-        M3 Rt = m3(mk3(R.c[0].x, R.c[1].x, R.c[2].x), mk3(R.c[0].y, R.c[1].y, R.c[2].y), mk3(R.c[0].z, R.c[1].z, R.c[2].z));
-        j.rB = f4(mv(Rt, d), 0.f);
-        j.rel0 = f4(qB);
+        return push_joint(w, a, b, make_float4(anchorA[0], anchorA[1], anchorA[2], 0.f), make_float4(anchorB[0], anchorB[1], anchorB[2], 0.f),
+                          f4(qmul(qconj(quat(pa.rot)), qB)), linK, angK);                    // joint.cpp:19
     }
-    for (int r = 0; r < 6; ++r) { j.lambda[r] = 0.0f; j.penalty[r] = kPenaltyMin; }
-    w->hJoints.push_back(j);
-    w->hForces.push_back(HostForce{0, a, b});
-    w->forcesDirty = true;
-    return (int)w->hJoints.size() - 1;
+    V3 wa = mk3(anchorA[0], anchorA[1], anchorA[2]);
+    M3 R = qmat(qB);                                                            // joint.cpp:47: transpose(R) * (anchor - pos)
+    V3 d = wa - xyz(pb.pos);
+    M3 Rt = m3(mk3(R.c[0].x, R.c[1].x, R.c[2].x), mk3(R.c[0].y, R.c[1].y, R.c[2].y), mk3(R.c[0].z, R.c[1].z, R.c[2].z));
+    return push_joint(w, a, b, f4(wa, 0.f), f4(mv(Rt, d), 0.f), f4(qB), linK, angK);
+}
+
+int avbd_add_joint_raw(avbd_world* w, int a, int b, const float* rA3, const float* rB3, const float* rel0, float linK, float angK) {
+    if (!w || b < 0 || b >= w->n || a >= w->n || a < -1 || a == b || !rA3 || !rB3 || !rel0) return fail(AVBD_ERR_ARG, "bad joint");
+    return push_joint(w, a, b, make_float4(rA3[0], rA3[1], rA3[2], 0.f), make_float4(rB3[0], rB3[1], rB3[2], 0.f),
+                      make_float4(rel0[0], rel0[1], rel0[2], rel0[3]), linK, angK);
 }
 
 int avbd_add_spring(avbd_world* w, int a, int b, const float* anchorA, const float* anchorB, float k, float rest) {
@@ -877,7 +911,7 @@ int avbd_add_spring(avbd_world* w, int a, int b, const float* anchorA, const flo
         V3 pA = xyz(pa.pos) + qrot(quat(pa.rot), xyz(sp.rA)), pB = xyz(pb.pos) + qrot(quat(pb.rot), xyz(sp.rB));
         sp.rest = len(pA - pB);
     }
-    sp.lambda = 0.0f; sp.penalty = kPenaltyMin;
+    sp.lambda = 0.0f; sp.penalty = kPenaltyMin; sp.motor = 0.0f;
     w->hSprings.push_back(sp);
     w->hForces.push_back(HostForce{1, a, b});
     w->forcesDirty = true;
@@ -888,6 +922,227 @@ int avbd_add_ignore(avbd_world* w, int a, int b) {
     if (!w || a < 0 || b < 0 || a >= w->n || b >= w->n || a == b) return fail(AVBD_ERR_ARG, "bad ignore pair");
     w->hForces.push_back(HostForce{2, a, b});
     w->forcesDirty = true;
+    return 0;
+}
+
+int avbd_set_force_rows(avbd_world* w, int kind, int index, const float* lambda, const float* penalty, const float* motor, const float* stiffness) {
+    if (!w || kind < 0 || kind > 1 || index < 0 || index >= (int)(kind == 0 ? w->hJoints.size() : w->hSprings.size()))
+        return fail(AVBD_ERR_ARG, "bad force row edit");
+    CK(cudaSetDevice(w->device));
+    TRY(prepare(w));                         // the record is on the device from here on (lambda / penalty live there)
+    cudaStream_t s = w->stream;
+    if (kind == 0) {
+        JointRec j;
+        CK(cudaMemcpyAsync(&j, w->joints.p + index, sizeof(j), cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+        for (int r = 0; r < 6; ++r) {
+            if (lambda) j.lambda[r] = lambda[r];
+            if (penalty) j.penalty[r] = penalty[r];
+            if (motor) j.motor[r] = motor[r];
+            if (stiffness) j.stiffness[r] = stiffness[r];
+        }
+        w->hJoints[index] = j;
+        CK(cudaMemcpyAsync(w->joints.p + index, &w->hJoints[index], sizeof(j), cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
+    } else {
+        SpringRec sp;
+        CK(cudaMemcpyAsync(&sp, w->springs.p + index, sizeof(sp), cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+        if (lambda) sp.lambda = lambda[0];
+        if (penalty) sp.penalty = penalty[0];
+        if (motor) sp.motor = motor[0];
+        if (stiffness) sp.k = stiffness[0];
+        w->hSprings[index] = sp;
+        CK(cudaMemcpyAsync(w->springs.p + index, &w->hSprings[index], sizeof(sp), cudaMemcpyHostToDevice, s)); CK(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int avbd_get_force_rows(avbd_world* w, int kind, int index, float* lambda, float* penalty, float* motor, float* stiffness) {
+    if (!w || kind < 0 || kind > 1 || index < 0 || index >= (int)(kind == 0 ? w->hJoints.size() : w->hSprings.size()))
+        return fail(AVBD_ERR_ARG, "bad force row query");
+    CK(cudaSetDevice(w->device));
+    TRY(prepare(w));
+    cudaStream_t s = w->stream;
+    if (kind == 0) {
+        JointRec j;
+        CK(cudaMemcpyAsync(&j, w->joints.p + index, sizeof(j), cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+        for (int r = 0; r < 6; ++r) {
+            if (lambda) lambda[r] = j.lambda[r];
+            if (penalty) penalty[r] = j.penalty[r];
+            if (motor) motor[r] = j.motor[r];
+            if (stiffness) stiffness[r] = j.stiffness[r];
+        }
+    } else {
+        SpringRec sp;
+        CK(cudaMemcpyAsync(&sp, w->springs.p + index, sizeof(sp), cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s));
+        if (lambda) lambda[0] = sp.lambda;
+        if (penalty) penalty[0] = sp.penalty;
+        if (motor) motor[0] = sp.motor;
+        if (stiffness) stiffness[0] = sp.k;
+    }
+    return 0;
+}
+
+int avbd_num_joints(const avbd_world* w) { return w ? (int)w->hJoints.size() : 0; }
+int avbd_num_springs(const avbd_world* w) { return w ? (int)w->hSprings.size() : 0; }
+
+int avbd_download_user_rows(avbd_world* w, float* joints12, float* springs2) {
+    if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    TRY(prepare(w));
+    cudaStream_t s = w->stream;
+    size_t nj = w->hJoints.size(), ns = w->hSprings.size();
+    if (nj && joints12) CK(cudaMemcpyAsync(w->hJoints.data(), w->joints.p, nj * sizeof(JointRec), cudaMemcpyDeviceToHost, s));
+    if (ns && springs2) CK(cudaMemcpyAsync(w->hSprings.data(), w->springs.p, ns * sizeof(SpringRec), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (joints12) for (size_t k = 0; k < nj; ++k) for (int r = 0; r < 6; ++r) { joints12[12 * k + r] = w->hJoints[k].lambda[r]; joints12[12 * k + 6 + r] = w->hJoints[k].penalty[r]; }
+    if (springs2) for (size_t k = 0; k < ns; ++k) { springs2[2 * k] = w->hSprings[k].lambda; springs2[2 * k + 1] = w->hSprings[k].penalty; }
+    return 0;
+}
+
+int avbd_upload_manifolds(avbd_world* w, int count, const int* ints, const int* feats, const int* stick, const float* flts) {
+    if (!w || count < 0 || (count > 0 && (!ints || !feats || !stick || !flts))) return fail(AVBD_ERR_ARG, "bad argument to avbd_upload_manifolds");
+    CK(cudaSetDevice(w->device));
+    TRY(prepare(w));
+    cudaStream_t s = w->stream;
+    std::vector<int> idx(count);
+    size_t nC = 0;
+    for (int m = 0; m < count; ++m) {
+        int a = ints[3 * m], b = ints[3 * m + 1], nc = ints[3 * m + 2];
+        if (a <= b || b < 0 || a >= w->n || nc < 1 || nc > 4) return fail(AVBD_ERR_ARG, "bad manifold (need n > idxA > idxB >= 0, 1..4 contacts)");
+        idx[m] = m; nC += (size_t)nc;
+    }
+    auto key_of = [&](int m) { return ((unsigned long long)(unsigned)ints[3 * m] << w->keyShift) | (unsigned)ints[3 * m + 1]; };
+    std::sort(idx.begin(), idx.end(), [&](int x, int y) { return key_of(x) < key_of(y); });
+    for (int m = 1; m < count; ++m) if (key_of(idx[m]) == key_of(idx[m - 1])) return fail(AVBD_ERR_ARG, "duplicate manifold pair");
+    std::vector<unsigned long long> key(count); std::vector<int4> hdr(count); std::vector<int> cstart(count + 1), cM(nC);
+    std::vector<float4> cA(nC), cB(nC), cN(nC); std::vector<ContactLP> lp(nC);
+    size_t ci = 0;
+    for (int q = 0; q < count; ++q) {
+        int m = idx[q];
+        const float* f = flts + 81 * (size_t)m;
+        int nc = ints[3 * m + 2];
+        int muBits; std::memcpy(&muBits, &f[0], 4);
+        key[q] = key_of(m); hdr[q] = make_int4(ints[3 * m], ints[3 * m + 1], nc, muBits); cstart[q] = (int)ci;
+        for (int c = 0; c < nc; ++c, ++ci) {
+            const float* g = f + 1 + 14 * c;
+            cA[ci] = make_float4(g[0], g[1], g[2], g[10]); cB[ci] = make_float4(g[3], g[4], g[5], g[11]); cN[ci] = make_float4(g[6], g[7], g[8], g[12]);
+            float featBits; std::memcpy(&featBits, &feats[4 * m + c], 4);
+            lp[ci].l = make_float4(f[57 + 3 * c], f[58 + 3 * c], f[59 + 3 * c], stick[4 * m + c] ? 1.0f : 0.0f);
+            lp[ci].p = make_float4(f[69 + 3 * c], f[70 + 3 * c], f[71 + 3 * c], featBits);
+            cM[ci] = q;
+        }
+    }
+    cstart[count] = (int)ci;
+    w->nM = count; w->nContacts = (int)nC;
+    if (count > 0) {
+        TRY(w->ensure_manifolds(w->cur, count));
+        ManifoldSet ms = w->mset(w->cur);
+        CK(cudaMemcpyAsync(ms.key, key.data(), count * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ms.hdr, hdr.data(), count * sizeof(int4), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ms.cstart, cstart.data(), (count + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ms.cM, cM.data(), nC * sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ms.cA, cA.data(), nC * sizeof(float4), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ms.cB, cB.data(), nC * sizeof(float4), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ms.cN, cN.data(), nC * sizeof(float4), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ms.lp, lp.data(), nC * sizeof(ContactLP), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false;
+    return 0;
+}
+
+// ---- snapshot / restore -------------------------------------------------------------------------------------------------------
+namespace {
+struct SnapHeader {
+    char magic[8];
+    int version, n, nM, nContacts, nJoints, nSprings, nForces, keyShift;
+    SolveParams prm;
+    long long bytes;
+};
+constexpr char kSnapMagic[8] = {'A', 'V', 'B', 'D', 'S', 'N', 'P', '2'};
+size_t snap_bytes(const avbd_world* w) {
+    size_t n = w->n, m = w->nM, c = w->nContacts;
+    return sizeof(SnapHeader) + n * (sizeof(HostBody) + sizeof(BodyPose) + sizeof(BodyAux) + sizeof(BodyVel) + sizeof(BodyInit) + 2 * sizeof(float4))
+         + w->hJoints.size() * sizeof(JointRec) + w->hSprings.size() * sizeof(SpringRec) + w->hForces.size() * sizeof(HostForce)
+         + m * (sizeof(unsigned long long) + sizeof(int4)) + (m + 1) * sizeof(int) + c * (sizeof(int) + 3 * sizeof(float4) + sizeof(ContactLP));
+}
+}
+
+long long avbd_snapshot_bytes(avbd_world* w) { return w ? (long long)snap_bytes(w) : 0; }
+
+int avbd_snapshot(avbd_world* w, void* buf, long long cap) {
+    if (!w || !buf) return fail(AVBD_ERR_ARG, "null argument");
+    CK(cudaSetDevice(w->device));
+    TRY(prepare(w));                                   // user-force records are on the device
+    size_t need = snap_bytes(w);
+    if ((long long)need > cap) return fail(AVBD_ERR_CAPACITY, "snapshot buffer too small (see avbd_snapshot_bytes)");
+    cudaStream_t s = w->stream;
+    char* o = static_cast<char*>(buf);
+    SnapHeader h{};
+    std::memcpy(h.magic, kSnapMagic, 8);
+    h.version = 2; h.n = w->n; h.nM = w->nM; h.nContacts = w->nContacts; h.nJoints = (int)w->hJoints.size(); h.nSprings = (int)w->hSprings.size();
+    h.nForces = (int)w->hForces.size(); h.keyShift = w->keyShift; h.prm = w->prm; h.bytes = (long long)need;
+    std::memcpy(o, &h, sizeof(h)); o += sizeof(h);
+    auto put_host = [&](const void* src, size_t bytes) { if (bytes) std::memcpy(o, src, bytes); o += bytes; };
+    auto put_dev = [&](const void* src, size_t bytes) -> int {
+        if (bytes) CK(cudaMemcpyAsync(o, src, bytes, cudaMemcpyDeviceToHost, s));
+        o += bytes; return 0;
+    };
+    size_t n = w->n, m = w->nM, c = w->nContacts;
+    put_host(w->hb.data(), n * sizeof(HostBody));
+    TRY(put_dev(w->pose.p, n * sizeof(BodyPose))); TRY(put_dev(w->aux.p, n * sizeof(BodyAux))); TRY(put_dev(w->vel.p, n * sizeof(BodyVel)));
+    TRY(put_dev(w->init.p, n * sizeof(BodyInit))); TRY(put_dev(w->prevLin.p, n * sizeof(float4))); TRY(put_dev(w->size.p, n * sizeof(float4)));
+    TRY(put_dev(w->joints.p, w->hJoints.size() * sizeof(JointRec))); TRY(put_dev(w->springs.p, w->hSprings.size() * sizeof(SpringRec)));
+    put_host(w->hForces.data(), w->hForces.size() * sizeof(HostForce));
+    ManifoldSet ms = w->mset(w->cur);
+    if (m) {
+        TRY(put_dev(ms.key, m * sizeof(unsigned long long))); TRY(put_dev(ms.hdr, m * sizeof(int4))); TRY(put_dev(ms.cstart, (m + 1) * sizeof(int)));
+        TRY(put_dev(ms.cM, c * sizeof(int))); TRY(put_dev(ms.cA, c * sizeof(float4))); TRY(put_dev(ms.cB, c * sizeof(float4)));
+        TRY(put_dev(ms.cN, c * sizeof(float4))); TRY(put_dev(ms.lp, c * sizeof(ContactLP)));
+    } else {
+        int zero = 0; put_host(&zero, sizeof(int));
+    }
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int avbd_restore(avbd_world* w, const void* buf, long long bytes) {
+    if (!w || !buf || bytes < (long long)sizeof(SnapHeader)) return fail(AVBD_ERR_ARG, "bad snapshot");
+    CK(cudaSetDevice(w->device));
+    SnapHeader h;
+    std::memcpy(&h, buf, sizeof(h));
+    if (std::memcmp(h.magic, kSnapMagic, 8) != 0 || h.version != 2 || h.bytes > bytes || h.n < 0 || h.nM < 0 || h.nContacts < 0)
+        return fail(AVBD_ERR_ARG, "not a snapshot of this library build");
+    TRY(avbd_clear(w));
+    cudaStream_t s = w->stream;
+    const char* o = static_cast<const char*>(buf) + sizeof(h);
+    size_t n = h.n, m = h.nM, c = h.nContacts;
+    w->prm = h.prm;
+    w->hb.assign(reinterpret_cast<const HostBody*>(o), reinterpret_cast<const HostBody*>(o) + n); o += n * sizeof(HostBody);
+    auto get_dev = [&](void* dst, size_t nbytes) -> int {
+        if (nbytes) CK(cudaMemcpyAsync(dst, o, nbytes, cudaMemcpyHostToDevice, s));
+        o += nbytes; return 0;
+    };
+    TRY(w->pose.ensure(n, false, s)); TRY(w->aux.ensure(n, false, s)); TRY(w->vel.ensure(n, false, s)); TRY(w->init.ensure(n, false, s));
+    TRY(w->prevLin.ensure(n, false, s)); TRY(w->size.ensure(n, false, s));
+    TRY(get_dev(w->pose.p, n * sizeof(BodyPose))); TRY(get_dev(w->aux.p, n * sizeof(BodyAux))); TRY(get_dev(w->vel.p, n * sizeof(BodyVel)));
+    TRY(get_dev(w->init.p, n * sizeof(BodyInit))); TRY(get_dev(w->prevLin.p, n * sizeof(float4))); TRY(get_dev(w->size.p, n * sizeof(float4)));
+    w->n = (int)n;
+    w->hJoints.assign(reinterpret_cast<const JointRec*>(o), reinterpret_cast<const JointRec*>(o) + h.nJoints); o += (size_t)h.nJoints * sizeof(JointRec);
+    w->hSprings.assign(reinterpret_cast<const SpringRec*>(o), reinterpret_cast<const SpringRec*>(o) + h.nSprings); o += (size_t)h.nSprings * sizeof(SpringRec);
+    w->hForces.assign(reinterpret_cast<const HostForce*>(o), reinterpret_cast<const HostForce*>(o) + h.nForces); o += (size_t)h.nForces * sizeof(HostForce);
+    w->uploadedJoints = 0; w->uploadedSprings = 0;            // prepare() uploads the records (with their saved lambda / penalty)
+    w->topoDirty = true; w->forcesDirty = true;
+    w->keyShift = h.keyShift;                                 // the saved keys are packed with it; prepare() re-derives the same value from n
+    w->cur = 0; w->nM = (int)m; w->nContacts = (int)c;
+    if (m) {
+        TRY(w->ensure_manifolds(0, m));
+        ManifoldSet ms = w->mset(0);
+        TRY(get_dev(ms.key, m * sizeof(unsigned long long))); TRY(get_dev(ms.hdr, m * sizeof(int4))); TRY(get_dev(ms.cstart, (m + 1) * sizeof(int)));
+        TRY(get_dev(ms.cM, c * sizeof(int))); TRY(get_dev(ms.cA, c * sizeof(float4))); TRY(get_dev(ms.cB, c * sizeof(float4)));
+        TRY(get_dev(ms.cN, c * sizeof(float4))); TRY(get_dev(ms.lp, c * sizeof(ContactLP)));
+    }
+    CK(cudaStreamSynchronize(s));
+    w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false; w->lastPairs = 0;
     return 0;
 }
 
@@ -952,6 +1207,18 @@ int avbd_upload_state(avbd_world* w, const float* in) {
     TRY(w->stateDev.ensure((size_t)n * 13, false, w->stream));
     CK(cudaMemcpyAsync(w->stateDev.p, in, (size_t)n * 13 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
     launch_dep(unpack_state, dim3(blocks_for(n)), dim3(kThreads), 0, w->stream, w->bview(), w->stateDev.p);
+    w->launches++;
+    CK(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int avbd_upload_state_range(avbd_world* w, int first, int count, const float* in) {
+    if (!w || first < 0 || count < 0 || first + count > w->n || (!in && count)) return fail(AVBD_ERR_ARG, "bad body range");
+    CK(cudaSetDevice(w->device));
+    if (!count) return 0;
+    TRY(w->stateDev.ensure((size_t)w->n * 13, false, w->stream));
+    CK(cudaMemcpyAsync(w->stateDev.p + (size_t)first * 13, in, (size_t)count * 13 * sizeof(float), cudaMemcpyHostToDevice, w->stream));
+    launch_dep(unpack_state_range, dim3(blocks_for(count)), dim3(kThreads), 0, w->stream, w->bview(), w->stateDev.p, first, count);
     w->launches++;
     CK(cudaStreamSynchronize(w->stream));
     return 0;

@@ -272,7 +272,7 @@ __global__ void decay_user_forces(ForceView fv, SolveParams prm) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < fv.nJoints) {
         JointRec& j = fv.joints[t];
-        for (int r = 0; r < 6; ++r) decay_row(j.lambda[r], j.penalty[r], r < 3 ? j.kLin : j.kAng, prm);
+        for (int r = 0; r < 6; ++r) decay_row(j.lambda[r], j.penalty[r], j.stiffness[r], prm);
     } else if (t - fv.nJoints < fv.nSprings) {
         SpringRec& s = fv.springs[t - fv.nJoints];
         decay_row(s.lambda, s.penalty, s.k, prm);
@@ -338,6 +338,18 @@ __global__ void unpack_state(BodyView b, const float* in13) {
     cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= b.n) return;
+    const float* o = in13 + 13 * (size_t)i;
+    float invMass = b.aux[i].mass.y;
+    BodyPose p; p.pos = make_float4(o[0], o[1], o[2], invMass); p.rot = make_float4(o[3], o[4], o[5], o[6]);
+    BodyVel v; v.lin = make_float4(o[7], o[8], o[9], 0.f); v.ang = make_float4(o[10], o[11], o[12], 0.f);
+    b.pose[i] = p; b.vel[i] = v;
+}
+
+__global__ void unpack_state_range(BodyView b, const float* in13, int first, int count) {
+    cudaGridDependencySynchronize();
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    int i = first + k;
     const float* o = in13 + 13 * (size_t)i;
     float invMass = b.aux[i].mass.y;
     BodyPose p; p.pos = make_float4(o[0], o[1], o[2], invMass); p.rot = make_float4(o[3], o[4], o[5], o[6]);

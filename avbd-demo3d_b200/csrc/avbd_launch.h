@@ -125,13 +125,13 @@ constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodie
 // primal_flat_grid(vEnd - vBegin).  `range` == nullptr: chunks round-robin over the blocks, `carry` takes 28 floats per chunk;
 // `range` != nullptr (batches of several worlds): the colour's grid + 1 body-aligned block boundaries (launch_flat_ranges, once
 // per graph build) — sums do not depend on the batch.  `sums` holds 28 floats per dynamic body (row = position in `order`).
-// alphaDual >= 0: the previous iteration's dual pass (run with that alpha) is still pending and each contact's first visit applies
+// biasDual >= 0: the previous iteration's dual pass (whose clamp(1 - alpha, 0, 1) it is; any alpha maps into [0, 1], so the sign is free to mean "none") is still pending and each contact's first visit applies
 // it (deferred dual); < 0: plain primal sweep.  Returns the kernels launched.
 int primal_flat_chunk_threads();
 int primal_flat_grid(int nVisits);
 void launch_flat_ranges(cudaStream_t s, const int* vstart, int first, int count, int vBegin, int vEnd, int grid, int* range);
 int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                       const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float alphaDual,
+                       const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float biasDual,
                        float* sums, float* carry, float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live (densely stored) contacts.
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics

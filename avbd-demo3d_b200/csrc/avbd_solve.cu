@@ -12,7 +12,7 @@
 // static or has a higher colour) neither endpoint has moved yet, so that visit sees exactly the poses the dual pass
 // would have seen: it applies the pending dual update in registers (same operations, same order), then evaluates the
 // primal rows, and writes lambda / penalty back once.  A step therefore runs ONE stand-alone dual pass (after the last
-// sweep, fused with the contact diagnostics) instead of `iterations` of them.  alphaDual < 0 = nothing pending (first sweep
+// sweep, fused with the contact diagnostics) instead of `iterations` of them.  biasDual (= clamp(1 - alpha, 0, 1) of the pending pass; manifold.cpp:179) < 0 = nothing pending (first sweep
 // of a step, stage API).
 #include <cstdio>
 #include <cstdlib>
@@ -43,7 +43,7 @@ __device__ void accumulate_user_forces(BodySystem& s, const ForceView& fv, const
             V3 Jl, Ja;
             spring_jacobian(sp, hasA, pA, qA, pB, qB, isA, Jl, Ja);
             float lamWarm = (sp.k == FLT_MAX) ? sp.lambda : 0.0f;
-            float f = clampf(sp.penalty * C + lamWarm + 0.0f, -FLT_MAX, FLT_MAX);
+            float f = clampf(sp.penalty * C + lamWarm + sp.motor, -FLT_MAX, FLT_MAX);
             accumulate_row(s, Jl, Ja, f, sp.penalty, false, invIw);
         } else {
             const JointRec& j = fv.joints[idx];
@@ -57,9 +57,8 @@ __device__ void accumulate_user_forces(BodySystem& s, const ForceView& fv, const
             for (int r = 0; r < 6; ++r) {
                 V3 Jl, Ja;
                 joint_jacobian(j, isA, rot, r, Jl, Ja);
-                float k_ = r < 3 ? j.kLin : j.kAng;
-                float lamWarm = (k_ == FLT_MAX) ? j.lambda[r] : 0.0f;
-                float f = clampf(j.penalty[r] * ev.C[r] + lamWarm + 0.0f, ev.fmin[r], ev.fmax[r]);
+                float lamWarm = (j.stiffness[r] == FLT_MAX) ? j.lambda[r] : 0.0f;
+                float f = clampf(j.penalty[r] * ev.C[r] + lamWarm + j.motor[r], ev.fmin[r], ev.fmax[r]);
                 accumulate_row(s, Jl, Ja, f, j.penalty[r], false, invIw);
             }
         }
@@ -198,12 +197,12 @@ __device__ __forceinline__ float rows_geometry(float4 sp, float4 sq, float4 op, 
     float ims = sp.w + op.w;
     return kNormalForceCap * ((ims > 1.0e-6f) ? __fdividef(1.0f, ims) : 1.0f);       // normal force cap (manifold.cpp:199-203)
 }
-__device__ __forceinline__ void visit_rows(float4 sp, float4 sq, float4 op, float4 oq, float sg, float mu, float alpha, bool pending, float alphaDual,
+__device__ __forceinline__ void visit_rows(float4 sp, float4 sq, float4 op, float4 oq, float sg, float mu, float alpha, bool pending, float biasDual,
                                            float beta, bool gyro, const M3& invIw, ContactState& cs, BodySystem& sys) {
     ContactEval ev; float sep[3];
     float cap = rows_geometry(sp, sq, op, oq, sg, cs, ev, sep);
     if (pending) {
-        limits_fast(cap, mu, fminf(fmaxf(1.0f - alphaDual, 0.0f), 1.0f), sep, cs, ev);
+        limits_fast(cap, mu, biasDual, sep, cs, ev);
         dual_fast(cs, ev, beta);
     }
     limits_fast(cap, mu, fminf(fmaxf(1.0f - alpha, 0.0f), 1.0f), sep, cs, ev);
@@ -284,7 +283,7 @@ __device__ __forceinline__ void fill_tile_cache(TileCache<BPB>& tc, const BodyVi
 template <int BPB, bool COH>
 __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int* __restrict__ vstart, const int4* __restrict__ visits,
                                                    const ManifoldSet& ms, const ForceView& fv, const int* __restrict__ order, int count, int tile,
-                                                   const SolveParams& prm, float alpha, float alphaDual, float* dxOut, Diag* diag, PrimalSmem<BPB>& sm,
+                                                   const SolveParams& prm, float alpha, float biasDual, float* dxOut, Diag* diag, PrimalSmem<BPB>& sm,
                                                    const TileCache<BPB>* tc = nullptr) {
     constexpr int L = kThreads / BPB;
     constexpr int CPL = (27 + L - 1) / L;
@@ -331,7 +330,7 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
             int lo = 0, hi = nb;                                  // slot: vs[lo] <= v < vs[lo + 1]
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sm.vs[mid] <= v) lo = mid; else hi = mid; }
             float4 sp = sm.pos[lo], sr = sm.rot[lo];
-            bool pending = alphaDual >= 0.0f && (e.z & 4) != 0;
+            bool pending = biasDual >= 0.0f && (e.z & 4) != 0;
             ContactState cs = unpack_contact(isA ? a4 : b4, isA ? b4 : a4, n4, l4, p4);     // rA = r_self, rB = r_other (visit_rows' frame)
             cs.C0n = a4.w; cs.C0t1 = b4.w;
             bool gyro = sm.inert[lo].w != 0.0f;
@@ -343,7 +342,7 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
                 invIw = m3(zero3(), zero3(), zero3());
             }
             BodySystem sys;
-            visit_rows(sp, sr, po.pos, po.rot, isA ? 1.0f : -1.0f, __int_as_float(e.w), alpha, pending, alphaDual, prm.beta, gyro, invIw, cs, sys);
+            visit_rows(sp, sr, po.pos, po.rot, isA ? 1.0f : -1.0f, __int_as_float(e.w), alpha, pending, biasDual, prm.beta, gyro, invIw, cs, sys);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
             if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); ms.lp[ci] = q; }
@@ -444,7 +443,7 @@ __device__ __forceinline__ unsigned long long l2_stream_policy() {
 template <int T, int MINB, bool ALIGNED>
 __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms,
                                                              int vFirst, int vLast, const int* __restrict__ range, const int* __restrict__ kOf,
-                                                             float alpha, float alphaDual, float beta, float* __restrict__ sums, float* __restrict__ carry) {
+                                                             float alpha, float biasDual, float beta, float* __restrict__ sums, float* __restrict__ carry) {
     __shared__ FlatSmem<T> sm;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned long long keep = l2_keep_policy(), stream = l2_stream_policy();
@@ -519,7 +518,7 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
         if (aligned && t == 0) sm.nextK[buf] = base + T < vEnd ? kCur : -1;     // row of the body the block's NEXT chunk opens with (kCur was loaded for it above)
         // ---- phase 1
         if (live) {
-            bool gyro = (e.z & 2) != 0, pending = alphaDual >= 0.0f && (e.z & 4) != 0;
+            bool gyro = (e.z & 2) != 0, pending = biasDual >= 0.0f && (e.z & 4) != 0;
             float sg = (e.z & 1) ? 1.0f : -1.0f;                       // visiting body is A / B of the manifold
             ContactState cs = unpack_contact(a4, b4, n4, l4, p4);       // rA = r_self, rB = r_other here
             M3 invIw = m3(zero3(), zero3(), zero3());
@@ -528,7 +527,7 @@ __global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const i
                 invIw = rot_diag(qmat(quat(ps.rot)), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
             }
             BodySystem sys;
-            visit_rows(ps.pos, ps.rot, po.pos, po.rot, sg, __int_as_float(e.w), alpha, pending, alphaDual, beta, gyro, invIw, cs, sys);
+            visit_rows(ps.pos, ps.rot, po.pos, po.rot, sg, __int_as_float(e.w), alpha, pending, biasDual, beta, gyro, invIw, cs, sys);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
             if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); *lp = q; }
@@ -701,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) solve_loop_cluster(BodyView b, co
                 fill_tile_cache<BPB>(slots[slot], b, visitStart + r.x, visits, ms, order + r.x, count, tile);
         }
     }
-    float alphaDual = -1.0f;                                    // dual pass of the previous iteration still to apply (deferred dual)
+    float biasDual = -1.0f;                                    // dual pass of the previous iteration still to apply (deferred dual)
     for (int it = 0; it < total; ++it) {
         float alpha = prm.postStabilize ? (it < prm.iterations ? 1.0f : 0.0f) : prm.alpha;      // solver.cpp:340-342
         int slot = 0;
@@ -710,17 +709,17 @@ __global__ void __launch_bounds__(kThreads, 1) solve_loop_cluster(BodyView b, co
             int count = r.y - r.x;
             for (int tile = rank; tile * BPB < count; tile += nCta, ++slot) {
                 const TileCache<BPB>* tc = (slot < nSlots && slots[slot].usable) ? &slots[slot] : nullptr;
-                primal_tile_visits<BPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, alphaDual, nullptr, diag, sm, tc);
+                primal_tile_visits<BPB, true>(b, visitStart + r.x, visits, ms, fv, order + r.x, count, tile, prm, alpha, biasDual, nullptr, diag, sm, tc);
                 __syncthreads();
             }
             cluster_barrier();
         }
-        alphaDual = it < prm.iterations ? alpha : -1.0f;
+        biasDual = it < prm.iterations ? fminf(fmaxf(1.0f - alpha, 0.0f), 1.0f) : -1.0f;
     }
     // what the sweeps could not apply: the last iteration's dual pass (nothing moves after it, so the contact diagnostics
     // are reduced from the same registers), or — when postStabilize's extra sweep already applied it — only the contacts
     // no dynamic body visits
-    bool lastPending = alphaDual >= 0.0f;
+    bool lastPending = biasDual >= 0.0f;
     if (prm.iterations > 0 && (lastPending || anyUnvisited)) {
         float alpha = prm.postStabilize ? 1.0f : prm.alpha;
         bool reduce = contactDiag && lastPending;
@@ -745,8 +744,7 @@ __global__ void dual_user_forces(BodyView b, ForceView fv, SolveParams prm) {
         ForceEval ev;
         joint_constraint(j, hasA, pA, qA, pB, qB, ev);
         for (int r = 0; r < 6; ++r) {
-            float k_ = r < 3 ? j.kLin : j.kAng;
-            if (k_ != FLT_MAX) continue;
+            if (j.stiffness[r] != FLT_MAX) continue;
             float lu = clampf(j.penalty[r] * ev.C[r] + j.lambda[r], ev.fmin[r], ev.fmax[r]);
             bool active = lu > ev.fmin[r] && lu < ev.fmax[r];
             j.lambda[r] = lu;
@@ -814,18 +812,24 @@ __global__ void flat_ranges(const int* __restrict__ vstart, int count, int vBegi
     range[r] = vstart[lo];
 }
 
+// Function attributes and occupancy are PER DEVICE (a process may hold worlds on several GPUs): cached by device index.
+constexpr int kMaxDevices = 64;
+static int current_device() { int dev = 0; cudaGetDevice(&dev); return (dev >= 0 && dev < kMaxDevices) ? dev : 0; }
+
 template <int T, int MINB>
 static int flat_resident_blocks() {
-    static const int n = [] {
+    static int cache[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!cache[dev]) {
         cudaFuncSetAttribute(primal_visit_flat<T, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(primal_visit_flat<T, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        int dev = 0, sms = 148, per = 0;
-        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int sms = 148, per = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, primal_visit_flat<T, MINB, true>, T, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 1; }
-        if (getenv("AVBD_DEBUG")) fprintf(stderr, "primal_visit_flat<%d,%d>: %d blocks per SM resident\n", T, MINB, per);
-        return sms * per;
-    }();
-    return n;
+        if (getenv("AVBD_DEBUG")) fprintf(stderr, "primal_visit_flat<%d,%d>: %d blocks per SM resident (device %d)\n", T, MINB, per, dev);
+        cache[dev] = sms * per;
+    }
+    return cache[dev];
 }
 static int flat_config() { static int cfg = [] { const char* e = getenv("AVBD_FLAT"); return e ? atoi(e) : 1284; }(); return cfg; }
 
@@ -847,13 +851,13 @@ void launch_flat_ranges(cudaStream_t s, const int* vstart, int first, int count,
 
 template <int T, int MINB>
 static void launch_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                        const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float alphaDual,
+                        const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float biasDual,
                         float* sums, float* carry, float* dxOut, Diag* diag) {
     // Programmatic dependent launch: each kernel of a sweep is launched while its predecessor still runs and blocks at
     // cudaGridDependencySynchronize() until that one has completed — a step has ~160 of these dependent launches, and the
     // launch latency of each would otherwise sit on the critical path.
-    if (grid > 0 && range) launch_dep(primal_visit_flat<T, MINB, true>, dim3(grid), dim3(T), 0, s, b, visits, vg, ms, vBegin, vEnd, range, kOf, alpha, alphaDual, prm.beta, sums, carry);
-    else if (grid > 0) launch_dep(primal_visit_flat<T, MINB, false>, dim3(grid), dim3(T), 0, s, b, visits, vg, ms, vBegin, vEnd, range, kOf, alpha, alphaDual, prm.beta, sums, carry);
+    if (grid > 0 && range) launch_dep(primal_visit_flat<T, MINB, true>, dim3(grid), dim3(T), 0, s, b, visits, vg, ms, vBegin, vEnd, range, kOf, alpha, biasDual, prm.beta, sums, carry);
+    else if (grid > 0) launch_dep(primal_visit_flat<T, MINB, false>, dim3(grid), dim3(T), 0, s, b, visits, vg, ms, vBegin, vEnd, range, kOf, alpha, biasDual, prm.beta, sums, carry);
     const int* orderC = order + first; const int* vstartC = vstart + first; const float* sumsC = sums + (size_t)first * kSumStride;
     const float* carryC = range ? nullptr : carry;                       // body-aligned ranges leave no pieces to add
     launch_dep(primal_solve_flat, dim3(blocks_of(count, kThreads)), dim3(kThreads), 0, s, b, fv, orderC, vstartC, count, vBegin, (int)T, sumsC, carryC, prm, dxOut, diag);
@@ -861,9 +865,9 @@ static void launch_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeo
 // `range` == nullptr: round-robin chunks (+ `carry`: 28 floats per chunk of the colour); else the colour's grid + 1 body-aligned
 // block boundaries (launch_flat_ranges, once per graph build).
 int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                       const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float alphaDual,
+                       const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float biasDual,
                        float* sums, float* carry, float* dxOut, Diag* diag) {
-#define AVBD_FL(T, M) launch_flat<T, M>(s, b, visits, vg, ms, fv, order, vstart, kOf, first, count, vBegin, vEnd, grid, range, prm, alpha, alphaDual, sums, carry, dxOut, diag)
+#define AVBD_FL(T, M) launch_flat<T, M>(s, b, visits, vg, ms, fv, order, vstart, kOf, first, count, vBegin, vEnd, grid, range, prm, alpha, biasDual, sums, carry, dxOut, diag)
     switch (flat_config()) {
         case 1286: AVBD_FL(128, 6); break;
         case 1285: AVBD_FL(128, 5); break;
@@ -876,23 +880,25 @@ bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const 
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
                        Diag* diag, bool contactDiag, bool anyUnvisited) {
     constexpr int BPB = kClusterBodiesPerTile;
-    static int maxCluster = [] {
+    static int maxClusterDev[kMaxDevices] = {0}, maxSlotsDev[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!maxClusterDev[dev]) {
         // 16 CTAs need the non-portable opt-in; fall back to the portable 8 if the device refuses it
-        if (cudaFuncSetAttribute(solve_loop_cluster<BPB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 8; }
-        if (const char* e = getenv("AVBD_CLUSTER_MAX")) { int v = atoi(e); if (v >= 1 && v <= 16) return v; }
-        return 16;
-    }();
-    // shared-memory slots for the tile cache: whatever the SM has left next to the kernel's static shared memory
-    static int maxSlots = [] {
-        int dev = 0, optin = 0; cudaGetDevice(&dev);
+        int mc = 16;
+        if (cudaFuncSetAttribute(solve_loop_cluster<BPB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); mc = 8; }
+        else if (const char* e = getenv("AVBD_CLUSTER_MAX")) { int v = atoi(e); if (v >= 1 && v <= 16) mc = v; }
+        // shared-memory slots for the tile cache: whatever the SM has left next to the kernel's static shared memory
+        int optin = 0;
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaFuncAttributes fa{}; cudaFuncGetAttributes(&fa, solve_loop_cluster<BPB>);
         long long room = (long long)optin - (long long)fa.sharedSizeBytes - 1024;
         int n = room > 0 ? (int)(room / (long long)sizeof(TileCache<BPB>)) : 0;
         if (const char* e = getenv("AVBD_TILE_CACHE_SLOTS")) n = atoi(e) < n ? atoi(e) : n;
         if (n > 0 && cudaFuncSetAttribute(solve_loop_cluster<BPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * (int)sizeof(TileCache<BPB>)) != cudaSuccess) { cudaGetLastError(); n = 0; }
-        return n;
-    }();
+        maxClusterDev[dev] = mc; maxSlotsDev[dev] = n + 1;          // + 1: 0 means "not initialised"
+    }
+    int& maxCluster = maxClusterDev[dev];
+    const int maxSlots = maxSlotsDev[dev] - 1;
     int want = blocks_of(maxColourCount, BPB);
     int wantDual = blocks_of(nContacts, kThreads);
     int need = want > wantDual ? want : wantDual;

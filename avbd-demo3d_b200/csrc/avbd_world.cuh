@@ -53,14 +53,14 @@ struct JointRec {
     int a, b;                 // a == -1: world anchor
     float4 rA, rB;            // local anchors (rA = world anchor when a < 0)
     float4 rel0;              // initial relative orientation
-    float lambda[6], penalty[6];
-    float kLin, kAng;         // stiffness per row group (FLT_MAX = hard)
+    // the row arrays of Force (solver.h:91-97) a caller may edit between steps; stiffness == FLT_MAX: hard row
+    float lambda[6], penalty[6], stiffness[6], motor[6];
 };
 struct SpringRec {
     int a, b;
     float4 rA, rB;
-    float rest, k;
-    float lambda, penalty;
+    float rest, k;            // k = stiffness[0]
+    float lambda, penalty, motor;
 };
 
 struct Diag {                 // Solver::Diagnostics, solver.h:155-164 (+ sanitiser events)

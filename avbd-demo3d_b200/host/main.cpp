@@ -1,21 +1,29 @@
 // main.cpp — headless CLI with the reference's flags and stdout format (alxspiker/avbd-demo3d source/main.cpp:189-248):
 //   --nogfx | --headless, --scene | -s <name>, --steps | -n <count>
 // Extensions (defaults leave the reference format untouched): --quiet (no per-step dump, one JSON timing line),
-// --grid N (N^3 Stress grid instead of a named scene), --stacked (spacingY 1.01 / startY 0.51 for --grid).
+// --grid N (N^3 Stress grid instead of a named scene), --stacked (spacingY 1.01 / startY 0.51 for --grid),
+// --warmup W (untimed steps before the counted ones), --dump-binary FILE (compact binary trajectory instead of the text
+// dump: 88 MB of text for Stress1000 x 600 upstream), --no-readback (state stays on the device; it is
+// fetched once at the end), --reupload (every body treated as edited before every step: the full-upload path),
+// --save-snapshot FILE / --load-snapshot FILE (device state after the run / before the first step; same scene required).
+//
+// Binary trajectory: header {char magic[8] = "AVBDTRJ1"; int32 bodies; int32 steps;} then per step
+// {int32 step; float state[bodies][13] (creation order: pos3 quat4 lin3 ang3); float diag[5]; int32 counts[3];}.
 // The SDL/ImGui front end is out of scope on a GPU box: without --nogfx this
 // binary says so on stderr and runs headless.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "solver.h"
 #include "scenes.h"
 
 int main(int argc, char** argv) {
-    bool headless = false, quiet = false, stacked = false;
-    const char* requestedScene = nullptr;
-    int steps = 300, grid = 0;
+    bool headless = false, quiet = false, stacked = false, readback = true, reupload = false;
+    const char* requestedScene = nullptr; const char* dumpPath = nullptr; const char* savePath = nullptr; const char* loadPath = nullptr;
+    int steps = 300, grid = 0, warmup = 0;
     for (int i = 1; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--nogfx") || !std::strcmp(argv[i], "--headless")) headless = true;
         else if ((!std::strcmp(argv[i], "--scene") || !std::strcmp(argv[i], "-s")) && i + 1 < argc) requestedScene = argv[++i];
@@ -23,6 +31,12 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[i], "--quiet")) quiet = true;
         else if (!std::strcmp(argv[i], "--grid") && i + 1 < argc) grid = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--stacked")) stacked = true;
+        else if (!std::strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--dump-binary") && i + 1 < argc) dumpPath = argv[++i];
+        else if (!std::strcmp(argv[i], "--no-readback")) readback = false;
+        else if (!std::strcmp(argv[i], "--reupload")) reupload = true;
+        else if (!std::strcmp(argv[i], "--save-snapshot") && i + 1 < argc) savePath = argv[++i];
+        else if (!std::strcmp(argv[i], "--load-snapshot") && i + 1 < argc) loadPath = argv[++i];
     }
     if (!headless) std::fprintf(stderr, "avbd-demo3d_b200: no graphics front end in this build; running headless (--nogfx).\n");
 
@@ -46,10 +60,40 @@ int main(int argc, char** argv) {
         scenes[sceneIdx](solver);
     }
 
-    if (!quiet) std::printf("Running in headless mode: scene '%s', steps=%d\n", label, steps);
+    solver->readBack = readback; solver->uploadAll = reupload;
+    if (loadPath) {
+        std::FILE* f = std::fopen(loadPath, "rb");
+        if (!f) { std::fprintf(stderr, "cannot open %s\n", loadPath); return 2; }
+        std::fseek(f, 0, SEEK_END); long sz = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+        std::vector<unsigned char> blob((size_t)sz);
+        if (std::fread(blob.data(), 1, blob.size(), f) != blob.size()) { std::fprintf(stderr, "short read on %s\n", loadPath); return 2; }
+        std::fclose(f);
+        solver->syncToDevice();
+        solver->restore(blob);
+    }
+    std::FILE* dump = nullptr;
+    int nBodies = (int)solver->order.size();
+    if (dumpPath) {
+        dump = std::fopen(dumpPath, "wb");
+        if (!dump) { std::fprintf(stderr, "cannot open %s\n", dumpPath); return 2; }
+        const char magic[8] = {'A', 'V', 'B', 'D', 'T', 'R', 'J', '1'};
+        std::fwrite(magic, 1, 8, dump); std::fwrite(&nBodies, 4, 1, dump); std::fwrite(&steps, 4, 1, dump);
+    }
+    if (!quiet && !dump) std::printf("Running in headless mode: scene '%s', steps=%d\n", label, steps);
+    for (int step = 0; step < warmup; ++step) solver->step();
     auto t0 = std::chrono::steady_clock::now();
     for (int step = 0; step < steps; ++step) {
         solver->step();
+        if (dump) {          // the state the step left in the pinned exchange buffer, creation order — no per-body formatting
+            const Solver::Diagnostics& st = solver->lastDiagnostics;
+            if (!readback) solver->fetchState();
+            std::fwrite(&step, 4, 1, dump);
+            std::fwrite(solver->shadow, sizeof(float), (size_t)nBodies * 13, dump);
+            const float df[5] = {st.maxPenetration, st.maxConstraintViolation, st.maxLinearSpeed, st.maxAngularSpeed, st.maxNormalImpulse};
+            const int di[3] = {st.activeManifolds, st.activeContacts, st.dynamicBodies};
+            std::fwrite(df, 4, 5, dump); std::fwrite(di, 4, 3, dump);
+            continue;
+        }
         if (quiet) continue;
         std::printf("Step %d:\n", step);
         for (Rigid* body = solver->bodies; body != nullptr; body = body->next) {
@@ -63,11 +107,21 @@ int main(int argc, char** argv) {
                     st.activeManifolds, st.activeContacts, st.dynamicBodies, st.maxPenetration, st.maxConstraintViolation, st.maxLinearSpeed,
                     st.maxAngularSpeed, st.maxNormalImpulse);
     }
-    if (quiet) {
-        double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!readback) solver->fetchState();
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (dump) std::fclose(dump);
+    if (quiet || dump) {
         const Solver::Diagnostics& st = solver->lastDiagnostics;
-        std::printf("{\"scene\": \"%s\", \"steps\": %d, \"seconds\": %.6f, \"steps_per_s\": %.3f, \"manifolds\": %d, \"contacts\": %d, \"dynBodies\": %d, \"maxPen\": %.6f}\n",
-                    label, steps, sec, steps / sec, st.activeManifolds, st.activeContacts, st.dynamicBodies, st.maxPenetration);
+        std::printf("{\"scene\": \"%s\", \"steps\": %d, \"warmup\": %d, \"seconds\": %.6f, \"steps_per_s\": %.3f, \"ms_per_step\": %.4f, \"bodies\": %d, \"manifolds\": %d, \"contacts\": %d, "
+                    "\"dynBodies\": %d, \"maxPen\": %.6f, \"readback\": %s, \"reupload\": %s, \"h2d_bytes\": %lld, \"d2h_bytes\": %lld}\n",
+                    label, steps, warmup, sec, steps / sec, 1e3 * sec / (steps > 0 ? steps : 1), nBodies, st.activeManifolds, st.activeContacts, st.dynamicBodies, st.maxPenetration,
+                    readback ? "true" : "false", reupload ? "true" : "false", solver->uploadedBytes, solver->downloadedBytes);
+    }
+    if (savePath) {
+        std::vector<unsigned char> blob = solver->snapshot();
+        std::FILE* f = std::fopen(savePath, "wb");
+        if (!f) { std::fprintf(stderr, "cannot open %s\n", savePath); return 2; }
+        std::fwrite(blob.data(), 1, blob.size(), f); std::fclose(f);
     }
     delete solver;
     return 0;

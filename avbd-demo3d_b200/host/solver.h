@@ -25,7 +25,8 @@ struct Rigid {                       // solver.h:48-82
     vec3 linearVelocity, angularVelocity, prevLinearVelocity, prevAngularVelocity;
     vec3 initialPosition; quat initialOrientation; vec3 inertialPosition; quat inertialOrientation;
     vec3 size; float mass, invMass; mat3 inertiaTensor, invInertiaTensor; float friction, radius;
-    int index;                       // creation index inside the device world (extension)
+    int index;                       // position among the solver's live bodies, creation order (extension)
+    int deviceIndex;                 // index inside the device world, -1 until uploaded (extension)
     float density;                   // kept so the body can be re-uploaded (extension)
 
     Rigid(Solver* solver, const vec3& size, float density, float friction, const vec3& pos, const quat& orient = quat(),
@@ -84,12 +85,25 @@ struct Solver {                      // solver.h:146-181
 
     // ---- extensions (not in the reference) ----
     void refreshManifolds();         // rebuilds the Manifold mirrors in `forces` from the device (contacts, lambda, penalty)
-    void syncToDevice();             // uploads parameters, host edits, new bodies and new user forces (step() and pick() call it)
+    void syncToDevice();             // uploads parameters, host edits (bodies, Force rows, Manifold rows), new bodies and new user forces
+    // Snapshot / restore of the DEVICE state for a solver whose body and force set is unchanged since the snapshot
+    // (SURVEY.md section 8f-3): poses, velocities, manifolds with lambda / penalty / anchors, user-force rows.
+    std::vector<unsigned char> snapshot();
+    void restore(const std::vector<unsigned char>& blob);
     avbd_world* world;               // the device world behind this Solver
     int device;
-    bool rebuild;                    // a body or force was deleted: re-upload everything at the next step
-    std::vector<Rigid*> order;       // bodies by creation index
-    std::vector<float> shadow;       // host copy of the last state exchanged with the device (13 floats per body)
+    bool rebuild;                    // a body or force was deleted: the device world is re-created at the next step (manifolds and rows kept)
+    bool readBack;                   // true (default): step() refreshes every Rigid from the device; false: only on fetchState()
+    bool uploadAll;                  // treat every body as edited before each step (exercises the full-upload path)
+    void fetchState();               // device -> Rigid fields (what step() does when readBack is set)
+    std::vector<Rigid*> order;       // live bodies by creation order
+    std::vector<Rigid*> deviceOrder; // bodies as the device world indexes them (nullptr: deleted since the upload)
+    float* shadow; size_t shadowCap; // pinned host copy of the last state exchanged with the device (13 floats per body)
     int uploadedBodies, uploadedForces;
     std::vector<Force*> userForces;  // joints / springs / ignore markers in creation order
+    std::vector<int> userForceSlot;  // their joint / spring index on the device (-1: no rows)
+    std::vector<float> rowShadow;    // per user force 48 floats: lambda12 penalty12 motor12 stiffness12 as last exchanged with the device
+    bool mirrorsFresh;               // the Manifold mirrors equal the device's set (refreshManifolds ran since the last step)
+    std::vector<float> mirrorRows;   // lambda12 penalty12 of every mirror at refresh time, to detect host edits
+    long long uploadedBytes, downloadedBytes;   // state exchange traffic since construction (diagnostics of the e2e path)
 };

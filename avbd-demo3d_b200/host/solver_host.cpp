@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace {
 [[noreturn]] void die(const char* what) {
@@ -46,7 +47,7 @@ int Rigid::next_id = 1;      // process-global and never reset, as upstream (rig
 
 Rigid::Rigid(Solver* s, const vec3& sz, float dens, float fric, const vec3& pos, const quat& orient, const vec3& linVel, const vec3& angVel)
     : solver(s), forces(nullptr), next(nullptr), id(next_id++), position(pos), orientation(orient), linearVelocity(linVel),
-      angularVelocity(angVel), prevLinearVelocity(linVel), prevAngularVelocity(angVel), size(sz), friction(fric), density(dens) {
+      angularVelocity(angVel), prevLinearVelocity(linVel), prevAngularVelocity(angVel), size(sz), friction(fric), deviceIndex(-1), density(dens) {
     next = s->bodies; s->bodies = this;
     index = (int)s->order.size(); s->order.push_back(this);
     mass = size.x * size.y * size.z * density;                               // rigid.cpp:24-40
@@ -67,7 +68,8 @@ Rigid::~Rigid() {
     Rigid** p = &solver->bodies;
     while (*p != this) p = &(*p)->next;
     *p = next;
-    if (!g_clearing) {           // a single body removed: the device world is rebuilt at the next step
+    if (!g_clearing) {           // a single body removed: the device world is re-created at the next step (manifolds of the others are kept)
+        if (deviceIndex >= 0 && deviceIndex < (int)solver->deviceOrder.size()) solver->deviceOrder[deviceIndex] = nullptr;
         solver->order.erase(std::find(solver->order.begin(), solver->order.end(), this));
         for (size_t i = 0; i < solver->order.size(); ++i) solver->order[i]->index = (int)i;
         solver->rebuild = true;
@@ -233,13 +235,15 @@ void Spring::computeDerivatives(vec3& Jl, vec3& Ja, const Rigid* body, int) cons
 // ----------------------------------------------------------------------------------------------- Solver
 Solver::Solver()
     : bodies(nullptr), forces(nullptr), enableDiagnostics(false), logFrequency(60), stepIndex(0), lastDiagnostics{}, world(nullptr),
-      device(0), rebuild(false), uploadedBodies(0), uploadedForces(0) {
+      device(0), rebuild(false), readBack(true), uploadAll(false), shadow(nullptr), shadowCap(0), uploadedBodies(0), uploadedForces(0),
+      mirrorsFresh(false), uploadedBytes(0), downloadedBytes(0) {
     if (const char* d = std::getenv("AVBD_DEVICE")) device = std::atoi(d);
     defaultParams();
 }
 
 Solver::~Solver() {
     clear();
+    if (shadow) avbd_host_free(shadow);
     if (world) avbd_world_destroy(world);
 }
 
@@ -249,7 +253,8 @@ void Solver::clear() {                                                   // solv
     while (bodies) delete bodies;
     g_clearing = false;
     bodies = nullptr; forces = nullptr; stepIndex = 0; lastDiagnostics = Diagnostics{};
-    order.clear(); userForces.clear(); shadow.clear(); uploadedBodies = 0; uploadedForces = 0; rebuild = false;
+    order.clear(); deviceOrder.clear(); userForces.clear(); userForceSlot.clear(); rowShadow.clear(); mirrorRows.clear();
+    uploadedBodies = 0; uploadedForces = 0; rebuild = false; mirrorsFresh = false;
     if (world) check(avbd_clear(world), "avbd_clear");
 }
 
@@ -267,43 +272,126 @@ void pack_body(const Rigid* b, float* o) {
     o[7] = b->linearVelocity.x; o[8] = b->linearVelocity.y; o[9] = b->linearVelocity.z;
     o[10] = b->angularVelocity.x; o[11] = b->angularVelocity.y; o[12] = b->angularVelocity.z;
 }
+// Slices [begin, end) of n items over a few host threads (a million Rigid nodes are 264 MB of scattered heap: one thread
+// walking them was most of Solver::step()'s host time).  fn(begin, end, slice).
+template <class Fn>
+void parallel_slices(int n, int& slices, Fn fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int want = n >= 65536 ? (int)std::min<unsigned>(hw ? hw : 1u, 16u) : 1;
+    if (const char* e = std::getenv("AVBD_HOST_THREADS")) want = std::max(1, std::atoi(e));
+    slices = want;
+    if (want == 1) { fn(0, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < want; ++t) {
+        int b = (int)((long long)n * t / want), e = (int)((long long)n * (t + 1) / want);
+        th.emplace_back([=] { fn(b, e, t); });
+    }
+    for (auto& x : th) x.join();
+}
+void ensure_shadow(Solver* s, size_t bodies) {
+    if (bodies * 13 <= s->shadowCap) return;
+    size_t cap = std::max<size_t>(bodies + bodies / 2, 1024) * 13;
+    float* p = static_cast<float*>(avbd_host_alloc((long long)(cap * sizeof(float))));
+    if (!p) die("avbd_host_alloc");
+    if (s->shadow) { std::memcpy(p, s->shadow, s->shadowCap * sizeof(float)); avbd_host_free(s->shadow); }
+    s->shadow = p; s->shadowCap = cap;
+}
+void rows_of(const Force* f, float* o48) {
+    std::memcpy(o48, f->lambda, 12 * sizeof(float)); std::memcpy(o48 + 12, f->penalty, 12 * sizeof(float));
+    std::memcpy(o48 + 24, f->motor, 12 * sizeof(float)); std::memcpy(o48 + 36, f->stiffness, 12 * sizeof(float));
+}
 }
 
 // Everything the host side created or edited since the device last saw it: parameters, moved bodies, new bodies, new
-// user forces.  Runs before every step and before Solver::pick (the reference's pick works on a solver that never stepped).
+// user forces, edited Force rows.  Runs before every step and before Solver::pick (the reference's pick works on a solver
+// that never stepped).
 void Solver::syncToDevice() {
     if (!world) { world = avbd_world_create(device); if (!world) die("avbd_world_create"); }
-    if (rebuild) {               // something was deleted: start the device world over (warm-start history is lost)
+    std::vector<int> keepInts, keepFeats, keepStick; std::vector<float> keepFlts; int keepCount = -1;
+    std::vector<Rigid*> oldDeviceOrder;
+    if (rebuild) {
+        // A body or a user force was deleted (force.cpp:43-69 / ~Rigid are O(degree) upstream): the device world is re-created
+        // from the host mirror, and everything that carries warm-start history goes with it — the manifold set (re-indexed;
+        // manifolds of a deleted body are dropped, as upstream deletes them with the body) and the user forces' rows.
+        int slots = avbd_num_manifolds(world);
+        if (slots > 0) {
+            keepInts.resize(3 * (size_t)slots); keepFeats.resize(4 * (size_t)slots); keepStick.resize(4 * (size_t)slots); keepFlts.resize(81 * (size_t)slots);
+            keepCount = avbd_download_manifolds(world, keepInts.data(), keepFeats.data(), keepStick.data(), keepFlts.data());
+            check(keepCount, "avbd_download_manifolds");
+        }
+        oldDeviceOrder = deviceOrder;
         check(avbd_clear(world), "avbd_clear");
-        uploadedBodies = 0; uploadedForces = 0; shadow.clear(); rebuild = false;
+        uploadedBodies = 0; uploadedForces = 0; deviceOrder.clear(); userForceSlot.clear(); rowShadow.clear(); rebuild = false;
+        for (Rigid* b : order) b->deviceIndex = -1;
     }
     const float g[3] = {gravity.x, gravity.y, gravity.z};
     check(avbd_set_params(world, dt, g, iterations, alpha, beta, gamma, postStabilize ? 1 : 0), "avbd_set_params");
 
     int n = (int)order.size();
-    // 1. host edits of already-uploaded bodies (the GUI moves / re-spins bodies between steps, main.cpp:88-142)
+    ensure_shadow(this, (size_t)n);
+    // 1. host edits of already-uploaded bodies (the GUI moves / re-spins bodies between steps, main.cpp:88-142): each slice
+    //    uploads the range between its first and last edited body — nothing at all in a headless run
     if (uploadedBodies > 0) {
-        std::vector<float> cur((size_t)uploadedBodies * 13);
-        for (int i = 0; i < uploadedBodies; ++i) pack_body(order[i], &cur[(size_t)i * 13]);
-        if (std::memcmp(cur.data(), shadow.data(), cur.size() * sizeof(float)) != 0) {
-            std::memcpy(shadow.data(), cur.data(), cur.size() * sizeof(float));
-            check(avbd_upload_state(world, shadow.data()), "avbd_upload_state");
-        }
+        int slices = 1;
+        std::vector<int> lo(16, -1), hi(16, -1);
+        const bool all = uploadAll;
+        parallel_slices(uploadedBodies, slices, [&](int b, int e, int t) {
+            float cur[13];
+            int first = -1, last = -1;
+            for (int i = b; i < e; ++i) {
+                pack_body(order[i], cur);
+                float* sh = shadow + (size_t)i * 13;
+                if (all || std::memcmp(cur, sh, sizeof(cur)) != 0) { std::memcpy(sh, cur, sizeof(cur)); if (first < 0) first = i; last = i; }
+            }
+            lo[t] = first; hi[t] = last;
+        });
+        for (int t = 0; t < slices; ++t)
+            if (lo[t] >= 0) {
+                int cnt = hi[t] - lo[t] + 1;
+                check(avbd_upload_state_range(world, lo[t], cnt, shadow + (size_t)lo[t] * 13), "avbd_upload_state_range");
+                uploadedBytes += (long long)cnt * 52;
+            }
     }
     // 2. bodies created since the last step (append-only)
+    bool reAdded = false;
     if (n > uploadedBodies) {
         int k = n - uploadedBodies;
-        std::vector<float> size(3 * (size_t)k), dens(k), fric(k), pos(3 * (size_t)k), rot(4 * (size_t)k), lin(3 * (size_t)k), ang(3 * (size_t)k);
+        std::vector<float> size(3 * (size_t)k), dens(k), fric(k), pos(3 * (size_t)k), rot(4 * (size_t)k), lin(3 * (size_t)k), ang(3 * (size_t)k), prev(3 * (size_t)k);
+        bool prevDiffers = false;
         for (int j = 0; j < k; ++j) {
-            const Rigid* b = order[uploadedBodies + j];
-            for (int c = 0; c < 3; ++c) { size[3 * j + c] = b->size[c]; pos[3 * j + c] = b->position[c]; lin[3 * j + c] = b->linearVelocity[c]; ang[3 * j + c] = b->angularVelocity[c]; }
+            Rigid* b = order[uploadedBodies + j];
+            for (int c = 0; c < 3; ++c) {
+                size[3 * j + c] = b->size[c]; pos[3 * j + c] = b->position[c]; lin[3 * j + c] = b->linearVelocity[c]; ang[3 * j + c] = b->angularVelocity[c];
+                prev[3 * j + c] = b->prevLinearVelocity[c];
+                if (b->prevLinearVelocity[c] != b->linearVelocity[c]) prevDiffers = true;
+            }
             rot[4 * j] = b->orientation.x; rot[4 * j + 1] = b->orientation.y; rot[4 * j + 2] = b->orientation.z; rot[4 * j + 3] = b->orientation.w;
             dens[j] = b->density; fric[j] = b->friction;
+            b->deviceIndex = uploadedBodies + j;
         }
         check(avbd_add_bodies(world, k, size.data(), dens.data(), fric.data(), pos.data(), rot.data(), lin.data(), ang.data(), nullptr), "avbd_add_bodies");
-        shadow.resize((size_t)n * 13);
-        for (int i = uploadedBodies; i < n; ++i) pack_body(order[i], &shadow[(size_t)i * 13]);
+        deviceOrder.insert(deviceOrder.end(), order.begin() + uploadedBodies, order.end());
+        if (prevDiffers && uploadedBodies == 0) {      // a re-created world: the adaptive gravity weight (solver.cpp:318-326) needs the real previous velocities
+            check(avbd_upload_prev_linvel(world, prev.data()), "avbd_upload_prev_linvel");
+        }
+        for (int i = uploadedBodies; i < n; ++i) pack_body(order[i], shadow + (size_t)i * 13);
+        uploadedBytes += (long long)k * 52;
+        reAdded = uploadedBodies == 0;
         uploadedBodies = n;
+    }
+    // 2b. the manifold set a re-created world inherits
+    if (keepCount > 0 && reAdded) {
+        int live = 0;
+        for (int m = 0; m < keepCount; ++m) {
+            Rigid* a = oldDeviceOrder[keepInts[3 * m]]; Rigid* b = oldDeviceOrder[keepInts[3 * m + 1]];
+            if (!a || !b) continue;
+            keepInts[3 * live] = a->deviceIndex; keepInts[3 * live + 1] = b->deviceIndex; keepInts[3 * live + 2] = keepInts[3 * m + 2];
+            std::memmove(&keepFeats[4 * (size_t)live], &keepFeats[4 * (size_t)m], 4 * sizeof(int));
+            std::memmove(&keepStick[4 * (size_t)live], &keepStick[4 * (size_t)m], 4 * sizeof(int));
+            std::memmove(&keepFlts[81 * (size_t)live], &keepFlts[81 * (size_t)m], 81 * sizeof(float));
+            ++live;
+        }
+        check(avbd_upload_manifolds(world, live, keepInts.data(), keepFeats.data(), keepStick.data(), keepFlts.data()), "avbd_upload_manifolds");
     }
     // 3. user forces created since the last step: every Force in the solver's list that is not a Manifold mirror and not
     //    registered yet (the list is newest first; whatever subclass it is, it is found here — header-only ones included)
@@ -315,37 +403,123 @@ void Solver::syncToDevice() {
     }
     for (; uploadedForces < (int)userForces.size(); ++uploadedForces) {
         Force* f = userForces[uploadedForces];
-        int a = f->bodyA ? f->bodyA->index : -1, b = f->bodyB->index;
+        int a = f->bodyA ? f->bodyA->deviceIndex : -1, b = f->bodyB->deviceIndex;
+        int slot = -1;
         if (f->deviceKind() == 0) {
+            // the construction-time anchor / reference orientation the Joint already holds (joint.cpp:19, :47-50), NOT values
+            // re-derived from the current poses: a joint that is re-uploaded keeps the error it has accumulated
             Joint* j = static_cast<Joint*>(f);
             const float aa[3] = {j->rA.x, j->rA.y, j->rA.z}, bb[3] = {j->rB.x, j->rB.y, j->rB.z};
-            check(avbd_add_joint(world, a, b, aa, bb, j->stiffness[0], j->stiffness[3]), "avbd_add_joint");
+            const float q[4] = {j->initialRelativeOrientation.x, j->initialRelativeOrientation.y, j->initialRelativeOrientation.z, j->initialRelativeOrientation.w};
+            slot = avbd_add_joint_raw(world, a, b, aa, bb, q, j->stiffness[0], j->stiffness[3]);
+            check(slot, "avbd_add_joint_raw");
         } else if (f->deviceKind() == 1) {
-            Spring* s = static_cast<Spring*>(f);
-            const float aa[3] = {s->rA.x, s->rA.y, s->rA.z}, bb[3] = {s->rB.x, s->rB.y, s->rB.z};
-            check(avbd_add_spring(world, a, b, aa, bb, s->springStiffness, s->restLength), "avbd_add_spring");
+            Spring* sp = static_cast<Spring*>(f);
+            const float aa[3] = {sp->rA.x, sp->rA.y, sp->rA.z}, bb[3] = {sp->rB.x, sp->rB.y, sp->rB.z};
+            slot = avbd_add_spring(world, a, b, aa, bb, sp->stiffness[0], sp->restLength);
+            check(slot, "avbd_add_spring");
         } else if (f->deviceKind() == 2) {
             check(avbd_add_ignore(world, a, b), "avbd_add_ignore");
         } else {
             std::fprintf(stderr, "avbd-demo3d_b200: user-defined Force subclasses cannot run on the device (no CPU fallback)\n");
             std::exit(2);
         }
+        userForceSlot.push_back(slot);
+        // device rows start as the constructor left them (lambda 0, penalty PENALTY_MIN, motor 0); anything else the host holds
+        // (rows edited before the first step, or the history of a re-created world) is an edit and is uploaded below
+        rowShadow.resize(rowShadow.size() + 48, 0.0f);
+        float* sh = &rowShadow[48 * (size_t)uploadedForces];
+        int rows = f->getRowCount();
+        for (int r = 0; r < 12; ++r) { sh[r] = 0.0f; sh[12 + r] = r < rows ? PENALTY_MIN : f->penalty[r]; sh[24 + r] = 0.0f; sh[36 + r] = f->stiffness[r]; }
+        if (f->deviceKind() == 0) for (int r = 0; r < 6; ++r) sh[36 + r] = f->stiffness[r < 3 ? 0 : 3];
     }
+    // 4. host edits of the public row arrays of user forces (solver.h:91-97): lambda, penalty, motor (enters the primal at
+    //    solver.cpp:380), stiffness (hard / soft, :290, :378, :416)
+    for (size_t k = 0; k < userForces.size(); ++k) {
+        int slot = userForceSlot[k];
+        if (slot < 0) continue;
+        Force* f = userForces[k];
+        int rows = f->getRowCount();
+        float cur[48]; rows_of(f, cur);
+        float* sh = &rowShadow[48 * k];
+        bool edited = false;
+        for (int part = 0; part < 4 && !edited; ++part) edited = std::memcmp(cur + 12 * part, sh + 12 * part, rows * sizeof(float)) != 0;
+        if (!edited) continue;
+        check(avbd_set_force_rows(world, f->deviceKind(), slot, f->lambda, f->penalty, f->motor, f->stiffness), "avbd_set_force_rows");
+        std::memcpy(sh, cur, sizeof(cur));
+    }
+    // 5. host edits of Manifold mirrors' lambda / penalty (only meaningful while the mirrors are the device's current set)
+    if (mirrorsFresh) {
+        std::vector<int> ints, feats, stick; std::vector<float> flts;
+        bool edited = false; size_t m = 0;
+        for (Force* f = forces; f; f = f->next) {
+            if (!f->isManifold()) continue;
+            if (24 * (m + 1) > mirrorRows.size()) { edited = false; break; }
+            if (std::memcmp(f->lambda, &mirrorRows[24 * m], 12 * sizeof(float)) || std::memcmp(f->penalty, &mirrorRows[24 * m + 12], 12 * sizeof(float))) edited = true;
+            ++m;
+        }
+        if (edited) {
+            for (Force* f = forces; f; f = f->next) {
+                if (!f->isManifold()) continue;
+                Manifold* mf = static_cast<Manifold*>(f);
+                if (mf->numContacts <= 0) continue;
+                ints.push_back(mf->bodyA->deviceIndex); ints.push_back(mf->bodyB->deviceIndex); ints.push_back(mf->numContacts);
+                size_t fo = flts.size(); flts.resize(fo + 81, 0.0f);
+                flts[fo] = mf->combinedFriction;
+                for (int c = 0; c < 4; ++c) {
+                    bool on = c < mf->numContacts; const Manifold::Contact& k = mf->contacts[c];
+                    feats.push_back(on ? k.feature.value : 0); stick.push_back(on && k.stick ? 1 : 0);
+                    if (!on) continue;
+                    float* g = &flts[fo + 1 + 14 * c];
+                    g[0] = k.rA.x; g[1] = k.rA.y; g[2] = k.rA.z; g[3] = k.rB.x; g[4] = k.rB.y; g[5] = k.rB.z; g[6] = k.normal.x; g[7] = k.normal.y; g[8] = k.normal.z;
+                    g[9] = k.penetration; g[10] = k.C0_n; g[11] = k.C0_t.x; g[12] = k.C0_t.y; g[13] = 0.0f;
+                    for (int r = 0; r < 3; ++r) { flts[fo + 57 + 3 * c + r] = mf->lambda[3 * c + r]; flts[fo + 69 + 3 * c + r] = mf->penalty[3 * c + r]; }
+                }
+            }
+            check(avbd_upload_manifolds(world, (int)(ints.size() / 3), ints.data(), feats.data(), stick.data(), flts.data()), "avbd_upload_manifolds");
+        }
+    }
+}
 
+void Solver::fetchState() {
+    int n = (int)order.size();
+    if (n == 0 || !world) return;
+    check(avbd_download_state(world, shadow), "avbd_download_state");
+    downloadedBytes += (long long)n * 52;
+    int slices = 1;
+    parallel_slices(n, slices, [&](int b0, int e0, int) {
+        for (int i = b0; i < e0; ++i) {
+            Rigid* b = order[i]; const float* o = shadow + (size_t)i * 13;
+            b->position = vec3(o[0], o[1], o[2]); b->orientation = quat(o[3], o[4], o[5], o[6]);
+            b->linearVelocity = vec3(o[7], o[8], o[9]); b->angularVelocity = vec3(o[10], o[11], o[12]);
+        }
+    });
 }
 
 void Solver::step() {                                                    // solver.cpp:255-514, on the device
     syncToDevice();
     int n = (int)order.size();
     ++stepIndex;
+    mirrorsFresh = false;
     check(avbd_step(world, 1), "avbd_step");
-    if (n > 0) {
-        check(avbd_download_state(world, shadow.data()), "avbd_download_state");
-        for (int i = 0; i < n; ++i) {
-            Rigid* b = order[i]; const float* o = &shadow[(size_t)i * 13];
-            if (b->invMass > 0.0f) { b->prevLinearVelocity = b->linearVelocity; b->prevAngularVelocity = b->angularVelocity; }
-            b->position = vec3(o[0], o[1], o[2]); b->orientation = quat(o[3], o[4], o[5], o[6]);
-            b->linearVelocity = vec3(o[7], o[8], o[9]); b->angularVelocity = vec3(o[10], o[11], o[12]);
+    if (n > 0 && readBack) {
+        // previous velocities (solver.cpp:457-458) are last step's values the host already holds
+        int slices = 1;
+        parallel_slices(n, slices, [&](int b0, int e0, int) {
+            for (int i = b0; i < e0; ++i) { Rigid* b = order[i]; if (b->invMass > 0.0f) { b->prevLinearVelocity = b->linearVelocity; b->prevAngularVelocity = b->angularVelocity; } }
+        });
+        fetchState();
+    }
+    // lambda / penalty of the user forces' rows, as the reference leaves them in the public arrays after a step
+    if (!userForces.empty()) {
+        int nj = avbd_num_joints(world), ns = avbd_num_springs(world);
+        std::vector<float> jr(12 * (size_t)std::max(1, nj)), sr(2 * (size_t)std::max(1, ns));
+        check(avbd_download_user_rows(world, nj ? jr.data() : nullptr, ns ? sr.data() : nullptr), "avbd_download_user_rows");
+        for (size_t k = 0; k < userForces.size(); ++k) {
+            int slot = userForceSlot[k]; if (slot < 0) continue;
+            Force* f = userForces[k]; float* sh = &rowShadow[48 * k];
+            if (f->deviceKind() == 0) for (int r = 0; r < 6; ++r) { f->lambda[r] = sh[r] = jr[12 * (size_t)slot + r]; f->penalty[r] = sh[12 + r] = jr[12 * (size_t)slot + 6 + r]; }
+            else { f->lambda[0] = sh[0] = sr[2 * (size_t)slot]; f->penalty[0] = sh[12] = sr[2 * (size_t)slot + 1]; }
         }
     }
     avbd_diagnostics d;
@@ -363,9 +537,42 @@ void Solver::step() {                                                    // solv
     }
 }
 
+std::vector<unsigned char> Solver::snapshot() {
+    syncToDevice();
+    long long bytes = avbd_snapshot_bytes(world);
+    std::vector<unsigned char> blob((size_t)bytes);
+    check(avbd_snapshot(world, blob.data(), bytes), "avbd_snapshot");
+    return blob;
+}
+
+void Solver::restore(const std::vector<unsigned char>& blob) {
+    if (!world) { world = avbd_world_create(device); if (!world) die("avbd_world_create"); }
+    check(avbd_restore(world, blob.data(), (long long)blob.size()), "avbd_restore");
+    if (avbd_num_bodies(world) != (int)order.size()) { std::fprintf(stderr, "avbd-demo3d_b200: snapshot holds a different body set\n"); std::exit(2); }
+    uploadedBodies = (int)order.size(); rebuild = false; mirrorsFresh = false;
+    ensure_shadow(this, order.size());
+    deviceOrder = order;
+    for (size_t i = 0; i < order.size(); ++i) order[i]->deviceIndex = (int)i;
+    fetchState();                                   // the host mirror shows the restored state (and is not mistaken for an edit)
+    if (!order.empty()) {
+        std::vector<float> prev(3 * order.size());
+        check(avbd_download_prev_linvel(world, prev.data()), "avbd_download_prev_linvel");
+        for (size_t i = 0; i < order.size(); ++i) order[i]->prevLinearVelocity = vec3(prev[3 * i], prev[3 * i + 1], prev[3 * i + 2]);
+    }
+    if (!userForces.empty()) {                      // rows as saved
+        for (size_t k = 0; k < userForces.size(); ++k) {
+            int slot = userForceSlot[k]; if (slot < 0) continue;
+            Force* f = userForces[k];
+            check(avbd_get_force_rows(world, f->deviceKind(), slot, f->lambda, f->penalty, f->motor, f->stiffness), "avbd_get_force_rows");
+            rows_of(f, &rowShadow[48 * k]);
+        }
+    }
+}
+
 void Solver::refreshManifolds() {
     for (Force* f = forces; f;) { Force* nx = f->next; if (f->isManifold()) delete f; f = nx; }
-    if (!world) return;
+    mirrorRows.clear(); mirrorsFresh = false;
+    if (!world || rebuild) return;
     int slots = avbd_num_manifolds(world);
     if (slots <= 0) return;
     std::vector<int> ints(3 * (size_t)slots), feats(4 * (size_t)slots), stick(4 * (size_t)slots);
@@ -373,7 +580,7 @@ void Solver::refreshManifolds() {
     int live = avbd_download_manifolds(world, ints.data(), feats.data(), stick.data(), flts.data());
     check(live, "avbd_download_manifolds");
     for (int m = 0; m < live; ++m) {
-        Manifold* mf = new Manifold(this, order[ints[3 * m]], order[ints[3 * m + 1]]);
+        Manifold* mf = new Manifold(this, deviceOrder[ints[3 * m]], deviceOrder[ints[3 * m + 1]]);
         const float* f = &flts[81 * (size_t)m];
         mf->numContacts = ints[3 * m + 2]; mf->combinedFriction = f[0];
         for (int c = 0; c < mf->numContacts; ++c) {
@@ -387,6 +594,12 @@ void Solver::refreshManifolds() {
             for (int r = 0; r < 3; ++r) { mf->lambda[c * 3 + r] = f[57 + c * 3 + r]; mf->penalty[c * 3 + r] = f[69 + c * 3 + r]; mf->stiffness[c * 3 + r] = FLT_MAX; }
         }
     }
+    for (Force* f = forces; f; f = f->next) {          // what the mirrors hold now, in list order, to recognise host edits later
+        if (!f->isManifold()) continue;
+        mirrorRows.insert(mirrorRows.end(), f->lambda, f->lambda + 12);
+        mirrorRows.insert(mirrorRows.end(), f->penalty, f->penalty + 12);
+    }
+    mirrorsFresh = true;
 }
 
 void Solver::draw() { refreshManifolds(); }     // GL drawing is out of scope; keeping the mirrors fresh is what a renderer would need
@@ -399,5 +612,5 @@ Rigid* Solver::pick(const vec3& origin, const vec3& dir, vec3& local) {      // 
     int hit = avbd_pick(world, o, d, l);
     if (hit < 0) return nullptr;
     local = vec3(l[0], l[1], l[2]);
-    return order[hit];
+    return deviceOrder[hit];
 }

@@ -2,18 +2,27 @@
 """bench.py — AVBD step-loop throughput on B200 (BASELINE.json metric: steps/s at Stress1000 & 1M-box,
 body-solves/s/GPU, HBM GB/s vs peak).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload grid100|stress1000|ensemble] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload grid100|grid50|stress1000|ensemble] [--impl reference]
 
 One "step" = one Solver::step() (broadphase -> narrowphase/warm-start -> predict -> iterations x (primal per
-colour, dual) -> velocities) over one resident world.  Default workload (N=1): the 100x100x100 = 1M-box
-pre-stacked grid of SURVEY.md section 8d(4), iterations=10 — the largest single-GPU configuration BASELINE.json
-names and the one the HBM roofline is meaningful on; Stress1000 (the reference's own scene, latency-bound on a
-GPU) is measured in the same run and reported under "stress1000".  N>1: one such world per GPU (independent
-worlds, no data-path collective; NCCL only gathers diagnostics) => weak scaling.
+colour, dual) -> velocities) over one resident world.  Headline workload: the 100x100x100 = 1M-box pre-stacked
+grid of SURVEY.md section 8d(4), iterations=10 — the largest single-GPU configuration BASELINE.json names and the
+one the HBM roofline is meaningful on.  N>1: one such world per GPU (independent worlds, no data-path collective)
+=> weak scaling for the headline.
 
-Printed: ONE JSON line (rank 0).  `value` = body-solves/s of the whole job with state resident in HBM, timed
-with CUDA events on the solver's stream, max over ranks.  `e2e` = the same metric through the public API with
-host buffers: every step uploads the body state from pinned host memory, steps, and downloads it back.
+Every line (all N) ALSO carries
+  ensemble     BASELINE.json config 4: 8192 jittered Pyramid worlds block-sharded over the N ranks (strong scaling:
+               whole-job steps/s and body-solves/s, device-timed max over ranks, e2e, per-rank ms); NCCL only
+               gathers timings and diagnostics;
+  roofline     the dominant kernel (the primal colour sweep) plus `stages`: broadphase, narrowphase, graph, predict,
+               primal, dual, velocity — algorithmic bytes (SURVEY.md section 8d formulas), CUDA-event ms, GB/s, frac;
+  same_config  workloads BOTH arms can run as they are — Stress1000 (settled 400 steps) and the 20^3 pre-stacked
+               grid — device-resident and end to end; `--impl reference` prints the same record from the
+               reference's CPU solver, so a like-for-like ratio can be formed from the two lines.
+
+`value` = body-solves/s of the whole job with state resident in HBM, timed with CUDA events on the solver's
+stream (no profiling hooks inside), max over ranks.  `e2e` = the same metric through the public API with host
+buffers: every step uploads the body state from pinned host memory, steps, and downloads it back.
 """
 import argparse
 import json
@@ -28,11 +37,34 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
-PRIMAL_BYTES_PER_BODY, PRIMAL_BYTES_PER_VISIT, DUAL_BYTES_PER_CONTACT = 100, 124, 156      # SURVEY.md section 8d / DESIGN.md
-# A dual pass applied INSIDE a primal sweep (deferred dual) re-uses what the visit already loaded; the only
-# compulsory traffic it adds is the penalty + stick write-back.  Counted this way the fused sweep gets no credit for the
-# 156 B/contact pass it made unnecessary — removing traffic must not raise the "achieved" figure.
+# Algorithmic (compulsory) bytes, SURVEY.md section 8d / DESIGN.md section 4: FP32 SoA, every array touched once per pass.
+PRIMAL_BYTES_PER_BODY, PRIMAL_BYTES_PER_VISIT, DUAL_BYTES_PER_CONTACT = 100, 124, 156
+# A dual pass applied INSIDE a primal sweep (deferred dual) re-uses what the visit already loaded; the only compulsory traffic
+# it adds is the penalty + stick write-back.  Counted this way the fused sweep gets no credit for the 156 B/contact pass it
+# made unnecessary — removing traffic must not raise the "achieved" figure.
 DEFERRED_DUAL_BYTES_PER_CONTACT = 16
+ENSEMBLE_WORLDS = 8192
+GRID_SAMPLE = 20            # the CPU arm's bounded sample of the headline workload: a 20^3 pre-stacked sub-grid
+
+
+def stage_bytes(p):
+    """Per-stage algorithmic bytes summed over the profiled steps (p = avbd_profile as a dict).
+    broadphase  16 N (pos + radius) + 64 N (8 B key/index x 4 radix passes, read + write) + 8 P (pairs out)
+    narrowphase 96 P (2 x (pos, quat, half) as float4) + 336 M (16 B header + 4 x 80 B contact) + 272 M_old (warm-start read)
+    graph       (this repo's formula; SURVEY gives none) 16 M header read + 8 N colour r/w + 16 V visit entries + 96 V visit
+                geometry (48 B gathered by contact + 48 B written in visit order) + 8 N_dyn order / run starts; per graph BUILD
+                (a step whose topology did not change re-uses the graph and only refreshes the 96 V geometry)
+    predict     176 N          velocity + diagnostics 144 N + 48 K
+    primal      100 N_dyn + 124 V per sweep (+ 16 K when the sweep carries the deferred dual)      dual 156 K per stand-alone pass"""
+    N, P, M, Mo, K, V = p["bodies"], p["pairs"], p["manifolds"], p["manifolds_prev"], p["contacts"], p["visits"]
+    steps = max(p["steps"], 1)
+    builds = p["graph_builds"]
+    per_step = lambda tot: tot / steps
+    graph = (16 * per_step(M) + 8 * per_step(N) + 16 * per_step(V) + 8 * per_step(N)) * builds + 96 * V
+    return dict(broadphase=80 * N + 8 * P, narrowphase=96 * P + 336 * M + 272 * Mo, graph=graph, predict=176 * N,
+                primal=PRIMAL_BYTES_PER_BODY * p["primal_bodies"] + PRIMAL_BYTES_PER_VISIT * p["primal_visits"]
+                + DEFERRED_DUAL_BYTES_PER_CONTACT * p["deferred_dual_contacts"],
+                dual=DUAL_BYTES_PER_CONTACT * p["dual_contacts"], velocity=144 * N + 48 * K)
 
 
 def parse():
@@ -43,6 +75,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="grid100", choices=["grid100", "grid50", "stress1000", "ensemble"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip ensemble / same_config / C++ host legs")
     return ap.parse_args()
 
 
@@ -55,14 +88,16 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """DRAM bytes per primal colour sweep from the committed `ncu --set full` capture of this workload (profiles/r01_traffic.json,
-    written by profiles/summarize.py traffic); None when the file is absent.  Cold-cache, serialised launches: an upper bound."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)
-        return float(t["dram_bytes_per_colour_sweep"]), "profiles/r01_traffic.json (%s)" % t.get("source", "ncu")
-    except Exception:
-        return None, None
+    """DRAM bytes per primal colour sweep from the committed `ncu --set full` capture of this workload at this kernel version
+    (profiles/r02_traffic.json, written by profiles/summarize.py traffic); None when absent or stale."""
+    for name in ("r02_traffic.json",):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            return float(t["dram_bytes_per_colour_sweep"]), "profiles/%s (%s)" % (name, t.get("source", "ncu"))
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -98,75 +133,185 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
+def bind_to_gpu_numa_node(index):
+    """CPU affinity (and with it first-touch placement of the pinned staging buffers) on the NUMA node the GPU hangs off: eight
+    ranks pinning and copying 104 MB per step through ONE node's memory controllers is what made the 8-GPU e2e scale at 0.77."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            return f"{len(use)} cpus of the GPU's NUMA node ({spec})"
+        return f"GPU-local cpus ({spec}) not in this process's allowed set: unchanged"
+    except Exception as e:          # containers without sysfs / NVML: leave the affinity alone
+        return f"unchanged ({type(e).__name__})"
+
+
 def workload_preset(name):
     from avbd_demo3d_b200 import scenes
-    if name == "grid100":
-        s = scenes.stress_grid(100, 100, 100, spacing_y=1.01, start_y=0.51, wide_ground=True)
+    if name in ("grid100", "grid50", "grid20"):
+        n = int(name[4:])
+        s = scenes.stress_grid(n, n, n, spacing_y=1.01, start_y=0.51, wide_ground=True)
         s["params"]["iterations"] = 10
-        return s, "synthetic 100x100x100 = 1M-box pre-stacked drop grid (Stress1000 generator, spacingY=1.01, startY=0.51, widened ground), iterations=10"
-    if name == "grid50":
-        s = scenes.stress_grid(50, 50, 50, spacing_y=1.01, start_y=0.51, wide_ground=True)
-        s["params"]["iterations"] = 10
-        return s, "synthetic 50x50x50 = 125k-box pre-stacked grid, iterations=10"
+        big = "synthetic 100x100x100 = 1M-box" if n == 100 else f"synthetic {n}x{n}x{n} = {n ** 3}-box"
+        return s, (f"{big} pre-stacked drop grid (Stress1000 generator with its 0.25 y-jitter, spacingY=1.01, startY=0.51: layers start "
+                   "up to 0.24 interpenetrating and settle in the untimed steps; widened ground), iterations=10")
     if name == "stress1000":
         return scenes.scene("Stress1000"), "--scene Stress1000 (iterations=20 beta=30000 gamma=0.995), settled for 400 steps"
     if name == "ensemble":
-        s = scenes.ensemble(scenes.scene("Pyramid"), 8192)
-        return s, "batched ensemble of 8192 independent Pyramid worlds (56 bodies each), iterations=10"
+        s = scenes.ensemble(scenes.scene("Pyramid"), ENSEMBLE_WORLDS)
+        return s, f"batched ensemble of {ENSEMBLE_WORLDS} independent Pyramid worlds (56 bodies each), iterations=10"
     raise ValueError(name)
 
 
-def cpu_reference_rate(sample_n, steps, kind):
-    """body-solves/s of the CPU implementation on a bounded sample: an n^3 pre-stacked sub-grid of the workload."""
+def headline_config(workload, desc):
+    """The SAME dict in both arms (the reference arm runs a bounded sample of it, described in cpu_baseline.sample)."""
+    return dict(workload=desc, iterations=20 if workload == "stress1000" else 10,
+                l2="inputs larger than L2 (body + contact state > 126 MB)" if workload in ("grid100", "ensemble") else
+                   "state is L2-resident; steady-state stepping, no flush")
+
+
+# ----------------------------------------------------------------------------------------------------------------- CPU arm
+def _oracle(kind="reference"):
     from _libs import Oracle, ref_available
-    from avbd_demo3d_b200 import scenes
     use_ref = kind == "reference" and ref_available()
-    o = Oracle("ref" if use_ref else "port").create()
+    return Oracle("ref" if use_ref else "port").create(), ("reference" if use_ref else "port")
+
+
+def cpu_grid_rate(sample_n, warmup, steps):
+    """The reference's CPU solver on an n^3 pre-stacked sub-grid of the headline workload (the full 1M grid is ~2600 s/step on the
+    O(n^2) pair loop).  Returns body-solves/s and steps/s, wall clock around Solver::step() only."""
+    from avbd_demo3d_b200 import scenes
+    o, kind = _oracle()
     s = scenes.stress_grid(sample_n, sample_n, sample_n, spacing_y=1.01, start_y=0.51, wide_ground=True)
     for i in range(len(s["size"])):
         o.add_body(s["size"][i], float(s["density"][i]), float(s["friction"][i]), s["pos"][i], s["quat"][i], s["lin"][i], s["ang"][i])
     o.set_params(iterations=10, beta=30000.0, gamma=0.995)
-    o.step(2)
+    o.step(warmup)
     t0 = time.perf_counter()
     o.step(steps)
     dt = time.perf_counter() - t0
     dyn = len(s["size"]) - 1
+    d = o.diagnostics()
     o.close()
-    return dict(value=dyn * 10 * steps / dt, unit="body-solves/s", cores=1, kind="reference" if use_ref else "port",
-                sample=f"{sample_n}^3={dyn}-box pre-stacked sub-grid of the workload, iterations=10, {steps} steps in {dt:.1f}s "
-                       f"(reference broadphase is O(n^2): the full 1M grid is ~2600 s/step extrapolated)",
-                steps_per_s=steps / dt)
+    return dict(value=dyn * 10 * steps / dt, unit="body-solves/s", cores=1, kind=kind, steps_per_s=steps / dt, ms_per_step=1e3 * dt / steps,
+                bodies=dyn + 1, contacts=d["contacts"],
+                sample=f"{sample_n}^3={dyn}-box pre-stacked sub-grid of the workload, iterations=10, {warmup} untimed + {steps} timed steps in {dt:.1f}s, "
+                       f"single-threaded like the reference (its broadphase is O(n^2): the full 1M grid is ~2600 s/step extrapolated)")
 
 
 def cpu_stress1000_rate(steps=40):
-    from _libs import Oracle, ref_available
-    o = Oracle("ref" if ref_available() else "port").create()
+    o, kind = _oracle()
     o.load_scene("Stress1000")
     o.step(400)        # settle into the contact-heavy regime the GPU number is quoted on
     t0 = time.perf_counter()
     o.step(steps)
     dt = time.perf_counter() - t0
+    d = o.diagnostics()
     o.close()
-    return steps / dt
+    return dict(steps_per_s=steps / dt, ms_per_step=1e3 * dt / steps, body_solves_per_s=1000 * 20 * steps / dt, cores=1, kind=kind,
+                contacts=d["contacts"], manifolds=d["manifolds"], steps=steps)
 
 
 def run_reference(args, rank):
+    """The reference's own CPU implementation of the path (oracle/_ref when it compiled here, else the port), rank 0 only."""
     if rank != 0:
         return
-    sample_n, steps = 16, max(1, args.steps)
     t0 = time.perf_counter()
-    per = []
-    for _ in range(1):
-        per.append(cpu_reference_rate(sample_n, args.warmup + steps, "reference"))
-    r = per[0]
-    _, desc = workload_preset(args.workload if args.workload != "stress1000" else "grid100")
-    line = dict(metric="body_solves_per_s", value=r["value"], unit="body-solves/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 / r["steps_per_s"], higher_is_better=True, scaling="strong" if args.workload == "ensemble" else "weak", vs_baseline=None, dtype="f32", data="synthetic",
-                impl="reference", config=dict(workload=desc, sample=r["sample"]),
-                cpu_baseline=dict(value=r["value"], unit=r["unit"], cores=r["cores"], kind=r["kind"], sample=r["sample"]),
-                e2e=dict(value=r["value"], unit="body-solves/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                wall_s=time.perf_counter() - t0)
+    workload = args.workload
+    _, desc = workload_preset(workload)
+    if workload == "stress1000":
+        s = cpu_stress1000_rate(max(args.steps, 1))
+        value, ms, sample, kind = s["body_solves_per_s"], s["ms_per_step"], "Stress1000 as it is (settled 400 steps), 1 core", s["kind"]
+        same = dict(stress1000=s)
+    else:
+        # steps are capped so the run ends within minutes whatever K the driver passes (20^3: ~0.65 s per step on one core)
+        k = max(1, min(args.steps, 24))
+        g = cpu_grid_rate(GRID_SAMPLE, min(max(args.warmup, 1), 6), k)
+        value, ms, sample, kind = g["value"], g["ms_per_step"], g["sample"], g["kind"]
+        same = dict(grid20=dict(steps_per_s=g["steps_per_s"], ms_per_step=g["ms_per_step"], body_solves_per_s=g["value"], cores=1, kind=kind,
+                                bodies=g["bodies"], contacts=g["contacts"]),
+                    stress1000=cpu_stress1000_rate(30))
+    line = dict(metric="body_solves_per_s", value=value, unit="body-solves/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference", config=headline_config(workload, desc),
+                cpu_baseline=dict(value=value, unit="body-solves/s", cores=1, kind=kind, sample=sample),
+                e2e=dict(value=value, unit="body-solves/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                same_config=same, wall_s=time.perf_counter() - t0)
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------- GPU arm
+def pinned(n_rows):
+    import torch
+    t = torch.empty((n_rows, 13), dtype=torch.float32).pin_memory()
+    return t, t.numpy()
+
+
+def e2e_loop(w, host_np, steps):
+    """Host buffers in, host buffers out, every step; returns seconds."""
+    w.download_state_into(host_np)
+    w.sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.set_state(host_np)            # H2D of the step's inputs (pinned)
+        w.step(1, sync=False)
+        w.download_state_into(host_np)  # D2H of the step's result (pinned), synchronises
+    w.diagnostics()
+    return time.perf_counter() - t0
+
+
+def small_world_leg(avbd, device, preset, settle, steps, iters):
+    """One world both arms can run as it is: device-resident steps/s and e2e through host buffers."""
+    from avbd_demo3d_b200 import scenes
+    w = avbd.World(device)
+    scenes.load(w, preset)
+    w.step(settle)
+    ms = w.step_timed(steps)
+    st = w.step_stats()
+    _, host_np = pinned(w.n)
+    sec = e2e_loop(w, host_np, steps)
+    n_dyn = st["dynamicBodies"]
+    out = dict(steps_per_s=steps / (ms * 1e-3), ms_per_step=ms / steps, body_solves_per_s=n_dyn * iters * steps / (ms * 1e-3),
+               e2e=dict(steps_per_s=steps / sec, ms_per_step=1e3 * sec / steps, body_solves_per_s=n_dyn * iters * steps / sec,
+                        h2d_bytes_per_step=w.n * 52, d2h_bytes_per_step=w.n * 52),
+               bodies=w.n, manifolds=st["manifolds"], contacts=st["contacts"], colours=st["colours"], steps=steps)
+    w.close()
+    return out
+
+
+def cpp_host_leg(steps, reupload):
+    """Solver::step() of the C++17 host mirror (the boundary the drop-in advertises) on the headline workload, as a subprocess."""
+    exe = os.path.join(ROOT, "avbd-demo3d_b200", "host", "avbd_demo3d")
+    if not os.path.exists(exe):
+        return dict(unavailable="host CLI not built")
+    cmd = [exe, "--nogfx", "--quiet", "--grid", "100", "--stacked", "--warmup", "15", "--steps", str(steps)] + (["--reupload"] if reupload else [])
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()[-1]
+        j = json.loads(out)
+        dyn = j["dynBodies"]
+        return dict(ms_per_step=j["ms_per_step"], steps_per_s=j["steps_per_s"], body_solves_per_s=dyn * 10 * j["steps_per_s"],
+                    h2d_bytes_per_step=j["h2d_bytes"] / max(1, steps + 15), d2h_bytes_per_step=j["d2h_bytes"] / max(1, steps + 15),
+                    cmd=" ".join(cmd[1:]))
+    except Exception as e:
+        return dict(unavailable=f"{type(e).__name__}: {e}"[:200])
 
 
 def main():
@@ -178,21 +323,30 @@ def main():
         run_reference(args, rank)
         return
 
+    affinity = bind_to_gpu_numa_node(local_rank)
+
+    # CPU legs first, on rank 0 at N=1 only, BEFORE any GPU or process-group work: nothing spins while the host cores are timed
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        g = cpu_grid_rate(GRID_SAMPLE, 2, 10)
+        cpu = dict(baseline=dict(value=g["value"], unit=g["unit"], cores=1, kind=g["kind"], sample=g["sample"]),
+                   grid20=dict(steps_per_s=g["steps_per_s"], ms_per_step=g["ms_per_step"], body_solves_per_s=g["value"], cores=1, kind=g["kind"],
+                               bodies=g["bodies"], contacts=g["contacts"]),
+                   stress1000=cpu_stress1000_rate(30))
+
     import torch
     import avbd_demo3d_b200 as avbd
     from avbd_demo3d_b200 import scenes
 
     dist = None
+    torch.cuda.set_device(local_rank)
     if world_size > 1:
         # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (printed from level VERSION up, which some images
         # configure) out of it; an explicit INFO / TRACE request is left alone
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
             os.environ["NCCL_DEBUG"] = "NONE"
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
     def barrier():
@@ -200,10 +354,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(vals):
+        mine = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if dist is None:
+            return [[float(x) for x in mine.tolist()]]
+        allv = [torch.zeros_like(mine) for _ in range(world_size)]
+        dist.all_gather(allv, mine)
+        return [[float(x) for x in v.tolist()] for v in allv]
+
+    W = max(3, args.warmup)
     preset, desc = workload_preset(args.workload)
     if args.workload == "ensemble" and world_size > 1:      # shard the worlds (block partition) across ranks
-        total = 8192
-        per = total // world_size
+        per = ENSEMBLE_WORLDS // world_size
         preset = scenes.ensemble(scenes.scene("Pyramid"), per, first_world=rank * per)
     w = avbd.World(local_rank)
     scenes.load(w, preset)
@@ -212,98 +380,124 @@ def main():
     # has plateaued so no device buffer grows inside the timed region
     w.step(400 if args.workload == "stress1000" else 12)
     iters = w.params["iterations"]
-    w.step(max(3, args.warmup))
-    stats0 = w.step_stats()
-    n_dyn = stats0["dynamicBodies"]
+    w.step(W)
+    n_dyn = w.step_stats()["dynamicBodies"]
 
-    # ---- timed region: K steps, state resident in HBM
-    w.set_profiling(True)
+    # ---- timed region: K steps, state resident in HBM, no profiling hooks (no host sync inside a step beyond the solver's own)
     launches0 = w.profile()["kernel_launches"]
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms = w.step_timed(args.steps)
     barrier()
+    clocks = sampler.stop() if sampler else None
+    launches_timed = w.profile()["kernel_launches"] - launches0
+    ms_max = max_over_ranks(ms)
+
+    # ---- the same K steps again with per-kernel CUDA events (roofline): stage splits, sweep / dual times, sizes
+    w.set_profiling(True)
+    ms_prof = w.step_timed(args.steps)
     prof = w.profile()
     w.set_profiling(False)
-    launches_timed = prof["kernel_launches"] - launches0
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     stats = w.step_stats()
     diag = w.diagnostics()
 
     # ---- end to end: host buffers in, host buffers out, every step
-    host = torch.empty((n_bodies, 13), dtype=torch.float32).pin_memory()
-    host_np = host.numpy()
-    w.download_state_into(host_np)
+    _, host_np = pinned(n_bodies)
     e2e_steps = max(3, min(args.steps, 10))
+    e2e_loop(w, host_np, 1)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        w.set_state(host_np)            # H2D of the step's inputs (pinned)
-        w.step(1, sync=False)
-        w.download_state_into(host_np)  # D2H of the step's result (pinned), synchronises
-    d = w.diagnostics()
+    e2e_s = max_over_ranks(e2e_loop(w, host_np, e2e_steps))
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    w.close()
 
-    # ---- diagnostics gather over NCCL (the only inter-GPU traffic of the path)
-    gathered = None
-    if dist is not None:
-        mine = torch.tensor([diag["maxPen"], diag["maxLin"], float(diag["contacts"]), float(diag["manifolds"])], device=dev)
-        allv = [torch.zeros_like(mine) for _ in range(world_size)]
-        dist.all_gather(allv, mine)
-        gathered = [[float(x) for x in v.tolist()] for v in allv]
+    # ---- BASELINE.json config 4 in EVERY line: 8192 Pyramid worlds block-sharded over the ranks (strong scaling)
+    ensemble = None
+    if not args.no_extras:
+        per = ENSEMBLE_WORLDS // world_size
+        ens = scenes.ensemble(scenes.scene("Pyramid"), per, first_world=rank * per)
+        we = avbd.World(local_rank)
+        scenes.load(we, ens)
+        we.step(12 + W)
+        barrier()
+        ems = we.step_timed(args.steps)
+        barrier()
+        est = we.step_stats()
+        ed = we.diagnostics()
+        _, ehost = pinned(we.n)
+        e2e_loop(we, ehost, 1)
+        barrier()
+        esec = e2e_loop(we, ehost, e2e_steps)
+        barrier()
+        rows = gather([ems / args.steps, 1e3 * esec / e2e_steps, float(est["dynamicBodies"]), float(ed["contacts"]), float(ed["manifolds"]), float(ed["maxPen"])])
+        we.close()
+        ems_max = max(r[0] for r in rows)
+        e2e_max = max(r[1] for r in rows)
+        dyn_total = sum(r[2] for r in rows)
+        ensemble = dict(workload=f"{ENSEMBLE_WORLDS} independent jittered Pyramid worlds, {per} per rank (block partition), iterations=10; strong scaling over n_gpus",
+                        worlds=ENSEMBLE_WORLDS, worlds_per_rank=per, dynamic_bodies=int(dyn_total), ms_per_step=ems_max, steps_per_s=1e3 / ems_max,
+                        body_solves_per_s=dyn_total * 10 * 1e3 / ems_max, per_rank_ms=[r[0] for r in rows],
+                        e2e=dict(ms_per_step=e2e_max, steps_per_s=1e3 / e2e_max, body_solves_per_s=dyn_total * 10 * 1e3 / e2e_max,
+                                 h2d_bytes_per_step=per * 56 * 52, d2h_bytes_per_step=per * 56 * 52, per_rank_ms=[r[1] for r in rows]),
+                        contacts=int(sum(r[3] for r in rows)), manifolds=int(sum(r[4] for r in rows)), max_penetration=max(r[5] for r in rows),
+                        collective="NCCL all_gather of 6 floats per rank after the timed region (timings + diagnostics); none on the data path")
+
+    gathered = gather([diag["maxPen"], diag["maxLin"], float(diag["contacts"]), float(diag["manifolds"])]) if dist is not None else None
 
     if rank == 0:
         total_dyn = n_dyn * world_size
         value = total_dyn * iters * args.steps / (ms_max * 1e-3)
         peak, peak_src = measured_peak()
         traffic, traffic_src = ncu_traffic()
-        primal_bytes = (PRIMAL_BYTES_PER_BODY * prof["primal_bodies"] + PRIMAL_BYTES_PER_VISIT * prof["primal_visits"]
-                        + DEFERRED_DUAL_BYTES_PER_CONTACT * prof["deferred_dual_contacts"])
-        dual_bytes = DUAL_BYTES_PER_CONTACT * prof["dual_contacts"]
-        primal_gbs = primal_bytes / max(prof["ms_primal"], 1e-9) / 1e6
-        dual_gbs = dual_bytes / max(prof["ms_dual"], 1e-9) / 1e6
+        sb = stage_bytes(prof)
+        sms = dict(broadphase=prof["ms_broadphase"], narrowphase=prof["ms_narrowphase"], graph=prof["ms_graph"], predict=prof["ms_predict"],
+                   primal=prof["ms_primal"], dual=prof["ms_dual"], velocity=prof["ms_velocity"])
+        stages = {}
+        for k in sb:
+            gbs = sb[k] / max(sms[k], 1e-9) / 1e6
+            stages[k] = dict(algorithmic_bytes_per_step=sb[k] / max(prof["steps"], 1), ms_per_step=sms[k] / max(prof["steps"], 1), achieved=gbs, frac=gbs / peak)
+        primal_gbs, dual_gbs = stages["primal"]["achieved"], stages["dual"]["achieved"]
+        whole = sum(sb.values()) / max(prof["ms_step"], 1e-9) / 1e6
         line = dict(
-            metric="body_solves_per_s", value=value, unit="body-solves/s", n_gpus=world_size, steps=args.steps, warmup=max(3, args.warmup),
-            ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="strong" if args.workload == "ensemble" else "weak", vs_baseline=None, dtype="f32", data="synthetic",
-            config=dict(workload=desc, bodies_per_gpu=n_bodies, dynamic_bodies_per_gpu=n_dyn, manifolds=stats["manifolds"], contacts=stats["contacts"],
-                        colours=stats["colours"], iterations=iters, parallelism=f"independent-worlds x{world_size}",
-                        l2="inputs larger than L2 (body + contact state > 126 MB)" if n_bodies > 300000 else "state is L2-resident; steady-state stepping, no flush"),
+            metric="body_solves_per_s", value=value, unit="body-solves/s", n_gpus=world_size, steps=args.steps, warmup=W,
+            ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="strong" if args.workload == "ensemble" else "weak", vs_baseline=None,
+            dtype="f32", data="synthetic", config=headline_config(args.workload, desc),
+            workload_stats=dict(bodies_per_gpu=n_bodies, dynamic_bodies_per_gpu=n_dyn, manifolds=stats["manifolds"], contacts=stats["contacts"],
+                                contact_visits=stats["contactVisits"], colours=stats["colours"], parallelism=f"independent-worlds x{world_size}"),
             steps_per_s=args.steps / (ms_max * 1e-3),
-            roofline=dict(bound="hbm", kernel="primal_visit_flat<128,4> + primal_solve_flat (one pair per colour = one colour sweep; sweeps 2.. also apply the deferred dual)", achieved=primal_gbs, peak=peak, unit="GB/s", frac=primal_gbs / peak,
+            roofline=dict(bound="hbm", kernel="primal colour sweep (one launch per colour: contact visits -> per-body 6x6 sums -> block solve; sweeps 2.. also apply the deferred dual)",
+                          achieved=primal_gbs, peak=peak, unit="GB/s", frac=primal_gbs / peak,
                           traffic=traffic if args.workload == "grid100" else None, traffic_source=traffic_src if args.workload == "grid100" else None,
-                          peak_source=peak_src, algorithmic_bytes_per_launch=primal_bytes / max(prof["primal_launches"], 1),
-                          avg_launch_ms=prof["ms_primal"] / max(prof["primal_launches"], 1), share_of_step=prof["ms_primal"] / ms,
-                          deferred_dual_passes_per_step=prof["deferred_dual_contacts"] / max(1, prof["steps"] * max(1, stats["contacts"])),
-                          dual=dict(kernel="dual_contacts (stand-alone passes only: the step's last)", achieved=dual_gbs, frac=dual_gbs / peak, share_of_step=prof["ms_dual"] / ms,
-                                    avg_launch_ms=prof["ms_dual"] / max(prof["dual_launches"], 1))),
-            stage_ms=dict(broadphase=stats["ms_broadphase"], narrowphase=stats["ms_narrowphase"], predict=stats["ms_predict"], graph=stats["ms_graph"],
-                          primal_dual=stats["ms_primal"], velocity_diag=stats["ms_velocity"], total=stats["ms_total"]),
+                          peak_source=peak_src, algorithmic_bytes_per_launch=sb["primal"] / max(prof["primal_launches"], 1),
+                          avg_launch_ms=prof["ms_primal"] / max(prof["primal_launches"], 1), share_of_step=prof["ms_primal"] / max(prof["ms_step"], 1e-9),
+                          deferred_dual_passes_per_step=prof["deferred_dual_contacts"] / max(1, prof["contacts"]),
+                          dual=dict(kernel="dual_contacts (stand-alone passes only: the step's last)", achieved=dual_gbs, frac=dual_gbs / peak,
+                                    share_of_step=prof["ms_dual"] / max(prof["ms_step"], 1e-9), avg_launch_ms=prof["ms_dual"] / max(prof["dual_launches"], 1)),
+                          stages=stages, whole_step=dict(achieved=whole, frac=whole / peak, ms_per_step=prof["ms_step"] / max(prof["steps"], 1)),
+                          measured="the K steps after the timed region, per-stage CUDA events on the solver's stream (profiled ms_per_step %.3f vs %.3f unprofiled)"
+                                   % (ms_prof / args.steps, ms / args.steps)),
+            stage_ms={k: v["ms_per_step"] for k, v in stages.items()},
             e2e=dict(value=total_dyn * iters * e2e_steps / e2e_s, unit="body-solves/s", h2d_bytes_per_step=n_bodies * 52, d2h_bytes_per_step=n_bodies * 52 + 48,
-                     steps=e2e_steps, ms_per_step=1e3 * e2e_s / e2e_steps),
-            gpu_launches=int(launches_timed), clocks=clocks, diagnostics=diag, nccl_gathered_diagnostics=gathered)
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_rate(16, 25, "reference")
-            if args.workload in ("grid100", "grid50"):
-                # the metric's other half: Stress1000 steps/s, GPU and CPU, same regime (settled, contact-heavy)
-                w2 = avbd.World(local_rank)
-                scenes.load(w2, scenes.scene("Stress1000"))
-                w2.step(400)
-                ms2 = w2.step_timed(200)
-                st2 = w2.step_stats()
-                w2.close()
-                line["stress1000"] = dict(steps_per_s=200 / (ms2 * 1e-3), ms_per_step=ms2 / 200, manifolds=st2["manifolds"], contacts=st2["contacts"],
-                                          cpu_steps_per_s=cpu_stress1000_rate(), cpu_cores=1)
+                     steps=e2e_steps, ms_per_step=1e3 * e2e_s / e2e_steps, cpu_affinity=affinity),
+            gpu_launches=int(launches_timed), clocks=clocks, diagnostics=diag, nccl_gathered_diagnostics=gathered, ensemble=ensemble)
+        if cpu is not None:
+            line["cpu_baseline"] = cpu["baseline"]
+        if not args.no_extras and world_size == 1:
+            # workloads both arms run as they are: the reference arm prints the same record (`--impl reference`), and the CPU side measured
+            # in THIS run sits next to it
+            same = dict(stress1000=small_world_leg(avbd, local_rank, scenes.scene("Stress1000"), 400, 200, 20),
+                        grid20=small_world_leg(avbd, local_rank, workload_preset("grid20")[0], 12 + W, 50, 10))
+            if cpu is not None:
+                for k in ("stress1000", "grid20"):
+                    same[k]["cpu"] = cpu[k]
+                    same[k]["speedup_device_resident"] = same[k]["steps_per_s"] / cpu[k]["steps_per_s"]
+                    same[k]["speedup_e2e"] = same[k]["e2e"]["steps_per_s"] / cpu[k]["steps_per_s"]
+            line["same_config"] = same
+            line["stress1000"] = dict(steps_per_s=same["stress1000"]["steps_per_s"], ms_per_step=same["stress1000"]["ms_per_step"],
+                                      cpu_steps_per_s=cpu["stress1000"]["steps_per_s"] if cpu else None, cpu_cores=1)
+            if args.workload == "grid100":
+                line["e2e_cpp_host"] = dict(no_edits=cpp_host_leg(10, False), every_body_reuploaded=cpp_host_leg(10, True),
+                                            note="Solver::step() of the C++17 mirror, 1M-box grid: sync host edits (dirty ranges) -> avbd_step -> read every Rigid back")
         print(json.dumps(line), flush=True)
-    w.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -54,9 +54,16 @@ typedef struct avbd_profile {
     long long steps, primal_sweeps, primal_launches, primal_bodies, primal_visits, dual_launches, dual_contacts;
     long long kernel_launches, library_launches;   /* totals since world creation: own kernels / CUB passes */
     long long deferred_dual_contacts;              /* contact dual updates applied INSIDE primal sweeps (deferred dual): their time is in ms_primal */
+    /* per-stage device time and the sizes SURVEY.md section 8d's byte formulas need, summed over the profiled steps */
+    double ms_broadphase, ms_narrowphase, ms_graph, ms_predict, ms_solve, ms_velocity, ms_step;
+    long long bodies, pairs, candidates, manifolds, manifolds_prev, contacts, visits, graph_builds;
 } avbd_profile;
 
 const char* avbd_last_error(void);
+/* Page-locked host buffers for the state exchange (avbd_upload_state / avbd_download_state run at DMA speed from these;
+ * any other host pointer works too, through the driver's staging copy). */
+void* avbd_host_alloc(long long bytes);
+void  avbd_host_free(void* p);
 int  avbd_device_count(void);
 
 /* Solver::Solver / ~Solver (solver.cpp:129-143). */
@@ -81,10 +88,27 @@ int  avbd_num_bodies(const avbd_world* w);
 /* new Joint(...) (joint.cpp:11-63).  a = -1: body-world weld at world anchor anchorA. */
 int  avbd_add_joint(avbd_world* w, int a, int b, const float* anchorA3, const float* anchorB3, float linearStiffness,
                     float angularStiffness);
+/* The same weld with the construction-time values the caller already holds (Joint::rB and
+ * Joint::initialRelativeOrientation, joint.h:17-19, captured by the constructors at joint.cpp:19, :47-50) instead of
+ * values derived from the device poses at upload time: a joint re-added after a rebuild keeps its original reference. */
+int  avbd_add_joint_raw(avbd_world* w, int a, int b, const float* rA3, const float* rB3, const float* rel0_4,
+                        float linearStiffness, float angularStiffness);
 /* new Spring(...) (spring.cpp:10-30).  rest < 0: current distance. */
 int  avbd_add_spring(avbd_world* w, int a, int b, const float* anchorA3, const float* anchorB3, float stiffness, float rest);
 /* new IgnoreCollision(...) (ignorecollision.h:14-16). */
 int  avbd_add_ignore(avbd_world* w, int a, int b);
+
+/* The public row arrays of a user Force (solver.h:91-97: lambda, penalty, motor, stiffness) — kind 0 joint (6 rows),
+ * 1 spring (1 row), index = the value avbd_add_joint / avbd_add_spring returned.  set: a NULL array is left alone
+ * (motor enters the primal at solver.cpp:380, stiffness decides hard / soft at :378, :290, :416).  get: device values. */
+int  avbd_set_force_rows(avbd_world* w, int kind, int index, const float* lambda, const float* penalty, const float* motor,
+                         const float* stiffness);
+int  avbd_get_force_rows(avbd_world* w, int kind, int index, float* lambda, float* penalty, float* motor, float* stiffness);
+/* lambda / penalty of EVERY user force after a step, one copy: joints12 = lambda6 penalty6 per joint, springs2 = lambda penalty
+ * per spring (the host mirror refreshes Force::lambda / Force::penalty from it).  Either may be NULL. */
+int  avbd_download_user_rows(avbd_world* w, float* joints12, float* springs2);
+int  avbd_num_joints(const avbd_world* w);
+int  avbd_num_springs(const avbd_world* w);
 
 /* Solver::step() x n (solver.cpp:255-514).  Asynchronous on the world's stream. */
 int  avbd_step(avbd_world* w, int n);
@@ -97,6 +121,8 @@ int  avbd_get_profile(avbd_world* w, avbd_profile* out);
 /* Rigid public state (solver.h:56-60): 13 floats per body pos3 quat4 lin3 ang3, creation order. */
 int  avbd_download_state(avbd_world* w, float* out13);
 int  avbd_upload_state(avbd_world* w, const float* in13);
+/* Host edits of a few bodies (main.cpp:88-142 moves / re-spins bodies between steps): bodies [first, first + count). */
+int  avbd_upload_state_range(avbd_world* w, int first, int count, const float* in13);
 int  avbd_download_prev_linvel(avbd_world* w, float* out3);
 int  avbd_upload_prev_linvel(avbd_world* w, const float* in3);
 /* size3 mass invMass inertiaDiag3 friction radius (solver.h:67-72), 10 floats per body. */
@@ -117,6 +143,18 @@ int  avbd_world_diagnostics_device_ptr(avbd_world* w, void** ptr, int* count);
  * as the reference deletes them (solver.cpp:274-279). */
 int  avbd_num_manifolds(avbd_world* w);
 int  avbd_download_manifolds(avbd_world* w, int* ints3, int* feats4, int* stick4, float* flts81);
+
+/* Inverse of avbd_download_manifolds: replaces the manifold set (any order; idxA > idxB; dead manifolds not allowed).
+ * What Manifold::initialize carries over next step (manifold.cpp:111-155) is exactly this set, so a caller can hand the
+ * solver a warm-start history (parity tests, host edits of Manifold rows, avbd_restore). */
+int  avbd_upload_manifolds(avbd_world* w, int count, const int* ints3, const int* feats4, const int* stick4, const float* flts81);
+
+/* Snapshot / restore of the whole simulation state (the reference can only clear() and re-run a
+ * scene, solver.cpp:230-238): parameters, bodies, user forces with their rows, the manifold set with lambda / penalty /
+ * stick anchors.  A restored world continues bit-identically.  The blob is opaque and only valid for this library build. */
+long long avbd_snapshot_bytes(avbd_world* w);
+int  avbd_snapshot(avbd_world* w, void* buf, long long cap);
+int  avbd_restore(avbd_world* w, const void* buf, long long bytes);
 
 /* ---- per-stage entry points (parity tests drive these one at a time) ------------------------- */
 /* solver.cpp:262-270: sphere-overlap pair set of the current poses, sorted (a > b); returns count. */

@@ -1108,6 +1108,30 @@ void orc_get_manifolds(void* h, int* ints, int* feats, int* stick, float* flts) 
     }
 }
 
+// Replaces the world's manifold set (test seam: lets a parity test start BOTH sides of a per-stage comparison from the same
+// warm-start history).  Same layout and order as orc_get_manifolds (newest first), so get -> set is the identity.
+void orc_set_manifolds(void* h, int count, const int* ints, const int* feats, const int* stick, const float* flts) {
+    World& w = W(h);
+    for (int s = 0; s < (int)w.forces.size(); ++s) if (w.forces[s].alive && w.forces[s].kind == MANIFOLD) killForce(w, s);
+    compactForces(w);
+    for (int m = count - 1; m >= 0; --m) {               // oldest first = creation order
+        const int* I = ints + 3 * m; const float* F = flts + 81 * m;
+        int s = newForce(w, MANIFOLD, I[0], I[1]);
+        Force& f = w.forces[s];
+        f.nct = I[2]; f.mu = F[0];
+        for (int i = 0; i < 4; ++i) {
+            Contact& c = f.ct[i]; const float* v = F + 1 + 14 * i;
+            c.feature = feats[4 * m + i]; c.stick = stick[4 * m + i] != 0;
+            c.rA = mk(v[0], v[1], v[2]); c.rB = mk(v[3], v[4], v[5]); c.normal = mk(v[6], v[7], v[8]);
+            c.penetration = v[9]; c.C0n = v[10]; c.C0t = mk(v[11], v[12], v[13]);
+        }
+        for (int k = 0; k < 12; ++k) {
+            f.lambda[k] = F[57 + k]; f.penalty[k] = F[69 + k];
+            if (k < f.nct * 3) { f.stiffness[k] = FLT_MAX; f.motor[k] = 0.0f; }
+        }
+    }
+}
+
 int orc_overlap_pairs(void* h, int* pairs, int cap) {       // the sphere test of solver.cpp:264-266, no exclusion
     World& w = W(h);
     int n = (int)w.bodies.size(), cnt = 0;

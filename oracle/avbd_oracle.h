@@ -69,6 +69,8 @@ void  orc_get_diagnostics(void* w, float* out5f, int* out3i);
 
 int   orc_num_manifolds(void* w);
 void  orc_get_manifolds(void* w, int* ints3, int* feats4, int* stick4, float* flts81);
+/* test seam: replace the manifold set (same layout / order as orc_get_manifolds) */
+void  orc_set_manifolds(void* w, int count, const int* ints3, const int* feats4, const int* stick4, const float* flts81);
 /* sphere-overlap pairs (a > b) of the CURRENT poses, reference loop order; returns count (may exceed cap) */
 int   orc_overlap_pairs(void* w, int* pairs2, int cap);
 

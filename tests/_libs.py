@@ -93,6 +93,7 @@ class Oracle:
             self._fn("overlap_pairs", C.c_int, [C.c_void_p, i32p, C.c_int])
             self._fn("load_stress_grid", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int])
             self._fn("set_logging", None, [C.c_void_p, C.c_int, C.c_int])
+            self._fn("set_manifolds", None, [C.c_void_p, C.c_int, i32p, i32p, i32p, f32p])
         self.h = None
 
     def _fn(self, name, res, args):
@@ -188,6 +189,20 @@ class Oracle:
         if m:
             self._get_manifolds(self.h, ints, feats, stick, flts)
         return manifold_dict(ints, feats, stick, flts)
+
+    def manifolds_raw(self):
+        m = self._num_manifolds(self.h)
+        ints, feats, stick, flts = (np.zeros((m, 3), np.int32), np.zeros((m, 4), np.int32), np.zeros((m, 4), np.int32), np.zeros((m, 81), np.float32))
+        if m:
+            self._get_manifolds(self.h, ints, feats, stick, flts)
+        return ints, feats, stick, flts
+
+    def set_manifolds(self, ints, feats, stick, flts):
+        """port only: replace the manifold set (same layout / order manifolds_raw() returns)."""
+        ints = np.ascontiguousarray(ints, np.int32).reshape(-1, 3)
+        m = len(ints)
+        self._set_manifolds(self.h, m, ints, np.ascontiguousarray(feats, np.int32).reshape(m, 4),
+                            np.ascontiguousarray(stick, np.int32).reshape(m, 4), _f(flts).reshape(m, 81))
 
     def overlap_pairs(self):
         cap = max(1024, self.n * 64)

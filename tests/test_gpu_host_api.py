@@ -72,3 +72,67 @@ def test_same_source_against_reference_and_mirror():
         assert [x for x in a if not x[0].isdigit() and x[0] != "-"] == [x for x in b if not x[0].isdigit() and x[0] != "-"]      # same words
         for i in (14, 17, 20, 23, 26):                                   # maxPen maxDrift maxLin maxAng maxLambda
             assert abs(float(a[i]) - float(b[i])) <= 0.05, (i, a, b)
+
+
+EDIT = os.path.join(ROOT, "tests", "host_api", "edit_probe_b200")
+CLI = os.path.join(PKG_DIR, "host", "avbd_demo3d")
+
+
+def test_host_mirror_edits_deletes_and_snapshots():
+    """tests/host_api/edit_probe.cpp: body deletion keeps the other manifolds' warm-start history, a re-uploaded Joint keeps its
+    construction-time anchor, motor / stiffness edits reach the solver, one moved body uploads one body, snapshot resumes exactly."""
+    if not os.path.exists(EDIT):
+        subprocess.run(["make", "-s", "-C", os.path.join(PKG_DIR, "host")], check=True)
+    rows = {}
+    for line in subprocess.run([EDIT], capture_output=True, text=True, check=True, timeout=300).stdout.splitlines():
+        key, *vals = line.split()
+        rows.setdefault(key, []).append(vals)
+    d = rows["delete_body"][0]
+    assert int(d[1]) == 10 and int(d[2]) == 9 and int(d[8]) == 10, d               # 11 bodies -> 10; the top manifold went with its body
+    before, after = float(d[4]), float(d[6])
+    assert before > 3.0e4, before                                                  # the ramp had raised it well above PENALTY_MIN
+    assert after >= 0.97 * before, (before, after)                                 # kept (one step's gamma decay), not restarted at 2e4
+    s = rows["delete_body"][1]
+    assert float(s[1]) < 0.2, s                                                    # the stack did not re-settle
+    assert int(rows["edit_one_body"][0][1]) == 52 and int(rows["edit_nothing"][0][1]) == 0
+    soft = rows["soft_row"][0]
+    assert abs(float(soft[1]) - 10.0 / 400.0) < 3e-3 and float(soft[3]) <= 400.0 and float(soft[5]) == 0.0, soft
+    keep = rows["rebuild_keeps_anchor"][0]
+    assert abs(float(keep[1]) - 10.0 / 400.0) < 3e-3, keep                         # still hangs below the ORIGINAL anchor (C != 0 at the sagged pose)
+    assert abs(float(keep[3])) < 1e-6 and abs(float(keep[4])) < 1e-6 and abs(float(keep[5])) < 1e-6, keep
+    assert abs(float(rows["motor"][0][1]) - (10.0 - 4.0) / 400.0) < 3e-3, rows["motor"]
+    assert rows["snapshot_resume_identical"][0][0] == "1"
+
+
+def test_host_cli_binary_dump_and_snapshot(tmp_path):
+    """--dump-binary holds what the text dump prints; --save-snapshot / --load-snapshot resume exactly."""
+    import numpy as np
+    full, part, rest, snap = (str(tmp_path / n) for n in ("full.trj", "part.trj", "rest.trj", "state.snp"))
+    run = lambda *a: subprocess.run([CLI, "--nogfx", "--scene", "Pyramid"] + list(a), capture_output=True, text=True, check=True, timeout=300).stdout
+    text = run("--steps", "30").splitlines()
+    run("--steps", "30", "--dump-binary", full)
+
+    def load(path):
+        raw = open(path, "rb").read()
+        assert raw[:8] == b"AVBDTRJ1"
+        n, steps = np.frombuffer(raw, np.int32, 2, 8)
+        rec = 4 + n * 13 * 4 + 5 * 4 + 3 * 4
+        assert len(raw) == 16 + steps * rec
+        states = np.stack([np.frombuffer(raw, np.float32, n * 13, 16 + k * rec + 4).reshape(n, 13) for k in range(steps)])
+        counts = np.stack([np.frombuffer(raw, np.int32, 3, 16 + k * rec + 4 + n * 52 + 20) for k in range(steps)])
+        return states, counts
+
+    states, counts = load(full)
+    n = states.shape[1]
+    per_step = n + 2
+    last = text[1 + 29 * per_step: 1 + 30 * per_step]
+    pos = lambda l: [float(x) for x in l.split("Pos(")[1].split(")")[0].split(",")]
+    for k, line in enumerate(last[1:1 + n]):          # text lists newest first, the binary record is in creation order
+        assert np.allclose(pos(line), states[-1, n - 1 - k, :3], atol=5.1e-5), (k, line)
+    assert f"manifolds={counts[-1, 0]} contacts={counts[-1, 1]} dynBodies={counts[-1, 2]}" in last[-1]
+    # resume: 18 steps + snapshot, then 12 steps from the snapshot == 30 steps in one go, bit for bit
+    run("--steps", "18", "--dump-binary", part, "--save-snapshot", snap)
+    run("--steps", "12", "--dump-binary", rest, "--load-snapshot", snap)
+    a, _ = load(part); b, _ = load(rest)
+    assert a[-1].tobytes() == states[17].tobytes()
+    assert b[-1].tobytes() == states[-1].tobytes()

@@ -1,0 +1,348 @@
+"""Per-stage parity on IDENTICAL inputs at a step k > 0 (round-2 additions).  Needs a GPU.
+
+Both sides of every comparison start from the SAME state: the oracle's bodies (avbd_upload_state) and the oracle's
+manifold set with its lambda / penalty / stick anchors (avbd_upload_manifolds, the inverse of avbd_download_manifolds).
+
+  dual / penalty ramp   solver.cpp:411-430, rowPenaltyGain :94-125 — `dual_fast` is re-derived algebra (|w x b|^2 =
+                        |w|^2 - (w.b)^2, __fdividef, fminf/fmaxf), so it is held to a stated FP32 tolerance:
+                        lambda and penalty <= 1e-4 relative (+ 1e-3 / 1e-1 absolute), stick equal except where the
+                        oracle's |lambda_t| sits within 1e-4 of the friction-cone limit (the test is decided by rounding)
+  warm-start carry-over manifold.cpp:111-155 (first unused equal feature key, dot >= 0.9 / drift <= 0.08 carry, stick-anchor
+                        reuse 0.995 / 0.015) — bit-exact, at step k > 0, including old manifolds with DUPLICATE feature keys
+  ensemble world        one jittered Pyramid world of an 8192-world batch against the oracle on the same bodies
+  snapshot / restore    a restored world continues bit-identically (avbd_snapshot / avbd_restore)
+"""
+import numpy as np
+import pytest
+
+from _libs import Oracle, add_all, manifold_dict, random_pile
+from test_gpu_parity import assert_manifolds_equal, colour_order, gpu_manifolds, make_pair
+
+pytestmark = pytest.mark.gpu
+
+LAM_RTOL, LAM_ATOL = 1e-4, 1e-3          # lambda is O(10..5000)
+PEN_RTOL, PEN_ATOL = 1e-4, 1e-1          # penalty is O(2e4..2e6)
+CONE_RTOL = 1e-4                         # a stick flag may differ only this close to the cone limit
+
+
+def _advance(o, steps):
+    o.step(steps)
+
+
+def _oracle_pre_dual(o, sweeps):
+    """Runs the oracle's next step up to (and including) the primal sweep of iteration `sweeps` - 1; returns alpha."""
+    p = o.params()
+    o.stage("broadphase"); o.stage("init"); o.stage("predict")
+    for it in range(sweeps - 1):
+        o.stage_primal(p["alpha"]); o.stage("dual", p["alpha"])
+    o.stage_primal(p["alpha"])
+    return p["alpha"]
+
+
+def _compare_dual(got, pre, want, ctx):
+    assert set(got) == set(want), (ctx, sorted(set(got) ^ set(want))[:10])
+    n_contacts = n_stick_diff = n_far = 0
+    worst_l = worst_p = 0.0
+    for k, r in want.items():
+        g, q = got[k], pre[k]
+        assert g["n"] == r["n"], (ctx, k)
+        el = np.abs(g["lam"] - r["lam"]) - (LAM_RTOL * np.abs(r["lam"]) + LAM_ATOL)
+        ep = np.abs(g["pen"] - r["pen"]) - (PEN_RTOL * np.abs(r["pen"]) + PEN_ATOL)
+        assert (el <= 0).all(), (ctx, k, g["lam"], r["lam"])
+        assert (ep <= 0).all(), (ctx, k, g["pen"], r["pen"])
+        worst_l = max(worst_l, float((np.abs(g["lam"] - r["lam"]) / (np.abs(r["lam"]) + 1.0)).max()))
+        worst_p = max(worst_p, float((np.abs(g["pen"] - r["pen"]) / np.abs(r["pen"])).max()))
+        for c in range(r["n"]):
+            n_contacts += 1
+            if g["stick"][c] == r["stick"][c]:
+                continue
+            n_stick_diff += 1
+            # manifold.cpp:213-241: lim = mu_eff * min(max(|lambda_n-| before, |(penalty C_n + lambda_n)-|), cap); the dual leaves
+            # lambda_n = that trial value, so the limit is recoverable from the oracle's rows before / after the pass
+            mu_eff = r["mu"] * (1.0 if q["stick"][c] else 0.9)
+            nmag = max(abs(min(float(q["lam"][c, 0]), 0.0)), abs(min(float(r["lam"][c, 0]), 0.0)))
+            lim = mu_eff * nmag
+            tl = float(np.hypot(q["lam"][c, 1], q["lam"][c, 2]))          # the tangential lambda the stick test saw (pre-dual, cone-clamped)
+            tl = min(tl, lim) if tl > lim else tl
+            if abs(tl - lim) > CONE_RTOL * max(lim, 1.0):
+                n_far += 1        # then it must be the OTHER rounding-decided test, slip^2 <= 0.02^2 (rare)
+    assert n_contacts > 0
+    assert n_far <= 1, (ctx, n_far, "stick flags differ away from the cone limit")
+    assert n_stick_diff <= max(2, n_contacts // 100), (ctx, n_stick_diff, n_contacts)
+    return n_contacts, worst_l, worst_p
+
+
+DUAL_CASES = [("Stack", 30, 3, False), ("Pyramid", 40, 2, False), ("Stress1000", 150, 3, False), ("Pyramid", 25, 2, True),
+              ("Stack", 12, 1, True)]
+
+
+@pytest.mark.parametrize("scene,warm,sweeps,post", DUAL_CASES)
+def test_dual_stage_matches_oracle_on_identical_inputs(avbd, scene, warm, sweeps, post):
+    """solver.cpp:411-430 + rowPenaltyGain :94-125 on the same poses and the same pre-dual rows."""
+    o, w = make_pair(avbd, scene=scene)
+    try:
+        p = o.params()
+        if post:
+            o.set_params(p["dt"], p["g"], p["iterations"], p["alpha"], p["beta"], p["gamma"], True)
+            w.set_params(p["dt"], p["g"], p["iterations"], p["alpha"], p["beta"], p["gamma"], True)
+        _advance(o, warm)
+        alpha = 1.0 if post else p["alpha"]          # solver.cpp:340-342
+        o.stage("broadphase"); o.stage("init"); o.stage("predict")
+        for it in range(sweeps - 1):
+            o.stage_primal(alpha); o.stage("dual", alpha)
+        o.stage_primal(alpha)
+        raw = o.manifolds_raw()
+        pre = manifold_dict(*raw)
+        w.set_state(o.state())
+        w.upload_manifolds(*raw)
+        assert_manifolds_equal(gpu_manifolds(w), pre, exact_rows=True, ctx=(scene, "upload round trip"))
+        w.stage("dual", alpha)
+        o.stage("dual", alpha)
+        n, wl, wp = _compare_dual(gpu_manifolds(w), pre, o.manifolds(), (scene, warm, sweeps, post))
+        changed = sum(int((o.manifolds()[k]["pen"] != pre[k]["pen"]).any()) for k in pre)
+        assert changed > 0, "vacuous: the dual pass changed no penalty"
+    finally:
+        o.close(); w.close()
+
+
+def test_dual_stage_random_tilted_pile(avbd):
+    rng = np.random.default_rng(23)
+    o, w = make_pair(avbd, bodies=random_pile(rng, 250, 2.5))
+    try:
+        _advance(o, 6)
+        alpha = _oracle_pre_dual(o, 2)
+        raw = o.manifolds_raw()
+        pre = manifold_dict(*raw)
+        w.set_state(o.state())
+        w.upload_manifolds(*raw)
+        w.stage("dual", alpha)
+        o.stage("dual", alpha)
+        n, wl, wp = _compare_dual(gpu_manifolds(w), pre, o.manifolds(), "pile")
+        assert n > 300
+    finally:
+        o.close(); w.close()
+
+
+# --------------------------------------------------------------------------- warm-start carry-over at step k > 0
+def _carry_over_case(avbd, o, w, ctx, tamper=None):
+    """Both sides hold the oracle's bodies and the oracle's (possibly tampered) manifold history; one collide stage each."""
+    raw = [a.copy() for a in o.manifolds_raw()]
+    if tamper:
+        tamper(raw)
+        o.set_manifolds(*raw)
+    w.set_state(o.state()); w.set_prev_linvel(o.prev_linvel())
+    w.upload_manifolds(*raw)
+    w.stage("collide")
+    o.stage("broadphase"); o.stage("init")
+    want, got = o.manifolds(), gpu_manifolds(w)
+    assert_manifolds_equal(got, want, exact_rows=True, ctx=ctx)
+    return manifold_dict(*raw), want
+
+
+@pytest.mark.parametrize("scene,steps", [("Stack", 7), ("Stack", 40), ("Pyramid", 30), ("Wall", 25), ("TwoBlockDrop", 45), ("Stress1000", 150)])
+def test_warm_start_carry_over_bit_exact_at_step_k(avbd, scene, steps):
+    """Manifold::initialize (manifold.cpp:71-175) + decay (solver.cpp:281-293) from the oracle's history at step k > 0:
+    membership, features, anchors (incl. re-used stick anchors), C0, lambda, penalty, stick — all bit for bit."""
+    o, w = make_pair(avbd, scene=scene)
+    try:
+        _advance(o, steps)
+        old, new = _carry_over_case(avbd, o, w, (scene, steps))
+        carried = sum(int((new[k]["lam"] != 0).any()) for k in new if k in old)
+        sticky = sum(int(new[k]["stick"].any()) for k in new)
+        assert carried > 0, "vacuous: nothing was carried over"
+        if scene in ("Stack", "Pyramid", "Wall") and steps >= 25:
+            assert sticky > 0, "vacuous: no stick anchor was re-used"
+    finally:
+        o.close(); w.close()
+
+
+def test_warm_start_carry_over_random_pile(avbd):
+    rng = np.random.default_rng(31)
+    o, w = make_pair(avbd, bodies=random_pile(rng, 300, 2.5))
+    try:
+        _advance(o, 5)
+        old, new = _carry_over_case(avbd, o, w, "pile")
+        assert len(new) > 200
+    finally:
+        o.close(); w.close()
+
+
+@pytest.mark.parametrize("variant", ["first_two_same_as_c1", "all_same_as_c0", "swap_lambda_dup"])
+def test_warm_start_tie_break_with_duplicate_feature_keys(avbd, variant):
+    """manifold.cpp:111-119: a new contact takes the FIRST UNUSED old contact with an equal feature key.  The old manifolds are
+    given duplicate keys (with distinguishable lambda / penalty per slot), so any other tie-break shows in the carried rows."""
+    o, w = make_pair(avbd, scene="Pyramid")
+    try:
+        _advance(o, 35)
+
+        def tamper(raw):
+            ints, feats, stick, flts = raw
+            hit = 0
+            for m in range(len(ints)):
+                n = int(ints[m, 2])
+                if n < 2:
+                    continue
+                hit += 1
+                lam = flts[m, 57:69].reshape(4, 3); pen = flts[m, 69:81].reshape(4, 3)
+                for c in range(n):      # make every slot's rows distinguishable
+                    lam[c] *= (1.0 + 0.125 * c); pen[c] = np.minimum(pen[c] * (1.0 + 0.25 * c), 2.0e6)
+                if variant == "first_two_same_as_c1":
+                    feats[m, 0] = feats[m, 1]
+                elif variant == "all_same_as_c0":
+                    feats[m, 1:n] = feats[m, 0]
+                else:
+                    feats[m, n - 1] = feats[m, 0]
+                    stick[m, :n] = 0      # anchors not re-used: only the row carry-over is at stake
+            assert hit > 20
+
+        _carry_over_case(avbd, o, w, ("dup", variant), tamper)
+    finally:
+        o.close(); w.close()
+
+
+# --------------------------------------------------------------------------- one world of a big ensemble vs the oracle
+@pytest.mark.parametrize("pick", [0, 4097, 8191])
+def test_ensemble_world_tracks_the_oracle(avbd, pick):
+    """BASELINE.json config 4: world `pick` of an 8192-world jittered Pyramid batch against the oracle on the same bodies.
+    Same tolerances as the single-world Pyramid test (rest heights 1e-3, counts +-2 manifolds / +-8 contacts, maxPen 1e-3)."""
+    from avbd_demo3d_b200 import scenes
+    base = scenes.scene("Pyramid")
+    nb = len(base["size"])
+    ens = scenes.ensemble(base, 8192)
+    w = avbd.World()
+    o = Oracle("port").create()
+    try:
+        scenes.load(w, ens)
+        sl = slice(pick * nb, (pick + 1) * nb)
+        for i in range(sl.start, sl.stop):
+            o.add_body(ens["size"][i], float(ens["density"][i]), float(ens["friction"][i]), ens["pos"][i], ens["quat"][i], ens["lin"][i], ens["ang"][i])
+        steps, tail = 400, 100
+        w.step(steps - tail); o.step(steps - tail)
+        ys, yo = [], []
+        for _ in range(tail):
+            w.step(1); o.step(1)
+            ys.append(w.state()[sl, 1].copy()); yo.append(o.state()[:, 1].copy())
+        y, yr = np.mean(ys, axis=0), np.mean(yo, axis=0)
+        assert np.abs(y - yr).max() < 1e-3, float(np.abs(y - yr).max())
+        d, do = w.world_diagnostics()[pick], o.diagnostics()
+        assert abs(d["activeManifolds"] - do["manifolds"]) <= 2 and abs(d["activeContacts"] - do["contacts"]) <= 8, (d, do)
+        assert d["maxPenetration"] <= 1e-3 and d["nanEvents"] == 0 and d["dynamicBodies"] == do["dynBodies"]
+    finally:
+        w.close(); o.close()
+
+
+def test_ensemble_world_first_steps_match_with_same_colour_order(avbd):
+    """A small batch, world 5: the oracle driven in the GPU's colour order tracks it to summation-order rounding."""
+    from avbd_demo3d_b200 import scenes
+    base = scenes.scene("Pyramid")
+    nb = len(base["size"])
+    ens = scenes.ensemble(base, 16)
+    w = avbd.World()
+    o = Oracle("port").create()
+    try:
+        scenes.load(w, ens)
+        pick = 5
+        sl = slice(pick * nb, (pick + 1) * nb)
+        for i in range(sl.start, sl.stop):
+            o.add_body(ens["size"][i], float(ens["density"][i]), float(ens["friction"][i]), ens["pos"][i], ens["quat"][i], ens["lin"][i], ens["ang"][i])
+        worst = 0.0
+        for s in range(6):
+            w.stage("collide"); w.stage("predict"); w.stage("colour")
+            col, k = w.colours()
+            mine = np.arange(sl.start, sl.stop)
+            dyn = mine[col[mine] >= 0]
+            order = (dyn[np.lexsort((dyn, col[dyn]))] - sl.start).astype(np.int32)
+            p = o.params()
+            for it in range(p["iterations"]):
+                w.stage_primal(p["alpha"]); w.stage("dual", p["alpha"])
+            w.stage("velocity")
+            o.step_ordered(order)
+            worst = max(worst, float(np.abs(o.state()[:, :7] - w.state()[sl, :7]).max()))
+        assert worst <= 5e-4, worst
+    finally:
+        w.close(); o.close()
+
+
+# --------------------------------------------------------------------------- snapshot / restore
+@pytest.mark.parametrize("scene,steps", [("Pyramid", 60), ("Stress1000", 160)])
+def test_snapshot_restore_resumes_bit_identically(avbd, scene, steps):
+    from avbd_demo3d_b200 import scenes
+    w = avbd.World()
+    w2 = avbd.World()
+    try:
+        scenes.load(w, scenes.scene(scene))
+        w.step(steps)
+        blob = w.snapshot()
+        w.step(40)
+        a, ma = w.state(), w.manifolds_raw()
+        # into a FRESH world (nothing but the blob), and back into the original
+        for tgt in (w2, w):
+            tgt.restore(blob)
+            assert tgt.n == len(a)
+            tgt.step(40)
+            b, mb = tgt.state(), tgt.manifolds_raw()
+            assert a.tobytes() == b.tobytes()
+            for x, y in zip(ma, mb):
+                assert x.tobytes() == y.tobytes()
+    finally:
+        w.close(); w2.close()
+
+
+def test_snapshot_restore_keeps_user_force_rows(avbd):
+    from test_gpu_scenes import _jointed
+    w = avbd.World()
+    w2 = avbd.World()
+    try:
+        _jointed(w)
+        w.step(50)
+        blob = w.snapshot()
+        rows = w.force_rows(0, 0)
+        w.step(30)
+        a = w.state()
+        w2.restore(blob)
+        assert w2.force_rows(0, 0)["lam"].tobytes() == rows["lam"].tobytes()
+        assert w2.force_rows(0, 0)["pen"].tobytes() == rows["pen"].tobytes()
+        w2.step(30)
+        assert a.tobytes() == w2.state().tobytes()
+        ints, _, _, _ = w2.manifolds_raw()
+        assert (5, 4) not in {(int(x), int(y)) for x, y, _ in ints}          # the IgnoreCollision pair survived the restore
+    finally:
+        w.close(); w2.close()
+
+
+# --------------------------------------------------------------------------- host-edited Force rows (solver.h:91-97)
+def test_motor_row_enters_the_primal(avbd):
+    """solver.cpp:380: desired = penalty * C + lambda + motor.  On a SOFT vertical row (stiffness k, no dual update) of a
+    body-world weld the body hangs where k C + motor = m g, i.e. C = (m g - motor) / k below the anchor."""
+    w = avbd.World()
+    try:
+        w.add_body((20, 1, 20), 0.0, 0.5, (0, -0.5, 0))
+        w.add_body((1, 1, 1), 1.0, 0.5, (0, 3, 0))
+        j = w.add_joint(-1, 1, (0, 3, 0))
+        hard = 3.4028234663852886e38
+        w.set_force_rows(0, j, stiffness=[hard, 500.0, hard, hard, hard, hard], motor=[0, 5.0, 0, 0, 0, 0])
+        assert w.force_rows(0, j)["motor"][1] == 5.0
+        w.step(240)
+        assert abs((3.0 - float(w.state()[1, 1])) - (10.0 - 5.0) / 500.0) < 3e-3, w.state()[1, 1]
+        w.set_force_rows(0, j, motor=[0, -5.0, 0, 0, 0, 0])
+        w.step(240)
+        assert abs((3.0 - float(w.state()[1, 1])) - (10.0 + 5.0) / 500.0) < 3e-3, w.state()[1, 1]
+    finally:
+        w.close()
+
+
+def test_stiffness_edit_switches_row_to_soft(avbd):
+    """solver.cpp:290-292, :378, :416-418: a finite stiffness caps the penalty and stops the dual update of that row."""
+    w = avbd.World()
+    try:
+        w.add_body((20, 1, 20), 0.0, 0.5, (0, -0.5, 0))
+        w.add_body((1, 1, 1), 1.0, 0.5, (0, 3, 0))
+        j = w.add_joint(-1, 1, (0, 3, 0))
+        w.set_force_rows(0, j, stiffness=[3.4028234663852886e38, 500.0, 3.4028234663852886e38] + [3.4028234663852886e38] * 3)
+        w.step(200)
+        st = w.state()
+        rows = w.force_rows(0, j)
+        assert rows["pen"][1] <= 500.0 and rows["lam"][1] == 0.0           # soft row: penalty capped, lambda never updated
+        assert abs((3.0 - float(st[1, 1])) - 10.0 / 500.0) < 4e-3, st[1, 1]  # hangs at m g / k below the anchor
+    finally:
+        w.close()
