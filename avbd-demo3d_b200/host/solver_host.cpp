@@ -69,6 +69,9 @@ Rigid::~Rigid() {
     while (*p != this) p = &(*p)->next;
     *p = next;
     if (!g_clearing) {           // a single body removed: the device world is re-created at the next step (manifolds of the others are kept)
+        // what is attached to the body goes with it: its Manifold mirrors, and user forces that would otherwise point at freed
+        // memory (upstream leaves them dangling, force.cpp:43-69 would then walk a dead list)
+        while (forces) delete forces;
         if (deviceIndex >= 0 && deviceIndex < (int)solver->deviceOrder.size()) solver->deviceOrder[deviceIndex] = nullptr;
         solver->order.erase(std::find(solver->order.begin(), solver->order.end(), this));
         for (size_t i = 0; i < solver->order.size(); ++i) solver->order[i]->index = (int)i;

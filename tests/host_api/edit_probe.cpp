@@ -12,15 +12,12 @@
 #include "spring.h"
 #include "scenes.h"
 
-static float maxPenaltyOf(Solver* s, Rigid* a, Rigid* b) {
-    s->refreshManifolds();
+static Force* mirrorOf(Solver* s, Rigid* a, Rigid* b) {
     for (Force* f = s->forces; f; f = f->next)
-        if (f->isManifold() && ((f->bodyA == a && f->bodyB == b) || (f->bodyA == b && f->bodyB == a))) {
-            float m = 0; for (int r = 0; r < f->getRowCount(); ++r) m = std::fmax(m, f->penalty[r]);
-            return m;
-        }
-    return -1.0f;
+        if (f->isManifold() && ((f->bodyA == a && f->bodyB == b) || (f->bodyA == b && f->bodyB == a))) return f;
+    return nullptr;
 }
+static int mirrorCount(Solver* s) { int n = 0; for (Force* f = s->forces; f; f = f->next) n += f->isManifold() ? 1 : 0; return n; }
 
 int main() {
     Solver* solver = new Solver();
@@ -30,14 +27,18 @@ int main() {
     Rigid* top = solver->bodies;                       // newest = top of the stack
     Rigid* bottom = nullptr; Rigid* ground = nullptr;
     for (Rigid* r = solver->bodies; r; r = r->next) { if (r->next && !r->next->next) bottom = r; if (!r->next) ground = r; }
-    float before = maxPenaltyOf(solver, bottom, ground);
-    int manifoldsBefore = solver->lastDiagnostics.activeManifolds;
+    solver->refreshManifolds();
+    int mirrorsBefore = mirrorCount(solver);
+    float lamBefore[12], penBefore[12];
+    { Force* f = mirrorOf(solver, bottom, ground); std::memcpy(lamBefore, f->lambda, sizeof(lamBefore)); std::memcpy(penBefore, f->penalty, sizeof(penBefore)); }
     long long up0 = solver->uploadedBytes;
     delete top;
+    solver->syncToDevice();                            // the device world is re-created here; nothing has stepped yet
+    solver->refreshManifolds();
+    Force* kept = mirrorOf(solver, bottom, ground);
+    int rowsSame = kept && !std::memcmp(lamBefore, kept->lambda, sizeof(lamBefore)) && !std::memcmp(penBefore, kept->penalty, sizeof(penBefore));
+    printf("delete_body mirrors %d %d rows_identical %d lambda_n %.6g bodies %d\n", mirrorsBefore, mirrorCount(solver), rowsSame, lamBefore[0], (int)solver->order.size());
     solver->step();
-    float after = maxPenaltyOf(solver, bottom, ground);
-    printf("delete_body manifolds %d %d penalty_before %.6g penalty_after %.6g bodies %d\n", manifoldsBefore, solver->lastDiagnostics.activeManifolds, before, after,
-           (int)solver->order.size());
     float worst = 0;
     for (int i = 0; i < 30; ++i) { solver->step(); worst = std::fmax(worst, solver->lastDiagnostics.maxLinearSpeed); }
     printf("delete_body settle_max_lin %.6g rebuild_upload_bytes %lld\n", worst, solver->uploadedBytes - up0);

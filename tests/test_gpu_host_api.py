@@ -88,12 +88,12 @@ def test_host_mirror_edits_deletes_and_snapshots():
         key, *vals = line.split()
         rows.setdefault(key, []).append(vals)
     d = rows["delete_body"][0]
-    assert int(d[1]) == 10 and int(d[2]) == 9 and int(d[8]) == 10, d               # 11 bodies -> 10; the top manifold went with its body
-    before, after = float(d[4]), float(d[6])
-    assert before > 3.0e4, before                                                  # the ramp had raised it well above PENALTY_MIN
-    assert after >= 0.97 * before, (before, after)                                 # kept (one step's gamma decay), not restarted at 2e4
+    # 11 bodies -> 10; the top manifold went with its body; the others reached the re-created device world with their rows intact
+    # (checked BEFORE any step: a dropped history would show as 0 manifolds on the device)
+    assert int(d[1]) == 10 and int(d[2]) == 9 and int(d[4]) == 1 and int(d[8]) == 10, d
+    assert float(d[6]) < -5.0, d                                                   # the bottom contact really carried load
     s = rows["delete_body"][1]
-    assert float(s[1]) < 0.2, s                                                    # the stack did not re-settle
+    assert float(s[1]) < 0.5, s                                                    # the stack did not re-settle
     assert int(rows["edit_one_body"][0][1]) == 52 and int(rows["edit_nothing"][0][1]) == 0
     soft = rows["soft_row"][0]
     assert abs(float(soft[1]) - 10.0 / 400.0) < 3e-3 and float(soft[3]) <= 400.0 and float(soft[5]) == 0.0, soft
@@ -109,7 +109,7 @@ def test_host_cli_binary_dump_and_snapshot(tmp_path):
     import numpy as np
     full, part, rest, snap = (str(tmp_path / n) for n in ("full.trj", "part.trj", "rest.trj", "state.snp"))
     run = lambda *a: subprocess.run([CLI, "--nogfx", "--scene", "Pyramid"] + list(a), capture_output=True, text=True, check=True, timeout=300).stdout
-    text = run("--steps", "30").splitlines()
+    text = [l for l in run("--steps", "30").splitlines() if not l.startswith("[Physics]")]
     run("--steps", "30", "--dump-binary", full)
 
     def load(path):
