@@ -91,8 +91,8 @@ struct avbd_world {
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<int> candCode, candCodeSorted;
-    DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;
-    DevBuf<float4> vgA, vgB, vgN; bool visitGeomStale = true;      // contact geometry in visit order (VisitGeom)
+    DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;      // per-contact visit lists: small worlds (cluster loop) only
+    DevBuf<int> deg, estart, colCursor; DevBuf<int4> entries;      // body -> manifold entries CSR (graph stage): colouring adjacency + the large-world sweep's work list
     DevBuf<float4> stA, stB, stN; DevBuf<ContactLP> stLP;      // np_build staging (4 slots per manifold), packed by np_compact
 
     // manifolds (ping-pong)
@@ -102,7 +102,7 @@ struct avbd_world {
     // graph
     DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
-    int2 hColRange[64]; int2 hColVisit[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
+    int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
     long long graphReuses = 0; int persistentMaxBodies = 4096;
 
     // user forces
@@ -113,9 +113,7 @@ struct avbd_world {
     // counters / diagnostics
     Counters* dCnt = nullptr; Counters* hCnt = nullptr;
     DevBuf<Diag> dDiag; Diag* hDiag = nullptr; size_t hDiagCap = 0;
-    DevBuf<float> dx, sums, carry; DevBuf<int2> colVisit; DevBuf<int> kOf, flatRange;      // flatRange: per colour, the flat sweep's block boundaries
-    int flatGrid[64] = {0}, flatRangeOff[64] = {0};
-    bool flatAligned = false;          // several worlds in the batch: body-aligned block ranges (sums independent of the batch)     // kOf[body] = position in colOrder
+    DevBuf<float> dx;
     DevBuf<char> temp;
 
     // per-kernel profiling (avbd_set_profiling): events around every primal sweep and dual pass
@@ -141,7 +139,6 @@ struct avbd_world {
         TRY(b.lp.ensure(4 * m, false, stream));
         return 0;
     }
-    VisitGeom vgeom() { VisitGeom g; g.a = vgA.p; g.b = vgB.p; g.n = vgN.p; return g; }
     ContactStage stage() { ContactStage c; c.cA = stA.p; c.cB = stB.p; c.cN = stN.p; c.lp = stLP.p; return c; }
     int ensure_stage(size_t m) {
         TRY(stA.ensure(4 * m, false, stream)); TRY(stB.ensure(4 * m, false, stream)); TRY(stN.ensure(4 * m, false, stream));
@@ -424,7 +421,6 @@ int run_collide(avbd_world* w) {
         w->launches++;
     }
     w->graphValid = sameTopology;
-    w->visitGeomStale = true;         // every contact was rebuilt
     if (w->timed || w->profiling) cudaEventRecord(w->ev[2], s);
     CK(cudaGetLastError());
     return 0;
@@ -456,16 +452,24 @@ int run_colour(avbd_world* w) {
     } else {
         TRY(w->bList.ensure(1, false, s));
     }
+    // body -> manifold entries (CSR by body): the colouring's adjacency and the large-world sweep's work list
+    TRY(w->deg.ensure((size_t)n + 1, false, s)); TRY(w->estart.ensure((size_t)n + 1, false, s));
+    TRY(w->entries.ensure((size_t)std::max(1, 2 * nM), false, s));
+    CK(cudaMemsetAsync(w->deg.p, 0, sizeof(int) * ((size_t)n + 1), s));
+    launch_dep(entry_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->deg.p);
+    TRY(exclusive_scan(w, w->deg.p, w->estart.p, n + 1));
+    launch_dep(entry_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->estart.p, w->entries.p);
+    w->launches += 2;
     ForceView fv = w->fview();
     // Opt-in (AVBD_INCREMENTAL_COLOUR=1): keep last step's colouring of the same body set and uncolour only what new manifolds put
-    // in conflict.  The graph stage gets a third cheaper (1M-box grid 0.85 -> 0.56 ms) but the colouring drifts to more, evenly
-    // filled colours (9 against 7; Stress1000 7 against 5), and every colour is a dependent phase of each sweep: measured a net
-    // loss (Stress1000 per-colour path 633 -> 535 steps/s, 1M-box grid 8.72 -> 8.77 ms), so colouring from scratch stays the default.
+    // in conflict.  The graph stage gets cheaper but the colouring drifts to more, evenly filled colours (9 against 7 on the 1M-box
+    // grid; Stress1000 7 against 5), and every colour is a dependent phase of each sweep: measured a net loss, so colouring from
+    // scratch — a pure function of the current graph — stays the default.
     bool incremental = w->incrementalColour && w->colouredBodies == n && !w->forceRegraph;
     if (incremental) {
         TRY(w->colourNext.ensure(n, false, s));
         CK(cudaMemcpyAsync(w->colourNext.p, w->colour.p, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));     // static bodies keep -2
-        launch_dep(colour_conflicts, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p,
+        launch_dep(colour_conflicts, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colour.p,
                                                                   w->colourNext.p);
         std::swap(w->colour.p, w->colourNext.p); std::swap(w->colour.cap, w->colourNext.cap);
     } else {
@@ -473,21 +477,43 @@ int run_colour(avbd_world* w) {
     }
     w->launches++;
     w->colouredBodies = -1;
-    // Jones-Plassmann rounds, launched in batches: a round is a no-op for bodies already coloured, so running a few
-    // rounds too many costs microseconds while every host check of the uncoloured count costs a round trip.  Only the
-    // last round of a batch counts the bodies it left uncoloured; when that is under half of the current work list the
-    // stragglers are compacted into a new list, so late rounds do not sweep a million coloured bodies to find a few thousand.
+    // Jones-Plassmann rounds (= the sequential greedy colouring in hashed-priority order, whatever the timing), all in ONE launch:
+    // one block for small worlds, a cooperative grid with a grid barrier per round otherwise — no host check of the uncoloured count
+    // between rounds.  If the cooperative launch is refused, rounds are launched in batches with a host check per batch.
+    bool coloured = false;
     if (w->nDyn <= kColourBlockMaxBodies) {
-        // small world: every round in one block, no launches or host checks in between (the count is read with the colour ranges below)
-        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p, w->dCnt);
+        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colour.p, w->dCnt);
         w->launches++;
+        coloured = true;
     } else {
+        static int residentDev[64] = {0};
+        int& resident = residentDev[w->device & 63];
+        if (!resident) {
+            int per = 0, sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, colour_rounds_grid, kColourGridThreads, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 0; }
+            int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, w->device);
+            resident = (coop && per > 0) ? sms * per : -1;
+        }
+        if (resident > 0 && !getenv("AVBD_NO_COOP_COLOUR")) {
+            TRY(w->colWorkA.ensure((size_t)w->nDyn, false, s)); TRY(w->colWorkB.ensure((size_t)w->nDyn, false, s)); TRY(w->colCursor.ensure(4, false, s));
+            CK(cudaMemsetAsync(w->colCursor.p, 0, 4 * sizeof(int), s));
+            const int* dynList = w->dynList.p; int nDyn = w->nDyn; const int* estart = w->estart.p; const int4* entries = w->entries.p;
+            const int* localIdx = w->localIdx.p; volatile int* colour = w->colour.p; Counters* cnt = w->dCnt;
+            int* listA = w->colWorkA.p; int* listB = w->colWorkB.p; int* cursors = w->colCursor.p;
+            void* args[] = {&dynList, &nDyn, &estart, &entries, &fv, &localIdx, &colour, &cnt, &listA, &listB, &cursors};
+            int grid = std::min(resident, blocks_for(w->nDyn, kColourGridThreads));
+            cudaError_t e = cudaLaunchCooperativeKernel((void*)colour_rounds_grid, dim3(grid), dim3(kColourGridThreads), args, 0, s);
+            if (e == cudaSuccess) { w->launches++; coloured = true; } else { cudaGetLastError(); resident = -1; }
+        }
+    }
+    if (!coloured) {
         const int* list = w->dynList.p; int listCount = w->nDyn; int which = 0;
         for (int round = 0, batch = incremental ? 2 : 6;;) {
             if (round > 4096) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
             CK(cudaMemsetAsync(&w->dCnt->nUncoloured, 0, sizeof(int), s));
             for (int k = 0; k < batch; ++k)
-                launch_dep(colour_round, dim3(blocks_for(listCount)), dim3(kThreads), 0, s, list, listCount, w->adjRange.p, w->bList.p, ms.hdr, fv, w->localIdx.p, w->colour.p,
+                launch_dep(colour_round, dim3(blocks_for(listCount)), dim3(kThreads), 0, s, list, listCount, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colour.p,
                                                                         w->dCnt, k == batch - 1);
             w->launches += batch; round += batch;
             TRY(read_counters(w));
@@ -505,52 +531,29 @@ int run_colour(avbd_world* w) {
         }
     }
     w->colouredBodies = n;
-    launch_dep(colour_keys, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);
+    launch_dep(colour_keys, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p, w->estart.p, w->entries.p);
     TRY(sort_pairs(w, w->colKey.p, w->colKeySorted.p, w->colVal.p, w->colOrder.p, w->nDyn, 7));
     CK(cudaMemsetAsync(w->colRange.p, 0, sizeof(int2) * 64, s));
     launch_dep(colour_bounds, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);
     w->launches += 2;
-    // contact visits in colour order (the primal's work list): visitStart[k] belongs to colOrder[k]
-    TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
-    TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
-    w->visitGeomStale = true;
-    CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
-    launch_dep(visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
-    TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
-    launch_dep(visit_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
-    w->launches += 2;
-    // first / last visit of every colour (the flat primal partitions a colour's visits, not its bodies)
-    TRY(w->colVisit.ensure(64, false, s)); TRY(w->kOf.ensure(n, false, s));
-    launch_dep(colour_visit_bounds, dim3(1), dim3(64), 0, s, w->colRange.p, w->dCnt, w->visitStart.p, w->colVisit.p);
-    launch_dep(invert_order, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->kOf.p);
-    w->launches += 2;
-    // ONE host round trip for everything the launches of the sweeps need: colour ranges, their visit ranges, counters
+    if (w->nDyn <= w->persistentMaxBodies) {
+        // small worlds: per-contact visits in colour order, the cluster loop's work list (visitStart[k] belongs to colOrder[k])
+        TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
+        TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
+        CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
+        launch_dep(visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
+        TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
+        launch_dep(visit_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
+        w->launches += 2;
+    }
+    // ONE host round trip for everything the launches of the sweeps need: colour ranges, counters
     CK(cudaMemcpyAsync(w->hColRange, w->colRange.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(w->hColVisit, w->colVisit.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
     TRY(read_counters(w));
     if (w->hCnt->nUncoloured != 0) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
     if (w->hCnt->overflow & 4) return fail(AVBD_ERR_CAPACITY, "more than 64 colours needed");
     w->nColours = w->hCnt->nColours;
     w->maxColourCount = 0;
     for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);
-    // the flat sweep's grids; for a batch of several worlds also its body-aligned block ranges (device only: nothing below waits)
-    {
-        w->flatAligned = w->nWorlds > 1;
-        int total = 0;
-        for (int c = 0; c < w->nColours; ++c) {
-            w->flatGrid[c] = primal_flat_grid(w->hColVisit[c].y - w->hColVisit[c].x);
-            w->flatRangeOff[c] = total; total += w->flatGrid[c] + 1;
-        }
-        if (w->flatAligned) {
-            TRY(w->flatRange.ensure((size_t)std::max(1, total), false, s));
-            for (int c = 0; c < w->nColours; ++c) {
-                int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
-                if (count <= 0 || w->flatGrid[c] <= 0) continue;
-                launch_flat_ranges(s, w->visitStart.p, first, count, w->hColVisit[c].x, w->hColVisit[c].y, w->flatGrid[c], w->flatRange.p + w->flatRangeOff[c]);
-                w->launches++;
-            }
-        }
-    }
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;
@@ -565,21 +568,11 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float biasDual = -1.0f)
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
-    TRY(w->sums.ensure((size_t)std::max(1, w->nDyn) * 28, false, s));
-    if (!w->flatAligned) TRY(w->carry.ensure(((size_t)std::max(1, 2 * w->nContacts) / primal_flat_chunk_threads() + 2) * 28, false, s));
-    if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
-        size_t cap = w->visits.cap;
-        TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));
-        launch_dep(visit_geometry, dim3(blocks_for(2ll * w->nContacts)), dim3(kThreads), 0, s, w->visits.p, w->visitStart.p + w->nDyn, ms, w->vgeom());
-        w->launches++;
-    }
-    w->visitGeomStale = false;
     for (int c = 0; c < w->nColours; ++c) {
         int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
         if (count <= 0) continue;
-        w->launches += launch_primal_flat(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->colOrder.p, w->visitStart.p, w->kOf.p, first, count,
-                                          w->hColVisit[c].x, w->hColVisit[c].y, w->flatGrid[c], w->flatAligned ? w->flatRange.p + w->flatRangeOff[c] : nullptr,
-                                          w->prm, alpha, biasDual, w->sums.p, w->carry.p, dxDev, w->dDiag.p);
+        launch_primal_bodies(s, w->bview(), w->colOrder.p + first, count, w->estart.p, w->entries.p, ms, fv, w->prm, alpha, biasDual, dxDev, w->dDiag.p);
+        w->launches++;
     }
     CK(cudaGetLastError());
     return 0;
@@ -759,8 +752,8 @@ void avbd_world_destroy(avbd_world* w) {
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
-    w->dDiag.release(); w->dx.release(); w->sums.release(); w->carry.release(); w->colVisit.release(); w->kOf.release(); w->flatRange.release(); w->temp.release(); w->stateDev.release();
-    w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stLP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
+    w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release(); w->deg.release(); w->estart.release(); w->colCursor.release(); w->entries.release();
+    w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stLP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
     if (w->hCnt) cudaFreeHost(w->hCnt);
@@ -1046,7 +1039,7 @@ int avbd_upload_manifolds(avbd_world* w, int count, const int* ints, const int* 
         CK(cudaMemcpyAsync(ms.lp, lp.data(), nC * sizeof(ContactLP), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
     }
-    w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false;
+    w->graphValid = false; w->contactDiagDone = false;
     return 0;
 }
 
@@ -1142,7 +1135,7 @@ int avbd_restore(avbd_world* w, const void* buf, long long bytes) {
         TRY(get_dev(ms.cN, c * sizeof(float4))); TRY(get_dev(ms.lp, c * sizeof(ContactLP)));
     }
     CK(cudaStreamSynchronize(s));
-    w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false; w->lastPairs = 0;
+    w->graphValid = false; w->contactDiagDone = false; w->lastPairs = 0;
     return 0;
 }
 

@@ -31,6 +31,36 @@ __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, in
     if (t == nM - 1 || bKeySorted[t + 1] != k) adjRange[k].w = t + 1;
 }
 
+// ------------------------------------------------------------------ body -> manifold entries (CSR)
+// One entry per LIVE manifold touching a dynamic body, in pair-key order (the body's "I am A" run, then its "I am B" run):
+//   {other body, first dense contact, contact count | body-is-A << 3 | first-visit << 4, friction bits}
+// estart is indexed by BODY (n + 1 entries, static bodies own none).  The colouring walks it as the adjacency list, the large-world
+// primal sweep as its work list (avbd_solve.cu: primal_colour_bodies).  first-visit (set by colour_keys once colours exist): of a
+// contact's two visits per sweep this one comes first (the other endpoint is static or has a higher colour) — it applies the
+// previous iteration's deferred dual update.
+__global__ void entry_count(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* deg) {
+    cudaGridDependencySynchronize();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    int i = dynList[t];
+    int4 rg = adjRange[i];
+    int k = 0;
+    for (int m = rg.x; m < rg.y; ++m) k += hdr[m].z > 0 ? 1 : 0;
+    for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z > 0 ? 1 : 0;
+    deg[i] = k;
+}
+__global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
+                           const int* estart, int4* entries) {
+    cudaGridDependencySynchronize();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    int i = dynList[t];
+    int4 rg = adjRange[i];
+    int o = estart[i];
+    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; if (h.z > 0) entries[o++] = make_int4(h.y, cstart[m], h.z | 8, h.w); }
+    for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; if (h.z > 0) entries[o++] = make_int4(h.x, cstart[m], h.z, h.w); }
+}
+
 // ------------------------------------------------------------------ contact-visit lists
 // Contacts are stored densely (np_compact), so the dual walks them by index; the primal walks, per dynamic body, a run
 // of `visits` — one entry per live contact of every manifold touching the body, rebuilt whenever the topology changes.
@@ -72,21 +102,6 @@ __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, 
     }
 }
 
-// Once per step (the narrowphase rewrites every contact): copy each visit's contact geometry into visit order, so the
-// iterations x colours primal sweeps stream it instead of gathering it — already in the VISITING body's frame:
-// a = {r_self, C0n}, b = {r_other, C0t.x}, n = {n, C0t.y}.  nVisits lives on the device (visitStart[nDyn]).
-__global__ void visit_geometry(const int4* __restrict__ visits, const int* __restrict__ nVisits, ManifoldSet ms, VisitGeom vg) {
-    cudaGridDependencySynchronize();
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= *nVisits) return;
-    int4 e = visits[v];
-    float4 a = ms.cA[e.x], b = ms.cB[e.x];
-    bool isA = (e.z & 1) != 0;
-    vg.a[v] = isA ? a : make_float4(b.x, b.y, b.z, a.w);
-    vg.b[v] = isA ? b : make_float4(a.x, a.y, a.z, b.w);
-    vg.n[v] = ms.cN[e.x];
-}
-
 // ------------------------------------------------------------------ colouring
 __device__ __forceinline__ unsigned mix32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
@@ -109,21 +124,19 @@ __global__ void colour_init(const int* flags, int n, int* colour) {
 // coloured is exactly its higher-priority neighbourhood whenever it succeeds: the result is the sequential greedy
 // colouring in priority order, independent of timing (timing only changes how many attempts it takes).
 // Returns whether the body is coloured after the attempt.
-__device__ __forceinline__ bool try_colour(int i, const int4* adjRange, const int* bList, const int4* hdr, const ForceView& fv,
+__device__ __forceinline__ bool try_colour(int i, const int* estart, const int4* entries, const ForceView& fv,
                                            const int* localIdx, volatile int* colour, Counters* cnt) {
     if (colour[i] >= 0) return true;
     int li = localIdx[i];
     unsigned long long used = 0ull;
     bool ready = true;
-    int4 rg = adjRange[i];
     auto visit = [&](int other) {
         if (other < 0) return;
         int co = colour[other];
         if (co >= 0) used |= 1ull << co;
         else if (co == -1 && outranks(localIdx[other], li)) ready = false;
     };
-    for (int m = rg.x; m < rg.y && ready; ++m) visit(hdr[m].y);
-    for (int k = rg.z; k < rg.w && ready; ++k) visit(hdr[bList[k]].x);
+    for (int e = estart[i], e1 = estart[i + 1]; e < e1 && ready; ++e) visit(entries[e].x);
     if (fv.adjStart) {
         for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && ready; ++k) {
             int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
@@ -138,12 +151,12 @@ __device__ __forceinline__ bool try_colour(int i, const int4* adjRange, const in
     return true;
 }
 
-__global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
+__global__ void colour_round(const int* dynList, int nDyn, const int* estart, const int4* entries,
                              ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt, bool countLeft) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
-    if (!try_colour(dynList[t], adjRange, bList, hdr, fv, localIdx, colour, cnt) && countLeft) {
+    if (!try_colour(dynList[t], estart, entries, fv, localIdx, colour, cnt) && countLeft) {
         cg::coalesced_group grp = cg::coalesced_threads();
         if (grp.thread_rank() == 0) atomicAdd(&cnt->nUncoloured, (int)grp.size());
     }
@@ -152,24 +165,60 @@ __global__ void colour_round(const int* dynList, int nDyn, const int4* adjRange,
 // Small worlds: ALL rounds in one block (block barrier between rounds instead of a launch, no host check of the
 // uncoloured count).  Same attempts, hence the same colouring as colour_round.
 constexpr int kColourBlockThreads = 1024;
-__global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
+__global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int* estart, const int4* entries,
                                                                            ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt) {
     cudaGridDependencySynchronize();
     int left = 1;
     for (int round = 0; round < 4096 && left; ++round) {
         int mine = 0;
         for (int t = threadIdx.x; t < nDyn; t += blockDim.x)
-            if (!try_colour(dynList[t], adjRange, bList, hdr, fv, localIdx, colour, cnt)) mine = 1;
+            if (!try_colour(dynList[t], estart, entries, fv, localIdx, colour, cnt)) mine = 1;
         left = __syncthreads_or(mine);           // also makes this round's colours visible to the whole block
     }
     if (threadIdx.x == 0) cnt->nUncoloured = left;
+}
+
+// Large worlds: ALL rounds in one cooperative launch (grid barrier between rounds, no host round trip to learn how many bodies are
+// left).  Each round walks a work list of the still uncoloured bodies and appends the ones it could not colour to the next list
+// (warp-aggregated; the list's order is irrelevant to the result).  Same attempts, same colouring as colour_round.  Cursors rotate
+// over three slots: the slot a round fills was last READ two barriers ago.
+constexpr int kColourGridThreads = 256;
+__global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const int* dynList, int nDyn, const int* estart, const int4* entries,
+                                                                         ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt,
+                                                                         int* listA, int* listB, int* cursors) {
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int* list = dynList; int count = nDyn;
+    int round = 0;
+    for (; round < 4096 && count > 0; ++round) {
+        int* out = (round & 1) ? listB : listA;
+        int* cur = cursors + round % 3;
+        if (gtid == 0) cursors[(round + 1) % 3] = 0;            // next round's cursor (last read after the barrier of round - 2)
+        const int rounded = (count + 31) & ~31;
+        for (int t = gtid; t < rounded; t += gsize) {
+            bool left = false; int i = 0;
+            if (t < count) { i = list[t]; left = !try_colour(i, estart, entries, fv, localIdx, colour, cnt); }
+            unsigned vote = __ballot_sync(0xffffffffu, left);
+            if (vote) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cur, __popc(vote));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (left) out[base + __popc(vote & ((1u << lane) - 1u))] = i;
+            }
+        }
+        grid.sync();
+        count = *(volatile int*)cur;
+        list = out;
+    }
+    if (gtid == 0) cnt->nUncoloured = count;
 }
 
 // Incremental recolouring: last step's colouring is still valid except where a NEW manifold joins two bodies of one colour.
 // Of such a pair the lower-priority body is uncoloured (reads the old colours, writes the new array: no race, no dependence on
 // timing) and the usual rounds then colour only those bodies — typically a few hundred of a million, in one or two rounds
 // instead of the ~17 a colouring from scratch needs.
-__global__ void colour_conflicts(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, ForceView fv,
+__global__ void colour_conflicts(const int* dynList, int nDyn, const int* estart, const int4* entries, ForceView fv,
                                  const int* localIdx, const int* colourPrev, int* colourOut) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,9 +231,7 @@ __global__ void colour_conflicts(const int* dynList, int nDyn, const int4* adjRa
         auto visit = [&](int other) {
             if (other >= 0 && colourPrev[other] == mine && outranks(localIdx[other], li)) clash = true;
         };
-        int4 rg = adjRange[i];
-        for (int m = rg.x; m < rg.y && !clash; ++m) visit(hdr[m].y);
-        for (int k = rg.z; k < rg.w && !clash; ++k) visit(hdr[bList[k]].x);
+        for (int e = estart[i], e1 = estart[i + 1]; e < e1 && !clash; ++e) visit(entries[e].x);
         if (fv.adjStart) {
             for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && !clash; ++k) {
                 int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
@@ -210,13 +257,20 @@ __global__ void colour_compact(const int* list, int n, const int* colour, int* o
     if (keep) out[base + __popc(vote & ((1u << lane) - 1u))] = i;
 }
 
-__global__ void colour_keys(const int* dynList, int nDyn, const int* colour, unsigned* key, int* val) {
+// Sort keys of the colour order, and — now that colours exist — the first-visit bit of the body's entries.
+__global__ void colour_keys(const int* dynList, int nDyn, const int* colour, unsigned* key, int* val, const int* estart, int4* entries) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = dynList[t];
-    key[t] = (unsigned)colour[i];
+    int mine = colour[i];
+    key[t] = (unsigned)mine;
     val[t] = i;
+    for (int e = estart[i], e1 = estart[i + 1]; e < e1; ++e) {
+        int co = colour[entries[e].x];
+        int z = entries[e].z & ~16;
+        entries[e].z = z | ((co < 0 || mine < co) ? 16 : 0);
+    }
 }
 // colourRange[c] = {first, last+1} in the colour-sorted body order; must be zeroed first.
 __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourRange, Counters* cnt) {
@@ -227,22 +281,6 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
     if (t == 0 || keySorted[t - 1] != c) colourRange[c].x = t;
     if (t == nDyn - 1 || keySorted[t + 1] != c) colourRange[c].y = t + 1;
     if (t == nDyn - 1) cnt->nColours = (int)c + 1;
-}
-
-// out[c] = {first visit, one past the last visit} of colour c (a colour's bodies, hence its visits, are contiguous); {0, 0} for
-// a colour incremental recolouring left empty.
-__global__ void colour_visit_bounds(const int2* colourRange, const Counters* cnt, const int* visitStart, int2* out) {
-    cudaGridDependencySynchronize();
-    int c = threadIdx.x;
-    if (c >= 64) return;
-    int2 r = c < cnt->nColours ? colourRange[c] : make_int2(0, 0);
-    out[c] = r.y > r.x ? make_int2(visitStart[r.x], visitStart[r.y]) : make_int2(0, 0);
-}
-
-__global__ void invert_order(const int* order, int n, int* positionOf) {
-    cudaGridDependencySynchronize();
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) positionOf[order[k]] = k;
 }
 
 // ------------------------------------------------------------------ predict / warm-start decay of user forces

@@ -21,11 +21,6 @@ struct ForceView {
     const int* adjStart; const int* adj;    // entry = index*4 + type*2 + isA ; type 0 joint, 1 spring
 };
 
-// Contact geometry in VISIT order (one float4 per field per visit, refreshed once per step by visit_geometry): the primal's
-// visit kernel streams it fully coalesced instead of gathering 3 x 16 B per visit by contact id, in the visiting body's
-// frame: {r_self,C0n} {r_other,C0t.x} {n,C0t.y}.
-struct VisitGeom { float4* a; float4* b; float4* n; };
-
 #ifdef __CUDACC__
 // Programmatic dependent launch.  A step is a chain of ~50 (Stress1000) to ~200 (1M boxes) small dependent kernels on one
 // stream; launched this way a kernel may become resident while its predecessor drains, and waits at the
@@ -120,19 +115,14 @@ __device__ __forceinline__ void reduce_contact_diag_block(int world, float sepn,
 constexpr int kThreads = 256;
 constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodies per CTA tile (9 lanes per body in the sum phase)
 
-// One colour of the large-world primal sweep (flat visit partition, avbd_solve.cu): bodies [first, first + count) of the
-// colour-ordered arrays `order` / `vstart` (kOf[body] = position in `order`), whose visits are [vBegin, vEnd).  `grid` =
-// primal_flat_grid(vEnd - vBegin).  `range` == nullptr: chunks round-robin over the blocks, `carry` takes 28 floats per chunk;
-// `range` != nullptr (batches of several worlds): the colour's grid + 1 body-aligned block boundaries (launch_flat_ranges, once
-// per graph build) — sums do not depend on the batch.  `sums` holds 28 floats per dynamic body (row = position in `order`).
-// biasDual >= 0: the previous iteration's dual pass (whose clamp(1 - alpha, 0, 1) it is; any alpha maps into [0, 1], so the sign is free to mean "none") is still pending and each contact's first visit applies
-// it (deferred dual); < 0: plain primal sweep.  Returns the kernels launched.
-int primal_flat_chunk_threads();
-int primal_flat_grid(int nVisits);
-void launch_flat_ranges(cudaStream_t s, const int* vstart, int first, int count, int vBegin, int vEnd, int grid, int* range);
-int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                       const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float biasDual,
-                       float* sums, float* carry, float* dxOut, Diag* diag);
+// The large-world sweep of one colour, one body per thread (avbd_solve.cu: primal_colour_bodies): `order` points at the colour's
+// bodies, estart / entries are the body -> manifold-entry CSR of the graph stage (entry = {other body, first contact, contact count
+// | side << 3 | first-visit << 4, friction bits}).
+// biasDual >= 0: the previous iteration's dual pass is still pending and each contact's first visit applies it (deferred dual); the
+// value is that pass's clamp(1 - alpha, 0, 1) (manifold.cpp:179), which lies in [0, 1] for every alpha, so a negative value can only
+// mean "nothing pending" (plain primal sweep).
+void launch_primal_bodies(cudaStream_t s, BodyView b, const int* order, int count, const int* estart, const int4* entries, ManifoldSet ms, ForceView fv,
+                          SolveParams prm, float alpha, float biasDual, float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live (densely stored) contacts.
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics
 // (solver.cpp:472-497) are reduced here from the values already in registers instead of by a separate sweep.

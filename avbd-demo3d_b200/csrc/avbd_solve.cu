@@ -4,7 +4,7 @@
 //
 // The reference walks bodies serially (Gauss-Seidel, solver.cpp:344); here bodies of one colour share no
 // manifold, so a colour is one parallel phase, one contact visit (computeConstraint + 3 rows) per thread:
-//   large worlds   per colour primal_visit_flat (flat visit partition -> per-body sums) + primal_solve_flat (block solve)
+//   large worlds   per colour primal_colour_bodies: one body per thread, row sums in registers, block solve in the same thread
 //   small worlds   solve_loop_cluster: the whole iteration loop in one thread-block cluster, a tile of bodies per CTA and phase
 //
 // Deferred dual.  The dual / penalty-ramp pass of iteration k (solver.cpp:411-430) reads the poses left by sweep k, and
@@ -149,8 +149,7 @@ __device__ __forceinline__ void dual_fast(ContactState& c, const ContactEval& e,
 // The 27 products per row are issued as packed pairs (Blackwell's fma.rn.f32x2 / mul.rn.f32x2: two IEEE FP32 operations per
 // issue slot, each lane rounded exactly like the scalar instruction) in the order of the shared-memory row the visit kernel
 // stores: rl0 rl1 | rl2 ra0 | ra1 ra2 | ll0 ll1 | ll2 ll3 | ll4 ll5 | la0 la1 | la2 la3 | la4 la5 | la6 la7 | la8 aa0 | aa1 aa2 | aa3 aa4 | aa5 -.
-__device__ __forceinline__ void system_fast(BodySystem& s, const ContactState& c, const ContactEval& e, V3 w, float sg, bool gyro, const M3& invIw) {
-    float2 v[14];
+__device__ __forceinline__ void system_pairs(float2 (&v)[14], const ContactState& c, const ContactEval& e, V3 w, float sg, bool gyro, const M3& invIw) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         V3 Jl = e.basis[r];
@@ -177,6 +176,10 @@ __device__ __forceinline__ void system_fast(BodySystem& s, const ContactState& c
             v[10].y += g.x * af; v[12].x += g.y * af; v[13].x += g.z * af;
         }
     }
+}
+__device__ __forceinline__ void system_fast(BodySystem& s, const ContactState& c, const ContactEval& e, V3 w, float sg, bool gyro, const M3& invIw) {
+    float2 v[14];
+    system_pairs(v, c, e, w, sg, gyro, invIw);
     s.rl[0] = v[0].x; s.rl[1] = v[0].y; s.rl[2] = v[1].x; s.ra[0] = v[1].y; s.ra[1] = v[2].x; s.ra[2] = v[2].y;
     s.ll[0] = v[3].x; s.ll[1] = v[3].y; s.ll[2] = v[4].x; s.ll[3] = v[4].y; s.ll[4] = v[5].x; s.ll[5] = v[5].y;
     s.la[0] = v[6].x; s.la[1] = v[6].y; s.la[2] = v[7].x; s.la[3] = v[7].y; s.la[4] = v[8].x; s.la[5] = v[8].y; s.la[6] = v[9].x; s.la[7] = v[9].y;
@@ -209,6 +212,19 @@ __device__ __forceinline__ void visit_rows(float4 sp, float4 sq, float4 op, floa
     system_fast(sys, cs, ev, ev.wrA, sg, gyro, invIw);
 }
 
+// The same visit, leaving the 27 numbers as the 14 packed pairs system_pairs produces (order of FlatRow / the shared-memory rows).
+__device__ __forceinline__ void visit_rows_pairs(float4 sp, float4 sq, float4 op, float4 oq, float sg, float mu, float alpha, bool pending, float biasDual,
+                                                 float beta, bool gyro, const M3& invIw, ContactState& cs, float2 (&v)[14]) {
+    ContactEval ev; float sep[3];
+    float cap = rows_geometry(sp, sq, op, oq, sg, cs, ev, sep);
+    if (pending) {
+        limits_fast(cap, mu, biasDual, sep, cs, ev);
+        dual_fast(cs, ev, beta);
+    }
+    limits_fast(cap, mu, fminf(fmaxf(1.0f - alpha, 0.0f), 1.0f), sep, cs, ev);
+    system_pairs(v, cs, ev, ev.wrA, sg, gyro, invIw);
+}
+
 // Loads of data another CTA may have written earlier in the SAME launch (persistent loop): bypass L1.
 template <bool COH> __device__ __forceinline__ float4 ld4(const float4* p) { return COH ? __ldcg(p) : *p; }
 template <bool COH> __device__ __forceinline__ BodyPose load_pose(const BodyPose* p) {
@@ -222,7 +238,7 @@ template <bool COH> __device__ __forceinline__ ContactState load_contact_c(const
 // The visit list is laid out in colour order, so the visits of a tile of BPB consecutive bodies of one colour are ONE
 // contiguous run.  The tile walks that run one visit per thread (every lane busy, every lane's gathers independent
 // and in flight together) and solves its bodies in the same call — small worlds are latency bound, a phase must not
-// be split over launches.  (Large worlds use the flat visit partition further down.)
+// be split over launches.  (Large worlds use one body per thread, further down.)
 //   phase 0  thread t < BPB stages body t of the tile in shared memory (pose, inertial target, mass, inverse inertia)
 //   phase 1  thread t takes visit base+t: computeConstraint + 3 rows -> its 27 partial sums, parked transposed in
 //            shared memory (row stride 257: conflict free)
@@ -395,223 +411,87 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
     }
 }
 
-constexpr int kSumStride = 28;
-
-// ------------------------------------------------------------------ primal, flat visit partition (the default large-world path)
-// Giving each block a tile of BODIES makes it load where its visits start (one DRAM round trip), then the visit entries (a
-// second), then what they point at (a third), and leaves ~4 % of the lanes idle because a tile's visits rarely fill the block.
-// This kernel partitions the colour's VISITS instead: chunk c is visits [vBegin + c*T, vBegin + (c+1)*T), every lane busy,
-// start known from the block index.  Blocks are persistent (grid = a few per SM, chunks round-robin) and load the NEXT chunk's
-// visit entry before working on the current one, so only the gathers (poses, lambda / penalty) remain on the critical path.
-//   phase 0  segment heads: lane v starts a segment when visit v-1 belongs to another body (entries carry the visiting body);
-//            ballot -> each warp's compact list of the segments that start in its 32 visits (no barrier)
-//   phase 1  thread t takes visit base+t: computeConstraint (+ pending dual) + 3 rows -> 27 partial sums, one 112-byte row of
-//            shared memory per visit (7 x STS.128)
-//   ---- the chunk's only block barrier (rows and segment lists are double buffered) ----
-//   phase 2  7 lanes per segment add the segment's run of rows in visit order, one float4 column each (LDS.128, 4 in flight);
-//            a warp sums the segments that start in its visits
-//   output   a segment that STARTS in the chunk writes sums[k], k = the body's position in the colour order; a segment continuing from the previous chunk (a body whose
-//            visits straddle a chunk boundary) writes carry[chunk] instead, and primal_solve_flat adds main + carries in
-//            chunk order — deterministic, no atomics, nothing to zero.
-constexpr int kFlatLanes = 7;                 // lanes per segment in phase 2 (one float4 = 4 of the 27(+1) components each)
-template <int T>
-struct FlatSmem {
-    float4 c[2][T][7];   // one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad — 128-bit stores / loads, row stride 28 words: conflict free
-    float4 stage[9][T];  // the NEXT chunk's gathered operands, filled by cp.async: self pose (2), other pose (2), geometry (3), lambda, penalty
-    unsigned char segPos[2][T / 32][32];     // per warp: chunk-local positions (< T <= 256) of the segment heads among its 32 visits
-    int segK[2][T / 32][32];       // ... and each segment's row of `sums` (complemented: it continues the previous chunk's last segment)
-    unsigned headMask[2][T / 32];
-    float4 carry[2][8];            // partial sum of the body whose run crosses into the next chunk (by chunk parity)
-    int nextK[2];                  // row of the body the next chunk starts with (-1: this is the block's last chunk)
-};
-
-// cp.async (LDGSTS) of one 16-byte item into this thread's slot of the gather stage, with an L2 eviction policy.
-__device__ __forceinline__ void stage16(float4* dst, const float4* src, unsigned long long policy) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void stage16_nol1(float4* dst, const float4* src, unsigned long long policy) {      // bypasses L1 (streamed / single-use data)
-    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "l"(policy) : "memory");
-}
-__device__ __forceinline__ unsigned long long l2_stream_policy() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
+// ------------------------------------------------------------------ primal, one body per thread (the large-world path)
+// A colour's bodies share no manifold, so each thread owns ONE body for the whole phase: it walks the body's manifold entries
+// (graph stage: {other body, first contact, contact count | side | first-visit, friction}, in pair-key order), evaluates every
+// contact's computeConstraint + 3 rows, keeps the 27 row sums in registers (14 packed pairs, added in visit order — the same
+// sequence of additions the cluster loop performs through shared memory, so a world's sums do not depend on which path its batch
+// takes), then adds the inertial terms, solves the 6x6 system and moves the body — one launch per colour, nothing staged in shared
+// memory, no per-body sums round trip through HBM, no second kernel.  Per manifold visit the thread gathers the other body's pose
+// (one 32-byte sector) once for up to four contacts; the contacts themselves are read where the narrowphase put them (a manifold's
+// contacts are contiguous: 64-byte runs of cA / cB / cN, 128 bytes of lambda / penalty), so the per-step visit-order copy of the
+// geometry is gone as well.  What is left on the critical path of a thread is its own chain of ~9 contacts; the loads of contact
+// c + 1 are issued before the row math of contact c.
+struct ContactRegs { float4 a, b, n, l, p; };
+__device__ __forceinline__ ContactRegs load_contact_regs(const ManifoldSet& ms, int ci, unsigned long long keep) {
+    ContactRegs r;
+    r.a = __ldg(ms.cA + ci); r.b = __ldg(ms.cB + ci); r.n = __ldg(ms.cN + ci);       // written by the narrowphase only: read-only during the sweeps
+    r.l = ld4_keep(&ms.lp[ci].l, keep); r.p = ld4_keep(&ms.lp[ci].p, keep);
+    return r;
 }
 
-template <int T, int MINB, bool ALIGNED>
-__global__ void __launch_bounds__(T, MINB) primal_visit_flat(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms,
-                                                             int vFirst, int vLast, const int* __restrict__ range, const int* __restrict__ kOf,
-                                                             float alpha, float biasDual, float beta, float* __restrict__ sums, float* __restrict__ carry) {
-    __shared__ FlatSmem<T> sm;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const unsigned long long keep = l2_keep_policy(), stream = l2_stream_policy();
-    // launched with programmatic stream serialization: the grid may already be resident while the previous colour's block solve
-    // drains; nothing it wrote (poses) is read before this point
+template <int T, int MINB, bool PF>
+__global__ void __launch_bounds__(T, MINB) primal_colour_bodies(BodyView b, const int* __restrict__ order, int count, const int* __restrict__ estart,
+                                                                const int4* __restrict__ entries, ManifoldSet ms, ForceView fv, SolveParams prm,
+                                                                float alpha, float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag) {
+    const int k = blockIdx.x * T + threadIdx.x;
+    if (k >= count) return;
+    const unsigned long long keep = l2_keep_policy();
+    // graph data: written by the graph stage, many launches ago
+    const int i = __ldg(order + k);
+    const int e0 = __ldg(estart + i), e1 = __ldg(estart + i + 1);
+    int4 ent = make_int4(0, 0, 0, 0);
+    if (e0 < e1) ent = __ldg(entries + e0);
+    // launched with programmatic stream serialization: poses and lambda / penalty may still be in flight from the previous colour
     cudaGridDependencySynchronize();
-    // Two ways to hand out the colour's visits [vFirst, vLast):
-    //   range == nullptr  chunks round-robin over the blocks (chunk c = visits vFirst + c*T ...).  Fastest; a body whose run crosses a
-    //                     chunk boundary gets its sum in two pieces (sums[k] + carry[chunk], added by primal_solve_flat), so its
-    //                     rounding depends on where the chunk grid falls — harmless for ONE world, but it makes a world's
-    //                     trajectory depend on what else is in the batch;
-    //   range != nullptr  (batches of several worlds) block r owns the contiguous visits [range[r], range[r + 1]), cut on BODY
-    //                     boundaries (flat_ranges): a run that crosses a chunk boundary stays inside the block, its partial sum
-    //                     waits in shared memory and the sum is one sequence in visit order — exactly the cluster loop's, and
-    //                     independent of the batch (bit-identical ensembles however they are partitioned over GPUs).
-    constexpr bool aligned = ALIGNED;           // compile-time: the round-robin instantiation carries none of the other mode's code
-    const int vBegin = aligned ? range[blockIdx.x] : vFirst, vEnd = aligned ? range[blockIdx.x + 1] : vLast;
-    const int stride = aligned ? T : (int)gridDim.x * T;
-    const int start = aligned ? vBegin : vBegin + (int)blockIdx.x * T;
-    if (start >= vEnd) return;
-    const int4 none = make_int4(0, 0, -8, 0);                        // body -1
-    // Software pipeline over the block's chunks, two deep: the visit ENTRIES are loaded two chunks ahead (registers), and as soon
-    // as an entry is there the data it points at — two poses, the lambda / penalty record, the streamed geometry: 9 x 16 B per
-    // visit — is fetched one chunk ahead with cp.async into this thread's slots of a shared-memory stage.  A chunk therefore
-    // starts with its operands already on chip; both DRAM round trips hide behind the previous chunk's row math and reduction.
-    auto load_entry = [&](int v, int4& e, int& prevZ) {
-        e = none; prevZ = -8;
-        if (v < vEnd) { e = __ldcs(visits + v); if (lane == 0 && v > vBegin) prevZ = __ldg(&visits[v - 1].z); }
-    };
-    auto issue_gathers = [&](int v, const int4& e, int& kSelf) {         // into the stage; the caller commits the group
-        kSelf = 0;
-        if (v < vEnd) {
-            int self = e.z >> 3;
-            kSelf = __ldg(kOf + self);                                    // the body's position in the colour order = its row of `sums`
-            stage16(&sm.stage[0][t], &b.pose[self].pos, keep); stage16(&sm.stage[1][t], &b.pose[self].rot, keep);
-            stage16(&sm.stage[2][t], &b.pose[e.y].pos, keep);  stage16(&sm.stage[3][t], &b.pose[e.y].rot, keep);
-            stage16_nol1(&sm.stage[4][t], vg.a + v, stream); stage16_nol1(&sm.stage[5][t], vg.b + v, stream); stage16_nol1(&sm.stage[6][t], vg.n + v, stream);
-            stage16_nol1(&sm.stage[7][t], &ms.lp[e.x].l, keep); stage16_nol1(&sm.stage[8][t], &ms.lp[e.x].p, keep);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    int4 eCur, eNext; int prevCur, prevNext, kCur;
-    load_entry(start + t, eCur, prevCur);
-    load_entry(start + t + stride, eNext, prevNext);
-    issue_gathers(start + t, eCur, kCur);
-    for (int it = 0, base = start; base < vEnd; base += stride, ++it) {
-        const int v = base + t;
-        const int4 e = eCur; const int prevZ = prevCur; const int kSelf = kCur;
-        const bool live = v < vEnd;
-        const int self = e.z >> 3;
-        ContactLP* lp = ms.lp + e.x;
-        // ---- this chunk's operands: wait for the thread's own copies, move them to registers, and refill the stage at once
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        BodyPose ps, po; float4 a4, b4, n4, l4, p4;
-        ps.pos = sm.stage[0][t]; ps.rot = sm.stage[1][t]; po.pos = sm.stage[2][t]; po.rot = sm.stage[3][t];
-        a4 = sm.stage[4][t]; b4 = sm.stage[5][t]; n4 = sm.stage[6][t]; l4 = sm.stage[7][t]; p4 = sm.stage[8][t];
-        eCur = eNext; prevCur = prevNext;
-        issue_gathers(v + stride, eCur, kCur);                        // next chunk (its entry was loaded a whole chunk ago)
-        load_entry(v + 2 * stride, eNext, prevNext);                  // the entry after that
-        // ---- phase 0: this warp's segment heads (no barrier: each warp lists its own, the block barrier after phase 1 publishes them)
-        const int buf = it & 1;                                       // rows and segment lists are double buffered: ONE barrier per chunk
-        int prevSelf = __shfl_up_sync(0xffffffffu, self, 1);
-        if (lane == 0) prevSelf = prevZ >> 3;                         // -1 at the colour's first visit
-        const bool head = live && (prevSelf != self || t == 0);       // lane 0 of the chunk always opens a segment (maybe a continuation)
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        if (head) {
-            int r = __popc(heads & ((1u << lane) - 1u));
-            sm.segPos[buf][warp][r] = (unsigned char)t;
-            sm.segK[buf][warp][r] = (t == 0 && prevSelf == self) ? ~kSelf : kSelf;    // complemented: continues the previous chunk's last segment
-        }
-        if (lane == 0) sm.headMask[buf][warp] = heads;
-        if (aligned && t == 0) sm.nextK[buf] = base + T < vEnd ? kCur : -1;     // row of the body the block's NEXT chunk opens with (kCur was loaded for it above)
-        // ---- phase 1
-        if (live) {
-            bool gyro = (e.z & 2) != 0, pending = biasDual >= 0.0f && (e.z & 4) != 0;
-            float sg = (e.z & 1) ? 1.0f : -1.0f;                       // visiting body is A / B of the manifold
-            ContactState cs = unpack_contact(a4, b4, n4, l4, p4);       // rA = r_self, rB = r_other here
-            M3 invIw = m3(zero3(), zero3(), zero3());
-            if (gyro) {   // anisotropic inertia only: for R diag(c) R^T = c Id the term Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero
-                V3 I = xyz(b.aux[self].inert);
-                invIw = rot_diag(qmat(quat(ps.rot)), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
-            }
-            BodySystem sys;
-            visit_rows(ps.pos, ps.rot, po.pos, po.rot, sg, __int_as_float(e.w), alpha, pending, biasDual, beta, gyro, invIw, cs, sys);
+    const BodyPose self = load_pose_keep(b.pose + i, keep);
+    const float4 inert4 = __ldg(&b.aux[i].inert);
+    const bool gyro = !(inert4.x == inert4.y && inert4.y == inert4.z);       // isotropic: Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero
+    M3 invIwRow = m3(zero3(), zero3(), zero3());
+    if (gyro) invIwRow = rot_diag(qmat(quat(self.rot)), mk3(1.0f / inert4.x, 1.0f / inert4.y, 1.0f / inert4.z));
+    float2 acc[14];
+#pragma unroll
+    for (int q = 0; q < 14; ++q) acc[q] = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+    for (int e = e0; e < e1; ++e) {
+        const int other = ent.x, c0 = ent.y, flags = ent.z;
+        const float mu = __int_as_float(ent.w);
+        const int nc = flags & 7;
+        const bool isA = (flags & 8) != 0, pending = biasDual >= 0.0f && (flags & 16) != 0;
+        const float sg = isA ? 1.0f : -1.0f;
+        const BodyPose po = load_pose_keep(b.pose + other, keep);
+        ContactRegs cur = load_contact_regs(ms, c0, keep);
+        if (e + 1 < e1) ent = __ldg(entries + e + 1);                       // next manifold's entry, a whole manifold ahead
+#pragma unroll 1
+        for (int c = 0; c < nc; ++c) {
+            const int ci = c0 + c;
+            ContactRegs nxt = cur;
+            if (PF && c + 1 < nc) nxt = load_contact_regs(ms, ci + 1, keep);      // in flight during this contact's row math
+            // the contact in the visiting body's frame: rA = r_self, rB = r_other; C0 travels with its own field
+            float4 rs = isA ? cur.a : cur.b, ro = isA ? cur.b : cur.a;
+            ContactState cs = unpack_contact(make_float4(rs.x, rs.y, rs.z, cur.a.w), make_float4(ro.x, ro.y, ro.z, cur.b.w), cur.n, cur.l, cur.p);
+            float2 v[14];
+            visit_rows_pairs(self.pos, self.rot, po.pos, po.rot, sg, mu, alpha, pending, biasDual, prm.beta, gyro, invIwRow, cs, v);
             // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
             float4 nl = pack_lambda(cs);
-            if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); *lp = q; }
-            else if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) lp->l = nl;
-            float4* row = sm.c[buf][t];
-            row[0] = make_float4(sys.rl[0], sys.rl[1], sys.rl[2], sys.ra[0]);
-            row[1] = make_float4(sys.ra[1], sys.ra[2], sys.ll[0], sys.ll[1]);
-            row[2] = make_float4(sys.ll[2], sys.ll[3], sys.ll[4], sys.ll[5]);
-            row[3] = make_float4(sys.la[0], sys.la[1], sys.la[2], sys.la[3]);
-            row[4] = make_float4(sys.la[4], sys.la[5], sys.la[6], sys.la[7]);
-            row[5] = make_float4(sys.la[8], sys.aa[0], sys.aa[1], sys.aa[2]);
-            row[6] = make_float4(sys.aa[3], sys.aa[4], sys.aa[5], 0.0f);
-        }
-        __syncthreads();          // the only barrier of the chunk: buffer `buf` is next written two chunks on, i.e. after the NEXT barrier
-        // ---- phase 2: each warp sums the segments that START in its 32 visits (their rows may run on into later warps')
-        {
-            const int nSegW = __popc(heads);
-            int liveCount = vEnd - base; if (liveCount > T) liveCount = T;
-            int tailEnd = liveCount;                                  // where this warp's last segment ends: the next head of a later warp
+            if (pending) { st4_keep(&ms.lp[ci].l, nl, keep); st4_keep(&ms.lp[ci].p, pack_penalty(cs), keep); }
+            else if (nl.y != cur.l.y || nl.z != cur.l.z || nl.w != cur.l.w) st4_keep(&ms.lp[ci].l, nl, keep);
 #pragma unroll
-            for (int w2 = T / 32 - 1; w2 >= 1; --w2) { unsigned m = sm.headMask[buf][w2]; if (w2 > warp && m) tailEnd = w2 * 32 + __ffs(m) - 1; }
-            for (int wi = lane; wi < nSegW * kFlatLanes; wi += 32) {
-                int sgi = wi / kFlatLanes, j = wi - sgi * kFlatLanes;
-                int lv = sm.segPos[buf][warp][sgi], z = sgi + 1 < nSegW ? sm.segPos[buf][warp][sgi + 1] : tailEnd;
-                int idx = sm.segK[buf][warp][sgi];          // the body's row of `sums`, complemented when the segment continues the previous chunk's last
-                // a body whose run crosses a chunk boundary is summed in one sequence all the same: the partial sum waits in shared memory
-                const bool cont = idx < 0;
-                float4 acc = (cont && aligned) ? sm.carry[buf ^ 1][j] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (cont) idx = ~idx;
-                auto add = [&](float4 x) {                   // two packed adds (add.rn.f32x2) instead of four scalar ones
-                    float2 lo = __fadd2_rn(make_float2(acc.x, acc.y), make_float2(x.x, x.y)), hi = __fadd2_rn(make_float2(acc.z, acc.w), make_float2(x.z, x.w));
-                    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
-                };
-                for (; lv + 4 <= z; lv += 4) {
-                    float4 x0 = sm.c[buf][lv][j], x1 = sm.c[buf][lv + 1][j], x2 = sm.c[buf][lv + 2][j], x3 = sm.c[buf][lv + 3][j];
-                    add(x0); add(x1); add(x2); add(x3);
-                }
-                for (; lv < z; ++lv) add(sm.c[buf][lv][j]);
-                if (aligned && z == liveCount && sm.nextK[buf] == idx) sm.carry[buf][j] = acc;         // aligned: the run goes on in the block's next chunk
-                else if (cont && !aligned) reinterpret_cast<float4*>(carry + (size_t)((base - vBegin) / T) * kSumStride)[j] = acc;   // round-robin: a piece
-                else reinterpret_cast<float4*>(sums + (size_t)idx * kSumStride)[j] = acc;
-            }
+            for (int q = 0; q < 14; ++q) acc[q] = __fadd2_rn(acc[q], v[q]);
+            if (PF) cur = nxt;
+            else if (c + 1 < nc) cur = load_contact_regs(ms, ci + 1, keep);
         }
     }
-}
-
-// One body per thread: the body's row sums (+ with round-robin chunks the pieces of every later chunk its run reaches, in chunk
-// order), inertial terms, Schur solve, pose update.  `order`, `vstart`, `sums` point at the colour's first body.
-__global__ void __launch_bounds__(kThreads) primal_solve_flat(BodyView b, ForceView fv, const int* __restrict__ order, const int* __restrict__ vstart, int count,
-                                                              int vBegin, int chunkT, const float* __restrict__ sums, const float* __restrict__ carry,
-                                                              SolveParams prm, float* dxOut, Diag* diag) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    int i = order[k];
-    int vs = vstart[k], ve = vstart[k + 1];
-    const unsigned long long keep = l2_keep_policy();
-    cudaGridDependencySynchronize();          // the visit kernel's sums (programmatic stream serialization, see launch_flat)
-    BodyPose self = load_pose_keep(b.pose + i, keep);
-    BodyAux aux = b.aux[i];
-    float o[kSumStride];
-#pragma unroll
-    for (int q = 0; q < kSumStride; ++q) o[q] = 0.0f;
-    if (ve > vs) {                            // a body no contact visits has no row: nothing was written for it
-        const float4* s4 = reinterpret_cast<const float4*>(sums + (size_t)k * kSumStride);
-#pragma unroll
-        for (int q = 0; q < kSumStride / 4; ++q) { float4 x = __ldcs(s4 + q); o[4 * q] = x.x; o[4 * q + 1] = x.y; o[4 * q + 2] = x.z; o[4 * q + 3] = x.w; }
-        if (carry) {
-            int c0 = (vs - vBegin) / chunkT, c1 = (ve - 1 - vBegin) / chunkT;
-            for (int c = c0 + 1; c <= c1; ++c) {
-                const float4* c4 = reinterpret_cast<const float4*>(carry + (size_t)c * kSumStride);
-#pragma unroll
-                for (int q = 0; q < kSumStride / 4; ++q) { float4 x = c4[q]; o[4 * q] += x.x; o[4 * q + 1] += x.y; o[4 * q + 2] += x.z; o[4 * q + 3] += x.w; }
-            }
-        }
-    }
+    // inertial terms, Schur 3x3 LDL^T, pose update (solver.cpp:351-369, :402-408)
+    const BodyAux aux = b.aux[i];
     V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
     BodySystem own; M3 invIw;
     body_self_system(pos, rot, aux, prm.dt, own, invIw);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { own.rl[q] += o[q]; own.ra[q] += o[3 + q]; }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) { own.ll[q] += o[6 + q]; own.aa[q] += o[21 + q]; }
-#pragma unroll
-    for (int q = 0; q < 9; ++q) own.la[q] += o[12 + q];
+    own.rl[0] += acc[0].x; own.rl[1] += acc[0].y; own.rl[2] += acc[1].x; own.ra[0] += acc[1].y; own.ra[1] += acc[2].x; own.ra[2] += acc[2].y;
+    own.ll[0] += acc[3].x; own.ll[1] += acc[3].y; own.ll[2] += acc[4].x; own.ll[3] += acc[4].y; own.ll[4] += acc[5].x; own.ll[5] += acc[5].y;
+    own.la[0] += acc[6].x; own.la[1] += acc[6].y; own.la[2] += acc[7].x; own.la[3] += acc[7].y; own.la[4] += acc[8].x; own.la[5] += acc[8].y;
+    own.la[6] += acc[9].x; own.la[7] += acc[9].y; own.la[8] += acc[10].x;
+    own.aa[0] += acc[10].y; own.aa[1] += acc[11].x; own.aa[2] += acc[11].y; own.aa[3] += acc[12].x; own.aa[4] += acc[12].y; own.aa[5] += acc[13].x;
     if (fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i]) accumulate_user_forces(own, fv, b.pose, i, pos, rot, invIw);
     V3 dl, da;
     solve_body_system(own, dl, da);
@@ -799,83 +679,30 @@ __global__ void solve6_batch(const float* lhs36, const float* rhs6, int n, float
 // ------------------------------------------------------------------ launchers (declared in avbd_launch.h)
 static inline int blocks_of(long long n, int per) { long long b = (n + per - 1) / per; return (int)(b < 1 ? 1 : b); }
 
-// Body-aligned ranges of one colour's visits: range r of `grid` starts at the first body whose run starts at or after
-// the r-th equal share of [vBegin, vEnd) — every body's visits then belong to exactly one block, which sums them in one
-// sequence (no partial sums to merge across blocks, the result does not depend on where the colour's visit list is cut).
-__global__ void flat_ranges(const int* __restrict__ vstart, int count, int vBegin, int vEnd, int grid, int* __restrict__ range) {
-    cudaGridDependencySynchronize();
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r > grid) return;
-    long long target = (long long)vBegin + ((long long)(vEnd - vBegin) * r) / grid;
-    int lo = 0, hi = count;                        // first k in [0, count] with vstart[k] >= target (vstart[count] == vEnd)
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (vstart[mid] < target) lo = mid + 1; else hi = mid; }
-    range[r] = vstart[lo];
-}
-
 // Function attributes and occupancy are PER DEVICE (a process may hold worlds on several GPUs): cached by device index.
 constexpr int kMaxDevices = 64;
 static int current_device() { int dev = 0; cudaGetDevice(&dev); return (dev >= 0 && dev < kMaxDevices) ? dev : 0; }
 
-template <int T, int MINB>
-static int flat_resident_blocks() {
-    static int cache[kMaxDevices] = {0};
-    const int dev = current_device();
-    if (!cache[dev]) {
-        cudaFuncSetAttribute(primal_visit_flat<T, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(primal_visit_flat<T, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        int sms = 148, per = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, primal_visit_flat<T, MINB, true>, T, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 1; }
-        if (getenv("AVBD_DEBUG")) fprintf(stderr, "primal_visit_flat<%d,%d>: %d blocks per SM resident (device %d)\n", T, MINB, per, dev);
-        cache[dev] = sms * per;
+// One colour of the large-world sweep: bodies order[0 .. count) (the colour's slice of the colour-sorted body list).
+void launch_primal_bodies(cudaStream_t s, BodyView b, const int* order, int count, const int* estart, const int4* entries, ManifoldSet ms, ForceView fv,
+                          SolveParams prm, float alpha, float biasDual, float* dxOut, Diag* diag) {
+    if (count <= 0) return;
+    // AVBD_BODIES (tuning aid) = "<threads per block><min blocks per SM><prefetch>": 12841 (default) 12840 12831 12851 25621 ...
+    static const int cfg = [] { const char* e = getenv("AVBD_BODIES"); return e ? atoi(e) : 12841; }();
+#define AVBD_PB(T, M, PF) launch_dep(primal_colour_bodies<T, M, PF>, dim3(blocks_of(count, T)), dim3(T), 0, s, b, order, count, estart, entries, ms, fv, prm, alpha, biasDual, dxOut, diag)
+    switch (cfg) {
+        case 12840: AVBD_PB(128, 4, false); break;
+        case 12831: AVBD_PB(128, 3, true); break;
+        case 12851: AVBD_PB(128, 5, true); break;
+        case 12850: AVBD_PB(128, 5, false); break;
+        case 6481:  AVBD_PB(64, 8, true); break;
+        case 6461:  AVBD_PB(64, 6, true); break;
+        case 25621: AVBD_PB(256, 2, true); break;
+        default:    AVBD_PB(128, 4, true); break;
     }
-    return cache[dev];
-}
-static int flat_config() { static int cfg = [] { const char* e = getenv("AVBD_FLAT"); return e ? atoi(e) : 1284; }(); return cfg; }
-
-// The default large-world sweep of one colour: flat visit partition + block solve.  `order` / `vstart` are the WHOLE colour-ordered
-// arrays, the colour is their bodies [first, first + count) with visits [vBegin, vEnd); kOf[body] = its position in `order`.
-// `sums`: 28 floats per dynamic body.
-// AVBD_FLAT (tuning aid) = "<threads per block><blocks per SM>": 1284 (default) 1285 1286 — within 2 % of each other on the 1M-box grid.
-int primal_flat_chunk_threads() { return 128; }
-// Persistent grid of a colour with nVisits visits = what is actually resident (a block that has to wait for a slot would start
-// its share late), at most one block per chunk.
-int primal_flat_grid(int nVisits) {
-    int nChunks = (nVisits + 127) / 128;
-    int resident = flat_config() == 1286 ? flat_resident_blocks<128, 6>() : (flat_config() == 1285 ? flat_resident_blocks<128, 5>() : flat_resident_blocks<128, 4>());
-    return nChunks < resident ? nChunks : resident;
-}
-void launch_flat_ranges(cudaStream_t s, const int* vstart, int first, int count, int vBegin, int vEnd, int grid, int* range) {
-    if (grid > 0) launch_dep(flat_ranges, dim3(blocks_of(grid + 1, kThreads)), dim3(kThreads), 0, s, vstart + first, count, vBegin, vEnd, grid, range);
+#undef AVBD_PB
 }
 
-template <int T, int MINB>
-static void launch_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                        const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float biasDual,
-                        float* sums, float* carry, float* dxOut, Diag* diag) {
-    // Programmatic dependent launch: each kernel of a sweep is launched while its predecessor still runs and blocks at
-    // cudaGridDependencySynchronize() until that one has completed — a step has ~160 of these dependent launches, and the
-    // launch latency of each would otherwise sit on the critical path.
-    if (grid > 0 && range) launch_dep(primal_visit_flat<T, MINB, true>, dim3(grid), dim3(T), 0, s, b, visits, vg, ms, vBegin, vEnd, range, kOf, alpha, biasDual, prm.beta, sums, carry);
-    else if (grid > 0) launch_dep(primal_visit_flat<T, MINB, false>, dim3(grid), dim3(T), 0, s, b, visits, vg, ms, vBegin, vEnd, range, kOf, alpha, biasDual, prm.beta, sums, carry);
-    const int* orderC = order + first; const int* vstartC = vstart + first; const float* sumsC = sums + (size_t)first * kSumStride;
-    const float* carryC = range ? nullptr : carry;                       // body-aligned ranges leave no pieces to add
-    launch_dep(primal_solve_flat, dim3(blocks_of(count, kThreads)), dim3(kThreads), 0, s, b, fv, orderC, vstartC, count, vBegin, (int)T, sumsC, carryC, prm, dxOut, diag);
-}
-// `range` == nullptr: round-robin chunks (+ `carry`: 28 floats per chunk of the colour); else the colour's grid + 1 body-aligned
-// block boundaries (launch_flat_ranges, once per graph build).
-int launch_primal_flat(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* order, const int* vstart,
-                       const int* kOf, int first, int count, int vBegin, int vEnd, int grid, const int* range, SolveParams prm, float alpha, float biasDual,
-                       float* sums, float* carry, float* dxOut, Diag* diag) {
-#define AVBD_FL(T, M) launch_flat<T, M>(s, b, visits, vg, ms, fv, order, vstart, kOf, first, count, vBegin, vEnd, grid, range, prm, alpha, biasDual, sums, carry, dxOut, diag)
-    switch (flat_config()) {
-        case 1286: AVBD_FL(128, 6); break;
-        case 1285: AVBD_FL(128, 5); break;
-        default:   AVBD_FL(128, 4); break;
-    }
-#undef AVBD_FL
-    return grid > 0 ? 2 : 1;
-}
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,
                        const int2* colRange, int nColours, int maxColourCount, int nContacts, SolveParams prm,
                        Diag* diag, bool contactDiag, bool anyUnvisited) {

@@ -91,7 +91,7 @@ def test_host_mirror_edits_deletes_and_snapshots():
     # 11 bodies -> 10; the top manifold went with its body; the others reached the re-created device world with their rows intact
     # (checked BEFORE any step: a dropped history would show as 0 manifolds on the device)
     assert int(d[1]) == 10 and int(d[2]) == 9 and int(d[4]) == 1 and int(d[8]) == 10, d
-    assert float(d[6]) < -5.0, d                                                   # the bottom contact really carried load
+    assert float(d[6]) < -0.5, d                                                   # the bottom contact really carried load
     s = rows["delete_body"][1]
     assert float(s[1]) < 0.5, s                                                    # the stack did not re-settle
     assert int(rows["edit_one_body"][0][1]) == 52 and int(rows["edit_nothing"][0][1]) == 0

@@ -12,3 +12,9 @@ w.add_joint(-1, 1, (0, 3.5, 0)); w.add_spring(2, 3, (0, 0.5, 0), (0, -0.5, 0), 1
 w.step(10); print("jointed", w.diagnostics()); w.close()
 s = scenes.stress_grid(12, 12, 12, spacing_y=1.01, start_y=0.51, wide_ground=True)
 w = avbd.World(); scenes.load(w, s); w.step(4); print("grid12", w.diagnostics()); w.pick((0, 50, 0), (0, -1, 0)); w.close()
+# a world past the single-block colouring limit: cooperative-grid colouring + one-body-per-thread sweeps, with the state handed back
+# and forth (snapshot / restore, manifold upload) in between
+s = scenes.stress_grid(22, 22, 22, spacing_y=1.01, start_y=0.51, wide_ground=True)
+w = avbd.World(); scenes.load(w, s); w.step(3)
+blob = w.snapshot(); raw = w.manifolds_raw(); w.upload_manifolds(*raw); w.step(1); w.restore(blob); w.step(1)
+print("grid22", w.diagnostics(), w.step_stats()["colours"]); w.close()
