@@ -92,7 +92,10 @@ struct avbd_world {
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<int> candCode, candCodeSorted;
     DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;      // per-contact visit lists: small worlds (cluster loop) only
-    DevBuf<int> deg, estart, colCursor; DevBuf<int4> entries;      // body -> manifold entries CSR (graph stage): colouring adjacency + the large-world sweep's work list
+    DevBuf<int> deg, estart, colCursor, sweepRange, freeList, linkedList; DevBuf<int4> entries; DevBuf<int2> colVisit; DevBuf<float4> vgA, vgB, vgN;
+    int2 hColVisit[64]; int sweepWarps[64] = {0}, sweepOff[64] = {0};      // per colour: its visit range, warps of the sweep, offset of its warp ranges
+    int nFree = 0, nLinkedFree = 0; bool visitGeomStale = true;            // contact geometry in visit order (VisitGeom), refreshed once per step
+         // body -> manifold entries CSR (graph stage): colouring adjacency + the large-world sweep's work list
     DevBuf<float4> stA, stB, stN; DevBuf<ContactLP> stLP;      // np_build staging (4 slots per manifold), packed by np_compact
 
     // manifolds (ping-pong)
@@ -139,6 +142,7 @@ struct avbd_world {
         TRY(b.lp.ensure(4 * m, false, stream));
         return 0;
     }
+    VisitGeom vgeom() { VisitGeom g; g.a = vgA.p; g.b = vgB.p; g.n = vgN.p; return g; }
     ContactStage stage() { ContactStage c; c.cA = stA.p; c.cB = stB.p; c.cN = stN.p; c.lp = stLP.p; return c; }
     int ensure_stage(size_t m) {
         TRY(stA.ensure(4 * m, false, stream)); TRY(stB.ensure(4 * m, false, stream)); TRY(stN.ensure(4 * m, false, stream));
@@ -421,6 +425,7 @@ int run_collide(avbd_world* w) {
         w->launches++;
     }
     w->graphValid = sameTopology;
+    w->visitGeomStale = true;         // every contact was rebuilt
     if (w->timed || w->profiling) cudaEventRecord(w->ev[2], s);
     CK(cudaGetLastError());
     return 0;
@@ -536,24 +541,43 @@ int run_colour(avbd_world* w) {
     CK(cudaMemsetAsync(w->colRange.p, 0, sizeof(int2) * 64, s));
     launch_dep(colour_bounds, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);
     w->launches += 2;
-    if (w->nDyn <= w->persistentMaxBodies) {
-        // small worlds: per-contact visits in colour order, the cluster loop's work list (visitStart[k] belongs to colOrder[k])
-        TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
-        TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
-        CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
-        launch_dep(visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p);
-        TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
-        launch_dep(visit_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
-        w->launches += 2;
-    }
-    // ONE host round trip for everything the launches of the sweeps need: colour ranges, counters
+    // contact visits in colour order (the sweeps' work list): visitStart[k] belongs to colOrder[k]
+    TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
+    TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
+    TRY(w->freeList.ensure((size_t)w->nDyn, false, s)); TRY(w->linkedList.ensure((size_t)w->nDyn, false, s));
+    CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(&w->dCnt->nFree, 0, 2 * sizeof(int), s));         // nFree, nLinkedFree
+    launch_dep(visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p,
+               fv, w->freeList.p, w->linkedList.p, w->dCnt);
+    TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
+    launch_dep(visit_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
+    TRY(w->colVisit.ensure(64, false, s));
+    launch_dep(colour_visit_bounds, dim3(1), dim3(64), 0, s, w->colRange.p, w->dCnt, w->visitStart.p, w->colVisit.p);
+    w->launches += 3;
+    w->visitGeomStale = true;
+    // ONE host round trip for everything the launches of the sweeps need: colour ranges, their visit ranges, counters
     CK(cudaMemcpyAsync(w->hColRange, w->colRange.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(w->hColVisit, w->colVisit.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));
     TRY(read_counters(w));
     if (w->hCnt->nUncoloured != 0) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
     if (w->hCnt->overflow & 4) return fail(AVBD_ERR_CAPACITY, "more than 64 colours needed");
     w->nColours = w->hCnt->nColours;
+    w->nFree = w->hCnt->nFree; w->nLinkedFree = w->hCnt->nLinkedFree;
     w->maxColourCount = 0;
     for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);
+    // the sweeps' body-aligned warp ranges, every colour in one launch (device only: nothing below waits on it)
+    {
+        int total = 0;
+        for (int c = 0; c < w->nColours; ++c) {
+            int nv = w->hColVisit[c].y - w->hColVisit[c].x;
+            w->sweepWarps[c] = nv > 0 ? primal_sweep_warps(nv) : 0;
+            w->sweepOff[c] = total; total += w->sweepWarps[c] + 1;
+        }
+        TRY(w->sweepRange.ensure((size_t)std::max(1, total), false, s));
+        int nw[64], off[64];
+        for (int c = 0; c < 64; ++c) { nw[c] = c < w->nColours ? std::max(1, w->sweepWarps[c]) : 1; off[c] = c < w->nColours ? w->sweepOff[c] : 0; }
+        if (w->nColours > 0 && w->nContacts > 0) { launch_warp_ranges(s, w->visitStart.p, w->colRange.p, w->nColours, nw, off, w->sweepRange.p); w->launches++; }
+    }
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;
@@ -568,11 +592,22 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float biasDual = -1.0f)
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
-    for (int c = 0; c < w->nColours; ++c) {
-        int first = w->hColRange[c].x, count = w->hColRange[c].y - first;
-        if (count <= 0) continue;
-        launch_primal_bodies(s, w->bview(), w->colOrder.p + first, count, w->estart.p, w->entries.p, ms, fv, w->prm, alpha, biasDual, dxDev, w->dDiag.p);
+    if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
+        size_t cap = w->visits.cap;
+        TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));
+        launch_dep(visit_geometry, dim3(blocks_for(2ll * w->nContacts)), dim3(kThreads), 0, s, w->visits.p, w->visitStart.p + w->nDyn, ms, w->vgeom());
         w->launches++;
+    }
+    w->visitGeomStale = false;
+    if (w->nFree > 0) { launch_primal_free(s, w->bview(), fv, w->freeList.p, w->nFree, w->colour.p, -1, w->prm, dxDev, w->dDiag.p); w->launches++; }
+    for (int c = 0; c < w->nColours; ++c) {
+        int count = w->hColRange[c].y - w->hColRange[c].x;
+        if (count <= 0) continue;
+        if (w->nLinkedFree > 0) { launch_primal_free(s, w->bview(), fv, w->linkedList.p, w->nLinkedFree, w->colour.p, c, w->prm, dxDev, w->dDiag.p); w->launches++; }
+        if (w->sweepWarps[c] > 0) {
+            launch_primal_sweep(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->sweepRange.p + w->sweepOff[c], w->sweepWarps[c], w->prm, alpha, biasDual, dxDev, w->dDiag.p);
+            w->launches++;
+        }
     }
     CK(cudaGetLastError());
     return 0;
@@ -752,7 +787,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
-    w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release(); w->deg.release(); w->estart.release(); w->colCursor.release(); w->entries.release();
+    w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release(); w->deg.release(); w->estart.release(); w->colCursor.release(); w->entries.release(); w->sweepRange.release(); w->colVisit.release(); w->freeList.release(); w->linkedList.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
     w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stLP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
@@ -1039,7 +1074,7 @@ int avbd_upload_manifolds(avbd_world* w, int count, const int* ints, const int* 
         CK(cudaMemcpyAsync(ms.lp, lp.data(), nC * sizeof(ContactLP), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
     }
-    w->graphValid = false; w->contactDiagDone = false;
+    w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false;
     return 0;
 }
 
@@ -1135,7 +1170,7 @@ int avbd_restore(avbd_world* w, const void* buf, long long bytes) {
         TRY(get_dev(ms.cN, c * sizeof(float4))); TRY(get_dev(ms.lp, c * sizeof(ContactLP)));
     }
     CK(cudaStreamSynchronize(s));
-    w->graphValid = false; w->contactDiagDone = false; w->lastPairs = 0;
+    w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false; w->lastPairs = 0;
     return 0;
 }
 

@@ -69,7 +69,11 @@ __global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, c
 // Entry: {contact id, other body, (visiting body << 3) | first-visit << 2 | anisotropic-inertia << 1 | body-is-A, friction bits}.
 // first-visit: this is the visit of the contact that comes FIRST in a sweep (the other endpoint is static or has a higher
 // colour) — the one that applies the previous iteration's deferred dual update (avbd_solve.cu).
-__global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount) {
+// Also lists the dynamic bodies NO contact visits (the sweeps' visit pipeline never meets them; primal_free_bodies solves them):
+// `freeList` those no user force touches either, `linkedList` those a joint / spring links to another body (they keep their place
+// in the colour order).  The lists' order is irrelevant.
+__global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount,
+                            ForceView fv, int* freeList, int* linkedList, Counters* cnt) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
@@ -79,6 +83,16 @@ __global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange,
     for (int m = rg.x; m < rg.y; ++m) k += hdr[m].z;
     for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z;
     visitCount[t] = k;
+    if (k == 0) {
+        bool linked = fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i];
+        if (linked) linkedList[atomicAdd(&cnt->nLinkedFree, 1)] = i;           // rare: one atomic each
+        else {
+            cg::coalesced_group grp = cg::coalesced_threads();
+            int base = 0;
+            if (grp.thread_rank() == 0) base = atomicAdd(&cnt->nFree, (int)grp.size());
+            freeList[grp.shfl(base, 0) + (int)grp.thread_rank()] = i;
+        }
+    }
 }
 __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
                            const int* visitStart, const BodyAux* aux, const int* colour, int4* visits) {
@@ -100,6 +114,23 @@ __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, 
         int m = bList[q]; int4 h = hdr[m]; int c0 = cstart[m]; int tag = idx | first(h.x);
         for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.x, tag, h.w);
     }
+}
+
+// Once per step (the narrowphase rewrites every contact): copy each visit's contact geometry into visit order, so the
+// iterations x colours primal sweeps STREAM it (three fully coalesced 16-byte records per visit) instead of gathering it by contact
+// id — gathered, a sweep moved a third more DRAM bytes (ncu, 1M-box grid: 2.06 GB against 1.56 GB per iteration: a pile has about two
+// contacts per manifold, so a gather uses half of every 64-byte DRAM granule, and a body's "I am B" manifolds are scattered).
+// Already in the VISITING body's frame: a = {r_self, C0n}, b = {r_other, C0t.x}, n = {n, C0t.y}.  nVisits lives on the device.
+__global__ void visit_geometry(const int4* __restrict__ visits, const int* __restrict__ nVisits, ManifoldSet ms, VisitGeom vg) {
+    cudaGridDependencySynchronize();
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= *nVisits) return;
+    int4 e = visits[v];
+    float4 a = ms.cA[e.x], b = ms.cB[e.x];
+    bool isA = (e.z & 1) != 0;
+    vg.a[v] = isA ? a : make_float4(b.x, b.y, b.z, a.w);
+    vg.b[v] = isA ? b : make_float4(a.x, a.y, a.z, b.w);
+    vg.n[v] = ms.cN[e.x];
 }
 
 // ------------------------------------------------------------------ colouring
@@ -281,6 +312,15 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
     if (t == 0 || keySorted[t - 1] != c) colourRange[c].x = t;
     if (t == nDyn - 1 || keySorted[t + 1] != c) colourRange[c].y = t + 1;
     if (t == nDyn - 1) cnt->nColours = (int)c + 1;
+}
+
+// out[c] = {first visit, one past the last visit} of colour c (a colour's bodies, hence its visits, are contiguous)
+__global__ void colour_visit_bounds(const int2* colourRange, const Counters* cnt, const int* visitStart, int2* out) {
+    cudaGridDependencySynchronize();
+    int c = threadIdx.x;
+    if (c >= 64) return;
+    int2 r = c < cnt->nColours ? colourRange[c] : make_int2(0, 0);
+    out[c] = r.y > r.x ? make_int2(visitStart[r.x], visitStart[r.y]) : make_int2(0, 0);
 }
 
 // ------------------------------------------------------------------ predict / warm-start decay of user forces

@@ -21,6 +21,11 @@ struct ForceView {
     const int* adjStart; const int* adj;    // entry = index*4 + type*2 + isA ; type 0 joint, 1 spring
 };
 
+// Contact geometry in VISIT order (one float4 per field per visit, refreshed once per step by visit_geometry): the sweeps stream it
+// fully coalesced instead of gathering 3 x 16 B per visit by contact id, in the visiting body's frame:
+// {r_self,C0n} {r_other,C0t.x} {n,C0t.y}.
+struct VisitGeom { float4* a; float4* b; float4* n; };
+
 #ifdef __CUDACC__
 // Programmatic dependent launch.  A step is a chain of ~50 (Stress1000) to ~200 (1M boxes) small dependent kernels on one
 // stream; launched this way a kernel may become resident while its predecessor drains, and waits at the
@@ -115,14 +120,21 @@ __device__ __forceinline__ void reduce_contact_diag_block(int world, float sepn,
 constexpr int kThreads = 256;
 constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodies per CTA tile (9 lanes per body in the sum phase)
 
-// The large-world sweep of one colour, one body per thread (avbd_solve.cu: primal_colour_bodies): `order` points at the colour's
-// bodies, estart / entries are the body -> manifold-entry CSR of the graph stage (entry = {other body, first contact, contact count
-// | side << 3 | first-visit << 4, friction bits}).
+// The large-world sweep of one colour (avbd_solve.cu: primal_sweep_warp): the colour's contact visits — a contiguous run of the
+// colour-ordered visit list — cut into nWarps body-aligned warp ranges (range[0 .. nWarps], launch_warp_ranges, once per graph
+// build for all colours); each warp pipelines its range and solves the bodies it finishes.  primal_sweep_warps(nVisits) = warps for
+// a colour of that many visits.
 // biasDual >= 0: the previous iteration's dual pass is still pending and each contact's first visit applies it (deferred dual); the
 // value is that pass's clamp(1 - alpha, 0, 1) (manifold.cpp:179), which lies in [0, 1] for every alpha, so a negative value can only
 // mean "nothing pending" (plain primal sweep).
-void launch_primal_bodies(cudaStream_t s, BodyView b, const int* order, int count, const int* estart, const int4* entries, ManifoldSet ms, ForceView fv,
-                          SolveParams prm, float alpha, float biasDual, float* dxOut, Diag* diag);
+int primal_sweep_warps(int nVisits);
+void launch_warp_ranges(cudaStream_t s, const int* vstart, const int2* colRange, int nColours, const int* nWarps, const int* off, int* range);
+void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* range, int nWarps, SolveParams prm,
+                         float alpha, float biasDual, float* dxOut, Diag* diag);
+// Dynamic bodies no contact visits (listed by the graph stage).  onlyColour < 0: the list of bodies no user force touches, one
+// launch per sweep; onlyColour >= 0: the list of bodies a joint / spring links to another body, filtered to that colour.
+void launch_primal_free(cudaStream_t s, BodyView b, ForceView fv, const int* freeList, int nFree, const int* colour, int onlyColour, SolveParams prm,
+                        float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live (densely stored) contacts.
 // `diag` != nullptr: this is the step's last dual pass and no body moves after it, so the contact diagnostics
 // (solver.cpp:472-497) are reduced here from the values already in registers instead of by a separate sweep.

@@ -4,7 +4,7 @@
 //
 // The reference walks bodies serially (Gauss-Seidel, solver.cpp:344); here bodies of one colour share no
 // manifold, so a colour is one parallel phase, one contact visit (computeConstraint + 3 rows) per thread:
-//   large worlds   per colour primal_colour_bodies: one body per thread, row sums in registers, block solve in the same thread
+//   large worlds   per colour primal_sweep_warp: one contact visit per lane in warp-private pipelines, finished bodies solved in batches
 //   small worlds   solve_loop_cluster: the whole iteration loop in one thread-block cluster, a tile of bodies per CTA and phase
 //
 // Deferred dual.  The dual / penalty-ramp pass of iteration k (solver.cpp:411-430) reads the poses left by sweep k, and
@@ -238,7 +238,7 @@ template <bool COH> __device__ __forceinline__ ContactState load_contact_c(const
 // The visit list is laid out in colour order, so the visits of a tile of BPB consecutive bodies of one colour are ONE
 // contiguous run.  The tile walks that run one visit per thread (every lane busy, every lane's gathers independent
 // and in flight together) and solves its bodies in the same call — small worlds are latency bound, a phase must not
-// be split over launches.  (Large worlds use one body per thread, further down.)
+// be split over launches.  (Large worlds use the warp-private visit pipeline further down.)
 //   phase 0  thread t < BPB stages body t of the tile in shared memory (pose, inertial target, mass, inverse inertia)
 //   phase 1  thread t takes visit base+t: computeConstraint + 3 rows -> its 27 partial sums, parked transposed in
 //            shared memory (row stride 257: conflict free)
@@ -411,87 +411,207 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
     }
 }
 
-// ------------------------------------------------------------------ primal, one body per thread (the large-world path)
-// A colour's bodies share no manifold, so each thread owns ONE body for the whole phase: it walks the body's manifold entries
-// (graph stage: {other body, first contact, contact count | side | first-visit, friction}, in pair-key order), evaluates every
-// contact's computeConstraint + 3 rows, keeps the 27 row sums in registers (14 packed pairs, added in visit order — the same
-// sequence of additions the cluster loop performs through shared memory, so a world's sums do not depend on which path its batch
-// takes), then adds the inertial terms, solves the 6x6 system and moves the body — one launch per colour, nothing staged in shared
-// memory, no per-body sums round trip through HBM, no second kernel.  Per manifold visit the thread gathers the other body's pose
-// (one 32-byte sector) once for up to four contacts; the contacts themselves are read where the narrowphase put them (a manifold's
-// contacts are contiguous: 64-byte runs of cA / cB / cN, 128 bytes of lambda / penalty), so the per-step visit-order copy of the
-// geometry is gone as well.  What is left on the critical path of a thread is its own chain of ~9 contacts; the loads of contact
-// c + 1 are issued before the row math of contact c.
-struct ContactRegs { float4 a, b, n, l, p; };
-__device__ __forceinline__ ContactRegs load_contact_regs(const ManifoldSet& ms, int ci, unsigned long long keep) {
-    ContactRegs r;
-    r.a = __ldg(ms.cA + ci); r.b = __ldg(ms.cB + ci); r.n = __ldg(ms.cN + ci);       // written by the narrowphase only: read-only during the sweeps
-    r.l = ld4_keep(&ms.lp[ci].l, keep); r.p = ld4_keep(&ms.lp[ci].p, keep);
-    return r;
+// ------------------------------------------------------------------ primal, warp-private visit pipeline (the large-world path)
+// A colour's contact visits are one contiguous run of the colour-ordered visit list (graph stage).  The run is cut into one
+// contiguous, BODY-ALIGNED range per warp (warp_ranges): a body's visits never straddle two warps, so nothing in this kernel is
+// shared between warps — no block barrier, no atomics — and a body's 27 row sums are ONE sequence of additions in visit order
+// (exactly the cluster loop's, whatever else is in the batch: ensembles are bit-identical however they are partitioned).
+// Each warp runs its own software pipeline over chunks of 32 visits, one visit per lane:
+//   entries   two chunks ahead, in registers (streamed, 16 B per visit)
+//   operands  one chunk ahead, cp.async into the lane's slots of the warp's stage: self pose, other pose (L2 evict-last: poses are
+//             the data every sweep re-reads), the visit's geometry (streamed from the visit-order copy, evict-first), lambda / penalty
+//   phase 1   computeConstraint (+ the pending dual update on a contact's first visit) + 3 rows -> 27 partial sums, one 112-byte
+//             shared-memory row per lane (7 x STS.128, stride 28 words: conflict free)
+//   phase 2   8 lanes per segment (= consecutive visits of one body, found with one ballot; 7 of the 8 carry a float4 column, so a
+//             quarter warp reads one row: conflict free) add the segment's rows in visit order, four segments per pass, the pass's
+//             trip count uniform over the warp; a segment that runs on into the next chunk leaves its partial sum in the carry slot
+//   solve     finished bodies queue up in shared memory (sums + body index) and are solved in batches, one body per lane:
+//             inertial terms, Schur 3x3 LDL^T, pose update (solver.cpp:351-369, :402-408) — no per-body sums round trip through
+//             HBM, no second kernel, and the serial 6x6 solve runs with most lanes busy.
+constexpr int kQueueSlots = 26;
+struct WarpPipe {
+    float4 rows[32][7];              // this chunk's partial sums, one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad
+    float4 stage[9][32];             // the NEXT chunk's operands (cp.async): self pose (2), other pose (2), geometry (3), lambda, penalty
+    float4 queue[kQueueSlots][7];    // row sums of finished bodies waiting for the batched solve
+    float4 carry[7];                 // partial sum of the body whose run crosses into the next chunk
+    int    qBody[kQueueSlots];
+    unsigned char segStart[32];      // lane of each segment's first visit
+};
+constexpr int kSweepWarps = 4;                     // warps per block (they share nothing but the block's shared-memory allocation)
+
+__device__ __forceinline__ void stage16(float4* dst, const float4* src, unsigned long long policy) {       // cp.async (LDGSTS), L1-allocating
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void stage16_nol1(float4* dst, const float4* src, unsigned long long policy) {  // bypasses L1 (single-use data)
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_stream_policy() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
-template <int T, int MINB, bool PF>
-__global__ void __launch_bounds__(T, MINB) primal_colour_bodies(BodyView b, const int* __restrict__ order, int count, const int* __restrict__ estart,
-                                                                const int4* __restrict__ entries, ManifoldSet ms, ForceView fv, SolveParams prm,
-                                                                float alpha, float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag) {
-    const int k = blockIdx.x * T + threadIdx.x;
-    if (k >= count) return;
-    const unsigned long long keep = l2_keep_policy();
-    // graph data: written by the graph stage, many launches ago
-    const int i = __ldg(order + k);
-    const int e0 = __ldg(estart + i), e1 = __ldg(estart + i + 1);
-    int4 ent = make_int4(0, 0, 0, 0);
-    if (e0 < e1) ent = __ldg(entries + e0);
+// One body per lane (lanes [0, qn)): queued row sums + inertial terms -> 6x6 solve -> pose update.
+__device__ __forceinline__ void solve_queue(WarpPipe& w, int qn, int lane, const BodyView& b, const ForceView& fv, const SolveParams& prm,
+                                            float* dxOut, Diag* diag, unsigned long long keep) {
+    if (lane < qn) {
+        const int i = w.qBody[lane];
+        BodyPose self = load_pose_keep(b.pose + i, keep);
+        BodyAux aux = b.aux[i];
+        float o[28];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) { float4 x = w.queue[lane][q]; o[4 * q] = x.x; o[4 * q + 1] = x.y; o[4 * q + 2] = x.z; o[4 * q + 3] = x.w; }
+        V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
+        BodySystem own; M3 invIw;
+        body_self_system(pos, rot, aux, prm.dt, own, invIw);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { own.rl[q] += o[q]; own.ra[q] += o[3 + q]; }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { own.ll[q] += o[6 + q]; own.aa[q] += o[21 + q]; }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) own.la[q] += o[12 + q];
+        if (fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i]) accumulate_user_forces(own, fv, b.pose, i, pos, rot, invIw);
+        V3 dl, da;
+        solve_body_system(own, dl, da);
+        int evn = apply_body_update(pos, rot, dl, da);
+        st4_keep(&b.pose[i].pos, f4(pos, self.pos.w), keep);
+        st4_keep(&b.pose[i].rot, f4(rot), keep);
+        if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
+        if (evn) atomicAdd(&diag[b.worldId[i]].nanEvents, evn);
+    }
+    __syncwarp();
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
+                                                                           const int* __restrict__ range, int nWarps, SolveParams prm,
+                                                                           float alpha, float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag) {
+    __shared__ WarpPipe pipes[kSweepWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kSweepWarps + warp;
+    if (gw >= nWarps) return;                                  // no block-wide barrier anywhere in this kernel: a warp may leave on its own
+    WarpPipe& w = pipes[warp];
+    const unsigned long long keep = l2_keep_policy(), stream = l2_stream_policy();
+    const int vBegin = __ldg(range + gw), vEnd = __ldg(range + gw + 1);      // written by the graph stage, many launches ago
+    if (vBegin >= vEnd) return;
     // launched with programmatic stream serialization: poses and lambda / penalty may still be in flight from the previous colour
     cudaGridDependencySynchronize();
-    const BodyPose self = load_pose_keep(b.pose + i, keep);
-    const float4 inert4 = __ldg(&b.aux[i].inert);
-    const bool gyro = !(inert4.x == inert4.y && inert4.y == inert4.z);       // isotropic: Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero
-    M3 invIwRow = m3(zero3(), zero3(), zero3());
-    if (gyro) invIwRow = rot_diag(qmat(quat(self.rot)), mk3(1.0f / inert4.x, 1.0f / inert4.y, 1.0f / inert4.z));
-    float2 acc[14];
-#pragma unroll
-    for (int q = 0; q < 14; ++q) acc[q] = make_float2(0.0f, 0.0f);
-#pragma unroll 1
-    for (int e = e0; e < e1; ++e) {
-        const int other = ent.x, c0 = ent.y, flags = ent.z;
-        const float mu = __int_as_float(ent.w);
-        const int nc = flags & 7;
-        const bool isA = (flags & 8) != 0, pending = biasDual >= 0.0f && (flags & 16) != 0;
-        const float sg = isA ? 1.0f : -1.0f;
-        const BodyPose po = load_pose_keep(b.pose + other, keep);
-        ContactRegs cur = load_contact_regs(ms, c0, keep);
-        if (e + 1 < e1) ent = __ldg(entries + e + 1);                       // next manifold's entry, a whole manifold ahead
-#pragma unroll 1
-        for (int c = 0; c < nc; ++c) {
-            const int ci = c0 + c;
-            ContactRegs nxt = cur;
-            if (PF && c + 1 < nc) nxt = load_contact_regs(ms, ci + 1, keep);      // in flight during this contact's row math
-            // the contact in the visiting body's frame: rA = r_self, rB = r_other; C0 travels with its own field
-            float4 rs = isA ? cur.a : cur.b, ro = isA ? cur.b : cur.a;
-            ContactState cs = unpack_contact(make_float4(rs.x, rs.y, rs.z, cur.a.w), make_float4(ro.x, ro.y, ro.z, cur.b.w), cur.n, cur.l, cur.p);
-            float2 v[14];
-            visit_rows_pairs(self.pos, self.rot, po.pos, po.rot, sg, mu, alpha, pending, biasDual, prm.beta, gyro, invIwRow, cs, v);
-            // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
-            float4 nl = pack_lambda(cs);
-            if (pending) { st4_keep(&ms.lp[ci].l, nl, keep); st4_keep(&ms.lp[ci].p, pack_penalty(cs), keep); }
-            else if (nl.y != cur.l.y || nl.z != cur.l.z || nl.w != cur.l.w) st4_keep(&ms.lp[ci].l, nl, keep);
-#pragma unroll
-            for (int q = 0; q < 14; ++q) acc[q] = __fadd2_rn(acc[q], v[q]);
-            if (PF) cur = nxt;
-            else if (c + 1 < nc) cur = load_contact_regs(ms, ci + 1, keep);
+    const int4 none = make_int4(0, 0, -8, 0);                                // body -1
+    auto load_entry = [&](int v) { return v < vEnd ? __ldcs(visits + v) : none; };
+    auto issue_gathers = [&](int v, const int4& e) {                         // into the stage; one commit group per chunk
+        if (v < vEnd) {
+            const int self = e.z >> 3;
+            stage16(&w.stage[0][lane], &b.pose[self].pos, keep); stage16(&w.stage[1][lane], &b.pose[self].rot, keep);
+            stage16(&w.stage[2][lane], &b.pose[e.y].pos, keep);  stage16(&w.stage[3][lane], &b.pose[e.y].rot, keep);
+            stage16_nol1(&w.stage[4][lane], vg.a + v, stream); stage16_nol1(&w.stage[5][lane], vg.b + v, stream); stage16_nol1(&w.stage[6][lane], vg.n + v, stream);
+            stage16_nol1(&w.stage[7][lane], &ms.lp[e.x].l, keep); stage16_nol1(&w.stage[8][lane], &ms.lp[e.x].p, keep);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int4 eCur = load_entry(vBegin + lane), eNext = load_entry(vBegin + 32 + lane);
+    issue_gathers(vBegin + lane, eCur);
+    int qn = 0;                      // bodies waiting in the solve queue (warp-uniform)
+    int tailSelf = -1;               // body of the previous chunk's last visit
+    const int sub = lane >> 3, j = lane & 7;                                 // phase 2: segment of the pass / float4 column (7 = idle)
+    for (int base = vBegin; base < vEnd; base += 32) {
+        const int v = base + lane;
+        const int4 e = eCur;
+        const bool live = v < vEnd;
+        const int self = e.z >> 3;
+        // ---- this chunk's operands: wait for the lane's own copies, move them to registers, refill the stage at once
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        BodyPose ps, po; float4 a4, b4, n4, l4, p4;
+        ps.pos = w.stage[0][lane]; ps.rot = w.stage[1][lane]; po.pos = w.stage[2][lane]; po.rot = w.stage[3][lane];
+        a4 = w.stage[4][lane]; b4 = w.stage[5][lane]; n4 = w.stage[6][lane]; l4 = w.stage[7][lane]; p4 = w.stage[8][lane];
+        eCur = eNext;
+        issue_gathers(v + 32, eCur);                                         // next chunk (its entry was loaded a whole chunk ago)
+        eNext = load_entry(v + 64);                                          // the entry after that
+        // ---- segments: lane l opens one when visit l - 1 belongs to another body (lane 0: compare with the previous chunk's tail)
+        int prevSelf = __shfl_up_sync(0xffffffffu, self, 1);
+        if (lane == 0) prevSelf = tailSelf;
+        const bool cont = __shfl_sync(0xffffffffu, (int)(prevSelf == self), 0) != 0;      // the first segment continues the previous chunk's last
+        const bool head = live && (lane == 0 || prevSelf != self);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (head) w.segStart[__popc(heads & ((1u << lane) - 1u))] = (unsigned char)lane;
+        // ---- phase 1
+        if (live) {
+            const bool gyro = (e.z & 2) != 0, pending = biasDual >= 0.0f && (e.z & 4) != 0;
+            const float sg = (e.z & 1) ? 1.0f : -1.0f;                         // visiting body is A / B of the manifold
+            ContactState cs = unpack_contact(a4, b4, n4, l4, p4);               // rA = r_self, rB = r_other here
+            M3 invIw = m3(zero3(), zero3(), zero3());
+            if (gyro) {   // anisotropic inertia only: for R diag(c) R^T = c Id the term Ja x (I^-1 Ja) of solver.cpp:393-397 is exactly zero
+                V3 I = xyz(b.aux[self].inert);
+                invIw = rot_diag(qmat(quat(ps.rot)), mk3(1.0f / I.x, 1.0f / I.y, 1.0f / I.z));
+            }
+            float2 vv[14];
+            visit_rows_pairs(ps.pos, ps.rot, po.pos, po.rot, sg, __int_as_float(e.w), alpha, pending, biasDual, prm.beta, gyro, invIw, cs, vv);
+            // computeConstraint's side effects (manifold.cpp:224-241): written only when they changed something
+            ContactLP* lp = ms.lp + e.x;
+            float4 nl = pack_lambda(cs);
+            if (pending) { ContactLP q; q.l = nl; q.p = pack_penalty(cs); *lp = q; }
+            else if (nl.y != l4.y || nl.z != l4.z || nl.w != l4.w) lp->l = nl;
+            float4* row = w.rows[lane];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) row[q] = make_float4(vv[2 * q].x, vv[2 * q].y, vv[2 * q + 1].x, vv[2 * q + 1].y);      // the pairs ARE the row's order
+        }
+        __syncwarp();
+        // ---- phase 2: segment sums
+        int liveCount = vEnd - base; if (liveCount > 32) liveCount = 32;
+        const int nSeg = __popc(heads);
+        const int lastSelf = __shfl_sync(0xffffffffu, self, liveCount - 1);
+        const int nextSelf0 = __shfl_sync(0xffffffffu, eCur.z >> 3, 0);           // body the next chunk opens with (-1 past the warp's range)
+        const bool lastContinues = nextSelf0 == lastSelf;
+        const int nDone = nSeg - (lastContinues ? 1 : 0);
+        for (int s0 = 0; s0 < nSeg; s0 += 4) {
+            // queue slots in use: qn + s0 (every segment before this pass is finished: only a chunk's LAST segment can run on).
+            // No room for four more: solve what is queued first.
+            if (qn + s0 + 4 > kQueueSlots) { __syncwarp(); solve_queue(w, qn + s0, lane, b, fv, prm, dxOut, diag, keep); qn = -s0; }
+            const int sgi = s0 + sub;
+            const bool active = j < 7 && sgi < nSeg;
+            const int start = active ? (int)w.segStart[sgi] : 0;
+            const int end = (active && sgi + 1 < nSeg) ? (int)w.segStart[sgi + 1] : liveCount;
+            const int body = __shfl_sync(0xffffffffu, self, start);
+            const int len = active ? end - start : 0;
+            const int maxLen = __reduce_max_sync(0xffffffffu, len);
+            float4 acc = (active && sgi == 0 && cont) ? w.carry[j] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const float4* src = &w.rows[start][j < 7 ? j : 0];
+            for (int k = 0; k < maxLen; ++k) {                                    // warp-uniform trip count, predicated adds: no divergence
+                if (k < len) {
+                    float4 x = src[k * 7];
+                    float2 lo = __fadd2_rn(make_float2(acc.x, acc.y), make_float2(x.x, x.y)), hi = __fadd2_rn(make_float2(acc.z, acc.w), make_float2(x.z, x.w));
+                    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+                }
+            }
+            if (active) {
+                if (sgi == nSeg - 1 && lastContinues) w.carry[j] = acc;          // the run goes on in the warp's next chunk
+                else { w.queue[qn + sgi][j] = acc; if (j == 0) w.qBody[qn + sgi] = body; }
+            }
+        }
+        qn += nDone;
+        tailSelf = lastSelf;
+        __syncwarp();               // rows consumed, carry / queue visible, before the next chunk overwrites the rows
     }
-    // inertial terms, Schur 3x3 LDL^T, pose update (solver.cpp:351-369, :402-408)
-    const BodyAux aux = b.aux[i];
+    if (qn > 0) solve_queue(w, qn, lane, b, fv, prm, dxOut, diag, keep);
+}
+
+// Dynamic bodies no contact visits: inertial terms (plus user forces) -> 6x6 solve -> pose update.  onlyColour < 0: the bodies no
+// user force touches either — nothing they read is written by anyone else, so one launch per sweep covers them whatever their
+// colour.  onlyColour >= 0: bodies a joint / spring links to another body, one colour per launch like every other body.
+__global__ void __launch_bounds__(kThreads) primal_free_bodies(BodyView b, ForceView fv, const int* __restrict__ freeList, int nFree, const int* __restrict__ colour,
+                                                               int onlyColour, SolveParams prm, float* __restrict__ dxOut, Diag* __restrict__ diag) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nFree) return;
+    const int i = __ldg(freeList + t);
+    if (onlyColour >= 0 && __ldg(colour + i) != onlyColour) return;
+    const unsigned long long keep = l2_keep_policy();
+    cudaGridDependencySynchronize();
+    BodyPose self = load_pose_keep(b.pose + i, keep);
+    BodyAux aux = b.aux[i];
     V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
     BodySystem own; M3 invIw;
     body_self_system(pos, rot, aux, prm.dt, own, invIw);
-    own.rl[0] += acc[0].x; own.rl[1] += acc[0].y; own.rl[2] += acc[1].x; own.ra[0] += acc[1].y; own.ra[1] += acc[2].x; own.ra[2] += acc[2].y;
-    own.ll[0] += acc[3].x; own.ll[1] += acc[3].y; own.ll[2] += acc[4].x; own.ll[3] += acc[4].y; own.ll[4] += acc[5].x; own.ll[5] += acc[5].y;
-    own.la[0] += acc[6].x; own.la[1] += acc[6].y; own.la[2] += acc[7].x; own.la[3] += acc[7].y; own.la[4] += acc[8].x; own.la[5] += acc[8].y;
-    own.la[6] += acc[9].x; own.la[7] += acc[9].y; own.la[8] += acc[10].x;
-    own.aa[0] += acc[10].y; own.aa[1] += acc[11].x; own.aa[2] += acc[11].y; own.aa[3] += acc[12].x; own.aa[4] += acc[12].y; own.aa[5] += acc[13].x;
     if (fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i]) accumulate_user_forces(own, fv, b.pose, i, pos, rot, invIw);
     V3 dl, da;
     solve_body_system(own, dl, da);
@@ -500,6 +620,24 @@ __global__ void __launch_bounds__(T, MINB) primal_colour_bodies(BodyView b, cons
     st4_keep(&b.pose[i].rot, f4(rot), keep);
     if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
     if (evn) atomicAdd(&diag[b.worldId[i]].nanEvents, evn);
+}
+
+// Body-aligned warp ranges of every colour's visits, one launch: range[c][r] (r = 0 .. nWarps[c]) starts at the first body whose run
+// starts at or after the r-th equal share of the colour's visits — every body's visits then belong to exactly one warp.
+struct SweepGrids { int nWarps[64]; int off[64]; };
+__global__ void warp_ranges(const int* __restrict__ vstart, const int2* __restrict__ colRange, SweepGrids g, int* __restrict__ range) {
+    cudaGridDependencySynchronize();
+    const int c = blockIdx.y;
+    const int nW = g.nWarps[c];
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > nW) return;
+    int2 cr = colRange[c];
+    const int* vs = vstart + cr.x; int count = cr.y - cr.x;
+    int vBegin = vs[0], vEnd = vs[count];
+    long long target = (long long)vBegin + ((long long)(vEnd - vBegin) * r) / nW;
+    int lo = 0, hi = count;                        // first k in [0, count] with vs[k] >= target (vs[count] == vEnd)
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (vs[mid] < target) lo = mid + 1; else hi = mid; }
+    range[g.off[c] + r] = vs[lo];
 }
 
 // ------------------------------------------------------------------ dual
@@ -683,24 +821,58 @@ static inline int blocks_of(long long n, int per) { long long b = (n + per - 1) 
 constexpr int kMaxDevices = 64;
 static int current_device() { int dev = 0; cudaGetDevice(&dev); return (dev >= 0 && dev < kMaxDevices) ? dev : 0; }
 
-// One colour of the large-world sweep: bodies order[0 .. count) (the colour's slice of the colour-sorted body list).
-void launch_primal_bodies(cudaStream_t s, BodyView b, const int* order, int count, const int* estart, const int4* entries, ManifoldSet ms, ForceView fv,
-                          SolveParams prm, float alpha, float biasDual, float* dxOut, Diag* diag) {
-    if (count <= 0) return;
-    // AVBD_BODIES (tuning aid) = "<threads per block><min blocks per SM><prefetch>": 12841 (default) 12840 12831 12851 25621 ...
-    static const int cfg = [] { const char* e = getenv("AVBD_BODIES"); return e ? atoi(e) : 12841; }();
-#define AVBD_PB(T, M, PF) launch_dep(primal_colour_bodies<T, M, PF>, dim3(blocks_of(count, T)), dim3(T), 0, s, b, order, count, estart, entries, ms, fv, prm, alpha, biasDual, dxOut, diag)
-    switch (cfg) {
-        case 12840: AVBD_PB(128, 4, false); break;
-        case 12831: AVBD_PB(128, 3, true); break;
-        case 12851: AVBD_PB(128, 5, true); break;
-        case 12850: AVBD_PB(128, 5, false); break;
-        case 6481:  AVBD_PB(64, 8, true); break;
-        case 6461:  AVBD_PB(64, 6, true); break;
-        case 25621: AVBD_PB(256, 2, true); break;
-        default:    AVBD_PB(128, 4, true); break;
+// Resident warps of the sweep kernel on the current device (persistent-style sizing: a colour never gets more warps than fit at once).
+static int sweep_cfg() { static const int cfg = [] { const char* e = getenv("AVBD_SWEEP"); return e ? atoi(e) : 5; }(); return cfg; }
+template <int MINB> static int sweep_blocks_per_sm() {
+    int per = 0;
+    cudaFuncSetAttribute(primal_sweep_warp<MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, primal_sweep_warp<MINB>, 32 * kSweepWarps, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 1; }
+    return per;
+}
+int primal_sweep_max_warps() {
+    static int cache[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!cache[dev]) {
+        int sms = 148, per = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        switch (sweep_cfg()) {
+            case 3:  per = sweep_blocks_per_sm<3>(); break;
+            case 4:  per = sweep_blocks_per_sm<4>(); break;
+            default: per = sweep_blocks_per_sm<5>(); break;
+        }
+        if (getenv("AVBD_DEBUG")) fprintf(stderr, "primal_sweep_warp<%d>: %d blocks per SM resident, %d B shared memory per block (device %d)\n", sweep_cfg(), per,
+                                          (int)(kSweepWarps * sizeof(WarpPipe)), dev);
+        cache[dev] = sms * per * kSweepWarps;
     }
-#undef AVBD_PB
+    return cache[dev];
+}
+// Warps a colour with nVisits contact visits is cut into: what is resident, at most one warp per 4 chunks of 32 visits (a warp's
+// pipeline needs a few chunks to be worth its prologue).
+int primal_sweep_warps(int nVisits) {
+    int want = (nVisits + 127) / 128;
+    int mx = primal_sweep_max_warps();
+    return want < 1 ? 1 : (want < mx ? want : mx);
+}
+void launch_warp_ranges(cudaStream_t s, const int* vstart, const int2* colRange, int nColours, const int* nWarps, const int* off, int* range) {
+    SweepGrids g{};
+    int mx = 0;
+    for (int c = 0; c < nColours && c < 64; ++c) { g.nWarps[c] = nWarps[c]; g.off[c] = off[c]; mx = nWarps[c] > mx ? nWarps[c] : mx; }
+    if (nColours > 0) launch_dep(warp_ranges, dim3(blocks_of(mx + 1, kThreads), nColours), dim3(kThreads), 0, s, vstart, colRange, g, range);
+}
+void launch_primal_free(cudaStream_t s, BodyView b, ForceView fv, const int* freeList, int nFree, const int* colour, int onlyColour, SolveParams prm,
+                        float* dxOut, Diag* diag) {
+    if (nFree > 0) launch_dep(primal_free_bodies, dim3(blocks_of(nFree, kThreads)), dim3(kThreads), 0, s, b, fv, freeList, nFree, colour, onlyColour, prm, dxOut, diag);
+}
+// One colour of the large-world sweep: its visits, cut into nWarps body-aligned warp ranges (range[0 .. nWarps]).
+void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* range, int nWarps, SolveParams prm,
+                         float alpha, float biasDual, float* dxOut, Diag* diag) {
+    if (nWarps <= 0) return;
+    dim3 grid(blocks_of(nWarps, kSweepWarps)), block(32 * kSweepWarps);
+    switch (sweep_cfg()) {
+        case 3:  launch_dep(primal_sweep_warp<3>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag); break;
+        case 4:  launch_dep(primal_sweep_warp<4>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag); break;
+        default: launch_dep(primal_sweep_warp<5>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag); break;
+    }
 }
 
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,

@@ -80,6 +80,8 @@ struct Counters {             // device-side sizes produced by one stage, consum
     int nContacts;            // live contacts this step (dense contact list length)
     int overflow;             // bit0 pairs, bit1 manifolds, bit2 colours
     int topoChanged;          // set by np_build when a manifold's slot or contact count differs from last step
+    int nFree;                // dynamic bodies no contact visits and no user force touches (graph stage): solved by their own small kernel
+    int nLinkedFree;          // ... no contact visits, but a joint / spring: solved in colour order by the same kernel
 };
 
 } // namespace avbd

@@ -12,8 +12,8 @@ for w in $what; do case $w in
 launches)  # every launch of ONE steady-state step with its device time
   timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/${tag}_launches.csv $T > gpurun_out/${tag}_launches.log 2>&1;;
 solve)     # first iteration of the step: every colour's {visit sums, block solve} + the dual pass
-  timeout 900 $NCU --set full --import-source on -k 'regex:primal_|dual_contacts' -c ${SOLVE_COUNT:-17} -o gpurun_out/${tag}_solve -f $T > gpurun_out/${tag}_solve.log 2>&1;;
+  timeout 900 $NCU --set full --import-source on -k 'regex:primal_|dual_contacts' -c ${SOLVE_COUNT:-9} -o gpurun_out/${tag}_solve -f $T > gpurun_out/${tag}_solve.log 2>&1;;
 collide)   # broadphase sweep, SAT cull, manifold build, graph kernels of the same step
-  timeout 900 $NCU --set full --import-source on -k 'regex:bp_|np_|visit_fill|colour_round|velocity_bodies|predict_bodies' -c 16 -o gpurun_out/${tag}_collide -f $T > gpurun_out/${tag}_collide.log 2>&1;;
+  timeout 900 $NCU --set full --import-source on -k 'regex:bp_|np_|visit_fill|entry_fill|colour_round|velocity_bodies|predict_bodies' -c 16 -o gpurun_out/${tag}_collide -f $T > gpurun_out/${tag}_collide.log 2>&1;;
 esac; done
 ls -la gpurun_out

@@ -56,7 +56,7 @@ def kernels(path):
 
 def traffic(path):
     """dram__bytes_read.sum + dram__bytes_write.sum of the primal kernels of a `capture.sh solve` report, per colour sweep
-    (= one primal_visit_flat + one primal_solve_flat launch, the unit bench.py's roofline is quoted per)."""
+    (= one primal_sweep_warp launch, the unit bench.py's roofline is quoted per)."""
     import json
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -67,7 +67,7 @@ def traffic(path):
     gi, lastGrid, done = H.index("launch__grid_size"), None, False
     for r in rows[2:]:
         bytes_ = float(r[ri].replace(",", "")) * scale[U[ri]] + float(r[wi].replace(",", "")) * scale[U[wi]]
-        if "primal_visit" in r[ki]:
+        if "primal_visit" in r[ki] or "primal_sweep" in r[ki]:
             # ONE whole iteration (every colour once): colours come largest first, so a grid that grows again starts the next iteration
             grid = int(r[gi].replace(",", ""))
             if lastGrid is not None and grid > lastGrid: done = True
