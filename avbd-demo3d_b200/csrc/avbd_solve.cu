@@ -416,22 +416,44 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
 // contiguous, BODY-ALIGNED range per warp (warp_ranges): a body's visits never straddle two warps, so nothing in this kernel is
 // shared between warps — no block barrier, no atomics — and a body's 27 row sums are ONE sequence of additions in visit order
 // (exactly the cluster loop's, whatever else is in the batch: ensembles are bit-identical however they are partitioned).
-// Each warp runs its own software pipeline over chunks of 32 visits, one visit per lane:
-//   entries   two chunks ahead, in registers (streamed, 16 B per visit)
-//   operands  one chunk ahead, cp.async into the lane's slots of the warp's stage: self pose, other pose (L2 evict-last: poses are
-//             the data every sweep re-reads), the visit's geometry (streamed from the visit-order copy, evict-first), lambda / penalty
-//   phase 1   computeConstraint (+ the pending dual update on a contact's first visit) + 3 rows -> 27 partial sums, one 112-byte
-//             shared-memory row per lane (7 x STS.128, stride 28 words: conflict free)
-//   phase 2   8 lanes per segment (= consecutive visits of one body, found with one ballot; 7 of the 8 carry a float4 column, so a
-//             quarter warp reads one row: conflict free) add the segment's rows in visit order, four segments per pass, the pass's
-//             trip count uniform over the warp; a segment that runs on into the next chunk leaves its partial sum in the carry slot
-//   solve     finished bodies queue up in shared memory (sums + body index) and are solved in batches, one body per lane:
-//             inertial terms, Schur 3x3 LDL^T, pose update (solver.cpp:351-369, :402-408) — no per-body sums round trip through
-//             HBM, no second kernel, and the serial 6x6 solve runs with most lanes busy.
-constexpr int kQueueSlots = 26;
+// Each warp runs its own software pipeline over chunks of 32 visits, one visit per lane.  The kernel is bound by the SM's load /
+// store data pipe (ncu: l1tex data-pipe wavefronts at 68 % of peak with every operand staged through shared memory by cp.async —
+// a gathering LDGSTS costs ~25-30 wavefronts, one per lane, however few sectors it touches), so operands take the cheapest road:
+//   entries     two chunks ahead, in registers (streamed, 16 B per visit)
+//   geometry    one chunk ahead, three coalesced 16-byte loads per lane straight into registers (visit-order copy, evict-first)
+//   lambda /    one chunk ahead into registers; the two 16-byte halves of a contact's 32-byte record are fetched by a PAIR of lanes
+//   penalty     in one instruction (16 whole sectors per instruction instead of 32 half-used ones) and swapped with one shuffle each
+//   self pose   one chunk ahead, cp.async by the segment heads only (a body's visits are consecutive lanes: one fetch per body, not
+//               per visit) into a per-segment slot every lane of the segment then reads (broadcast)
+//   other pose  one chunk ahead, cp.async into the lane's own slot (L2 evict-last: poses are the data every sweep re-reads)
+//   phase 1     computeConstraint (+ the pending dual update on a contact's first visit) + 3 rows -> 27 partial sums, one 112-byte
+//               shared-memory row per lane (7 x STS.128, stride 28 words: conflict free)
+//   phase 2     8 lanes per segment (= consecutive visits of one body, found with one ballot; 7 of the 8 carry a float4 column, so a
+//               quarter warp reads one row: conflict free) add the segment's rows in visit order, four segments per pass, the pass's
+//               trip count uniform over the warp; a segment that runs on into the next chunk leaves its partial sum in the carry slot
+//   solve       finished bodies queue up in shared memory (sums + body index) and are solved in batches, one body per lane:
+//               inertial terms, Schur 3x3 LDL^T, pose update (solver.cpp:351-369, :402-408) — no per-body sums round trip through
+//               HBM, no second kernel, and the serial 6x6 solve runs with most lanes busy.
+#ifndef AVBD_VG_REG
+#define AVBD_VG_REG 1        // visit-order geometry: 1 = coalesced loads into registers, 0 = cp.async into the stage
+#endif
+#ifndef AVBD_LP_REG
+#define AVBD_LP_REG 1        // lambda / penalty: 1 = lane-pair loads into registers + shuffle, 0 = cp.async into the stage
+#endif
+#ifndef AVBD_SELF_SEG
+#define AVBD_SELF_SEG 1      // visiting-body pose: 1 = one cp.async per segment (broadcast read), 0 = one per lane
+#endif
+#ifndef AVBD_QUEUE_SLOTS
+#define AVBD_QUEUE_SLOTS 26
+#endif
+constexpr int kQueueSlots = AVBD_QUEUE_SLOTS;
+constexpr bool kVgReg = AVBD_VG_REG != 0, kLpReg = AVBD_LP_REG != 0, kSelfSeg = AVBD_SELF_SEG != 0;
 struct WarpPipe {
     float4 rows[32][7];              // this chunk's partial sums, one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad
-    float4 stage[9][32];             // the NEXT chunk's operands (cp.async): self pose (2), other pose (2), geometry (3), lambda, penalty
+    float4 other[2][32];             // the NEXT chunk's other-body poses, per lane (cp.async)
+    float4 selfp[2][32];             // the NEXT chunk's visiting-body poses, per segment (cp.async by the segment's first lane) or per lane
+    float4 geom[kVgReg ? 1 : 3][32]; // geometry / lambda, penalty when they are staged rather than loaded into registers
+    float4 lamp[kLpReg ? 1 : 2][32];
     float4 queue[kQueueSlots][7];    // row sums of finished bodies waiting for the batched solve
     float4 carry[7];                 // partial sum of the body whose run crosses into the next chunk
     int    qBody[kQueueSlots];
@@ -451,6 +473,11 @@ __device__ __forceinline__ unsigned long long l2_stream_policy() {
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+__device__ __forceinline__ float4 ld4_keep_cg(const float4* ptr, unsigned long long pol) {                // single use in this launch: L2 only
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+    return v;
 }
 
 // One body per lane (lanes [0, qn)): queued row sums + inertial terms -> 6x6 solve -> pose update.
@@ -499,19 +526,44 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
     // launched with programmatic stream serialization: poses and lambda / penalty may still be in flight from the previous colour
     cudaGridDependencySynchronize();
     const int4 none = make_int4(0, 0, -8, 0);                                // body -1
+    const bool odd = (lane & 1) != 0;
     auto load_entry = [&](int v) { return v < vEnd ? __ldcs(visits + v) : none; };
-    auto issue_gathers = [&](int v, const int4& e) {                         // into the stage; one commit group per chunk
-        if (v < vEnd) {
-            const int self = e.z >> 3;
-            stage16(&w.stage[0][lane], &b.pose[self].pos, keep); stage16(&w.stage[1][lane], &b.pose[self].rot, keep);
-            stage16(&w.stage[2][lane], &b.pose[e.y].pos, keep);  stage16(&w.stage[3][lane], &b.pose[e.y].rot, keep);
-            stage16_nol1(&w.stage[4][lane], vg.a + v, stream); stage16_nol1(&w.stage[5][lane], vg.b + v, stream); stage16_nol1(&w.stage[6][lane], vg.n + v, stream);
-            stage16_nol1(&w.stage[7][lane], &ms.lp[e.x].l, keep); stage16_nol1(&w.stage[8][lane], &ms.lp[e.x].p, keep);
-        }
+    // Everything chunk [vb, vb + 32) needs, issued a whole chunk ahead.  `e` = the lane's entry of that chunk, `prevTail` = body of the
+    // visit before the chunk (-1: none).  Returns the chunk's segment heads; nvA / nvB / nvN / nL0 / nL1 receive the register operands.
+    float4 nvA, nvB, nvN, nL0, nL1;
+    nvA = nvB = nvN = nL0 = nL1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    auto prefetch = [&](int vb, const int4& e, int prevTail) -> unsigned {
+        const int v = vb + lane;
+        const bool lv = v < vEnd;
+        const int self = e.z >> 3;
+        int prevSelf = __shfl_up_sync(0xffffffffu, self, 1);
+        if (lane == 0) prevSelf = prevTail;
+        const bool head = lv && (lane == 0 || prevSelf != self);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (kSelfSeg) {
+            if (head) {                                                      // one fetch of the visiting body's pose per segment
+                const int seg = __popc(heads & ((1u << lane) - 1u));
+                stage16(&w.selfp[0][seg], &b.pose[self].pos, keep); stage16(&w.selfp[1][seg], &b.pose[self].rot, keep);
+            }
+        } else if (lv) { stage16(&w.selfp[0][lane], &b.pose[self].pos, keep); stage16(&w.selfp[1][lane], &b.pose[self].rot, keep); }
+        if (lv) { stage16(&w.other[0][lane], &b.pose[e.y].pos, keep); stage16(&w.other[1][lane], &b.pose[e.y].rot, keep); }
+        if (!kVgReg && lv) { stage16_nol1(&w.geom[0][lane], vg.a + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 1][lane], vg.b + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 2][lane], vg.n + v, stream); }
+        if (!kLpReg && lv) { stage16_nol1(&w.lamp[0][lane], &ms.lp[e.x].l, keep); stage16_nol1(&w.lamp[kLpReg ? 0 : 1][lane], &ms.lp[e.x].p, keep); }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        if (kVgReg && lv) { nvA = __ldcs(vg.a + v); nvB = __ldcs(vg.b + v); nvN = __ldcs(vg.n + v); }
+        if (kLpReg) {
+            // lambda / penalty: lanes 2k and 2k + 1 fetch the two halves of ONE contact's record per instruction
+            const int cPar = __shfl_xor_sync(0xffffffffu, e.x, 1);
+            const bool lvPar = __shfl_xor_sync(0xffffffffu, (int)lv, 1) != 0;
+            const int c0 = odd ? cPar : e.x, c1 = odd ? e.x : cPar;          // instruction 0: the even lane's contact, 1: the odd lane's
+            const bool ok0 = odd ? lvPar : lv, ok1 = odd ? lv : lvPar;
+            if (ok0) nL0 = ld4_keep_cg(odd ? &ms.lp[c0].p : &ms.lp[c0].l, keep);
+            if (ok1) nL1 = ld4_keep_cg(odd ? &ms.lp[c1].p : &ms.lp[c1].l, keep);
+        }
+        return heads;
     };
     int4 eCur = load_entry(vBegin + lane), eNext = load_entry(vBegin + 32 + lane);
-    issue_gathers(vBegin + lane, eCur);
+    unsigned headsNext = prefetch(vBegin, eCur, -1);
     int qn = 0;                      // bodies waiting in the solve queue (warp-uniform)
     int tailSelf = -1;               // body of the previous chunk's last visit
     const int sub = lane >> 3, j = lane & 7;                                 // phase 2: segment of the pass / float4 column (7 = idle)
@@ -520,21 +572,33 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
         const int4 e = eCur;
         const bool live = v < vEnd;
         const int self = e.z >> 3;
-        // ---- this chunk's operands: wait for the lane's own copies, move them to registers, refill the stage at once
+        const unsigned heads = headsNext;
+        int liveCount = vEnd - base; if (liveCount > 32) liveCount = 32;
+        const int lastSelf = __shfl_sync(0xffffffffu, self, liveCount - 1);
+        const bool cont = tailSelf == __shfl_sync(0xffffffffu, self, 0);                  // the first segment continues the previous chunk's last
+        // ---- this chunk's operands: registers filled a chunk ago (+ the pair swap), staged poses; then refill for the next chunk at once
+        float4 a4 = nvA, b4 = nvB, n4 = nvN;
+        float4 l4 = nL0, p4 = nL1;
+        if (kLpReg) {
+            const float4 give = odd ? nL0 : nL1;                             // the half fetched for the partner
+            float4 got;
+            got.x = __shfl_xor_sync(0xffffffffu, give.x, 1); got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+            got.z = __shfl_xor_sync(0xffffffffu, give.z, 1); got.w = __shfl_xor_sync(0xffffffffu, give.w, 1);
+            l4 = odd ? got : nL0; p4 = odd ? nL1 : got;
+        }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        BodyPose ps, po; float4 a4, b4, n4, l4, p4;
-        ps.pos = w.stage[0][lane]; ps.rot = w.stage[1][lane]; po.pos = w.stage[2][lane]; po.rot = w.stage[3][lane];
-        a4 = w.stage[4][lane]; b4 = w.stage[5][lane]; n4 = w.stage[6][lane]; l4 = w.stage[7][lane]; p4 = w.stage[8][lane];
+        if (kSelfSeg) __syncwarp();                                          // the self poses were fetched by the segment heads
+        const int seg = __popc(heads & ((2u << lane) - 1u)) - 1;
+        const int sslot = kSelfSeg ? (seg < 0 ? 0 : seg) : lane;
+        BodyPose ps, po;
+        ps.pos = w.selfp[0][sslot]; ps.rot = w.selfp[1][sslot]; po.pos = w.other[0][lane]; po.rot = w.other[1][lane];
+        if (!kVgReg) { a4 = w.geom[0][lane]; b4 = w.geom[kVgReg ? 0 : 1][lane]; n4 = w.geom[kVgReg ? 0 : 2][lane]; }
+        if (!kLpReg) { l4 = w.lamp[0][lane]; p4 = w.lamp[kLpReg ? 0 : 1][lane]; }
+        if (live && (heads >> lane & 1u)) w.segStart[seg] = (unsigned char)lane;
+        __syncwarp();                                                        // everyone holds its poses: the stage may be refilled
         eCur = eNext;
-        issue_gathers(v + 32, eCur);                                         // next chunk (its entry was loaded a whole chunk ago)
+        headsNext = prefetch(base + 32, eCur, lastSelf);                     // next chunk (its entry was loaded a whole chunk ago)
         eNext = load_entry(v + 64);                                          // the entry after that
-        // ---- segments: lane l opens one when visit l - 1 belongs to another body (lane 0: compare with the previous chunk's tail)
-        int prevSelf = __shfl_up_sync(0xffffffffu, self, 1);
-        if (lane == 0) prevSelf = tailSelf;
-        const bool cont = __shfl_sync(0xffffffffu, (int)(prevSelf == self), 0) != 0;      // the first segment continues the previous chunk's last
-        const bool head = live && (lane == 0 || prevSelf != self);
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        if (head) w.segStart[__popc(heads & ((1u << lane) - 1u))] = (unsigned char)lane;
         // ---- phase 1
         if (live) {
             const bool gyro = (e.z & 2) != 0, pending = biasDual >= 0.0f && (e.z & 4) != 0;
@@ -558,9 +622,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
         }
         __syncwarp();
         // ---- phase 2: segment sums
-        int liveCount = vEnd - base; if (liveCount > 32) liveCount = 32;
         const int nSeg = __popc(heads);
-        const int lastSelf = __shfl_sync(0xffffffffu, self, liveCount - 1);
         const int nextSelf0 = __shfl_sync(0xffffffffu, eCur.z >> 3, 0);           // body the next chunk opens with (-1 past the warp's range)
         const bool lastContinues = nextSelf0 == lastSelf;
         const int nDone = nSeg - (lastContinues ? 1 : 0);
