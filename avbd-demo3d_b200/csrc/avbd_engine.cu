@@ -91,12 +91,12 @@ struct avbd_world {
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<int> candCode, candCodeSorted;
+    DevBuf<unsigned long long> buildTiles;      // np_build's chained scan over its blocks
     DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;      // per-contact visit lists: small worlds (cluster loop) only
     DevBuf<int> deg, estart, colCursor, sweepRange, freeList, linkedList; DevBuf<int4> entries; DevBuf<int2> colVisit; DevBuf<float4> vgA, vgB, vgN;
     int2 hColVisit[64]; int sweepWarps[64] = {0}, sweepOff[64] = {0};      // per colour: its visit range, warps of the sweep, offset of its warp ranges
     int nFree = 0, nLinkedFree = 0; bool visitGeomStale = true;            // contact geometry in visit order (VisitGeom), refreshed once per step
          // body -> manifold entries CSR (graph stage): colouring adjacency + the large-world sweep's work list
-    DevBuf<float4> stA, stB, stN; DevBuf<ContactLP> stLP;      // np_build staging (4 slots per manifold), packed by np_compact
 
     // manifolds (ping-pong)
     struct MBuf { DevBuf<unsigned long long> key; DevBuf<int4> hdr; DevBuf<int> cstart, cM; DevBuf<float4> cA, cB, cN; DevBuf<ContactLP> lp; } mb[2];
@@ -143,12 +143,6 @@ struct avbd_world {
         return 0;
     }
     VisitGeom vgeom() { VisitGeom g; g.a = vgA.p; g.b = vgB.p; g.n = vgN.p; return g; }
-    ContactStage stage() { ContactStage c; c.cA = stA.p; c.cB = stB.p; c.cN = stN.p; c.lp = stLP.p; return c; }
-    int ensure_stage(size_t m) {
-        TRY(stA.ensure(4 * m, false, stream)); TRY(stB.ensure(4 * m, false, stream)); TRY(stN.ensure(4 * m, false, stream));
-        TRY(stLP.ensure(4 * m, false, stream));
-        return 0;
-    }
     BodyView bview() {
         BodyView v; v.pose = pose.p; v.aux = aux.p; v.vel = vel.p; v.init = init.p; v.prevLin = prevLin.p; v.size = size.p;
         v.flags = flags.p; v.worldId = worldId.p; v.localIdx = localIdx.p; v.n = n;
@@ -395,20 +389,18 @@ int run_collide(avbd_world* w) {
     int nSurv = w->nCand;
     int nxt = w->cur ^ 1;
     if (nSurv > 0) {
-        TRY(w->ensure_manifolds(nxt, nSurv)); TRY(w->ensure_stage(nSurv));
-        TRY(w->mcount.ensure((size_t)nSurv + 1, false, s));
-        CK(cudaMemsetAsync(w->mcount.p + nSurv, 0, sizeof(int), s));
+        TRY(w->ensure_manifolds(nxt, nSurv));
         static bool polySmem[64] = {false};          // a function attribute is per device
         if (!polySmem[w->device & 63]) {
             cudaFuncSetAttribute(np_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kBuildThreads * kPolyFloatsPerThread * (int)sizeof(float));
             polySmem[w->device & 63] = true;
         }
-        launch_dep(np_build, dim3(blocks_for(nSurv, kBuildThreads)), dim3(kBuildThreads), kBuildThreads * kPolyFloatsPerThread * sizeof(float), s, 
-            w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift, w->mset(w->cur), w->nM, w->mset(nxt), w->stage(), w->mcount.p, w->prm, w->dCnt);
-        w->launches++;
-        // live contacts packed densely in manifold order (the dual's and the visit lists' index space)
-        TRY(exclusive_scan(w, w->mcount.p, w->mset(nxt).cstart, nSurv + 1));
-        launch_dep(np_compact, dim3(blocks_for(4ll * nSurv)), dim3(kThreads), 0, s, w->mset(nxt).hdr, w->mset(nxt).cstart, nSurv, w->stage(), w->mset(nxt), w->dCnt);
+        // contacts go straight to their dense place, in manifold order (chained scan over the build's blocks)
+        int buildBlocks = blocks_for(nSurv, kBuildThreads);
+        TRY(w->buildTiles.ensure((size_t)buildBlocks, false, s));
+        CK(cudaMemsetAsync(w->buildTiles.p, 0, (size_t)buildBlocks * sizeof(unsigned long long), s));
+        launch_dep(np_build, dim3(buildBlocks), dim3(kBuildThreads), kBuildThreads * kPolyFloatsPerThread * sizeof(float), s,
+            w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift, w->mset(w->cur), w->nM, w->mset(nxt), w->prm, w->dCnt, w->buildTiles.p);
         w->launches++;
         TRY(read_counters(w));
         w->nContacts = w->hCnt->nContacts;
@@ -788,7 +780,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
     w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release(); w->deg.release(); w->estart.release(); w->colCursor.release(); w->entries.release(); w->sweepRange.release(); w->colVisit.release(); w->freeList.release(); w->linkedList.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
-    w->mcount.release(); w->stA.release(); w->stB.release(); w->stN.release(); w->stLP.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
+    w->mcount.release(); w->buildTiles.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
     for (auto& e : w->pev) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
     if (w->hCnt) cudaFreeHost(w->hCnt);

@@ -274,34 +274,63 @@ __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int 
 // K3b: build the manifold of each surviving pair at its final (key-sorted) slot, carrying lambda / penalty / stick
 // anchors over from last step's manifold of the same pair, then apply the per-step warm-start decay.  One thread per
 // manifold; nothing is held in per-thread arrays (the clipper's polygons and the raw contacts live in shared memory, one
-// column per thread); finished contacts go to the 4-slot staging arrays and np_compact then packs the live ones densely.
+// column per thread).  Contacts are written DENSELY, straight to their final place, in manifold order: once a block's raw
+// contacts are parked its contact counts are scanned, and the block learns where its range starts from a single-pass chained scan
+// over the blocks (decoupled look-back: every block publishes its total at once, then adds up its predecessors' totals until it
+// meets one whose inclusive prefix is already known) — cstart[m] = where manifold m's contacts start.  No staging copy, no
+// separate scan or compaction pass, and the placement is deterministic (the graph of a step whose topology did not change is
+// re-used, and its visit lists hold contact indices).
 constexpr int kBuildThreads = 128;
+// tile[b] = (status << 32) | value; status 0 not ready, 1 the block's own total, 2 the inclusive prefix up to and including the block.
+// Blocks are dispatched in index order, so a predecessor a block waits on is always resident or done.
+__device__ __forceinline__ int chained_block_prefix(unsigned long long* tile, int block, int total) {
+    const int lane = threadIdx.x & 31;            // called by the whole first warp
+    if (block == 0) {
+        if (lane == 0) atomicExch(&tile[0], (2ull << 32) | (unsigned)total);
+        return 0;
+    }
+    if (lane == 0) atomicExch(&tile[block], (1ull << 32) | (unsigned)total);
+    int exclusive = 0;
+    for (int start = block - 1;; start -= 32) {
+        const int idx = start - lane;
+        unsigned long long v;
+        do {
+            v = idx >= 0 ? *(volatile unsigned long long*)&tile[idx] : (2ull << 32);
+        } while (__any_sync(0xffffffffu, (v >> 32) == 0ull));
+        const unsigned incl = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
+        const int stop = incl ? __ffs(incl) - 1 : 31;                 // nearest predecessor whose inclusive prefix is known
+        int val = lane <= stop ? (int)(unsigned)(v & 0xffffffffull) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+        exclusive += val;
+        if (incl) break;
+    }
+    if (lane == 0) atomicExch(&tile[block], (2ull << 32) | (unsigned)(exclusive + total));
+    return exclusive;
+}
 __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsigned long long* cand, const int* info, int nSurvive,
-                                                          int keyShift, ManifoldSet old, int nOld, ManifoldSet out, ContactStage st, int* mcount,
-                                                          SolveParams prm, Counters* cnt) {
+                                                          int keyShift, ManifoldSet old, int nOld, ManifoldSet out,
+                                                          SolveParams prm, Counters* cnt, unsigned long long* tile) {
     cudaGridDependencySynchronize();
     extern __shared__ float sPoly[];
+    __shared__ int sWarpTotal[kBuildThreads / 32], sBase;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nSurvive) return;
-    unsigned long long k = cand[s];
+    const bool inRange = s < nSurvive;
+    unsigned long long k = inRange ? cand[s] : 0ull;
     int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
-    out.key[s] = k;
-    if (s > 0 && cand[s - 1] == k) {      // the sweeps emit every pair once; a repeat would double a manifold: keep a dead slot, flag it
-        atomicOr(&cnt->overflow, 8);
-        out.hdr[s] = make_int4(a, c, 0, 0); mcount[s] = 0;
-        return;
+    bool build = inRange;
+    if (inRange) {
+        out.key[s] = k;
+        if (s > 0 && cand[s - 1] == k) {      // the sweeps emit every pair once; a repeat would double a manifold: keep a dead slot, flag it
+            atomicOr(&cnt->overflow, 8);
+            build = false;
+        }
     }
-    BodyPose pa = b.pose[a], pb = b.pose[c];
-    float4 sa = b.size[a], sb = b.size[c];
-    V3 posA = xyz(pa.pos), posB = xyz(pb.pos); Q4 rotA = quat(pa.rot), rotB = quat(pb.rot);
-    int oldN = 0, oldBase = 0;
+    BodyPose pa{}, pb{}; float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+    V3 posA = zero3(), posB = zero3(); Q4 rotA = qid(), rotB = qid();
+    int oldN = 0, oldBase = 0, slot = -1;
     int oldFeat[4] = {0, 0, 0, 0};
-    int slot = find_key(old.key, nOld, k);
-    if (slot >= 0) {
-        oldN = old.hdr[slot].z; oldBase = old.cstart[slot];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) if (j < oldN) oldFeat[j] = f2i(old.lp[oldBase + j].p.w);
-    }
     // Two passes so the expensive half runs converged: the builder's loops (clip, dedupe) reach their emit at different
     // trip counts in every lane, so finishing a contact inside emit would serialise the lanes; emit only parks the raw contact
     // (10 floats) in the clipper's second polygon buffer, which is free once the clipped polygon sits in the first, and a
@@ -310,44 +339,60 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
     float* raw = sPoly + threadIdx.x + (size_t)(kMaxPoly * 3) * blockDim.x;            // buffer 1, this thread's column
     const int rs = (int)blockDim.x;
     int n = 0;
-    auto emit = [&](int feature, V3 rA, V3 rB, V3 normal) {
-        float* q = raw + (size_t)(n * 10) * rs;
-        q[0] = i2f(feature); q[rs] = rA.x; q[2 * rs] = rA.y; q[3 * rs] = rA.z; q[4 * rs] = rB.x; q[5 * rs] = rB.y; q[6 * rs] = rB.z;
-        q[7 * rs] = normal.x; q[8 * rs] = normal.y; q[9 * rs] = normal.z;
-        ++n;
-    };
-    build_contacts_emit(posA, rotA, xyz(sa), posB, rotB, xyz(sb), info[s], poly, emit);
+    if (build) {
+        pa = b.pose[a]; pb = b.pose[c];
+        sa = b.size[a]; sb = b.size[c];
+        posA = xyz(pa.pos); posB = xyz(pb.pos); rotA = quat(pa.rot); rotB = quat(pb.rot);
+        slot = find_key(old.key, nOld, k);
+        if (slot >= 0) {
+            oldN = old.hdr[slot].z; oldBase = old.cstart[slot];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < oldN) oldFeat[j] = f2i(old.lp[oldBase + j].p.w);
+        }
+        auto emit = [&](int feature, V3 rA, V3 rB, V3 normal) {
+            float* q = raw + (size_t)(n * 10) * rs;
+            q[0] = i2f(feature); q[rs] = rA.x; q[2 * rs] = rA.y; q[3 * rs] = rA.z; q[4 * rs] = rB.x; q[5 * rs] = rB.y; q[6 * rs] = rB.z;
+            q[7 * rs] = normal.x; q[8 * rs] = normal.y; q[9 * rs] = normal.z;
+            ++n;
+        };
+        build_contacts_emit(posA, rotA, xyz(sa), posB, rotB, xyz(sb), info[s], poly, emit);
+    }
+    // this block's range of the dense contact arrays: warp scan of the counts, block total, one atomic
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+    if (lane == 31) sWarpTotal[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int tot = 0, mine = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kBuildThreads / 32; ++w2) { int t = sWarpTotal[w2]; if (lane == w2) mine = tot; tot += t; }
+        int base = chained_block_prefix(tile, (int)blockIdx.x, tot);
+        __syncwarp();
+        if (lane < kBuildThreads / 32) sWarpTotal[lane] = mine;
+        if (lane == 0) { sBase = base; if (blockIdx.x == gridDim.x - 1) cnt->nContacts = base + tot; }
+    }
+    __syncthreads();
+    const int first = sBase + sWarpTotal[warp] + incl - n;
+    if (!inRange) return;
     unsigned used = 0u;
     auto loadOld = [&](int j) { return load_contact(old, oldBase + j); };
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-        if (c < n) {
-            const float* q = raw + (size_t)(c * 10) * rs;
+    for (int cc = 0; cc < 4; ++cc) {
+        if (cc < n) {
+            const float* q = raw + (size_t)(cc * 10) * rs;
             ContactState ct = contact_initialize(posA, rotA, posB, rotB, f2i(q[0]), mk3(q[rs], q[2 * rs], q[3 * rs]), mk3(q[4 * rs], q[5 * rs], q[6 * rs]),
                                                  mk3(q[7 * rs], q[8 * rs], q[9 * rs]), oldN, oldFeat, used, loadOld, prm);
-            int ci = s * 4 + c;
-            st.cA[ci] = f4(ct.rA, ct.C0n); st.cB[ci] = f4(ct.rB, ct.C0t1); st.cN[ci] = f4(ct.n, ct.C0t2);
-            ContactLP lpq; lpq.l = pack_lambda(ct); lpq.p = pack_penalty(ct); st.lp[ci] = lpq;
+            int ci = first + cc;
+            out.cA[ci] = f4(ct.rA, ct.C0n); out.cB[ci] = f4(ct.rB, ct.C0t1); out.cN[ci] = f4(ct.n, ct.C0t2);
+            ContactLP lpq; lpq.l = pack_lambda(ct); lpq.p = pack_penalty(ct); out.lp[ci] = lpq;
+            out.cM[ci] = s;
         }
     }
-    float mu = sqrtf(sa.w * sb.w);                                   // manifold.cpp:73
+    float mu = build ? sqrtf(sa.w * sb.w) : 0.0f;                                   // manifold.cpp:73
     out.hdr[s] = make_int4(a, c, n, __float_as_int(mu));
-    mcount[s] = n;
-    if (slot != s || oldN != n) cnt->topoChanged = 1;      // same-value racing stores are fine
-}
-
-// K3c: pack the live contacts of the staging slots densely (ci = cstart[m] + c) and record each contact's manifold.
-// cstart is the exclusive scan of mcount over nM + 1 entries (mcount[nM] = 0), so cstart[nM] is the live contact count.
-__global__ void np_compact(const int4* hdr, const int* cstart, int nM, ContactStage st, ManifoldSet out, Counters* cnt) {
-    cudaGridDependencySynchronize();
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 4 * nM) return;
-    int m = t >> 2, c = t & 3;
-    if (t == 0) cnt->nContacts = cstart[nM];
-    if (c >= hdr[m].z) return;
-    int d = cstart[m] + c;
-    out.cA[d] = st.cA[t]; out.cB[d] = st.cB[t]; out.cN[d] = st.cN[t]; out.lp[d] = st.lp[t];
-    out.cM[d] = m;
+    out.cstart[s] = first;
+    if (build && (slot != s || oldN != n)) cnt->topoChanged = 1;      // same-value racing stores are fine
 }
 
 // Stand-alone narrowphase on caller-supplied pairs (parity harness for

@@ -435,10 +435,10 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
 //               inertial terms, Schur 3x3 LDL^T, pose update (solver.cpp:351-369, :402-408) — no per-body sums round trip through
 //               HBM, no second kernel, and the serial 6x6 solve runs with most lanes busy.
 #ifndef AVBD_VG_REG
-#define AVBD_VG_REG 1        // visit-order geometry: 1 = coalesced loads into registers, 0 = cp.async into the stage
+#define AVBD_VG_REG 0        // visit-order geometry: 1 = coalesced loads into registers, 0 = cp.async into the stage
 #endif
 #ifndef AVBD_LP_REG
-#define AVBD_LP_REG 1        // lambda / penalty: 1 = lane-pair loads into registers + shuffle, 0 = cp.async into the stage
+#define AVBD_LP_REG 0        // lambda / penalty: 1 = lane-pair loads into registers + shuffle, 0 = cp.async into the stage
 #endif
 #ifndef AVBD_SELF_SEG
 #define AVBD_SELF_SEG 1      // visiting-body pose: 1 = one cp.async per segment (broadcast read), 0 = one per lane

@@ -7,7 +7,8 @@
 //   vel[i]   {lin | ang}, init[i] {pos0 | rot0}, prevLin[i], size[i] {sx,sy,sz,friction}
 // Manifolds (replaces 704-byte Manifold nodes, solver.h:112-143), slot m, sorted by pair key:
 //   mhdr[m]  {bodyA, bodyB, numContacts, friction-bits}     16 B
-//   cstart[m] first contact of manifold m; contacts are stored DENSE (ci = cstart[m] + c, live contacts only, about 2 per
+//   cstart[m] first contact of manifold m; contacts are stored DENSE (ci = cstart[m] + c, live contacts only, written in place by the
+//   manifold build, about 2 per
 //   manifold on a box pile — a fixed 4-slot layout made every 64-byte DRAM granule half dead), one float4 per field:
 //     cA {rA.xyz, C0_n}  cB {rB.xyz, C0_t.x}  cN {normal.xyz, C0_t.y}
 //     lp {lambda_n, lambda_t1, lambda_t2, stick | penalty_n, penalty_t1, penalty_t2, feature-bits}   32 B = one sector: the
@@ -41,9 +42,6 @@ struct ManifoldSet {          // one of the two ping-pong generations
     int4*   hdr;
     int*    cstart;           // nM + 1 entries
     int*    cM;               // per dense contact
-    float4* cA; float4* cB; float4* cN; ContactLP* lp;
-};
-struct ContactStage {         // np_build's output before compaction: 4 slots per manifold (ci = 4*m + c)
     float4* cA; float4* cB; float4* cN; ContactLP* lp;
 };
 
