@@ -95,7 +95,7 @@ struct avbd_world {
     DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;      // per-contact visit lists: small worlds (cluster loop) only
     DevBuf<int> deg, estart, colCursor, sweepRange, freeList, linkedList; DevBuf<int4> entries; DevBuf<int2> colVisit; DevBuf<float4> vgA, vgB, vgN;
     int2 hColVisit[64]; int sweepWarps[64] = {0}, sweepOff[64] = {0};      // per colour: its visit range, warps of the sweep, offset of its warp ranges
-    int nFree = 0, nLinkedFree = 0; bool visitGeomStale = true;            // contact geometry in visit order (VisitGeom), refreshed once per step
+    int nFree = 0, nLinkedFree = 0; bool visitGeomStale = true, sweepRangesValid = false;            // contact geometry in visit order (VisitGeom), refreshed once per step
          // body -> manifold entries CSR (graph stage): colouring adjacency + the large-world sweep's work list
 
     // manifolds (ping-pong)
@@ -432,6 +432,23 @@ int run_predict(avbd_world* w) {
     return 0;
 }
 
+// Body-aligned warp ranges of every colour's visits (avbd_solve.cu: warp_ranges), one launch, no host wait.
+int build_sweep_ranges(avbd_world* w) {
+    cudaStream_t s = w->stream;
+    int total = 0;
+    for (int c = 0; c < w->nColours; ++c) {
+        int nv = w->hColVisit[c].y - w->hColVisit[c].x;
+        w->sweepWarps[c] = nv > 0 ? primal_sweep_warps(nv) : 0;
+        w->sweepOff[c] = total; total += w->sweepWarps[c] + 1;
+    }
+    TRY(w->sweepRange.ensure((size_t)std::max(1, total), false, s));
+    int nw[64], off[64];
+    for (int c = 0; c < 64; ++c) { nw[c] = c < w->nColours ? std::max(1, w->sweepWarps[c]) : 1; off[c] = c < w->nColours ? w->sweepOff[c] : 0; }
+    if (w->nColours > 0 && w->nContacts > 0) { launch_warp_ranges(s, w->visitStart.p, w->colRange.p, w->nColours, nw, off, w->sweepRange.p); w->launches++; }
+    w->sweepRangesValid = true;
+    return 0;
+}
+
 int run_colour(avbd_world* w) {
     cudaStream_t s = w->stream;
     TRY(prepare(w));
@@ -557,19 +574,9 @@ int run_colour(avbd_world* w) {
     w->nFree = w->hCnt->nFree; w->nLinkedFree = w->hCnt->nLinkedFree;
     w->maxColourCount = 0;
     for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);
-    // the sweeps' body-aligned warp ranges, every colour in one launch (device only: nothing below waits on it)
-    {
-        int total = 0;
-        for (int c = 0; c < w->nColours; ++c) {
-            int nv = w->hColVisit[c].y - w->hColVisit[c].x;
-            w->sweepWarps[c] = nv > 0 ? primal_sweep_warps(nv) : 0;
-            w->sweepOff[c] = total; total += w->sweepWarps[c] + 1;
-        }
-        TRY(w->sweepRange.ensure((size_t)std::max(1, total), false, s));
-        int nw[64], off[64];
-        for (int c = 0; c < 64; ++c) { nw[c] = c < w->nColours ? std::max(1, w->sweepWarps[c]) : 1; off[c] = c < w->nColours ? w->sweepOff[c] : 0; }
-        if (w->nColours > 0 && w->nContacts > 0) { launch_warp_ranges(s, w->visitStart.p, w->colRange.p, w->nColours, nw, off, w->sweepRange.p); w->launches++; }
-    }
+    // the sweeps' body-aligned warp ranges: built at once for a large world, on first use for a world the cluster loop takes
+    w->sweepRangesValid = false;
+    if (w->nDyn > w->persistentMaxBodies || w->fview().nJoints + w->fview().nSprings > 0 || w->profiling) TRY(build_sweep_ranges(w));
     w->graphValid = true;
     CK(cudaGetLastError());
     return 0;
@@ -584,6 +591,7 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float biasDual = -1.0f)
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
+    if (!w->sweepRangesValid) TRY(build_sweep_ranges(w));
     if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
         size_t cap = w->visits.cap;
         TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));

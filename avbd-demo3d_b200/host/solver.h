@@ -96,6 +96,7 @@ struct Solver {                      // solver.h:146-181
     bool readBack;                   // true (default): step() refreshes every Rigid from the device; false: only on fetchState()
     bool uploadAll;                  // treat every body as edited before each step (exercises the full-upload path)
     void fetchState();               // device -> Rigid fields (what step() does when readBack is set)
+    void fetchStateImpl(bool advancePrev);
     std::vector<Rigid*> order;       // live bodies by creation order
     std::vector<Rigid*> deviceOrder; // bodies as the device world indexes them (nullptr: deleted since the upload)
     float* shadow; size_t shadowCap; // pinned host copy of the last state exchanged with the device (13 floats per body)

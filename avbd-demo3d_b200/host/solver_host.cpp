@@ -15,7 +15,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 namespace {
@@ -275,21 +278,70 @@ void pack_body(const Rigid* b, float* o) {
     o[7] = b->linearVelocity.x; o[8] = b->linearVelocity.y; o[9] = b->linearVelocity.z;
     o[10] = b->angularVelocity.x; o[11] = b->angularVelocity.y; o[12] = b->angularVelocity.z;
 }
-// Slices [begin, end) of n items over a few host threads (a million Rigid nodes are 264 MB of scattered heap: one thread
-// walking them was most of Solver::step()'s host time).  fn(begin, end, slice).
+// Slices [begin, end) of n items over a few host threads (a million Rigid nodes are ~270 MB of heap: one thread walking them was
+// most of Solver::step()'s host time).  fn(begin, end, slice).  The workers are created once and parked on a condition variable:
+// spawning 16 threads per pass cost more than a small world's whole step.
+class SlicePool {
+public:
+    static SlicePool& get() { static SlicePool p; return p; }
+    int workers() const { return (int)threads_.size() + 1; }
+    void run(int n, int slices, const std::function<void(int, int, int)>& fn) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn; n_ = n; slices_ = slices; next_ = 1; pending_ = slices - 1; ++gen_;
+        }
+        cv_.notify_all();
+        fn(0, (int)((long long)n / slices), 0);                        // the caller takes slice 0
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    SlicePool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int want = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+        if (const char* e = std::getenv("AVBD_HOST_THREADS")) want = std::max(1, std::atoi(e));
+        for (int t = 1; t < want; ++t) threads_.emplace_back([this] { loop(); });
+    }
+    ~SlicePool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            while (fn_ && next_ < slices_) {
+                int t = next_++;
+                const std::function<void(int, int, int)>* fn = fn_;
+                int b = (int)((long long)n_ * t / slices_), e = (int)((long long)n_ * (t + 1) / slices_);
+                lk.unlock();
+                (*fn)(b, e, t);
+                lk.lock();
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int, int)>* fn_ = nullptr;
+    int n_ = 0, slices_ = 0, next_ = 0, pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
 template <class Fn>
 void parallel_slices(int n, int& slices, Fn fn) {
-    unsigned hw = std::thread::hardware_concurrency();
-    int want = n >= 65536 ? (int)std::min<unsigned>(hw ? hw : 1u, 16u) : 1;
-    if (const char* e = std::getenv("AVBD_HOST_THREADS")) want = std::max(1, std::atoi(e));
-    slices = want;
-    if (want == 1) { fn(0, n, 0); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < want; ++t) {
-        int b = (int)((long long)n * t / want), e = (int)((long long)n * (t + 1) / want);
-        th.emplace_back([=] { fn(b, e, t); });
-    }
-    for (auto& x : th) x.join();
+    if (n < 65536) { slices = 1; fn(0, n, 0); return; }
+    SlicePool& pool = SlicePool::get();
+    slices = pool.workers();
+    if (slices == 1) { fn(0, n, 0); return; }
+    std::function<void(int, int, int)> f = fn;
+    pool.run(n, slices, f);
 }
 void ensure_shadow(Solver* s, size_t bodies) {
     if (bodies * 13 <= s->shadowCap) return;
@@ -484,7 +536,11 @@ void Solver::syncToDevice() {
     }
 }
 
-void Solver::fetchState() {
+void Solver::fetchState() { fetchStateImpl(false); }
+
+// device -> Rigid fields; advancePrev: the step just taken makes the old velocities the "previous" ones (solver.cpp:457-458) — done
+// in the same walk over the bodies, every Rigid is touched once.
+void Solver::fetchStateImpl(bool advancePrev) {
     int n = (int)order.size();
     if (n == 0 || !world) return;
     check(avbd_download_state(world, shadow), "avbd_download_state");
@@ -493,6 +549,7 @@ void Solver::fetchState() {
     parallel_slices(n, slices, [&](int b0, int e0, int) {
         for (int i = b0; i < e0; ++i) {
             Rigid* b = order[i]; const float* o = shadow + (size_t)i * 13;
+            if (advancePrev && b->invMass > 0.0f) { b->prevLinearVelocity = b->linearVelocity; b->prevAngularVelocity = b->angularVelocity; }
             b->position = vec3(o[0], o[1], o[2]); b->orientation = quat(o[3], o[4], o[5], o[6]);
             b->linearVelocity = vec3(o[7], o[8], o[9]); b->angularVelocity = vec3(o[10], o[11], o[12]);
         }
@@ -505,14 +562,7 @@ void Solver::step() {                                                    // solv
     ++stepIndex;
     mirrorsFresh = false;
     check(avbd_step(world, 1), "avbd_step");
-    if (n > 0 && readBack) {
-        // previous velocities (solver.cpp:457-458) are last step's values the host already holds
-        int slices = 1;
-        parallel_slices(n, slices, [&](int b0, int e0, int) {
-            for (int i = b0; i < e0; ++i) { Rigid* b = order[i]; if (b->invMass > 0.0f) { b->prevLinearVelocity = b->linearVelocity; b->prevAngularVelocity = b->angularVelocity; } }
-        });
-        fetchState();
-    }
+    if (n > 0 && readBack) fetchStateImpl(true);
     // lambda / penalty of the user forces' rows, as the reference leaves them in the public arrays after a step
     if (!userForces.empty()) {
         int nj = avbd_num_joints(world), ns = avbd_num_springs(world);
