@@ -599,15 +599,21 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float biasDual = -1.0f)
         w->launches++;
     }
     w->visitGeomStale = false;
-    if (w->nFree > 0) { launch_primal_free(s, w->bview(), fv, w->freeList.p, w->nFree, w->colour.p, -1, w->prm, dxDev, w->dDiag.p); w->launches++; }
+    int freeLeft = w->nFree;                 // ride on the first sweep launch of the pass
     for (int c = 0; c < w->nColours; ++c) {
         int count = w->hColRange[c].y - w->hColRange[c].x;
         if (count <= 0) continue;
         if (w->nLinkedFree > 0) { launch_primal_free(s, w->bview(), fv, w->linkedList.p, w->nLinkedFree, w->colour.p, c, w->prm, dxDev, w->dDiag.p); w->launches++; }
-        if (w->sweepWarps[c] > 0) {
-            launch_primal_sweep(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->sweepRange.p + w->sweepOff[c], w->sweepWarps[c], w->prm, alpha, biasDual, dxDev, w->dDiag.p);
+        if (w->sweepWarps[c] > 0 || freeLeft > 0) {
+            launch_primal_sweep(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->sweepRange.p + w->sweepOff[c], w->sweepWarps[c], w->prm, alpha, biasDual, dxDev, w->dDiag.p,
+                                w->freeList.p, freeLeft);
             w->launches++;
+            freeLeft = 0;
         }
+    }
+    if (freeLeft > 0) {                      // no colour at all (nothing but free bodies cannot happen: every dynamic body has a colour), kept for safety
+        launch_primal_sweep(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->sweepRange.p, 0, w->prm, alpha, biasDual, dxDev, w->dDiag.p, w->freeList.p, freeLeft);
+        w->launches++;
     }
     CK(cudaGetLastError());
     return 0;
@@ -665,43 +671,42 @@ int step_once(avbd_world* w) {
                                        w->nColours, w->maxColourCount, w->nContacts, w->prm, w->dDiag.p, fuseDiag, w->anyUnvisited);
         if (persistent) { w->launches++; w->contactDiagDone = fuseDiag; } else cudaGetLastError();
     }
-    if (prof) {
-        while ((int)w->pev.size() < 2 * total + 1) { cudaEvent_t e; CK(cudaEventCreate(&e)); w->pev.push_back(e); }
-        cudaEventRecord(w->pev[0], s);
-    }
+    // Profiling: the iteration loop is timed as a whole (stage events 4 -> 5) and only the stand-alone dual launches are bracketed by
+    // their own events — an event between every pair of sweeps would serialise launches that otherwise overlap (programmatic
+    // dependent launch) and inflate the very thing it measures.  ms_primal = loop - stand-alone duals.
+    if (prof) while ((int)w->pev.size() < 2 * total + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); w->pev.push_back(e); }
     // Deferred dual: the manifold rows' dual pass of iteration k rides on sweep k+1 (each contact's first visit applies it);
     // only the pass after the LAST sweep runs as a kernel.  AVBD_SEPARATE_DUAL=1 keeps one dual launch per iteration.
     const char* sepEnv = getenv("AVBD_SEPARATE_DUAL");
     const bool separateDual = sepEnv && atoi(sepEnv) != 0;
-    int duals = 0, deferred = 0;
+    int duals = 0, deferred = 0, timedDuals = 0;
     float pendingBias = -1.0f;
     for (int it = 0; it < total && !persistent; ++it) {
         float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
         TRY(run_primal(w, a, nullptr, pendingBias));
         if (pendingBias >= 0.0f) ++deferred;
         pendingBias = -1.0f;
-        if (prof) cudaEventRecord(w->pev[2 * it + 1], s);
         if (it < w->prm.iterations) {
             bool lastSweep = it == total - 1;                 // nothing moves after this pass: it also reduces the contact diagnostics
+            bool standalone = separateDual || lastSweep;
+            if (prof && standalone) cudaEventRecord(w->pev[2 * timedDuals], s);
             if (separateDual) { TRY(run_dual(w, a, lastSweep)); ++duals; }
             else if (lastSweep) { TRY(run_dual(w, a, true, true, w->prm.iterations, false)); ++duals; }
             else { TRY(run_dual(w, a, false, false)); pendingBias = dual_bias(a); }
+            if (prof && standalone) { cudaEventRecord(w->pev[2 * timedDuals + 1], s); ++timedDuals; }
         } else if (!separateDual && w->anyUnvisited && w->prm.iterations > 0) {
             TRY(run_dual(w, 1.0f, false, true, w->prm.iterations, true));    // postStabilize: contacts between static bodies only
         }
-        if (prof) cudaEventRecord(w->pev[2 * it + 2], s);
     }
     if (w->timed || w->profiling) cudaEventRecord(w->ev[5], s);
     TRY(run_velocity(w));
     if (w->timed || w->profiling) cudaEventRecord(w->ev[6], s);
     if (prof) {
         CK(cudaStreamSynchronize(s));
-        for (int it = 0; it < total; ++it) {
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, w->pev[2 * it], w->pev[2 * it + 1]);
-            cudaEventElapsedTime(&b, w->pev[2 * it + 1], w->pev[2 * it + 2]);
-            w->prof.ms_primal += a; w->prof.ms_dual += b;
-        }
+        float loopMs = 0.0f, dualMs = 0.0f;
+        cudaEventElapsedTime(&loopMs, w->ev[4], w->ev[5]);
+        for (int k = 0; k < timedDuals; ++k) { float b = 0; cudaEventElapsedTime(&b, w->pev[2 * k], w->pev[2 * k + 1]); dualMs += b; }
+        w->prof.ms_primal += loopMs - dualMs; w->prof.ms_dual += dualMs;
         long long contacts = 0, visits = 0;
         for (int k = 0; k < w->nWorlds && w->hDiag; ++k) { contacts += w->hDiag[k].activeContacts; visits += w->hDiag[k].contactVisits; }
         w->prof.steps += 1;

@@ -129,10 +129,12 @@ constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodie
 // mean "nothing pending" (plain primal sweep).
 int primal_sweep_warps(int nVisits);
 void launch_warp_ranges(cudaStream_t s, const int* vstart, const int2* colRange, int nColours, const int* nWarps, const int* off, int* range);
+// freeList / nFree: bodies no contact visits and no user force touches; extra warps of THIS launch solve them (pass them with one
+// colour per sweep).
 void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* range, int nWarps, SolveParams prm,
-                         float alpha, float biasDual, float* dxOut, Diag* diag);
-// Dynamic bodies no contact visits (listed by the graph stage).  onlyColour < 0: the list of bodies no user force touches, one
-// launch per sweep; onlyColour >= 0: the list of bodies a joint / spring links to another body, filtered to that colour.
+                         float alpha, float biasDual, float* dxOut, Diag* diag, const int* freeList, int nFree);
+// Dynamic bodies no contact visits that a joint / spring links to another body (listed by the graph stage), filtered to one colour
+// (onlyColour < 0: no filter).
 void launch_primal_free(cudaStream_t s, BodyView b, ForceView fv, const int* freeList, int nFree, const int* colour, int onlyColour, SolveParams prm,
                         float* dxOut, Diag* diag);
 // Dual + penalty ramp over the nContacts live (densely stored) contacts.

@@ -480,6 +480,24 @@ __device__ __forceinline__ float4 ld4_keep_cg(const float4* ptr, unsigned long l
     return v;
 }
 
+// A body no contact visits: inertial terms (plus user forces) -> 6x6 solve -> pose update (solver.cpp:351-369, :402-408).
+__device__ __forceinline__ void solve_free_body(const BodyView& b, const ForceView& fv, int i, const SolveParams& prm, float* dxOut, Diag* diag,
+                                                unsigned long long keep) {
+    BodyPose self = load_pose_keep(b.pose + i, keep);
+    BodyAux aux = b.aux[i];
+    V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
+    BodySystem own; M3 invIw;
+    body_self_system(pos, rot, aux, prm.dt, own, invIw);
+    if (fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i]) accumulate_user_forces(own, fv, b.pose, i, pos, rot, invIw);
+    V3 dl, da;
+    solve_body_system(own, dl, da);
+    int evn = apply_body_update(pos, rot, dl, da);
+    st4_keep(&b.pose[i].pos, f4(pos, self.pos.w), keep);
+    st4_keep(&b.pose[i].rot, f4(rot), keep);
+    if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
+    if (evn) atomicAdd(&diag[b.worldId[i]].nanEvents, evn);
+}
+
 // One body per lane (lanes [0, qn)): queued row sums + inertial terms -> 6x6 solve -> pose update.
 __device__ __forceinline__ void solve_queue(WarpPipe& w, int qn, int lane, const BodyView& b, const ForceView& fv, const SolveParams& prm,
                                             float* dxOut, Diag* diag, unsigned long long keep) {
@@ -514,11 +532,22 @@ __device__ __forceinline__ void solve_queue(WarpPipe& w, int qn, int lane, const
 template <int MINB>
 __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
                                                                            const int* __restrict__ range, int nWarps, SolveParams prm,
-                                                                           float alpha, float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag) {
+                                                                           float alpha, float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag,
+                                                                           const int* __restrict__ freeList, int nFree) {
     __shared__ WarpPipe pipes[kSweepWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kSweepWarps + warp;
-    if (gw >= nWarps) return;                                  // no block-wide barrier anywhere in this kernel: a warp may leave on its own
+    if (gw >= nWarps) {                                        // no block-wide barrier anywhere in this kernel: a warp may leave on its own
+        // the warps past the colour's ranges (first colour of a sweep only) take the bodies no contact visits and no user force
+        // touches, one per lane: nothing they read is written by anyone else, so their colour does not matter
+        const int t = (gw - nWarps) * 32 + lane;
+        if (t < nFree) {
+            const int i = __ldg(freeList + t);
+            cudaGridDependencySynchronize();
+            solve_free_body(b, fv, i, prm, dxOut, diag, l2_keep_policy());
+        }
+        return;
+    }
     WarpPipe& w = pipes[warp];
     const unsigned long long keep = l2_keep_policy(), stream = l2_stream_policy();
     const int vBegin = __ldg(range + gw), vEnd = __ldg(range + gw + 1);      // written by the graph stage, many launches ago
@@ -658,30 +687,16 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
     if (qn > 0) solve_queue(w, qn, lane, b, fv, prm, dxOut, diag, keep);
 }
 
-// Dynamic bodies no contact visits: inertial terms (plus user forces) -> 6x6 solve -> pose update.  onlyColour < 0: the bodies no
-// user force touches either — nothing they read is written by anyone else, so one launch per sweep covers them whatever their
-// colour.  onlyColour >= 0: bodies a joint / spring links to another body, one colour per launch like every other body.
+// Dynamic bodies no contact visits that a joint / spring links to another body: inertial terms + user forces -> 6x6 solve -> pose
+// update, one colour per launch like every other body.  (The ones no user force touches ride on the first colour's sweep launch.)
 __global__ void __launch_bounds__(kThreads) primal_free_bodies(BodyView b, ForceView fv, const int* __restrict__ freeList, int nFree, const int* __restrict__ colour,
                                                                int onlyColour, SolveParams prm, float* __restrict__ dxOut, Diag* __restrict__ diag) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nFree) return;
     const int i = __ldg(freeList + t);
     if (onlyColour >= 0 && __ldg(colour + i) != onlyColour) return;
-    const unsigned long long keep = l2_keep_policy();
     cudaGridDependencySynchronize();
-    BodyPose self = load_pose_keep(b.pose + i, keep);
-    BodyAux aux = b.aux[i];
-    V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
-    BodySystem own; M3 invIw;
-    body_self_system(pos, rot, aux, prm.dt, own, invIw);
-    if (fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i]) accumulate_user_forces(own, fv, b.pose, i, pos, rot, invIw);
-    V3 dl, da;
-    solve_body_system(own, dl, da);
-    int evn = apply_body_update(pos, rot, dl, da);
-    st4_keep(&b.pose[i].pos, f4(pos, self.pos.w), keep);
-    st4_keep(&b.pose[i].rot, f4(rot), keep);
-    if (dxOut) { float* d = dxOut + 6 * i; d[0] = dl.x; d[1] = dl.y; d[2] = dl.z; d[3] = da.x; d[4] = da.y; d[5] = da.z; }
-    if (evn) atomicAdd(&diag[b.worldId[i]].nanEvents, evn);
+    solve_free_body(b, fv, i, prm, dxOut, diag, l2_keep_policy());
 }
 
 // Body-aligned warp ranges of every colour's visits, one launch: range[c][r] (r = 0 .. nWarps[c]) starts at the first body whose run
@@ -908,10 +923,10 @@ int primal_sweep_max_warps() {
     }
     return cache[dev];
 }
-// Warps a colour with nVisits contact visits is cut into: what is resident, at most one warp per 4 chunks of 32 visits (a warp's
-// pipeline needs a few chunks to be worth its prologue).
+// Warps a colour with nVisits contact visits is cut into: one per chunk of 32 visits until every resident slot is taken (a small
+// colour is latency bound: short ranges finish sooner), then longer ranges on the resident warps.
 int primal_sweep_warps(int nVisits) {
-    int want = (nVisits + 127) / 128;
+    int want = (nVisits + 31) / 32;
     int mx = primal_sweep_max_warps();
     return want < 1 ? 1 : (want < mx ? want : mx);
 }
@@ -927,13 +942,15 @@ void launch_primal_free(cudaStream_t s, BodyView b, ForceView fv, const int* fre
 }
 // One colour of the large-world sweep: its visits, cut into nWarps body-aligned warp ranges (range[0 .. nWarps]).
 void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* range, int nWarps, SolveParams prm,
-                         float alpha, float biasDual, float* dxOut, Diag* diag) {
-    if (nWarps <= 0) return;
-    dim3 grid(blocks_of(nWarps, kSweepWarps)), block(32 * kSweepWarps);
+                         float alpha, float biasDual, float* dxOut, Diag* diag, const int* freeList, int nFree) {
+    if (nWarps <= 0 && nFree <= 0) return;
+    if (nWarps < 0) nWarps = 0;
+    if (nFree < 0) nFree = 0;
+    dim3 grid(blocks_of(nWarps + (nFree + 31) / 32, kSweepWarps)), block(32 * kSweepWarps);
     switch (sweep_cfg()) {
-        case 3:  launch_dep(primal_sweep_warp<3>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag); break;
-        case 4:  launch_dep(primal_sweep_warp<4>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag); break;
-        default: launch_dep(primal_sweep_warp<5>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag); break;
+        case 3:  launch_dep(primal_sweep_warp<3>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree); break;
+        case 4:  launch_dep(primal_sweep_warp<4>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree); break;
+        default: launch_dep(primal_sweep_warp<5>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree); break;
     }
 }
 

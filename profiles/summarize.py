@@ -76,7 +76,7 @@ def traffic(path):
         elif "primal_solve" in r[ki]:
             if not done: solve += bytes_; ns += 1
         elif "dual_contacts" in r[ki]: dual += bytes_; nd += 1
-    sweeps = max(ns, 1)
+    sweeps = max(ns, nv, 1)          # the fused sweep kernel (round 2) has no separate solve launch: one launch = one colour sweep
     print(json.dumps({"source": path.split("/")[-1], "how": "ncu --set full --clock-control none (cold caches, serialised launches), 1M-box pre-stacked grid, the first iteration (every colour once) of one step",
                       "colour_sweeps_captured": sweeps, "visit_kernel_launches": nv, "dram_bytes_per_colour_sweep": (visit + solve) / sweeps,
                       "visit_kernel_bytes_per_colour_sweep": visit / sweeps, "solve_kernel_bytes_per_colour_sweep": solve / sweeps,

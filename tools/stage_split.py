@@ -9,8 +9,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 w = avbd.World()
 if name == "stress1000":
     scenes.load(w, scenes.scene("Stress1000")); w.step(400)
-elif name == "ensemble":
-    scenes.load(w, scenes.ensemble(scenes.scene("Pyramid"), 8192)); w.step(30)
+elif name.startswith("ensemble"):
+    scenes.load(w, scenes.ensemble(scenes.scene("Pyramid"), int(name[8:] or 8192))); w.step(30)
 else:
     n = int(name[4:])
     s = scenes.stress_grid(n, n, n, spacing_y=1.01, start_y=0.51, wide_ground=True); s["params"]["iterations"] = 10
