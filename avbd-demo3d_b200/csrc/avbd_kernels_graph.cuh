@@ -62,7 +62,7 @@ __global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, c
 }
 
 // ------------------------------------------------------------------ contact-visit lists
-// Contacts are stored densely (np_compact), so the dual walks them by index; the primal walks, per dynamic body, a run
+// Contacts are stored densely (written in place by np_build), so the dual walks them by index; the primal walks, per dynamic body, a run
 // of `visits` — one entry per live contact of every manifold touching the body, rebuilt whenever the topology changes.
 // Both run over the COLOUR-SORTED body order (colOrder[k], k = 0..nDyn-1): visitStart[k] is indexed by that position, so the
 // visits of the bodies of one colour tile are one contiguous run of `visits` and a tile can be walked one visit per thread.

@@ -89,7 +89,7 @@ __device__ __forceinline__ BodyPose load_pose_keep(const BodyPose* p, unsigned l
 // The large-world visit kernel is instruction-issue bound (ncu: ~45 % issue slots busy, DRAM at a third of peak), so the device
 // copy of the row math is written for instruction count.  Same formulas as avbd_rows.cuh (which the host mirror and the host
 // emulation build use, and which the parity tests compare this against), with:
-//   * the contact seen from the VISITING body: geometry arrives as {r_self, r_other, n} (visit_geometry swaps once per step) and
+//   * the contact seen from the VISITING body: geometry arrives as {r_self, r_other, n} (visit_geometry swaps once per step; the cluster loop swaps per visit) and
 //     the A/B orientation is one sign, sg — (pA + wA) - (pB + wB) = sg ((pS + wS) - (pO + wO)) exactly, so no operand selects;
 //   * clamps as fminf / fmaxf (one FMNMX each; a NaN operand yields the bound where the reference's ternary clamp passes the
 //     NaN on — NaN states are scrubbed by the pose update either way);
@@ -187,7 +187,7 @@ __device__ __forceinline__ void system_fast(BodySystem& s, const ContactState& c
 }
 // One contact visit in the visiting body's frame: computeConstraint (with the pending dual update first), then the 3 rows'
 // contribution to the body's 6x6 system.  `sp,sq` / `op,oq` = self / other pose, g0 g1 g2 = {r_self,C0n} {r_other,C0t.x} {n,C0t.y}.
-// Every solver kernel (flat visit kernel, cluster loop, dual pass) evaluates rows through these, so the deferred and the
+// Every solver kernel (sweep kernel, cluster loop, dual pass) evaluates rows through these, so the deferred and the
 // stand-alone dual agree to FMA-contraction rounding: `stick` is decided by comparing a just-clamped |lambda_t|^2 with lim^2, i.e.
 // by rounding, and a flipped `stick` changes friction by 10 % — two row-math variants would drift apart within a few steps.
 __device__ __forceinline__ float rows_geometry(float4 sp, float4 sq, float4 op, float4 oq, float sg, const ContactState& cs, ContactEval& ev, float (&sep)[3]) {

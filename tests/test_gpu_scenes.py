@@ -244,9 +244,9 @@ def test_ensemble_is_bit_identical_across_partitions(avbd, name, steps):
 
 
 def test_large_ensemble_is_bit_identical_across_partitions(avbd):
-    """The same at a size the per-colour kernels handle (800 Stack worlds = 8800 bodies, beyond the cluster loop's limit): the
-    flat visit kernel hands each block a body-aligned range of the visit list, so a body's rows are summed in one sequence
-    wherever the world sits in the batch — 800 worlds in one batch == two batches of 400, bit for bit."""
+    """The same at a size the per-colour sweep kernel handles (800 Stack worlds = 8800 bodies, beyond the cluster loop's limit): the
+    sweep hands each warp a body-aligned range of the visit list, so a body's rows are summed in one sequence wherever the world
+    sits in the batch — 800 worlds in one batch (sweep kernel) == two batches of 400 (cluster loop), bit for bit."""
     from avbd_demo3d_b200 import scenes
     base = scenes.scene("Stack")
     n = len(base["size"])
