@@ -106,7 +106,8 @@ struct avbd_world {
     DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
     int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
-    long long graphReuses = 0; int persistentMaxBodies = 4096;
+    long long graphReuses = 0; int persistentMaxBodies = 256;      // measured (tools/loop_modes.py): the cluster loop wins by 6-10 % up to a Wall (64 bodies), the per-colour sweep launches from Stress1000 up (+7 % at 1000 bodies, +66 % at 8000)
+    int loopMode = 0;      // AVBD_LOOP: 0 auto, 1 per-colour launches, 2 cooperative grid loop, 3 cluster loop where eligible
 
     // user forces
     std::vector<JointRec> hJoints; std::vector<SpringRec> hSprings; std::vector<HostForce> hForces;
@@ -663,7 +664,29 @@ int step_once(avbd_world* w) {
     int total = w->prm.iterations + (w->prm.postStabilize ? 1 : 0);
     bool prof = w->profiling;
     ForceView fvAll = w->fview();
-    bool persistent = !prof && w->nColours > 0 && w->nDyn <= w->persistentMaxBodies && fvAll.nJoints + fvAll.nSprings == 0;
+    const bool noUserForces = fvAll.nJoints + fvAll.nSprings == 0;
+    bool persistent = !prof && w->nColours > 0 && w->nDyn <= w->persistentMaxBodies && noUserForces && (w->loopMode == 0 || w->loopMode == 3);
+    bool gridLoop = !persistent && !prof && w->nColours > 0 && noUserForces && w->loopMode == 2 && w->prm.iterations > 0;
+    if (gridLoop) {
+        // the iteration loop in one cooperative launch of the sweep kernel's warp pipelines (grid barrier between colour phases)
+        if (!w->sweepRangesValid) TRY(build_sweep_ranges(w));
+        if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
+            size_t cap = w->visits.cap;
+            TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));
+            launch_dep(visit_geometry, dim3(blocks_for(2ll * w->nContacts)), dim3(kThreads), 0, s, w->visits.p, w->visitStart.p + w->nDyn, w->mset(w->cur), w->vgeom());
+            w->launches++;
+        }
+        w->visitGeomStale = false;
+        gridLoop = launch_solve_loop_grid(s, w->bview(), w->visits.p, w->vgeom(), w->mset(w->cur), fvAll, w->sweepRange.p, w->nColours, w->sweepWarps, w->sweepOff,
+                                          w->prm, w->dDiag.p, w->freeList.p, w->nFree);
+        if (gridLoop) {
+            w->launches++;
+            // what the loop could not apply: the last iteration's dual pass (+ contact diagnostics), or with postStabilize only the
+            // contacts no dynamic body visits
+            if (!w->prm.postStabilize) { TRY(run_dual(w, w->prm.alpha, true, true, w->prm.iterations, false)); }
+            else if (w->anyUnvisited) { TRY(run_dual(w, 1.0f, false, true, w->prm.iterations, true)); }
+        }
+    }
     if (persistent) {
         // small world: the whole iteration loop in one cluster launch (cluster barriers instead of kernel boundaries)
         bool fuseDiag = !w->prm.postStabilize && w->prm.iterations > 0;
@@ -681,7 +704,7 @@ int step_once(avbd_world* w) {
     const bool separateDual = sepEnv && atoi(sepEnv) != 0;
     int duals = 0, deferred = 0, timedDuals = 0;
     float pendingBias = -1.0f;
-    for (int it = 0; it < total && !persistent; ++it) {
+    for (int it = 0; it < total && !persistent && !gridLoop; ++it) {
         float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
         TRY(run_primal(w, a, nullptr, pendingBias));
         if (pendingBias >= 0.0f) ++deferred;
@@ -773,6 +796,7 @@ avbd_world* avbd_world_create(int device) {
     for (auto& e : w->ev) cudaEventCreate(&e);
     if (const char* e = std::getenv("AVBD_PERSISTENT_MAX_BODIES")) w->persistentMaxBodies = std::atoi(e);
     if (const char* e = std::getenv("AVBD_FORCE_REGRAPH")) w->forceRegraph = std::atoi(e) != 0;
+    if (const char* e = std::getenv("AVBD_LOOP")) w->loopMode = !std::strcmp(e, "launch") ? 1 : (!std::strcmp(e, "grid") ? 2 : (!std::strcmp(e, "cluster") ? 3 : 0));
     if (const char* e = std::getenv("AVBD_INCREMENTAL_COLOUR")) w->incrementalColour = std::atoi(e) != 0;
     std::memset(w->hCnt, 0, sizeof(Counters));
     avbd_default_params(w);

@@ -133,6 +133,11 @@ void launch_warp_ranges(cudaStream_t s, const int* vstart, const int2* colRange,
 // colour per sweep).
 void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* range, int nWarps, SolveParams prm,
                          float alpha, float biasDual, float* dxOut, Diag* diag, const int* freeList, int nFree);
+// The whole iteration loop (solver.cpp:340-431, manifold rows only) in ONE cooperative launch of the same warp pipelines, a grid
+// barrier between colour phases (avbd_solve.cu: solve_loop_grid).  ranges / nWarps / off as built for the per-colour launches.
+// Returns false if the launch was refused (caller falls back to per-colour launches).
+bool launch_solve_loop_grid(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* ranges, int nColours,
+                            const int* nWarps, const int* off, SolveParams prm, Diag* diag, const int* freeList, int nFree);
 // Dynamic bodies no contact visits that a joint / spring links to another body (listed by the graph stage), filtered to one colour
 // (onlyColour < 0: no filter).
 void launch_primal_free(cudaStream_t s, BodyView b, ForceView fv, const int* freeList, int nFree, const int* colour, int onlyColour, SolveParams prm,

@@ -16,11 +16,13 @@
 // of a step, stage API).
 #include <cstdio>
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include "avbd_launch.h"
 #include "avbd_body.cuh"
 #include "avbd_forces.cuh"
 
 namespace avbd {
+namespace cg = cooperative_groups;
 
 __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int ci) {
     ContactLP q = ms.lp[ci];
@@ -83,6 +85,18 @@ __device__ __forceinline__ void st4_keep(float4* ptr, float4 v, unsigned long lo
 }
 __device__ __forceinline__ BodyPose load_pose_keep(const BodyPose* p, unsigned long long pol) {
     BodyPose r; r.pos = ld4_keep(&p->pos, pol); r.rot = ld4_keep(&p->rot, pol); return r;
+}
+// The same through L2 only: inside a persistent loop another SM may have rewritten the pose since this SM's L1 last saw it.
+__device__ __forceinline__ float4 ld4_keep_l2(const float4* ptr, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+    return v;
+}
+template <bool COH> __device__ __forceinline__ BodyPose load_pose_keep_c(const BodyPose* p, unsigned long long pol) {
+    BodyPose r;
+    if (COH) { r.pos = ld4_keep_l2(&p->pos, pol); r.rot = ld4_keep_l2(&p->rot, pol); }
+    else { r.pos = ld4_keep(&p->pos, pol); r.rot = ld4_keep(&p->rot, pol); }
+    return r;
 }
 
 // ------------------------------------------------------------------ row math of the solver kernels
@@ -465,6 +479,7 @@ __device__ __forceinline__ void stage16(float4* dst, const float4* src, unsigned
     unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "l"(policy) : "memory");
 }
+template <bool COH> __device__ __forceinline__ void stage_pose(float4* dstPos, float4* dstRot, const BodyPose* src, unsigned long long policy);
 __device__ __forceinline__ void stage16_nol1(float4* dst, const float4* src, unsigned long long policy) {  // bypasses L1 (single-use data)
     unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "l"(policy) : "memory");
@@ -474,6 +489,10 @@ __device__ __forceinline__ unsigned long long l2_stream_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+template <bool COH> __device__ __forceinline__ void stage_pose(float4* dstPos, float4* dstRot, const BodyPose* src, unsigned long long policy) {
+    if (COH) { stage16_nol1(dstPos, &src->pos, policy); stage16_nol1(dstRot, &src->rot, policy); }
+    else { stage16(dstPos, &src->pos, policy); stage16(dstRot, &src->rot, policy); }
+}
 __device__ __forceinline__ float4 ld4_keep_cg(const float4* ptr, unsigned long long pol) {                // single use in this launch: L2 only
     float4 v;
     asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
@@ -481,9 +500,10 @@ __device__ __forceinline__ float4 ld4_keep_cg(const float4* ptr, unsigned long l
 }
 
 // A body no contact visits: inertial terms (plus user forces) -> 6x6 solve -> pose update (solver.cpp:351-369, :402-408).
+template <bool COH>
 __device__ __forceinline__ void solve_free_body(const BodyView& b, const ForceView& fv, int i, const SolveParams& prm, float* dxOut, Diag* diag,
                                                 unsigned long long keep) {
-    BodyPose self = load_pose_keep(b.pose + i, keep);
+    BodyPose self = load_pose_keep_c<COH>(b.pose + i, keep);
     BodyAux aux = b.aux[i];
     V3 pos = xyz(self.pos); Q4 rot = quat(self.rot);
     BodySystem own; M3 invIw;
@@ -499,11 +519,12 @@ __device__ __forceinline__ void solve_free_body(const BodyView& b, const ForceVi
 }
 
 // One body per lane (lanes [0, qn)): queued row sums + inertial terms -> 6x6 solve -> pose update.
+template <bool COH>
 __device__ __forceinline__ void solve_queue(WarpPipe& w, int qn, int lane, const BodyView& b, const ForceView& fv, const SolveParams& prm,
                                             float* dxOut, Diag* diag, unsigned long long keep) {
     if (lane < qn) {
         const int i = w.qBody[lane];
-        BodyPose self = load_pose_keep(b.pose + i, keep);
+        BodyPose self = load_pose_keep_c<COH>(b.pose + i, keep);
         BodyAux aux = b.aux[i];
         float o[28];
 #pragma unroll
@@ -529,31 +550,13 @@ __device__ __forceinline__ void solve_queue(WarpPipe& w, int qn, int lane, const
     __syncwarp();
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
-                                                                           const int* __restrict__ range, int nWarps, SolveParams prm,
-                                                                           float alpha, float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag,
-                                                                           const int* __restrict__ freeList, int nFree) {
-    __shared__ WarpPipe pipes[kSweepWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * kSweepWarps + warp;
-    if (gw >= nWarps) {                                        // no block-wide barrier anywhere in this kernel: a warp may leave on its own
-        // the warps past the colour's ranges (first colour of a sweep only) take the bodies no contact visits and no user force
-        // touches, one per lane: nothing they read is written by anyone else, so their colour does not matter
-        const int t = (gw - nWarps) * 32 + lane;
-        if (t < nFree) {
-            const int i = __ldg(freeList + t);
-            cudaGridDependencySynchronize();
-            solve_free_body(b, fv, i, prm, dxOut, diag, l2_keep_policy());
-        }
-        return;
-    }
-    WarpPipe& w = pipes[warp];
+// One warp's pipeline over the visits [vBegin, vEnd) (a body-aligned range).  COH: poses are read through L2 only (persistent loop:
+// other SMs rewrote them since this SM's L1 last saw them); the per-colour launches let L1 keep them (L1 is flushed between launches).
+template <bool COH>
+__device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const int vBegin, const int vEnd, const BodyView& b, const int4* __restrict__ visits,
+                                            const VisitGeom& vg, const ManifoldSet& ms, const ForceView& fv, const SolveParams& prm,
+                                            const float alpha, const float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag) {
     const unsigned long long keep = l2_keep_policy(), stream = l2_stream_policy();
-    const int vBegin = __ldg(range + gw), vEnd = __ldg(range + gw + 1);      // written by the graph stage, many launches ago
-    if (vBegin >= vEnd) return;
-    // launched with programmatic stream serialization: poses and lambda / penalty may still be in flight from the previous colour
-    cudaGridDependencySynchronize();
     const int4 none = make_int4(0, 0, -8, 0);                                // body -1
     const bool odd = (lane & 1) != 0;
     auto load_entry = [&](int v) { return v < vEnd ? __ldcs(visits + v) : none; };
@@ -572,10 +575,10 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
         if (kSelfSeg) {
             if (head) {                                                      // one fetch of the visiting body's pose per segment
                 const int seg = __popc(heads & ((1u << lane) - 1u));
-                stage16(&w.selfp[0][seg], &b.pose[self].pos, keep); stage16(&w.selfp[1][seg], &b.pose[self].rot, keep);
+                stage_pose<COH>(&w.selfp[0][seg], &w.selfp[1][seg], b.pose + self, keep);
             }
-        } else if (lv) { stage16(&w.selfp[0][lane], &b.pose[self].pos, keep); stage16(&w.selfp[1][lane], &b.pose[self].rot, keep); }
-        if (lv) { stage16(&w.other[0][lane], &b.pose[e.y].pos, keep); stage16(&w.other[1][lane], &b.pose[e.y].rot, keep); }
+        } else if (lv) { stage_pose<COH>(&w.selfp[0][lane], &w.selfp[1][lane], b.pose + self, keep); }
+        if (lv) { stage_pose<COH>(&w.other[0][lane], &w.other[1][lane], b.pose + e.y, keep); }
         if (!kVgReg && lv) { stage16_nol1(&w.geom[0][lane], vg.a + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 1][lane], vg.b + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 2][lane], vg.n + v, stream); }
         if (!kLpReg && lv) { stage16_nol1(&w.lamp[0][lane], &ms.lp[e.x].l, keep); stage16_nol1(&w.lamp[kLpReg ? 0 : 1][lane], &ms.lp[e.x].p, keep); }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -658,7 +661,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
         for (int s0 = 0; s0 < nSeg; s0 += 4) {
             // queue slots in use: qn + s0 (every segment before this pass is finished: only a chunk's LAST segment can run on).
             // No room for four more: solve what is queued first.
-            if (qn + s0 + 4 > kQueueSlots) { __syncwarp(); solve_queue(w, qn + s0, lane, b, fv, prm, dxOut, diag, keep); qn = -s0; }
+            if (qn + s0 + 4 > kQueueSlots) { __syncwarp(); solve_queue<COH>(w, qn + s0, lane, b, fv, prm, dxOut, diag, keep); qn = -s0; }
             const int sgi = s0 + sub;
             const bool active = j < 7 && sgi < nSeg;
             const int start = active ? (int)w.segStart[sgi] : 0;
@@ -684,8 +687,73 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
         tailSelf = lastSelf;
         __syncwarp();               // rows consumed, carry / queue visible, before the next chunk overwrites the rows
     }
-    if (qn > 0) solve_queue(w, qn, lane, b, fv, prm, dxOut, diag, keep);
+    if (qn > 0) solve_queue<COH>(w, qn, lane, b, fv, prm, dxOut, diag, keep);
 }
+
+template <int MINB>
+__global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
+                                                                           const int* __restrict__ range, int nWarps, SolveParams prm,
+                                                                           float alpha, float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag,
+                                                                           const int* __restrict__ freeList, int nFree) {
+    __shared__ WarpPipe pipes[kSweepWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kSweepWarps + warp;
+    if (gw >= nWarps) {                                        // no block-wide barrier anywhere in this kernel: a warp may leave on its own
+        // the warps past the colour's ranges (first colour of a sweep only) take the bodies no contact visits and no user force
+        // touches, one per lane: nothing they read is written by anyone else, so their colour does not matter
+        const int t = (gw - nWarps) * 32 + lane;
+        if (t < nFree) {
+            const int i = __ldg(freeList + t);
+            cudaGridDependencySynchronize();
+            solve_free_body<false>(b, fv, i, prm, dxOut, diag, l2_keep_policy());
+        }
+        return;
+    }
+    const int vBegin = __ldg(range + gw), vEnd = __ldg(range + gw + 1);      // written by the graph stage, many launches ago
+    if (vBegin >= vEnd) return;
+    // launched with programmatic stream serialization: poses and lambda / penalty may still be in flight from the previous colour
+    cudaGridDependencySynchronize();
+    sweep_range<false>(pipes[warp], lane, vBegin, vEnd, b, visits, vg, ms, fv, prm, alpha, biasDual, dxOut, diag);
+}
+
+// The whole iteration loop of solver.cpp:340-431 (manifold rows) in ONE cooperative launch: the same warp pipelines, a grid barrier
+// where the per-colour path has a kernel boundary.  A step of a mid-size batch (tens of thousands of bodies) is ~40-100 dependent
+// colour phases of a few microseconds each; a grid barrier costs less than a launch + drain + ramp-up, and nothing but the barrier
+// sits between two phases.  Poses / lambda / penalty are read through L2 only (COH).  The step's last dual pass stays a launch of its own.
+struct SweepPlan { int nColours; int nWarps[64]; int off[64]; };
+template <int MINB>
+__global__ void __launch_bounds__(32 * kSweepWarps, MINB) solve_loop_grid(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
+                                                                         const int* __restrict__ ranges, SweepPlan plan, SolveParams prm, Diag* __restrict__ diag,
+                                                                         const int* __restrict__ freeList, int nFree) {
+    __shared__ WarpPipe pipes[kSweepWarps];
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw0 = blockIdx.x * kSweepWarps + warp, nGridWarps = gridDim.x * kSweepWarps;
+    const int total = prm.iterations + (prm.postStabilize ? 1 : 0);
+    float biasDual = -1.0f;                                                  // dual pass of the previous iteration still to apply (deferred dual)
+    for (int it = 0; it < total; ++it) {
+        const float alpha = prm.postStabilize ? (it < prm.iterations ? 1.0f : 0.0f) : prm.alpha;      // solver.cpp:340-342
+        bool freeDone = nFree <= 0;
+        for (int c = 0; c < plan.nColours; ++c) {
+            const int nW = plan.nWarps[c];
+            const int* range = ranges + plan.off[c];
+            const int extra = freeDone ? 0 : (nFree + 31) / 32;             // contact-free bodies ride on the first phase
+            for (int gw = gw0; gw < nW + extra; gw += nGridWarps) {
+                if (gw < nW) {
+                    const int vBegin = range[gw], vEnd = range[gw + 1];
+                    if (vBegin < vEnd) sweep_range<true>(pipes[warp], lane, vBegin, vEnd, b, visits, vg, ms, fv, prm, alpha, biasDual, nullptr, diag);
+                } else {
+                    const int t = (gw - nW) * 32 + lane;
+                    if (t < nFree) solve_free_body<true>(b, fv, freeList[t], prm, nullptr, diag, l2_keep_policy());
+                }
+            }
+            freeDone = true;
+            grid.sync();
+        }
+        biasDual = it < prm.iterations ? fminf(fmaxf(1.0f - alpha, 0.0f), 1.0f) : -1.0f;
+    }
+}
+
 
 // Dynamic bodies no contact visits that a joint / spring links to another body: inertial terms + user forces -> 6x6 solve -> pose
 // update, one colour per launch like every other body.  (The ones no user force touches ride on the first colour's sweep launch.)
@@ -696,7 +764,7 @@ __global__ void __launch_bounds__(kThreads) primal_free_bodies(BodyView b, Force
     const int i = __ldg(freeList + t);
     if (onlyColour >= 0 && __ldg(colour + i) != onlyColour) return;
     cudaGridDependencySynchronize();
-    solve_free_body(b, fv, i, prm, dxOut, diag, l2_keep_policy());
+    solve_free_body<false>(b, fv, i, prm, dxOut, diag, l2_keep_policy());
 }
 
 // Body-aligned warp ranges of every colour's visits, one launch: range[c][r] (r = 0 .. nWarps[c]) starts at the first body whose run
@@ -952,6 +1020,45 @@ void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGe
         case 4:  launch_dep(primal_sweep_warp<4>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree); break;
         default: launch_dep(primal_sweep_warp<5>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree); break;
     }
+}
+
+// The whole iteration loop in one cooperative launch (solve_loop_grid).  nWarps / off: per colour, as for launch_warp_ranges.
+// Returns false if the launch was refused (caller falls back to per-colour launches).
+template <int MINB> static int loop_blocks_per_sm() {
+    int per = 0;
+    cudaFuncSetAttribute(solve_loop_grid<MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, solve_loop_grid<MINB>, 32 * kSweepWarps, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 0; }
+    return per;
+}
+bool launch_solve_loop_grid(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* ranges, int nColours,
+                            const int* nWarps, const int* off, SolveParams prm, Diag* diag, const int* freeList, int nFree) {
+    static int residentDev[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!residentDev[dev]) {
+        int sms = 148, coop = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        int per = sweep_cfg() == 4 ? loop_blocks_per_sm<4>() : loop_blocks_per_sm<5>();
+        residentDev[dev] = (coop && per > 0) ? sms * per : -1;
+        if (getenv("AVBD_DEBUG")) fprintf(stderr, "solve_loop_grid: %d blocks per SM resident (device %d)\n", per, dev);
+    }
+    if (residentDev[dev] <= 0 || nColours <= 0 || nColours > 64) return false;
+    SweepPlan plan{};
+    plan.nColours = nColours;
+    int mx = 1;
+    for (int c = 0; c < nColours; ++c) {
+        plan.nWarps[c] = nWarps[c]; plan.off[c] = off[c];
+        int need = nWarps[c] + (c == 0 ? (nFree + 31) / 32 : 0);
+        mx = need > mx ? need : mx;
+    }
+    int grid = blocks_of(mx, kSweepWarps);
+    if (grid > residentDev[dev]) grid = residentDev[dev];
+    void* args[] = {&b, &visits, &vg, &ms, &fv, &ranges, &plan, &prm, &diag, &freeList, &nFree};
+    cudaError_t e = sweep_cfg() == 4
+        ? cudaLaunchCooperativeKernel((void*)solve_loop_grid<4>, dim3(grid), dim3(32 * kSweepWarps), args, 0, s)
+        : cudaLaunchCooperativeKernel((void*)solve_loop_grid<5>, dim3(grid), dim3(32 * kSweepWarps), args, 0, s);
+    if (e != cudaSuccess) { cudaGetLastError(); residentDev[dev] = -1; return false; }
+    return true;
 }
 
 bool launch_solve_loop(cudaStream_t s, BodyView b, const int* visitStart, const int4* visits, ManifoldSet ms, ForceView fv, const int* order,

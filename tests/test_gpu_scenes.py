@@ -214,9 +214,18 @@ def test_host_cli_unknown_scene_falls_back_to_empty(avbd):
 
 
 # --------------------------------------------------------------------------- ensembles
-def _ensemble_states(avbd, base, worlds, first, steps):
+def _ensemble_states(avbd, base, worlds, first, steps, cluster_max=None):
+    """cluster_max: AVBD_PERSISTENT_MAX_BODIES for this world (read at world creation) — forces which solver path the batch takes."""
     from avbd_demo3d_b200 import scenes
-    w = avbd.World()
+    old = os.environ.get("AVBD_PERSISTENT_MAX_BODIES")
+    if cluster_max is not None:
+        os.environ["AVBD_PERSISTENT_MAX_BODIES"] = str(cluster_max)
+    try:
+        w = avbd.World()
+    finally:
+        if cluster_max is not None:
+            if old is None: os.environ.pop("AVBD_PERSISTENT_MAX_BODIES", None)
+            else: os.environ["AVBD_PERSISTENT_MAX_BODIES"] = old
     scenes.load(w, scenes.ensemble(base, worlds, first_world=first))
     w.step(steps)
     st, dg = w.state(), w.world_diagnostics()
@@ -250,9 +259,9 @@ def test_large_ensemble_is_bit_identical_across_partitions(avbd):
     from avbd_demo3d_b200 import scenes
     base = scenes.scene("Stack")
     n = len(base["size"])
-    whole, dwhole = _ensemble_states(avbd, base, 800, 0, 40)
-    lo, dlo = _ensemble_states(avbd, base, 400, 0, 40)
-    hi, dhi = _ensemble_states(avbd, base, 400, 400, 40)
+    whole, dwhole = _ensemble_states(avbd, base, 800, 0, 40, cluster_max=0)          # per-colour sweep launches
+    lo, dlo = _ensemble_states(avbd, base, 400, 0, 40, cluster_max=4096)              # 4000 dynamic bodies: the cluster loop
+    hi, dhi = _ensemble_states(avbd, base, 400, 400, 40, cluster_max=4096)
     assert whole[: 400 * n].tobytes() == lo.tobytes()
     assert whole[400 * n:].tobytes() == hi.tobytes()
     assert dwhole[:400] == dlo and dwhole[400:] == dhi
