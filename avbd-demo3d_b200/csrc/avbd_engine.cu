@@ -592,12 +592,14 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float biasDual = -1.0f)
     cudaStream_t s = w->stream;
     ManifoldSet ms = w->mset(w->cur);
     ForceView fv = w->fview();
-    if (!w->sweepRangesValid) TRY(build_sweep_ranges(w));
+    bool staticsJustWritten = false;         // a static input of the sweeps was written by a launch with no host wait since
+    if (!w->sweepRangesValid) { TRY(build_sweep_ranges(w)); staticsJustWritten = true; }
     if (w->visitGeomStale && w->nContacts > 0 && w->nDyn > 0) {
         size_t cap = w->visits.cap;
         TRY(w->vgA.ensure(cap, false, s)); TRY(w->vgB.ensure(cap, false, s)); TRY(w->vgN.ensure(cap, false, s));
         launch_dep(visit_geometry, dim3(blocks_for(2ll * w->nContacts)), dim3(kThreads), 0, s, w->visits.p, w->visitStart.p + w->nDyn, ms, w->vgeom());
         w->launches++;
+        staticsJustWritten = true;
     }
     w->visitGeomStale = false;
     int freeLeft = w->nFree;                 // ride on the first sweep launch of the pass
@@ -607,13 +609,13 @@ int run_primal(avbd_world* w, float alpha, float* dxDev, float biasDual = -1.0f)
         if (w->nLinkedFree > 0) { launch_primal_free(s, w->bview(), fv, w->linkedList.p, w->nLinkedFree, w->colour.p, c, w->prm, dxDev, w->dDiag.p); w->launches++; }
         if (w->sweepWarps[c] > 0 || freeLeft > 0) {
             launch_primal_sweep(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->sweepRange.p + w->sweepOff[c], w->sweepWarps[c], w->prm, alpha, biasDual, dxDev, w->dDiag.p,
-                                w->freeList.p, freeLeft);
+                                w->freeList.p, freeLeft, staticsJustWritten);
             w->launches++;
-            freeLeft = 0;
+            freeLeft = 0; staticsJustWritten = false;
         }
     }
     if (freeLeft > 0) {                      // no colour at all (nothing but free bodies cannot happen: every dynamic body has a colour), kept for safety
-        launch_primal_sweep(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->sweepRange.p, 0, w->prm, alpha, biasDual, dxDev, w->dDiag.p, w->freeList.p, freeLeft);
+        launch_primal_sweep(s, w->bview(), w->visits.p, w->vgeom(), ms, fv, w->sweepRange.p, 0, w->prm, alpha, biasDual, dxDev, w->dDiag.p, w->freeList.p, freeLeft, staticsJustWritten);
         w->launches++;
     }
     CK(cudaGetLastError());

@@ -143,6 +143,15 @@ __device__ __forceinline__ bool outranks(int localA, int localB) {
     unsigned ha = mix32((unsigned)localA + 0x9e3779b9u), hb = mix32((unsigned)localB + 0x9e3779b9u);
     return ha != hb ? ha > hb : localA > localB;
 }
+// Priority order of the greedy colouring.  AVBD_COLOUR_LDF: largest degree first (ties by the hash) — degree = manifold entries of the
+// body, a world-local quantity like the hash.
+#ifndef AVBD_COLOUR_LDF
+#define AVBD_COLOUR_LDF 0
+#endif
+__device__ __forceinline__ bool outranks_deg(int localA, int degA, int localB, int degB) {
+    if (AVBD_COLOUR_LDF && degA != degB) return degA > degB;
+    return outranks(localA, localB);
+}
 
 __global__ void colour_init(const int* flags, int n, int* colour) {
     cudaGridDependencySynchronize();
@@ -159,13 +168,14 @@ __device__ __forceinline__ bool try_colour(int i, const int* estart, const int4*
                                            const int* localIdx, volatile int* colour, Counters* cnt) {
     if (colour[i] >= 0) return true;
     int li = localIdx[i];
+    const int di = estart[i + 1] - estart[i];
     unsigned long long used = 0ull;
     bool ready = true;
     auto visit = [&](int other) {
         if (other < 0) return;
         int co = colour[other];
         if (co >= 0) used |= 1ull << co;
-        else if (co == -1 && outranks(localIdx[other], li)) ready = false;
+        else if (co == -1 && outranks_deg(localIdx[other], AVBD_COLOUR_LDF ? estart[other + 1] - estart[other] : 0, li, di)) ready = false;
     };
     for (int e = estart[i], e1 = estart[i + 1]; e < e1 && ready; ++e) visit(entries[e].x);
     if (fv.adjStart) {

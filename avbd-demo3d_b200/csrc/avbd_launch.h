@@ -130,9 +130,10 @@ constexpr int kClusterBodiesPerTile = 28;     // small-world cluster loop: bodie
 int primal_sweep_warps(int nVisits);
 void launch_warp_ranges(cudaStream_t s, const int* vstart, const int2* colRange, int nColours, const int* nWarps, const int* off, int* range);
 // freeList / nFree: bodies no contact visits and no user force touches; extra warps of THIS launch solve them (pass them with one
-// colour per sweep).
+// colour per sweep).  staticsJustWritten: the launch right before this one wrote visits / vg / ranges (the kernel then waits for its
+// predecessor before it reads them; otherwise it issues its static loads first and waits only for poses / lambda / penalty).
 void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* range, int nWarps, SolveParams prm,
-                         float alpha, float biasDual, float* dxOut, Diag* diag, const int* freeList, int nFree);
+                         float alpha, float biasDual, float* dxOut, Diag* diag, const int* freeList, int nFree, bool staticsJustWritten);
 // The whole iteration loop (solver.cpp:340-431, manifold rows only) in ONE cooperative launch of the same warp pipelines, a grid
 // barrier between colour phases (avbd_solve.cu: solve_loop_grid).  ranges / nWarps / off as built for the per-colour launches.
 // Returns false if the launch was refused (caller falls back to per-colour launches).

@@ -451,6 +451,10 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
 #ifndef AVBD_VG_REG
 #define AVBD_VG_REG 0        // visit-order geometry: 1 = coalesced loads into registers, 0 = cp.async into the stage
 #endif
+#ifndef AVBD_VG_BULK
+#define AVBD_VG_BULK 0       // visit-order geometry (when staged): 1 = three bulk copies per chunk by one lane (TMA + mbarrier; measured 4 % SLOWER:
+                             // 4.39 vs 4.23 ms of sweeps on the 1M grid — the wait + proxy fence cost more than the wavefronts saved), 0 = cp.async per lane
+#endif
 #ifndef AVBD_LP_REG
 #define AVBD_LP_REG 0        // lambda / penalty: 1 = lane-pair loads into registers + shuffle, 0 = cp.async into the stage
 #endif
@@ -461,7 +465,7 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
 #define AVBD_QUEUE_SLOTS 26
 #endif
 constexpr int kQueueSlots = AVBD_QUEUE_SLOTS;
-constexpr bool kVgReg = AVBD_VG_REG != 0, kLpReg = AVBD_LP_REG != 0, kSelfSeg = AVBD_SELF_SEG != 0;
+constexpr bool kVgReg = AVBD_VG_REG != 0, kLpReg = AVBD_LP_REG != 0, kSelfSeg = AVBD_SELF_SEG != 0, kVgBulk = AVBD_VG_BULK != 0 && !kVgReg;
 struct WarpPipe {
     float4 rows[32][7];              // this chunk's partial sums, one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad
     float4 other[2][32];             // the NEXT chunk's other-body poses, per lane (cp.async)
@@ -472,6 +476,7 @@ struct WarpPipe {
     float4 carry[7];                 // partial sum of the body whose run crosses into the next chunk
     int    qBody[kQueueSlots];
     unsigned char segStart[32];      // lane of each segment's first visit
+    unsigned long long mbar;         // completion barrier of the chunk's bulk copies (kVgBulk)
 };
 constexpr int kSweepWarps = 4;                     // warps per block (they share nothing but the block's shared-memory allocation)
 
@@ -488,6 +493,26 @@ __device__ __forceinline__ unsigned long long l2_stream_policy() {
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+// Bulk asynchronous copy global -> shared (the TMA engine: no per-lane address math, no load / store pipe wavefronts) completing on
+// an mbarrier.  `bytes` a multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar), done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)), "l"(policy) : "memory");
 }
 template <bool COH> __device__ __forceinline__ void stage_pose(float4* dstPos, float4* dstRot, const BodyPose* src, unsigned long long policy) {
     if (COH) { stage16_nol1(dstPos, &src->pos, policy); stage16_nol1(dstRot, &src->rot, policy); }
@@ -552,19 +577,26 @@ __device__ __forceinline__ void solve_queue(WarpPipe& w, int qn, int lane, const
 
 // One warp's pipeline over the visits [vBegin, vEnd) (a body-aligned range).  COH: poses are read through L2 only (persistent loop:
 // other SMs rewrote them since this SM's L1 last saw them); the per-colour launches let L1 keep them (L1 is flushed between launches).
-template <bool COH>
+// DEP: the launch waits for its predecessor (cudaGridDependencySynchronize) only after it has issued everything that does not depend
+// on it — the first chunk's entries and its streamed geometry are static for the whole step.
+template <bool COH, bool DEP>
 __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const int vBegin, const int vEnd, const BodyView& b, const int4* __restrict__ visits,
                                             const VisitGeom& vg, const ManifoldSet& ms, const ForceView& fv, const SolveParams& prm,
                                             const float alpha, const float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag) {
     const unsigned long long keep = l2_keep_policy(), stream = l2_stream_policy();
     const int4 none = make_int4(0, 0, -8, 0);                                // body -1
     const bool odd = (lane & 1) != 0;
+    unsigned bulkPhase = 0;
+    if (kVgBulk) {
+        if (lane == 0) { mbar_init(&w.mbar, 1); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+        __syncwarp();
+    }
     auto load_entry = [&](int v) { return v < vEnd ? __ldcs(visits + v) : none; };
     // Everything chunk [vb, vb + 32) needs, issued a whole chunk ahead.  `e` = the lane's entry of that chunk, `prevTail` = body of the
     // visit before the chunk (-1: none).  Returns the chunk's segment heads; nvA / nvB / nvN / nL0 / nL1 receive the register operands.
     float4 nvA, nvB, nvN, nL0, nL1;
     nvA = nvB = nvN = nL0 = nL1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    auto prefetch = [&](int vb, const int4& e, int prevTail) -> unsigned {
+    auto prefetch = [&](int vb, const int4& e, int prevTail, bool first) -> unsigned {
         const int v = vb + lane;
         const bool lv = v < vEnd;
         const int self = e.z >> 3;
@@ -572,6 +604,18 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
         if (lane == 0) prevSelf = prevTail;
         const bool head = lv && (lane == 0 || prevSelf != self);
         const unsigned heads = __ballot_sync(0xffffffffu, head);
+        if (kVgBulk) {
+            int cnt = vEnd - vb; if (cnt > 32) cnt = 32;
+            if (lane == 0 && cnt > 0) {                                      // every lane has read the previous contents (callers sync the warp first)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect(&w.mbar, 3u * 16u * (unsigned)cnt);
+                bulk_copy(&w.geom[0][0], vg.a + vb, 16u * (unsigned)cnt, &w.mbar, stream);
+                bulk_copy(&w.geom[kVgReg ? 0 : 1][0], vg.b + vb, 16u * (unsigned)cnt, &w.mbar, stream);
+                bulk_copy(&w.geom[kVgReg ? 0 : 2][0], vg.n + vb, 16u * (unsigned)cnt, &w.mbar, stream);
+            }
+        } else if (!kVgReg && lv) { stage16_nol1(&w.geom[0][lane], vg.a + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 1][lane], vg.b + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 2][lane], vg.n + v, stream); }
+        // what follows was written by the previous launch (poses, lambda / penalty): wait for it now, not before
+        if (DEP && first) cudaGridDependencySynchronize();
         if (kSelfSeg) {
             if (head) {                                                      // one fetch of the visiting body's pose per segment
                 const int seg = __popc(heads & ((1u << lane) - 1u));
@@ -579,7 +623,6 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
             }
         } else if (lv) { stage_pose<COH>(&w.selfp[0][lane], &w.selfp[1][lane], b.pose + self, keep); }
         if (lv) { stage_pose<COH>(&w.other[0][lane], &w.other[1][lane], b.pose + e.y, keep); }
-        if (!kVgReg && lv) { stage16_nol1(&w.geom[0][lane], vg.a + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 1][lane], vg.b + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 2][lane], vg.n + v, stream); }
         if (!kLpReg && lv) { stage16_nol1(&w.lamp[0][lane], &ms.lp[e.x].l, keep); stage16_nol1(&w.lamp[kLpReg ? 0 : 1][lane], &ms.lp[e.x].p, keep); }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (kVgReg && lv) { nvA = __ldcs(vg.a + v); nvB = __ldcs(vg.b + v); nvN = __ldcs(vg.n + v); }
@@ -595,7 +638,7 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
         return heads;
     };
     int4 eCur = load_entry(vBegin + lane), eNext = load_entry(vBegin + 32 + lane);
-    unsigned headsNext = prefetch(vBegin, eCur, -1);
+    unsigned headsNext = prefetch(vBegin, eCur, -1, true);
     int qn = 0;                      // bodies waiting in the solve queue (warp-uniform)
     int tailSelf = -1;               // body of the previous chunk's last visit
     const int sub = lane >> 3, j = lane & 7;                                 // phase 2: segment of the pass / float4 column (7 = idle)
@@ -624,12 +667,13 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
         const int sslot = kSelfSeg ? (seg < 0 ? 0 : seg) : lane;
         BodyPose ps, po;
         ps.pos = w.selfp[0][sslot]; ps.rot = w.selfp[1][sslot]; po.pos = w.other[0][lane]; po.rot = w.other[1][lane];
+        if (kVgBulk) { mbar_wait(&w.mbar, bulkPhase); bulkPhase ^= 1u; }      // a chunk inside the loop always has visits: its copies were issued
         if (!kVgReg) { a4 = w.geom[0][lane]; b4 = w.geom[kVgReg ? 0 : 1][lane]; n4 = w.geom[kVgReg ? 0 : 2][lane]; }
         if (!kLpReg) { l4 = w.lamp[0][lane]; p4 = w.lamp[kLpReg ? 0 : 1][lane]; }
         if (live && (heads >> lane & 1u)) w.segStart[seg] = (unsigned char)lane;
         __syncwarp();                                                        // everyone holds its poses: the stage may be refilled
         eCur = eNext;
-        headsNext = prefetch(base + 32, eCur, lastSelf);                     // next chunk (its entry was loaded a whole chunk ago)
+        headsNext = prefetch(base + 32, eCur, lastSelf, false);                     // next chunk (its entry was loaded a whole chunk ago)
         eNext = load_entry(v + 64);                                          // the entry after that
         // ---- phase 1
         if (live) {
@@ -688,14 +732,22 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
         __syncwarp();               // rows consumed, carry / queue visible, before the next chunk overwrites the rows
     }
     if (qn > 0) solve_queue<COH>(w, qn, lane, b, fv, prm, dxOut, diag, keep);
+    if (kVgBulk) { __syncwarp(); if (lane == 0) mbar_inval(&w.mbar); __syncwarp(); }
 }
 
 template <int MINB>
 __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
                                                                            const int* __restrict__ range, int nWarps, SolveParams prm,
                                                                            float alpha, float biasDual, float* __restrict__ dxOut, Diag* __restrict__ diag,
-                                                                           const int* __restrict__ freeList, int nFree) {
+                                                                           const int* __restrict__ freeList, int nFree, int flags) {
     __shared__ WarpPipe pipes[kSweepWarps];
+    // Let the NEXT launch become resident now and run its own static prologue (every kernel of this library waits at
+    // cudaGridDependencySynchronize before it touches anything a predecessor writes): a small colour is a chain of latencies and its
+    // grid leaves the machine empty.  Measured: Stress1000 0.746 -> 0.722 ms per step, 8192-world ensemble 3.50 -> 3.46, 1M grid
+    // 7.61 -> 7.59 — never a loss with this kernel, so the host sets it for every grid (AVBD_EARLY_TRIGGER_BLOCKS caps the grid size).
+    if (flags & 1) cudaTriggerProgrammaticLaunchCompletion();
+    // bit 1: the immediate predecessor wrote the static inputs (visit-order geometry refreshed just before this launch): wait first
+    if (flags & 2) cudaGridDependencySynchronize();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kSweepWarps + warp;
     if (gw >= nWarps) {                                        // no block-wide barrier anywhere in this kernel: a warp may leave on its own
@@ -711,9 +763,9 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
     }
     const int vBegin = __ldg(range + gw), vEnd = __ldg(range + gw + 1);      // written by the graph stage, many launches ago
     if (vBegin >= vEnd) return;
-    // launched with programmatic stream serialization: poses and lambda / penalty may still be in flight from the previous colour
-    cudaGridDependencySynchronize();
-    sweep_range<false>(pipes[warp], lane, vBegin, vEnd, b, visits, vg, ms, fv, prm, alpha, biasDual, dxOut, diag);
+    // launched with programmatic stream serialization: poses and lambda / penalty may still be in flight from the previous colour —
+    // sweep_range waits for them after it has issued its static loads
+    sweep_range<false, true>(pipes[warp], lane, vBegin, vEnd, b, visits, vg, ms, fv, prm, alpha, biasDual, dxOut, diag);
 }
 
 // The whole iteration loop of solver.cpp:340-431 (manifold rows) in ONE cooperative launch: the same warp pipelines, a grid barrier
@@ -741,7 +793,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) solve_loop_grid(BodyVi
             for (int gw = gw0; gw < nW + extra; gw += nGridWarps) {
                 if (gw < nW) {
                     const int vBegin = range[gw], vEnd = range[gw + 1];
-                    if (vBegin < vEnd) sweep_range<true>(pipes[warp], lane, vBegin, vEnd, b, visits, vg, ms, fv, prm, alpha, biasDual, nullptr, diag);
+                    if (vBegin < vEnd) sweep_range<true, false>(pipes[warp], lane, vBegin, vEnd, b, visits, vg, ms, fv, prm, alpha, biasDual, nullptr, diag);
                 } else {
                     const int t = (gw - nW) * 32 + lane;
                     if (t < nFree) solve_free_body<true>(b, fv, freeList[t], prm, nullptr, diag, l2_keep_policy());
@@ -1010,15 +1062,17 @@ void launch_primal_free(cudaStream_t s, BodyView b, ForceView fv, const int* fre
 }
 // One colour of the large-world sweep: its visits, cut into nWarps body-aligned warp ranges (range[0 .. nWarps]).
 void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* range, int nWarps, SolveParams prm,
-                         float alpha, float biasDual, float* dxOut, Diag* diag, const int* freeList, int nFree) {
+                         float alpha, float biasDual, float* dxOut, Diag* diag, const int* freeList, int nFree, bool staticsJustWritten) {
     if (nWarps <= 0 && nFree <= 0) return;
     if (nWarps < 0) nWarps = 0;
     if (nFree < 0) nFree = 0;
     dim3 grid(blocks_of(nWarps + (nFree + 31) / 32, kSweepWarps)), block(32 * kSweepWarps);
+    static const int triggerBlocks = [] { const char* e = getenv("AVBD_EARLY_TRIGGER_BLOCKS"); return e ? atoi(e) : (1 << 30); }();
+    const int early = ((int)grid.x <= triggerBlocks ? 1 : 0) | (staticsJustWritten ? 2 : 0);
     switch (sweep_cfg()) {
-        case 3:  launch_dep(primal_sweep_warp<3>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree); break;
-        case 4:  launch_dep(primal_sweep_warp<4>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree); break;
-        default: launch_dep(primal_sweep_warp<5>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree); break;
+        case 3:  launch_dep(primal_sweep_warp<3>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree, early); break;
+        case 4:  launch_dep(primal_sweep_warp<4>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree, early); break;
+        default: launch_dep(primal_sweep_warp<5>, grid, block, 0, s, b, visits, vg, ms, fv, range, nWarps, prm, alpha, biasDual, dxOut, diag, freeList, nFree, early); break;
     }
 }
 
