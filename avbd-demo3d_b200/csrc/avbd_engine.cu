@@ -106,8 +106,8 @@ struct avbd_world {
     DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
     int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
-    long long graphReuses = 0; int persistentMaxBodies = 256;      // measured (tools/loop_modes.py): the cluster loop wins by 6-10 % up to a Wall (64 bodies), the per-colour sweep launches from Stress1000 up (+7 % at 1000 bodies, +66 % at 8000)
-    int loopMode = 0;      // AVBD_LOOP: 0 auto, 1 per-colour launches, 2 cooperative grid loop, 3 cluster loop where eligible
+    long long graphReuses = 0; int persistentMaxBodies = 0;      // the tile cluster loop (solve_loop_cluster) is opt-in (AVBD_PERSISTENT_MAX_BODIES): measured (tools/loop_modes.py) the per-colour sweep launches match or beat it at every size (TwoBlockDrop 6.8k vs 6.6k steps/s, Pyramid 3.75k vs 3.6k, Stress1000 1.39k vs 1.23k, 8000 bodies 1.26k vs 0.69k)
+    int loopMode = 0;      // AVBD_LOOP: 0 auto, 1 per-colour launches, 2 cooperative grid loop, 3 tile cluster loop where eligible, 4 warp-pipeline cluster loop
 
     // user forces
     std::vector<JointRec> hJoints; std::vector<SpringRec> hSprings; std::vector<HostForce> hForces;
@@ -497,7 +497,7 @@ int run_colour(avbd_world* w) {
     // between rounds.  If the cooperative launch is refused, rounds are launched in batches with a host check per batch.
     bool coloured = false;
     if (w->nDyn <= kColourBlockMaxBodies) {
-        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colour.p, w->dCnt);
+        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colour.p, w->dCnt, n);
         w->launches++;
         coloured = true;
     } else {
@@ -668,7 +668,7 @@ int step_once(avbd_world* w) {
     ForceView fvAll = w->fview();
     const bool noUserForces = fvAll.nJoints + fvAll.nSprings == 0;
     bool persistent = !prof && w->nColours > 0 && w->nDyn <= w->persistentMaxBodies && noUserForces && (w->loopMode == 0 || w->loopMode == 3);
-    bool gridLoop = !persistent && !prof && w->nColours > 0 && noUserForces && w->loopMode == 2 && w->prm.iterations > 0;
+    bool gridLoop = !persistent && !prof && w->nColours > 0 && noUserForces && (w->loopMode == 2 || w->loopMode == 4) && w->prm.iterations > 0;
     if (gridLoop) {
         // the iteration loop in one cooperative launch of the sweep kernel's warp pipelines (grid barrier between colour phases)
         if (!w->sweepRangesValid) TRY(build_sweep_ranges(w));
@@ -679,8 +679,11 @@ int step_once(avbd_world* w) {
             w->launches++;
         }
         w->visitGeomStale = false;
-        gridLoop = launch_solve_loop_grid(s, w->bview(), w->visits.p, w->vgeom(), w->mset(w->cur), fvAll, w->sweepRange.p, w->nColours, w->sweepWarps, w->sweepOff,
-                                          w->prm, w->dDiag.p, w->freeList.p, w->nFree);
+        gridLoop = w->loopMode == 4
+            ? launch_solve_loop_warps(s, w->bview(), w->visits.p, w->vgeom(), w->mset(w->cur), fvAll, w->sweepRange.p, w->nColours, w->sweepWarps, w->sweepOff,
+                                      w->prm, w->dDiag.p, w->freeList.p, w->nFree)
+            : launch_solve_loop_grid(s, w->bview(), w->visits.p, w->vgeom(), w->mset(w->cur), fvAll, w->sweepRange.p, w->nColours, w->sweepWarps, w->sweepOff,
+                                     w->prm, w->dDiag.p, w->freeList.p, w->nFree);
         if (gridLoop) {
             w->launches++;
             // what the loop could not apply: the last iteration's dual pass (+ contact diagnostics), or with postStabilize only the
@@ -798,7 +801,7 @@ avbd_world* avbd_world_create(int device) {
     for (auto& e : w->ev) cudaEventCreate(&e);
     if (const char* e = std::getenv("AVBD_PERSISTENT_MAX_BODIES")) w->persistentMaxBodies = std::atoi(e);
     if (const char* e = std::getenv("AVBD_FORCE_REGRAPH")) w->forceRegraph = std::atoi(e) != 0;
-    if (const char* e = std::getenv("AVBD_LOOP")) w->loopMode = !std::strcmp(e, "launch") ? 1 : (!std::strcmp(e, "grid") ? 2 : (!std::strcmp(e, "cluster") ? 3 : 0));
+    if (const char* e = std::getenv("AVBD_LOOP")) w->loopMode = !std::strcmp(e, "launch") ? 1 : (!std::strcmp(e, "grid") ? 2 : (!std::strcmp(e, "cluster") ? 3 : (!std::strcmp(e, "warps") ? 4 : 0)));
     if (const char* e = std::getenv("AVBD_INCREMENTAL_COLOUR")) w->incrementalColour = std::atoi(e) != 0;
     std::memset(w->hCnt, 0, sizeof(Counters));
     avbd_default_params(w);

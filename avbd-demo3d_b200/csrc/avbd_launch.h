@@ -139,6 +139,9 @@ void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGe
 // Returns false if the launch was refused (caller falls back to per-colour launches).
 bool launch_solve_loop_grid(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* ranges, int nColours,
                             const int* nWarps, const int* off, SolveParams prm, Diag* diag, const int* freeList, int nFree);
+// The same loop as ONE thread-block cluster of up to 16 CTAs, hardware cluster barrier between colour phases (small worlds).
+bool launch_solve_loop_warps(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* ranges, int nColours,
+                             const int* nWarps, const int* off, SolveParams prm, Diag* diag, const int* freeList, int nFree);
 // Dynamic bodies no contact visits that a joint / spring links to another body (listed by the graph stage), filtered to one colour
 // (onlyColour < 0: no filter).
 void launch_primal_free(cudaStream_t s, BodyView b, ForceView fv, const int* freeList, int nFree, const int* colour, int onlyColour, SolveParams prm,

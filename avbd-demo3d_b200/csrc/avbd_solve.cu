@@ -773,12 +773,18 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
 // colour phases of a few microseconds each; a grid barrier costs less than a launch + drain + ramp-up, and nothing but the barrier
 // sits between two phases.  Poses / lambda / penalty are read through L2 only (COH).  The step's last dual pass stays a launch of its own.
 struct SweepPlan { int nColours; int nWarps[64]; int off[64]; };
-template <int MINB>
+// CLUSTER: the grid is ONE thread-block cluster (<= 16 CTAs = 64 warps) and phases are separated by the hardware cluster barrier
+// (release / acquire at cluster scope, a fraction of a microsecond) instead of a grid-wide barrier: the small-world form.
+__device__ __forceinline__ void phase_barrier_cluster() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int MINB, bool CLUSTER>
 __global__ void __launch_bounds__(32 * kSweepWarps, MINB) solve_loop_grid(BodyView b, const int4* __restrict__ visits, VisitGeom vg, ManifoldSet ms, ForceView fv,
                                                                          const int* __restrict__ ranges, SweepPlan plan, SolveParams prm, Diag* __restrict__ diag,
                                                                          const int* __restrict__ freeList, int nFree) {
     __shared__ WarpPipe pipes[kSweepWarps];
     cg::grid_group grid = cg::this_grid();
+    if (CLUSTER) cudaGridDependencySynchronize();                           // launched with programmatic stream serialization
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw0 = blockIdx.x * kSweepWarps + warp, nGridWarps = gridDim.x * kSweepWarps;
     const int total = prm.iterations + (prm.postStabilize ? 1 : 0);
@@ -800,7 +806,7 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) solve_loop_grid(BodyVi
                 }
             }
             freeDone = true;
-            grid.sync();
+            if (CLUSTER) phase_barrier_cluster(); else grid.sync();
         }
         biasDual = it < prm.iterations ? fminf(fmaxf(1.0f - alpha, 0.0f), 1.0f) : -1.0f;
     }
@@ -1080,8 +1086,8 @@ void launch_primal_sweep(cudaStream_t s, BodyView b, const int4* visits, VisitGe
 // Returns false if the launch was refused (caller falls back to per-colour launches).
 template <int MINB> static int loop_blocks_per_sm() {
     int per = 0;
-    cudaFuncSetAttribute(solve_loop_grid<MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, solve_loop_grid<MINB>, 32 * kSweepWarps, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 0; }
+    cudaFuncSetAttribute(solve_loop_grid<MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, solve_loop_grid<MINB, false>, 32 * kSweepWarps, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 0; }
     return per;
 }
 bool launch_solve_loop_grid(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* ranges, int nColours,
@@ -1109,9 +1115,49 @@ bool launch_solve_loop_grid(cudaStream_t s, BodyView b, const int4* visits, Visi
     if (grid > residentDev[dev]) grid = residentDev[dev];
     void* args[] = {&b, &visits, &vg, &ms, &fv, &ranges, &plan, &prm, &diag, &freeList, &nFree};
     cudaError_t e = sweep_cfg() == 4
-        ? cudaLaunchCooperativeKernel((void*)solve_loop_grid<4>, dim3(grid), dim3(32 * kSweepWarps), args, 0, s)
-        : cudaLaunchCooperativeKernel((void*)solve_loop_grid<5>, dim3(grid), dim3(32 * kSweepWarps), args, 0, s);
+        ? cudaLaunchCooperativeKernel((void*)solve_loop_grid<4, false>, dim3(grid), dim3(32 * kSweepWarps), args, 0, s)
+        : cudaLaunchCooperativeKernel((void*)solve_loop_grid<5, false>, dim3(grid), dim3(32 * kSweepWarps), args, 0, s);
     if (e != cudaSuccess) { cudaGetLastError(); residentDev[dev] = -1; return false; }
+    return true;
+}
+
+// The same loop as ONE thread-block cluster (small worlds: every colour fits the cluster's warps a few times over).
+bool launch_solve_loop_warps(cudaStream_t s, BodyView b, const int4* visits, VisitGeom vg, ManifoldSet ms, ForceView fv, const int* ranges, int nColours,
+                             const int* nWarps, const int* off, SolveParams prm, Diag* diag, const int* freeList, int nFree) {
+    static int maxClusterDev[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!maxClusterDev[dev]) {
+        int mc = 16;
+        if (cudaFuncSetAttribute(solve_loop_grid<4, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); mc = 8; }
+        else if (const char* e = getenv("AVBD_CLUSTER_MAX")) { int v = atoi(e); if (v >= 1 && v <= 16) mc = v; }
+        maxClusterDev[dev] = mc;
+    }
+    if (nColours <= 0 || nColours > 64) return false;
+    SweepPlan plan{};
+    plan.nColours = nColours;
+    int mx = 1;
+    for (int c = 0; c < nColours; ++c) {
+        plan.nWarps[c] = nWarps[c]; plan.off[c] = off[c];
+        int need = nWarps[c] + (c == 0 ? (nFree + 31) / 32 : 0);
+        mx = need > mx ? need : mx;
+    }
+    int nCta = 1;
+    while (nCta * kSweepWarps < mx && nCta < maxClusterDev[dev]) nCta <<= 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nCta); cfg.blockDim = dim3(32 * kSweepWarps); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, solve_loop_grid<4, true>, b, visits, vg, ms, fv, ranges, plan, prm, diag, freeList, nFree);
+    if (e != cudaSuccess && nCta > 8) {          // a 16-CTA cluster may not be placeable: retry with the portable size
+        cudaGetLastError();
+        maxClusterDev[dev] = 8;
+        attr[0].val.clusterDim.x = 8; cfg.gridDim = dim3(8);
+        e = cudaLaunchKernelEx(&cfg, solve_loop_grid<4, true>, b, visits, vg, ms, fv, ranges, plan, prm, diag, freeList, nFree);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
     return true;
 }
 

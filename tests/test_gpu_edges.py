@@ -246,3 +246,32 @@ def test_live_parameter_edits(avbd):
     assert np.abs(a[:, 1] - b[:, 1]).max() < 1e-3 and np.abs(b[1:, 7:]).max() < 1e-3
     assert (w.diagnostics()["manifolds"], w.diagnostics()["contacts"]) == (o.diagnostics()["manifolds"], o.diagnostics()["contacts"]) == (2, 8)
     o.close(); w.close()
+
+
+def test_world_wider_than_1024_cells_pair_set_exact(avbd):
+    """The broadphase identifies a cell inside a bucket by 10 bits per axis (`pack_cell`): two cells exactly 1024 cells apart share
+    that identity, and share a bucket whenever their block hashes collide.  Bodies placed in cells that alias this way (clusters
+    1024 and 2048 cells apart along each axis, unit cubes: cell edge 1.749) must still give exactly the reference's pair set — the
+    sphere test rejects what the mix-up lets through."""
+    rng = np.random.default_rng(17)
+    cell = 2.02 * 0.5 * np.sqrt(3.0)               # 2.02 x the bounding radius of a unit cube (prepare())
+    bodies = []
+    for off in ((0, 0, 0), (1024, 0, 0), (2048, 0, 0), (0, 1024, 0), (0, 0, 1024), (1024, 1024, 1024)):
+        base = np.array(off, np.float64) * cell
+        for _ in range(40):
+            p = base + rng.uniform(0.0, 3.0 * cell, 3)
+            bodies.append(dict(size=(1, 1, 1), density=1.0, friction=0.5, pos=tuple(np.float32(p)), quat=(0, 0, 0, 1), lin=(0, 0, 0), ang=(0, 0, 0)))
+    o = Oracle("port").create()
+    w = avbd.World()
+    add_all(o, bodies); add_all(w, bodies)
+    try:
+        got = set((int(a), int(b)) for a, b in w.stage_broadphase())
+        want = set((int(a), int(b)) for a, b in o.overlap_pairs())
+        assert got == want, (len(got), len(want), sorted(got ^ want)[:10])
+        assert len(want) > 100
+        far = [(a, b) for a, b in want if abs(bodies[a]["pos"][0] - bodies[b]["pos"][0]) > 100]
+        assert not far
+        w.step(2)                                   # and the rest of the pipeline runs at these coordinates
+        assert w.diagnostics()["nanEvents"] == 0
+    finally:
+        o.close(); w.close()

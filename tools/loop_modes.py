@@ -15,7 +15,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         ms = w.step_timed(100); out[f"grid{n}"] = round(100 / (ms * 1e-3), 1); w.close()
     print(json.dumps(out))
 else:
-    for mode in ("launch", "cluster"):
+    for mode in ("launch", "cluster", "warps"):
         env = dict(os.environ, AVBD_LOOP=mode, AVBD_PERSISTENT_MAX_BODIES="8192")
         r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         print(mode, r.stdout.strip(), r.stderr[-300:])
