@@ -122,7 +122,9 @@ struct avbd_world {
 
     // per-kernel profiling (avbd_set_profiling): events around every primal sweep and dual pass
     bool profiling = false;
-    std::vector<cudaEvent_t> pev;
+    // one record per profiled step, resolved at avbd_get_profile: no host wait inside or between the profiled steps
+    struct ProfStep { cudaEvent_t ev[7]; std::vector<cudaEvent_t> dual; int timedDuals, total, colours, duals, deferred, rebuilt; long long n, nDyn, pairs, cand, nM, nMPrev, contacts, visits; };
+    std::vector<ProfStep> profSteps; int profUsed = 0; ProfStep* profCur = nullptr;
     avbd_profile prof{};
     DevBuf<float> stateDev;
 
@@ -164,6 +166,12 @@ struct avbd_world {
 };
 
 namespace {
+
+// Stage boundary k of the current step: the last-step events avbd_get_step_stats reads, and the profiled step's own record.
+inline void stage_event(avbd_world* w, int k) {
+    if (w->timed) cudaEventRecord(w->ev[k], w->stream);
+    if (w->profCur) cudaEventRecord(w->profCur->ev[k], w->stream);
+}
 
 int read_counters(avbd_world* w) {
     CK(cudaMemcpyAsync(w->hCnt, w->dCnt, sizeof(Counters), cudaMemcpyDeviceToHost, w->stream));
@@ -383,10 +391,10 @@ int run_collide(avbd_world* w) {
     cudaStream_t s = w->stream;
     TRY(prepare(w));
     if (w->n > 0) CK(cudaMemsetAsync(w->dDiag.p, 0, sizeof(Diag) * w->nWorlds, s));
-    if (w->timed || w->profiling) cudaEventRecord(w->ev[0], s);
+    stage_event(w, 0);
     w->nMPrev = w->nM;
     TRY(run_broadphase(w, true));
-    if (w->timed || w->profiling) cudaEventRecord(w->ev[1], s);
+    stage_event(w, 1);
     int nSurv = w->nCand;
     int nxt = w->cur ^ 1;
     if (nSurv > 0) {
@@ -419,7 +427,7 @@ int run_collide(avbd_world* w) {
     }
     w->graphValid = sameTopology;
     w->visitGeomStale = true;         // every contact was rebuilt
-    if (w->timed || w->profiling) cudaEventRecord(w->ev[2], s);
+    stage_event(w, 2);
     CK(cudaGetLastError());
     return 0;
 }
@@ -657,12 +665,21 @@ int run_velocity(avbd_world* w) {
 
 int step_once(avbd_world* w) {
     cudaStream_t s = w->stream;
+    w->profCur = nullptr;
+    if (w->profiling) {
+        if (w->profUsed == (int)w->profSteps.size()) {
+            avbd_world::ProfStep ps{};
+            for (auto& e : ps.ev) CK(cudaEventCreate(&e));
+            w->profSteps.push_back(ps);
+        }
+        w->profCur = &w->profSteps[w->profUsed++];
+    }
     TRY(run_collide(w));
     TRY(run_predict(w));
-    if (w->timed || w->profiling) cudaEventRecord(w->ev[3], s);
+    stage_event(w, 3);
     bool rebuiltGraph = !w->graphValid;
     if (!w->graphValid) TRY(run_colour(w)); else w->graphReuses++;
-    if (w->timed || w->profiling) cudaEventRecord(w->ev[4], s);
+    stage_event(w, 4);
     int total = w->prm.iterations + (w->prm.postStabilize ? 1 : 0);
     bool prof = w->profiling;
     ForceView fvAll = w->fview();
@@ -702,7 +719,7 @@ int step_once(avbd_world* w) {
     // Profiling: the iteration loop is timed as a whole (stage events 4 -> 5) and only the stand-alone dual launches are bracketed by
     // their own events — an event between every pair of sweeps would serialise launches that otherwise overlap (programmatic
     // dependent launch) and inflate the very thing it measures.  ms_primal = loop - stand-alone duals.
-    if (prof) while ((int)w->pev.size() < 2 * total + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); w->pev.push_back(e); }
+    if (prof) while ((int)w->profCur->dual.size() < 2 * total + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); w->profCur->dual.push_back(e); }
     // Deferred dual: the manifold rows' dual pass of iteration k rides on sweep k+1 (each contact's first visit applies it);
     // only the pass after the LAST sweep runs as a kernel.  AVBD_SEPARATE_DUAL=1 keeps one dual launch per iteration.
     const char* sepEnv = getenv("AVBD_SEPARATE_DUAL");
@@ -717,38 +734,24 @@ int step_once(avbd_world* w) {
         if (it < w->prm.iterations) {
             bool lastSweep = it == total - 1;                 // nothing moves after this pass: it also reduces the contact diagnostics
             bool standalone = separateDual || lastSweep;
-            if (prof && standalone) cudaEventRecord(w->pev[2 * timedDuals], s);
+            if (prof && standalone) cudaEventRecord(w->profCur->dual[2 * timedDuals], s);
             if (separateDual) { TRY(run_dual(w, a, lastSweep)); ++duals; }
             else if (lastSweep) { TRY(run_dual(w, a, true, true, w->prm.iterations, false)); ++duals; }
             else { TRY(run_dual(w, a, false, false)); pendingBias = dual_bias(a); }
-            if (prof && standalone) { cudaEventRecord(w->pev[2 * timedDuals + 1], s); ++timedDuals; }
+            if (prof && standalone) { cudaEventRecord(w->profCur->dual[2 * timedDuals + 1], s); ++timedDuals; }
         } else if (!separateDual && w->anyUnvisited && w->prm.iterations > 0) {
             TRY(run_dual(w, 1.0f, false, true, w->prm.iterations, true));    // postStabilize: contacts between static bodies only
         }
     }
-    if (w->timed || w->profiling) cudaEventRecord(w->ev[5], s);
+    stage_event(w, 5);
     TRY(run_velocity(w));
-    if (w->timed || w->profiling) cudaEventRecord(w->ev[6], s);
-    if (prof) {
-        CK(cudaStreamSynchronize(s));
-        float loopMs = 0.0f, dualMs = 0.0f;
-        cudaEventElapsedTime(&loopMs, w->ev[4], w->ev[5]);
-        for (int k = 0; k < timedDuals; ++k) { float b = 0; cudaEventElapsedTime(&b, w->pev[2 * k], w->pev[2 * k + 1]); dualMs += b; }
-        w->prof.ms_primal += loopMs - dualMs; w->prof.ms_dual += dualMs;
-        long long contacts = 0, visits = 0;
-        for (int k = 0; k < w->nWorlds && w->hDiag; ++k) { contacts += w->hDiag[k].activeContacts; visits += w->hDiag[k].contactVisits; }
-        w->prof.steps += 1;
-        w->prof.primal_sweeps += total; w->prof.primal_launches += (long long)total * w->nColours;
-        w->prof.primal_bodies += (long long)total * w->nDyn; w->prof.primal_visits += (long long)total * visits;
-        w->prof.dual_launches += duals; w->prof.dual_contacts += (long long)duals * contacts;
-        w->prof.deferred_dual_contacts += (long long)deferred * contacts;
-        float t[6] = {0, 0, 0, 0, 0, 0}, tot = 0;
-        for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], w->ev[k], w->ev[k + 1]);
-        cudaEventElapsedTime(&tot, w->ev[0], w->ev[6]);
-        w->prof.ms_broadphase += t[0]; w->prof.ms_narrowphase += t[1]; w->prof.ms_predict += t[2]; w->prof.ms_graph += t[3];
-        w->prof.ms_solve += t[4]; w->prof.ms_velocity += t[5]; w->prof.ms_step += tot;
-        w->prof.bodies += w->n; w->prof.pairs += w->nPairs; w->prof.candidates += w->nCand; w->prof.manifolds += w->nM; w->prof.manifolds_prev += w->nMPrev;
-        w->prof.contacts += contacts; w->prof.visits += visits; w->prof.graph_builds += rebuiltGraph ? 1 : 0;
+    stage_event(w, 6);
+    if (prof) {          // sizes of this step (all known on the host); times are resolved at avbd_get_profile
+        avbd_world::ProfStep& ps = *w->profCur;
+        ps.timedDuals = timedDuals; ps.total = total; ps.colours = w->nColours; ps.duals = duals; ps.deferred = deferred; ps.rebuilt = rebuiltGraph ? 1 : 0;
+        ps.n = w->n; ps.nDyn = w->nDyn; ps.pairs = w->nPairs; ps.cand = w->nCand; ps.nM = w->nM; ps.nMPrev = w->nMPrev; ps.contacts = w->nContacts;
+        ps.visits = w->nColours > 0 ? w->hColVisit[w->nColours - 1].y : 0;
+        w->profCur = nullptr;
     }
     return 0;
 }
@@ -823,7 +826,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
     w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release(); w->deg.release(); w->estart.release(); w->colCursor.release(); w->entries.release(); w->sweepRange.release(); w->colVisit.release(); w->freeList.release(); w->linkedList.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
     w->mcount.release(); w->buildTiles.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
-    for (auto& e : w->pev) cudaEventDestroy(e);
+    for (auto& ps : w->profSteps) { for (auto& e : ps.ev) cudaEventDestroy(e); for (auto& e : ps.dual) cudaEventDestroy(e); }
     if (w->dCnt) cudaFree(w->dCnt);
     if (w->hCnt) cudaFreeHost(w->hCnt);
     if (w->hDiag) cudaFreeHost(w->hDiag);
@@ -1204,7 +1207,7 @@ int avbd_restore(avbd_world* w, const void* buf, long long bytes) {
         TRY(get_dev(ms.cN, c * sizeof(float4))); TRY(get_dev(ms.lp, c * sizeof(ContactLP)));
     }
     CK(cudaStreamSynchronize(s));
-    w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false; w->lastPairs = 0;
+    w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false;      // lastPairs (a sizing hint) is kept: buffers are still there
     return 0;
 }
 
@@ -1229,8 +1232,11 @@ int avbd_step_timed(avbd_world* w, int nSteps, float* ms) {
 
 int avbd_set_profiling(avbd_world* w, int on) {
     if (!w) return fail(AVBD_ERR_ARG, "null world");
+    CK(cudaSetDevice(w->device));
+    CK(cudaStreamSynchronize(w->stream));
     w->profiling = on != 0;
     w->prof = avbd_profile{};
+    w->profUsed = 0; w->profCur = nullptr;
     return 0;
 }
 
@@ -1238,6 +1244,25 @@ int avbd_get_profile(avbd_world* w, avbd_profile* out) {
     if (!w || !out) return fail(AVBD_ERR_ARG, "null argument");
     CK(cudaSetDevice(w->device));
     CK(cudaStreamSynchronize(w->stream));
+    for (int k = 0; k < w->profUsed; ++k) {              // the profiled steps since the last call
+        avbd_world::ProfStep& ps = w->profSteps[k];
+        float t[6] = {0, 0, 0, 0, 0, 0}, tot = 0, dualMs = 0;
+        for (int q = 0; q < 6; ++q) cudaEventElapsedTime(&t[q], ps.ev[q], ps.ev[q + 1]);
+        cudaEventElapsedTime(&tot, ps.ev[0], ps.ev[6]);
+        for (int q = 0; q < ps.timedDuals; ++q) { float b = 0; cudaEventElapsedTime(&b, ps.dual[2 * q], ps.dual[2 * q + 1]); dualMs += b; }
+        cudaGetLastError();
+        avbd_profile& p = w->prof;
+        p.ms_broadphase += t[0]; p.ms_narrowphase += t[1]; p.ms_predict += t[2]; p.ms_graph += t[3]; p.ms_solve += t[4]; p.ms_velocity += t[5]; p.ms_step += tot;
+        p.ms_primal += t[4] - dualMs; p.ms_dual += dualMs;
+        p.steps += 1;
+        p.primal_sweeps += ps.total; p.primal_launches += (long long)ps.total * ps.colours;
+        p.primal_bodies += (long long)ps.total * ps.nDyn; p.primal_visits += (long long)ps.total * ps.visits;
+        p.dual_launches += ps.duals; p.dual_contacts += (long long)ps.duals * ps.contacts;
+        p.deferred_dual_contacts += (long long)ps.deferred * ps.contacts;
+        p.bodies += ps.n; p.pairs += ps.pairs; p.candidates += ps.cand; p.manifolds += ps.nM; p.manifolds_prev += ps.nMPrev;
+        p.contacts += ps.contacts; p.visits += ps.visits; p.graph_builds += ps.rebuilt;
+    }
+    w->profUsed = 0;
     *out = w->prof;
     out->kernel_launches = w->launches; out->library_launches = w->libLaunches;
     return 0;
