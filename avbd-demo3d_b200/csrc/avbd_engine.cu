@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -77,8 +78,11 @@ struct avbd_world {
     DevBuf<BodyPose> pose; DevBuf<BodyAux> aux; DevBuf<BodyVel> vel; DevBuf<BodyInit> init;
     DevBuf<float4> prevLin, size;
     int colouredBodies = -1;     // body count the `colour` array holds a valid colouring for (-1: none)
-    bool incrementalColour = false;   // AVBD_INCREMENTAL_COLOUR=1 (see run_colour)
-    DevBuf<int> colourNext;
+    bool freshColour = true;          // AVBD_ITERATED_COLOUR=1 clears it: rank the bodies by the previous colouring (see run_colour)
+    bool coloursRestored = false;     // `colour` came from a snapshot and no graph has been built since
+    bool topoSameAsLast = false;      // this step's manifolds have last step's slots and contact counts (np_build)
+    DevBuf<int> colourWord;           // work words of the colouring rounds
+    std::vector<int> savedColours;    // colouring read from a snapshot, uploaded by prepare()
     DevBuf<int> flags, worldId, localIdx, dynList, colWorkA, colWorkB;      // colWork*: uncoloured-body work lists of the colouring rounds
     bool topoDirty = true;
     bool contactDiagDone = false;   // the step's last dual pass reduced the contact diagnostics already
@@ -87,7 +91,7 @@ struct avbd_world {
     // broadphase
     float cell = 1.0f; unsigned tableSize = 256;
     DevBuf<unsigned> cellKey, cellKeySorted; DevBuf<int> cellVal, cellValSorted; DevBuf<int2> cellRange;
-    DevBuf<int2> sortedCell; DevBuf<float4> sortedPos;
+    DevBuf<int2> sortedCell; DevBuf<float4> sortedPos, sortedRot, sortedSize;
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<int> candCode, candCodeSorted;
@@ -107,6 +111,8 @@ struct avbd_world {
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
     int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
     long long graphReuses = 0; int persistentMaxBodies = 0;      // the tile cluster loop (solve_loop_cluster) is opt-in (AVBD_PERSISTENT_MAX_BODIES): measured (tools/loop_modes.py) the per-colour sweep launches match or beat it at every size (TwoBlockDrop 6.8k vs 6.6k steps/s, Pyramid 3.75k vs 3.6k, Stress1000 1.39k vs 1.23k, 8000 bodies 1.26k vs 0.69k)
+    bool bodySweep = true;  // AVBD_BROADPHASE=cell: fused per-cell sweep + SAT cull instead of the per-body sweep + separate cull
+    double hostLoopSec = 0.0; long long hostLoopSteps = 0;   // AVBD_DEBUG: host time spent issuing the iteration loop's launches
     int loopMode = 0;      // AVBD_LOOP: 0 auto, 1 per-colour launches, 2 cooperative grid loop, 3 tile cluster loop where eligible, 4 warp-pipeline cluster loop
 
     // user forces
@@ -154,7 +160,7 @@ struct avbd_world {
     GridView gview() {
         GridView g; g.cell = cell; g.tableMask = tableSize - 1; g.key = cellKey.p; g.keySorted = cellKeySorted.p;
         g.val = cellVal.p; g.valSorted = cellValSorted.p; g.cellRange = cellRange.p;
-        g.sortedCell = sortedCell.p; g.sortedPos = sortedPos.p; g.largeList = largeList.p; g.worldLargeStart = worldLargeStart.p;
+        g.sortedCell = sortedCell.p; g.sortedPos = sortedPos.p; g.sortedRot = sortedRot.p; g.sortedSize = sortedSize.p; g.largeList = largeList.p; g.worldLargeStart = worldLargeStart.p;
         return g;
     }
     ForceView fview() {
@@ -166,6 +172,8 @@ struct avbd_world {
 };
 
 namespace {
+
+constexpr size_t kPickSlotOffset = (sizeof(Counters) + 7) / 8 * 8;     // 8-byte aligned scratch word after the counters (avbd_pick)
 
 // Stage boundary k of the current step: the last-step events avbd_get_step_stats reads, and the profiled step's own record.
 inline void stage_event(avbd_world* w, int k) {
@@ -273,6 +281,7 @@ int prepare(avbd_world* w) {
         // per-body scratch
         TRY(w->cellKey.ensure(n, false, s)); TRY(w->cellKeySorted.ensure(n, false, s)); TRY(w->cellVal.ensure(n, false, s));
         TRY(w->cellValSorted.ensure(n, false, s)); TRY(w->sortedCell.ensure(n, false, s)); TRY(w->sortedPos.ensure(n, false, s));
+        TRY(w->sortedRot.ensure(n, false, s)); TRY(w->sortedSize.ensure(n, false, s));
         TRY(w->cellRange.ensure(table, false, s));
         TRY(w->adjRange.ensure(n, false, s)); TRY(w->colour.ensure(n, false, s));
         TRY(w->colKey.ensure(std::max(1, w->nDyn), false, s)); TRY(w->colKeySorted.ensure(std::max(1, w->nDyn), false, s));
@@ -293,6 +302,12 @@ int prepare(avbd_world* w) {
         }
         w->graphValid = false;
         w->colouredBodies = -1;          // the colour array was reallocated / the body set changed
+        if ((int)w->savedColours.size() == n && n > 0) {                     // ... unless a snapshot brought the colouring along
+            CK(cudaMemcpyAsync(w->colour.p, w->savedColours.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+            w->colouredBodies = n; w->coloursRestored = true;
+        }
+        w->savedColours.clear();
     }
     if (w->forcesDirty || w->topoDirty) {
         int nj = (int)w->hJoints.size(), ns = (int)w->hSprings.size();
@@ -357,13 +372,17 @@ int run_broadphase(avbd_world* w, bool sat) {
         CK(cudaMemsetAsync(w->dCnt, 0, sizeof(Counters), s));
         PairSink raw; raw.keys = w->pairs.p; raw.codes = nullptr; raw.cap = (int)w->pairs.cap; raw.keyShift = w->keyShift;
         raw.count = &w->dCnt->nPairs; raw.cnt = w->dCnt; raw.overflowBit = 1;
-        launch_dep(bp_sweep, dim3(blocks_for(16ll * n)), dim3(kThreads), 0, s, bv, gv, raw);
+        PairSink out; out.keys = w->cand.p; out.codes = w->candCode.p; out.cap = (int)std::min(w->cand.cap, w->candCode.cap); out.keyShift = w->keyShift;
+        out.count = &w->dCnt->nCand; out.cnt = w->dCnt; out.overflowBit = 2;
+        // small-vs-small pairs: one warp per 32 cell-sorted bodies; with `sat` the cull is fused in and only survivors are written.
+        // AVBD_BROADPHASE=cell selects the fused per-cell kernel (A/B measurements; default is the per-body sweep + separate cull).
+        if (sat && !w->bodySweep) launch_dep(bp_sweep_cells<true>, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)w->excl.p, w->nExcl, out);
+        else if (!w->bodySweep) launch_dep(bp_sweep_cells<false>, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)nullptr, 0, raw);
+        else launch_dep(bp_sweep, dim3(blocks_for(16ll * n)), dim3(kThreads), 0, s, bv, gv, raw);
         if (w->nLarge) launch_dep(bp_large, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, raw);
         w->launches += 1 + (w->nLarge ? 1 : 0);
         if (sat) {
             if (w->nM > 0) { launch_dep(bp_persisting, dim3(blocks_for(w->nM)), dim3(kThreads), 0, s, bv, w->mset(w->cur), w->nM, raw); w->launches++; }
-            PairSink out; out.keys = w->cand.p; out.codes = w->candCode.p; out.cap = (int)std::min(w->cand.cap, w->candCode.cap); out.keyShift = w->keyShift;
-            out.count = &w->dCnt->nCand; out.cnt = w->dCnt; out.overflowBit = 2;
             // sized by the pair count of the previous step (+ slack); the kernel reads the real count, a shortfall shows as overflow bit 16
             long long expect = std::min<long long>((long long)raw.cap, std::max<long long>(w->lastPairs + w->lastPairs / 8 + 4096, 1024));
             np_sat_launch(w, bv, raw, (int)expect, out);
@@ -371,7 +390,7 @@ int run_broadphase(avbd_world* w, bool sat) {
         TRY(read_counters(w));
         bool rawOver = w->hCnt->nPairs > raw.cap, satShort = sat && w->hCnt->nPairs > w->satLaunched, outOver = sat && w->hCnt->nCand > (int)std::min(w->cand.cap, w->candCode.cap);
         w->lastPairs = w->hCnt->nPairs;
-        if (!rawOver && !satShort && !outOver) { w->nPairs = w->hCnt->nPairs; w->nCand = sat ? w->hCnt->nCand : w->hCnt->nPairs; break; }
+        if (!rawOver && !satShort && !outOver) { w->nPairs = w->hCnt->nPairs + w->hCnt->nSphere; w->nCand = sat ? w->hCnt->nCand : w->hCnt->nPairs; break; }
         if (rawOver) TRY(w->pairs.ensure((size_t)w->hCnt->nPairs + w->hCnt->nPairs / 4 + 1024, false, s));
         if (outOver) { TRY(w->cand.ensure((size_t)w->hCnt->nCand + w->hCnt->nCand / 4 + 1024, false, s)); TRY(w->candCode.ensure(w->cand.cap, false, s)); }
         if (attempt == 7) return fail(AVBD_ERR_CAPACITY, "pair buffer kept overflowing");
@@ -418,7 +437,8 @@ int run_collide(avbd_world* w) {
         w->nContacts = 0;
     }
     // adjacency, colouring and visit lists only depend on (pair, contact count) per slot: keep them when nothing moved
-    bool sameTopology = w->graphValid && nSurv == w->nM && nSurv > 0 && !w->hCnt->topoChanged && !w->forceRegraph;
+    w->topoSameAsLast = nSurv == w->nM && nSurv > 0 && !w->hCnt->topoChanged;
+    bool sameTopology = w->graphValid && w->topoSameAsLast && !w->forceRegraph;
     w->cur = nxt; w->nM = nSurv;
     ForceView fv = w->fview();
     if (fv.nJoints + fv.nSprings > 0) {
@@ -484,28 +504,27 @@ int run_colour(avbd_world* w) {
     launch_dep(entry_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->estart.p, w->entries.p);
     w->launches += 2;
     ForceView fv = w->fview();
-    // Opt-in (AVBD_INCREMENTAL_COLOUR=1): keep last step's colouring of the same body set and uncolour only what new manifolds put
-    // in conflict.  The graph stage gets cheaper but the colouring drifts to more, evenly filled colours (9 against 7 on the 1M-box
-    // grid; Stress1000 7 against 5), and every colour is a dependent phase of each sweep: measured a net loss, so colouring from
-    // scratch — a pure function of the current graph — stays the default.
-    bool incremental = w->incrementalColour && w->colouredBodies == n && !w->forceRegraph;
-    if (incremental) {
-        TRY(w->colourNext.ensure(n, false, s));
-        CK(cudaMemcpyAsync(w->colourNext.p, w->colour.p, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));     // static bodies keep -2
-        launch_dep(colour_conflicts, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colour.p,
-                                                                  w->colourNext.p);
-        std::swap(w->colour.p, w->colourNext.p); std::swap(w->colour.cap, w->colourNext.cap);
-    } else {
-        launch_dep(colour_init, dim3(blocks_for(n)), dim3(kThreads), 0, s, w->flags.p, n, w->colour.p);
-    }
+    // Default: hashed priority order only — the colouring is a pure function of the current graph.
+    // Opt-in (AVBD_ITERATED_COLOUR=1): the previous colouring of the same body set ranks the bodies (avbd_kernels_graph.cuh: outranks),
+    // Culberson's iterated greedy.  Fewer colours and fewer rounds (1M-box grid 9 -> 7 colours, step 7.73 -> 7.59 ms; 8192-world
+    // ensemble 4 -> 3, 3.55 -> 3.39 ms; 8000-box grid 6 -> 5, 0.81 -> 0.73 ms), but a chain of bodies ends up two-coloured and a
+    // red/black sweep carries a load change two links per iteration: the 10-box Stack then rests 1.8e-3 m from the reference's heights
+    // instead of < 1e-3 (tests/test_gpu_scenes.py), so it is not the default.  The colouring then also depends on the world's history:
+    // a snapshot carries the colours, and a restored world whose first step finds the topology it was saved with keeps them as they are.
+    const bool havePrev = !w->freshColour && w->colouredBodies == n;
+    const bool keepSaved = havePrev && w->coloursRestored && w->topoSameAsLast;
+    w->coloursRestored = false;
+    TRY(w->colourWord.ensure(n, false, s));
+    if (!keepSaved) launch_dep(colour_init, dim3(blocks_for(n)), dim3(kThreads), 0, s, w->flags.p, n, havePrev ? (const int*)w->colour.p : (const int*)nullptr, w->colourWord.p, w->colour.p);
     w->launches++;
     w->colouredBodies = -1;
     // Jones-Plassmann rounds (= the sequential greedy colouring in hashed-priority order, whatever the timing), all in ONE launch:
     // one block for small worlds, a cooperative grid with a grid barrier per round otherwise — no host check of the uncoloured count
     // between rounds.  If the cooperative launch is refused, rounds are launched in batches with a host check per batch.
-    bool coloured = false;
-    if (w->nDyn <= kColourBlockMaxBodies) {
-        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colour.p, w->dCnt, n);
+    bool coloured = keepSaved;
+    if (coloured) {
+    } else if (w->nDyn <= kColourBlockMaxBodies) {
+        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colourWord.p, w->colour.p, w->dCnt, n);
         w->launches++;
         coloured = true;
     } else {
@@ -522,9 +541,9 @@ int run_colour(avbd_world* w) {
             TRY(w->colWorkA.ensure((size_t)w->nDyn, false, s)); TRY(w->colWorkB.ensure((size_t)w->nDyn, false, s)); TRY(w->colCursor.ensure(4, false, s));
             CK(cudaMemsetAsync(w->colCursor.p, 0, 4 * sizeof(int), s));
             const int* dynList = w->dynList.p; int nDyn = w->nDyn; const int* estart = w->estart.p; const int4* entries = w->entries.p;
-            const int* localIdx = w->localIdx.p; volatile int* colour = w->colour.p; Counters* cnt = w->dCnt;
+            const int* localIdx = w->localIdx.p; volatile int* word = w->colourWord.p; int* colour = w->colour.p; Counters* cnt = w->dCnt;
             int* listA = w->colWorkA.p; int* listB = w->colWorkB.p; int* cursors = w->colCursor.p;
-            void* args[] = {&dynList, &nDyn, &estart, &entries, &fv, &localIdx, &colour, &cnt, &listA, &listB, &cursors};
+            void* args[] = {&dynList, &nDyn, &estart, &entries, &fv, &localIdx, &word, &colour, &cnt, &listA, &listB, &cursors};
             int grid = std::min(resident, blocks_for(w->nDyn, kColourGridThreads));
             cudaError_t e = cudaLaunchCooperativeKernel((void*)colour_rounds_grid, dim3(grid), dim3(kColourGridThreads), args, 0, s);
             if (e == cudaSuccess) { w->launches++; coloured = true; } else { cudaGetLastError(); resident = -1; }
@@ -532,11 +551,11 @@ int run_colour(avbd_world* w) {
     }
     if (!coloured) {
         const int* list = w->dynList.p; int listCount = w->nDyn; int which = 0;
-        for (int round = 0, batch = incremental ? 2 : 6;;) {
+        for (int round = 0, batch = 6;;) {
             if (round > 4096) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
             CK(cudaMemsetAsync(&w->dCnt->nUncoloured, 0, sizeof(int), s));
             for (int k = 0; k < batch; ++k)
-                launch_dep(colour_round, dim3(blocks_for(listCount)), dim3(kThreads), 0, s, list, listCount, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colour.p,
+                launch_dep(colour_round, dim3(blocks_for(listCount)), dim3(kThreads), 0, s, list, listCount, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colourWord.p, w->colour.p,
                                                                         w->dCnt, k == batch - 1);
             w->launches += batch; round += batch;
             TRY(read_counters(w));
@@ -726,6 +745,7 @@ int step_once(avbd_world* w) {
     const bool separateDual = sepEnv && atoi(sepEnv) != 0;
     int duals = 0, deferred = 0, timedDuals = 0;
     float pendingBias = -1.0f;
+    const auto hostT0 = std::chrono::steady_clock::now();
     for (int it = 0; it < total && !persistent && !gridLoop; ++it) {
         float a = w->prm.postStabilize ? (it < w->prm.iterations ? 1.0f : 0.0f) : w->prm.alpha;   // solver.cpp:340-342
         TRY(run_primal(w, a, nullptr, pendingBias));
@@ -743,6 +763,7 @@ int step_once(avbd_world* w) {
             TRY(run_dual(w, 1.0f, false, true, w->prm.iterations, true));    // postStabilize: contacts between static bodies only
         }
     }
+    w->hostLoopSec += std::chrono::duration<double>(std::chrono::steady_clock::now() - hostT0).count(); w->hostLoopSteps++;
     stage_event(w, 5);
     TRY(run_velocity(w));
     stage_event(w, 6);
@@ -796,7 +817,7 @@ avbd_world* avbd_world_create(int device) {
     avbd_world* w = new avbd_world();
     w->device = device;
     if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&w->dCnt, sizeof(Counters) + 16) != cudaSuccess || cudaMallocHost(&w->hCnt, sizeof(Counters)) != cudaSuccess) {
+        cudaMalloc(&w->dCnt, kPickSlotOffset + 8) != cudaSuccess || cudaMallocHost(&w->hCnt, sizeof(Counters)) != cudaSuccess) {
         fail(AVBD_ERR_CUDA, "world allocation failed");
         delete w;
         return nullptr;
@@ -804,8 +825,9 @@ avbd_world* avbd_world_create(int device) {
     for (auto& e : w->ev) cudaEventCreate(&e);
     if (const char* e = std::getenv("AVBD_PERSISTENT_MAX_BODIES")) w->persistentMaxBodies = std::atoi(e);
     if (const char* e = std::getenv("AVBD_FORCE_REGRAPH")) w->forceRegraph = std::atoi(e) != 0;
+    if (const char* e = std::getenv("AVBD_BROADPHASE")) w->bodySweep = std::strcmp(e, "cell") != 0;
     if (const char* e = std::getenv("AVBD_LOOP")) w->loopMode = !std::strcmp(e, "launch") ? 1 : (!std::strcmp(e, "grid") ? 2 : (!std::strcmp(e, "cluster") ? 3 : (!std::strcmp(e, "warps") ? 4 : 0)));
-    if (const char* e = std::getenv("AVBD_INCREMENTAL_COLOUR")) w->incrementalColour = std::atoi(e) != 0;
+    if (const char* e = std::getenv("AVBD_ITERATED_COLOUR")) w->freshColour = std::atoi(e) == 0;
     std::memset(w->hCnt, 0, sizeof(Counters));
     avbd_default_params(w);
     return w;
@@ -815,10 +837,12 @@ void avbd_world_destroy(avbd_world* w) {
     if (!w) return;
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
+    if (std::getenv("AVBD_DEBUG") && w->hostLoopSteps > 0)
+        std::fprintf(stderr, "avbd-demo3d_b200: host time issuing the iteration loop: %.1f us per step over %lld steps\n", 1e6 * w->hostLoopSec / w->hostLoopSteps, w->hostLoopSteps);
     w->pose.release(); w->aux.release(); w->vel.release(); w->init.release(); w->prevLin.release(); w->size.release();
-    w->flags.release(); w->worldId.release(); w->localIdx.release(); w->dynList.release(); w->colWorkA.release(); w->colWorkB.release(); w->colourNext.release();
+    w->flags.release(); w->worldId.release(); w->localIdx.release(); w->dynList.release(); w->colWorkA.release(); w->colWorkB.release(); w->colourWord.release();
     w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellRange.release();
-    w->sortedCell.release(); w->sortedPos.release(); w->largeList.release(); w->worldLargeStart.release();
+    w->sortedCell.release(); w->sortedPos.release(); w->sortedRot.release(); w->sortedSize.release(); w->largeList.release(); w->worldLargeStart.release();
     w->pairs.release(); w->cand.release(); w->candSorted.release(); w->candCode.release(); w->candCodeSorted.release();
     for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cstart.release(); b.cM.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.lp.release(); }
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
@@ -842,6 +866,7 @@ int avbd_clear(avbd_world* w) {
     w->n = 0; w->nDyn = 0; w->nWorlds = 1; w->hb.clear(); w->nM = 0; w->nCand = 0; w->nPairs = 0; w->nContacts = 0;
     w->hJoints.clear(); w->hSprings.clear(); w->hForces.clear(); w->uploadedJoints = 0; w->uploadedSprings = 0; w->nExcl = 0;
     w->topoDirty = true; w->forcesDirty = true; w->graphValid = false; w->nColours = 0;
+    w->colouredBodies = -1; w->coloursRestored = false; w->savedColours.clear();
     if (w->hDiag) std::memset(w->hDiag, 0, sizeof(Diag) * w->hDiagCap);
     return 0;
 }
@@ -1123,12 +1148,13 @@ struct SnapHeader {
     SolveParams prm;
     long long bytes;
 };
-constexpr char kSnapMagic[8] = {'A', 'V', 'B', 'D', 'S', 'N', 'P', '2'};
+constexpr char kSnapMagic[8] = {'A', 'V', 'B', 'D', 'S', 'N', 'P', '3'};
 size_t snap_bytes(const avbd_world* w) {
     size_t n = w->n, m = w->nM, c = w->nContacts;
     return sizeof(SnapHeader) + n * (sizeof(HostBody) + sizeof(BodyPose) + sizeof(BodyAux) + sizeof(BodyVel) + sizeof(BodyInit) + 2 * sizeof(float4))
          + w->hJoints.size() * sizeof(JointRec) + w->hSprings.size() * sizeof(SpringRec) + w->hForces.size() * sizeof(HostForce)
-         + m * (sizeof(unsigned long long) + sizeof(int4)) + (m + 1) * sizeof(int) + c * (sizeof(int) + 3 * sizeof(float4) + sizeof(ContactLP));
+         + m * (sizeof(unsigned long long) + sizeof(int4)) + (m + 1) * sizeof(int) + c * (sizeof(int) + 3 * sizeof(float4) + sizeof(ContactLP))
+         + sizeof(int) + (w->colouredBodies == w->n ? n * sizeof(int) : 0);        // the colouring the next one is ranked by
 }
 }
 
@@ -1144,7 +1170,7 @@ int avbd_snapshot(avbd_world* w, void* buf, long long cap) {
     char* o = static_cast<char*>(buf);
     SnapHeader h{};
     std::memcpy(h.magic, kSnapMagic, 8);
-    h.version = 2; h.n = w->n; h.nM = w->nM; h.nContacts = w->nContacts; h.nJoints = (int)w->hJoints.size(); h.nSprings = (int)w->hSprings.size();
+    h.version = 3; h.n = w->n; h.nM = w->nM; h.nContacts = w->nContacts; h.nJoints = (int)w->hJoints.size(); h.nSprings = (int)w->hSprings.size();
     h.nForces = (int)w->hForces.size(); h.keyShift = w->keyShift; h.prm = w->prm; h.bytes = (long long)need;
     std::memcpy(o, &h, sizeof(h)); o += sizeof(h);
     auto put_host = [&](const void* src, size_t bytes) { if (bytes) std::memcpy(o, src, bytes); o += bytes; };
@@ -1166,6 +1192,9 @@ int avbd_snapshot(avbd_world* w, void* buf, long long cap) {
     } else {
         int zero = 0; put_host(&zero, sizeof(int));
     }
+    const int hasColours = (w->colouredBodies == w->n && n > 0) ? 1 : 0;
+    put_host(&hasColours, sizeof(int));
+    if (hasColours) TRY(put_dev(w->colour.p, n * sizeof(int)));
     CK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -1175,7 +1204,7 @@ int avbd_restore(avbd_world* w, const void* buf, long long bytes) {
     CK(cudaSetDevice(w->device));
     SnapHeader h;
     std::memcpy(&h, buf, sizeof(h));
-    if (std::memcmp(h.magic, kSnapMagic, 8) != 0 || h.version != 2 || h.bytes > bytes || h.n < 0 || h.nM < 0 || h.nContacts < 0)
+    if (std::memcmp(h.magic, kSnapMagic, 8) != 0 || h.version != 3 || h.bytes > bytes || h.n < 0 || h.nM < 0 || h.nContacts < 0)
         return fail(AVBD_ERR_ARG, "not a snapshot of this library build");
     TRY(avbd_clear(w));
     cudaStream_t s = w->stream;
@@ -1205,7 +1234,13 @@ int avbd_restore(avbd_world* w, const void* buf, long long bytes) {
         TRY(get_dev(ms.key, m * sizeof(unsigned long long))); TRY(get_dev(ms.hdr, m * sizeof(int4))); TRY(get_dev(ms.cstart, (m + 1) * sizeof(int)));
         TRY(get_dev(ms.cM, c * sizeof(int))); TRY(get_dev(ms.cA, c * sizeof(float4))); TRY(get_dev(ms.cB, c * sizeof(float4)));
         TRY(get_dev(ms.cN, c * sizeof(float4))); TRY(get_dev(ms.lp, c * sizeof(ContactLP)));
+    } else {
+        o += sizeof(int);
     }
+    int hasColours = 0;
+    std::memcpy(&hasColours, o, sizeof(int)); o += sizeof(int);
+    w->savedColours.clear(); w->coloursRestored = false;
+    if (hasColours) { w->savedColours.assign(reinterpret_cast<const int*>(o), reinterpret_cast<const int*>(o) + n); o += n * sizeof(int); }
     CK(cudaStreamSynchronize(s));
     w->graphValid = false; w->visitGeomStale = true; w->contactDiagDone = false;      // lastPairs (a sizing hint) is kept: buffers are still there
     return 0;
@@ -1551,7 +1586,7 @@ int avbd_pick(avbd_world* w, const float* origin3, const float* dir3, float* loc
     float l2 = len2(dir);
     if (l2 < 1.0e-6f) return -1;                                    // solver.cpp:153-157
     V3 rayDir = dir / sqrtf(l2);
-    unsigned long long* dBest = reinterpret_cast<unsigned long long*>(w->dCnt + 1);   // scratch slot after the counters
+    unsigned long long* dBest = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(w->dCnt) + kPickSlotOffset);   // scratch slot after the counters
     unsigned long long init = ~0ull, best = ~0ull;
     CK(cudaMemcpyAsync(dBest, &init, sizeof(init), cudaMemcpyHostToDevice, w->stream));
     launch_dep(pick_bodies, dim3(blocks_for(w->n)), dim3(kThreads), 0, w->stream, w->bview(), origin, rayDir, dBest);

@@ -137,45 +137,50 @@ __global__ void visit_geometry(const int4* __restrict__ visits, const int* __res
 __device__ __forceinline__ unsigned mix32(unsigned x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
 }
-// Priority is a function of the WORLD-LOCAL index only, so a world colours the
-// same way wherever it sits in a batch (ensemble runs are partition-invariant).
-__device__ __forceinline__ bool outranks(int localA, int localB) {
+// Priority order of the greedy colouring: rank first (higher goes first), ties by a hash of the WORLD-LOCAL index.  By default every
+// body has rank 0 and the order is the hashed one: the colouring is a pure function of the graph.  With AVBD_ITERATED_COLOUR=1 the
+// rank is the body's colour in the PREVIOUS colouring of the same body set + 1 (0: it had none) — walking the old colour classes
+// one after another is Culberson's iterated greedy: on an unchanged graph the new colouring never needs more colours than the old
+// one and often fewer, and because the members of an old class are (nearly all) mutually non-adjacent the Jones-Plassmann rounds
+// finish in about as many rounds as there are classes.  Rank and hash are world-local quantities, so a world colours the same way
+// wherever it sits in a batch (ensemble runs are partition-invariant).  See run_colour (avbd_engine.cu) for why it is opt-in.
+__device__ __forceinline__ bool outranks(int rankA, int localA, int rankB, int localB) {
+    if (rankA != rankB) return rankA > rankB;
     unsigned ha = mix32((unsigned)localA + 0x9e3779b9u), hb = mix32((unsigned)localB + 0x9e3779b9u);
     return ha != hb ? ha > hb : localA > localB;
 }
-// Priority order of the greedy colouring.  AVBD_COLOUR_LDF: largest degree first (ties by the hash) — degree = manifold entries of the
-// body, a world-local quantity like the hash.
-#ifndef AVBD_COLOUR_LDF
-#define AVBD_COLOUR_LDF 0
-#endif
-__device__ __forceinline__ bool outranks_deg(int localA, int degA, int localB, int degB) {
-    if (AVBD_COLOUR_LDF && degA != degB) return degA > degB;
-    return outranks(localA, localB);
-}
+// Work word of the rounds: low byte = state (0 static, 1 uncoloured, 2 + c coloured c), the rest = priority rank (old colour + 1, 0 = none).
+__device__ __forceinline__ int colour_word(int rank, int state) { return (rank << 8) | state; }
 
-__global__ void colour_init(const int* flags, int n, int* colour) {
+// oldColour: the previous colouring to rank by (nullptr / negative entries: none).  May alias `colour`.
+__global__ void colour_init(const int* flags, int n, const int* oldColour, int* word, int* colour) {
     cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) colour[i] = (flags[i] & kDynamic) ? -1 : -2;
+    if (i >= n) return;
+    const bool dyn = (flags[i] & kDynamic) != 0;
+    int old = oldColour ? oldColour[i] : -1;
+    word[i] = dyn ? colour_word(old >= 0 ? old + 1 : 0, 1) : 0;
+    colour[i] = dyn ? -1 : -2;
 }
 
 // One Jones-Plassmann attempt for body i: it takes the smallest colour unused by its neighbours once every
 // higher-priority neighbour is coloured.  A lower-priority neighbour cannot be coloured before i is, so what i sees
 // coloured is exactly its higher-priority neighbourhood whenever it succeeds: the result is the sequential greedy
-// colouring in priority order, independent of timing (timing only changes how many attempts it takes).
+// colouring in priority order, independent of timing (timing only changes how many attempts it takes).  Reading a
+// neighbour's word while that neighbour writes it is part of the scheme: either value leads to the same colouring.
 // Returns whether the body is coloured after the attempt.
 __device__ __forceinline__ bool try_colour(int i, const int* estart, const int4* entries, const ForceView& fv,
-                                           const int* localIdx, volatile int* colour, Counters* cnt) {
-    if (colour[i] >= 0) return true;
-    int li = localIdx[i];
-    const int di = estart[i + 1] - estart[i];
+                                           const int* localIdx, volatile int* word, int* colour, Counters* cnt) {
+    const int wi = word[i];
+    if ((wi & 255) != 1) return true;
+    const int li = localIdx[i], ri = wi >> 8;
     unsigned long long used = 0ull;
     bool ready = true;
     auto visit = [&](int other) {
         if (other < 0) return;
-        int co = colour[other];
-        if (co >= 0) used |= 1ull << co;
-        else if (co == -1 && outranks_deg(localIdx[other], AVBD_COLOUR_LDF ? estart[other + 1] - estart[other] : 0, li, di)) ready = false;
+        const int wo = word[other], so = wo & 255;
+        if (so >= 2) used |= 1ull << (so - 2);
+        else if (so == 1 && outranks(wo >> 8, localIdx[other], ri, li)) ready = false;
     };
     for (int e = estart[i], e1 = estart[i + 1]; e < e1 && ready; ++e) visit(entries[e].x);
     if (fv.adjStart) {
@@ -188,46 +193,45 @@ __device__ __forceinline__ bool try_colour(int i, const int* estart, const int4*
     if (!ready) return false;
     int c = __ffsll((long long)~used) - 1;
     if (c < 0) { c = 63; atomicOr(&cnt->overflow, 4); }
+    word[i] = colour_word(ri, 2 + c);
     colour[i] = c;
     return true;
 }
 
 __global__ void colour_round(const int* dynList, int nDyn, const int* estart, const int4* entries,
-                             ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt, bool countLeft) {
+                             ForceView fv, const int* localIdx, volatile int* word, int* colour, Counters* cnt, bool countLeft) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
-    if (!try_colour(dynList[t], estart, entries, fv, localIdx, colour, cnt) && countLeft) {
+    if (!try_colour(dynList[t], estart, entries, fv, localIdx, word, colour, cnt) && countLeft) {
         cg::coalesced_group grp = cg::coalesced_threads();
         if (grp.thread_rank() == 0) atomicAdd(&cnt->nUncoloured, (int)grp.size());
     }
 }
 
 // Small worlds: ALL rounds in one block (block barrier between rounds instead of a launch, no host check of the
-// uncoloured count).  Same attempts, hence the same colouring as colour_round.  When the world's colour array fits (nBodies <=
+// uncoloured count).  Same attempts, hence the same colouring as colour_round.  When the world's work words fit (nBodies <=
 // kColourSmemBodies) the rounds run on a shared-memory copy: a round is then a handful of shared-memory reads per body instead of a
 // chain of L2 round trips (Stress1000: 30 -> ~8 us).
 constexpr int kColourBlockThreads = 1024;
 constexpr int kColourSmemBodies = 10240;          // 40 KB of static shared memory
 __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int* estart, const int4* entries,
-                                                                           ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt, int nBodies) {
+                                                                           ForceView fv, const int* localIdx, int* word, int* colour, Counters* cnt, int nBodies) {
     cudaGridDependencySynchronize();
-    __shared__ int sCol[kColourSmemBodies];
-    const bool inSmem = nBodies <= kColourSmemBodies;
-    volatile int* col = colour;
-    if (inSmem) {
-        for (int i = threadIdx.x; i < nBodies; i += blockDim.x) sCol[i] = colour[i];
+    __shared__ int sWord[kColourSmemBodies];
+    volatile int* wd = word;
+    if (nBodies <= kColourSmemBodies) {
+        for (int i = threadIdx.x; i < nBodies; i += blockDim.x) sWord[i] = word[i];
         __syncthreads();
-        col = sCol;
+        wd = sWord;
     }
     int left = 1;
     for (int round = 0; round < 4096 && left; ++round) {
         int mine = 0;
         for (int t = threadIdx.x; t < nDyn; t += blockDim.x)
-            if (!try_colour(dynList[t], estart, entries, fv, localIdx, col, cnt)) mine = 1;
+            if (!try_colour(dynList[t], estart, entries, fv, localIdx, wd, colour, cnt)) mine = 1;
         left = __syncthreads_or(mine);           // also makes this round's colours visible to the whole block
     }
-    if (inSmem) for (int t = threadIdx.x; t < nDyn; t += blockDim.x) { int i = dynList[t]; colour[i] = sCol[i]; }
     if (threadIdx.x == 0) cnt->nUncoloured = left;
 }
 
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const
 // over three slots: the slot a round fills was last READ two barriers ago.
 constexpr int kColourGridThreads = 256;
 __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const int* dynList, int nDyn, const int* estart, const int4* entries,
-                                                                         ForceView fv, const int* localIdx, volatile int* colour, Counters* cnt,
+                                                                         ForceView fv, const int* localIdx, volatile int* word, int* colour, Counters* cnt,
                                                                          int* listA, int* listB, int* cursors) {
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const i
         const int rounded = (count + 31) & ~31;
         for (int t = gtid; t < rounded; t += gsize) {
             bool left = false; int i = 0;
-            if (t < count) { i = list[t]; left = !try_colour(i, estart, entries, fv, localIdx, colour, cnt); }
+            if (t < count) { i = list[t]; left = !try_colour(i, estart, entries, fv, localIdx, word, colour, cnt); }
             unsigned vote = __ballot_sync(0xffffffffu, left);
             if (vote) {
                 int base = 0;
@@ -264,36 +268,7 @@ __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const i
         count = *(volatile int*)cur;
         list = out;
     }
-    if (gtid == 0) cnt->nUncoloured = count;
-}
-
-// Incremental recolouring: last step's colouring is still valid except where a NEW manifold joins two bodies of one colour.
-// Of such a pair the lower-priority body is uncoloured (reads the old colours, writes the new array: no race, no dependence on
-// timing) and the usual rounds then colour only those bodies — typically a few hundred of a million, in one or two rounds
-// instead of the ~17 a colouring from scratch needs.
-__global__ void colour_conflicts(const int* dynList, int nDyn, const int* estart, const int4* entries, ForceView fv,
-                                 const int* localIdx, const int* colourPrev, int* colourOut) {
-    cudaGridDependencySynchronize();
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nDyn) return;
-    int i = dynList[t];
-    int mine = colourPrev[i];
-    if (mine >= 0) {
-        int li = localIdx[i];
-        bool clash = false;
-        auto visit = [&](int other) {
-            if (other >= 0 && colourPrev[other] == mine && outranks(localIdx[other], li)) clash = true;
-        };
-        for (int e = estart[i], e1 = estart[i + 1]; e < e1 && !clash; ++e) visit(entries[e].x);
-        if (fv.adjStart) {
-            for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && !clash; ++k) {
-                int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
-                visit((e & 2) ? (isA ? fv.springs[idx].b : fv.springs[idx].a) : (isA ? fv.joints[idx].b : fv.joints[idx].a));
-            }
-        }
-        if (clash) mine = -1;
-    } else mine = -1;
-    colourOut[i] = mine;
+    if (gtid == 0) { cnt->nUncoloured = count; cnt->colourRounds = round; }
 }
 
 // Work list of the bodies still uncoloured (order is irrelevant: the colouring does not depend on it).

@@ -467,6 +467,9 @@ __device__ __forceinline__ void primal_tile_visits(const BodyView& b, const int*
 constexpr int kQueueSlots = AVBD_QUEUE_SLOTS;
 constexpr bool kVgReg = AVBD_VG_REG != 0, kLpReg = AVBD_LP_REG != 0, kSelfSeg = AVBD_SELF_SEG != 0, kVgBulk = AVBD_VG_BULK != 0 && !kVgReg;
 struct WarpPipe {
+#ifdef AVBD_TIMELINE
+    int tlRow;
+#endif
     float4 rows[32][7];              // this chunk's partial sums, one row of 28 floats per visit: rl(3) ra(3) ll(6) la(9) aa(6) pad
     float4 other[2][32];             // the NEXT chunk's other-body poses, per lane (cp.async)
     float4 selfp[2][32];             // the NEXT chunk's visiting-body poses, per segment (cp.async by the segment's first lane) or per lane
@@ -575,6 +578,26 @@ __device__ __forceinline__ void solve_queue(WarpPipe& w, int qn, int lane, const
     __syncwarp();
 }
 
+// Debug build only (make variant SOLVE_DEFS=-DAVBD_TIMELINE, tools/sweep_timeline.py): %globaltimer stamps of the first warp of every
+// sweep launch — entry, before / after the wait for the predecessor, operands of the first chunk landed, rows of the first chunk
+// stored, range done.  Shows what a colour phase of a small world is made of.
+#ifdef AVBD_TIMELINE
+__device__ unsigned long long g_timeline[16384][6];
+__device__ unsigned g_timelineCount;
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define AVBD_TL(row, slot) do { if ((row) >= 0 && (threadIdx.x & 31) == 0) g_timeline[(row)][(slot)] = global_ns(); } while (0)
+extern "C" int avbd_debug_timeline(unsigned long long* out, int capRows) {
+    unsigned n = 0;
+    if (cudaMemcpyFromSymbol(&n, g_timelineCount, sizeof(n)) != cudaSuccess) return -1;
+    int rows = (int)(n < 16384u ? n : 16384u); if (rows > capRows) rows = capRows;
+    if (rows > 0 && cudaMemcpyFromSymbol(out, g_timeline, (size_t)rows * 6 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    unsigned zero = 0; cudaMemcpyToSymbol(g_timelineCount, &zero, sizeof(zero));
+    return rows;
+}
+#else
+#define AVBD_TL(row, slot) do { } while (0)
+#endif
+
 // One warp's pipeline over the visits [vBegin, vEnd) (a body-aligned range).  COH: poses are read through L2 only (persistent loop:
 // other SMs rewrote them since this SM's L1 last saw them); the per-colour launches let L1 keep them (L1 is flushed between launches).
 // DEP: the launch waits for its predecessor (cudaGridDependencySynchronize) only after it has issued everything that does not depend
@@ -615,7 +638,13 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
             }
         } else if (!kVgReg && lv) { stage16_nol1(&w.geom[0][lane], vg.a + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 1][lane], vg.b + v, stream); stage16_nol1(&w.geom[kVgReg ? 0 : 2][lane], vg.n + v, stream); }
         // what follows was written by the previous launch (poses, lambda / penalty): wait for it now, not before
+#ifdef AVBD_TIMELINE
+        if (first) AVBD_TL(w.tlRow, 1);
+#endif
         if (DEP && first) cudaGridDependencySynchronize();
+#ifdef AVBD_TIMELINE
+        if (first) AVBD_TL(w.tlRow, 2);
+#endif
         if (kSelfSeg) {
             if (head) {                                                      // one fetch of the visiting body's pose per segment
                 const int seg = __popc(heads & ((1u << lane) - 1u));
@@ -663,6 +692,9 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (kSelfSeg) __syncwarp();                                          // the self poses were fetched by the segment heads
+#ifdef AVBD_TIMELINE
+        if (base == vBegin) AVBD_TL(w.tlRow, 3);
+#endif
         const int seg = __popc(heads & ((2u << lane) - 1u)) - 1;
         const int sslot = kSelfSeg ? (seg < 0 ? 0 : seg) : lane;
         BodyPose ps, po;
@@ -697,6 +729,9 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
             for (int q = 0; q < 7; ++q) row[q] = make_float4(vv[2 * q].x, vv[2 * q].y, vv[2 * q + 1].x, vv[2 * q + 1].y);      // the pairs ARE the row's order
         }
         __syncwarp();
+#ifdef AVBD_TIMELINE
+        if (base == vBegin) AVBD_TL(w.tlRow, 4);
+#endif
         // ---- phase 2: segment sums
         const int nSeg = __popc(heads);
         const int nextSelf0 = __shfl_sync(0xffffffffu, eCur.z >> 3, 0);           // body the next chunk opens with (-1 past the warp's range)
@@ -732,6 +767,9 @@ __device__ __forceinline__ void sweep_range(WarpPipe& w, const int lane, const i
         __syncwarp();               // rows consumed, carry / queue visible, before the next chunk overwrites the rows
     }
     if (qn > 0) solve_queue<COH>(w, qn, lane, b, fv, prm, dxOut, diag, keep);
+#ifdef AVBD_TIMELINE
+    AVBD_TL(w.tlRow, 5);
+#endif
     if (kVgBulk) { __syncwarp(); if (lane == 0) mbar_inval(&w.mbar); __syncwarp(); }
 }
 
@@ -750,6 +788,16 @@ __global__ void __launch_bounds__(32 * kSweepWarps, MINB) primal_sweep_warp(Body
     if (flags & 2) cudaGridDependencySynchronize();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kSweepWarps + warp;
+#ifdef AVBD_TIMELINE
+    {
+        int row = -1;
+        if (gw == 0 && lane == 0) { unsigned r = atomicAdd(&g_timelineCount, 1u); row = r < 16384u ? (int)r : -1; }
+        row = __shfl_sync(0xffffffffu, row, 0);
+        if (lane == 0) pipes[warp].tlRow = gw == 0 ? row : -1;
+        __syncwarp();
+        AVBD_TL(pipes[warp].tlRow, 0);
+    }
+#endif
     if (gw >= nWarps) {                                        // no block-wide barrier anywhere in this kernel: a warp may leave on its own
         // the warps past the colour's ranges (first colour of a sweep only) take the bodies no contact visits and no user force
         // touches, one per lane: nothing they read is written by anyone else, so their colour does not matter
