@@ -73,6 +73,9 @@ ABI = {
     "avbd_num_springs": (C.c_int, [C.c_void_p]),
     "avbd_host_alloc": (C.c_void_p, [C.c_longlong]),
     "avbd_host_free": (None, [C.c_void_p]),
+    "avbd_host_register": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "avbd_download_state_chunked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "avbd_host_unregister": (C.c_int, [C.c_void_p]),
     "avbd_add_spring": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, C.c_float, C.c_float]),
     "avbd_add_ignore": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "avbd_step": (C.c_int, [C.c_void_p, C.c_int]),

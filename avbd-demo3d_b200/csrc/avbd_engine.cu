@@ -83,6 +83,7 @@ struct avbd_world {
     bool topoSameAsLast = false;      // this step's manifolds have last step's slots and contact counts (np_build)
     DevBuf<int> colourWord;           // work words of the colouring rounds
     std::vector<int> savedColours;    // colouring read from a snapshot, uploaded by prepare()
+    std::vector<cudaEvent_t> chunkEvents;   // avbd_download_state_chunked
     DevBuf<int> flags, worldId, localIdx, dynList, colWorkA, colWorkB;      // colWork*: uncoloured-body work lists of the colouring rounds
     bool topoDirty = true;
     bool contactDiagDone = false;   // the step's last dual pass reduced the contact diagnostics already
@@ -805,6 +806,16 @@ void* avbd_host_alloc(long long bytes) {
     return p;
 }
 void avbd_host_free(void* p) { if (p) cudaFreeHost(p); }
+int avbd_host_register(void* p, long long bytes) {
+    if (!p || bytes <= 0) return fail(AVBD_ERR_ARG, "bad host range");
+    if (cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return fail(AVBD_ERR_CUDA, "cudaHostRegister failed"); }
+    return 0;
+}
+int avbd_host_unregister(void* p) {
+    if (!p) return 0;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return fail(AVBD_ERR_CUDA, "cudaHostUnregister failed"); }
+    return 0;
+}
 
 int avbd_device_count(void) {
     int count = 0;
@@ -851,6 +862,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release(); w->deg.release(); w->estart.release(); w->colCursor.release(); w->entries.release(); w->sweepRange.release(); w->colVisit.release(); w->freeList.release(); w->linkedList.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
     w->mcount.release(); w->buildTiles.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
     for (auto& ps : w->profSteps) { for (auto& e : ps.ev) cudaEventDestroy(e); for (auto& e : ps.dual) cudaEventDestroy(e); }
+    for (cudaEvent_t e : w->chunkEvents) cudaEventDestroy(e);
     if (w->dCnt) cudaFree(w->dCnt);
     if (w->hCnt) cudaFreeHost(w->hCnt);
     if (w->hDiag) cudaFreeHost(w->hDiag);
@@ -1319,6 +1331,29 @@ int avbd_download_state(avbd_world* w, float* out) {
     w->launches++;
     CK(cudaMemcpyAsync(out, w->stateDev.p, (size_t)n * 13 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+int avbd_download_state_chunked(avbd_world* w, float* out, int chunkBodies, avbd_chunk_fn landed, void* user) {
+    if (!w || (!out && w->n) || chunkBodies <= 0) return fail(AVBD_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(w->device));
+    int n = w->n; if (!n) return 0;
+    TRY(w->stateDev.ensure((size_t)n * 13, false, w->stream));
+    launch_dep(pack_state, dim3(blocks_for(n)), dim3(kThreads), 0, w->stream, w->bview(), w->stateDev.p);
+    w->launches++;
+    int chunks = (n + chunkBodies - 1) / chunkBodies;
+    if (chunks > 64) { chunkBodies = (n + 63) / 64; chunks = (n + chunkBodies - 1) / chunkBodies; }
+    while ((int)w->chunkEvents.size() < chunks) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); w->chunkEvents.push_back(e); }
+    for (int k = 0; k < chunks; ++k) {
+        int first = k * chunkBodies, count = std::min(chunkBodies, n - first);
+        CK(cudaMemcpyAsync(out + (size_t)first * 13, w->stateDev.p + (size_t)first * 13, (size_t)count * 13 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaEventRecord(w->chunkEvents[k], w->stream));
+    }
+    for (int k = 0; k < chunks; ++k) {
+        int first = k * chunkBodies, count = std::min(chunkBodies, n - first);
+        CK(cudaEventSynchronize(w->chunkEvents[k]));
+        if (landed) landed(first, count, user);
+    }
     return 0;
 }
 

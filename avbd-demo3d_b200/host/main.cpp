@@ -81,6 +81,7 @@ int main(int argc, char** argv) {
     }
     if (!quiet && !dump) std::printf("Running in headless mode: scene '%s', steps=%d\n", label, steps);
     for (int step = 0; step < warmup; ++step) solver->step();
+    solver->hostSyncSec = solver->deviceStepSec = solver->hostFetchSec = 0.0;
     auto t0 = std::chrono::steady_clock::now();
     for (int step = 0; step < steps; ++step) {
         solver->step();
@@ -88,7 +89,7 @@ int main(int argc, char** argv) {
             const Solver::Diagnostics& st = solver->lastDiagnostics;
             if (!readback) solver->fetchState();
             std::fwrite(&step, 4, 1, dump);
-            std::fwrite(solver->shadow, sizeof(float), (size_t)nBodies * 13, dump);
+            std::fwrite(solver->hostState(), sizeof(float), (size_t)nBodies * 13, dump);
             const float df[5] = {st.maxPenetration, st.maxConstraintViolation, st.maxLinearSpeed, st.maxAngularSpeed, st.maxNormalImpulse};
             const int di[3] = {st.activeManifolds, st.activeContacts, st.dynamicBodies};
             std::fwrite(df, 4, 5, dump); std::fwrite(di, 4, 3, dump);
@@ -113,9 +114,11 @@ int main(int argc, char** argv) {
     if (quiet || dump) {
         const Solver::Diagnostics& st = solver->lastDiagnostics;
         std::printf("{\"scene\": \"%s\", \"steps\": %d, \"warmup\": %d, \"seconds\": %.6f, \"steps_per_s\": %.3f, \"ms_per_step\": %.4f, \"bodies\": %d, \"manifolds\": %d, \"contacts\": %d, "
-                    "\"dynBodies\": %d, \"maxPen\": %.6f, \"readback\": %s, \"reupload\": %s, \"h2d_bytes\": %lld, \"d2h_bytes\": %lld}\n",
+                    "\"dynBodies\": %d, \"maxPen\": %.6f, \"readback\": %s, \"reupload\": %s, \"h2d_bytes\": %lld, \"d2h_bytes\": %lld, "
+                    "\"ms_sync_edits\": %.4f, \"ms_device_step\": %.4f, \"ms_read_back\": %.4f}\n",
                     label, steps, warmup, sec, steps / sec, 1e3 * sec / (steps > 0 ? steps : 1), nBodies, st.activeManifolds, st.activeContacts, st.dynamicBodies, st.maxPenetration,
-                    readback ? "true" : "false", reupload ? "true" : "false", solver->uploadedBytes, solver->downloadedBytes);
+                    readback ? "true" : "false", reupload ? "true" : "false", solver->uploadedBytes, solver->downloadedBytes,
+                    1e3 * solver->hostSyncSec / (steps > 0 ? steps : 1), 1e3 * solver->deviceStepSec / (steps > 0 ? steps : 1), 1e3 * solver->hostFetchSec / (steps > 0 ? steps : 1));
     }
     if (savePath) {
         std::vector<unsigned char> blob = solver->snapshot();

@@ -21,8 +21,13 @@ struct avbd_world;
 struct Rigid {                       // solver.h:48-82
     Solver* solver; Force* forces; Rigid* next;
     int id; static int next_id;
-    vec3 position; quat orientation;
-    vec3 linearVelocity, angularVelocity, prevLinearVelocity, prevAngularVelocity;
+    int slot;                        // row of the solver's state arena this body's fields below live in (extension)
+    // The pose / velocity fields are REFERENCES into the solver's page-locked state arena (one row of 13 floats per body, in the
+    // layout of avbd_upload_state / avbd_download_state): `body->position = ...`, `body->linearVelocity.y`, `&body->position` all read
+    // and write as upstream's plain members do, while Solver::step() exchanges the whole body set with the device as ONE DMA
+    // transfer to / from that arena instead of walking a million heap objects twice per step.
+    vec3& position; quat& orientation;
+    vec3& linearVelocity; vec3& angularVelocity; vec3& prevLinearVelocity; vec3& prevAngularVelocity;
     vec3 initialPosition; quat initialOrientation; vec3 inertialPosition; quat inertialOrientation;
     vec3 size; float mass, invMass; mat3 inertiaTensor, invInertiaTensor; float friction, radius;
     int index;                       // position among the solver's live bodies, creation order (extension)
@@ -97,9 +102,19 @@ struct Solver {                      // solver.h:146-181
     bool uploadAll;                  // treat every body as edited before each step (exercises the full-upload path)
     void fetchState();               // device -> Rigid fields (what step() does when readBack is set)
     void fetchStateImpl(bool advancePrev);
+    const float* hostState() const;  // 13 floats per body in device order, as of the last exchange with the device
     std::vector<Rigid*> order;       // live bodies by creation order
     std::vector<Rigid*> deviceOrder; // bodies as the device world indexes them (nullptr: deleted since the upload)
-    float* shadow; size_t shadowCap; // pinned host copy of the last state exchanged with the device (13 floats per body)
+    float* shadow; size_t shadowCap; // pinned host copy of the last state exchanged with the device (13 floats per body, device order);
+                                     // the staging buffer of the general path (after a body was deleted rows and device order differ)
+    // State arena: rows[13 * slot] = pos3 quat4 lin3 ang3 of the body created slot-th since the last clear(), prev[6 * slot] its
+    // previous velocities.  Both are reserved once as large virtual ranges (they never move: Rigid fields alias them) and page-locked
+    // in growing pieces.  While no body has been deleted (`arenaDense`) slot == device index, and step() uploads the edited row ranges
+    // straight from the arena and downloads straight into it; `arenaShadow` is the copy of what the device last saw (edit detection).
+    float* arenaRows; float* arenaPrev; size_t arenaCapBodies, arenaPinnedBodies; int arenaCount; bool arenaDense;
+    std::vector<float> arenaShadow; std::vector<unsigned char> arenaDynamic;
+    float* claimRow(int& slot);      // called by Rigid's constructor
+    void pinArena(size_t bodies);
     int uploadedBodies, uploadedForces;
     std::vector<Force*> userForces;  // joints / springs / ignore markers in creation order
     std::vector<int> userForceSlot;  // their joint / spring index on the device (-1: no rows)
@@ -107,4 +122,5 @@ struct Solver {                      // solver.h:146-181
     bool mirrorsFresh;               // the Manifold mirrors equal the device's set (refreshManifolds ran since the last step)
     std::vector<float> mirrorRows;   // lambda12 penalty12 of every mirror at refresh time, to detect host edits
     long long uploadedBytes, downloadedBytes;   // state exchange traffic since construction (diagnostics of the e2e path)
+    double hostSyncSec, deviceStepSec, hostFetchSec;   // where step() spent its wall time: edit scan + uploads, avbd_step, read-back
 };

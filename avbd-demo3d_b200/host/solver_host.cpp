@@ -13,6 +13,7 @@
 #include "../csrc/avbd_forces.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <condition_variable>
@@ -20,6 +21,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <sys/mman.h>
 
 namespace {
 [[noreturn]] void die(const char* what) {
@@ -48,14 +50,26 @@ void from_state(Manifold& m, int i, const avbd::ContactState& c) {
 // ----------------------------------------------------------------------------------------------- Rigid
 int Rigid::next_id = 1;      // process-global and never reset, as upstream (rigid.cpp:10)
 
+namespace {
+// rows of the state arena as the typed fields of a Rigid (vec3 / quat are plain float triples / quadruples)
+inline vec3& row_vec3(float* p) { return *reinterpret_cast<vec3*>(p); }
+inline quat& row_quat(float* p) { return *reinterpret_cast<quat*>(p); }
+static_assert(sizeof(vec3) == 3 * sizeof(float) && sizeof(quat) == 4 * sizeof(float), "arena rows alias vec3 / quat");
+}
+
 Rigid::Rigid(Solver* s, const vec3& sz, float dens, float fric, const vec3& pos, const quat& orient, const vec3& linVel, const vec3& angVel)
-    : solver(s), forces(nullptr), next(nullptr), id(next_id++), position(pos), orientation(orient), linearVelocity(linVel),
-      angularVelocity(angVel), prevLinearVelocity(linVel), prevAngularVelocity(angVel), size(sz), friction(fric), deviceIndex(-1), density(dens) {
+    : solver(s), forces(nullptr), next(nullptr), id(next_id++), slot(-1),
+      position(row_vec3(s->claimRow(slot))), orientation(row_quat(s->arenaRows + 13 * (size_t)slot + 3)),
+      linearVelocity(row_vec3(s->arenaRows + 13 * (size_t)slot + 7)), angularVelocity(row_vec3(s->arenaRows + 13 * (size_t)slot + 10)),
+      prevLinearVelocity(row_vec3(s->arenaPrev + 6 * (size_t)slot)), prevAngularVelocity(row_vec3(s->arenaPrev + 6 * (size_t)slot + 3)),
+      size(sz), friction(fric), deviceIndex(-1), density(dens) {
+    position = pos; orientation = orient; linearVelocity = linVel; angularVelocity = angVel; prevLinearVelocity = linVel; prevAngularVelocity = angVel;
     next = s->bodies; s->bodies = this;
     index = (int)s->order.size(); s->order.push_back(this);
     mass = size.x * size.y * size.z * density;                               // rigid.cpp:24-40
     invMass = (mass > 0.0f) ? 1.0f / mass : 0.0f;
     radius = length(size) * 0.5f;
+    s->arenaDynamic[(size_t)slot] = invMass > 0.0f ? 1 : 0;
     if (invMass > 0.0f) {
         float ixx = (1.0f / 12.0f) * mass * (size.y * size.y + size.z * size.z);
         float iyy = (1.0f / 12.0f) * mass * (size.x * size.x + size.z * size.z);
@@ -79,6 +93,7 @@ Rigid::~Rigid() {
         solver->order.erase(std::find(solver->order.begin(), solver->order.end(), this));
         for (size_t i = 0; i < solver->order.size(); ++i) solver->order[i]->index = (int)i;
         solver->rebuild = true;
+        solver->arenaDense = false;      // rows and device order differ from now on (until clear())
     }
 }
 
@@ -241,8 +256,9 @@ void Spring::computeDerivatives(vec3& Jl, vec3& Ja, const Rigid* body, int) cons
 // ----------------------------------------------------------------------------------------------- Solver
 Solver::Solver()
     : bodies(nullptr), forces(nullptr), enableDiagnostics(false), logFrequency(60), stepIndex(0), lastDiagnostics{}, world(nullptr),
-      device(0), rebuild(false), readBack(true), uploadAll(false), shadow(nullptr), shadowCap(0), uploadedBodies(0), uploadedForces(0),
-      mirrorsFresh(false), uploadedBytes(0), downloadedBytes(0) {
+      device(0), rebuild(false), readBack(true), uploadAll(false), shadow(nullptr), shadowCap(0), arenaRows(nullptr), arenaPrev(nullptr),
+      arenaCapBodies(0), arenaPinnedBodies(0), arenaCount(0), arenaDense(true), uploadedBodies(0), uploadedForces(0),
+      mirrorsFresh(false), uploadedBytes(0), downloadedBytes(0), hostSyncSec(0), deviceStepSec(0), hostFetchSec(0) {
     if (const char* d = std::getenv("AVBD_DEVICE")) device = std::atoi(d);
     defaultParams();
 }
@@ -250,7 +266,38 @@ Solver::Solver()
 Solver::~Solver() {
     clear();
     if (shadow) avbd_host_free(shadow);
+    if (arenaRows) {
+        if (arenaPinnedBodies) avbd_host_unregister(arenaRows);
+        munmap(arenaRows, arenaCapBodies * 13 * sizeof(float)); munmap(arenaPrev, arenaCapBodies * 6 * sizeof(float));
+    }
     if (world) avbd_world_destroy(world);
+}
+
+// The arena is address space first, memory later: 2^26 rows (3.5 GB + 1.6 GB of virtual range, MAP_NORESERVE) that the kernel backs
+// page by page as bodies are created.  Rows never move, so the references inside every Rigid stay valid however many bodies follow.
+float* Solver::claimRow(int& slot) {
+    if (!arenaRows) {
+        arenaCapBodies = (size_t)1 << 26;
+        if (const char* e = std::getenv("AVBD_HOST_MAX_BODIES")) arenaCapBodies = std::max<size_t>(1024, (size_t)std::atoll(e));
+        void* r = mmap(nullptr, arenaCapBodies * 13 * sizeof(float), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        void* q = mmap(nullptr, arenaCapBodies * 6 * sizeof(float), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (r == MAP_FAILED || q == MAP_FAILED) { std::fprintf(stderr, "avbd-demo3d_b200: cannot reserve the host state arena (AVBD_HOST_MAX_BODIES lowers it)\n"); std::exit(2); }
+        arenaRows = static_cast<float*>(r); arenaPrev = static_cast<float*>(q);
+    }
+    if ((size_t)arenaCount >= arenaCapBodies) { std::fprintf(stderr, "avbd-demo3d_b200: host state arena is full (AVBD_HOST_MAX_BODIES)\n"); std::exit(2); }
+    slot = arenaCount++;
+    if (arenaDynamic.size() < (size_t)arenaCount) arenaDynamic.resize(std::max<size_t>(1024, 2 * (size_t)arenaCount), 0);
+    return arenaRows + 13 * (size_t)slot;
+}
+
+// Page-locks the arena's first `bodies` rows (doubling, so a growing world re-registers O(log n) times).
+void Solver::pinArena(size_t bodies) {
+    if (bodies <= arenaPinnedBodies || !arenaRows) return;
+    size_t want = std::min(arenaCapBodies, std::max<size_t>(2 * arenaPinnedBodies, std::max<size_t>(bodies, 4096)));
+    if (arenaPinnedBodies) avbd_host_unregister(arenaRows);
+    size_t bytes = (want * 13 * sizeof(float) + 4095) / 4096 * 4096;
+    if (avbd_host_register(arenaRows, (long long)bytes) < 0) { arenaPinnedBodies = 0; return; }     // still correct: the copies go through the driver's staging buffer
+    arenaPinnedBodies = want;
 }
 
 void Solver::clear() {                                                   // solver.cpp:230-238
@@ -261,6 +308,7 @@ void Solver::clear() {                                                   // solv
     bodies = nullptr; forces = nullptr; stepIndex = 0; lastDiagnostics = Diagnostics{};
     order.clear(); deviceOrder.clear(); userForces.clear(); userForceSlot.clear(); rowShadow.clear(); mirrorRows.clear();
     uploadedBodies = 0; uploadedForces = 0; rebuild = false; mirrorsFresh = false;
+    arenaCount = 0; arenaDense = true;
     if (world) check(avbd_clear(world), "avbd_clear");
 }
 
@@ -383,10 +431,39 @@ void Solver::syncToDevice() {
     check(avbd_set_params(world, dt, g, iterations, alpha, beta, gamma, postStabilize ? 1 : 0), "avbd_set_params");
 
     int n = (int)order.size();
-    ensure_shadow(this, (size_t)n);
+    const bool dense = arenaDense;            // no body deleted since clear(): arena row == creation index == device index
+    if (dense) {
+        pinArena((size_t)n);
+        if (arenaShadow.size() < 13 * (size_t)n) arenaShadow.resize(13 * std::max<size_t>((size_t)n + (size_t)n / 2, 1024));
+    } else {
+        ensure_shadow(this, (size_t)n);
+    }
     // 1. host edits of already-uploaded bodies (the GUI moves / re-spins bodies between steps, main.cpp:88-142): each slice
     //    uploads the range between its first and last edited body — nothing at all in a headless run
-    if (uploadedBodies > 0) {
+    if (uploadedBodies > 0 && dense) {
+        // the rows ARE the bodies' fields: one sequential compare against what the device last saw, uploads straight from the arena
+        int slices = 1;
+        std::vector<int> lo(64, -1), hi(64, -1);
+        const bool all = uploadAll;
+        parallel_slices(uploadedBodies, slices, [&](int b, int e, int t) {
+            const float* rows = arenaRows + 13 * (size_t)b; float* sh = arenaShadow.data() + 13 * (size_t)b;
+            int first = -1, last = -1;
+            if (all) { first = b; last = e - 1; }
+            else if (e > b && std::memcmp(rows, sh, 52 * (size_t)(e - b)) != 0) {
+                for (int i = b; i < e; ++i) if (std::memcmp(rows + 13 * (size_t)(i - b), sh + 13 * (size_t)(i - b), 52) != 0) { if (first < 0) first = i; last = i; }
+            }
+            if (first >= 0) std::memcpy(sh + 13 * (size_t)(first - b), rows + 13 * (size_t)(first - b), 52 * (size_t)(last - first + 1));
+            lo[t] = first; hi[t] = last;
+        });
+        for (int t = 0; t < slices; ++t) {
+            if (lo[t] < 0) continue;
+            int first = lo[t], last = hi[t];
+            while (t + 1 < slices && lo[t + 1] == last + 1) last = hi[++t];      // edited ranges that touch travel as one transfer
+            int cnt = last - first + 1;
+            check(avbd_upload_state_range(world, first, cnt, arenaRows + 13 * (size_t)first), "avbd_upload_state_range");
+            uploadedBytes += (long long)cnt * 52;
+        }
+    } else if (uploadedBodies > 0) {
         int slices = 1;
         std::vector<int> lo(16, -1), hi(16, -1);
         const bool all = uploadAll;
@@ -429,7 +506,8 @@ void Solver::syncToDevice() {
         if (prevDiffers && uploadedBodies == 0) {      // a re-created world: the adaptive gravity weight (solver.cpp:318-326) needs the real previous velocities
             check(avbd_upload_prev_linvel(world, prev.data()), "avbd_upload_prev_linvel");
         }
-        for (int i = uploadedBodies; i < n; ++i) pack_body(order[i], shadow + (size_t)i * 13);
+        if (dense) std::memcpy(arenaShadow.data() + 13 * (size_t)uploadedBodies, arenaRows + 13 * (size_t)uploadedBodies, 52 * (size_t)k);
+        else for (int i = uploadedBodies; i < n; ++i) pack_body(order[i], shadow + (size_t)i * 13);
         uploadedBytes += (long long)k * 52;
         reAdded = uploadedBodies == 0;
         uploadedBodies = n;
@@ -537,15 +615,35 @@ void Solver::syncToDevice() {
 }
 
 void Solver::fetchState() { fetchStateImpl(false); }
+const float* Solver::hostState() const { return arenaDense ? arenaRows : shadow; }
 
 // device -> Rigid fields; advancePrev: the step just taken makes the old velocities the "previous" ones (solver.cpp:457-458) — done
 // in the same walk over the bodies, every Rigid is touched once.
 void Solver::fetchStateImpl(bool advancePrev) {
     int n = (int)order.size();
     if (n == 0 || !world) return;
-    check(avbd_download_state(world, shadow), "avbd_download_state");
     downloadedBytes += (long long)n * 52;
     int slices = 1;
+    if (arenaDense) {
+        // one DMA transfer into the rows the Rigid fields alias; the previous velocities advance in a sequential pass first
+        pinArena((size_t)n);
+        if (arenaShadow.size() < 13 * (size_t)n) arenaShadow.resize(13 * std::max<size_t>((size_t)n + (size_t)n / 2, 1024));
+        if (advancePrev)
+            parallel_slices(n, slices, [&](int b0, int e0, int) {
+                for (int i = b0; i < e0; ++i) if (arenaDynamic[(size_t)i]) std::memcpy(arenaPrev + 6 * (size_t)i, arenaRows + 13 * (size_t)i + 7, 6 * sizeof(float));
+            });
+        // four pieces (at least 128K bodies each): a piece is copied to the edit-detection shadow while the next one is still on the bus
+        struct Landed { Solver* s; } ctx{this};
+        check(avbd_download_state_chunked(world, arenaRows, std::max(131072, (n + 3) / 4), [](int first, int count, void* user) {
+            Solver* s = static_cast<Landed*>(user)->s;
+            int sl = 1;
+            parallel_slices(count, sl, [&](int b0, int e0, int) {
+                std::memcpy(s->arenaShadow.data() + 13 * (size_t)(first + b0), s->arenaRows + 13 * (size_t)(first + b0), 52 * (size_t)(e0 - b0));
+            });
+        }, &ctx), "avbd_download_state_chunked");
+        return;
+    }
+    check(avbd_download_state(world, shadow), "avbd_download_state");
     parallel_slices(n, slices, [&](int b0, int e0, int) {
         for (int i = b0; i < e0; ++i) {
             Rigid* b = order[i]; const float* o = shadow + (size_t)i * 13;
@@ -557,12 +655,18 @@ void Solver::fetchStateImpl(bool advancePrev) {
 }
 
 void Solver::step() {                                                    // solver.cpp:255-514, on the device
+    const auto t0 = std::chrono::steady_clock::now();
     syncToDevice();
+    const auto t1 = std::chrono::steady_clock::now();
     int n = (int)order.size();
     ++stepIndex;
     mirrorsFresh = false;
     check(avbd_step(world, 1), "avbd_step");
+    const auto t2 = std::chrono::steady_clock::now();
     if (n > 0 && readBack) fetchStateImpl(true);
+    const auto t3 = std::chrono::steady_clock::now();
+    hostSyncSec += std::chrono::duration<double>(t1 - t0).count(); deviceStepSec += std::chrono::duration<double>(t2 - t1).count();
+    hostFetchSec += std::chrono::duration<double>(t3 - t2).count();
     // lambda / penalty of the user forces' rows, as the reference leaves them in the public arrays after a step
     if (!userForces.empty()) {
         int nj = avbd_num_joints(world), ns = avbd_num_springs(world);
@@ -603,7 +707,7 @@ void Solver::restore(const std::vector<unsigned char>& blob) {
     check(avbd_restore(world, blob.data(), (long long)blob.size()), "avbd_restore");
     if (avbd_num_bodies(world) != (int)order.size()) { std::fprintf(stderr, "avbd-demo3d_b200: snapshot holds a different body set\n"); std::exit(2); }
     uploadedBodies = (int)order.size(); rebuild = false; mirrorsFresh = false;
-    ensure_shadow(this, order.size());
+    if (!arenaDense) ensure_shadow(this, order.size());
     deviceOrder = order;
     for (size_t i = 0; i < order.size(); ++i) order[i]->deviceIndex = (int)i;
     fetchState();                                   // the host mirror shows the restored state (and is not mistaken for an edit)

@@ -309,6 +309,7 @@ def cpp_host_leg(steps, reupload):
         dyn = j["dynBodies"]
         return dict(ms_per_step=j["ms_per_step"], steps_per_s=j["steps_per_s"], body_solves_per_s=dyn * 10 * j["steps_per_s"],
                     h2d_bytes_per_step=j["h2d_bytes"] / max(1, steps + 15), d2h_bytes_per_step=j["d2h_bytes"] / max(1, steps + 15),
+                    ms_sync_edits=j.get("ms_sync_edits"), ms_device_step=j.get("ms_device_step"), ms_read_back=j.get("ms_read_back"),
                     cmd=" ".join(cmd[1:]))
     except Exception as e:
         return dict(unavailable=f"{type(e).__name__}: {e}"[:200])

@@ -64,6 +64,10 @@ const char* avbd_last_error(void);
  * any other host pointer works too, through the driver's staging copy). */
 void* avbd_host_alloc(long long bytes);
 void  avbd_host_free(void* p);
+/* Page-lock / release a host range the caller owns (page-aligned; e.g. the C++ host mirror's state arena, whose rows the Rigid
+ * objects' public fields alias — host/solver.h).  0 on success. */
+int   avbd_host_register(void* p, long long bytes);
+int   avbd_host_unregister(void* p);
 int  avbd_device_count(void);
 
 /* Solver::Solver / ~Solver (solver.cpp:129-143). */
@@ -121,6 +125,11 @@ int  avbd_get_profile(avbd_world* w, avbd_profile* out);
 /* Rigid public state (solver.h:56-60): 13 floats per body pos3 quat4 lin3 ang3, creation order. */
 int  avbd_download_state(avbd_world* w, float* out13);
 int  avbd_upload_state(avbd_world* w, const float* in13);
+/* avbd_download_state in pieces of chunkBodies bodies: `landed(first, count, user)` runs on the calling thread as each piece has
+ * arrived in out13 while the following pieces are still in flight (the C++ host mirror copies each piece to its edit-detection
+ * shadow under the next piece's transfer). */
+typedef void (*avbd_chunk_fn)(int first, int count, void* user);
+int  avbd_download_state_chunked(avbd_world* w, float* out13, int chunkBodies, avbd_chunk_fn landed, void* user);
 /* Host edits of a few bodies (main.cpp:88-142 moves / re-spins bodies between steps): bodies [first, first + count). */
 int  avbd_upload_state_range(avbd_world* w, int first, int count, const float* in13);
 int  avbd_download_prev_linvel(avbd_world* w, float* out3);
