@@ -92,7 +92,7 @@ struct avbd_world {
     // broadphase
     float cell = 1.0f; unsigned tableSize = 256;
     DevBuf<unsigned> cellKey, cellKeySorted; DevBuf<int> cellVal, cellValSorted; DevBuf<int2> cellRange;
-    DevBuf<int2> sortedCell; DevBuf<float4> sortedPos, sortedRot, sortedSize;
+    DevBuf<int2> sortedCell; DevBuf<float4> sortedPos, sortedFrame;
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<int> candCode, candCodeSorted;
@@ -161,7 +161,7 @@ struct avbd_world {
     GridView gview() {
         GridView g; g.cell = cell; g.tableMask = tableSize - 1; g.key = cellKey.p; g.keySorted = cellKeySorted.p;
         g.val = cellVal.p; g.valSorted = cellValSorted.p; g.cellRange = cellRange.p;
-        g.sortedCell = sortedCell.p; g.sortedPos = sortedPos.p; g.sortedRot = sortedRot.p; g.sortedSize = sortedSize.p; g.largeList = largeList.p; g.worldLargeStart = worldLargeStart.p;
+        g.sortedCell = sortedCell.p; g.sortedPos = sortedPos.p; g.sortedFrame = bodySweep ? nullptr : sortedFrame.p; g.largeList = largeList.p; g.worldLargeStart = worldLargeStart.p;
         return g;
     }
     ForceView fview() {
@@ -282,7 +282,7 @@ int prepare(avbd_world* w) {
         // per-body scratch
         TRY(w->cellKey.ensure(n, false, s)); TRY(w->cellKeySorted.ensure(n, false, s)); TRY(w->cellVal.ensure(n, false, s));
         TRY(w->cellValSorted.ensure(n, false, s)); TRY(w->sortedCell.ensure(n, false, s)); TRY(w->sortedPos.ensure(n, false, s));
-        TRY(w->sortedRot.ensure(n, false, s)); TRY(w->sortedSize.ensure(n, false, s));
+        if (!w->bodySweep) TRY(w->sortedFrame.ensure(6 * (size_t)n, false, s));
         TRY(w->cellRange.ensure(table, false, s));
         TRY(w->adjRange.ensure(n, false, s)); TRY(w->colour.ensure(n, false, s));
         TRY(w->colKey.ensure(std::max(1, w->nDyn), false, s)); TRY(w->colKeySorted.ensure(std::max(1, w->nDyn), false, s));
@@ -377,8 +377,11 @@ int run_broadphase(avbd_world* w, bool sat) {
         out.count = &w->dCnt->nCand; out.cnt = w->dCnt; out.overflowBit = 2;
         // small-vs-small pairs: one warp per 32 cell-sorted bodies; with `sat` the cull is fused in and only survivors are written.
         // AVBD_BROADPHASE=cell selects the fused per-cell kernel (A/B measurements; default is the per-body sweep + separate cull).
-        if (sat && !w->bodySweep) launch_dep(bp_sweep_cells<true>, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)w->excl.p, w->nExcl, out);
-        else if (!w->bodySweep) launch_dep(bp_sweep_cells<false>, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)nullptr, 0, raw);
+        // bodies per warp: 32 on a world that fills the machine; a small one is cut finer (a warp walks its cells one after another)
+        const int bpw = n >= 37888 ? 32 : (n >= 18944 ? 16 : (n >= 9472 ? 8 : 4));
+        const int cellBlocks = blocks_for(n, bpw * (kThreads / 32));
+        if (sat && !w->bodySweep) launch_dep(bp_sweep_cells<true>, dim3(cellBlocks), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)w->excl.p, w->nExcl, out, bpw);
+        else if (!w->bodySweep) launch_dep(bp_sweep_cells<false>, dim3(cellBlocks), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)nullptr, 0, raw, bpw);
         else launch_dep(bp_sweep, dim3(blocks_for(16ll * n)), dim3(kThreads), 0, s, bv, gv, raw);
         if (w->nLarge) launch_dep(bp_large, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, raw);
         w->launches += 1 + (w->nLarge ? 1 : 0);
@@ -853,7 +856,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->pose.release(); w->aux.release(); w->vel.release(); w->init.release(); w->prevLin.release(); w->size.release();
     w->flags.release(); w->worldId.release(); w->localIdx.release(); w->dynList.release(); w->colWorkA.release(); w->colWorkB.release(); w->colourWord.release();
     w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellRange.release();
-    w->sortedCell.release(); w->sortedPos.release(); w->sortedRot.release(); w->sortedSize.release(); w->largeList.release(); w->worldLargeStart.release();
+    w->sortedCell.release(); w->sortedPos.release(); w->sortedFrame.release(); w->largeList.release(); w->worldLargeStart.release();
     w->pairs.release(); w->cand.release(); w->candSorted.release(); w->candCode.release(); w->candCodeSorted.release();
     for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cstart.release(); b.cM.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.lp.release(); }
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();

@@ -24,8 +24,7 @@ struct GridView {
     int2* cellRange;                    // per bucket: [start, end) in the sorted order
     int2* sortedCell;                   // {packed cell (10 low bits of cx, cy, cz), world}
     float4* sortedPos;                  // pos.xyz, radius
-    float4* sortedRot;                  // orientation
-    float4* sortedSize;                 // size.xyz, creation index (bit pattern) — what the fused SAT cull reads
+    float4* sortedFrame;                // 6 per body: {ax0, h.x} {ax1, h.y} {ax2, h.z} {n0, raSelf0} {n1, raSelf1} {n2, raSelf2} (ObbFrame) — the fused SAT cull's operands
     const int* largeList; const int* worldLargeStart;
 };
 
@@ -70,9 +69,12 @@ __global__ void bp_cell_bounds(BodyView b, GridView g) {
     float r = body_radius(b.size[i]);
     int3 c = cell_of(pos, g.cell);
     g.sortedPos[p] = make_float4(pos.x, pos.y, pos.z, r);
-    g.sortedRot[p] = b.pose[i].rot;
-    float4 sz = b.size[i];
-    g.sortedSize[p] = make_float4(sz.x, sz.y, sz.z, __int_as_float(i));
+    if (g.sortedFrame) {
+        const ObbFrame f = make_obb_frame(xyz(pos), quat(b.pose[i].rot), xyz(b.size[i]));
+        float4* o = g.sortedFrame + 6 * (size_t)p;
+        o[0] = f4(f.ax[0], f.h.x); o[1] = f4(f.ax[1], f.h.y); o[2] = f4(f.ax[2], f.h.z);
+        o[3] = f4(f.n[0], f.raSelf[0]); o[4] = f4(f.n[1], f.raSelf[1]); o[5] = f4(f.n[2], f.raSelf[2]);
+    }
     g.sortedCell[p] = make_int2(pack_cell(c.x, c.y, c.z), b.worldId[i]);
     if (k > g.tableMask) return;
     if (p == 0 || g.keySorted[p - 1] != k) g.cellRange[k].x = p;
@@ -109,6 +111,50 @@ __device__ __forceinline__ bool spheres_overlap(float4 pa, float4 pb) {
 
 __device__ __forceinline__ int find_key(const unsigned long long* keys, int n, unsigned long long k) {
     int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+    return (lo < n && keys[lo] == k) ? lo : -1;
+}
+// First index in the sorted keys[0, n) whose key is not below k, found by the whole warp: every step probes 32 evenly spaced keys
+// of the live range, so a list of two million keys takes 5 dependent loads instead of the 21 of a binary search.  k is warp-uniform.
+__device__ __forceinline__ int warp_lower_bound(const unsigned long long* keys, int n, unsigned long long k, int lane) {
+    int lo = 0, hi = n;
+    while (hi - lo > 32) {
+        const int stride = (hi - lo + 32) / 33;
+        const long long q = (long long)lo + (long long)(lane + 1) * stride - 1;
+        const bool below = q < hi && keys[q] < k;
+        const int c = __popc(__ballot_sync(0xffffffffu, below));              // sorted: the probes below k are the first c
+        const int nlo = c == 0 ? lo : lo + c * stride;
+        const long long nhi = c == 32 ? hi : (long long)lo + (long long)(c + 1) * stride - 1;
+        lo = nlo; hi = nhi < hi ? (int)nhi : hi;
+    }
+    const bool below = lo + lane < hi && keys[lo + lane] < k;
+    return lo + __popc(__ballot_sync(0xffffffffu, below));
+}
+// Slot of key k in last step's sorted manifold keys, -1 if it had none.  The new list is sorted too and mostly the same pairs, so the
+// warp's keys sit (nearly) side by side in the old list: the warp locates its first key together, each lane then looks at the slot the
+// same distance further on — one coalesced load, a hit for every pair when nothing appeared or vanished in between — and only the lanes
+// that miss search on, in a window first.  Same result as find_key for every lane.  Called by the whole warp; k = 0 / has = false for idle lanes.
+__device__ __forceinline__ int warp_find_keys(const unsigned long long* keys, int n, unsigned long long k, bool has, int lane) {
+    if (n <= 0) return -1;
+    const unsigned who = __ballot_sync(0xffffffffu, has);
+    if (!who) return -1;
+    const int lead = __ffs(who) - 1;
+    const unsigned long long k0 = __shfl_sync(0xffffffffu, k, lead);
+    const int p0 = warp_lower_bound(keys, n, k0, lane);
+    if (!has) return -1;
+    const int guess = p0 + (lane - lead);
+    if (guess < n) {
+        const unsigned long long g = keys[guess];
+        if (g == k) return guess;
+        if (g > k) {                                                       // between the lead's slot and the guess
+            int lo = p0, hi = guess;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+            return (lo < n && keys[lo] == k) ? lo : -1;
+        }
+    }
+    int lo = guess < n ? guess + 1 : p0, hi = lo + 64 < n ? lo + 64 : n;      // past the guess: a window, the rest of the list if the window ends below k
+    if (guess >= n) { lo = p0; hi = n; }
+    else if (hi < n && keys[hi - 1] < k) { lo = hi; hi = n; }
     while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
     return (lo < n && keys[lo] == k) ? lo : -1;
 }
@@ -183,7 +229,7 @@ constexpr int kCellStage = 1536;           // staged survivors per block of 256 
 constexpr int kCellSub = 8;                // bodies of a run handled per pass over its candidates (bounds the hit queue)
 constexpr int kCellQ1 = 32 + kCellSub * 32;
 template <bool SAT>
-__global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView g, const unsigned long long* excl, int nExcl, PairSink sink) {
+__global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView g, const unsigned long long* excl, int nExcl, PairSink sink, int bpw) {
     cudaGridDependencySynchronize();
     constexpr int W = kThreads / 32;
     constexpr unsigned kFull = 0xffffffffu;
@@ -199,9 +245,9 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView 
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    const int base = (blockIdx.x * W + w) * 32;
+    const int base = (blockIdx.x * W + w) * bpw;         // bpw bodies per warp: 32, fewer for a small world (a warp's runs are walked one after another)
     const int p = base + lane;
-    bool valid = p < b.n;
+    bool valid = lane < bpw && p < b.n;
     const unsigned myKey = valid ? g.keySorted[p] : 0xffffffffu;
     valid = valid && myKey <= g.tableMask;                 // small bodies sort first: the valid lanes are a prefix of the warp
     const float4 myPos = valid ? g.sortedPos[p] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -224,10 +270,17 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView 
             else emit_pair(sink, key, code);               // stage full (a very dense neighbourhood): straight to the list
         }
     };
-    auto load_obb = [&](int q, int& index) {
-        const float4 ps = g.sortedPos[q], rt = g.sortedRot[q], sz = g.sortedSize[q];
-        index = __float_as_int(sz.w);
-        return make_obb(xyz(ps), quat(rt), xyz(sz));
+    auto load_frame = [&](int q, bool faces) {
+        ObbFrame F;
+        const float4 ps = g.sortedPos[q];
+        const float4* fr = g.sortedFrame + 6 * (size_t)q;
+        const float4 a0 = fr[0], a1 = fr[1], a2 = fr[2];
+        F.c = xyz(ps); F.h = mk3(a0.w, a1.w, a2.w); F.ax[0] = xyz(a0); F.ax[1] = xyz(a1); F.ax[2] = xyz(a2);
+        if (faces) {
+            const float4 n0 = fr[3], n1 = fr[4], n2 = fr[5];
+            F.n[0] = xyz(n0); F.n[1] = xyz(n1); F.n[2] = xyz(n2); F.raSelf[0] = n0.w; F.raSelf[1] = n1.w; F.raSelf[2] = n2.w;
+        }
+        return F;
     };
 
     int cur = 0, runEnd = 0;                               // lanes [cur, runEnd) of the run being walked
@@ -264,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView 
             for (int d = 1; d < 16; d <<= 1) { const int up = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += up; }
             total = __shfl_sync(kFull, incl, 15);
             __syncwarp();                                  // the previous pass is done with the tables
-            if (lane < 14) { sStart[w][lane] = st; sOff[w][lane] = incl - len; sWant[w][lane] = want; }
+            if (lane < 16) { sStart[w][lane] = st; sOff[w][lane] = lane < 14 ? incl - len : 0x7fffffff; sWant[w][lane] = want; }
             __syncwarp();
         }
         int t0 = 0;
@@ -273,9 +326,9 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView 
                 const int t = t0 + lane;
                 const bool act = t < total;
                 int k = 0;
-                if (act) {
-#pragma unroll
-                    for (int kk = 1; kk < 14; ++kk) if (sOff[w][kk] <= t) k = kk;      // the piece t falls in (empty pieces share their successor's offset)
+                if (act) {                                                 // the piece t falls in: the LAST one starting at or before t (empty pieces share their successor's offset)
+                    k = sOff[w][8] <= t ? 8 : 0;
+                    k += sOff[w][k + 4] <= t ? 4 : 0; k += sOff[w][k + 2] <= t ? 2 : 0; k += sOff[w][k + 1] <= t ? 1 : 0;
                 }
                 const int q = act ? sStart[w][k] + (t - sOff[w][k]) : 0;
                 bool match = false; float4 pq = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -303,10 +356,9 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView 
                         const int2 pr = sQ2[SAT ? w : 0][e];
                         const int fk = sQ2k[SAT ? w : 0][e];
                         SatFaces f{fk >= 0, fk >= 0 ? sQ2sep[SAT ? w : 0][e] : -FLT_MAX, fk >= 0 ? fk : 0};
-                        int i, j;
-                        const Obb A = load_obb(pr.x, i), B = load_obb(pr.y, j);
+                        const Obb A = frame_obb(load_frame(pr.x, false)), B = frame_obb(load_frame(pr.y, false));
                         code = sat_edges(A, B, f);
-                        key = pair_key(i, j, sink.keyShift);
+                        key = pair_key(g.valSorted[pr.x], g.valSorted[pr.y], sink.keyShift);
                     }
                     __syncwarp();
                     n2 -= c;
@@ -318,13 +370,12 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView 
                     bool alive = false; SatFaces f{false, 0.0f, 0}; unsigned long long key = 0ull; int hi = 0, lo = 0;
                     if (lane < c) {
                         const int2 pr = sQ1[w][n1 - c + lane];
-                        const int i = __float_as_int(g.sortedSize[pr.x].w), j = __float_as_int(g.sortedSize[pr.y].w);
+                        const int i = g.valSorted[pr.x], j = g.valSorted[pr.y];
                         hi = i > j ? pr.x : pr.y; lo = i > j ? pr.y : pr.x;            // A is the higher creation index
                         key = i > j ? pair_key(i, j, sink.keyShift) : pair_key(j, i, sink.keyShift);
                         if (SAT && !(nExcl > 0 && find_key(excl, nExcl, key) >= 0)) {
-                            int ia, ib;
-                            const Obb A = load_obb(hi, ia), B = load_obb(lo, ib);
-                            alive = sat_faces(A, B, f);
+                            const ObbFrame A = load_frame(hi, true), B = load_frame(lo, true);
+                            alive = sat_faces_frames(A, B, f);
                         }
                     }
                     __syncwarp();
@@ -490,9 +541,11 @@ __device__ __forceinline__ int chained_block_prefix(unsigned long long* tile, in
     for (int start = block - 1;; start -= 32) {
         const int idx = start - lane;
         unsigned long long v;
-        do {
+        for (;;) {
             v = idx >= 0 ? *(volatile unsigned long long*)&tile[idx] : (2ull << 32);
-        } while (__any_sync(0xffffffffu, (v >> 32) == 0ull));
+            if (!__any_sync(0xffffffffu, (v >> 32) == 0ull)) break;
+            __nanosleep(40);                                              // a predecessor is still clipping: leave the issue slots to the warps that work
+        }
         const unsigned incl = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
         const int stop = incl ? __ffs(incl) - 1 : 31;                 // nearest predecessor whose inclusive prefix is known
         int val = lane <= stop ? (int)(unsigned)(v & 0xffffffffull) : 0;
@@ -535,11 +588,11 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
     float* raw = sPoly + threadIdx.x + (size_t)(kMaxPoly * 3) * blockDim.x;            // buffer 1, this thread's column
     const int rs = (int)blockDim.x;
     int n = 0;
+    slot = warp_find_keys(old.key, nOld, k, build, lane);
     if (build) {
         pa = b.pose[a]; pb = b.pose[c];
         sa = b.size[a]; sb = b.size[c];
         posA = xyz(pa.pos); posB = xyz(pb.pos); rotA = quat(pa.rot); rotB = quat(pb.rot);
-        slot = find_key(old.key, nOld, k);
         if (slot >= 0) {
             oldN = old.hdr[slot].z; oldBase = old.cstart[slot];
 #pragma unroll
