@@ -79,6 +79,7 @@ struct avbd_world {
     DevBuf<float4> prevLin, size;
     int colouredBodies = -1;     // body count the `colour` array holds a valid colouring for (-1: none)
     bool freshColour = true;          // AVBD_ITERATED_COLOUR=1 clears it: rank the bodies by the previous colouring (see run_colour)
+    bool keepColour = false;          // AVBD_KEEP_COLOUR=1: keep last step's colours where the new graph allows, colour only the bodies that lost theirs (see run_colour)
     bool coloursRestored = false;     // `colour` came from a snapshot and no graph has been built since
     bool topoSameAsLast = false;      // this step's manifolds have last step's slots and contact counts (np_build)
     DevBuf<int> colourWord;           // work words of the colouring rounds
@@ -92,7 +93,7 @@ struct avbd_world {
     // broadphase
     float cell = 1.0f; unsigned tableSize = 256;
     DevBuf<unsigned> cellKey, cellKeySorted; DevBuf<int> cellVal, cellValSorted; DevBuf<int2> cellRange;
-    DevBuf<int2> sortedCell; DevBuf<float4> sortedPos, sortedFrame;
+    DevBuf<int2> sortedCell; DevBuf<float4> sortedPos, sortedFrame, bodyFrame;
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<int> candCode, candCodeSorted;
@@ -112,6 +113,8 @@ struct avbd_world {
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
     int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
     long long graphReuses = 0; int persistentMaxBodies = 0;      // the tile cluster loop (solve_loop_cluster) is opt-in (AVBD_PERSISTENT_MAX_BODIES): measured (tools/loop_modes.py) the per-colour sweep launches match or beat it at every size (TwoBlockDrop 6.8k vs 6.6k steps/s, Pyramid 3.75k vs 3.6k, Stress1000 1.39k vs 1.23k, 8000 bodies 1.26k vs 0.69k)
+    bool cellRaw = true;    // default: the per-cell sweep emits the sphere pairs, np_sat culls them.  AVBD_BROADPHASE=body: the per-body sweep instead
+                            // (1M-box grid: bp_sweep 472 us against bp_sweep_cells<false> 328 us; small worlds: no difference)
     bool bodySweep = true;  // AVBD_BROADPHASE=cell: fused per-cell sweep + SAT cull instead of the per-body sweep + separate cull
     double hostLoopSec = 0.0; long long hostLoopSteps = 0;   // AVBD_DEBUG: host time spent issuing the iteration loop's launches
     int loopMode = 0;      // AVBD_LOOP: 0 auto, 1 per-colour launches, 2 cooperative grid loop, 3 tile cluster loop where eligible, 4 warp-pipeline cluster loop
@@ -161,7 +164,7 @@ struct avbd_world {
     GridView gview() {
         GridView g; g.cell = cell; g.tableMask = tableSize - 1; g.key = cellKey.p; g.keySorted = cellKeySorted.p;
         g.val = cellVal.p; g.valSorted = cellValSorted.p; g.cellRange = cellRange.p;
-        g.sortedCell = sortedCell.p; g.sortedPos = sortedPos.p; g.sortedFrame = bodySweep ? nullptr : sortedFrame.p; g.largeList = largeList.p; g.worldLargeStart = worldLargeStart.p;
+        g.sortedCell = sortedCell.p; g.sortedPos = sortedPos.p; g.sortedFrame = bodySweep ? nullptr : sortedFrame.p; g.bodyFrame = bodyFrame.p; g.largeList = largeList.p; g.worldLargeStart = worldLargeStart.p;
         return g;
     }
     ForceView fview() {
@@ -227,8 +230,18 @@ __global__ void rekey_manifolds(ManifoldSet ms, int nM, int keyShift) {
 }
 
 int np_sat_launch(avbd_world* w, const BodyView& bv, const PairSink& raw, int expect, const PairSink& out) {
-    launch_dep(np_sat, dim3(blocks_for(expect)), dim3(kThreads), 0, w->stream, bv, raw.keys, raw.count, raw.cap, w->keyShift, w->excl.p, w->nExcl, out);
-    w->satLaunched = (long long)blocks_for(expect) * kThreads;
+    // persistent warps striding over the candidates (the count is read on the device): enough blocks to fill the machine, no more
+    static int residentDev[64] = {0};
+    int& resident = residentDev[w->device & 63];
+    if (!resident) {
+        int per = 0, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, np_sat, kThreads, 0) != cudaSuccess || per < 1) { cudaGetLastError(); per = 4; }
+        resident = sms * per;
+    }
+    int grid = std::max(1, std::min(resident, blocks_for(expect, 32 * (kThreads / 32))));
+    launch_dep(np_sat, dim3(grid), dim3(kThreads), 0, w->stream, bv, (const float4*)w->bodyFrame.p, raw.keys, raw.count, raw.cap, w->keyShift, w->excl.p, w->nExcl, out);
+    w->satLaunched = (long long)raw.cap;        // every candidate the list holds is tested, whatever `expect` said
     w->launches++;
     return 0;
 }
@@ -283,6 +296,7 @@ int prepare(avbd_world* w) {
         TRY(w->cellKey.ensure(n, false, s)); TRY(w->cellKeySorted.ensure(n, false, s)); TRY(w->cellVal.ensure(n, false, s));
         TRY(w->cellValSorted.ensure(n, false, s)); TRY(w->sortedCell.ensure(n, false, s)); TRY(w->sortedPos.ensure(n, false, s));
         if (!w->bodySweep) TRY(w->sortedFrame.ensure(6 * (size_t)n, false, s));
+        TRY(w->bodyFrame.ensure(6 * (size_t)n, false, s));
         TRY(w->cellRange.ensure(table, false, s));
         TRY(w->adjRange.ensure(n, false, s)); TRY(w->colour.ensure(n, false, s));
         TRY(w->colKey.ensure(std::max(1, w->nDyn), false, s)); TRY(w->colKeySorted.ensure(std::max(1, w->nDyn), false, s));
@@ -381,7 +395,7 @@ int run_broadphase(avbd_world* w, bool sat) {
         const int bpw = n >= 37888 ? 32 : (n >= 18944 ? 16 : (n >= 9472 ? 8 : 4));
         const int cellBlocks = blocks_for(n, bpw * (kThreads / 32));
         if (sat && !w->bodySweep) launch_dep(bp_sweep_cells<true>, dim3(cellBlocks), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)w->excl.p, w->nExcl, out, bpw);
-        else if (!w->bodySweep) launch_dep(bp_sweep_cells<false>, dim3(cellBlocks), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)nullptr, 0, raw, bpw);
+        else if (!w->bodySweep || w->cellRaw) launch_dep(bp_sweep_cells<false>, dim3(cellBlocks), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)nullptr, 0, raw, bpw);
         else launch_dep(bp_sweep, dim3(blocks_for(16ll * n)), dim3(kThreads), 0, s, bv, gv, raw);
         if (w->nLarge) launch_dep(bp_large, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, raw);
         w->launches += 1 + (w->nLarge ? 1 : 0);
@@ -515,12 +529,20 @@ int run_colour(avbd_world* w) {
     // red/black sweep carries a load change two links per iteration: the 10-box Stack then rests 1.8e-3 m from the reference's heights
     // instead of < 1e-3 (tests/test_gpu_scenes.py), so it is not the default.  The colouring then also depends on the world's history:
     // a snapshot carries the colours, and a restored world whose first step finds the topology it was saved with keeps them as they are.
+    // Opt-in (AVBD_KEEP_COLOUR=1; kept colouring, avbd_kernels_graph.cuh: kept_word): a body keeps last step's colour unless a
+    // higher-priority neighbour of the new graph holds the same one; only the bodies that lose theirs are coloured again.  Measured: the
+    // graph stage gets cheaper (1M-box grid 0.95 -> 0.65 ms, 8192-world ensemble 0.42 -> 0.34, Stress1000 0.135 -> 0.118) but the colour
+    // count creeps up while a pile settles (a re-coloured body takes the smallest colour its kept neighbours leave, nobody ever moves
+    // down): 1M grid 9 -> 11-12 colours, Stress1000 5 -> 7, and every colour is a launch per sweep — the sweeps lose what the graph stage
+    // gains (1M grid solve 4.92 -> 5.22 ms, Stress1000 0.71 -> 0.88 ms per step), and the settled Pyramid misses its rest-height gate.
+    // Hence not the default.
+    const bool keep = w->keepColour && w->freshColour && w->colouredBodies == n;
     const bool havePrev = !w->freshColour && w->colouredBodies == n;
     const bool keepSaved = havePrev && w->coloursRestored && w->topoSameAsLast;
     w->coloursRestored = false;
     TRY(w->colourWord.ensure(n, false, s));
-    if (!keepSaved) launch_dep(colour_init, dim3(blocks_for(n)), dim3(kThreads), 0, s, w->flags.p, n, havePrev ? (const int*)w->colour.p : (const int*)nullptr, w->colourWord.p, w->colour.p);
-    w->launches++;
+    if (!keepSaved && !keep) { launch_dep(colour_init, dim3(blocks_for(n)), dim3(kThreads), 0, s, w->flags.p, n, havePrev ? (const int*)w->colour.p : (const int*)nullptr, w->colourWord.p, w->colour.p); w->launches++; }
+    const int* keepFlags = keep ? (const int*)w->flags.p : (const int*)nullptr;
     w->colouredBodies = -1;
     // Jones-Plassmann rounds (= the sequential greedy colouring in hashed-priority order, whatever the timing), all in ONE launch:
     // one block for small worlds, a cooperative grid with a grid barrier per round otherwise — no host check of the uncoloured count
@@ -528,7 +550,7 @@ int run_colour(avbd_world* w) {
     bool coloured = keepSaved;
     if (coloured) {
     } else if (w->nDyn <= kColourBlockMaxBodies) {
-        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colourWord.p, w->colour.p, w->dCnt, n);
+        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colourWord.p, w->colour.p, w->dCnt, n, keepFlags);
         w->launches++;
         coloured = true;
     } else {
@@ -547,13 +569,15 @@ int run_colour(avbd_world* w) {
             const int* dynList = w->dynList.p; int nDyn = w->nDyn; const int* estart = w->estart.p; const int4* entries = w->entries.p;
             const int* localIdx = w->localIdx.p; volatile int* word = w->colourWord.p; int* colour = w->colour.p; Counters* cnt = w->dCnt;
             int* listA = w->colWorkA.p; int* listB = w->colWorkB.p; int* cursors = w->colCursor.p;
-            void* args[] = {&dynList, &nDyn, &estart, &entries, &fv, &localIdx, &word, &colour, &cnt, &listA, &listB, &cursors};
+            int nBodies = n;
+            void* args[] = {&dynList, &nDyn, &estart, &entries, &fv, &localIdx, &word, &colour, &cnt, &listA, &listB, &cursors, &keepFlags, &nBodies};
             int grid = std::min(resident, blocks_for(w->nDyn, kColourGridThreads));
             cudaError_t e = cudaLaunchCooperativeKernel((void*)colour_rounds_grid, dim3(grid), dim3(kColourGridThreads), args, 0, s);
             if (e == cudaSuccess) { w->launches++; coloured = true; } else { cudaGetLastError(); resident = -1; }
         }
     }
     if (!coloured) {
+        if (keep) { launch_dep(colour_keep, dim3(blocks_for(n)), dim3(kThreads), 0, s, w->flags.p, n, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colourWord.p, w->colour.p); w->launches++; }
         const int* list = w->dynList.p; int listCount = w->nDyn; int which = 0;
         for (int round = 0, batch = 6;;) {
             if (round > 4096) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
@@ -839,9 +863,10 @@ avbd_world* avbd_world_create(int device) {
     for (auto& e : w->ev) cudaEventCreate(&e);
     if (const char* e = std::getenv("AVBD_PERSISTENT_MAX_BODIES")) w->persistentMaxBodies = std::atoi(e);
     if (const char* e = std::getenv("AVBD_FORCE_REGRAPH")) w->forceRegraph = std::atoi(e) != 0;
-    if (const char* e = std::getenv("AVBD_BROADPHASE")) w->bodySweep = std::strcmp(e, "cell") != 0;
+    if (const char* e = std::getenv("AVBD_BROADPHASE")) { w->bodySweep = std::strcmp(e, "cell") != 0; w->cellRaw = std::strcmp(e, "body") != 0 && w->bodySweep; }
     if (const char* e = std::getenv("AVBD_LOOP")) w->loopMode = !std::strcmp(e, "launch") ? 1 : (!std::strcmp(e, "grid") ? 2 : (!std::strcmp(e, "cluster") ? 3 : (!std::strcmp(e, "warps") ? 4 : 0)));
     if (const char* e = std::getenv("AVBD_ITERATED_COLOUR")) w->freshColour = std::atoi(e) == 0;
+    if (const char* e = std::getenv("AVBD_KEEP_COLOUR")) w->keepColour = std::atoi(e) != 0;
     std::memset(w->hCnt, 0, sizeof(Counters));
     avbd_default_params(w);
     return w;
@@ -856,7 +881,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->pose.release(); w->aux.release(); w->vel.release(); w->init.release(); w->prevLin.release(); w->size.release();
     w->flags.release(); w->worldId.release(); w->localIdx.release(); w->dynList.release(); w->colWorkA.release(); w->colWorkB.release(); w->colourWord.release();
     w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellRange.release();
-    w->sortedCell.release(); w->sortedPos.release(); w->sortedFrame.release(); w->largeList.release(); w->worldLargeStart.release();
+    w->sortedCell.release(); w->sortedPos.release(); w->sortedFrame.release(); w->bodyFrame.release(); w->largeList.release(); w->worldLargeStart.release();
     w->pairs.release(); w->cand.release(); w->candSorted.release(); w->candCode.release(); w->candCodeSorted.release();
     for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cstart.release(); b.cM.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.lp.release(); }
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();

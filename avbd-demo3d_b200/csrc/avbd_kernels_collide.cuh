@@ -25,6 +25,7 @@ struct GridView {
     int2* sortedCell;                   // {packed cell (10 low bits of cx, cy, cz), world}
     float4* sortedPos;                  // pos.xyz, radius
     float4* sortedFrame;                // 6 per body: {ax0, h.x} {ax1, h.y} {ax2, h.z} {n0, raSelf0} {n1, raSelf1} {n2, raSelf2} (ObbFrame) — the fused SAT cull's operands
+    float4* bodyFrame;                  // the same six, indexed by BODY (not by sorted position): what np_sat gathers per candidate (per-body sweep path)
     const int* largeList; const int* worldLargeStart;
 };
 
@@ -72,6 +73,12 @@ __global__ void bp_cell_bounds(BodyView b, GridView g) {
     if (g.sortedFrame) {
         const ObbFrame f = make_obb_frame(xyz(pos), quat(b.pose[i].rot), xyz(b.size[i]));
         float4* o = g.sortedFrame + 6 * (size_t)p;
+        o[0] = f4(f.ax[0], f.h.x); o[1] = f4(f.ax[1], f.h.y); o[2] = f4(f.ax[2], f.h.z);
+        o[3] = f4(f.n[0], f.raSelf[0]); o[4] = f4(f.n[1], f.raSelf[1]); o[5] = f4(f.n[2], f.raSelf[2]);
+    }
+    if (g.bodyFrame) {
+        const ObbFrame f = make_obb_frame(xyz(pos), quat(b.pose[i].rot), xyz(b.size[i]));
+        float4* o = g.bodyFrame + 6 * (size_t)i;
         o[0] = f4(f.ax[0], f.h.x); o[1] = f4(f.ax[1], f.h.y); o[2] = f4(f.ax[2], f.h.z);
         o[3] = f4(f.n[0], f.raSelf[0]); o[4] = f4(f.n[1], f.raSelf[1]); o[5] = f4(f.n[2], f.raSelf[2]);
     }
@@ -445,72 +452,96 @@ __global__ void bp_persisting(BodyView b, ManifoldSet old, int nOld, PairSink si
     if (!spheres_overlap(pa, pb)) emit_pair(sink, old.key[m], 1);
 }
 
-// K3a: SAT cull (collision.cpp:420-468), one thread per candidate in emission order — which follows the cell-sorted
-// body order, so neighbouring threads gather neighbouring poses.  Survivors {key, winning axis} go to `out`; only
-// they (about a fifth of the candidates on a dense pile) are sorted.  The candidate count is read on the device.
-// Two phases per block so lanes stay dense: every thread runs the 6 face axes of its pair (most candidates of a pile die
-// there); the pairs still alive are compacted in shared memory and the first nAlive threads run the 9 edge axes.
-__global__ void __launch_bounds__(kThreads) np_sat(BodyView b, const unsigned long long* cand, const int* nCand, int cap, int keyShift,
+// K3a: SAT cull (collision.cpp:420-468).  Candidates are read in emission order — which follows the cell-sorted body order, so
+// neighbouring lanes gather neighbouring bodies.  Survivors {key, winning axis} go to `out`; only they (about a fifth of the candidates
+// on a dense pile) are sorted.  The candidate count is read on the device.
+// Persistent warps, no block barrier: a warp takes 32 candidates at a time and runs the 6 face axes, one candidate per lane (most
+// candidates of a pile die there); the pairs still alive wait in the warp's queue in shared memory, and whenever 32 are waiting the 9
+// edge axes run with every lane busy; survivors collect in a second per-warp queue and leave 32 at a time with one atomic on the list
+// counter.  (The first form of this kernel compacted per BLOCK between two __syncthreads: ncu showed its warps waiting at the barrier
+// 7 cycles per issued instruction with the issue slots 41 % busy — a chain of dependent gathers per phase and four resident blocks.)
+// `frames` (6 float4 per body, written by bp_cell_bounds this step): the face axes use each body's normalised axes and own
+// projection radii from there instead of re-deriving them per candidate — every body sits in ~10 candidates of a dense pile, and the
+// square root + three IEEE divisions per axis were most of the face phase's instructions.  sat_faces_frames == sat_faces bit for bit.
+constexpr int kSatQueue = 64;
+__global__ void __launch_bounds__(kThreads, 4) np_sat(BodyView b, const float4* __restrict__ frames, const unsigned long long* cand, const int* nCand, int cap, int keyShift,
                                                    const unsigned long long* excl, int nExcl, PairSink out) {
     cudaGridDependencySynchronize();
-    __shared__ int sWarp[kThreads / 32], sBase;
-    __shared__ int sAliveP[kThreads]; __shared__ float sAliveSep[kThreads]; __shared__ int sAliveK[kThreads];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int W = kThreads / 32;
+    constexpr unsigned kFull = 0xffffffffu;
+    __shared__ unsigned long long sAliveKey[W][kSatQueue], sOutKey[W][kSatQueue];
+    __shared__ float sAliveSep[W][kSatQueue];
+    __shared__ int sAliveK[W][kSatQueue], sOutCode[W][kSatQueue];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
     int n = *nCand; if (n > cap) n = cap;
-    auto load_pair = [&](unsigned long long k, Obb& A, Obb& B) {
-        int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
-        BodyPose pa = b.pose[a], pb = b.pose[c];
-        A = make_obb(xyz(pa.pos), quat(pa.rot), xyz(b.size[a]));
-        B = make_obb(xyz(pb.pos), quat(pb.rot), xyz(b.size[c]));
+    auto load_obb = [&](int i) {
+        Obb o;
+        const float4 ps = b.pose[i].pos;
+        const float4* fr = frames + 6 * (size_t)i;
+        const float4 a0 = fr[0], a1 = fr[1], a2 = fr[2];
+        o.c = xyz(ps); o.h = mk3(a0.w, a1.w, a2.w); o.ax[0] = xyz(a0); o.ax[1] = xyz(a1); o.ax[2] = xyz(a2);
+        return o;
     };
-    // ---- phase 1: face axes
-    bool alive = false; SatFaces f{false, 0.0f, 0};
-    if (p < n) {
-        unsigned long long k = cand[p];
-        if (!(nExcl > 0 && find_key(excl, nExcl, k) >= 0)) {
-            Obb A, B;
-            load_pair(k, A, B);
-            alive = sat_faces(A, B, f);
+    auto load_frame = [&](int i) {
+        ObbFrame F;
+        const Obb o = load_obb(i);
+        const float4* fr = frames + 6 * (size_t)i;
+        const float4 n0 = fr[3], n1 = fr[4], n2 = fr[5];
+        F.c = o.c; F.h = o.h; F.ax[0] = o.ax[0]; F.ax[1] = o.ax[1]; F.ax[2] = o.ax[2];
+        F.n[0] = xyz(n0); F.n[1] = xyz(n1); F.n[2] = xyz(n2); F.raSelf[0] = n0.w; F.raSelf[1] = n1.w; F.raSelf[2] = n2.w;
+        return F;
+    };
+    int nAlive = 0, nOut = 0;                                  // queue fill levels (warp-uniform)
+    auto flush_out = [&](int count) {                         // the LAST `count` survivors of the queue leave
+        int base = 0;
+        if (lane == 0) base = atomicAdd(out.count, count);
+        base = __shfl_sync(kFull, base, 0);
+        if (lane < count) {
+            const int idx = base + lane, e = nOut - count + lane;
+            if (idx < out.cap) { out.keys[idx] = sOutKey[w][e]; out.codes[idx] = sOutCode[w][e]; }
+            else atomicOr(&out.cnt->overflow, out.overflowBit);
         }
+        __syncwarp();
+        nOut -= count;
+    };
+    auto run_edges = [&](int count) {                         // edge axes of the LAST `count` (<= 32) pairs of the alive queue
+        int code = 0; unsigned long long k = 0ull;
+        if (lane < count) {
+            const int e = nAlive - count + lane;
+            k = sAliveKey[w][e];
+            const int fk = sAliveK[w][e];
+            const SatFaces g{fk >= 0, fk >= 0 ? sAliveSep[w][e] : -FLT_MAX, fk >= 0 ? fk : 0};
+            const int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
+            code = sat_edges(load_obb(a), load_obb(c), g);
+        }
+        __syncwarp();
+        nAlive -= count;
+        const unsigned vote = __ballot_sync(kFull, code != 0);
+        if (code) { const int e = nOut + __popc(vote & lt); sOutKey[w][e] = k; sOutCode[w][e] = code; }
+        __syncwarp();
+        nOut += __popc(vote);
+        if (nOut >= 32) flush_out(32);
+    };
+    const int stride = gridDim.x * kThreads;
+    for (int base = (blockIdx.x * W + w) * 32; base < n; base += stride) {
+        const int p = base + lane;
+        bool alive = false; SatFaces f{false, 0.0f, 0}; unsigned long long k = 0ull;
+        if (p < n) {
+            k = cand[p];
+            if (!(nExcl > 0 && find_key(excl, nExcl, k) >= 0)) {
+                const int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
+                alive = sat_faces_frames(load_frame(a), load_frame(c), f);
+            }
+        }
+        const unsigned av = __ballot_sync(kFull, alive);
+        if (alive) { const int e = nAlive + __popc(av & lt); sAliveKey[w][e] = k; sAliveSep[w][e] = f.sep; sAliveK[w][e] = f.valid ? f.k : -1; }
+        __syncwarp();
+        nAlive += __popc(av);
+        if (nAlive >= 32) run_edges(32);
     }
-    unsigned av = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) sWarp[warp] = __popc(av);
-    __syncthreads();
-    int aBase = 0, nAlive = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) { int c = sWarp[w]; if (w < warp) aBase += c; nAlive += c; }
-    if (alive) {
-        int idx = aBase + __popc(av & ((1u << lane) - 1u));
-        sAliveP[idx] = p; sAliveSep[idx] = f.sep; sAliveK[idx] = f.valid ? f.k : -1;
-    }
-    __syncthreads();
-    // ---- phase 2: edge axes, dense
-    int code = 0; unsigned long long k = 0;
-    if ((int)threadIdx.x < nAlive) {
-        k = cand[sAliveP[threadIdx.x]];
-        int fk = sAliveK[threadIdx.x];
-        SatFaces g{fk >= 0, fk >= 0 ? sAliveSep[threadIdx.x] : -FLT_MAX, fk >= 0 ? fk : 0};
-        Obb A, B;
-        load_pair(k, A, B);
-        code = sat_edges(A, B, g);
-    }
-    // block-wide compaction of the survivors: one atomic on the list counter per block
-    unsigned vote = __ballot_sync(0xffffffffu, code != 0);
-    __syncthreads();                                   // everyone is done reading the phase-1 counts
-    if (lane == 0) sWarp[warp] = __popc(vote);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int w = 0; w < kThreads / 32; ++w) { int c = sWarp[w]; sWarp[w] = tot; tot += c; }
-        sBase = tot > 0 ? atomicAdd(out.count, tot) : 0;
-    }
-    __syncthreads();
-    if (code) {
-        int idx = sBase + sWarp[warp] + __popc(vote & ((1u << lane) - 1u));
-        if (idx < out.cap) { out.keys[idx] = k; out.codes[idx] = code; }
-        else atomicOr(&out.cnt->overflow, out.overflowBit);
-    }
+    if (nAlive > 0) run_edges(nAlive);
+    if (nOut > 0) flush_out(nOut);
 }
 
 __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int ci) {
@@ -530,13 +561,14 @@ __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int 
 constexpr int kBuildThreads = 128;
 // tile[b] = (status << 32) | value; status 0 not ready, 1 the block's own total, 2 the inclusive prefix up to and including the block.
 // Blocks are dispatched in index order, so a predecessor a block waits on is always resident or done.
-__device__ __forceinline__ int chained_block_prefix(unsigned long long* tile, int block, int total) {
-    const int lane = threadIdx.x & 31;            // called by the whole first warp
-    if (block == 0) {
-        if (lane == 0) atomicExch(&tile[0], (2ull << 32) | (unsigned)total);
-        return 0;
-    }
-    if (lane == 0) atomicExch(&tile[block], (1ull << 32) | (unsigned)total);
+// Called by the whole first warp.  Publishing and looking back are separate calls: a block publishes its total as soon as it knows
+// it, does the work that does not need its base, and only then adds up its predecessors — which have long published by then.
+__device__ __forceinline__ void chained_publish(unsigned long long* tile, int block, int total) {
+    if ((threadIdx.x & 31) == 0) atomicExch(&tile[block], ((block == 0 ? 2ull : 1ull) << 32) | (unsigned)total);
+}
+__device__ __forceinline__ int chained_lookback(unsigned long long* tile, int block, int total) {
+    const int lane = threadIdx.x & 31;
+    if (block == 0) return 0;
     int exclusive = 0;
     for (int start = block - 1;; start -= 32) {
         const int idx = start - lane;
@@ -544,7 +576,7 @@ __device__ __forceinline__ int chained_block_prefix(unsigned long long* tile, in
         for (;;) {
             v = idx >= 0 ? *(volatile unsigned long long*)&tile[idx] : (2ull << 32);
             if (!__any_sync(0xffffffffu, (v >> 32) == 0ull)) break;
-            __nanosleep(40);                                              // a predecessor is still clipping: leave the issue slots to the warps that work
+            __nanosleep(100);                                             // a predecessor is still clipping: leave the issue slots to the warps that work
         }
         const unsigned incl = __ballot_sync(0xffffffffu, (v >> 32) == 2ull);
         const int stop = incl ? __ffs(incl) - 1 : 31;                 // nearest predecessor whose inclusive prefix is known
@@ -606,35 +638,65 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
         };
         build_contacts_emit(posA, rotA, xyz(sa), posB, rotB, xyz(sb), info[s], poly, emit);
     }
-    // this block's range of the dense contact arrays: warp scan of the counts, block total, one atomic
+    // this block's range of the dense contact arrays: warp scan of the counts, block total PUBLISHED at once (the blocks after this one
+    // can go on); the block's own base — the sum of its predecessors' totals — is only needed by the stores, so it is looked up after the
+    // per-contact work below instead of before it (ncu, 1M-box grid: a seventh of this kernel's instructions were the first warp polling
+    // its predecessors while the other three sat at the barrier).
     int incl = n;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
     if (lane == 31) sWarpTotal[warp] = incl;
     __syncthreads();
+    int blockTotal = 0;
     if (warp == 0) {
-        int tot = 0, mine = 0;
+        int mine = 0;
 #pragma unroll
-        for (int w2 = 0; w2 < kBuildThreads / 32; ++w2) { int t = sWarpTotal[w2]; if (lane == w2) mine = tot; tot += t; }
-        int base = chained_block_prefix(tile, (int)blockIdx.x, tot);
+        for (int w2 = 0; w2 < kBuildThreads / 32; ++w2) { int t = sWarpTotal[w2]; if (lane == w2) mine = blockTotal; blockTotal += t; }
+        chained_publish(tile, (int)blockIdx.x, blockTotal);
         __syncwarp();
         if (lane < kBuildThreads / 32) sWarpTotal[lane] = mine;
-        if (lane == 0) { sBase = base; if (blockIdx.x == gridDim.x - 1) cnt->nContacts = base + tot; }
+    }
+    // Manifold::initialize's per-contact part.  A finished contact is parked in this thread's shared-memory column: its 12 geometry floats
+    // in the clipper's first polygon buffer (free since the last emit), lambda / penalty over its own raw record (just consumed).
+    float* fin = sPoly + threadIdx.x;                                          // buffer 0, this thread's column
+    if (inRange) {
+        unsigned used = 0u;
+        auto loadOld = [&](int j) { return load_contact(old, oldBase + j); };
+        BasisCache cache;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+            if (cc < n) {
+                float* q = raw + (size_t)(cc * 10) * rs;
+                ContactState ct = contact_initialize(posA, rotA, posB, rotB, f2i(q[0]), mk3(q[rs], q[2 * rs], q[3 * rs]), mk3(q[4 * rs], q[5 * rs], q[6 * rs]),
+                                                     mk3(q[7 * rs], q[8 * rs], q[9 * rs]), oldN, oldFeat, used, loadOld, prm, &cache);
+                float* g = fin + (size_t)(cc * 12) * rs;
+                g[0] = ct.rA.x; g[rs] = ct.rA.y; g[2 * rs] = ct.rA.z; g[3 * rs] = ct.C0n;
+                g[4 * rs] = ct.rB.x; g[5 * rs] = ct.rB.y; g[6 * rs] = ct.rB.z; g[7 * rs] = ct.C0t1;
+                g[8 * rs] = ct.n.x; g[9 * rs] = ct.n.y; g[10 * rs] = ct.n.z; g[11 * rs] = ct.C0t2;
+                const float4 l = pack_lambda(ct), pq = pack_penalty(ct);
+                q[0] = l.x; q[rs] = l.y; q[2 * rs] = l.z; q[3 * rs] = l.w; q[4 * rs] = pq.x; q[5 * rs] = pq.y; q[6 * rs] = pq.z; q[7 * rs] = pq.w;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int base = chained_lookback(tile, (int)blockIdx.x, blockTotal);
+        if (lane == 0) { sBase = base; if (blockIdx.x == gridDim.x - 1) cnt->nContacts = base + blockTotal; }
     }
     __syncthreads();
     const int first = sBase + sWarpTotal[warp] + incl - n;
     if (!inRange) return;
-    unsigned used = 0u;
-    auto loadOld = [&](int j) { return load_contact(old, oldBase + j); };
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         if (cc < n) {
+            const float* g = fin + (size_t)(cc * 12) * rs;
             const float* q = raw + (size_t)(cc * 10) * rs;
-            ContactState ct = contact_initialize(posA, rotA, posB, rotB, f2i(q[0]), mk3(q[rs], q[2 * rs], q[3 * rs]), mk3(q[4 * rs], q[5 * rs], q[6 * rs]),
-                                                 mk3(q[7 * rs], q[8 * rs], q[9 * rs]), oldN, oldFeat, used, loadOld, prm);
-            int ci = first + cc;
-            out.cA[ci] = f4(ct.rA, ct.C0n); out.cB[ci] = f4(ct.rB, ct.C0t1); out.cN[ci] = f4(ct.n, ct.C0t2);
-            ContactLP lpq; lpq.l = pack_lambda(ct); lpq.p = pack_penalty(ct); out.lp[ci] = lpq;
+            const int ci = first + cc;
+            out.cA[ci] = make_float4(g[0], g[rs], g[2 * rs], g[3 * rs]);
+            out.cB[ci] = make_float4(g[4 * rs], g[5 * rs], g[6 * rs], g[7 * rs]);
+            out.cN[ci] = make_float4(g[8 * rs], g[9 * rs], g[10 * rs], g[11 * rs]);
+            ContactLP lpq; lpq.l = make_float4(q[0], q[rs], q[2 * rs], q[3 * rs]); lpq.p = make_float4(q[4 * rs], q[5 * rs], q[6 * rs], q[7 * rs]);
+            out.lp[ci] = lpq;
             out.cM[ci] = s;
         }
     }

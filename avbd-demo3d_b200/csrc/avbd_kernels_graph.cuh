@@ -163,6 +163,41 @@ __global__ void colour_init(const int* flags, int n, const int* oldColour, int* 
     colour[i] = dyn ? -1 : -2;
 }
 
+// Kept colouring (the default once a world has one): the contact graph of a pile changes by a percent or two per step, so last step's
+// colouring is still valid almost everywhere.  A dynamic body keeps its colour unless a neighbour of the NEW graph that outranks it (hashed
+// world-local priority) holds the same one; the bodies that lose theirs — and only those — go through the Jones-Plassmann rounds below,
+// which see the kept colours as already taken.  Decided from the OLD colours alone (nothing is written that another thread reads here),
+// so the result does not depend on timing, and from world-local quantities only, so a world colours the same way wherever it sits in a
+// batch.  The colouring is then a function of the world's history, not of the current graph alone: snapshots carry it.
+__device__ __forceinline__ int kept_word(int i, const int* flags, const int* estart, const int4* entries, const ForceView& fv,
+                                         const int* localIdx, const int* oldColour) {
+    if (!(flags[i] & kDynamic)) return 0;
+    const int c = oldColour[i];
+    if (c < 0 || c > 61) return colour_word(0, 1);
+    const int li = localIdx[i];
+    bool keep = true;
+    auto visit = [&](int other) {
+        if (other < 0) return;
+        if (oldColour[other] == c && (flags[other] & kDynamic) && outranks(0, localIdx[other], 0, li)) keep = false;
+    };
+    for (int e = estart[i], e1 = estart[i + 1]; e < e1 && keep; ++e) visit(entries[e].x);
+    if (fv.adjStart) {
+        for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && keep; ++k) {
+            int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
+            int other = (e & 2) ? (isA ? fv.springs[idx].b : fv.springs[idx].a) : (isA ? fv.joints[idx].b : fv.joints[idx].a);
+            visit(other);
+        }
+    }
+    return keep ? colour_word(0, 2 + c) : colour_word(0, 1);
+}
+
+// Stand-alone form (fallback path with one launch per round; the one-launch round kernels do this in their prologue).
+__global__ void colour_keep(const int* flags, int n, const int* estart, const int4* entries, ForceView fv, const int* localIdx, int* word, const int* colour) {
+    cudaGridDependencySynchronize();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) word[i] = kept_word(i, flags, estart, entries, fv, localIdx, colour);
+}
+
 // One Jones-Plassmann attempt for body i: it takes the smallest colour unused by its neighbours once every
 // higher-priority neighbour is coloured.  A lower-priority neighbour cannot be coloured before i is, so what i sees
 // coloured is exactly its higher-priority neighbourhood whenever it succeeds: the result is the sequential greedy
@@ -216,10 +251,15 @@ __global__ void colour_round(const int* dynList, int nDyn, const int* estart, co
 constexpr int kColourBlockThreads = 1024;
 constexpr int kColourSmemBodies = 10240;          // 40 KB of static shared memory
 __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int* estart, const int4* entries,
-                                                                           ForceView fv, const int* localIdx, int* word, int* colour, Counters* cnt, int nBodies) {
+                                                                           ForceView fv, const int* localIdx, int* word, int* colour, Counters* cnt, int nBodies,
+                                                                           const int* keepFlags) {
     cudaGridDependencySynchronize();
     __shared__ int sWord[kColourSmemBodies];
     volatile int* wd = word;
+    if (keepFlags) {                               // kept colouring: the work words come from last step's colours (colour_init was not launched)
+        for (int i = threadIdx.x; i < nBodies; i += blockDim.x) word[i] = kept_word(i, keepFlags, estart, entries, fv, localIdx, colour);
+        __syncthreads();
+    }
     if (nBodies <= kColourSmemBodies) {
         for (int i = threadIdx.x; i < nBodies; i += blockDim.x) sWord[i] = word[i];
         __syncthreads();
@@ -242,11 +282,30 @@ __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const
 constexpr int kColourGridThreads = 256;
 __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const int* dynList, int nDyn, const int* estart, const int4* entries,
                                                                          ForceView fv, const int* localIdx, volatile int* word, int* colour, Counters* cnt,
-                                                                         int* listA, int* listB, int* cursors) {
+                                                                         int* listA, int* listB, int* cursors, const int* keepFlags, int nBodies) {
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     const int* list = dynList; int count = nDyn;
+    if (keepFlags) {
+        // kept colouring: work words from last step's colours; the bodies that lost theirs are the first work list (listB, count in cursors[3])
+        const int rounded = (nBodies + 31) & ~31;
+        for (int i = gtid; i < rounded; i += gsize) {
+            bool left = false;
+            if (i < nBodies) { const int wv = kept_word(i, keepFlags, estart, entries, fv, localIdx, colour); word[i] = wv; left = (wv & 255) == 1; }
+            unsigned vote = __ballot_sync(0xffffffffu, left);
+            if (vote) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cursors + 3, __popc(vote));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (left) listB[base + __popc(vote & ((1u << lane) - 1u))] = i;
+            }
+        }
+        grid.sync();
+        count = *(volatile int*)(cursors + 3);
+        list = listB;
+        if (gtid == 0) cnt->colourKept = nDyn - count;
+    }
     int round = 0;
     for (; round < 4096 && count > 0; ++round) {
         int* out = (round & 1) ? listB : listA;

@@ -245,9 +245,18 @@ struct NewManifold {
 // Solver::step (solver.cpp:281-293; manifold rows are hard so the stiffness cap at :290-292 never applies).
 // `oldFeat[j]` (j < oldN) are last step's feature keys of the same pair, `used` the bit mask of old contacts already
 // matched (first unused equal feature wins, manifold.cpp:111-119); `loadOld(j)` fetches old contact j on a match.
+// `cache` (optional): the contacts of a face manifold all carry the SAME normal, bit for bit, so its unit vector and tangent frame —
+// five square roots and fifteen IEEE divisions per contact — are worth remembering from one contact of a manifold to the next.  Keyed by
+// the normal's bit pattern: a hit returns exactly what the computation would.
+struct BasisCache {
+    bool valid = false; V3 key, n, t1, t2;
+    bool oldValid = false; V3 oldKey, oldFb, oldUnit;
+};
+AVBD_HD bool same_bits(V3 a, V3 b) { return f2i(a.x) == f2i(b.x) && f2i(a.y) == f2i(b.y) && f2i(a.z) == f2i(b.z); }
 template <class LoadOld>
 AVBD_HD ContactState contact_initialize(V3 posA, Q4 rotA, V3 posB, Q4 rotB, int feature, V3 rA, V3 rB, V3 normal,
-                                        int oldN, const int (&oldFeat)[4], unsigned& used, LoadOld&& loadOld, const SolveParams& prm) {
+                                        int oldN, const int (&oldFeat)[4], unsigned& used, LoadOld&& loadOld, const SolveParams& prm,
+                                        BasisCache* cache = nullptr) {
     ContactState c;
     c.feature = feature; c.rA = rA; c.rB = rB; c.n = normal;
 #pragma unroll
@@ -259,8 +268,16 @@ AVBD_HD ContactState contact_initialize(V3 posA, Q4 rotA, V3 posB, Q4 rotB, int 
     if (hit >= 0) {
         used |= 1u << hit;
         ContactState o = loadOld(hit);
-        V3 nn = unit_or(c.n, mk3(0.0f, 1.0f, 0.0f));
-        V3 on = unit_or(o.n, nn);
+        if (cache && !(cache->valid && same_bits(cache->key, c.n))) {
+            cache->key = c.n; contact_basis(c.n, cache->n, cache->t1, cache->t2); cache->valid = true;
+        }
+        V3 nn = cache ? cache->n : unit_or(c.n, mk3(0.0f, 1.0f, 0.0f));        // contact_basis' n is this very unit_or
+        V3 on;
+        if (cache && cache->oldValid && same_bits(cache->oldKey, o.n) && same_bits(cache->oldFb, nn)) on = cache->oldUnit;
+        else {
+            on = unit_or(o.n, nn);
+            if (cache) { cache->oldKey = o.n; cache->oldFb = nn; cache->oldUnit = on; cache->oldValid = true; }
+        }
         float nd = dot(nn, on);
         V3 oldMid = ((posA + qrot(rotA, o.rA)) + (posB + qrot(rotB, o.rB))) * 0.5f;
         V3 newMid = ((posA + qrot(rotA, c.rA)) + (posB + qrot(rotB, c.rB))) * 0.5f;
@@ -276,7 +293,11 @@ AVBD_HD ContactState contact_initialize(V3 posA, Q4 rotA, V3 posB, Q4 rotB, int 
         if (reuse) { c.rA = o.rA; c.rB = o.rB; }
     }
     V3 n, t1, t2;
-    contact_basis(c.n, n, t1, t2);
+    if (cache && cache->valid && same_bits(cache->key, c.n)) { n = cache->n; t1 = cache->t1; t2 = cache->t2; }
+    else {
+        contact_basis(c.n, n, t1, t2);
+        if (cache) { cache->key = c.n; cache->n = n; cache->t1 = t1; cache->t2 = t2; cache->valid = true; }
+    }
     c.n = n;
     V3 dlt = (posA + qrot(rotA, c.rA)) - (posB + qrot(rotB, c.rB));
     c.C0n = dot(dlt, n) - kNormalContactMargin;

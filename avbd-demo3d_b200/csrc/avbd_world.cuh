@@ -81,6 +81,7 @@ struct Counters {             // device-side sizes produced by one stage, consum
     int nFree;                // dynamic bodies no contact visits and no user force touches (graph stage): solved by their own small kernel
     int nLinkedFree;          // ... no contact visits, but a joint / spring: solved in colour order by the same kernel
     int colourRounds;         // Jones-Plassmann rounds the cooperative colouring took (statistics)
+    int colourKept;           // dynamic bodies that kept last step's colour (kept colouring; statistics)
     int nSphere;              // sphere-overlap pairs the fused sweep + SAT kernel tested (they never reach a list; statistics only)
 };
 
