@@ -627,6 +627,7 @@ int run_colour(avbd_world* w) {
     if (w->hCnt->nUncoloured != 0) return fail(AVBD_ERR_CUDA, "graph colouring did not converge");
     if (w->hCnt->overflow & 4) return fail(AVBD_ERR_CAPACITY, "more than 64 colours needed");
     w->nColours = w->hCnt->nColours;
+    if (getenv("AVBD_DEBUG_COLOUR")) fprintf(stderr, "[avbd] colouring: %d colours, %d rounds, %d bodies kept\n", w->hCnt->nColours, w->hCnt->colourRounds, w->hCnt->colourKept);
     w->nFree = w->hCnt->nFree; w->nLinkedFree = w->hCnt->nLinkedFree;
     w->maxColourCount = 0;
     for (int c = 0; c < w->nColours; ++c) w->maxColourCount = std::max(w->maxColourCount, w->hColRange[c].y - w->hColRange[c].x);

@@ -280,6 +280,10 @@ __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const
 // (warp-aggregated; the list's order is irrelevant to the result).  Same attempts, same colouring as colour_round.  Cursors rotate
 // over three slots: the slot a round fills was last READ two barriers ago.
 constexpr int kColourGridThreads = 256;
+#ifndef AVBD_COLOUR_ATTEMPTS
+#define AVBD_COLOUR_ATTEMPTS 4
+#endif
+constexpr int kColourAttempts = AVBD_COLOUR_ATTEMPTS;
 __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const int* dynList, int nDyn, const int* estart, const int4* entries,
                                                                          ForceView fv, const int* localIdx, volatile int* word, int* colour, Counters* cnt,
                                                                          int* listA, int* listB, int* cursors, const int* keepFlags, int nBodies) {
@@ -314,7 +318,13 @@ __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const i
         const int rounded = (count + 31) & ~31;
         for (int t = gtid; t < rounded; t += gsize) {
             bool left = false; int i = 0;
-            if (t < count) { i = list[t]; left = !try_colour(i, estart, entries, fv, localIdx, word, colour, cnt); }
+            // a few attempts per round: the neighbours a body waits for are being coloured by other threads of this very round, and an
+            // attempt is cheaper than a trip through the work list and a grid barrier
+            if (t < count) {
+                i = list[t]; left = true;
+#pragma unroll 1
+                for (int attempt = 0; attempt < kColourAttempts && left; ++attempt) left = !try_colour(i, estart, entries, fv, localIdx, word, colour, cnt);
+            }
             unsigned vote = __ballot_sync(0xffffffffu, left);
             if (vote) {
                 int base = 0;
