@@ -111,6 +111,9 @@ template <bool COH> __device__ __forceinline__ BodyPose load_pose_keep_c(const B
 //   * approximate (2 ulp) reciprocal / square root / reciprocal square root instructions, IN THE ROWS ONLY: the block solve and the
 //     pose update keep IEEE division and sqrt — building the whole translation unit with -prec-div=false -prec-sqrt=false
 //     moved the Stack's rest heights by 2e-3 and toppled the Pyramid's apex box (tools/rest_probe.py).
+#ifndef AVBD_SYSTEM_FORM
+#define AVBD_SYSTEM_FORM 1
+#endif
 __device__ __forceinline__ float clampq(float x, float lo, float hi) { return fmaxf(lo, fminf(hi, x)); }
 __device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // contact_basis_unit of avbd_math.cuh (manifold.cpp:39-50 on an already-unit normal)
@@ -164,6 +167,50 @@ __device__ __forceinline__ void dual_fast(ContactState& c, const ContactEval& e,
 // issue slot, each lane rounded exactly like the scalar instruction) in the order of the shared-memory row the visit kernel
 // stores: rl0 rl1 | rl2 ra0 | ra1 ra2 | ll0 ll1 | ll2 ll3 | ll4 ll5 | la0 la1 | la2 la3 | la4 la5 | la6 la7 | la8 aa0 | aa1 aa2 | aa3 aa4 | aa5 -.
 __device__ __forceinline__ void system_pairs(float2 (&v)[14], const ContactState& c, const ContactEval& e, V3 w, float sg, bool gyro, const M3& invIw) {
+#if AVBD_SYSTEM_FORM == 0
+    // The contact's three rows share one lever arm w and an orthonormal basis b_r, J_r = [b_r, w x b_r], so their sum factors:
+    //   S = sum_r pen_r b_r b_r^T (6 unique),  F = sum_r f_r b_r
+    //   rhs = [F, w x F],   LL = S,   LA = S [w]x^T  (row i = w x S_i),   AA = [w]x LA  (column k = w x LA_k)
+    // 72 multiply-adds against 3 x (6 + 27) for the row-by-row form, and no operand shuffling into register pairs.  Measured (build with
+    // SOLVE_DEFS=-DAVBD_SYSTEM_FORM=0): Stress1000 1405 -> 1455 steps/s, 8192-world ensemble solve 2.34 -> 2.26 ms, 1M-box grid solve
+    // 4.92 -> 4.84 ms.  NOT the default: AA comes out as differences of products of magnitude pen |w|^2 instead of a sum of squares, and
+    // with penalties near the cap that rounding noise is of the order of the inertia term I / dt^2 — the Pyramid's apex box (balanced on
+    // two supports) topples within 600 steps with this form and stays with the row-by-row one, as it does in the reference.
+    float f0[3];
+    float Sxx, Syx, Szx, Syy, Szy, Szz; V3 F;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const V3 b = e.basis[r];
+        f0[r] = clampq(c.pen[r] * e.C[r] + c.lam[r], e.fmin[r], e.fmax[r]);
+        const float f = f0[r] * sg, pen = c.pen[r];
+        const float px = pen * b.x, py = pen * b.y, pz = pen * b.z;
+        if (r == 0) { Sxx = px * b.x; Syx = py * b.x; Szx = pz * b.x; Syy = py * b.y; Szy = pz * b.y; Szz = pz * b.z; F = b * f; }
+        else {
+            Sxx = fmaf(px, b.x, Sxx); Syx = fmaf(py, b.x, Syx); Szx = fmaf(pz, b.x, Szx); Syy = fmaf(py, b.y, Syy); Szy = fmaf(pz, b.y, Szy); Szz = fmaf(pz, b.z, Szz);
+            F.x = fmaf(f, b.x, F.x); F.y = fmaf(f, b.y, F.y); F.z = fmaf(f, b.z, F.z);
+        }
+    }
+    const V3 Ra = cross(w, F);
+    // la[3 i + j] = (w x S_i)_j with S_i the i-th row of the symmetric S
+    const V3 l0 = cross(w, mk3(Sxx, Syx, Szx)), l1 = cross(w, mk3(Syx, Syy, Szy)), l2 = cross(w, mk3(Szx, Szy, Szz));
+    // aa = lower triangle of [w]x LA, column k of LA = (l0[k], l1[k], l2[k])
+    float aa0 = w.y * l2.x - w.z * l1.x, aa1 = w.z * l0.x - w.x * l2.x, aa2 = w.x * l1.x - w.y * l0.x;
+    float aa3 = w.z * l0.y - w.x * l2.y, aa4 = w.x * l1.y - w.y * l0.y;
+    float aa5 = w.x * l1.z - w.y * l0.z;
+    if (gyro) {                                                  // solver.cpp:393-397; exactly zero for isotropic inertia
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const V3 Ja = cross(w, e.basis[r]);
+            const V3 g = vabs(cross(Ja, mv(invIw, Ja)));
+            const float af = fabsf(f0[r]);
+            aa0 += g.x * af; aa3 += g.y * af; aa5 += g.z * af;
+        }
+    }
+    v[0] = make_float2(F.x, F.y); v[1] = make_float2(F.z, Ra.x); v[2] = make_float2(Ra.y, Ra.z);
+    v[3] = make_float2(Sxx, Syx); v[4] = make_float2(Szx, Syy); v[5] = make_float2(Szy, Szz);
+    v[6] = make_float2(l0.x, l0.y); v[7] = make_float2(l0.z, l1.x); v[8] = make_float2(l1.y, l1.z); v[9] = make_float2(l2.x, l2.y);
+    v[10] = make_float2(l2.z, aa0); v[11] = make_float2(aa1, aa2); v[12] = make_float2(aa3, aa4); v[13] = make_float2(aa5, 0.0f);
+#else
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         V3 Jl = e.basis[r];
@@ -190,6 +237,7 @@ __device__ __forceinline__ void system_pairs(float2 (&v)[14], const ContactState
             v[10].y += g.x * af; v[12].x += g.y * af; v[13].x += g.z * af;
         }
     }
+#endif
 }
 __device__ __forceinline__ void system_fast(BodySystem& s, const ContactState& c, const ContactEval& e, V3 w, float sg, bool gyro, const M3& invIw) {
     float2 v[14];
