@@ -99,7 +99,7 @@ struct avbd_world {
     DevBuf<int> candCode, candCodeSorted;
     DevBuf<unsigned long long> buildTiles;      // np_build's chained scan over its blocks
     DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;      // per-contact visit lists: small worlds (cluster loop) only
-    DevBuf<int> deg, estart, colCursor, sweepRange, freeList, linkedList; DevBuf<int4> entries; DevBuf<int2> colVisit; DevBuf<float4> vgA, vgB, vgN;
+    DevBuf<int> deg, estart, colCursor, sweepRange, freeList, linkedList; DevBuf<int> entries; DevBuf<int2> colVisit; DevBuf<float4> vgA, vgB, vgN;
     int2 hColVisit[64]; int sweepWarps[64] = {0}, sweepOff[64] = {0};      // per colour: its visit range, warps of the sweep, offset of its warp ranges
     int nFree = 0, nLinkedFree = 0; bool visitGeomStale = true, sweepRangesValid = false;            // contact geometry in visit order (VisitGeom), refreshed once per step
          // body -> manifold entries CSR (graph stage): colouring adjacency + the large-world sweep's work list
@@ -519,7 +519,7 @@ int run_colour(avbd_world* w) {
     CK(cudaMemsetAsync(w->deg.p, 0, sizeof(int) * ((size_t)n + 1), s));
     launch_dep(entry_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->deg.p);
     TRY(exclusive_scan(w, w->deg.p, w->estart.p, n + 1));
-    launch_dep(entry_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->estart.p, w->entries.p);
+    launch_dep(entry_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->estart.p, w->entries.p);
     w->launches += 2;
     ForceView fv = w->fview();
     // Default: hashed priority order only — the colouring is a pure function of the current graph.
@@ -566,7 +566,7 @@ int run_colour(avbd_world* w) {
         if (resident > 0 && !getenv("AVBD_NO_COOP_COLOUR")) {
             TRY(w->colWorkA.ensure((size_t)w->nDyn, false, s)); TRY(w->colWorkB.ensure((size_t)w->nDyn, false, s)); TRY(w->colCursor.ensure(4, false, s));
             CK(cudaMemsetAsync(w->colCursor.p, 0, 4 * sizeof(int), s));
-            const int* dynList = w->dynList.p; int nDyn = w->nDyn; const int* estart = w->estart.p; const int4* entries = w->entries.p;
+            const int* dynList = w->dynList.p; int nDyn = w->nDyn; const int* estart = w->estart.p; const int* entries = w->entries.p;
             const int* localIdx = w->localIdx.p; volatile int* word = w->colourWord.p; int* colour = w->colour.p; Counters* cnt = w->dCnt;
             int* listA = w->colWorkA.p; int* listB = w->colWorkB.p; int* cursors = w->colCursor.p;
             int nBodies = n;
@@ -601,7 +601,7 @@ int run_colour(avbd_world* w) {
         }
     }
     w->colouredBodies = n;
-    launch_dep(colour_keys, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p, w->estart.p, w->entries.p);
+    launch_dep(colour_keys, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);
     TRY(sort_pairs(w, w->colKey.p, w->colKeySorted.p, w->colVal.p, w->colOrder.p, w->nDyn, 7));
     CK(cudaMemsetAsync(w->colRange.p, 0, sizeof(int2) * 64, s));
     launch_dep(colour_bounds, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);

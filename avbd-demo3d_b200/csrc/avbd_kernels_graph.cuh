@@ -32,12 +32,9 @@ __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, in
 }
 
 // ------------------------------------------------------------------ body -> manifold entries (CSR)
-// One entry per LIVE manifold touching a dynamic body, in pair-key order (the body's "I am A" run, then its "I am B" run):
-//   {other body, first dense contact, contact count | body-is-A << 3 | first-visit << 4, friction bits}
-// estart is indexed by BODY (n + 1 entries, static bodies own none).  The colouring walks it as the adjacency list, the large-world
-// primal sweep as its work list (avbd_solve.cu: primal_colour_bodies).  first-visit (set by colour_keys once colours exist): of a
-// contact's two visits per sweep this one comes first (the other endpoint is static or has a higher colour) — it applies the
-// previous iteration's deferred dual update.
+// One entry per LIVE manifold touching a dynamic body, in pair-key order (the body's "I am A" run, then its "I am B" run): the OTHER
+// body, 4 bytes — the colouring's adjacency list and nothing else (the sweeps walk the visit lists).  estart is indexed by BODY
+// (n + 1 entries, static bodies own none).
 __global__ void entry_count(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* deg) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,16 +46,16 @@ __global__ void entry_count(const int* dynList, int nDyn, const int4* adjRange, 
     for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z > 0 ? 1 : 0;
     deg[i] = k;
 }
-__global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
-                           const int* estart, int4* entries) {
+__global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
+                           const int* estart, int* entries) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = dynList[t];
     int4 rg = adjRange[i];
     int o = estart[i];
-    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; if (h.z > 0) entries[o++] = make_int4(h.y, cstart[m], h.z | 8, h.w); }
-    for (int q = rg.z; q < rg.w; ++q) { int m = bList[q]; int4 h = hdr[m]; if (h.z > 0) entries[o++] = make_int4(h.x, cstart[m], h.z, h.w); }
+    for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; if (h.z > 0) entries[o++] = h.y; }
+    for (int q = rg.z; q < rg.w; ++q) { int4 h = hdr[bList[q]]; if (h.z > 0) entries[o++] = h.x; }
 }
 
 // ------------------------------------------------------------------ contact-visit lists
@@ -169,7 +166,7 @@ __global__ void colour_init(const int* flags, int n, const int* oldColour, int* 
 // which see the kept colours as already taken.  Decided from the OLD colours alone (nothing is written that another thread reads here),
 // so the result does not depend on timing, and from world-local quantities only, so a world colours the same way wherever it sits in a
 // batch.  The colouring is then a function of the world's history, not of the current graph alone: snapshots carry it.
-__device__ __forceinline__ int kept_word(int i, const int* flags, const int* estart, const int4* entries, const ForceView& fv,
+__device__ __forceinline__ int kept_word(int i, const int* flags, const int* estart, const int* entries, const ForceView& fv,
                                          const int* localIdx, const int* oldColour) {
     if (!(flags[i] & kDynamic)) return 0;
     const int c = oldColour[i];
@@ -180,7 +177,7 @@ __device__ __forceinline__ int kept_word(int i, const int* flags, const int* est
         if (other < 0) return;
         if (oldColour[other] == c && (flags[other] & kDynamic) && outranks(0, localIdx[other], 0, li)) keep = false;
     };
-    for (int e = estart[i], e1 = estart[i + 1]; e < e1 && keep; ++e) visit(entries[e].x);
+    for (int e = estart[i], e1 = estart[i + 1]; e < e1 && keep; ++e) visit(entries[e]);
     if (fv.adjStart) {
         for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && keep; ++k) {
             int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
@@ -192,7 +189,7 @@ __device__ __forceinline__ int kept_word(int i, const int* flags, const int* est
 }
 
 // Stand-alone form (fallback path with one launch per round; the one-launch round kernels do this in their prologue).
-__global__ void colour_keep(const int* flags, int n, const int* estart, const int4* entries, ForceView fv, const int* localIdx, int* word, const int* colour) {
+__global__ void colour_keep(const int* flags, int n, const int* estart, const int* entries, ForceView fv, const int* localIdx, int* word, const int* colour) {
     cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) word[i] = kept_word(i, flags, estart, entries, fv, localIdx, colour);
@@ -204,7 +201,7 @@ __global__ void colour_keep(const int* flags, int n, const int* estart, const in
 // colouring in priority order, independent of timing (timing only changes how many attempts it takes).  Reading a
 // neighbour's word while that neighbour writes it is part of the scheme: either value leads to the same colouring.
 // Returns whether the body is coloured after the attempt.
-__device__ __forceinline__ bool try_colour(int i, const int* estart, const int4* entries, const ForceView& fv,
+__device__ __forceinline__ bool try_colour(int i, const int* estart, const int* entries, const ForceView& fv,
                                            const int* localIdx, volatile int* word, int* colour, Counters* cnt) {
     const int wi = word[i];
     if ((wi & 255) != 1) return true;
@@ -217,7 +214,7 @@ __device__ __forceinline__ bool try_colour(int i, const int* estart, const int4*
         if (so >= 2) used |= 1ull << (so - 2);
         else if (so == 1 && outranks(wo >> 8, localIdx[other], ri, li)) ready = false;
     };
-    for (int e = estart[i], e1 = estart[i + 1]; e < e1 && ready; ++e) visit(entries[e].x);
+    for (int e = estart[i], e1 = estart[i + 1]; e < e1 && ready; ++e) visit(entries[e]);
     if (fv.adjStart) {
         for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && ready; ++k) {
             int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
@@ -233,7 +230,7 @@ __device__ __forceinline__ bool try_colour(int i, const int* estart, const int4*
     return true;
 }
 
-__global__ void colour_round(const int* dynList, int nDyn, const int* estart, const int4* entries,
+__global__ void colour_round(const int* dynList, int nDyn, const int* estart, const int* entries,
                              ForceView fv, const int* localIdx, volatile int* word, int* colour, Counters* cnt, bool countLeft) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,7 +247,7 @@ __global__ void colour_round(const int* dynList, int nDyn, const int* estart, co
 // chain of L2 round trips (Stress1000: 30 -> ~8 us).
 constexpr int kColourBlockThreads = 1024;
 constexpr int kColourSmemBodies = 10240;          // 40 KB of static shared memory
-__global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int* estart, const int4* entries,
+__global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int* estart, const int* entries,
                                                                            ForceView fv, const int* localIdx, int* word, int* colour, Counters* cnt, int nBodies,
                                                                            const int* keepFlags) {
     cudaGridDependencySynchronize();
@@ -284,7 +281,7 @@ constexpr int kColourGridThreads = 256;
 #define AVBD_COLOUR_ATTEMPTS 4
 #endif
 constexpr int kColourAttempts = AVBD_COLOUR_ATTEMPTS;
-__global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const int* dynList, int nDyn, const int* estart, const int4* entries,
+__global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const int* dynList, int nDyn, const int* estart, const int* entries,
                                                                          ForceView fv, const int* localIdx, volatile int* word, int* colour, Counters* cnt,
                                                                          int* listA, int* listB, int* cursors, const int* keepFlags, int nBodies) {
     cg::grid_group grid = cg::this_grid();
@@ -354,20 +351,14 @@ __global__ void colour_compact(const int* list, int n, const int* colour, int* o
     if (keep) out[base + __popc(vote & ((1u << lane) - 1u))] = i;
 }
 
-// Sort keys of the colour order, and — now that colours exist — the first-visit bit of the body's entries.
-__global__ void colour_keys(const int* dynList, int nDyn, const int* colour, unsigned* key, int* val, const int* estart, int4* entries) {
+// Sort keys of the colour order.
+__global__ void colour_keys(const int* dynList, int nDyn, const int* colour, unsigned* key, int* val) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
     int i = dynList[t];
-    int mine = colour[i];
-    key[t] = (unsigned)mine;
+    key[t] = (unsigned)colour[i];
     val[t] = i;
-    for (int e = estart[i], e1 = estart[i + 1]; e < e1; ++e) {
-        int co = colour[entries[e].x];
-        int z = entries[e].z & ~16;
-        entries[e].z = z | ((co < 0 || mine < co) ? 16 : 0);
-    }
 }
 // colourRange[c] = {first, last+1} in the colour-sorted body order; must be zeroed first.
 __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourRange, Counters* cnt) {
