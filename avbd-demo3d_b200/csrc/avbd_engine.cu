@@ -53,7 +53,8 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-constexpr int kColourBlockMaxBodies = 8192;      // at most this many dynamic bodies: colouring rounds run in one block
+constexpr int kColourBlockMaxBodies = 2048;      // at most this many dynamic bodies: colouring rounds run in one block
+static int colour_block_max() { static const int v = [] { const char* e = getenv("AVBD_COLOUR_BLOCK_MAX"); return e ? atoi(e) : kColourBlockMaxBodies; }(); return v; }
 inline int blocks_for(long long n, int threads = kThreads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
 
 struct HostBody {   // what the host must remember to (re)classify bodies; dynamic state lives on the device
@@ -375,16 +376,15 @@ int run_broadphase(avbd_world* w, bool sat) {
     w->nCand = 0; w->nPairs = 0;
     if (n == 0) return 0;
     BodyView bv = w->bview(); GridView gv = w->gview();
-    launch_dep(bp_cells, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv);
+    launch_dep(bp_cells, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, w->dCnt);
     int tbits = bits_for(w->tableSize);   // sentinel bucket == tableSize needs one more bit
     TRY(sort_pairs(w, w->cellKey.p, w->cellKeySorted.p, w->cellVal.p, w->cellValSorted.p, n, tbits));
-    CK(cudaMemsetAsync(w->cellRange.p, 0, w->tableSize * sizeof(int2), s));
     launch_dep(bp_cell_bounds, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv);
     w->launches += 2;
     if (w->pairs.cap == 0) TRY(w->pairs.ensure((size_t)std::max(1024, 12 * n), false, s));
     if (w->cand.cap == 0) { TRY(w->cand.ensure((size_t)std::max(1024, 3 * n), false, s)); TRY(w->candCode.ensure(w->cand.cap, false, s)); }
     for (int attempt = 0; attempt < 8; ++attempt) {
-        CK(cudaMemsetAsync(w->dCnt, 0, sizeof(Counters), s));
+        if (attempt > 0) CK(cudaMemsetAsync(w->dCnt, 0, sizeof(Counters), s));        // the first attempt's counters were cleared by bp_cells
         PairSink raw; raw.keys = w->pairs.p; raw.codes = nullptr; raw.cap = (int)w->pairs.cap; raw.keyShift = w->keyShift;
         raw.count = &w->dCnt->nPairs; raw.cnt = w->dCnt; raw.overflowBit = 1;
         PairSink out; out.keys = w->cand.p; out.codes = w->candCode.p; out.cap = (int)std::min(w->cand.cap, w->candCode.cap); out.keyShift = w->keyShift;
@@ -502,8 +502,18 @@ int run_colour(avbd_world* w) {
     w->nColours = 0;
     if (w->n == 0 || w->nDyn == 0) { w->graphValid = true; return 0; }
     int nM = w->nM, n = w->n;
-    CK(cudaMemsetAsync(w->adjRange.p, 0, sizeof(int4) * n, s));
     ManifoldSet ms = w->mset(w->cur);
+    // (how the colouring starts is decided here because the stage's one prologue launch also initialises its work words; see below)
+    const bool keep = w->keepColour && w->freshColour && w->colouredBodies == n;
+    const bool havePrev = !w->freshColour && w->colouredBodies == n;
+    const bool keepSaved = havePrev && w->coloursRestored && w->topoSameAsLast;
+    w->coloursRestored = false;
+    TRY(w->deg.ensure((size_t)n + 1, false, s)); TRY(w->estart.ensure((size_t)n + 1, false, s));
+    TRY(w->colourWord.ensure(n, false, s)); TRY(w->colCursor.ensure(4, false, s));
+    TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
+    launch_dep(graph_prologue, dim3(blocks_for((long long)n + 1)), dim3(kThreads), 0, s, w->flags.p, n, w->nDyn, w->adjRange.p, w->deg.p, w->colRange.p, w->visitCount.p,
+               w->colCursor.p, w->dCnt, (keepSaved || keep) ? 0 : (havePrev ? 2 : 1), w->colourWord.p, w->colour.p);
+    w->launches++;
     if (nM > 0) {
         TRY(w->bKey.ensure(nM, false, s)); TRY(w->bKeySorted.ensure(nM, false, s)); TRY(w->bVal.ensure(nM, false, s)); TRY(w->bList.ensure(nM, false, s));
         launch_dep(adj_a_ranges, dim3(blocks_for(nM)), dim3(kThreads), 0, s, ms.hdr, nM, w->flags.p, n, w->adjRange.p, w->bKey.p, w->bVal.p);
@@ -514,9 +524,7 @@ int run_colour(avbd_world* w) {
         TRY(w->bList.ensure(1, false, s));
     }
     // body -> manifold entries (CSR by body): the colouring's adjacency and the large-world sweep's work list
-    TRY(w->deg.ensure((size_t)n + 1, false, s)); TRY(w->estart.ensure((size_t)n + 1, false, s));
     TRY(w->entries.ensure((size_t)std::max(1, 2 * nM), false, s));
-    CK(cudaMemsetAsync(w->deg.p, 0, sizeof(int) * ((size_t)n + 1), s));
     launch_dep(entry_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->deg.p);
     TRY(exclusive_scan(w, w->deg.p, w->estart.p, n + 1));
     launch_dep(entry_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->estart.p, w->entries.p);
@@ -536,12 +544,6 @@ int run_colour(avbd_world* w) {
     // down): 1M grid 9 -> 11-12 colours, Stress1000 5 -> 7, and every colour is a launch per sweep — the sweeps lose what the graph stage
     // gains (1M grid solve 4.92 -> 5.22 ms, Stress1000 0.71 -> 0.88 ms per step), and the settled Pyramid misses its rest-height gate.
     // Hence not the default.
-    const bool keep = w->keepColour && w->freshColour && w->colouredBodies == n;
-    const bool havePrev = !w->freshColour && w->colouredBodies == n;
-    const bool keepSaved = havePrev && w->coloursRestored && w->topoSameAsLast;
-    w->coloursRestored = false;
-    TRY(w->colourWord.ensure(n, false, s));
-    if (!keepSaved && !keep) { launch_dep(colour_init, dim3(blocks_for(n)), dim3(kThreads), 0, s, w->flags.p, n, havePrev ? (const int*)w->colour.p : (const int*)nullptr, w->colourWord.p, w->colour.p); w->launches++; }
     const int* keepFlags = keep ? (const int*)w->flags.p : (const int*)nullptr;
     w->colouredBodies = -1;
     // Jones-Plassmann rounds (= the sequential greedy colouring in hashed-priority order, whatever the timing), all in ONE launch:
@@ -549,7 +551,7 @@ int run_colour(avbd_world* w) {
     // between rounds.  If the cooperative launch is refused, rounds are launched in batches with a host check per batch.
     bool coloured = keepSaved;
     if (coloured) {
-    } else if (w->nDyn <= kColourBlockMaxBodies) {
+    } else if (w->nDyn <= colour_block_max()) {
         launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colourWord.p, w->colour.p, w->dCnt, n, keepFlags);
         w->launches++;
         coloured = true;
@@ -564,8 +566,7 @@ int run_colour(avbd_world* w) {
             resident = (coop && per > 0) ? sms * per : -1;
         }
         if (resident > 0 && !getenv("AVBD_NO_COOP_COLOUR")) {
-            TRY(w->colWorkA.ensure((size_t)w->nDyn, false, s)); TRY(w->colWorkB.ensure((size_t)w->nDyn, false, s)); TRY(w->colCursor.ensure(4, false, s));
-            CK(cudaMemsetAsync(w->colCursor.p, 0, 4 * sizeof(int), s));
+            TRY(w->colWorkA.ensure((size_t)w->nDyn, false, s)); TRY(w->colWorkB.ensure((size_t)w->nDyn, false, s));
             const int* dynList = w->dynList.p; int nDyn = w->nDyn; const int* estart = w->estart.p; const int* entries = w->entries.p;
             const int* localIdx = w->localIdx.p; volatile int* word = w->colourWord.p; int* colour = w->colour.p; Counters* cnt = w->dCnt;
             int* listA = w->colWorkA.p; int* listB = w->colWorkB.p; int* cursors = w->colCursor.p;
@@ -603,15 +604,11 @@ int run_colour(avbd_world* w) {
     w->colouredBodies = n;
     launch_dep(colour_keys, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);
     TRY(sort_pairs(w, w->colKey.p, w->colKeySorted.p, w->colVal.p, w->colOrder.p, w->nDyn, 7));
-    CK(cudaMemsetAsync(w->colRange.p, 0, sizeof(int2) * 64, s));
     launch_dep(colour_bounds, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);
     w->launches += 2;
     // contact visits in colour order (the sweeps' work list): visitStart[k] belongs to colOrder[k]
-    TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
     TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
     TRY(w->freeList.ensure((size_t)w->nDyn, false, s)); TRY(w->linkedList.ensure((size_t)w->nDyn, false, s));
-    CK(cudaMemsetAsync(w->visitCount.p + w->nDyn, 0, sizeof(int), s));
-    CK(cudaMemsetAsync(&w->dCnt->nFree, 0, 2 * sizeof(int), s));         // nFree, nLinkedFree
     launch_dep(visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p,
                fv, w->freeList.p, w->linkedList.p, w->dCnt);
     TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));

@@ -149,6 +149,29 @@ __device__ __forceinline__ bool outranks(int rankA, int localA, int rankB, int l
 // Work word of the rounds: low byte = state (0 static, 1 uncoloured, 2 + c coloured c), the rest = priority rank (old colour + 1, 0 = none).
 __device__ __forceinline__ int colour_word(int rank, int state) { return (rank << 8) | state; }
 
+// Everything the graph stage wants zeroed or initialised before its first real kernel, in ONE launch instead of six memset nodes and
+// colour_init (a step of a small world is a chain of dependent launches of a few microseconds each): adjacency ranges, entry counts, colour
+// ranges, the visit counts' terminator, the free-body counters, the colouring's list cursors, and — initMode 1: fresh, 2: ranked by the
+// previous colouring, 0: leave the work words alone — the colouring's work words.
+__global__ void graph_prologue(const int* flags, int n, int nDyn, int4* adjRange, int* deg, int2* colRange, int* visitCount, int* colCursor,
+                               Counters* cnt, int initMode, int* word, int* colour) {
+    cudaGridDependencySynchronize();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) deg[i] = 0;
+    if (i < n) {
+        adjRange[i] = make_int4(0, 0, 0, 0);
+        if (initMode) {
+            const bool dyn = (flags[i] & kDynamic) != 0;
+            int old = initMode == 2 ? colour[i] : -1;
+            word[i] = dyn ? colour_word(old >= 0 ? old + 1 : 0, 1) : 0;
+            colour[i] = dyn ? -1 : -2;
+        }
+    }
+    if (i < 64) colRange[i] = make_int2(0, 0);
+    if (i < 4) colCursor[i] = 0;
+    if (i == 0) { visitCount[nDyn] = 0; cnt->nFree = 0; cnt->nLinkedFree = 0; }
+}
+
 // oldColour: the previous colouring to rank by (nullptr / negative entries: none).  May alias `colour`.
 __global__ void colour_init(const int* flags, int n, const int* oldColour, int* word, int* colour) {
     cudaGridDependencySynchronize();
