@@ -114,6 +114,7 @@ struct avbd_world {
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
     int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
     long long graphReuses = 0; int persistentMaxBodies = 0;      // the tile cluster loop (solve_loop_cluster) is opt-in (AVBD_PERSISTENT_MAX_BODIES): measured (tools/loop_modes.py) the per-colour sweep launches match or beat it at every size (TwoBlockDrop 6.8k vs 6.6k steps/s, Pyramid 3.75k vs 3.6k, Stress1000 1.39k vs 1.23k, 8000 bodies 1.26k vs 0.69k)
+    size_t tilesCleared = 0;  // scan tiles bp_cells cleared at the start of this step's collision stage
     bool cellRaw = true;    // default: the per-cell sweep emits the sphere pairs, np_sat culls them.  AVBD_BROADPHASE=body: the per-body sweep instead
                             // (1M-box grid: bp_sweep 472 us against bp_sweep_cells<false> 328 us; small worlds: no difference)
     bool bodySweep = true;  // AVBD_BROADPHASE=cell: fused per-cell sweep + SAT cull instead of the per-body sweep + separate cull
@@ -212,8 +213,34 @@ int sort_keys(avbd_world* w, const K* kin, K* kout, int n, int bits) {
     w->libLaunches += 1 + (bits + 7) / 8 * 2;
     return 0;
 }
+// Exclusive prefix sum of a short array in ONE block (CUB's device scan is two launches; a small world's step is a chain of launches).
+constexpr int kScanSmallMax = 16384;
+__global__ void __launch_bounds__(1024) scan_small(const int* __restrict__ in, int* __restrict__ out, int n) {
+    cudaGridDependencySynchronize();
+    __shared__ int sWarp[32];
+    const int per = (n + 1023) / 1024;                     // consecutive items per thread
+    const int b = threadIdx.x * per, e = b + per < n ? b + per : n;
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += in[i];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+    if (lane == 31) sWarp[wp] = incl;
+    __syncthreads();
+    if (wp == 0) {
+        int v = sWarp[lane], sc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int up = __shfl_up_sync(0xffffffffu, sc, d); if (lane >= d) sc += up; }
+        sWarp[lane] = sc - v;
+    }
+    __syncthreads();
+    int run = sWarp[wp] + incl - sum;
+    for (int i = b; i < e; ++i) { int x = in[i]; out[i] = run; run += x; }
+}
 int exclusive_scan(avbd_world* w, const int* in, int* out, int n) {
     if (n <= 0) return 0;
+    if (n <= kScanSmallMax && in != out) { launch_dep(scan_small, dim3(1), dim3(1024), 0, w->stream, in, out, n); w->launches++; return 0; }
     size_t bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, w->stream));
     TRY(w->temp.ensure(bytes, false, w->stream));
@@ -370,13 +397,17 @@ int prepare(avbd_world* w) {
 // candCodeSorted).  sat = false stops at the sphere-overlap pairs (stage API: the reference's solver.cpp:262-266
 // candidate set).  sat = true merges last step's manifolds whose spheres no longer overlap, applies the exclusion list
 // and the 15-axis test, so what comes out is exactly the set of manifolds to build.  One host sync (sizes + overflow).
-int run_broadphase(avbd_world* w, bool sat) {
+int run_broadphase(avbd_world* w, bool sat, bool clearStepScratch = false) {
     cudaStream_t s = w->stream;
     int n = w->n;
     w->nCand = 0; w->nPairs = 0;
     if (n == 0) return 0;
     BodyView bv = w->bview(); GridView gv = w->gview();
-    launch_dep(bp_cells, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, w->dCnt);
+    // clearStepScratch (a whole step): the per-world diagnostics and the manifold build's scan tiles are cleared on the way
+    launch_dep(bp_cells, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, w->dCnt,
+               clearStepScratch ? (int*)w->dDiag.p : (int*)nullptr, clearStepScratch ? (int)(sizeof(Diag) / sizeof(int)) * w->nWorlds : 0,
+               clearStepScratch ? (int*)w->buildTiles.p : (int*)nullptr, clearStepScratch ? 2 * (int)w->buildTiles.cap : 0);
+    w->tilesCleared = clearStepScratch ? w->buildTiles.cap : 0;
     int tbits = bits_for(w->tableSize);   // sentinel bucket == tableSize needs one more bit
     TRY(sort_pairs(w, w->cellKey.p, w->cellKeySorted.p, w->cellVal.p, w->cellValSorted.p, n, tbits));
     launch_dep(bp_cell_bounds, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv);
@@ -397,10 +428,10 @@ int run_broadphase(avbd_world* w, bool sat) {
         if (sat && !w->bodySweep) launch_dep(bp_sweep_cells<true>, dim3(cellBlocks), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)w->excl.p, w->nExcl, out, bpw);
         else if (!w->bodySweep || w->cellRaw) launch_dep(bp_sweep_cells<false>, dim3(cellBlocks), dim3(kThreads), 0, s, bv, gv, (const unsigned long long*)nullptr, 0, raw, bpw);
         else launch_dep(bp_sweep, dim3(blocks_for(16ll * n)), dim3(kThreads), 0, s, bv, gv, raw);
-        if (w->nLarge) launch_dep(bp_large, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv, raw);
-        w->launches += 1 + (w->nLarge ? 1 : 0);
+        const int nOld = sat ? w->nM : 0;
+        if (w->nLarge || nOld > 0) { launch_dep(bp_side_pairs, dim3(blocks_for(std::max(w->nLarge ? n : 0, nOld))), dim3(kThreads), 0, s, bv, gv, w->mset(w->cur), nOld, raw, w->nLarge ? 1 : 0); w->launches++; }
+        w->launches += 1;
         if (sat) {
-            if (w->nM > 0) { launch_dep(bp_persisting, dim3(blocks_for(w->nM)), dim3(kThreads), 0, s, bv, w->mset(w->cur), w->nM, raw); w->launches++; }
             // sized by the pair count of the previous step (+ slack); the kernel reads the real count, a shortfall shows as overflow bit 16
             long long expect = std::min<long long>((long long)raw.cap, std::max<long long>(w->lastPairs + w->lastPairs / 8 + 4096, 1024));
             np_sat_launch(w, bv, raw, (int)expect, out);
@@ -427,10 +458,9 @@ int run_broadphase(avbd_world* w, bool sat) {
 int run_collide(avbd_world* w) {
     cudaStream_t s = w->stream;
     TRY(prepare(w));
-    if (w->n > 0) CK(cudaMemsetAsync(w->dDiag.p, 0, sizeof(Diag) * w->nWorlds, s));
     stage_event(w, 0);
     w->nMPrev = w->nM;
-    TRY(run_broadphase(w, true));
+    TRY(run_broadphase(w, true, true));
     stage_event(w, 1);
     int nSurv = w->nCand;
     int nxt = w->cur ^ 1;
@@ -444,7 +474,8 @@ int run_collide(avbd_world* w) {
         // contacts go straight to their dense place, in manifold order (chained scan over the build's blocks)
         int buildBlocks = blocks_for(nSurv, kBuildThreads);
         TRY(w->buildTiles.ensure((size_t)buildBlocks, false, s));
-        CK(cudaMemsetAsync(w->buildTiles.p, 0, (size_t)buildBlocks * sizeof(unsigned long long), s));
+        if (w->tilesCleared < (size_t)buildBlocks)      // grown since bp_cells cleared it (or not cleared at all)
+            CK(cudaMemsetAsync(w->buildTiles.p, 0, (size_t)buildBlocks * sizeof(unsigned long long), s));
         launch_dep(np_build, dim3(buildBlocks), dim3(kBuildThreads), kBuildThreads * kPolyFloatsPerThread * sizeof(float), s,
             w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift, w->mset(w->cur), w->nM, w->mset(nxt), w->prm, w->dCnt, w->buildTiles.p);
         w->launches++;

@@ -47,10 +47,15 @@ __device__ __forceinline__ int3 cell_of(float4 pos, float cell) {
 
 // K1a: bucket key per body.  Large bodies (flag) go to the sentinel bucket past the table.
 // Also clears the bucket table and the step's counters (two memset nodes less in the launch chain of a small world's step).
-__global__ void bp_cells(BodyView b, GridView g, Counters* cnt) {
+// `zeroA / zeroB`: two more scratch arrays the step wants cleared before the collision kernels run (per-world diagnostics, the manifold
+// build's scan tiles), as 4-byte words.
+__global__ void bp_cells(BodyView b, GridView g, Counters* cnt, int* zeroA, int nZeroA, int* zeroB, int nZeroB) {
     cudaGridDependencySynchronize();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    for (unsigned k = (unsigned)i; k <= g.tableMask; k += gridDim.x * blockDim.x) g.cellRange[k] = make_int2(0, 0);
+    const int stride = gridDim.x * blockDim.x;
+    for (unsigned k = (unsigned)i; k <= g.tableMask; k += stride) g.cellRange[k] = make_int2(0, 0);
+    for (int k = i; k < nZeroA; k += stride) zeroA[k] = 0;
+    for (int k = i; k < nZeroB; k += stride) zeroB[k] = 0;
     if (i < (int)(sizeof(Counters) / sizeof(int))) reinterpret_cast<int*>(cnt)[i] = 0;
     if (i >= b.n) return;
     unsigned k = g.tableMask + 1u;
@@ -422,11 +427,23 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView 
     }
 }
 
-// K1d: every body against the large bodies of its own world.
-__global__ void bp_large(BodyView b, GridView g, PairSink sink) {
+// K1d + K2 in one launch.
+// K1d (thread j < n): every body against the large bodies of its own world.
+// K2 (thread m < nOld): manifolds that survived last step persist as candidates whether or not their spheres still overlap
+// (solver.cpp:274-279 only deletes on initialize()==false).  Pairs whose spheres DO overlap were emitted by the sweeps; this adds
+// the rest (rare), so every candidate appears exactly once.  nOld = 0: the sphere pairs only (stage API).
+__global__ void bp_side_pairs(BodyView b, GridView g, ManifoldSet old, int nOld, PairSink sink, int anyLarge) {
     cudaGridDependencySynchronize();
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= b.n) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nOld) {
+        int4 h = old.hdr[j];
+        if (h.z > 0) {
+            float4 pa = b.pose[h.x].pos; pa.w = body_radius(b.size[h.x]);
+            float4 pb = b.pose[h.y].pos; pb.w = body_radius(b.size[h.y]);
+            if (!spheres_overlap(pa, pb)) emit_pair(sink, old.key[j], 1);
+        }
+    }
+    if (!anyLarge || j >= b.n) return;
     int w = b.worldId[j];
     int t0 = g.worldLargeStart[w], t1 = g.worldLargeStart[w + 1];
     if (t0 == t1) return;
@@ -439,20 +456,6 @@ __global__ void bp_large(BodyView b, GridView g, PairSink sink) {
         float4 pl = b.pose[l].pos; pl.w = body_radius(b.size[l]);
         if (spheres_overlap(pj, pl)) emit_pair(sink, j > l ? pair_key(j, l, sink.keyShift) : pair_key(l, j, sink.keyShift), 1);
     }
-}
-
-// K2: manifolds that survived last step persist as candidates whether or not their spheres still overlap
-// (solver.cpp:274-279 only deletes on initialize()==false).  Pairs whose spheres DO overlap were emitted by the sweeps
-// above; this kernel adds the rest (rare), so every candidate appears exactly once.
-__global__ void bp_persisting(BodyView b, ManifoldSet old, int nOld, PairSink sink) {
-    cudaGridDependencySynchronize();
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= nOld) return;
-    int4 h = old.hdr[m];
-    if (h.z <= 0) return;
-    float4 pa = b.pose[h.x].pos; pa.w = body_radius(b.size[h.x]);
-    float4 pb = b.pose[h.y].pos; pb.w = body_radius(b.size[h.y]);
-    if (!spheres_overlap(pa, pb)) emit_pair(sink, old.key[m], 1);
 }
 
 // K3a: SAT cull (collision.cpp:420-468).  Candidates are read in emission order — which follows the cell-sorted body order, so
