@@ -542,6 +542,25 @@ int run_colour(avbd_world* w) {
     TRY(w->deg.ensure((size_t)n + 1, false, s)); TRY(w->estart.ensure((size_t)n + 1, false, s));
     TRY(w->colourWord.ensure(n, false, s)); TRY(w->colCursor.ensure(4, false, s));
     TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
+    // a small world: the whole stage in one block (avbd_kernels_graph.cuh: graph_small)
+    const bool smallGraph = nM <= kSmallGraphMax && w->nDyn <= kSmallGraphMax && n <= kSmallGraphMax + 64 && !keep && !havePrev && !getenv("AVBD_NO_SMALL_GRAPH");
+    if (smallGraph) {
+        TRY(w->bKeySorted.ensure(std::max(1, nM), false, s)); TRY(w->bList.ensure(std::max(1, nM), false, s));
+        TRY(w->entries.ensure((size_t)std::max(1, 2 * nM), false, s));
+        TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
+        TRY(w->freeList.ensure((size_t)w->nDyn, false, s)); TRY(w->linkedList.ensure((size_t)w->nDyn, false, s));
+        TRY(w->colVisit.ensure(64, false, s));
+        SmallGraph g;
+        g.flags = w->flags.p; g.n = n; g.dynList = w->dynList.p; g.nDyn = w->nDyn; g.localIdx = w->localIdx.p;
+        g.hdr = ms.hdr; g.cstart = ms.cstart; g.nM = nM; g.sortBits = bits_for((unsigned long long)n);
+        g.adjRange = w->adjRange.p; g.bList = w->bList.p; g.bKeySorted = w->bKeySorted.p; g.deg = w->deg.p; g.estart = w->estart.p; g.entries = w->entries.p;
+        g.colour = w->colour.p; g.colKeySorted = w->colKeySorted.p; g.colOrder = w->colOrder.p; g.colRange = w->colRange.p;
+        g.visitCount = w->visitCount.p; g.visitStart = w->visitStart.p; g.visits = w->visits.p; g.colVisit = w->colVisit.p;
+        g.freeList = w->freeList.p; g.linkedList = w->linkedList.p; g.aux = w->aux.p; g.cnt = w->dCnt;
+        launch_dep(graph_small, dim3(1), dim3(kSmallGraphThreads), 0, s, g, w->fview());
+        w->launches++;
+        w->colouredBodies = n;
+    } else {
     launch_dep(graph_prologue, dim3(blocks_for((long long)n + 1)), dim3(kThreads), 0, s, w->flags.p, n, w->nDyn, w->adjRange.p, w->deg.p, w->colRange.p, w->visitCount.p,
                w->colCursor.p, w->dCnt, (keepSaved || keep) ? 0 : (havePrev ? 2 : 1), w->colourWord.p, w->colour.p);
     w->launches++;
@@ -647,6 +666,7 @@ int run_colour(avbd_world* w) {
     TRY(w->colVisit.ensure(64, false, s));
     launch_dep(colour_visit_bounds, dim3(1), dim3(64), 0, s, w->colRange.p, w->dCnt, w->visitStart.p, w->colVisit.p);
     w->launches += 3;
+    }
     w->visitGeomStale = true;
     // ONE host round trip for everything the launches of the sweeps need: colour ranges, their visit ranges, counters
     CK(cudaMemcpyAsync(w->hColRange, w->colRange.p, sizeof(int2) * 64, cudaMemcpyDeviceToHost, s));

@@ -4,6 +4,7 @@
 #pragma once
 #include "avbd_kernels_collide.cuh"
 #include "avbd_launch.h"
+#include <cub/block/block_radix_sort.cuh>
 
 namespace avbd {
 
@@ -11,34 +12,37 @@ namespace avbd {
 // Manifolds are sorted by (A,B): a body's "I am A" manifolds are one contiguous
 // run [x,y).  Its "I am B" manifolds are a run [z,w) of bList (manifold ids
 // stably sorted by B).  adjRange must be zeroed before these two kernels.
+__device__ __forceinline__ unsigned adj_a_one(int m, const int4* hdr, int nM, const int* flags, int nBodies, int4* adjRange) {
+    int4 h = hdr[m];
+    if (m == 0 || hdr[m - 1].x != h.x) adjRange[h.x].x = m;
+    if (m == nM - 1 || hdr[m + 1].x != h.x) adjRange[h.x].y = m + 1;
+    return (flags[h.y] & kDynamic) ? (unsigned)h.y : (unsigned)nBodies;          // static B never solves: park at the end
+}
 __global__ void adj_a_ranges(const int4* hdr, int nM, const int* flags, int nBodies, int4* adjRange, unsigned* bKey, int* bVal) {
     cudaGridDependencySynchronize();
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nM) return;
-    int4 h = hdr[m];
-    if (m == 0 || hdr[m - 1].x != h.x) adjRange[h.x].x = m;
-    if (m == nM - 1 || hdr[m + 1].x != h.x) adjRange[h.x].y = m + 1;
-    bKey[m] = (flags[h.y] & kDynamic) ? (unsigned)h.y : (unsigned)nBodies;   // static B never solves: park at the end
+    bKey[m] = adj_a_one(m, hdr, nM, flags, nBodies, adjRange);
     bVal[m] = m;
+}
+__device__ __forceinline__ void adj_b_one(int t, const unsigned* bKeySorted, int nM, int nBodies, int4* adjRange) {
+    unsigned k = bKeySorted[t];
+    if (k >= (unsigned)nBodies) return;
+    if (t == 0 || bKeySorted[t - 1] != k) adjRange[k].z = t;
+    if (t == nM - 1 || bKeySorted[t + 1] != k) adjRange[k].w = t + 1;
 }
 __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, int4* adjRange) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nM) return;
-    unsigned k = bKeySorted[t];
-    if (k >= (unsigned)nBodies) return;
-    if (t == 0 || bKeySorted[t - 1] != k) adjRange[k].z = t;
-    if (t == nM - 1 || bKeySorted[t + 1] != k) adjRange[k].w = t + 1;
+    adj_b_one(t, bKeySorted, nM, nBodies, adjRange);
 }
 
 // ------------------------------------------------------------------ body -> manifold entries (CSR)
 // One entry per LIVE manifold touching a dynamic body, in pair-key order (the body's "I am A" run, then its "I am B" run): the OTHER
 // body, 4 bytes — the colouring's adjacency list and nothing else (the sweeps walk the visit lists).  estart is indexed by BODY
 // (n + 1 entries, static bodies own none).
-__global__ void entry_count(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* deg) {
-    cudaGridDependencySynchronize();
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nDyn) return;
+__device__ __forceinline__ void entry_count_one(int t, const int* dynList, const int4* adjRange, const int* bList, const int4* hdr, int* deg) {
     int i = dynList[t];
     int4 rg = adjRange[i];
     int k = 0;
@@ -46,16 +50,25 @@ __global__ void entry_count(const int* dynList, int nDyn, const int4* adjRange, 
     for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z > 0 ? 1 : 0;
     deg[i] = k;
 }
-__global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
-                           const int* estart, int* entries) {
+__global__ void entry_count(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* deg) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
+    entry_count_one(t, dynList, adjRange, bList, hdr, deg);
+}
+__device__ __forceinline__ void entry_fill_one(int t, const int* dynList, const int4* adjRange, const int* bList, const int4* hdr, const int* estart, int* entries) {
     int i = dynList[t];
     int4 rg = adjRange[i];
     int o = estart[i];
     for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; if (h.z > 0) entries[o++] = h.y; }
     for (int q = rg.z; q < rg.w; ++q) { int4 h = hdr[bList[q]]; if (h.z > 0) entries[o++] = h.x; }
+}
+__global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
+                           const int* estart, int* entries) {
+    cudaGridDependencySynchronize();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    entry_fill_one(t, dynList, adjRange, bList, hdr, estart, entries);
 }
 
 // ------------------------------------------------------------------ contact-visit lists
@@ -69,11 +82,8 @@ __global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, c
 // Also lists the dynamic bodies NO contact visits (the sweeps' visit pipeline never meets them; primal_free_bodies solves them):
 // `freeList` those no user force touches either, `linkedList` those a joint / spring links to another body (they keep their place
 // in the colour order).  The lists' order is irrelevant.
-__global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount,
-                            ForceView fv, int* freeList, int* linkedList, Counters* cnt) {
-    cudaGridDependencySynchronize();
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nDyn) return;
+__device__ __forceinline__ void visit_count_one(int t, const int* colOrder, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount,
+                                                const ForceView& fv, int* freeList, int* linkedList, Counters* cnt) {
     int i = colOrder[t];
     int4 rg = adjRange[i];
     int k = 0;
@@ -91,11 +101,15 @@ __global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange,
         }
     }
 }
-__global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
-                           const int* visitStart, const BodyAux* aux, const int* colour, int4* visits) {
+__global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount,
+                            ForceView fv, int* freeList, int* linkedList, Counters* cnt) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
+    visit_count_one(t, colOrder, adjRange, bList, hdr, visitCount, fv, freeList, linkedList, cnt);
+}
+__device__ __forceinline__ void visit_fill_one(int t, const int* colOrder, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
+                                               const int* visitStart, const BodyAux* aux, const int* colour, int4* visits) {
     int i = colOrder[t];
     int4 rg = adjRange[i];
     int o = visitStart[t];
@@ -111,6 +125,13 @@ __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, 
         int m = bList[q]; int4 h = hdr[m]; int c0 = cstart[m]; int tag = idx | first(h.x);
         for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.x, tag, h.w);
     }
+}
+__global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
+                           const int* visitStart, const BodyAux* aux, const int* colour, int4* visits) {
+    cudaGridDependencySynchronize();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    visit_fill_one(t, colOrder, adjRange, bList, hdr, cstart, visitStart, aux, colour, visits);
 }
 
 // Once per step (the narrowphase rewrites every contact): copy each visit's contact geometry into visit order, so the
@@ -401,6 +422,132 @@ __global__ void colour_visit_bounds(const int2* colourRange, const Counters* cnt
     if (c >= 64) return;
     int2 r = c < cnt->nColours ? colourRange[c] : make_int2(0, 0);
     out[c] = r.y > r.x ? make_int2(visitStart[r.x], visitStart[r.y]) : make_int2(0, 0);
+}
+
+// ------------------------------------------------------------------ the whole graph stage of a SMALL world in one block
+// A small world's step is a chain of dependent launches of a few microseconds each, and the graph stage alone was sixteen of them
+// (Stress1000: 0.107 of 0.67 ms).  Up to kSmallGraphMax manifolds / dynamic bodies one block of 1024 threads runs every phase itself
+// — the very per-element routines of the kernels above, a block barrier where they have a kernel boundary, cub::BlockRadixSort (stable,
+// like the device-wide sorts it replaces) and a block prefix sum — so adjacency order, colours, colour order and visit lists come out
+// identical to the multi-launch path's.  Fresh colouring only (the default).
+constexpr int kSmallGraphThreads = 1024;
+constexpr int kSmallGraphItems = 4;
+constexpr int kSmallGraphMax = kSmallGraphThreads * kSmallGraphItems;
+// exclusive prefix sum of in[0, n) by the whole block (1024 threads); sWarp: 32 ints of shared memory.  in != out.
+__device__ __forceinline__ void block_scan_exclusive(const int* __restrict__ in, int* __restrict__ out, int n, int* sWarp) {
+    const int per = (n + kSmallGraphThreads - 1) / kSmallGraphThreads;      // consecutive items per thread
+    const int b = threadIdx.x * per, e = b + per < n ? b + per : n;
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += in[i];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+    __syncthreads();                                       // sWarp may still be read from a previous call
+    if (lane == 31) sWarp[wp] = incl;
+    __syncthreads();
+    if (wp == 0) {
+        int v = sWarp[lane], sc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int up = __shfl_up_sync(0xffffffffu, sc, d); if (lane >= d) sc += up; }
+        sWarp[lane] = sc - v;
+    }
+    __syncthreads();
+    int run = sWarp[wp] + incl - sum;
+    for (int i = b; i < e; ++i) { int x = in[i]; out[i] = run; run += x; }
+}
+struct SmallGraph {
+    const int* flags; int n; const int* dynList; int nDyn; const int* localIdx;
+    const int4* hdr; const int* cstart; int nM; int sortBits;
+    int4* adjRange; int* bList; unsigned* bKeySorted; int* deg; int* estart; int* entries;
+    int* colour; unsigned* colKeySorted; int* colOrder; int2* colRange;
+    int* visitCount; int* visitStart; int4* visits; int2* colVisit;
+    int* freeList; int* linkedList; const BodyAux* aux; Counters* cnt;
+};
+__global__ void __launch_bounds__(kSmallGraphThreads) graph_small(SmallGraph a, ForceView fv) {
+    cudaGridDependencySynchronize();
+    using Sort = cub::BlockRadixSort<unsigned, kSmallGraphThreads, kSmallGraphItems, int>;
+    __shared__ union Scratch { typename Sort::TempStorage sort; int word[kSmallGraphMax + 64]; Scratch() {} } sm;   // the sorts and the colouring never overlap
+    __shared__ int sWarp[32];
+    const int tid = threadIdx.x;
+    constexpr int T = kSmallGraphThreads;
+    // ---- prologue
+    for (int i = tid; i <= a.n; i += T) {
+        a.deg[i] = 0;
+        if (i < a.n) { a.adjRange[i] = make_int4(0, 0, 0, 0); a.colour[i] = (a.flags[i] & kDynamic) ? -1 : -2; }
+    }
+    if (tid < 64) a.colRange[tid] = make_int2(0, 0);
+    if (tid == 0) { a.visitCount[a.nDyn] = 0; a.cnt->nFree = 0; a.cnt->nLinkedFree = 0; }
+    __syncthreads();
+    // ---- adjacency: A runs, manifolds stably sorted by B, B runs
+    unsigned keys[kSmallGraphItems]; int vals[kSmallGraphItems];
+#pragma unroll
+    for (int k = 0; k < kSmallGraphItems; ++k) {
+        const int m = tid * kSmallGraphItems + k;
+        keys[k] = m < a.nM ? adj_a_one(m, a.hdr, a.nM, a.flags, a.n, a.adjRange) : 0xffffffffu;
+        vals[k] = m;
+    }
+    Sort(sm.sort).Sort(keys, vals, 0, a.sortBits);
+#pragma unroll
+    for (int k = 0; k < kSmallGraphItems; ++k) {
+        const int idx = tid * kSmallGraphItems + k;
+        if (idx < a.nM) { a.bKeySorted[idx] = keys[k]; a.bList[idx] = vals[k]; }
+    }
+    __syncthreads();
+    for (int t = tid; t < a.nM; t += T) adj_b_one(t, a.bKeySorted, a.nM, a.n, a.adjRange);
+    __syncthreads();
+    // ---- body -> neighbour entries
+    for (int t = tid; t < a.nDyn; t += T) entry_count_one(t, a.dynList, a.adjRange, a.bList, a.hdr, a.deg);
+    __syncthreads();
+    block_scan_exclusive(a.deg, a.estart, a.n + 1, sWarp);
+    __syncthreads();
+    for (int t = tid; t < a.nDyn; t += T) entry_fill_one(t, a.dynList, a.adjRange, a.bList, a.hdr, a.estart, a.entries);
+    // ---- colouring: Jones-Plassmann rounds on work words in shared memory (colour_rounds_block)
+    for (int i = tid; i < a.n; i += T) sm.word[i] = (a.flags[i] & kDynamic) ? colour_word(0, 1) : 0;
+    __syncthreads();
+    {
+        int left = 1;
+        for (int round = 0; round < 4096 && left; ++round) {
+            int mine = 0;
+            for (int t = tid; t < a.nDyn; t += T)
+                if (!try_colour(a.dynList[t], a.estart, a.entries, fv, a.localIdx, sm.word, a.colour, a.cnt)) mine = 1;
+            left = __syncthreads_or(mine);
+        }
+        if (tid == 0) a.cnt->nUncoloured = left;
+    }
+    __syncthreads();
+    // ---- colour order (stable by colour), colour ranges
+#pragma unroll
+    for (int k = 0; k < kSmallGraphItems; ++k) {
+        const int t = tid * kSmallGraphItems + k;
+        const int i = t < a.nDyn ? a.dynList[t] : -1;
+        keys[k] = i >= 0 ? (unsigned)a.colour[i] : 0xffffffffu;
+        vals[k] = i;
+    }
+    Sort(sm.sort).Sort(keys, vals, 0, 7);
+#pragma unroll
+    for (int k = 0; k < kSmallGraphItems; ++k) {
+        const int t = tid * kSmallGraphItems + k;
+        if (t < a.nDyn) { a.colKeySorted[t] = keys[k]; a.colOrder[t] = vals[k]; }
+    }
+    __syncthreads();
+    for (int t = tid; t < a.nDyn; t += T) {
+        unsigned c = a.colKeySorted[t];
+        if (t == 0 || a.colKeySorted[t - 1] != c) a.colRange[c].x = t;
+        if (t == a.nDyn - 1 || a.colKeySorted[t + 1] != c) a.colRange[c].y = t + 1;
+        if (t == a.nDyn - 1) a.cnt->nColours = (int)c + 1;
+    }
+    __syncthreads();
+    // ---- contact visits in colour order
+    for (int t = tid; t < a.nDyn; t += T) visit_count_one(t, a.colOrder, a.adjRange, a.bList, a.hdr, a.visitCount, fv, a.freeList, a.linkedList, a.cnt);
+    __syncthreads();
+    block_scan_exclusive(a.visitCount, a.visitStart, a.nDyn + 1, sWarp);
+    __syncthreads();
+    for (int t = tid; t < a.nDyn; t += T) visit_fill_one(t, a.colOrder, a.adjRange, a.bList, a.hdr, a.cstart, a.visitStart, a.aux, a.colour, a.visits);
+    if (tid < 64) {
+        int2 r = tid < a.cnt->nColours ? a.colRange[tid] : make_int2(0, 0);
+        a.colVisit[tid] = r.y > r.x ? make_int2(a.visitStart[r.x], a.visitStart[r.y]) : make_int2(0, 0);
+    }
 }
 
 // ------------------------------------------------------------------ predict / warm-start decay of user forces
