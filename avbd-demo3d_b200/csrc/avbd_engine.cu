@@ -97,7 +97,6 @@ struct avbd_world {
     DevBuf<int2> sortedCell; DevBuf<float4> sortedPos, sortedFrame, bodyFrame;
     DevBuf<int> largeList, worldLargeStart; int nLarge = 0;
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
-    DevBuf<int> candCode, candCodeSorted;
     DevBuf<unsigned long long> buildTiles;      // np_build's chained scan over its blocks
     DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;      // per-contact visit lists: small worlds (cluster loop) only
     DevBuf<int> deg, estart, colCursor, sweepRange, freeList, linkedList; DevBuf<int> entries; DevBuf<int2> colVisit; DevBuf<float4> vgA, vgB, vgN;
@@ -394,7 +393,7 @@ int prepare(avbd_world* w) {
 }
 
 // Broadphase (+ SAT cull): leaves the key-sorted pairs in candSorted (and, with `sat`, their winning SAT axis in
-// candCodeSorted).  sat = false stops at the sphere-overlap pairs (stage API: the reference's solver.cpp:262-266
+// the upper bits of each key).  sat = false stops at the sphere-overlap pairs (stage API: the reference's solver.cpp:262-266
 // candidate set).  sat = true merges last step's manifolds whose spheres no longer overlap, applies the exclusion list
 // and the 15-axis test, so what comes out is exactly the set of manifolds to build.  One host sync (sizes + overflow).
 int run_broadphase(avbd_world* w, bool sat, bool clearStepScratch = false) {
@@ -413,12 +412,12 @@ int run_broadphase(avbd_world* w, bool sat, bool clearStepScratch = false) {
     launch_dep(bp_cell_bounds, dim3(blocks_for(n)), dim3(kThreads), 0, s, bv, gv);
     w->launches += 2;
     if (w->pairs.cap == 0) TRY(w->pairs.ensure((size_t)std::max(1024, 12 * n), false, s));
-    if (w->cand.cap == 0) { TRY(w->cand.ensure((size_t)std::max(1024, 3 * n), false, s)); TRY(w->candCode.ensure(w->cand.cap, false, s)); }
+    if (w->cand.cap == 0) TRY(w->cand.ensure((size_t)std::max(1024, 3 * n), false, s));
     for (int attempt = 0; attempt < 8; ++attempt) {
         if (attempt > 0) CK(cudaMemsetAsync(w->dCnt, 0, sizeof(Counters), s));        // the first attempt's counters were cleared by bp_cells
-        PairSink raw; raw.keys = w->pairs.p; raw.codes = nullptr; raw.cap = (int)w->pairs.cap; raw.keyShift = w->keyShift;
+        PairSink raw; raw.keys = w->pairs.p; raw.codes = nullptr; raw.cap = (int)w->pairs.cap; raw.keyShift = w->keyShift; raw.codeShift = 0;
         raw.count = &w->dCnt->nPairs; raw.cnt = w->dCnt; raw.overflowBit = 1;
-        PairSink out; out.keys = w->cand.p; out.codes = w->candCode.p; out.cap = (int)std::min(w->cand.cap, w->candCode.cap); out.keyShift = w->keyShift;
+        PairSink out; out.keys = w->cand.p; out.codes = nullptr; out.cap = (int)w->cand.cap; out.keyShift = w->keyShift; out.codeShift = 2 * w->keyShift;   // 2 * keyShift + 5 <= 64
         out.count = &w->dCnt->nCand; out.cnt = w->dCnt; out.overflowBit = 2;
         // small-vs-small pairs: one warp per 32 cell-sorted bodies; with `sat` the cull is fused in and only survivors are written.
         // AVBD_BROADPHASE=cell selects the fused per-cell kernel (A/B measurements; default is the per-body sweep + separate cull).
@@ -437,16 +436,16 @@ int run_broadphase(avbd_world* w, bool sat, bool clearStepScratch = false) {
             np_sat_launch(w, bv, raw, (int)expect, out);
         }
         TRY(read_counters(w));
-        bool rawOver = w->hCnt->nPairs > raw.cap, satShort = sat && w->hCnt->nPairs > w->satLaunched, outOver = sat && w->hCnt->nCand > (int)std::min(w->cand.cap, w->candCode.cap);
+        bool rawOver = w->hCnt->nPairs > raw.cap, satShort = sat && w->hCnt->nPairs > w->satLaunched, outOver = sat && w->hCnt->nCand > (int)w->cand.cap;
         w->lastPairs = w->hCnt->nPairs;
         if (!rawOver && !satShort && !outOver) { w->nPairs = w->hCnt->nPairs + w->hCnt->nSphere; w->nCand = sat ? w->hCnt->nCand : w->hCnt->nPairs; break; }
         if (rawOver) TRY(w->pairs.ensure((size_t)w->hCnt->nPairs + w->hCnt->nPairs / 4 + 1024, false, s));
-        if (outOver) { TRY(w->cand.ensure((size_t)w->hCnt->nCand + w->hCnt->nCand / 4 + 1024, false, s)); TRY(w->candCode.ensure(w->cand.cap, false, s)); }
+        if (outOver) TRY(w->cand.ensure((size_t)w->hCnt->nCand + w->hCnt->nCand / 4 + 1024, false, s));
         if (attempt == 7) return fail(AVBD_ERR_CAPACITY, "pair buffer kept overflowing");
     }
     if (sat) {
-        TRY(w->candSorted.ensure(w->cand.cap, false, s)); TRY(w->candCodeSorted.ensure(w->cand.cap, false, s));
-        TRY(sort_pairs(w, w->cand.p, w->candSorted.p, w->candCode.p, w->candCodeSorted.p, w->nCand, 2 * w->keyShift));
+        TRY(w->candSorted.ensure(w->cand.cap, false, s));
+        TRY(sort_keys(w, w->cand.p, w->candSorted.p, w->nCand, 2 * w->keyShift));       // the SAT codes ride in the keys' upper bits
     } else {
         TRY(w->candSorted.ensure(w->pairs.cap, false, s));
         TRY(sort_keys(w, w->pairs.p, w->candSorted.p, w->nCand, 2 * w->keyShift));
@@ -477,7 +476,7 @@ int run_collide(avbd_world* w) {
         if (w->tilesCleared < (size_t)buildBlocks)      // grown since bp_cells cleared it (or not cleared at all)
             CK(cudaMemsetAsync(w->buildTiles.p, 0, (size_t)buildBlocks * sizeof(unsigned long long), s));
         launch_dep(np_build, dim3(buildBlocks), dim3(kBuildThreads), kBuildThreads * kPolyFloatsPerThread * sizeof(float), s,
-            w->bview(), w->candSorted.p, w->candCodeSorted.p, nSurv, w->keyShift, w->mset(w->cur), w->nM, w->mset(nxt), w->prm, w->dCnt, w->buildTiles.p);
+            w->bview(), w->candSorted.p, (const int*)nullptr, nSurv, w->keyShift, w->mset(w->cur), w->nM, w->mset(nxt), w->prm, w->dCnt, w->buildTiles.p);
         w->launches++;
         TRY(read_counters(w));
         w->nContacts = w->hCnt->nContacts;
@@ -931,7 +930,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->flags.release(); w->worldId.release(); w->localIdx.release(); w->dynList.release(); w->colWorkA.release(); w->colWorkB.release(); w->colourWord.release();
     w->cellKey.release(); w->cellKeySorted.release(); w->cellVal.release(); w->cellValSorted.release(); w->cellRange.release();
     w->sortedCell.release(); w->sortedPos.release(); w->sortedFrame.release(); w->bodyFrame.release(); w->largeList.release(); w->worldLargeStart.release();
-    w->pairs.release(); w->cand.release(); w->candSorted.release(); w->candCode.release(); w->candCodeSorted.release();
+    w->pairs.release(); w->cand.release(); w->candSorted.release();
     for (auto& b : w->mb) { b.key.release(); b.hdr.release(); b.cstart.release(); b.cM.release(); b.cA.release(); b.cB.release(); b.cN.release(); b.lp.release(); }
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
@@ -1615,7 +1614,9 @@ int avbd_download_pairs(avbd_world* w, int* pairs, int cap) {
     CK(cudaMemcpyAsync(k.data(), w->candSorted.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
     int out = 0;
+    const unsigned long long pairMask = (1ull << (2 * w->keyShift)) - 1ull;      // after a step the SAT codes ride above the pair bits
     for (int i = 0; i < nc; ++i) {
+        k[i] &= pairMask;
         if (i > 0 && k[i] == k[i - 1]) continue;
         if (out < cap) { pairs[2 * out] = (int)(k[i] >> w->keyShift); pairs[2 * out + 1] = (int)(k[i] & ((1ull << w->keyShift) - 1ull)); }
         ++out;

@@ -96,9 +96,14 @@ __global__ void bp_cell_bounds(BodyView b, GridView g) {
     if (p == b.n - 1 || g.keySorted[p + 1] != k) g.cellRange[k].y = p + 1;
 }
 
+// codeShift > 0: the pair's code (the SAT's winning axis) rides in the key's bits from codeShift up — above the 2 * keyShift bits the
+// sort looks at — so the survivors are sorted keys-only (8 bytes per item through every radix pass instead of 12); codes is then unused.
 struct PairSink {
-    unsigned long long* keys; int* codes; int cap; int keyShift; int* count; Counters* cnt; int overflowBit;
+    unsigned long long* keys; int* codes; int cap; int keyShift; int* count; Counters* cnt; int overflowBit; int codeShift;
 };
+__device__ __forceinline__ unsigned long long sink_key(const PairSink& s, unsigned long long key, int code) {
+    return s.codeShift > 0 ? key | ((unsigned long long)(unsigned)code << s.codeShift) : key;
+}
 
 // Warp-aggregated append: the lanes that reach this call together take one
 // atomic for the group and write a contiguous run.
@@ -109,7 +114,7 @@ __device__ __forceinline__ void emit_pair(const PairSink& s, unsigned long long 
     base = grp.shfl(base, 0);
     int idx = base + (int)grp.thread_rank();
     if (idx < s.cap) {
-        s.keys[idx] = key;
+        s.keys[idx] = sink_key(s, key, code);
         if (s.codes) s.codes[idx] = code;
     } else atomicOr(&s.cnt->overflow, s.overflowBit);
 }
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_cells(BodyView b, GridView 
     __syncthreads();
     for (int e = threadIdx.x; e < staged; e += blockDim.x) {
         const int idx = sBase + e;
-        if (idx < sink.cap) { sink.keys[idx] = sKeys[e]; if (SAT) sink.codes[idx] = sCodes[e]; }
+        if (idx < sink.cap) { sink.keys[idx] = SAT ? sink_key(sink, sKeys[e], sCodes[e]) : sKeys[e]; if (SAT && sink.codes) sink.codes[idx] = sCodes[e]; }
         else atomicOr(&sink.cnt->overflow, sink.overflowBit);
     }
 }
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 4) np_sat(BodyView b, const float4* 
         base = __shfl_sync(kFull, base, 0);
         if (lane < count) {
             const int idx = base + lane, e = nOut - count + lane;
-            if (idx < out.cap) { out.keys[idx] = sOutKey[w][e]; out.codes[idx] = sOutCode[w][e]; }
+            if (idx < out.cap) { out.keys[idx] = sink_key(out, sOutKey[w][e], sOutCode[w][e]); if (out.codes) out.codes[idx] = sOutCode[w][e]; }
             else atomicOr(&out.cnt->overflow, out.overflowBit);
         }
         __syncwarp();
@@ -604,12 +609,15 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool inRange = s < nSurvive;
-    unsigned long long k = inRange ? cand[s] : 0ull;
+    const unsigned long long pairMask = (1ull << (2 * keyShift)) - 1ull;          // info == nullptr: the SAT code rides above the pair bits
+    const unsigned long long kc = inRange ? cand[s] : 0ull;
+    unsigned long long k = kc & pairMask;
+    const int satCode = inRange ? (info ? info[s] : (int)(kc >> (2 * keyShift))) : 0;
     int a = (int)(k >> keyShift), c = (int)(k & ((1ull << keyShift) - 1ull));
     bool build = inRange;
     if (inRange) {
         out.key[s] = k;
-        if (s > 0 && cand[s - 1] == k) {      // the sweeps emit every pair once; a repeat would double a manifold: keep a dead slot, flag it
+        if (s > 0 && (cand[s - 1] & pairMask) == k) {      // the sweeps emit every pair once; a repeat would double a manifold: keep a dead slot, flag it
             atomicOr(&cnt->overflow, 8);
             build = false;
         }
@@ -642,7 +650,7 @@ __global__ void __launch_bounds__(kBuildThreads) np_build(BodyView b, const unsi
             q[7 * rs] = normal.x; q[8 * rs] = normal.y; q[9 * rs] = normal.z;
             ++n;
         };
-        build_contacts_emit(posA, rotA, xyz(sa), posB, rotB, xyz(sb), info[s], poly, emit);
+        build_contacts_emit(posA, rotA, xyz(sa), posB, rotB, xyz(sb), satCode, poly, emit);
     }
     // this block's range of the dense contact arrays: warp scan of the counts, block total PUBLISHED at once (the blocks after this one
     // can go on); the block's own base — the sum of its predecessors' totals — is only needed by the stores, so it is looked up after the
