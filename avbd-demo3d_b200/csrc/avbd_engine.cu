@@ -54,7 +54,7 @@ struct DevBuf {
 };
 
 constexpr int kColourBlockMaxBodies = 2048;      // at most this many dynamic bodies: colouring rounds run in one block
-static int colour_block_max() { static const int v = [] { const char* e = getenv("AVBD_COLOUR_BLOCK_MAX"); return e ? atoi(e) : kColourBlockMaxBodies; }(); return v; }
+static int colour_block_max() { const char* e = getenv("AVBD_COLOUR_BLOCK_MAX"); return e ? atoi(e) : kColourBlockMaxBodies; }      // read every time (tests switch it)
 inline int blocks_for(long long n, int threads = kThreads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
 
 struct HostBody {   // what the host must remember to (re)classify bodies; dynamic state lives on the device

@@ -275,3 +275,29 @@ def test_world_wider_than_1024_cells_pair_set_exact(avbd):
         assert w.diagnostics()["nanEvents"] == 0
     finally:
         o.close(); w.close()
+
+
+@pytest.mark.parametrize("switch", ["AVBD_NO_SMALL_GRAPH", "AVBD_COLOUR_BLOCK_MAX"])
+def test_small_world_graph_stage_forms_agree_bit_for_bit(avbd, switch, monkeypatch):
+    """A small world's graph stage runs in one block (graph_small: block radix sorts, block prefix sums, colouring on shared-memory work
+    words); a large world's is ~16 launches with device-wide sorts and the cooperative colouring.  Same per-element routines, stable sorts
+    on both sides: adjacency order, colours, colour order and visit lists — hence whole trajectories — must be identical.  Second case:
+    the multi-launch path with the cooperative grid colouring instead of the one-block colouring (AVBD_COLOUR_BLOCK_MAX=0)."""
+    from avbd_demo3d_b200 import scenes
+    preset = scenes.stress_grid(8, 8, 8, spacing_y=1.01, start_y=0.51)          # 512 boxes, layers start interpenetrating: a busy graph
+    preset["params"]["iterations"] = 6
+    ref = avbd.World(); scenes.load(ref, preset)
+    ref.step(25)
+    want_state, want_colours = ref.state().copy(), ref.colours()
+    dref = ref.diagnostics()
+    ref.close()
+    monkeypatch.setenv("AVBD_NO_SMALL_GRAPH", "1")
+    if switch == "AVBD_COLOUR_BLOCK_MAX":
+        monkeypatch.setenv("AVBD_COLOUR_BLOCK_MAX", "0")
+    w = avbd.World(); scenes.load(w, preset)
+    w.step(25)
+    assert w.state().tobytes() == want_state.tobytes()
+    assert np.array_equal(w.colours()[0], want_colours[0]) and w.colours()[1] == want_colours[1]
+    d = w.diagnostics()
+    assert (d["manifolds"], d["contacts"]) == (dref["manifolds"], dref["contacts"]) and d["manifolds"] > 500
+    w.close()
