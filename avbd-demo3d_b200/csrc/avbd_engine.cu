@@ -542,7 +542,7 @@ int run_colour(avbd_world* w) {
     TRY(w->colourWord.ensure(n, false, s)); TRY(w->colCursor.ensure(4, false, s));
     TRY(w->visitCount.ensure((size_t)w->nDyn + 1, false, s)); TRY(w->visitStart.ensure((size_t)w->nDyn + 1, false, s));
     // a small world: the whole stage in one block (avbd_kernels_graph.cuh: graph_small)
-    const bool smallGraph = nM <= kSmallGraphMax && w->nDyn <= kSmallGraphMax && n <= kSmallGraphMax + 64 && !keep && !havePrev && !getenv("AVBD_NO_SMALL_GRAPH");
+    const bool smallGraph = nM <= kSmallGraphMax && w->nDyn <= colour_block_max() && w->nDyn <= kSmallGraphMax && n <= kSmallGraphMax + 64     /* its colouring is the one-block one: same size limit (2744 bodies: 1729 against 1808 steps/s) */ && !keep && !havePrev && !getenv("AVBD_NO_SMALL_GRAPH");
     if (smallGraph) {
         TRY(w->bKeySorted.ensure(std::max(1, nM), false, s)); TRY(w->bList.ensure(std::max(1, nM), false, s));
         TRY(w->entries.ensure((size_t)std::max(1, 2 * nM), false, s));

@@ -426,7 +426,7 @@ __global__ void colour_visit_bounds(const int2* colourRange, const Counters* cnt
 
 // ------------------------------------------------------------------ the whole graph stage of a SMALL world in one block
 // A small world's step is a chain of dependent launches of a few microseconds each, and the graph stage alone was sixteen of them
-// (Stress1000: 0.107 of 0.67 ms).  Up to kSmallGraphMax manifolds / dynamic bodies one block of 1024 threads runs every phase itself
+// (Stress1000: 0.107 of 0.67 ms).  Up to kSmallGraphMax manifolds and the one-block colouring's body limit one block of 1024 threads runs every phase itself
 // — the very per-element routines of the kernels above, a block barrier where they have a kernel boundary, cub::BlockRadixSort (stable,
 // like the device-wide sorts it replaces) and a block prefix sum — so adjacency order, colours, colour order and visit lists come out
 // identical to the multi-launch path's.  Fresh colouring only (the default).
