@@ -112,7 +112,7 @@ struct avbd_world {
     DevBuf<int4> adjRange; DevBuf<unsigned> bKey, bKeySorted; DevBuf<int> bVal, bList;
     DevBuf<int> colour; DevBuf<unsigned> colKey, colKeySorted; DevBuf<int> colVal, colOrder; DevBuf<int2> colRange;
     int2 hColRange[64]; int nColours = 0; bool graphValid = false; bool forceRegraph = false; int maxColourCount = 0;
-    long long graphReuses = 0; int persistentMaxBodies = 0;      // the tile cluster loop (solve_loop_cluster) is opt-in (AVBD_PERSISTENT_MAX_BODIES): measured (tools/loop_modes.py) the per-colour sweep launches match or beat it at every size (TwoBlockDrop 6.8k vs 6.6k steps/s, Pyramid 3.75k vs 3.6k, Stress1000 1.39k vs 1.23k, 8000 bodies 1.26k vs 0.69k)
+    long long graphReuses = 0; int persistentMaxBodies = 64;     // up to this many dynamic bodies the iteration loop is ONE cluster launch (solve_loop_cluster; AVBD_PERSISTENT_MAX_BODIES overrides): measured (tools/loop_modes.py, profiles/r02_stress1000_and_ensemble.md) it wins on the tiniest scenes only — TwoBlockDrop 8.1k vs 7.7k steps/s, Stack 5.5k vs 5.1k, Pyramid (55 bodies) 3.88k vs 3.78k, Wall (64) 3.44k vs 3.37k — and loses above: Stress1000 1.36k vs 1.52k, 1728 bodies 1.76k vs 2.08k, 8000 bodies 0.80k vs 1.47k.  Same additions in the same order: results are bit-identical either way
     size_t tilesCleared = 0;  // scan tiles bp_cells cleared at the start of this step's collision stage
     bool cellRaw = true;    // default: the per-cell sweep emits the sphere pairs, np_sat culls them.  AVBD_BROADPHASE=body: the per-body sweep instead
                             // (1M-box grid: bp_sweep 472 us against bp_sweep_cells<false> 328 us; small worlds: no difference)
