@@ -289,6 +289,10 @@ __global__ void colour_round(const int* dynList, int nDyn, const int* estart, co
 // uncoloured count).  Same attempts, hence the same colouring as colour_round.  When the world's work words fit (nBodies <=
 // kColourSmemBodies) the rounds run on a shared-memory copy: a round is then a handful of shared-memory reads per body instead of a
 // chain of L2 round trips (Stress1000: 30 -> ~8 us).
+#ifndef AVBD_COLOUR_ATTEMPTS
+#define AVBD_COLOUR_ATTEMPTS 4
+#endif
+constexpr int kColourAttempts = AVBD_COLOUR_ATTEMPTS;        // attempts per body per round: the neighbours a body waits for are being coloured in the same round
 constexpr int kColourBlockThreads = 1024;
 constexpr int kColourSmemBodies = 10240;          // 40 KB of static shared memory
 __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int* estart, const int* entries,
@@ -309,8 +313,12 @@ __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const
     int left = 1;
     for (int round = 0; round < 4096 && left; ++round) {
         int mine = 0;
-        for (int t = threadIdx.x; t < nDyn; t += blockDim.x)
-            if (!try_colour(dynList[t], estart, entries, fv, localIdx, wd, colour, cnt)) mine = 1;
+        for (int t = threadIdx.x; t < nDyn; t += blockDim.x) {
+            bool done = false;
+#pragma unroll 1
+            for (int attempt = 0; attempt < kColourAttempts && !done; ++attempt) done = try_colour(dynList[t], estart, entries, fv, localIdx, wd, colour, cnt);
+            if (!done) mine = 1;
+        }
         left = __syncthreads_or(mine);           // also makes this round's colours visible to the whole block
     }
     if (threadIdx.x == 0) cnt->nUncoloured = left;
@@ -321,10 +329,6 @@ __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const
 // (warp-aggregated; the list's order is irrelevant to the result).  Same attempts, same colouring as colour_round.  Cursors rotate
 // over three slots: the slot a round fills was last READ two barriers ago.
 constexpr int kColourGridThreads = 256;
-#ifndef AVBD_COLOUR_ATTEMPTS
-#define AVBD_COLOUR_ATTEMPTS 4
-#endif
-constexpr int kColourAttempts = AVBD_COLOUR_ATTEMPTS;
 __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const int* dynList, int nDyn, const int* estart, const int* entries,
                                                                          ForceView fv, const int* localIdx, volatile int* word, int* colour, Counters* cnt,
                                                                          int* listA, int* listB, int* cursors, const int* keepFlags, int nBodies) {
@@ -509,8 +513,12 @@ __global__ void __launch_bounds__(kSmallGraphThreads) graph_small(SmallGraph a, 
         int left = 1;
         for (int round = 0; round < 4096 && left; ++round) {
             int mine = 0;
-            for (int t = tid; t < a.nDyn; t += T)
-                if (!try_colour(a.dynList[t], a.estart, a.entries, fv, a.localIdx, sm.word, a.colour, a.cnt)) mine = 1;
+            for (int t = tid; t < a.nDyn; t += T) {
+                bool done = false;
+#pragma unroll 1
+                for (int attempt = 0; attempt < kColourAttempts && !done; ++attempt) done = try_colour(a.dynList[t], a.estart, a.entries, fv, a.localIdx, sm.word, a.colour, a.cnt);
+                if (!done) mine = 1;
+            }
             left = __syncthreads_or(mine);
         }
         if (tid == 0) a.cnt->nUncoloured = left;
