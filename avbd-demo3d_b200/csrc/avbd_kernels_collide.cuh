@@ -569,7 +569,7 @@ __device__ __forceinline__ ContactState load_contact(const ManifoldSet& ms, int 
 // meets one whose inclusive prefix is already known) — cstart[m] = where manifold m's contacts start.  No staging copy, no
 // separate scan or compaction pass, and the placement is deterministic (the graph of a step whose topology did not change is
 // re-used, and its visit lists hold contact indices).
-constexpr int kBuildThreads = 128;
+constexpr int kBuildThreads = 64;
 // tile[b] = (status << 32) | value; status 0 not ready, 1 the block's own total, 2 the inclusive prefix up to and including the block.
 // Blocks are dispatched in index order, so a predecessor a block waits on is always resident or done.
 // Called by the whole first warp.  Publishing and looking back are separate calls: a block publishes its total as soon as it knows
