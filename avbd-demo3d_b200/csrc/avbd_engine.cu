@@ -599,11 +599,12 @@ int run_colour(avbd_world* w) {
     // one block for small worlds, a cooperative grid with a grid barrier per round otherwise — no host check of the uncoloured count
     // between rounds.  If the cooperative launch is refused, rounds are launched in batches with a host check per batch.
     bool coloured = keepSaved;
+    bool keysDone = false;          // the one-launch round kernels also write the colour sort's keys
     if (coloured) {
     } else if (w->nDyn <= colour_block_max()) {
-        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colourWord.p, w->colour.p, w->dCnt, n, keepFlags);
+        launch_dep(colour_rounds_block, dim3(1), dim3(kColourBlockThreads), 0, s, w->dynList.p, w->nDyn, w->estart.p, w->entries.p, fv, w->localIdx.p, w->colourWord.p, w->colour.p, w->dCnt, n, keepFlags, w->colKey.p, w->colVal.p);
         w->launches++;
-        coloured = true;
+        coloured = true; keysDone = true;
     } else {
         static int residentDev[64] = {0};
         int& resident = residentDev[w->device & 63];
@@ -620,10 +621,11 @@ int run_colour(avbd_world* w) {
             const int* localIdx = w->localIdx.p; volatile int* word = w->colourWord.p; int* colour = w->colour.p; Counters* cnt = w->dCnt;
             int* listA = w->colWorkA.p; int* listB = w->colWorkB.p; int* cursors = w->colCursor.p;
             int nBodies = n;
-            void* args[] = {&dynList, &nDyn, &estart, &entries, &fv, &localIdx, &word, &colour, &cnt, &listA, &listB, &cursors, &keepFlags, &nBodies};
+            unsigned* ckey = w->colKey.p; int* cval = w->colVal.p;
+            void* args[] = {&dynList, &nDyn, &estart, &entries, &fv, &localIdx, &word, &colour, &cnt, &listA, &listB, &cursors, &keepFlags, &nBodies, &ckey, &cval};
             int grid = std::min(resident, blocks_for(w->nDyn, kColourGridThreads));
             cudaError_t e = cudaLaunchCooperativeKernel((void*)colour_rounds_grid, dim3(grid), dim3(kColourGridThreads), args, 0, s);
-            if (e == cudaSuccess) { w->launches++; coloured = true; } else { cudaGetLastError(); resident = -1; }
+            if (e == cudaSuccess) { w->launches++; coloured = true; keysDone = true; } else { cudaGetLastError(); resident = -1; }
         }
     }
     if (!coloured) {
@@ -651,20 +653,18 @@ int run_colour(avbd_world* w) {
         }
     }
     w->colouredBodies = n;
-    launch_dep(colour_keys, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p);
+    if (!keysDone) { launch_dep(colour_keys, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->colour.p, w->colKey.p, w->colVal.p); w->launches++; }
     TRY(sort_pairs(w, w->colKey.p, w->colKeySorted.p, w->colVal.p, w->colOrder.p, w->nDyn, 7));
-    launch_dep(colour_bounds, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colKeySorted.p, w->nDyn, w->colRange.p, w->dCnt);
-    w->launches += 2;
     // contact visits in colour order (the sweeps' work list): visitStart[k] belongs to colOrder[k]
     TRY(w->visits.ensure((size_t)std::max(1, 2 * w->nContacts), false, s));
     TRY(w->freeList.ensure((size_t)w->nDyn, false, s)); TRY(w->linkedList.ensure((size_t)w->nDyn, false, s));
-    launch_dep(visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->visitCount.p,
-               fv, w->freeList.p, w->linkedList.p, w->dCnt);
-    TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
-    launch_dep(visit_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p);
     TRY(w->colVisit.ensure(64, false, s));
-    launch_dep(colour_visit_bounds, dim3(1), dim3(64), 0, s, w->colRange.p, w->dCnt, w->visitStart.p, w->colVisit.p);
-    w->launches += 3;
+    launch_dep(colour_bounds_visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colKeySorted.p, w->nDyn, w->colRange.p, w->colOrder.p, w->adjRange.p, w->bList.p,
+               ms.hdr, w->visitCount.p, fv, w->freeList.p, w->linkedList.p, w->dCnt);
+    TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
+    launch_dep(visit_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p,
+               (const int2*)w->colRange.p, (const Counters*)w->dCnt, w->colVisit.p);
+    w->launches += 2;
     }
     w->visitGeomStale = true;
     // ONE host round trip for everything the launches of the sweeps need: colour ranges, their visit ranges, counters

@@ -126,10 +126,17 @@ __device__ __forceinline__ void visit_fill_one(int t, const int* colOrder, const
         for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.x, tag, h.w);
     }
 }
+// colVisit != nullptr: block 0 also writes each colour's visit range (colour_visit_bounds): the ranges and the visit starts are complete
+// before this launch.
 __global__ void visit_fill(const int* colOrder, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
-                           const int* visitStart, const BodyAux* aux, const int* colour, int4* visits) {
+                           const int* visitStart, const BodyAux* aux, const int* colour, int4* visits,
+                           const int2* colourRange, const Counters* cnt, int2* colVisit) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (colVisit != nullptr && t < 64) {
+        int2 r = t < cnt->nColours ? colourRange[t] : make_int2(0, 0);
+        colVisit[t] = r.y > r.x ? make_int2(visitStart[r.x], visitStart[r.y]) : make_int2(0, 0);
+    }
     if (t >= nDyn) return;
     visit_fill_one(t, colOrder, adjRange, bList, hdr, cstart, visitStart, aux, colour, visits);
 }
@@ -297,7 +304,7 @@ constexpr int kColourBlockThreads = 1024;
 constexpr int kColourSmemBodies = 10240;          // 40 KB of static shared memory
 __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const int* dynList, int nDyn, const int* estart, const int* entries,
                                                                            ForceView fv, const int* localIdx, int* word, int* colour, Counters* cnt, int nBodies,
-                                                                           const int* keepFlags) {
+                                                                           const int* keepFlags, unsigned* key, int* val) {
     cudaGridDependencySynchronize();
     __shared__ int sWord[kColourSmemBodies];
     volatile int* wd = word;
@@ -322,6 +329,8 @@ __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const
         left = __syncthreads_or(mine);           // also makes this round's colours visible to the whole block
     }
     if (threadIdx.x == 0) cnt->nUncoloured = left;
+    // the colour sort's keys (colour_keys), while the colours are at hand
+    for (int t = threadIdx.x; t < nDyn; t += blockDim.x) { const int i = dynList[t]; key[t] = (unsigned)colour[i]; val[t] = i; }
 }
 
 // Large worlds: ALL rounds in one cooperative launch (grid barrier between rounds, no host round trip to learn how many bodies are
@@ -331,7 +340,8 @@ __global__ void __launch_bounds__(kColourBlockThreads) colour_rounds_block(const
 constexpr int kColourGridThreads = 256;
 __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const int* dynList, int nDyn, const int* estart, const int* entries,
                                                                          ForceView fv, const int* localIdx, volatile int* word, int* colour, Counters* cnt,
-                                                                         int* listA, int* listB, int* cursors, const int* keepFlags, int nBodies) {
+                                                                         int* listA, int* listB, int* cursors, const int* keepFlags, int nBodies,
+                                                                         unsigned* key, int* val) {
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -383,6 +393,8 @@ __global__ void __launch_bounds__(kColourGridThreads) colour_rounds_grid(const i
         list = out;
     }
     if (gtid == 0) { cnt->nUncoloured = count; cnt->colourRounds = round; }
+    // the colour sort's keys (colour_keys), while the grid is here: every round ended with a grid barrier, all colours are visible
+    for (int t = gtid; t < nDyn; t += gsize) { const int i = dynList[t]; key[t] = (unsigned)__ldcg(colour + i); val[t] = i; }
 }
 
 // Work list of the bodies still uncoloured (order is irrelevant: the colouring does not depend on it).
@@ -417,6 +429,19 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
     if (t == 0 || keySorted[t - 1] != c) colourRange[c].x = t;
     if (t == nDyn - 1 || keySorted[t + 1] != c) colourRange[c].y = t + 1;
     if (t == nDyn - 1) cnt->nColours = (int)c + 1;
+}
+
+// colour_bounds and visit_count in one launch (both walk the colour-sorted bodies, neither reads what the other writes)
+__global__ void colour_bounds_visit_count(const unsigned* keySorted, int nDyn, int2* colourRange, const int* colOrder, const int4* adjRange, const int* bList,
+                                          const int4* hdr, int* visitCount, ForceView fv, int* freeList, int* linkedList, Counters* cnt) {
+    cudaGridDependencySynchronize();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nDyn) return;
+    unsigned c = keySorted[t];
+    if (t == 0 || keySorted[t - 1] != c) colourRange[c].x = t;
+    if (t == nDyn - 1 || keySorted[t + 1] != c) colourRange[c].y = t + 1;
+    if (t == nDyn - 1) cnt->nColours = (int)c + 1;
+    visit_count_one(t, colOrder, adjRange, bList, hdr, visitCount, fv, freeList, linkedList, cnt);
 }
 
 // out[c] = {first visit, one past the last visit} of colour c (a colour's bodies, hence its visits, are contiguous)
