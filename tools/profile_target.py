@@ -12,6 +12,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 w = avbd.World()
 if name == "stress1000":
     scenes.load(w, scenes.scene("Stress1000")); w.step(400)
+elif name.startswith("ensemble") and name != "ensemble":
+    scenes.load(w, scenes.ensemble(scenes.scene("Pyramid"), int(name[8:]))); w.step(30)
 elif name == "ensemble":
     scenes.load(w, scenes.ensemble(scenes.scene("Pyramid"), 8192)); w.step(30)
 else:
