@@ -58,6 +58,12 @@ __global__ void bp_cells(BodyView b, GridView g, Counters* cnt, int* zeroA, int 
     for (int k = i; k < nZeroB; k += stride) zeroB[k] = 0;
     if (i < (int)(sizeof(Counters) / sizeof(int))) reinterpret_cast<int*>(cnt)[i] = 0;
     if (i >= b.n) return;
+    if (g.bodyFrame) {          // the SAT frames np_sat gathers by body: written here, in body order (coalesced), not after the sort
+        const ObbFrame f = make_obb_frame(xyz(b.pose[i].pos), quat(b.pose[i].rot), xyz(b.size[i]));
+        float4* o = g.bodyFrame + 6 * (size_t)i;
+        o[0] = f4(f.ax[0], f.h.x); o[1] = f4(f.ax[1], f.h.y); o[2] = f4(f.ax[2], f.h.z);
+        o[3] = f4(f.n[0], f.raSelf[0]); o[4] = f4(f.n[1], f.raSelf[1]); o[5] = f4(f.n[2], f.raSelf[2]);
+    }
     unsigned k = g.tableMask + 1u;
     if (!(b.flags[i] & kLarge)) {
         int3 c = cell_of(b.pose[i].pos, g.cell);
@@ -81,12 +87,6 @@ __global__ void bp_cell_bounds(BodyView b, GridView g) {
     if (g.sortedFrame) {
         const ObbFrame f = make_obb_frame(xyz(pos), quat(b.pose[i].rot), xyz(b.size[i]));
         float4* o = g.sortedFrame + 6 * (size_t)p;
-        o[0] = f4(f.ax[0], f.h.x); o[1] = f4(f.ax[1], f.h.y); o[2] = f4(f.ax[2], f.h.z);
-        o[3] = f4(f.n[0], f.raSelf[0]); o[4] = f4(f.n[1], f.raSelf[1]); o[5] = f4(f.n[2], f.raSelf[2]);
-    }
-    if (g.bodyFrame) {
-        const ObbFrame f = make_obb_frame(xyz(pos), quat(b.pose[i].rot), xyz(b.size[i]));
-        float4* o = g.bodyFrame + 6 * (size_t)i;
         o[0] = f4(f.ax[0], f.h.x); o[1] = f4(f.ax[1], f.h.y); o[2] = f4(f.ax[2], f.h.z);
         o[3] = f4(f.n[0], f.raSelf[0]); o[4] = f4(f.n[1], f.raSelf[1]); o[5] = f4(f.n[2], f.raSelf[2]);
     }
