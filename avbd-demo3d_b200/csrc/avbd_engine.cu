@@ -99,7 +99,7 @@ struct avbd_world {
     DevBuf<unsigned long long> pairs, cand, candSorted; int nCand = 0, nPairs = 0; long long lastPairs = 0, satLaunched = 0;
     DevBuf<unsigned long long> buildTiles;      // np_build's chained scan over its blocks
     DevBuf<int> mcount, visitCount, visitStart; DevBuf<int4> visits; int nContacts = 0;      // per-contact visit lists: small worlds (cluster loop) only
-    DevBuf<int> deg, estart, colCursor, sweepRange, freeList, linkedList; DevBuf<int> entries; DevBuf<int2> colVisit; DevBuf<float4> vgA, vgB, vgN;
+    DevBuf<int> bodyContacts; DevBuf<int> deg, estart, colCursor, sweepRange, freeList, linkedList; DevBuf<int> entries; DevBuf<int2> colVisit; DevBuf<float4> vgA, vgB, vgN;
     int2 hColVisit[64]; int sweepWarps[64] = {0}, sweepOff[64] = {0};      // per colour: its visit range, warps of the sweep, offset of its warp ranges
     int nFree = 0, nLinkedFree = 0; bool visitGeomStale = true, sweepRangesValid = false;            // contact geometry in visit order (VisitGeom), refreshed once per step
          // body -> manifold entries CSR (graph stage): colouring adjacency + the large-world sweep's work list
@@ -574,7 +574,8 @@ int run_colour(avbd_world* w) {
     }
     // body -> manifold entries (CSR by body): the colouring's adjacency and the large-world sweep's work list
     TRY(w->entries.ensure((size_t)std::max(1, 2 * nM), false, s));
-    launch_dep(entry_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->deg.p);
+    TRY(w->bodyContacts.ensure((size_t)n, false, s));
+    launch_dep(entry_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->deg.p, w->bodyContacts.p);
     TRY(exclusive_scan(w, w->deg.p, w->estart.p, n + 1));
     launch_dep(entry_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->dynList.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, w->estart.p, w->entries.p);
     w->launches += 2;
@@ -660,7 +661,7 @@ int run_colour(avbd_world* w) {
     TRY(w->freeList.ensure((size_t)w->nDyn, false, s)); TRY(w->linkedList.ensure((size_t)w->nDyn, false, s));
     TRY(w->colVisit.ensure(64, false, s));
     launch_dep(colour_bounds_visit_count, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colKeySorted.p, w->nDyn, w->colRange.p, w->colOrder.p, w->adjRange.p, w->bList.p,
-               ms.hdr, w->visitCount.p, fv, w->freeList.p, w->linkedList.p, w->dCnt);
+               ms.hdr, w->visitCount.p, fv, w->freeList.p, w->linkedList.p, w->dCnt, (const int*)w->bodyContacts.p);
     TRY(exclusive_scan(w, w->visitCount.p, w->visitStart.p, w->nDyn + 1));
     launch_dep(visit_fill, dim3(blocks_for(w->nDyn)), dim3(kThreads), 0, s, w->colOrder.p, w->nDyn, w->adjRange.p, w->bList.p, ms.hdr, ms.cstart, w->visitStart.p, w->aux.p, w->colour.p, w->visits.p,
                (const int2*)w->colRange.p, (const Counters*)w->dCnt, w->colVisit.p);
@@ -935,7 +936,7 @@ void avbd_world_destroy(avbd_world* w) {
     w->adjRange.release(); w->bKey.release(); w->bKeySorted.release(); w->bVal.release(); w->bList.release();
     w->colour.release(); w->colKey.release(); w->colKeySorted.release(); w->colVal.release(); w->colOrder.release(); w->colRange.release();
     w->joints.release(); w->springs.release(); w->fadjStart.release(); w->fadj.release(); w->excl.release();
-    w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release(); w->deg.release(); w->estart.release(); w->colCursor.release(); w->entries.release(); w->sweepRange.release(); w->colVisit.release(); w->freeList.release(); w->linkedList.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
+    w->dDiag.release(); w->dx.release(); w->temp.release(); w->stateDev.release(); w->bodyContacts.release(); w->deg.release(); w->estart.release(); w->colCursor.release(); w->entries.release(); w->sweepRange.release(); w->colVisit.release(); w->freeList.release(); w->linkedList.release(); w->vgA.release(); w->vgB.release(); w->vgN.release();
     w->mcount.release(); w->buildTiles.release(); w->visitCount.release(); w->visitStart.release(); w->visits.release();
     for (auto& ps : w->profSteps) { for (auto& e : ps.ev) cudaEventDestroy(e); for (auto& e : ps.dual) cudaEventDestroy(e); }
     for (cudaEvent_t e : w->chunkEvents) cudaEventDestroy(e);

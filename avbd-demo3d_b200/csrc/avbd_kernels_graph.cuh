@@ -42,19 +42,22 @@ __global__ void adj_b_ranges(const unsigned* bKeySorted, int nM, int nBodies, in
 // One entry per LIVE manifold touching a dynamic body, in pair-key order (the body's "I am A" run, then its "I am B" run): the OTHER
 // body, 4 bytes — the colouring's adjacency list and nothing else (the sweeps walk the visit lists).  estart is indexed by BODY
 // (n + 1 entries, static bodies own none).
-__device__ __forceinline__ void entry_count_one(int t, const int* dynList, const int4* adjRange, const int* bList, const int4* hdr, int* deg) {
+// bodyContacts (optional): the body's live contact count, i.e. its number of visits — the same walk yields it, so visit_count need not
+// walk the manifolds again once the colour order exists.
+__device__ __forceinline__ void entry_count_one(int t, const int* dynList, const int4* adjRange, const int* bList, const int4* hdr, int* deg, int* bodyContacts) {
     int i = dynList[t];
     int4 rg = adjRange[i];
-    int k = 0;
-    for (int m = rg.x; m < rg.y; ++m) k += hdr[m].z > 0 ? 1 : 0;
-    for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z > 0 ? 1 : 0;
+    int k = 0, c = 0;
+    for (int m = rg.x; m < rg.y; ++m) { int z = hdr[m].z; k += z > 0 ? 1 : 0; c += z; }
+    for (int q = rg.z; q < rg.w; ++q) { int z = hdr[bList[q]].z; k += z > 0 ? 1 : 0; c += z; }
     deg[i] = k;
+    if (bodyContacts) bodyContacts[i] = c;
 }
-__global__ void entry_count(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* deg) {
+__global__ void entry_count(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr, int* deg, int* bodyContacts) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
-    entry_count_one(t, dynList, adjRange, bList, hdr, deg);
+    entry_count_one(t, dynList, adjRange, bList, hdr, deg, bodyContacts);
 }
 __device__ __forceinline__ void entry_fill_one(int t, const int* dynList, const int4* adjRange, const int* bList, const int4* hdr, const int* estart, int* entries) {
     int i = dynList[t];
@@ -83,12 +86,15 @@ __global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, c
 // `freeList` those no user force touches either, `linkedList` those a joint / spring links to another body (they keep their place
 // in the colour order).  The lists' order is irrelevant.
 __device__ __forceinline__ void visit_count_one(int t, const int* colOrder, const int4* adjRange, const int* bList, const int4* hdr, int* visitCount,
-                                                const ForceView& fv, int* freeList, int* linkedList, Counters* cnt) {
+                                                const ForceView& fv, int* freeList, int* linkedList, Counters* cnt, const int* bodyContacts = nullptr) {
     int i = colOrder[t];
-    int4 rg = adjRange[i];
     int k = 0;
-    for (int m = rg.x; m < rg.y; ++m) k += hdr[m].z;
-    for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z;
+    if (bodyContacts) k = bodyContacts[i];                  // counted by entry_count on its walk
+    else {
+        int4 rg = adjRange[i];
+        for (int m = rg.x; m < rg.y; ++m) k += hdr[m].z;
+        for (int q = rg.z; q < rg.w; ++q) k += hdr[bList[q]].z;
+    }
     visitCount[t] = k;
     if (k == 0) {
         bool linked = fv.adjStart != nullptr && fv.adjStart[i + 1] > fv.adjStart[i];
@@ -433,7 +439,7 @@ __global__ void colour_bounds(const unsigned* keySorted, int nDyn, int2* colourR
 
 // colour_bounds and visit_count in one launch (both walk the colour-sorted bodies, neither reads what the other writes)
 __global__ void colour_bounds_visit_count(const unsigned* keySorted, int nDyn, int2* colourRange, const int* colOrder, const int4* adjRange, const int* bList,
-                                          const int4* hdr, int* visitCount, ForceView fv, int* freeList, int* linkedList, Counters* cnt) {
+                                          const int4* hdr, int* visitCount, ForceView fv, int* freeList, int* linkedList, Counters* cnt, const int* bodyContacts) {
     cudaGridDependencySynchronize();
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nDyn) return;
@@ -441,7 +447,7 @@ __global__ void colour_bounds_visit_count(const unsigned* keySorted, int nDyn, i
     if (t == 0 || keySorted[t - 1] != c) colourRange[c].x = t;
     if (t == nDyn - 1 || keySorted[t + 1] != c) colourRange[c].y = t + 1;
     if (t == nDyn - 1) cnt->nColours = (int)c + 1;
-    visit_count_one(t, colOrder, adjRange, bList, hdr, visitCount, fv, freeList, linkedList, cnt);
+    visit_count_one(t, colOrder, adjRange, bList, hdr, visitCount, fv, freeList, linkedList, cnt, bodyContacts);
 }
 
 // out[c] = {first visit, one past the last visit} of colour c (a colour's bodies, hence its visits, are contiguous)
@@ -526,7 +532,7 @@ __global__ void __launch_bounds__(kSmallGraphThreads) graph_small(SmallGraph a, 
     for (int t = tid; t < a.nM; t += T) adj_b_one(t, a.bKeySorted, a.nM, a.n, a.adjRange);
     __syncthreads();
     // ---- body -> neighbour entries
-    for (int t = tid; t < a.nDyn; t += T) entry_count_one(t, a.dynList, a.adjRange, a.bList, a.hdr, a.deg);
+    for (int t = tid; t < a.nDyn; t += T) entry_count_one(t, a.dynList, a.adjRange, a.bList, a.hdr, a.deg, nullptr);
     __syncthreads();
     block_scan_exclusive(a.deg, a.estart, a.n + 1, sWarp);
     __syncthreads();
