@@ -271,7 +271,21 @@ __device__ __forceinline__ bool try_colour(int i, const int* estart, const int* 
         if (so >= 2) used |= 1ull << (so - 2);
         else if (so == 1 && outranks(wo >> 8, localIdx[other], ri, li)) ready = false;
     };
-    for (int e = estart[i], e1 = estart[i + 1]; e < e1 && ready; ++e) visit(entries[e]);
+    // four neighbours at a time: their ids, then their words and priorities, are fetched side by side — a body's walk is a chain of
+    // dependent gathers (id -> word -> priority) and the colouring kernels are made of nothing else
+    for (int e = estart[i], e1 = estart[i + 1]; e < e1 && ready; e += 4) {
+        int o[4], wv[4], lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = e + u < e1 ? entries[e + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { wv[u] = o[u] >= 0 ? word[o[u]] : 0; lo[u] = o[u] >= 0 ? localIdx[o[u]] : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int so = wv[u] & 255;
+            if (so >= 2) used |= 1ull << (so - 2);
+            else if (so == 1 && outranks(wv[u] >> 8, lo[u], ri, li)) ready = false;
+        }
+    }
     if (fv.adjStart) {
         for (int k = fv.adjStart[i]; k < fv.adjStart[i + 1] && ready; ++k) {
             int e = fv.adj[k]; int idx = e >> 2; bool isA = e & 1;
