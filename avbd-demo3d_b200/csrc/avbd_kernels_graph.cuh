@@ -49,7 +49,13 @@ __device__ __forceinline__ void entry_count_one(int t, const int* dynList, const
     int4 rg = adjRange[i];
     int k = 0, c = 0;
     for (int m = rg.x; m < rg.y; ++m) { int z = hdr[m].z; k += z > 0 ? 1 : 0; c += z; }
-    for (int q = rg.z; q < rg.w; ++q) { int z = hdr[bList[q]].z; k += z > 0 ? 1 : 0; c += z; }
+    for (int q = rg.z; q < rg.w; q += 4) {                     // slots first, then their headers side by side
+        int mm[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mm[u] = q + u < rg.w ? bList[q + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { int z = mm[u] >= 0 ? hdr[mm[u]].z : 0; k += z > 0 ? 1 : 0; c += z; }
+    }
     deg[i] = k;
     if (bodyContacts) bodyContacts[i] = c;
 }
@@ -64,7 +70,15 @@ __device__ __forceinline__ void entry_fill_one(int t, const int* dynList, const 
     int4 rg = adjRange[i];
     int o = estart[i];
     for (int m = rg.x; m < rg.y; ++m) { int4 h = hdr[m]; if (h.z > 0) entries[o++] = h.y; }
-    for (int q = rg.z; q < rg.w; ++q) { int4 h = hdr[bList[q]]; if (h.z > 0) entries[o++] = h.x; }
+    for (int q = rg.z; q < rg.w; q += 4) {
+        int mm[4]; int4 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mm[u] = q + u < rg.w ? bList[q + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = mm[u] >= 0 ? hdr[mm[u]] : make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (h[u].z > 0) entries[o++] = h[u].x;
+    }
 }
 __global__ void entry_fill(const int* dynList, int nDyn, const int4* adjRange, const int* bList, const int4* hdr,
                            const int* estart, int* entries) {
@@ -114,6 +128,8 @@ __global__ void visit_count(const int* colOrder, int nDyn, const int4* adjRange,
     if (t >= nDyn) return;
     visit_count_one(t, colOrder, adjRange, bList, hdr, visitCount, fv, freeList, linkedList, cnt);
 }
+// Four manifolds at a time: their slots (the B run goes through bList), then their headers and contact starts, then the other bodies'
+// colours are fetched side by side — one body's walk is otherwise a chain of three dependent gathers per manifold.
 __device__ __forceinline__ void visit_fill_one(int t, const int* colOrder, const int4* adjRange, const int* bList, const int4* hdr, const int* cstart,
                                                const int* visitStart, const BodyAux* aux, const int* colour, int4* visits) {
     int i = colOrder[t];
@@ -122,14 +138,25 @@ __device__ __forceinline__ void visit_fill_one(int t, const int* colOrder, const
     float4 I = aux[i].inert;
     int idx = (i << 3) | ((I.x == I.y && I.y == I.z) ? 0 : 2);
     int mine = colour[i];
-    auto first = [&](int other) { int co = colour[other]; return (co < 0 || mine < co) ? 4 : 0; };
-    for (int m = rg.x; m < rg.y; ++m) {
-        int4 h = hdr[m]; int c0 = cstart[m]; int tag = idx | 1 | first(h.y);
-        for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.y, tag, h.w);
-    }
-    for (int q = rg.z; q < rg.w; ++q) {
-        int m = bList[q]; int4 h = hdr[m]; int c0 = cstart[m]; int tag = idx | first(h.x);
-        for (int c = 0; c < h.z; ++c) visits[o++] = make_int4(c0 + c, h.x, tag, h.w);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {                     // 0: the body is A (slots rg.x .. rg.y), 1: it is B (bList[rg.z .. rg.w])
+        const int q0 = side ? rg.z : rg.x, q1 = side ? rg.w : rg.y;
+        for (int q = q0; q < q1; q += 4) {
+            int mm[4], c0[4], co[4]; int4 h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) mm[u] = q + u < q1 ? (side ? bList[q + u] : q + u) : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { h[u] = mm[u] >= 0 ? hdr[mm[u]] : make_int4(0, 0, 0, 0); c0[u] = mm[u] >= 0 ? cstart[mm[u]] : 0; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) co[u] = mm[u] >= 0 ? colour[side ? h[u].x : h[u].y] : 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (mm[u] < 0) continue;
+                const int other = side ? h[u].x : h[u].y;
+                const int tag = idx | (side ? 0 : 1) | ((co[u] < 0 || mine < co[u]) ? 4 : 0);     // first visit: the other endpoint is static or of a higher colour
+                for (int c = 0; c < h[u].z; ++c) visits[o++] = make_int4(c0[u] + c, other, tag, h[u].w);
+            }
+        }
     }
 }
 // colVisit != nullptr: block 0 also writes each colour's visit range (colour_visit_bounds): the ranges and the visit starts are complete
